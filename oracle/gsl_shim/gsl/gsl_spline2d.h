@@ -1,0 +1,2 @@
+/* oracle GSL shim (test infrastructure): see gsl_shim_all.h */
+#include "gsl_shim_all.h"
