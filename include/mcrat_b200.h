@@ -1,0 +1,173 @@
+/*
+ * mcrat_b200.h -- C ABI of the B200-native MCRaT photon-propagation / scattering hot path.
+ *
+ * One shared library (libmcrat_b200.so: hand-written sm_100a CUDA, FP64) that replaces
+ * the body of MCRaT's scatter-frame while-loop, Src/mcrat.c:761-851.  Plain pointers and
+ * sizes only; the host stays C.  Every entry point names the reference interface it
+ * replaces (file:line under the reference tree).  Photon records cross the boundary in
+ * the reference's own `struct photon` layout (Src/mcrat.h:142-171, 176 bytes) and cell
+ * data as the `struct hydro_dataframe` arrays (Src/mcrat.h:194-244); on the device both
+ * live as SoA columns.
+ *
+ * There is no CPU fallback: every call returns MCRAT_B200_ERR_CUDA if the device path
+ * cannot run.  All functions return 0 on success, a negative MCRAT_B200_ERR_* otherwise;
+ * mcrat_b200_last_error() gives the message.
+ *
+ * Thread-safety: one context per host thread / MPI rank / GPU (the reference runs one
+ * rank per shard, Src/mcrat.c:139-164).  A context owns one CUDA stream.
+ */
+#ifndef MCRAT_B200_H
+#define MCRAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCRAT_B200_ABI_VERSION 1
+
+/* reference codes, Src/mcrat.h:36-65 */
+enum { MCRAT_CARTESIAN = 0, MCRAT_SPHERICAL = 1, MCRAT_CYLINDRICAL = 2, MCRAT_POLAR = 3 };
+enum { MCRAT_TWO = 0, MCRAT_TWO_POINT_FIVE = 1, MCRAT_THREE = 2 };
+enum { MCRAT_INTERNAL_E = 0, MCRAT_TOTAL_E = 1, MCRAT_SIMULATION = 2 };
+enum { MCRAT_DIRECT = 1, MCRAT_TABLE = 2 };
+
+enum { MCRAT_RNG_PHILOX = 0, MCRAT_RNG_REPLAY = 1 };
+
+enum {
+    MCRAT_B200_OK = 0,
+    MCRAT_B200_ERR_CUDA = -1,     /* CUDA runtime / no device */
+    MCRAT_B200_ERR_ARG = -2,      /* bad argument */
+    MCRAT_B200_ERR_STATE = -3,    /* call out of order (e.g. no hydro frame loaded) */
+    MCRAT_B200_ERR_REPLAY = -4,   /* replay uniform buffer exhausted */
+    MCRAT_B200_ERR_TABLE = -5     /* hot cross-section lookup outside the table */
+};
+
+/* `struct photon`, Src/mcrat.h:142-171 with NONTHERMAL_E_DIST == OFF.  Same member order
+ * and types, hence the same 176-byte layout the reference dumps into checkpoints
+ * (Src/mcrat_io.c:902). */
+typedef struct mcrat_photon {
+    char type;
+    double p0, p1, p2, p3;
+    double comv_p0, comv_p1, comv_p2, comv_p3;
+    double r0, r1, r2;
+    double s0, s1, s2, s3;
+    double num_scatt;
+    int recalc_properties;
+    double weight;
+    int nearest_block_index;
+    double time_to_scatter;
+    double total_optical_depth;
+} mcrat_photon;
+
+/* The reference's compile-time switches (Src/mcrat_input.h, Src/mcrat.h:262-427) as an
+ * init-time struct, plus device selection. */
+typedef struct mcrat_b200_config {
+    int abi_version;       /* MCRAT_B200_ABI_VERSION */
+    int dimensions;        /* DIMENSIONS */
+    int geometry;          /* GEOMETRY */
+    int stokes_switch;     /* STOKES_SWITCH */
+    int tau_calculation;   /* TAU_CALCULATION */
+    int cyclosynch_switch; /* CYCLOSYNCHROTRON_SWITCH */
+    int b_field_calc;      /* B_FIELD_CALC */
+    double epsilon_b;      /* EPSILON_B */
+    int device;            /* CUDA device ordinal */
+    int rng_mode;          /* MCRAT_RNG_PHILOX (production) or MCRAT_RNG_REPLAY (parity harness) */
+    uint64_t seed;         /* Philox key, low/high words */
+    uint32_t shard;        /* shard (rank) id mixed into the Philox key */
+    int profile;           /* 1: time each kernel class with CUDA events (see kernel_times) */
+    void *stream;          /* cudaStream_t to run on, or NULL to let the library create one */
+} mcrat_b200_config;
+
+typedef struct mcrat_b200_ctx mcrat_b200_ctx;
+
+/* what one call of the device-resident frame loop did */
+typedef struct mcrat_b200_frame_stats {
+    long long iterations;   /* while-loop iterations executed, Src/mcrat.c:761 */
+    long long scatterings;  /* frame_scatt_cnt, Src/mclib.c:1318 */
+    long long relocations;  /* num_photons_find_new_element, Src/mcrat.c:768 */
+    long long photon_slots; /* sum over iterations of list_capacity (photon-iterations) */
+    long long cell_evals;   /* photon-cell containment tests executed by the scan kernels */
+    double time_now;
+    double last_time_step;
+    int last_scattered_index;
+    int not_found;          /* photons for which no containing cell exists (Src/mclib.c:583) */
+    int cs_host_pending;    /* loop paused: a pool photon scattered, host must emit (Src/mcrat.c:792-807) */
+    int error;              /* 0 or MCRAT_B200_ERR_* raised on the device */
+} mcrat_b200_frame_stats;
+
+typedef struct mcrat_b200_kernel_times {
+    double scan_ms;   long long scan_launches;   /* K1 photon x cell containment scan */
+    double pass_ms;   long long pass_launches;   /* K4+K2 fused push / re-check / free-path / block arg-min */
+    double event_ms;  long long event_launches;  /* K3 fused scatter */
+    double other_ms;  long long other_launches;
+} mcrat_b200_kernel_times;
+
+/* ---- life cycle ---------------------------------------------------------------------- */
+int mcrat_b200_abi_version(void);
+int mcrat_b200_device_count(void);
+int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out);
+void mcrat_b200_destroy(mcrat_b200_ctx *ctx);
+const char *mcrat_b200_last_error(const mcrat_b200_ctx *ctx); /* ctx may be NULL: last create() error */
+int mcrat_b200_synchronize(mcrat_b200_ctx *ctx);
+
+/* ---- inputs --------------------------------------------------------------------------- */
+/* Upload one hydro frame (replaces what getHydroData leaves in `struct hydro_dataframe`,
+ * Src/mcrat.c:721).  `fields` holds 19 host pointers in struct order: r0 r1 r2 r0_size
+ * r1_size r2_size r theta v0 v1 v2 dens dens_lab pres temp gamma B0 B1 B2 (unused ones
+ * may be NULL); `domains` = {r0_domain[2], r1_domain[2], r2_domain[2]}. */
+int mcrat_b200_set_hydro(mcrat_b200_ctx *ctx, int num_elements, const double *const *fields, const double *domains,
+                         double fps, int scatt_frame_number, int inj_frame_number);
+/* thermal_table[N_PH_E+1][N_T+1] of Src/hot_x_section.c:15 (221 x 81, log10 sigma/sigma_T) */
+int mcrat_b200_set_thermal_table(mcrat_b200_ctx *ctx, const double *table);
+/* Upload / download the photon list (`struct photonList`.photons, Src/mcrat.h:173-180). */
+int mcrat_b200_set_photons(mcrat_b200_ctx *ctx, const mcrat_photon *photons, int list_capacity);
+int mcrat_b200_get_photons(mcrat_b200_ctx *ctx, mcrat_photon *photons, int list_capacity);
+int mcrat_b200_get_photon(mcrat_b200_ctx *ctx, int index, mcrat_photon *out);
+int mcrat_b200_list_capacity(const mcrat_b200_ctx *ctx);
+/* parity harness: the uniform stream the reference's gsl_rng would hand out */
+int mcrat_b200_set_replay_uniforms(mcrat_b200_ctx *ctx, const double *u, size_t n);
+long long mcrat_b200_replay_consumed(mcrat_b200_ctx *ctx);
+
+/* ---- the reference's function surface ----------------------------- */
+/* findContainingHydroCell, Src/mclib.h:8, Src/mclib.c:436 */
+int mcrat_b200_find_containing_hydro_cell(mcrat_b200_ctx *ctx, int find_nearest_block_switch,
+                                          int *num_photons_find_new_element);
+/* calcMeanFreePath, Src/mclib.h:10, Src/mclib.c:617.  Returns the head of the time-ordered
+ * list: sorted_indexes[0] and its time_to_scatter (what Src/mcrat.c:777 reads). */
+int mcrat_b200_calc_mean_free_path(mcrat_b200_ctx *ctx, int *first_index, double *first_time_to_scatter);
+/* photonEvent, Src/mclib.h:23, Src/mclib.c:1107 */
+int mcrat_b200_photon_event(mcrat_b200_ctx *ctx, double dt_max, double *time_step, int *scattered_ph_index,
+                            int *frame_scatt_cnt, int *frame_abs_cnt);
+/* updatePhotonPosition, Src/mclib.h:21, Src/mclib.c:1054 */
+int mcrat_b200_update_photon_position(mcrat_b200_ctx *ctx, double t);
+/* phAbsCyclosynch, Src/mc_cyclosynch.h:92, Src/mc_cyclosynch.c:1571 */
+int mcrat_b200_ph_abs_cyclosynch(mcrat_b200_ctx *ctx, int *num_abs_ph, int *scatt_cyclosynch_num_ph,
+                                 double *absorbed_weight);
+/* phMinMax / phScattStats / averagePhotonEnergy, Src/mclib.c:1465 / 1385 / 1358 */
+int mcrat_b200_ph_min_max(mcrat_b200_ctx *ctx, double *min_r, double *max_r, double *min_theta, double *max_theta);
+int mcrat_b200_ph_scatt_stats(mcrat_b200_ctx *ctx, int *max_scatt, int *min_scatt, double *avg_scatt, double *avg_r);
+int mcrat_b200_average_photon_energy(mcrat_b200_ctx *ctx, double *avg_energy);
+
+/* ---- device-resident frame loop ------------------------------------------------------------- */
+/* The whole `while (remaining_time > 0)` loop of Src/mcrat.c:761-851 on the device.
+ * Stops when remaining_time reaches 0, after max_iters iterations (max_iters < 0: no cap),
+ * or when the host must act (stats->cs_host_pending, stats->error). */
+int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remaining_time, long long max_iters,
+                         int find_nearest_grid_switch, mcrat_b200_frame_stats *stats);
+
+/* ---- measurement ------------------------------------------------------------------------------ */
+int mcrat_b200_get_kernel_times(mcrat_b200_ctx *ctx, mcrat_b200_kernel_times *out, int reset);
+/* full photon x cell rescan only (the K1 kernel on the current list), for roofline timing */
+int mcrat_b200_rescan_all(mcrat_b200_ctx *ctx, long long *cell_evals, float *elapsed_ms);
+/* sustained FP64-pipe instruction rate of this GPU (DADD+DSETP mix of the scan), Ginstr/s */
+int mcrat_b200_measure_fp64_peak(mcrat_b200_ctx *ctx, double *ginstr_per_s);
+/* streaming copy bandwidth of this GPU, GB/s (read+write bytes) */
+int mcrat_b200_measure_hbm_peak(mcrat_b200_ctx *ctx, double *gb_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,747 @@
+// device_math.cuh -- FP64 device functions of the MCRaT hot path (sm_100a).
+//
+// Everything here is evaluated in the same operation order as the reference's C code
+// (file:line cited per function) and the library is compiled with -fmad=false, so the
+// only source of difference from the CPU path is the last-ulp behaviour of CUDA's
+// libdevice transcendental functions versus glibc's.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mcrat {
+
+// Src/mclib.c:4-5
+__device__ constexpr double A_RAD = 7.56e-15, C_LIGHT = 2.99792458e10, PL_CONST = 6.6260755e-27,
+                            FINE_STRUCT = 7.29735308e-3, CHARGE_EL = 4.8032068e-10;
+__device__ constexpr double K_B = 1.380658e-16, M_P = 1.6726231e-24, THOM_X_SECT = 6.65246e-25,
+                            M_EL = 9.1093879e-28, R_EL = 2.817941499892705e-13;
+__device__ constexpr double PI = 3.14159265358979323846;
+
+enum { G_CARTESIAN = 0, G_SPHERICAL = 1, G_CYLINDRICAL = 2, G_POLAR = 3 };
+enum { D_TWO = 0, D_TWO_POINT_FIVE = 1, D_THREE = 2 };
+enum { B_INTERNAL_E = 0, B_TOTAL_E = 1, B_SIMULATION = 2 };
+enum { TAU_DIRECT = 1, TAU_TABLE = 2 };
+
+// hot cross-section table extents, Src/hot_x_section.h:2-10
+constexpr int N_PH_E = 220, N_T = 80;
+constexpr double LOG_PH_E_MIN = -12.0, LOG_PH_E_MAX = 6.0, LOG_T_MIN = -4.0, LOG_T_MAX = 4.0;
+
+// ----------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  Counter-based: no RNG state in memory.
+// ----------------------------------------------------------------------------------------
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// two uniforms strictly inside (0,1): ((53-bit integer) + 0.5) * 2^-53
+__host__ __device__ inline void philox_doubles(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1, double &a, double &b)
+{
+    uint32_t r[4];
+    philox4x32_10(c0, c1, c2, c3, k0, k1, r);
+    uint64_t x = (((uint64_t)r[0] << 32) | r[1]) >> 11;
+    uint64_t y = (((uint64_t)r[2] << 32) | r[3]) >> 11;
+    a = ((double)x + 0.5) * (1.0 / 9007199254740992.0);
+    b = ((double)y + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// stream 0: the free-path draw of photon `slot` in while-loop iteration `iter`
+__device__ inline double philox_mfp_uniform(uint32_t k0, uint32_t k1, uint64_t iter, uint32_t slot)
+{
+    double a, b;
+    philox_doubles(slot, (uint32_t)iter, (uint32_t)(iter >> 32), 0u, k0, k1, a, b);
+    return a;
+}
+
+// Sequential uniform source of one scattering event: Philox stream 1 keyed by the iteration
+// number, or (parity harness) the replayed stream of the reference's gsl_rng.
+struct EventRng {
+    int replay;
+    uint32_t k0, k1;
+    uint64_t iter;
+    uint64_t draw;
+    const double *buf;
+    unsigned long long pos, n;
+    int exhausted;
+
+    __device__ double uniform()
+    {
+        if (replay) {
+            if (pos >= n) {
+                exhausted = 1;
+                return 0.5;
+            }
+            return buf[pos++];
+        }
+        double a, b;
+        philox_doubles((uint32_t)(draw >> 1), (uint32_t)iter, (uint32_t)(iter >> 32), 1u, k0, k1, a, b);
+        double u = (draw & 1ull) ? b : a;
+        draw++;
+        return u;
+    }
+    __device__ double uniform_pos()
+    {
+        double x;
+        do {
+            x = uniform();
+        } while (x == 0 && !exhausted);
+        return x;
+    }
+};
+
+// gsl_ran_gaussian (polar Box-Muller)
+__device__ inline double ran_gaussian(EventRng &r, double sigma)
+{
+    double x, y, r2;
+    do {
+        x = -1 + 2 * r.uniform_pos();
+        y = -1 + 2 * r.uniform_pos();
+        r2 = x * x + y * y;
+    } while ((r2 > 1.0 || r2 == 0) && !r.exhausted);
+    return sigma * y * sqrt(-2.0 * log(r2) / r2);
+}
+
+// ----------------------------------------------------------------------------------------
+// tiny BLAS with the reference CBLAS evaluation order (gsl cblas)
+// ----------------------------------------------------------------------------------------
+__device__ inline double dnrm2_3(const double *X)
+{
+    double scale = 0.0, ssq = 1.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const double x = X[i];
+        if (x != 0.0) {
+            const double ax = fabs(x);
+            if (scale < ax) {
+                ssq = 1.0 + ssq * (scale / ax) * (scale / ax);
+                scale = ax;
+            } else {
+                ssq += (ax / scale) * (ax / scale);
+            }
+        }
+    }
+    return scale * sqrt(ssq);
+}
+
+__device__ inline double ddot3(const double *x, const double *y)
+{
+    double r = 0.0;
+    r += x[0] * y[0];
+    r += x[1] * y[1];
+    r += x[2] * y[2];
+    return r;
+}
+
+template <int N>
+__device__ inline void dgemv(const double *A, const double *x, double *y)
+{
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        double temp = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; j++) temp += x[j] * A[N * i + j];
+        y[i] = 0.0 + 1.0 * temp;
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// geometry (Src/geometry.c)
+// ----------------------------------------------------------------------------------------
+// Src/geometry.c:15-64 mcratCoordinateToHydroCoordinate
+__device__ inline void coord_to_hydro(int dims, int g, double x, double y, double z, double &r0, double &r1,
+                                      double &r2)
+{
+    r0 = -1; r1 = -1; r2 = -1;
+    if (dims != D_THREE) {
+        if (g == G_CARTESIAN || g == G_CYLINDRICAL) {
+            r0 = sqrt(x * x + y * y);
+            r1 = z;
+        } else if (g == G_SPHERICAL) {
+            r0 = sqrt(x * x + y * y + z * z);
+            r1 = acos(z / r0);
+        }
+    } else {
+        if (g == G_CARTESIAN) {
+            r0 = x; r1 = y; r2 = z;
+        } else if (g == G_SPHERICAL) {
+            r0 = sqrt(x * x + y * y + z * z);
+            r1 = acos(z / r0);
+            r2 = fmod(atan2(y, x) * 180.0 / PI + 360.0, 360.0) * PI / 180;
+        } else if (g == G_POLAR) {
+            r0 = sqrt(x * x + y * y);
+            r1 = fmod(atan2(y, x) * 180.0 / PI + 360.0, 360.0) * PI / 180;
+            r2 = z;
+        }
+    }
+}
+
+// Src/geometry.c:189-253 hydroVectorToCartesian
+__device__ inline void hydro_vector_to_cartesian(int dims, int g, double *out, double v0, double v1, double v2,
+                                                 double x0, double x1, double x2)
+{
+    double t0 = 0, t1 = 0, t2 = 0;
+    (void)x0;
+    if (dims == D_TWO) {
+        if (g == G_CARTESIAN || g == G_CYLINDRICAL) {
+            t0 = v0 * cos(x2);
+            t1 = v0 * sin(x2);
+            t2 = v1;
+        } else if (g == G_SPHERICAL) {
+            v2 = 0;
+            t0 = v0 * sin(x1) * cos(x2) + v1 * cos(x1) * cos(x2) - v2 * sin(x2);
+            t1 = v0 * sin(x1) * sin(x2) + v1 * cos(x1) * sin(x2) + v2 * cos(x2);
+            t2 = v0 * cos(x1) - v1 * sin(x1);
+        }
+    } else if (dims == D_TWO_POINT_FIVE) {
+        if (g == G_CARTESIAN || g == G_CYLINDRICAL) {
+            t0 = v0 * cos(x2) - v2 * sin(x2);
+            t1 = v0 * sin(x2) + v2 * cos(x2);
+            t2 = v1;
+        } else if (g == G_SPHERICAL) {
+            t0 = v0 * sin(x1) * cos(x2) + v1 * cos(x1) * cos(x2) - v2 * sin(x2);
+            t1 = v0 * sin(x1) * sin(x2) + v1 * cos(x1) * sin(x2) + v2 * cos(x2);
+            t2 = v0 * cos(x1) - v1 * sin(x1);
+        }
+    } else {
+        if (g == G_CARTESIAN) {
+            t0 = v0; t1 = v1; t2 = v2;
+        } else if (g == G_SPHERICAL) {
+            t0 = v0 * sin(x1) * cos(x2) + v1 * cos(x1) * cos(x2) - v2 * sin(x2);
+            t1 = v0 * sin(x1) * sin(x2) + v1 * cos(x1) * sin(x2) + v2 * cos(x2);
+            t2 = v0 * cos(x1) - v1 * sin(x1);
+        } else if (g == G_POLAR) {
+            t0 = v0 * cos(x1) - v1 * sin(x1);
+            t1 = v0 * sin(x1) + v1 * cos(x1);
+            t2 = v2;
+        }
+    }
+    out[0] = t0; out[1] = t1; out[2] = t2;
+}
+
+// ----------------------------------------------------------------------------------------
+// Lorentz boost (Src/mclib.c:302-434)
+// ----------------------------------------------------------------------------------------
+// Src/mclib.c:409-434 zeroNorm
+__device__ inline void zero_norm(double *p)
+{
+    double nrm = dnrm2_3(p + 1);
+    if (p[0] != nrm) {
+        p[1] = (p[1] / nrm) * p[0];
+        p[2] = (p[2] / nrm) * p[0];
+        p[3] = (p[3] / nrm) * p[0];
+    }
+}
+
+// Src/mclib.c:302-407 lorentzBoost.  In the zero-velocity branch the reference renormalises
+// its *input* in place (Src/mclib.c:390); p_in is therefore mutable here too.
+__device__ inline void lorentz_boost(const double *b, double *p_in, double *result, bool photon)
+{
+    double beta = dnrm2_3(b);
+    if (beta > 0) {
+        double gamma = 1.0 / sqrt(1 - beta * beta);
+        double L[16];
+        double bb = beta * beta;
+        L[0] = gamma;
+        L[1] = -1 * b[0] * gamma;
+        L[2] = -1 * b[1] * gamma;
+        L[3] = -1 * b[2] * gamma;
+        L[5] = 1 + ((gamma - 1) * (b[0] * b[0]) / bb);
+        L[6] = ((gamma - 1) * (b[0] * b[1] / bb));
+        L[7] = ((gamma - 1) * (b[0] * b[2] / bb));
+        L[10] = 1 + ((gamma - 1) * (b[1] * b[1]) / bb);
+        L[11] = ((gamma - 1) * (b[1] * b[2]) / bb);
+        L[15] = 1 + ((gamma - 1) * (b[2] * b[2]) / bb);
+        L[4] = L[1]; L[8] = L[2]; L[12] = L[3];
+        L[9] = L[6]; L[13] = L[7]; L[14] = L[11];
+        double pp[4];
+        dgemv<4>(L, p_in, pp);
+        if (photon) zero_norm(pp);
+        result[0] = pp[0]; result[1] = pp[1]; result[2] = pp[2]; result[3] = pp[3];
+    } else {
+        if (photon) zero_norm(p_in);
+        result[0] = p_in[0]; result[1] = p_in[1]; result[2] = p_in[2]; result[3] = p_in[3];
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// modified Bessel function K_2 (stands in for gsl_sf_bessel_Kn(2, x); same algorithm as the
+// oracle's mc_bessel_Kn: ascending series for x <= 2, Temme/Steed continued fraction above)
+// ----------------------------------------------------------------------------------------
+__device__ inline double bessel_K2(double x)
+{
+    const double EULER = 0.57721566490153286060651209008240243;
+    double k0, k1;
+    if (x <= 2.0) {
+        double q = 0.25 * x * x;
+        double lh = log(0.5 * x);
+        double term = 1.0, i0 = 1.0, s0 = 0.0, h = 0.0;
+        double term1 = 1.0, i1 = 1.0;
+        double psi_sum = (-EULER) + (1.0 - EULER);
+        double s1 = psi_sum;
+        for (int k = 1; k < 60; ++k) {
+            term *= q / ((double)k * (double)k);
+            h += 1.0 / (double)k;
+            i0 += term;
+            s0 += term * h;
+            term1 *= q / ((double)k * (double)(k + 1));
+            i1 += term1;
+            psi_sum += 1.0 / (double)k + 1.0 / (double)(k + 1);
+            s1 += term1 * psi_sum;
+            if (term < 1e-18 * i0 && term1 < 1e-18 * i1) break;
+        }
+        k0 = -(lh + EULER) * i0 + s0;
+        k1 = 1.0 / x + lh * (0.5 * x) * i1 - 0.25 * x * s1;
+    } else {
+        const double a1 = 0.25;
+        double b = 2.0 * (1.0 + x);
+        double d = 1.0 / b;
+        double h = d, delh = d;
+        double q1 = 0.0, q2 = 1.0;
+        double q = a1, c = a1, a = -a1;
+        double s = 1.0 + q * delh;
+        for (int i = 2; i <= 100000; ++i) {
+            a -= 2.0 * (double)(i - 1);
+            c = -a * c / (double)i;
+            double qnew = (q1 - b * q2) / a;
+            q1 = q2;
+            q2 = qnew;
+            q += c * qnew;
+            b += 2.0;
+            d = 1.0 / (b + a * d);
+            delh = (b * d - 1.0) * delh;
+            h += delh;
+            double dels = q * delh;
+            s += dels;
+            if (fabs(dels / s) < 1e-17) break;
+        }
+        h = a1 * h;
+        double rk0 = sqrt(PI / (2.0 * x)) * exp(-x) / s;
+        k0 = rk0;
+        k1 = rk0 * (x + 0.5 - h) / x;
+    }
+    return k0 + (2.0 * 1.0 / x) * k1;
+}
+
+// ----------------------------------------------------------------------------------------
+// cross sections / optical depth
+// ----------------------------------------------------------------------------------------
+// Src/mc_cyclosynch.c:48-52 calcDimlessTheta
+__device__ inline double calc_dimless_theta(double temp) { return K_B * temp / (M_EL * C_LIGHT * C_LIGHT); }
+
+// Src/mcrat_scattering.c:597-623 kleinNishinaCrossSection
+__device__ inline double kn_cross_section(double e)
+{
+    if (e >= 1e-3) {
+        return (3. / 4.) * (2. / (e * e) + (1. / (2. * e) - (1. + e) / (e * e * e)) * log(1. + 2. * e) +
+                            (1. + e) / ((1. + 2. * e) * (1. + 2. * e)));
+    }
+    return (1. - 2. * e);
+}
+
+struct HotTable {
+    const double *xa; // N_PH_E+1
+    const double *ya; // N_T+1
+    const double *za; // za[j*(N_PH_E+1)+i]
+};
+
+__device__ inline int interp_bsearch(const double *xa, double x, int lo, int hi)
+{
+    int ilo = lo, ihi = hi;
+    while (ihi > ilo + 1) {
+        int i = (ihi + ilo) / 2;
+        if (xa[i] > x)
+            ihi = i;
+        else
+            ilo = i;
+    }
+    return ilo;
+}
+
+// gsl_interp2d bilinear (Src/hot_x_section.c:556); returns false outside the grid (GSL_EDOM)
+__device__ inline bool bilinear_eval(const HotTable &t, double x, double y, double &z)
+{
+    const int nx = N_PH_E + 1, ny = N_T + 1;
+    if (x < t.xa[0] || x > t.xa[nx - 1]) return false;
+    if (y < t.ya[0] || y > t.ya[ny - 1]) return false;
+    int xi = interp_bsearch(t.xa, x, 0, nx - 1);
+    int yi = interp_bsearch(t.ya, y, 0, ny - 1);
+    double xmin = t.xa[xi], xmax = t.xa[xi + 1];
+    double ymin = t.ya[yi], ymax = t.ya[yi + 1];
+    double zminmin = t.za[yi * nx + xi];
+    double zminmax = t.za[(yi + 1) * nx + xi];
+    double zmaxmin = t.za[yi * nx + xi + 1];
+    double zmaxmax = t.za[(yi + 1) * nx + xi + 1];
+    double dx = xmax - xmin, dy = ymax - ymin;
+    double tt = (x - xmin) / dx;
+    double u = (y - ymin) / dy;
+    z = (1. - tt) * (1. - u) * zminmin + tt * (1. - u) * zmaxmin + (1. - tt) * u * zminmax + tt * u * zmaxmax;
+    return true;
+}
+
+// Src/optical_depth.c:132-149 getThermalCrossSection + Src/hot_x_section.c:545-605.
+// Outside the table the reference integrates the cross section by plain Monte Carlo with its
+// gsl_rng (500 000 samples, Src/hot_x_section.c:324-357).  The two closed-form early returns of
+// that routine (theta below the table, :336-339) are reproduced; the Monte Carlo branch raises
+// `*table_err` instead (reported to the host as MCRAT_B200_ERR_TABLE).
+__device__ inline double thermal_cross_section(int tau_calc, const HotTable &t, double comv_e, double temp,
+                                               int *table_err)
+{
+    if (tau_calc != TAU_TABLE) return 1;
+    double ne = comv_e / (M_EL * C_LIGHT);
+    double theta = calc_dimless_theta(temp);
+    double le = log10(ne), lt = log10(theta);
+    double res;
+    if (!bilinear_eval(t, le, lt, res)) {
+        double ph_comv = pow(10.0, le);
+        double th = pow(10.0, lt);
+        double direct;
+        if (th < pow(10.0, LOG_T_MIN) && ph_comv < pow(10.0, LOG_PH_E_MIN)) {
+            direct = 1;
+        } else if (th < pow(10.0, LOG_T_MIN)) {
+            direct = kn_cross_section(ph_comv);
+        } else {
+            if (table_err) *table_err = 1;
+            direct = kn_cross_section(ph_comv);
+        }
+        res = log10(direct);
+    }
+    return pow(10.0, res);
+}
+
+// cell fields a photon needs once it is located
+struct CellState {
+    double v0, v1, v2, r0, r1, r2, gamma, dens_lab, temp;
+};
+
+// Src/optical_depth.c:7-115 calculateOpticalDepth (NONTHERMAL_E_DIST == OFF)
+__device__ inline double optical_depth(int dims, int g, int tau_calc, const HotTable &t, const CellState &c,
+                                       double ph_r0, double ph_r1, double p1, double p2, double p3, double comv_p0,
+                                       int *table_err)
+{
+    double fb[3];
+    if (dims == D_THREE) {
+        hydro_vector_to_cartesian(dims, g, fb, c.v0, c.v1, c.v2, c.r0, c.r1, c.r2);
+    } else if (dims == D_TWO_POINT_FIVE) {
+        double ph_phi = atan2(ph_r1, ph_r0);
+        hydro_vector_to_cartesian(dims, g, fb, c.v0, c.v1, c.v2, c.r0, c.r1, ph_phi);
+    } else {
+        double ph_phi = atan2(ph_r1, ph_r0);
+        hydro_vector_to_cartesian(dims, g, fb, c.v0, c.v1, 0, c.r0, c.r1, ph_phi);
+    }
+    double fl_v_norm = sqrt(fb[0] * fb[0] + fb[1] * fb[1] + fb[2] * fb[2]);
+    double ph_v_norm = sqrt(p1 * p1 + p2 * p2 + p3 * p3);
+    double n_cosangle = ((fb[0] * p1) + (fb[1] * p2) + (fb[2] * p3)) / (fl_v_norm * ph_v_norm);
+    double beta = sqrt(1.0 - 1.0 / (c.gamma * c.gamma));
+    double fluid_factor = (1.0 - beta * n_cosangle);
+    double n_lab = c.dens_lab / M_P;
+    double sig = thermal_cross_section(tau_calc, t, comv_p0, c.temp, table_err);
+    return (n_lab) * (THOM_X_SECT * sig) * fluid_factor;
+}
+
+// ----------------------------------------------------------------------------------------
+// Stokes-plane rotations (Src/mcrat_scattering.c:10-149)
+// ----------------------------------------------------------------------------------------
+// Src/mcrat_scattering.c:10-39 mullerMatrixRotation
+__device__ inline void muller_rotation(double theta, double *s)
+{
+    double M[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) M[i] = 0;
+    M[0] = 1;
+    M[15] = 1;
+    M[5] = cos(2 * theta);
+    M[10] = cos(2 * theta);
+    M[6] = -1 * sin(2 * theta);
+    M[9] = sin(2 * theta);
+    double r[4];
+    dgemv<4>(M, s, r);
+    s[0] = r[0]; s[1] = r[1]; s[2] = r[2]; s[3] = r[3];
+}
+
+// Src/mcrat_scattering.c:41-65 findXY
+__device__ inline void find_xy(const double *v, const double *a, double *x, double *y)
+{
+    y[0] = (v[1] * a[2] - v[2] * a[1]);
+    y[1] = -1 * (v[0] * a[2] - v[2] * a[0]);
+    y[2] = (v[0] * a[1] - v[1] * a[0]);
+    double norm = 1.0 / sqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);
+    y[0] *= norm; y[1] *= norm; y[2] *= norm;
+    x[0] = y[1] * v[2] - y[2] * v[1];
+    x[1] = -1 * (y[0] * v[2] - y[2] * v[0]);
+    x[2] = y[0] * v[1] - y[1] * v[0];
+    norm = 1.0 / sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    x[0] *= norm; x[1] *= norm; x[2] *= norm;
+}
+
+// Src/mcrat_scattering.c:67-101 findPhi
+__device__ inline double find_phi(const double *x_old, const double *y_old, const double *y_new)
+{
+    double dot = ddot3(x_old, y_new);
+    double factor = (dot > 0) ? 1.0 : ((dot < 0) ? -1.0 : 0.0);
+    dot = ddot3(y_old, y_new);
+    if ((dot < -1) || (dot > 1)) dot = round(dot);
+    return -1 * factor * acos(dot);
+}
+
+// Src/mcrat_scattering.c:103-149 stokesRotation
+__device__ inline void stokes_rotation(const double *v, const double *v_ph, const double *v_ph_boosted, double *s)
+{
+    const double z_hat[3] = {0, 0, 1};
+    double x[3], y[3], xn[3], yn[3];
+    find_xy(v_ph, z_hat, x, y);
+    find_xy(v_ph, v, xn, yn);
+    double phi = find_phi(x, y, yn);
+    muller_rotation(phi, s);
+    find_xy(v_ph_boosted, v, x, y);
+    find_xy(v_ph_boosted, z_hat, xn, yn);
+    phi = find_phi(x, y, yn);
+    muller_rotation(phi, s);
+}
+
+// ----------------------------------------------------------------------------------------
+// Klein-Nishina scatter (Src/mcrat_scattering.c:151-595)
+// ----------------------------------------------------------------------------------------
+// Src/mcrat_scattering.c:509-595 kleinNishinaScatter
+__device__ inline int kn_scatter(int stokes, double &theta, double &phi, double p0, double q, double u, EventRng &rng)
+{
+    double er = p0 / (M_EL * C_LIGHT);
+    double kn = kn_cross_section(er);
+    double rand_num = rng.uniform();
+    if (!(rand_num <= kn)) return 0;
+    double cty = 1, ct = 0, fct = 0;
+    while (cty > fct && !rng.exhausted) {
+        cty = rng.uniform() * 2;
+        ct = rng.uniform() * 2 - 1;
+        double m1 = (1 + er * (1 - ct));
+        fct = pow(m1, -2.0) * (er * (1 - ct) + (1 / (1 + er * (1 - ct))) + ct * ct);
+    }
+    theta = acos(ct);
+    double mu = 1 + er * (1 - cos(theta));
+    double st = sin(theta);
+    double f_theta = (pow(mu, -1.0) + pow(mu, -3.0) - pow(mu, -2.0) * st * st) * st;
+    double phi_y = 1, f_phi = 0, phi_dum = 0;
+    while (phi_y > f_phi && !rng.exhausted) {
+        if (!stokes || (u == 0 && q == 0)) {
+            phi_dum = rng.uniform() * 2 * PI;
+            phi_y = -1;
+        } else {
+            double phi_max = fabs(atan2(-u, q)) / 2.0;
+            double norm = (f_theta + pow(mu, -2.0) * st * st * st * (q * cos(2 * phi_max) - u * sin(2 * phi_max)));
+            phi_y = rng.uniform();
+            phi_dum = rng.uniform() * 2 * PI;
+            f_phi = (f_theta + pow(mu, -2.0) * st * st * st * (q * cos(2 * phi_dum) - u * sin(2 * phi_dum))) / norm;
+        }
+    }
+    phi = phi_dum;
+    return 1;
+}
+
+// Src/mcrat_scattering.c:151-485 singleScatter
+__device__ inline int single_scatter(int stokes, double *el_comov, double *ph_comov, double *s, EventRng &rng)
+{
+    const double z_axis[3] = {0, 0, 1};
+    double el_v[3], neg_el_v[3], php[4], elp[4];
+    double rot[9], result0[3], result1[3], result[4], orig[4];
+    double *ph_p = php + 1;
+
+    el_v[0] = el_comov[1] / el_comov[0];
+    el_v[1] = el_comov[2] / el_comov[0];
+    el_v[2] = el_comov[3] / el_comov[0];
+
+    lorentz_boost(el_v, el_comov, elp, false);
+    lorentz_boost(el_v, ph_comov, php, true);
+
+    if (stokes) stokes_rotation(el_v, ph_comov + 1, php + 1, s);
+
+    orig[0] = php[0]; orig[1] = php[1]; orig[2] = php[2]; orig[3] = php[3];
+
+    double phi0 = atan2(php[2], php[1]);
+#pragma unroll
+    for (int i = 0; i < 9; i++) rot[i] = 0;
+    rot[8] = 1;
+    rot[0] = cos(-phi0);
+    rot[4] = cos(-phi0);
+    rot[1] = -sin(-phi0);
+    rot[3] = sin(-phi0);
+    dgemv<3>(rot, ph_p, result0);
+    php[1] = result0[0];
+    php[2] = 0;
+    php[3] = result0[2];
+
+    double phi1 = atan2(result0[2], result0[0]);
+#pragma unroll
+    for (int i = 0; i < 9; i++) rot[i] = 0;
+    rot[4] = 1;
+    rot[0] = cos(-phi1);
+    rot[8] = cos(-phi1);
+    rot[2] = -sin(-phi1);
+    rot[6] = sin(-phi1);
+    dgemv<3>(rot, ph_p, result1);
+    php[1] = php[0];
+    php[2] = result1[1];
+    php[3] = 0;
+
+    double theta = 0, phi = 0;
+    int occurred = kn_scatter(stokes, theta, phi, php[0], s[1], s[2], rng);
+    if (occurred == 1) {
+        result[0] = (php[0]) / (1 + (((php[0]) * (1 - cos(theta))) / (M_EL * C_LIGHT)));
+        result[1] = result[0] * cos(theta);
+        result[2] = result[0] * sin(theta) * sin(phi);
+        result[3] = result[0] * sin(theta) * cos(phi);
+
+        php[0] = result[0]; php[1] = result[1]; php[2] = result[2]; php[3] = result[3];
+#pragma unroll
+        for (int i = 0; i < 9; i++) rot[i] = 0;
+        rot[4] = 1;
+        rot[0] = cos(-phi1);
+        rot[8] = cos(-phi1);
+        rot[2] = sin(-phi1);
+        rot[6] = -sin(-phi1);
+        dgemv<3>(rot, ph_p, result1);
+        php[1] = result1[0]; php[2] = result1[1]; php[3] = result1[2];
+#pragma unroll
+        for (int i = 0; i < 9; i++) rot[i] = 0;
+        rot[8] = 1;
+        rot[0] = cos(-phi0);
+        rot[4] = cos(-phi0);
+        rot[1] = sin(-phi0);
+        rot[3] = -sin(-phi0);
+        dgemv<3>(rot, ph_p, result0);
+
+        if (stokes) {
+            double xt[3], yt[3], xtn[3], ytn[3];
+            find_xy(orig + 1, z_axis, xt, yt);
+            find_xy(result0, orig + 1, xtn, ytn);
+            double ph = find_phi(xt, yt, ytn);
+            muller_rotation(ph, s);
+
+            double th = acos((orig[1] * result0[0] + orig[2] * result0[1] + orig[3] * result0[2]) / (orig[0] * (php[0])));
+            double ct = cos(th), sn = sin(th);
+            double scatt[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) scatt[i] = 0;
+            scatt[0] = 1.0 + pow(ct, 2.0) + ((1 - ct) * (orig[0] - result[0]) / (M_EL * C_LIGHT));
+            scatt[1] = sn * sn;
+            scatt[4] = sn * sn;
+            scatt[5] = 1.0 + ct * ct;
+            scatt[10] = 2.0 * ct;
+            scatt[15] = 2.0 * ct + ((ct) * (1 - ct) * (orig[0] - result[0]) / (M_EL * C_LIGHT));
+            double sr[4];
+            dgemv<4>(scatt, s, sr);
+            s[0] = sr[0] / sr[0];
+            s[1] = sr[1] / sr[0];
+            s[2] = sr[2] / sr[0];
+            s[3] = sr[3] / sr[0];
+
+            find_xy(result0, orig + 1, xt, yt);
+            find_xy(result0, z_axis, xtn, ytn);
+            ph = find_phi(xt, yt, ytn);
+            muller_rotation(ph, s);
+        }
+        php[1] = result0[0]; php[2] = result0[1]; php[3] = result0[2];
+        neg_el_v[0] = (-1 * el_v[0]);
+        neg_el_v[1] = (-1 * el_v[1]);
+        neg_el_v[2] = (-1 * el_v[2]);
+        lorentz_boost(neg_el_v, php, ph_comov, true);
+        if (stokes) stokes_rotation(neg_el_v, php + 1, ph_comov + 1, s);
+    }
+    return occurred;
+}
+
+// ----------------------------------------------------------------------------------------
+// electron sampling (Src/electron.c:70-237)
+// ----------------------------------------------------------------------------------------
+// Src/electron.c:202-237 sampleThermalElectron
+__device__ inline double sample_thermal_electron(double temp, EventRng &rng)
+{
+    double gamma = 1;
+    if (temp >= 1e7) {
+        double factor = K_B * temp / (M_EL * C_LIGHT * C_LIGHT);
+        double k2 = bessel_K2(1.0 / factor);
+        double y = 1, f = 0, x = 0;
+        while (((f != f) || (y > f)) && !rng.exhausted) {
+            x = rng.uniform_pos() * (1 + 100 * factor);
+            double bx = sqrt(1 - (1 / (x * x)));
+            y = rng.uniform() / 2.0;
+            f = x * x * (bx / k2) * exp(-1 * x / factor);
+        }
+        gamma = x;
+    } else {
+        double factor = sqrt(K_B * temp / M_EL);
+        double g1 = ran_gaussian(rng, factor);
+        double g2 = ran_gaussian(rng, factor);
+        double g3 = ran_gaussian(rng, factor);
+        double a = g1 / C_LIGHT, b = g2 / C_LIGHT, c = g3 / C_LIGHT;
+        gamma = 1.0 / sqrt(1 - (a * a + b * b + c * c));
+    }
+    return gamma;
+}
+
+// Src/electron.c:126-175 rotateElectron
+__device__ inline void rotate_electron(double *el_p, const double *ph_p)
+{
+    double rot[9], result[3];
+    double *e = el_p + 1;
+    double ph_phi = atan2(ph_p[2], ph_p[3]);
+    double ph_theta = atan2(sqrt(ph_p[2] * ph_p[2] + ph_p[3] * ph_p[3]), ph_p[1]);
+#pragma unroll
+    for (int i = 0; i < 9; i++) rot[i] = 0;
+    rot[4] = 1;
+    rot[8] = cos(ph_theta);
+    rot[0] = cos(ph_theta);
+    rot[2] = -sin(ph_theta);
+    rot[6] = sin(ph_theta);
+    dgemv<3>(rot, e, result);
+#pragma unroll
+    for (int i = 0; i < 9; i++) rot[i] = 0;
+    rot[0] = 1;
+    rot[4] = cos(-ph_phi);
+    rot[8] = cos(-ph_phi);
+    rot[5] = -sin(-ph_phi);
+    rot[7] = sin(-ph_phi);
+    double out[3];
+    dgemv<3>(rot, result, out);
+    e[0] = out[0]; e[1] = out[1]; e[2] = out[2];
+}
+
+// Src/electron.c:70-94 singleThermalElectron (+ :177-200 sampleElectronTheta)
+__device__ inline void single_thermal_electron(double *el_p, double temp, const double *ph_p, EventRng &rng)
+{
+    double gamma = sample_thermal_electron(temp, rng);
+    double beta = sqrt(1 - (1 / (gamma * gamma)));
+    double phi = rng.uniform() * 2 * PI;
+    double theta = acos((1 - sqrt(1 + beta * beta + 2 * beta - 4 * beta * rng.uniform())) / beta);
+    el_p[0] = gamma * (M_EL) * (C_LIGHT);
+    el_p[1] = gamma * (M_EL) * (C_LIGHT)*beta * cos(theta);
+    el_p[2] = gamma * (M_EL) * (C_LIGHT)*beta * sin(theta) * sin(phi);
+    el_p[3] = gamma * (M_EL) * (C_LIGHT)*beta * sin(theta) * cos(phi);
+    rotate_electron(el_p, ph_p);
+}
+
+// ----------------------------------------------------------------------------------------
+// cyclo-synchrotron helpers (Src/mc_cyclosynch.c:30-92)
+// ----------------------------------------------------------------------------------------
+__device__ inline double calc_cyclotron_freq(double b) { return CHARGE_EL * b / (2 * PI * M_EL * C_LIGHT); }
+
+__device__ inline double calc_b(int b_field_calc, double epsilon_b, double el_dens, double temp)
+{
+    if (b_field_calc == B_INTERNAL_E) return sqrt(epsilon_b * 8 * PI * 3 * el_dens * K_B * temp / 2);
+    if (b_field_calc == B_TOTAL_E)
+        return sqrt(8 * PI * epsilon_b * (el_dens * M_P * C_LIGHT * C_LIGHT + 4 * A_RAD * temp * temp * temp * temp / 3));
+    return 0;
+}
+
+} // namespace mcrat

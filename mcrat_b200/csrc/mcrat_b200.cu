@@ -1,0 +1,1960 @@
+// mcrat_b200.cu -- kernels and C ABI of the B200-native MCRaT hot path (sm_100a, FP64).
+//
+// Kernel map (DESIGN.md has the data layout and the roofline of each):
+//   K1  scan_kernel        photon x cell containment scan, cells staged in shared memory by
+//                          TMA bulk copies (cp.async.bulk + mbarrier), photons register-tiled.
+//                          Replaces findContainingBlock's O(N_cells) loop,
+//                          Src/geometry.c:350-391 -> :394-417, for a whole relocation list.
+//   K1b scan_few_kernel    the same test, cell-parallel, for the handful of photons that
+//                          leave their cell in a steady-state iteration.
+//   K4+K2 pass_kernel      fused push (Src/mclib.c:1054-1100) + domain / in-cell re-check
+//                          (Src/mclib.c:469-597) + free-path draw (Src/mclib.c:646-692) +
+//                          warp-shuffle / block arg-min over time_to_scatter (replaces the
+//                          qsort of Src/mclib.c:702-710: only the head of the order is used).
+//       finish_kernel      re-boost + optical depth of relocated photons (Src/mclib.c:538-580).
+//   K3  event_kernel       global arg-min + photonEvent (Src/mclib.c:1107-1356): fluid-frame
+//                          boost, electron sampling, polarised Klein-Nishina scatter, Stokes
+//                          rotations, boost back; plus the driver's bookkeeping of
+//                          Src/mcrat.c:777-846.
+//   K5  cs_absorb_kernel   phAbsCyclosynch, Src/mc_cyclosynch.c:1571-1644.
+// No CPU fallback exists: every entry point fails with MCRAT_B200_ERR_CUDA without a device.
+#include "../../include/mcrat_b200.h"
+#include "device_math.cuh"
+
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace mcrat;
+
+static_assert(sizeof(mcrat_photon) == 176, "struct photon layout (Src/mcrat.h:142-171) must be 176 bytes");
+
+#define API extern "C" __attribute__((visibility("default")))
+
+// ------------------------------------------------------------------------------------------
+// device-side data
+// ------------------------------------------------------------------------------------------
+enum : unsigned char { F_MOVABLE = 1, F_RECALC = 2 };
+
+constexpr int MAX_DT = 64;         // pushes recorded by one event (1 + Klein-Nishina rejections)
+constexpr int BLOCKMIN_CAP = 4096; // per-block arg-min slots
+constexpr int SCAN_THREADS = 128;
+constexpr int SCAN_P = 8;      // photons per thread held in registers
+constexpr int SCAN_TILE = 512; // cells per shared-memory stage
+constexpr int FEW_RMAX = 128;  // relocating photons handled per pass of the cell-parallel scan
+
+struct PhotonCols {
+    double *r0, *r1, *r2, *p0, *p1, *p2, *p3, *c0, *c1, *c2, *c3, *s0, *s1, *s2, *s3, *nscatt, *weight, *tau, *tts;
+    int *idx;
+    unsigned char *flags;
+    char *type;
+};
+
+struct CellCols {
+    int n, n_padded;
+    const double4 *geoA; // 2-D: (c0, c1, h0, h1); 3-D: (c0, c1, c2, h0)     h = 0.5 * size
+    const double2 *geoB; // 3-D: (h1, h2)
+    const double *r0, *r1, *r2, *v0, *v1, *v2, *dens, *dens_lab, *temp, *gamma, *B0, *B1, *B2;
+    double dom[6];
+};
+
+struct LoopState {
+    double time_now, remaining_time, last_time_step;
+    double dt_list[MAX_DT];
+    int n_dt;
+    int pushed_slot;
+    int reloc_count[2];
+    unsigned long long iter;
+    long long scatt_cnt, reloc_total, slots, cell_evals, iters_done, max_iters;
+    int done, pause_cs, error, not_found;
+    int last_scattered_idx;
+    int head_idx;
+    double head_tts;
+    unsigned long long replay_cursor, replay_base, replay_n;
+    int abs_count, cs_scatt_count;
+    double abs_weight;
+};
+
+struct DevCtx {
+    int dims, geom, stokes, tau_calc, cs, b_calc;
+    double epsilon_b;
+    uint32_t k0, k1;
+    int replay;
+    int cap;
+    PhotonCols ph;
+    CellCols cells;
+    HotTable table;
+    LoopState *st;
+    // relocation scratch
+    int *reloc_slot;
+    double *reloc_h0, *reloc_h1, *reloc_h2;
+    int *reloc_best;
+    int reloc_cap; // padded
+    // arg-min scratch: [0,BLOCKMIN_CAP) pass blocks, [BLOCKMIN_CAP, 2*BLOCKMIN_CAP) finish blocks
+    double *bm_t;
+    int *bm_i;
+    // replay
+    const double *replay_buf;
+    int *prefix_block; // per-256-block counts / offsets
+};
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+// every kernel of the frame loop evaluates the same stop condition, so one iteration is
+// either executed completely or not at all
+__device__ __forceinline__ bool loop_stopped(const LoopState &st)
+{
+    return st.done | st.pause_cs | (st.error != 0) | (st.max_iters >= 0 && st.iters_done >= st.max_iters);
+}
+
+__device__ __forceinline__ bool lex_less(double ta, int ia, double tb, int ib) { return (ta < tb) || (ta == tb && ia < ib); }
+
+// warp-shuffle + shared-memory arg-min over (time, slot); ties broken by lowest slot
+template <int THREADS>
+__device__ __forceinline__ void block_argmin(double &t, int &i)
+{
+    __shared__ double sh_t[THREADS / 32];
+    __shared__ int sh_i[THREADS / 32];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double ot = __shfl_xor_sync(0xffffffffu, t, off);
+        int oi = __shfl_xor_sync(0xffffffffu, i, off);
+        if (lex_less(ot, oi, t, i)) {
+            t = ot;
+            i = oi;
+        }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) {
+        sh_t[w] = t;
+        sh_i[w] = i;
+    }
+    __syncthreads();
+    if (w == 0) {
+        t = (lane < THREADS / 32) ? sh_t[lane] : DBL_MAX;
+        i = (lane < THREADS / 32) ? sh_i[lane] : INT_MAX;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double ot = __shfl_xor_sync(0xffffffffu, t, off);
+            int oi = __shfl_xor_sync(0xffffffffu, i, off);
+            if (lex_less(ot, oi, t, i)) {
+                t = ot;
+                i = oi;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ bool in_cell(int ndim3, const CellCols &c, int blk, double h0, double h1, double h2)
+{
+    // Src/geometry.c:394-417 checkInBlock: 2|x-c| - size <= 0  <=>  |x-c| <= size/2 (both exact scalings)
+    double4 a = c.geoA[blk];
+    if (!ndim3) return (fabs(h0 - a.x) <= a.z) & (fabs(h1 - a.y) <= a.w);
+    double2 b = c.geoB[blk];
+    return (fabs(h0 - a.x) <= a.w) & (fabs(h1 - a.y) <= b.x) & (fabs(h2 - a.z) <= b.y);
+}
+
+__device__ __forceinline__ CellState load_cell_state(const CellCols &c, int i)
+{
+    CellState s;
+    s.v0 = c.v0[i];
+    s.v1 = c.v1[i];
+    s.v2 = c.v2[i];
+    s.r0 = c.r0[i];
+    s.r1 = c.r1[i];
+    s.r2 = c.r2[i];
+    s.gamma = c.gamma[i];
+    s.dens_lab = c.dens_lab[i];
+    s.temp = c.temp[i];
+    return s;
+}
+
+__device__ __forceinline__ void fluid_beta_of(const DevCtx &d, const CellState &c, double ph_r0, double ph_r1, double *fb)
+{
+    if (d.dims == D_THREE) {
+        hydro_vector_to_cartesian(d.dims, d.geom, fb, c.v0, c.v1, c.v2, c.r0, c.r1, c.r2);
+    } else if (d.dims == D_TWO_POINT_FIVE) {
+        double ph_phi = atan2(ph_r1, ph_r0);
+        hydro_vector_to_cartesian(d.dims, d.geom, fb, c.v0, c.v1, c.v2, c.r0, c.r1, ph_phi);
+    } else {
+        double ph_phi = atan2(ph_r1, ph_r0);
+        hydro_vector_to_cartesian(d.dims, d.geom, fb, c.v0, c.v1, 0, c.r0, c.r1, ph_phi);
+    }
+}
+
+// time_to_scatter of an in-domain photon, Src/mclib.c:675-687
+__device__ __forceinline__ double free_path_time(double tau, double xi)
+{
+    double mfp = (-1.0 / tau) * log(xi);
+    return mfp / C_LIGHT;
+}
+
+// ------------------------------------------------------------------------------------------
+// AoS <-> SoA (the boundary: `struct photon` records <-> device columns)
+// ------------------------------------------------------------------------------------------
+__global__ void unpack_kernel(DevCtx d, const mcrat_photon *aos, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        mcrat_photon p = aos[i];
+        d.ph.type[i] = p.type;
+        d.ph.p0[i] = p.p0; d.ph.p1[i] = p.p1; d.ph.p2[i] = p.p2; d.ph.p3[i] = p.p3;
+        d.ph.c0[i] = p.comv_p0; d.ph.c1[i] = p.comv_p1; d.ph.c2[i] = p.comv_p2; d.ph.c3[i] = p.comv_p3;
+        d.ph.r0[i] = p.r0; d.ph.r1[i] = p.r1; d.ph.r2[i] = p.r2;
+        d.ph.s0[i] = p.s0; d.ph.s1[i] = p.s1; d.ph.s2[i] = p.s2; d.ph.s3[i] = p.s3;
+        d.ph.nscatt[i] = p.num_scatt;
+        d.ph.weight[i] = p.weight;
+        d.ph.idx[i] = p.nearest_block_index;
+        d.ph.tts[i] = p.time_to_scatter;
+        d.ph.tau[i] = p.total_optical_depth;
+        unsigned char f = 0;
+        if ((p.type != 'p') && (p.weight != 0)) f |= F_MOVABLE; // Src/mclib.c:1070
+        if (p.recalc_properties == 1) f |= F_RECALC;
+        d.ph.flags[i] = f;
+    }
+}
+
+__global__ void pack_kernel(DevCtx d, mcrat_photon *aos, int first, int n)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        int i = first + j;
+        mcrat_photon p;
+        memset(&p, 0, sizeof(p));
+        p.type = d.ph.type[i];
+        p.p0 = d.ph.p0[i]; p.p1 = d.ph.p1[i]; p.p2 = d.ph.p2[i]; p.p3 = d.ph.p3[i];
+        p.comv_p0 = d.ph.c0[i]; p.comv_p1 = d.ph.c1[i]; p.comv_p2 = d.ph.c2[i]; p.comv_p3 = d.ph.c3[i];
+        p.r0 = d.ph.r0[i]; p.r1 = d.ph.r1[i]; p.r2 = d.ph.r2[i];
+        p.s0 = d.ph.s0[i]; p.s1 = d.ph.s1[i]; p.s2 = d.ph.s2[i]; p.s3 = d.ph.s3[i];
+        p.num_scatt = d.ph.nscatt[i];
+        p.recalc_properties = (d.ph.flags[i] & F_RECALC) ? 1 : 0;
+        p.weight = d.ph.weight[i];
+        p.nearest_block_index = d.ph.idx[i];
+        p.time_to_scatter = d.ph.tts[i];
+        p.total_optical_depth = d.ph.tau[i];
+        aos[j] = p;
+    }
+}
+
+// cell SoA -> scan layout (centres + half sizes), NaN-padded so that padding never matches
+__global__ void build_geo_kernel(int ndim3, int n, int n_padded, const double *c0, const double *c1, const double *c2,
+                                 const double *s0, const double *s1, const double *s2, double4 *geoA, double2 *geoB)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += gridDim.x * blockDim.x) {
+        const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+        if (i < n) {
+            if (!ndim3) {
+                geoA[i] = make_double4(c0[i], c1[i], 0.5 * s0[i], 0.5 * s1[i]);
+            } else {
+                geoA[i] = make_double4(c0[i], c1[i], c2[i], 0.5 * s0[i]);
+                geoB[i] = make_double2(0.5 * s1[i], 0.5 * s2[i]);
+            }
+        } else {
+            geoA[i] = make_double4(qnan, qnan, qnan, qnan);
+            if (ndim3) geoB[i] = make_double2(qnan, qnan);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4+K2: fused push + locate re-check + free-path draw + block arg-min
+// ------------------------------------------------------------------------------------------
+constexpr int PASS_THREADS = 256;
+
+template <bool FUSE_MFP>
+__global__ void __launch_bounds__(PASS_THREADS) pass_kernel(DevCtx d, int sw, int parity)
+{
+    const LoopState &st = *d.st;
+    if (loop_stopped(st)) return;
+    const int n_dt = st.n_dt;
+    const int pushed = st.pushed_slot;
+    const unsigned long long iter = st.iter;
+    const int ndim3 = (d.dims == D_THREE);
+    if (blockIdx.x == 0 && threadIdx.x == 0) d.st->reloc_count[parity ^ 1] = 0;
+
+    double best_t = DBL_MAX;
+    int best_i = INT_MAX;
+    const double default_t = 1e12 / C_LIGHT; // Src/mclib.c:620, 684-687
+
+    for (int i = blockIdx.x * PASS_THREADS + threadIdx.x; i < d.cap; i += gridDim.x * PASS_THREADS) {
+        unsigned char flags = d.ph.flags[i];
+        int idx = d.ph.idx[i];
+        double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
+        // pending pushes of the previous event, Src/mclib.c:1054-1100 (applied one by one: the
+        // reference pushes once per candidate it tries, Src/mclib.c:1138, 1332)
+        if (n_dt > 0 && (flags & F_MOVABLE) && i != pushed) {
+            double p0 = d.ph.p0[i], p1 = d.ph.p1[i], p2 = d.ph.p2[i], p3 = d.ph.p3[i];
+            double div = 1.0 / p0;
+            for (int k = 0; k < n_dt; ++k) {
+                double t = st.dt_list[k];
+                r0 += p1 * div * C_LIGHT * t;
+                r1 += p2 * div * C_LIGHT * t;
+                r2 += p3 * div * C_LIGHT * t;
+            }
+            d.ph.r0[i] = r0;
+            d.ph.r1[i] = r1;
+            d.ph.r2[i] = r2;
+        }
+        // findContainingHydroCell, Src/mclib.c:469-597
+        double h0, h1, h2;
+        coord_to_hydro(d.dims, d.geom, r0, r1, r2, h0, h1, h2);
+        bool in_domain;
+        if (!ndim3)
+            in_domain = ((h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) && (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0])) &&
+                        (idx != -1);
+        else
+            in_domain = ((h2 < d.cells.dom[5]) && (h2 > d.cells.dom[4]) && (h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) &&
+                         (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0])) &&
+                        (idx != -1);
+        double t = default_t;
+        bool have_t = true;
+        if (in_domain) {
+            int blk = (sw == 0) ? idx : 0;
+            bool inb = in_cell(ndim3, d.cells, blk, h0, h1, h2);
+            if (d.cs && blk == 0) { // Src/mclib.c:510-515
+                if ((d.ph.c0[i]) + (d.ph.c1[i]) + (d.ph.c2[i]) + (d.ph.c3[i]) == 0) inb = false;
+            }
+            if (sw == 1 || !inb) {
+                int pos = atomicAdd(&d.st->reloc_count[parity], 1);
+                d.reloc_slot[pos] = i;
+                d.reloc_h0[pos] = h0;
+                d.reloc_h1[pos] = h1;
+                d.reloc_h2[pos] = h2;
+                d.reloc_best[pos] = INT_MAX;
+                have_t = false; // finish_kernel completes this photon
+            } else if (FUSE_MFP) {
+                // calcMeanFreePath, Src/mclib.c:657-687
+                double tau;
+                if (flags & F_RECALC) {
+                    CellState c = load_cell_state(d.cells, idx);
+                    int terr = 0;
+                    tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, d.ph.p1[i], d.ph.p2[i], d.ph.p3[i],
+                                        d.ph.c0[i], &terr);
+                    if (terr) d.st->error = MCRAT_B200_ERR_TABLE;
+                    d.ph.tau[i] = tau;
+                    d.ph.flags[i] = flags & ~F_RECALC;
+                } else {
+                    tau = d.ph.tau[i];
+                }
+                double xi = philox_mfp_uniform(d.k0, d.k1, iter, (uint32_t)i);
+                t = free_path_time(tau, xi);
+            }
+        } else {
+            if (idx != -1) d.ph.idx[i] = -1; // Src/mclib.c:589-595
+        }
+        if (FUSE_MFP && have_t) {
+            d.ph.tts[i] = t;
+            if (lex_less(t, i, best_t, best_i)) {
+                best_t = t;
+                best_i = i;
+            }
+        }
+    }
+    if (FUSE_MFP) {
+        block_argmin<PASS_THREADS>(best_t, best_i);
+        if (threadIdx.x == 0) {
+            d.bm_t[blockIdx.x] = best_t;
+            d.bm_i[blockIdx.x] = best_i;
+        }
+    }
+}
+
+// push only: updatePhotonPosition called directly by the driver (Src/mcrat.c:841), and the
+// materialisation of pending event pushes before a download
+__global__ void __launch_bounds__(PASS_THREADS) flush_push_kernel(DevCtx d)
+{
+    const LoopState &st = *d.st;
+    const int n_dt = st.n_dt;
+    const int pushed = st.pushed_slot;
+    if (n_dt == 0) return;
+    for (int i = blockIdx.x * PASS_THREADS + threadIdx.x; i < d.cap; i += gridDim.x * PASS_THREADS) {
+        unsigned char flags = d.ph.flags[i];
+        if ((flags & F_MOVABLE) && i != pushed) {
+            double p0 = d.ph.p0[i], p1 = d.ph.p1[i], p2 = d.ph.p2[i], p3 = d.ph.p3[i];
+            double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
+            double div = 1.0 / p0;
+            for (int k = 0; k < n_dt; ++k) {
+                double t = st.dt_list[k];
+                r0 += p1 * div * C_LIGHT * t;
+                r1 += p2 * div * C_LIGHT * t;
+                r2 += p3 * div * C_LIGHT * t;
+            }
+            d.ph.r0[i] = r0;
+            d.ph.r1[i] = r1;
+            d.ph.r2[i] = r2;
+        }
+    }
+}
+
+__global__ void clear_push_kernel(DevCtx d)
+{
+    d.st->n_dt = 0;
+    d.st->pushed_slot = -1;
+}
+
+__global__ void set_push_kernel(DevCtx d, double t)
+{
+    d.st->dt_list[0] = t;
+    d.st->n_dt = 1;
+    d.st->pushed_slot = -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: photon x cell containment scan.  Photons in registers (SCAN_P per thread), cells streamed
+// through a double-buffered shared-memory tile filled by TMA bulk copies.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int NDIM3>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(DevCtx d, int parity, int tiles_per_chunk, int count_override)
+{
+    const LoopState &st = *d.st;
+    if (loop_stopped(st)) return;
+    const int count = (count_override >= 0) ? count_override : st.reloc_count[parity];
+    const int pbase = blockIdx.x * (SCAN_THREADS * SCAN_P);
+    if (pbase >= count) return;
+
+    extern __shared__ __align__(128) unsigned char scan_smem[];
+    constexpr uint32_t BYTES_A = SCAN_TILE * sizeof(double4);
+    constexpr uint32_t BYTES_B = NDIM3 ? SCAN_TILE * sizeof(double2) : 0;
+    double4(*sA)[SCAN_TILE] = reinterpret_cast<double4(*)[SCAN_TILE]>(scan_smem);
+    double2(*sB)[SCAN_TILE] = reinterpret_cast<double2(*)[SCAN_TILE]>(scan_smem + 2 * BYTES_A);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(scan_smem + 2 * BYTES_A + 2 * BYTES_B);
+
+    const int ntiles_total = d.cells.n_padded / SCAN_TILE;
+    const int tile0 = blockIdx.y * tiles_per_chunk;
+    const int ntiles = min(tiles_per_chunk, ntiles_total - tile0);
+    if (ntiles <= 0) return;
+
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    double x0[SCAN_P], x1[SCAN_P], x2[SCAN_P];
+    int best[SCAN_P];
+#pragma unroll
+    for (int p = 0; p < SCAN_P; ++p) {
+        int j = pbase + p * SCAN_THREADS + threadIdx.x;
+        bool ok = j < count;
+        x0[p] = ok ? d.reloc_h0[j] : qnan;
+        x1[p] = ok ? d.reloc_h1[j] : qnan;
+        x2[p] = (ok && NDIM3) ? d.reloc_h2[j] : qnan;
+        best[p] = INT_MAX;
+    }
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar[0], BYTES_A + BYTES_B);
+        tma_bulk_g2s(&sA[0][0], d.cells.geoA + (size_t)tile0 * SCAN_TILE, BYTES_A, &bar[0]);
+        if (NDIM3) tma_bulk_g2s(&sB[0][0], d.cells.geoB + (size_t)tile0 * SCAN_TILE, BYTES_B, &bar[0]);
+    }
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t & 1;
+        if (threadIdx.x == 0 && t + 1 < ntiles) {
+            mbar_expect_tx(&bar[s ^ 1], BYTES_A + BYTES_B);
+            tma_bulk_g2s(&sA[s ^ 1][0], d.cells.geoA + (size_t)(tile0 + t + 1) * SCAN_TILE, BYTES_A, &bar[s ^ 1]);
+            if (NDIM3)
+                tma_bulk_g2s(&sB[s ^ 1][0], d.cells.geoB + (size_t)(tile0 + t + 1) * SCAN_TILE, BYTES_B, &bar[s ^ 1]);
+        }
+        mbar_wait(&bar[s], (uint32_t)((t >> 1) & 1));
+        const int cbase = (tile0 + t) * SCAN_TILE;
+#pragma unroll 4
+        for (int c = 0; c < SCAN_TILE; ++c) {
+            const double4 a = sA[s][c];
+            if (!NDIM3) {
+#pragma unroll
+                for (int p = 0; p < SCAN_P; ++p) {
+                    bool hit = (fabs(x0[p] - a.x) <= a.z) & (fabs(x1[p] - a.y) <= a.w);
+                    if (hit) best[p] = min(best[p], cbase + c);
+                }
+            } else {
+                const double2 b = sB[s][c];
+#pragma unroll
+                for (int p = 0; p < SCAN_P; ++p) {
+                    bool hit = (fabs(x0[p] - a.x) <= a.w) & (fabs(x1[p] - a.y) <= b.x) & (fabs(x2[p] - a.z) <= b.y);
+                    if (hit) best[p] = min(best[p], cbase + c);
+                }
+            }
+        }
+        __syncthreads(); // everyone is done with stage s before it is refilled at t+2
+    }
+#pragma unroll
+    for (int p = 0; p < SCAN_P; ++p) {
+        int j = pbase + p * SCAN_THREADS + threadIdx.x;
+        if (best[p] != INT_MAX && j < count) atomicMin(&d.reloc_best[j], best[p]);
+    }
+    if (threadIdx.x == 0 && blockIdx.y == 0) {
+        int nph = min(count - pbase, SCAN_THREADS * SCAN_P);
+        atomicAdd((unsigned long long *)&d.st->cell_evals, (unsigned long long)nph * (unsigned long long)d.cells.n);
+    }
+}
+
+// K1b: the same containment test, cell-parallel, for a short relocation list
+template <int NDIM3>
+__global__ void __launch_bounds__(256) scan_few_kernel(DevCtx d, int parity)
+{
+    const LoopState &st = *d.st;
+    if (loop_stopped(st)) return;
+    const int count = st.reloc_count[parity];
+    if (count == 0) return;
+    __shared__ double sx0[FEW_RMAX], sx1[FEW_RMAX], sx2[FEW_RMAX];
+    __shared__ int sbest[FEW_RMAX];
+    for (int base = 0; base < count; base += FEW_RMAX) {
+        const int r = min(FEW_RMAX, count - base);
+        __syncthreads();
+        for (int j = threadIdx.x; j < r; j += blockDim.x) {
+            sx0[j] = d.reloc_h0[base + j];
+            sx1[j] = d.reloc_h1[base + j];
+            sx2[j] = NDIM3 ? d.reloc_h2[base + j] : 0.0;
+            sbest[j] = INT_MAX;
+        }
+        __syncthreads();
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < d.cells.n; c += gridDim.x * blockDim.x) {
+            const double4 a = d.cells.geoA[c];
+            double2 b = make_double2(0, 0);
+            if (NDIM3) b = d.cells.geoB[c];
+            for (int j = 0; j < r; ++j) {
+                bool hit;
+                if (!NDIM3)
+                    hit = (fabs(sx0[j] - a.x) <= a.z) & (fabs(sx1[j] - a.y) <= a.w);
+                else
+                    hit = (fabs(sx0[j] - a.x) <= a.w) & (fabs(sx1[j] - a.y) <= b.x) & (fabs(sx2[j] - a.z) <= b.y);
+                if (hit) atomicMin(&sbest[j], c);
+            }
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < r; j += blockDim.x)
+            if (sbest[j] != INT_MAX) atomicMin(&d.reloc_best[base + j], sbest[j]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd((unsigned long long *)&d.st->cell_evals, (unsigned long long)count * (unsigned long long)d.cells.n);
+}
+
+// ------------------------------------------------------------------------------------------
+// finish: relocated photons get their new cell, comoving 4-momentum and optical depth
+// (Src/mclib.c:536-584); in the fused loop also their free-path draw
+// ------------------------------------------------------------------------------------------
+constexpr int FIN_THREADS = 128;
+
+template <bool FUSE_MFP>
+__global__ void __launch_bounds__(FIN_THREADS) finish_kernel(DevCtx d, int sw, int parity)
+{
+    const LoopState &st = *d.st;
+    if (loop_stopped(st)) return;
+    const int count = st.reloc_count[parity];
+    const unsigned long long iter = st.iter;
+    double best_t = DBL_MAX;
+    int best_i = INT_MAX;
+    int found = 0, missing = 0;
+    for (int j = blockIdx.x * FIN_THREADS + threadIdx.x; j < count; j += gridDim.x * FIN_THREADS) {
+        const int i = d.reloc_slot[j];
+        const int b = d.reloc_best[j];
+        double t = 1e12 / C_LIGHT;
+        if (b == INT_MAX) {
+            d.ph.idx[i] = -1; // Src/mclib.c:536, 581-584
+            missing++;
+        } else {
+            d.ph.idx[i] = b;
+            double p[4] = {d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i]};
+            double r0 = d.ph.r0[i], r1 = d.ph.r1[i];
+            CellState c = load_cell_state(d.cells, b);
+            double fb[3], pc[4];
+            fluid_beta_of(d, c, r0, r1, fb);
+            lorentz_boost(fb, p, pc, true);
+            d.ph.c0[i] = pc[0];
+            d.ph.c1[i] = pc[1];
+            d.ph.c2[i] = pc[2];
+            d.ph.c3[i] = pc[3];
+            int terr = 0;
+            double tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, p[1], p[2], p[3], pc[0], &terr);
+            if (terr) d.st->error = MCRAT_B200_ERR_TABLE;
+            d.ph.tau[i] = tau;
+            d.ph.flags[i] = d.ph.flags[i] & ~F_RECALC;
+            found++;
+            if (FUSE_MFP) {
+                double xi = philox_mfp_uniform(d.k0, d.k1, iter, (uint32_t)i);
+                t = free_path_time(tau, xi);
+            }
+        }
+        if (FUSE_MFP) {
+            d.ph.tts[i] = t;
+            if (lex_less(t, i, best_t, best_i)) {
+                best_t = t;
+                best_i = i;
+            }
+        }
+    }
+    if (found && sw == 0) atomicAdd((unsigned long long *)&d.st->reloc_total, (unsigned long long)found); // :608-611
+    if (missing) atomicAdd(&d.st->not_found, missing);
+    if (FUSE_MFP) {
+        block_argmin<FIN_THREADS>(best_t, best_i);
+        if (threadIdx.x == 0) {
+            d.bm_t[BLOCKMIN_CAP + blockIdx.x] = best_t;
+            d.bm_i[BLOCKMIN_CAP + blockIdx.x] = best_i;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// unfused calcMeanFreePath (step API and replay harness), Src/mclib.c:617-714
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mfp_count_kernel(DevCtx d)
+{
+    int i = blockIdx.x * 256 + threadIdx.x;
+    int in = (i < d.cap) && (d.ph.idx[i] != -1);
+    int c = __syncthreads_count(in);
+    if (threadIdx.x == 0) d.prefix_block[blockIdx.x] = c;
+}
+
+__global__ void mfp_scan_kernel(DevCtx d, int nblocks)
+{
+    // single thread: exclusive scan of per-block counts (replay harness only; small lists)
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int b = 0; b < nblocks; ++b) {
+            int c = d.prefix_block[b];
+            d.prefix_block[b] = (int)run;
+            run += (unsigned long long)c;
+        }
+        d.st->replay_base = d.st->replay_cursor;
+        d.st->replay_cursor += run;
+        if (d.st->replay_cursor > d.st->replay_n) d.st->error = MCRAT_B200_ERR_REPLAY;
+    }
+}
+
+__global__ void __launch_bounds__(256) mfp_kernel(DevCtx d)
+{
+    const LoopState &st = *d.st;
+    if (st.error != 0) return;
+    __shared__ int warp_off[8];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const bool valid = i < d.cap;
+    const int idx = valid ? d.ph.idx[i] : -1;
+    const bool in = valid && idx != -1;
+    double t = 1e12 / C_LIGHT;
+    // rank of this photon among the in-domain photons of the block (stream order = slot order)
+    unsigned ball = __ballot_sync(0xffffffffu, in);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) warp_off[w] = __popc(ball);
+    __syncthreads();
+    int off = 0;
+    for (int k = 0; k < w; ++k) off += warp_off[k];
+    off += __popc(ball & ((1u << lane) - 1u));
+    if (in) {
+        unsigned char flags = d.ph.flags[i];
+        double tau;
+        if (flags & F_RECALC) {
+            CellState c = load_cell_state(d.cells, idx);
+            int terr = 0;
+            tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, d.ph.r0[i], d.ph.r1[i], d.ph.p1[i], d.ph.p2[i],
+                                d.ph.p3[i], d.ph.c0[i], &terr);
+            if (terr) d.st->error = MCRAT_B200_ERR_TABLE;
+            d.ph.tau[i] = tau;
+            d.ph.flags[i] = flags & ~F_RECALC;
+        } else {
+            tau = d.ph.tau[i];
+        }
+        double xi;
+        if (d.replay)
+            xi = d.replay_buf[st.replay_base + (unsigned long long)d.prefix_block[blockIdx.x] + (unsigned long long)off];
+        else
+            xi = philox_mfp_uniform(d.k0, d.k1, st.iter, (uint32_t)i);
+        t = free_path_time(tau, xi);
+    }
+    int bi = valid ? i : INT_MAX;
+    double bt = valid ? t : DBL_MAX;
+    if (valid) d.ph.tts[i] = t;
+    block_argmin<256>(bt, bi);
+    if (threadIdx.x == 0) {
+        d.bm_t[blockIdx.x % BLOCKMIN_CAP] = bt; // (callers keep nblocks <= BLOCKMIN_CAP or reduce in rounds)
+        d.bm_i[blockIdx.x % BLOCKMIN_CAP] = bi;
+    }
+}
+
+// head of the time-ordered list for lists with more than BLOCKMIN_CAP*256 slots in the unfused path
+__global__ void __launch_bounds__(256) argmin_all_kernel(DevCtx d)
+{
+    double bt = DBL_MAX;
+    int bi = INT_MAX;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < d.cap; i += gridDim.x * 256) {
+        double t = d.ph.tts[i];
+        if (lex_less(t, i, bt, bi)) {
+            bt = t;
+            bi = i;
+        }
+    }
+    block_argmin<256>(bt, bi);
+    if (threadIdx.x == 0) {
+        d.bm_t[blockIdx.x] = bt;
+        d.bm_i[blockIdx.x] = bi;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: event kernel -- global arg-min, then photonEvent (Src/mclib.c:1107-1356) and the driver's
+// bookkeeping (Src/mcrat.c:777-846).  One block; lane 0 runs the serial scatter.
+// ------------------------------------------------------------------------------------------
+constexpr int EVT_THREADS = 256;
+
+struct EventShared {
+    double cand_t;
+    int cand_i;
+    int need_next;
+    int finished;
+};
+
+__device__ void scatter_candidate(DevCtx &d, LoopState &st, EventRng &rng, int i, int n_dt, bool &event_did_occur)
+{
+    // the candidate's own position after every push of this event so far (Src/mclib.c:1138)
+    const unsigned char flags = d.ph.flags[i];
+    double p[4] = {d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i]};
+    double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
+    if (flags & F_MOVABLE) {
+        double div = 1.0 / p[0];
+        for (int k = 0; k < n_dt; ++k) {
+            double t = st.dt_list[k];
+            r0 += p[1] * div * C_LIGHT * t;
+            r1 += p[2] * div * C_LIGHT * t;
+            r2 += p[3] * div * C_LIGHT * t;
+        }
+    }
+    const int index = d.ph.idx[i];
+    CellState c = load_cell_state(d.cells, index);
+    double fb[3];
+    fluid_beta_of(d, c, r0, r1, fb); // ph_phi = atan2(r1, r0), Src/mclib.c:1151-1174
+    double pc[4] = {d.ph.c0[i], d.ph.c1[i], d.ph.c2[i], d.ph.c3[i]};
+    double s[4] = {d.ph.s0[i], d.ph.s1[i], d.ph.s2[i], d.ph.s3[i]};
+    if (d.stokes) stokes_rotation(fb, p + 1, pc + 1, s);
+    double el[4];
+    single_thermal_electron(el, c.temp, pc, rng);
+    int occurred = single_scatter(d.stokes, el, pc, s, rng);
+    if (occurred == 1) {
+        double nfb[3] = {-1 * fb[0], -1 * fb[1], -1 * fb[2]};
+        lorentz_boost(nfb, pc, p, true);
+        if (d.stokes) {
+            stokes_rotation(nfb, pc + 1, p + 1, s);
+            d.ph.s0[i] = s[0];
+            d.ph.s1[i] = s[1];
+            d.ph.s2[i] = s[2];
+            d.ph.s3[i] = s[3];
+        }
+        d.ph.p0[i] = p[0]; d.ph.p1[i] = p[1]; d.ph.p2[i] = p[2]; d.ph.p3[i] = p[3];
+        d.ph.c0[i] = pc[0]; d.ph.c1[i] = pc[1]; d.ph.c2[i] = pc[2]; d.ph.c3[i] = pc[3];
+        d.ph.nscatt[i] = d.ph.nscatt[i] + 1;
+        d.ph.flags[i] = flags | F_RECALC;
+        // this photon is already at its pushed position: the next pass must not push it again
+        d.ph.r0[i] = r0;
+        d.ph.r1[i] = r1;
+        d.ph.r2[i] = r2;
+        st.pushed_slot = i;
+        st.scatt_cnt += 1;
+        event_did_occur = true;
+    }
+}
+
+// step_mode 0: frame loop (driver bookkeeping included); 1: photonEvent only (dt_max given)
+__global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int nb_pass, int nb_fin, int step_mode,
+                                                            double dt_max_arg)
+{
+    LoopState &st = *d.st;
+    if (loop_stopped(st)) return;
+
+    __shared__ EventShared sh;
+    // ---- head of the time order: reduce the per-block minima ----
+    double bt = DBL_MAX;
+    int bi = INT_MAX;
+    for (int k = threadIdx.x; k < nb_pass; k += EVT_THREADS)
+        if (lex_less(d.bm_t[k], d.bm_i[k], bt, bi)) {
+            bt = d.bm_t[k];
+            bi = d.bm_i[k];
+        }
+    for (int k = threadIdx.x; k < nb_fin; k += EVT_THREADS)
+        if (lex_less(d.bm_t[BLOCKMIN_CAP + k], d.bm_i[BLOCKMIN_CAP + k], bt, bi)) {
+            bt = d.bm_t[BLOCKMIN_CAP + k];
+            bi = d.bm_i[BLOCKMIN_CAP + k];
+        }
+    block_argmin<EVT_THREADS>(bt, bi);
+
+    __shared__ EventRng rng_sh;
+    __shared__ double old_scatt_time, scatt_time, dt_max;
+    __shared__ int n_dt, ph_index;
+    if (threadIdx.x == 0) {
+        sh.cand_t = bt;
+        sh.cand_i = bi;
+        sh.finished = 0;
+        sh.need_next = 0;
+        st.head_idx = bi;
+        st.head_tts = bt;
+        dt_max = (step_mode == 0) ? st.remaining_time : dt_max_arg;
+        old_scatt_time = 0;
+        scatt_time = 0;
+        n_dt = 0;
+        ph_index = bi;
+        st.n_dt = 0;
+        st.pushed_slot = -1;
+        rng_sh.replay = d.replay;
+        rng_sh.k0 = d.k0;
+        rng_sh.k1 = d.k1;
+        rng_sh.iter = st.iter;
+        rng_sh.draw = 0;
+        rng_sh.buf = d.replay_buf;
+        rng_sh.pos = st.replay_cursor;
+        rng_sh.n = st.replay_n;
+        rng_sh.exhausted = 0;
+        if (step_mode == 0) st.slots += d.cap;
+        if (step_mode == 0 && !(bt < dt_max)) {
+            // Src/mcrat.c:834-846: nothing scatters before the next hydro frame
+            st.time_now += st.remaining_time;
+            st.dt_list[0] = st.remaining_time;
+            st.n_dt = 1;
+            st.last_time_step = st.remaining_time;
+            st.remaining_time = 0;
+            st.done = 1;
+            st.iter += 1;
+            st.iters_done += 1;
+            sh.finished = 1;
+        }
+    }
+    __syncthreads();
+    if (sh.finished) return;
+
+    // ---- photonEvent: walk candidates in ascending time, Src/mclib.c:1128-1339 ----
+    while (true) {
+        if (threadIdx.x == 0) {
+            const int i = sh.cand_i;
+            const double t = sh.cand_t;
+            bool event = false;
+            ph_index = i;
+            scatt_time = t;
+            if (t < dt_max) {
+                if (n_dt < MAX_DT) {
+                    st.dt_list[n_dt] = t - old_scatt_time;
+                    n_dt++;
+                } else {
+                    st.error = MCRAT_B200_ERR_STATE;
+                    event = true;
+                }
+                if (!event) {
+                    EventRng rng = rng_sh;
+                    scatter_candidate(d, st, rng, i, n_dt, event);
+                    rng_sh = rng;
+                }
+            } else {
+                scatt_time = dt_max;
+                st.dt_list[n_dt < MAX_DT ? n_dt : MAX_DT - 1] = scatt_time - old_scatt_time;
+                n_dt = min(n_dt + 1, MAX_DT);
+                event = true;
+            }
+            old_scatt_time = scatt_time;
+            sh.need_next = event ? 0 : 1;
+            sh.finished = event ? 1 : 0;
+        }
+        __syncthreads();
+        if (sh.finished) break;
+        // Klein-Nishina rejection (rare): next entry of the time order after (cand_t, cand_i)
+        {
+            const double pt = sh.cand_t;
+            const int pi = sh.cand_i;
+            double nt = DBL_MAX;
+            int ni = INT_MAX;
+            for (int k = threadIdx.x; k < d.cap; k += EVT_THREADS) {
+                double t = d.ph.tts[k];
+                if (lex_less(pt, pi, t, k) && lex_less(t, k, nt, ni)) {
+                    nt = t;
+                    ni = k;
+                }
+            }
+            block_argmin<EVT_THREADS>(nt, ni);
+            if (threadIdx.x == 0) {
+                if (ni == INT_MAX) { // list exhausted (Src/mclib.c:1128 loop bound)
+                    sh.finished = 1;
+                } else {
+                    sh.cand_t = nt;
+                    sh.cand_i = ni;
+                }
+            }
+            __syncthreads();
+            if (sh.finished) break;
+        }
+    }
+
+    if (threadIdx.x == 0) {
+        st.n_dt = n_dt;
+        st.last_scattered_idx = ph_index;
+        st.last_time_step = scatt_time;
+        if (d.replay) {
+            st.replay_cursor = rng_sh.pos;
+            if (rng_sh.exhausted) st.error = MCRAT_B200_ERR_REPLAY;
+        }
+        if (step_mode == 0) {
+            st.time_now += scatt_time;
+            st.remaining_time -= scatt_time;
+            if (!(st.remaining_time > 0)) st.done = 1;
+            if (d.cs && d.ph.type[ph_index] == 'p') { // Src/mcrat.c:792-807: host replenishes the pool
+                d.ph.type[ph_index] = 'k';
+                if (d.ph.weight[ph_index] != 0) d.ph.flags[ph_index] |= F_MOVABLE;
+                st.pause_cs = 1;
+            }
+        }
+        st.iter += 1;
+        st.iters_done += 1;
+    }
+}
+
+// head of the time order only (step API calcMeanFreePath)
+__global__ void __launch_bounds__(EVT_THREADS) head_kernel(DevCtx d, int nb)
+{
+    double bt = DBL_MAX;
+    int bi = INT_MAX;
+    for (int k = threadIdx.x; k < nb; k += EVT_THREADS)
+        if (lex_less(d.bm_t[k], d.bm_i[k], bt, bi)) {
+            bt = d.bm_t[k];
+            bi = d.bm_i[k];
+        }
+    block_argmin<EVT_THREADS>(bt, bi);
+    if (threadIdx.x == 0) {
+        d.st->head_idx = bi;
+        d.st->head_tts = bt;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: phAbsCyclosynch, Src/mc_cyclosynch.c:1571-1644
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cs_absorb_kernel(DevCtx d)
+{
+    int abs_cnt = 0, scatt_cnt = 0;
+    double abs_w = 0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < d.cap; i += gridDim.x * 256) {
+        const double w = d.ph.weight[i];
+        const int idx = d.ph.idx[i];
+        if ((w != 0) && (idx != -1)) {
+            double b;
+            if (d.b_calc == B_TOTAL_E || d.b_calc == B_INTERNAL_E) {
+                double el_dens = d.cells.dens[idx] / M_P;
+                b = calc_b(d.b_calc, d.epsilon_b, el_dens, d.cells.temp[idx]);
+            } else if (d.dims == D_TWO) {
+                double b0 = d.cells.B0[idx], b1 = d.cells.B1[idx];
+                b = sqrt(b0 * b0 + b1 * b1);
+            } else {
+                double b0 = d.cells.B0[idx], b1 = d.cells.B1[idx], b2 = d.cells.B2[idx];
+                b = sqrt(b0 * b0 + b1 * b1 + b2 * b2);
+            }
+            const double nu_c = calc_cyclotron_freq(b);
+            const char type = d.ph.type[i];
+            if ((d.ph.c0[i] * C_LIGHT / PL_CONST <= nu_c) || (type == 'p')) {
+                abs_cnt++;
+                if (!((type != 'i') && (type != 'c'))) abs_w += w;
+                // setNullPhoton, Src/photons.c:208-251
+                d.ph.type[i] = 'N';
+                d.ph.weight[i] = 0;
+                d.ph.idx[i] = -1;
+                d.ph.flags[i] = 0;
+                d.ph.p0[i] = 0; d.ph.p1[i] = 0; d.ph.p2[i] = 0; d.ph.p3[i] = 0;
+                d.ph.c0[i] = 0; d.ph.c1[i] = 0; d.ph.c2[i] = 0; d.ph.c3[i] = 0;
+                d.ph.r0[i] = 0; d.ph.r1[i] = 0; d.ph.r2[i] = 0;
+                d.ph.s0[i] = 0; d.ph.s1[i] = 0; d.ph.s2[i] = 0; d.ph.s3[i] = 0;
+                d.ph.nscatt[i] = 0;
+                d.ph.tau[i] = 0;
+            } else if ((type == 'k') || (type == 'c')) {
+                scatt_cnt++;
+            }
+        }
+    }
+    // block reduction, then one atomic per block
+    __shared__ int s_abs[8], s_sc[8];
+    __shared__ double s_w[8];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        abs_cnt += __shfl_xor_sync(0xffffffffu, abs_cnt, off);
+        scatt_cnt += __shfl_xor_sync(0xffffffffu, scatt_cnt, off);
+        abs_w += __shfl_xor_sync(0xffffffffu, abs_w, off);
+    }
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_abs[wp] = abs_cnt;
+        s_sc[wp] = scatt_cnt;
+        s_w[wp] = abs_w;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int a = 0, s = 0;
+        double w = 0;
+        for (int k = 0; k < 8; ++k) {
+            a += s_abs[k];
+            s += s_sc[k];
+            w += s_w[k];
+        }
+        if (a) atomicAdd(&d.st->abs_count, a);
+        if (s) atomicAdd(&d.st->cs_scatt_count, s);
+        if (w != 0) atomicAdd(&d.st->abs_weight, w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// photon statistics (Src/mclib.c:1358-1515): per-block partials, finished on the host
+// ------------------------------------------------------------------------------------------
+struct StatPartial {
+    double e_sum, w_sum, ns_sum, r_sum, r_min, r_max, th_min, th_max;
+    long long count;
+    int ns_max, ns_min;
+};
+
+__global__ void __launch_bounds__(256) stats_kernel(DevCtx d, StatPartial *out)
+{
+    StatPartial a;
+    a.e_sum = a.w_sum = a.ns_sum = a.r_sum = 0;
+    a.r_min = DBL_MAX; a.r_max = 0; a.th_min = DBL_MAX; a.th_max = 0;
+    a.count = 0; a.ns_max = 0; a.ns_min = INT_MAX;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < d.cap; i += gridDim.x * 256) {
+        const double w = d.ph.weight[i];
+        const bool live = (w != 0);
+        if (!d.cs || live) { // Src/mclib.c:1373-1379, 1401-1404
+            a.e_sum += d.ph.p0[i] * w;
+            a.w_sum += w;
+            double ns = d.ph.nscatt[i];
+            double r = sqrt(d.ph.r0[i] * d.ph.r0[i] + d.ph.r1[i] * d.ph.r1[i] + d.ph.r2[i] * d.ph.r2[i]);
+            a.ns_sum += ns;
+            a.r_sum += r;
+            if (ns > a.ns_max) a.ns_max = (int)ns;
+            if (ns < a.ns_min) a.ns_min = (int)ns;
+            a.count++;
+        }
+        if (live) { // Src/mclib.c:1479-1508
+            double r = sqrt(d.ph.r0[i] * d.ph.r0[i] + d.ph.r1[i] * d.ph.r1[i] + d.ph.r2[i] * d.ph.r2[i]);
+            double th = acos(d.ph.r2[i] / r);
+            if (r > a.r_max) a.r_max = r;
+            if (r < a.r_min) a.r_min = r;
+            if (th > a.th_max) a.th_max = th;
+            if (th < a.th_min) a.th_min = th;
+        }
+    }
+    __shared__ StatPartial sh[256];
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            StatPartial &x = sh[threadIdx.x];
+            const StatPartial &y = sh[threadIdx.x + s];
+            x.e_sum += y.e_sum; x.w_sum += y.w_sum; x.ns_sum += y.ns_sum; x.r_sum += y.r_sum;
+            x.r_min = fmin(x.r_min, y.r_min); x.r_max = fmax(x.r_max, y.r_max);
+            x.th_min = fmin(x.th_min, y.th_min); x.th_max = fmax(x.th_max, y.th_max);
+            x.count += y.count;
+            x.ns_max = max(x.ns_max, y.ns_max); x.ns_min = min(x.ns_min, y.ns_min);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// peak probes (roofline denominators measured on the same GPU, same run)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double seed)
+{
+    // the scan's instruction mix: one DADD + one DSETP per dimension; 8 independent chains
+    double x[8], c = seed + threadIdx.x * 1e-9, h = 0.25;
+    int hits = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = seed * (k + 1);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            double dd = x[k] - c;
+            hits += (fabs(dd) <= h) ? 1 : 0;
+            x[k] = dd;
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += x[k];
+    if (hits == -1 || s == 12345.678) out[0] = s + hits;
+}
+
+__global__ void __launch_bounds__(256) copy_kernel(const double4 *__restrict__ a, double4 *__restrict__ b, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_create_error;
+
+struct mcrat_b200_ctx {
+    mcrat_b200_config cfg;
+    DevCtx d;
+    cudaStream_t stream;
+    bool own_stream;
+    int num_sms;
+    std::string err;
+    // device allocations
+    std::vector<void *> ph_allocs, cell_allocs, misc_allocs;
+    mcrat_photon *aos_dev;
+    size_t aos_cap;
+    int ph_cap_alloc;
+    bool have_hydro, have_photons;
+    int pass_parity;
+    int last_nb_mfp;
+    LoopState *st_host; // pinned
+    double *replay_dev;
+    size_t replay_cap;
+    double *table_dev;
+    StatPartial *stat_dev;
+    // profiling
+    cudaEvent_t ev0, ev1;
+    mcrat_b200_kernel_times times;
+};
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                          \
+            return MCRAT_B200_ERR_CUDA;                                                              \
+        }                                                                                            \
+    } while (0)
+
+static int fail(mcrat_b200_ctx *ctx, int code, const char *msg)
+{
+    ctx->err = msg;
+    return code;
+}
+
+template <typename T>
+static cudaError_t dev_alloc(std::vector<void *> &pool, T **p, size_t n)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (n ? n : 1) * sizeof(T));
+    if (e == cudaSuccess) {
+        pool.push_back(q);
+        *p = (T *)q;
+    }
+    return e;
+}
+
+static void free_pool(std::vector<void *> &pool)
+{
+    for (void *p : pool) cudaFree(p);
+    pool.clear();
+}
+
+enum { KC_SCAN = 0, KC_PASS = 1, KC_EVENT = 2, KC_OTHER = 3 };
+
+struct Timed {
+    mcrat_b200_ctx *ctx;
+    int cls;
+    bool on;
+    Timed(mcrat_b200_ctx *c, int k) : ctx(c), cls(k), on(c->cfg.profile != 0)
+    {
+        if (on) cudaEventRecord(ctx->ev0, ctx->stream);
+    }
+    ~Timed()
+    {
+        if (!on) return;
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaEventSynchronize(ctx->ev1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        mcrat_b200_kernel_times &t = ctx->times;
+        if (cls == KC_SCAN) { t.scan_ms += ms; t.scan_launches++; }
+        else if (cls == KC_PASS) { t.pass_ms += ms; t.pass_launches++; }
+        else if (cls == KC_EVENT) { t.event_ms += ms; t.event_launches++; }
+        else { t.other_ms += ms; t.other_launches++; }
+    }
+};
+
+API int mcrat_b200_abi_version(void) { return MCRAT_B200_ABI_VERSION; }
+
+API int mcrat_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+API const char *mcrat_b200_last_error(const mcrat_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
+{
+    if (!cfg || !out) {
+        g_create_error = "null argument";
+        return MCRAT_B200_ERR_ARG;
+    }
+    if (cfg->abi_version != MCRAT_B200_ABI_VERSION) {
+        g_create_error = "ABI version mismatch";
+        return MCRAT_B200_ERR_ARG;
+    }
+    if (cfg->dimensions < 0 || cfg->dimensions > 2 || cfg->geometry < 0 || cfg->geometry > 3) {
+        g_create_error = "bad DIMENSIONS / GEOMETRY";
+        return MCRAT_B200_ERR_ARG;
+    }
+    // the combinations the reference supports, Src/geometry.c:20-58
+    if (cfg->dimensions != MCRAT_THREE && cfg->geometry == MCRAT_POLAR) {
+        g_create_error = "POLAR geometry exists only in 3-D";
+        return MCRAT_B200_ERR_ARG;
+    }
+    if (cfg->dimensions == MCRAT_THREE && cfg->geometry == MCRAT_CYLINDRICAL) {
+        g_create_error = "CYLINDRICAL geometry exists only in 2-D / 2.5-D";
+        return MCRAT_B200_ERR_ARG;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)";
+        return MCRAT_B200_ERR_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) {
+        g_create_error = "device ordinal out of range";
+        return MCRAT_B200_ERR_ARG;
+    }
+    mcrat_b200_ctx *ctx = new mcrat_b200_ctx();
+    ctx->cfg = *cfg;
+    memset(&ctx->d, 0, sizeof(ctx->d));
+    memset(&ctx->times, 0, sizeof(ctx->times));
+    ctx->aos_dev = nullptr;
+    ctx->aos_cap = 0;
+    ctx->ph_cap_alloc = 0;
+    ctx->have_hydro = ctx->have_photons = false;
+    ctx->pass_parity = 0;
+    ctx->last_nb_mfp = 0;
+    ctx->replay_dev = nullptr;
+    ctx->replay_cap = 0;
+    ctx->table_dev = nullptr;
+    ctx->stat_dev = nullptr;
+    auto bail = [&](cudaError_t err, const char *what) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        delete ctx;
+        return MCRAT_B200_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cfg->stream) {
+        ctx->stream = (cudaStream_t)cfg->stream;
+        ctx->own_stream = false;
+    } else {
+        if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+        ctx->own_stream = true;
+    }
+    if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaMallocHost((void **)&ctx->st_host, sizeof(LoopState))) != cudaSuccess) return bail(e, "cudaMallocHost");
+    DevCtx &d = ctx->d;
+    d.dims = cfg->dimensions;
+    d.geom = cfg->geometry;
+    d.stokes = cfg->stokes_switch ? 1 : 0;
+    d.tau_calc = cfg->tau_calculation == MCRAT_TABLE ? TAU_TABLE : TAU_DIRECT;
+    d.cs = cfg->cyclosynch_switch ? 1 : 0;
+    d.b_calc = cfg->b_field_calc;
+    d.epsilon_b = cfg->epsilon_b;
+    d.k0 = (uint32_t)cfg->seed ^ 0x4D435261u;
+    d.k1 = (uint32_t)(cfg->seed >> 32) ^ cfg->shard;
+    d.replay = cfg->rng_mode == MCRAT_RNG_REPLAY ? 1 : 0;
+    if ((e = dev_alloc(ctx->misc_allocs, &d.st, 1)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMemsetAsync(d.st, 0, sizeof(LoopState), ctx->stream)) != cudaSuccess) return bail(e, "cudaMemset");
+    if ((e = dev_alloc(ctx->misc_allocs, &d.bm_t, 2 * BLOCKMIN_CAP)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = dev_alloc(ctx->misc_allocs, &d.bm_i, 2 * BLOCKMIN_CAP)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = dev_alloc(ctx->misc_allocs, &ctx->stat_dev, 1024)) != cudaSuccess) return bail(e, "cudaMalloc");
+    // interpolation grids, Src/hot_x_section.c:470-480
+    {
+        std::vector<double> grids(N_PH_E + 1 + N_T + 1);
+        double dt = (LOG_T_MAX - LOG_T_MIN) / N_T, dph_e = (LOG_PH_E_MAX - LOG_PH_E_MIN) / N_PH_E;
+        for (int i = 0; i <= N_PH_E; i++) grids[i] = LOG_PH_E_MIN + i * dph_e;
+        for (int i = 0; i <= N_T; i++) grids[N_PH_E + 1 + i] = LOG_T_MIN + i * dt;
+        double *g = nullptr;
+        if ((e = dev_alloc(ctx->misc_allocs, &g, grids.size() + (size_t)(N_PH_E + 1) * (N_T + 1))) != cudaSuccess)
+            return bail(e, "cudaMalloc");
+        if ((e = cudaMemcpyAsync(g, grids.data(), grids.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+            return bail(e, "cudaMemcpy");
+        if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail(e, "cudaStreamSynchronize");
+        d.table.xa = g;
+        d.table.ya = g + N_PH_E + 1;
+        d.table.za = g + N_PH_E + 1 + N_T + 1;
+        ctx->table_dev = g + N_PH_E + 1 + N_T + 1;
+    }
+    if ((e = cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(2 * SCAN_TILE * sizeof(double4) + 16))) != cudaSuccess)
+        return bail(e, "cudaFuncSetAttribute");
+    if ((e = cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(2 * SCAN_TILE * (sizeof(double4) + sizeof(double2)) + 16))) != cudaSuccess)
+        return bail(e, "cudaFuncSetAttribute");
+    *out = ctx;
+    return MCRAT_B200_OK;
+}
+
+API void mcrat_b200_destroy(mcrat_b200_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaStreamSynchronize(ctx->stream);
+    free_pool(ctx->ph_allocs);
+    free_pool(ctx->cell_allocs);
+    free_pool(ctx->misc_allocs);
+    if (ctx->aos_dev) cudaFree(ctx->aos_dev);
+    if (ctx->replay_dev) cudaFree(ctx->replay_dev);
+    if (ctx->st_host) cudaFreeHost(ctx->st_host);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+API int mcrat_b200_synchronize(mcrat_b200_ctx *ctx)
+{
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MCRAT_B200_OK;
+}
+
+static int fetch_state(mcrat_b200_ctx *ctx)
+{
+    CK(cudaMemcpyAsync(ctx->st_host, ctx->d.st, sizeof(LoopState), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MCRAT_B200_OK;
+}
+
+static int check_launch(mcrat_b200_ctx *ctx, const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+        return MCRAT_B200_ERR_CUDA;
+    }
+    return MCRAT_B200_OK;
+}
+
+static int grid_for(mcrat_b200_ctx *ctx, int n, int threads, int per_sm)
+{
+    int g = (n + threads - 1) / threads;
+    int cap = ctx->num_sms * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return g;
+}
+
+API int mcrat_b200_set_hydro(mcrat_b200_ctx *ctx, int n, const double *const *fields, const double *domains, double fps,
+                             int scatt_frame_number, int inj_frame_number)
+{
+    (void)fps; (void)scatt_frame_number; (void)inj_frame_number;
+    if (!ctx || !fields || !domains || n < 0) return ctx ? fail(ctx, MCRAT_B200_ERR_ARG, "set_hydro: bad argument") : MCRAT_B200_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_pool(ctx->cell_allocs);
+    CellCols &c = ctx->d.cells;
+    const int ndim3 = ctx->d.dims == D_THREE;
+    c.n = n;
+    c.n_padded = ((n + SCAN_TILE - 1) / SCAN_TILE) * SCAN_TILE;
+    if (c.n_padded == 0) c.n_padded = SCAN_TILE;
+    double *cols[19];
+    for (int f = 0; f < 19; ++f) {
+        CK(dev_alloc(ctx->cell_allocs, &cols[f], (size_t)n));
+        if (fields[f])
+            CK(cudaMemcpyAsync(cols[f], fields[f], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        else
+            CK(cudaMemsetAsync(cols[f], 0, (size_t)(n ? n : 1) * sizeof(double), ctx->stream));
+    }
+    c.r0 = cols[0]; c.r1 = cols[1]; c.r2 = cols[2];
+    c.v0 = cols[8]; c.v1 = cols[9]; c.v2 = cols[10];
+    c.dens = cols[11]; c.dens_lab = cols[12]; c.temp = cols[14]; c.gamma = cols[15];
+    c.B0 = cols[16]; c.B1 = cols[17]; c.B2 = cols[18];
+    double4 *geoA = nullptr;
+    double2 *geoB = nullptr;
+    CK(dev_alloc(ctx->cell_allocs, &geoA, (size_t)c.n_padded));
+    CK(dev_alloc(ctx->cell_allocs, &geoB, (size_t)(ndim3 ? c.n_padded : 1)));
+    build_geo_kernel<<<grid_for(ctx, c.n_padded, 256, 8), 256, 0, ctx->stream>>>(ndim3, n, c.n_padded, cols[0], cols[1], cols[2],
+                                                                               cols[3], cols[4], cols[5], geoA, geoB);
+    if (int rc = check_launch(ctx, "build_geo_kernel")) return rc;
+    c.geoA = geoA;
+    c.geoB = geoB;
+    for (int k = 0; k < 6; ++k) c.dom[k] = domains[k];
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_hydro = true;
+    return MCRAT_B200_OK;
+}
+
+API int mcrat_b200_set_thermal_table(mcrat_b200_ctx *ctx, const double *table)
+{
+    if (!ctx || !table) return ctx ? fail(ctx, MCRAT_B200_ERR_ARG, "set_thermal_table: null") : MCRAT_B200_ERR_ARG;
+    // za[j*(N_PH_E+1)+i] = thermal_table[i][j], Src/hot_x_section.c:482-488
+    std::vector<double> za((size_t)(N_PH_E + 1) * (N_T + 1));
+    for (int i = 0; i <= N_PH_E; i++)
+        for (int j = 0; j <= N_T; j++) za[(size_t)j * (N_PH_E + 1) + i] = table[(size_t)i * (N_T + 1) + j];
+    CK(cudaMemcpyAsync(ctx->table_dev, za.data(), za.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MCRAT_B200_OK;
+}
+
+static int ensure_photon_capacity(mcrat_b200_ctx *ctx, int n)
+{
+    if (n <= ctx->ph_cap_alloc) return MCRAT_B200_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_pool(ctx->ph_allocs);
+    int cap = n + n / 8 + 1024;
+    PhotonCols &p = ctx->d.ph;
+    double **cols[19] = {&p.r0, &p.r1, &p.r2, &p.p0, &p.p1, &p.p2, &p.p3, &p.c0, &p.c1, &p.c2,
+                         &p.c3, &p.s0, &p.s1, &p.s2, &p.s3, &p.nscatt, &p.weight, &p.tau, &p.tts};
+    for (int k = 0; k < 19; ++k) CK(dev_alloc(ctx->ph_allocs, cols[k], (size_t)cap));
+    CK(dev_alloc(ctx->ph_allocs, &p.idx, (size_t)cap));
+    CK(dev_alloc(ctx->ph_allocs, &p.flags, (size_t)cap));
+    CK(dev_alloc(ctx->ph_allocs, &p.type, (size_t)cap));
+    DevCtx &d = ctx->d;
+    d.reloc_cap = cap;
+    CK(dev_alloc(ctx->ph_allocs, &d.reloc_slot, (size_t)cap));
+    CK(dev_alloc(ctx->ph_allocs, &d.reloc_h0, (size_t)cap));
+    CK(dev_alloc(ctx->ph_allocs, &d.reloc_h1, (size_t)cap));
+    CK(dev_alloc(ctx->ph_allocs, &d.reloc_h2, (size_t)cap));
+    CK(dev_alloc(ctx->ph_allocs, &d.reloc_best, (size_t)cap));
+    CK(dev_alloc(ctx->ph_allocs, &d.prefix_block, (size_t)(cap / 256 + 2)));
+    if (ctx->aos_dev) cudaFree(ctx->aos_dev);
+    CK(cudaMalloc((void **)&ctx->aos_dev, (size_t)cap * sizeof(mcrat_photon)));
+    ctx->aos_cap = cap;
+    ctx->ph_cap_alloc = cap;
+    return MCRAT_B200_OK;
+}
+
+API int mcrat_b200_set_photons(mcrat_b200_ctx *ctx, const mcrat_photon *photons, int n)
+{
+    if (!ctx || n < 0 || (n > 0 && !photons)) return ctx ? fail(ctx, MCRAT_B200_ERR_ARG, "set_photons: bad argument") : MCRAT_B200_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (int rc = ensure_photon_capacity(ctx, n)) return rc;
+    ctx->d.cap = n;
+    if (n > 0) {
+        CK(cudaMemcpyAsync(ctx->aos_dev, photons, (size_t)n * sizeof(mcrat_photon), cudaMemcpyHostToDevice, ctx->stream));
+        unpack_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->d, ctx->aos_dev, n);
+        if (int rc = check_launch(ctx, "unpack_kernel")) return rc;
+    }
+    clear_push_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d);
+    ctx->have_photons = true;
+    return MCRAT_B200_OK;
+}
+
+static int flush_pushes(mcrat_b200_ctx *ctx)
+{
+    if (ctx->d.cap > 0) {
+        flush_push_kernel<<<grid_for(ctx, ctx->d.cap, PASS_THREADS, 8), PASS_THREADS, 0, ctx->stream>>>(ctx->d);
+        if (int rc = check_launch(ctx, "flush_push_kernel")) return rc;
+    }
+    clear_push_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d);
+    return check_launch(ctx, "clear_push_kernel");
+}
+
+API int mcrat_b200_get_photons(mcrat_b200_ctx *ctx, mcrat_photon *photons, int n)
+{
+    if (!ctx || !photons || n < 0 || n > ctx->d.cap) return ctx ? fail(ctx, MCRAT_B200_ERR_ARG, "get_photons: bad argument") : MCRAT_B200_ERR_ARG;
+    if (int rc = flush_pushes(ctx)) return rc;
+    if (n > 0) {
+        pack_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->d, ctx->aos_dev, 0, n);
+        if (int rc = check_launch(ctx, "pack_kernel")) return rc;
+        CK(cudaMemcpyAsync(photons, ctx->aos_dev, (size_t)n * sizeof(mcrat_photon), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MCRAT_B200_OK;
+}
+
+API int mcrat_b200_get_photon(mcrat_b200_ctx *ctx, int index, mcrat_photon *out)
+{
+    if (!ctx || !out || index < 0 || index >= ctx->d.cap) return ctx ? fail(ctx, MCRAT_B200_ERR_ARG, "get_photon: bad index") : MCRAT_B200_ERR_ARG;
+    if (int rc = flush_pushes(ctx)) return rc;
+    pack_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d, ctx->aos_dev, index, 1);
+    if (int rc = check_launch(ctx, "pack_kernel")) return rc;
+    CK(cudaMemcpyAsync(out, ctx->aos_dev, sizeof(mcrat_photon), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MCRAT_B200_OK;
+}
+
+API int mcrat_b200_list_capacity(const mcrat_b200_ctx *ctx) { return ctx ? ctx->d.cap : 0; }
+
+API int mcrat_b200_set_replay_uniforms(mcrat_b200_ctx *ctx, const double *u, size_t n)
+{
+    if (!ctx || (!u && n)) return ctx ? fail(ctx, MCRAT_B200_ERR_ARG, "set_replay_uniforms: null") : MCRAT_B200_ERR_ARG;
+    if (!ctx->d.replay) return fail(ctx, MCRAT_B200_ERR_STATE, "context was not created with MCRAT_RNG_REPLAY");
+    // gsl_rng_uniform_pos redraws on an exact 0 (1 in 2^24 for ranlxs0), which would shift every
+    // later free-path draw; the harness must supply a zero-free stream
+    for (size_t i = 0; i < n; ++i)
+        if (u[i] == 0.0) return fail(ctx, MCRAT_B200_ERR_ARG, "replay stream contains an exact 0.0; pick another seed");
+    if (n > ctx->replay_cap) {
+        if (ctx->replay_dev) cudaFree(ctx->replay_dev);
+        CK(cudaMalloc((void **)&ctx->replay_dev, (n ? n : 1) * sizeof(double)));
+        ctx->replay_cap = n;
+    }
+    CK(cudaMemcpyAsync(ctx->replay_dev, u, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->d.replay_buf = ctx->replay_dev;
+    if (int rc = fetch_state(ctx)) return rc;
+    ctx->st_host->replay_cursor = 0;
+    ctx->st_host->replay_base = 0;
+    ctx->st_host->replay_n = n;
+    CK(cudaMemcpyAsync(ctx->d.st, ctx->st_host, sizeof(LoopState), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MCRAT_B200_OK;
+}
+
+API long long mcrat_b200_replay_consumed(mcrat_b200_ctx *ctx)
+{
+    if (!ctx) return -1;
+    if (fetch_state(ctx)) return -1;
+    return (long long)ctx->st_host->replay_cursor;
+}
+
+// ---- launch helpers ---------------------------------------------------------------------------
+static int need_ready(mcrat_b200_ctx *ctx)
+{
+    if (!ctx->have_hydro) return fail(ctx, MCRAT_B200_ERR_STATE, "no hydro frame loaded (mcrat_b200_set_hydro)");
+    if (!ctx->have_photons) return fail(ctx, MCRAT_B200_ERR_STATE, "no photon list loaded (mcrat_b200_set_photons)");
+    if (ctx->d.cells.n <= 0) return fail(ctx, MCRAT_B200_ERR_STATE, "hydro frame has no cells");
+    return MCRAT_B200_OK;
+}
+
+static size_t scan_smem_bytes(int ndim3)
+{
+    return 2 * SCAN_TILE * sizeof(double4) + (ndim3 ? 2 * SCAN_TILE * sizeof(double2) : 0) + 2 * sizeof(uint64_t);
+}
+
+static void scan_grid(mcrat_b200_ctx *ctx, int nphot, dim3 &grid, int &tiles_per_chunk)
+{
+    const int ntiles = ctx->d.cells.n_padded / SCAN_TILE;
+    int pchunks = (nphot + SCAN_THREADS * SCAN_P - 1) / (SCAN_THREADS * SCAN_P);
+    if (pchunks < 1) pchunks = 1;
+    // enough cell chunks that the grid is ~8 CTAs per SM, each with >= 4 tiles
+    int want = (ctx->num_sms * 8 + pchunks - 1) / pchunks;
+    int maxc = ntiles / 4;
+    if (maxc < 1) maxc = 1;
+    int cchunks = want < maxc ? want : maxc;
+    if (cchunks < 1) cchunks = 1;
+    if (cchunks > 65535) cchunks = 65535;
+    tiles_per_chunk = (ntiles + cchunks - 1) / cchunks;
+    cchunks = (ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
+    grid = dim3(pchunks, cchunks, 1);
+}
+
+// full scan of the current relocation list with K1 (count known only on the device: sized for cap)
+static int launch_scan_full(mcrat_b200_ctx *ctx, int parity, int nphot_bound, int count_override)
+{
+    dim3 grid;
+    int tpc;
+    scan_grid(ctx, nphot_bound, grid, tpc);
+    Timed t(ctx, KC_SCAN);
+    if (ctx->d.dims == D_THREE)
+        scan_kernel<1><<<grid, SCAN_THREADS, scan_smem_bytes(1), ctx->stream>>>(ctx->d, parity, tpc, count_override);
+    else
+        scan_kernel<0><<<grid, SCAN_THREADS, scan_smem_bytes(0), ctx->stream>>>(ctx->d, parity, tpc, count_override);
+    return check_launch(ctx, "scan_kernel");
+}
+
+static int launch_scan_few(mcrat_b200_ctx *ctx, int parity)
+{
+    int g = grid_for(ctx, ctx->d.cells.n, 256, 4);
+    Timed t(ctx, KC_SCAN);
+    if (ctx->d.dims == D_THREE)
+        scan_few_kernel<1><<<g, 256, 0, ctx->stream>>>(ctx->d, parity);
+    else
+        scan_few_kernel<0><<<g, 256, 0, ctx->stream>>>(ctx->d, parity);
+    return check_launch(ctx, "scan_few_kernel");
+}
+
+// one locate step: pass (+ optional fused free-path draw), scan, finish.  Returns block counts.
+template <bool FUSE>
+static int launch_locate(mcrat_b200_ctx *ctx, int sw, int &nb_pass, int &nb_fin)
+{
+    const int parity = ctx->pass_parity;
+    ctx->pass_parity ^= 1;
+    nb_pass = grid_for(ctx, ctx->d.cap, PASS_THREADS, 8);
+    {
+        Timed t(ctx, KC_PASS);
+        pass_kernel<FUSE><<<nb_pass, PASS_THREADS, 0, ctx->stream>>>(ctx->d, sw, parity);
+        if (int rc = check_launch(ctx, "pass_kernel")) return rc;
+    }
+    if (sw == 1) {
+        if (int rc = launch_scan_full(ctx, parity, ctx->d.cap, -1)) return rc;
+        nb_fin = grid_for(ctx, ctx->d.cap, FIN_THREADS, 8);
+    } else {
+        if (int rc = launch_scan_few(ctx, parity)) return rc;
+        nb_fin = 8;
+    }
+    {
+        Timed t(ctx, KC_OTHER);
+        finish_kernel<FUSE><<<nb_fin, FIN_THREADS, 0, ctx->stream>>>(ctx->d, sw, parity);
+        if (int rc = check_launch(ctx, "finish_kernel")) return rc;
+    }
+    return MCRAT_B200_OK;
+}
+
+static int launch_mfp_unfused(mcrat_b200_ctx *ctx, int &nb)
+{
+    const int nblocks = (ctx->d.cap + 255) / 256;
+    Timed t(ctx, KC_PASS);
+    if (ctx->d.replay) {
+        mfp_count_kernel<<<nblocks, 256, 0, ctx->stream>>>(ctx->d);
+        mfp_scan_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d, nblocks);
+    }
+    mfp_kernel<<<nblocks, 256, 0, ctx->stream>>>(ctx->d);
+    if (int rc = check_launch(ctx, "mfp_kernel")) return rc;
+    if (nblocks > BLOCKMIN_CAP) {
+        nb = grid_for(ctx, ctx->d.cap, 256, 8);
+        argmin_all_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d);
+        if (int rc = check_launch(ctx, "argmin_all_kernel")) return rc;
+    } else {
+        nb = nblocks;
+    }
+    return MCRAT_B200_OK;
+}
+
+static int device_error(mcrat_b200_ctx *ctx)
+{
+    int e = ctx->st_host->error;
+    if (e == MCRAT_B200_ERR_REPLAY) return fail(ctx, e, "replay uniform stream exhausted");
+    if (e == MCRAT_B200_ERR_TABLE)
+        return fail(ctx, e, "hot cross-section lookup outside the table (the reference would integrate by Monte Carlo here)");
+    if (e) return fail(ctx, e, "device-side error");
+    return MCRAT_B200_OK;
+}
+
+// ---- reference function surface ------------------------------------------------------------------
+API int mcrat_b200_find_containing_hydro_cell(mcrat_b200_ctx *ctx, int sw, int *num_relocated)
+{
+    if (!ctx) return MCRAT_B200_ERR_ARG;
+    if (int rc = need_ready(ctx)) return rc;
+    if (int rc = fetch_state(ctx)) return rc;
+    const long long before = ctx->st_host->reloc_total;
+    int nbp, nbf;
+    if (int rc = launch_locate<false>(ctx, sw ? 1 : 0, nbp, nbf)) return rc;
+    clear_push_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d); // the pass consumed the pending pushes
+    if (int rc = fetch_state(ctx)) return rc;
+    if (num_relocated) *num_relocated = (int)(ctx->st_host->reloc_total - before);
+    return device_error(ctx);
+}
+
+API int mcrat_b200_calc_mean_free_path(mcrat_b200_ctx *ctx, int *first_index, double *first_tts)
+{
+    if (!ctx) return MCRAT_B200_ERR_ARG;
+    if (int rc = need_ready(ctx)) return rc;
+    if (int rc = flush_pushes(ctx)) return rc;
+    int nb;
+    if (int rc = launch_mfp_unfused(ctx, nb)) return rc;
+    head_kernel<<<1, EVT_THREADS, 0, ctx->stream>>>(ctx->d, nb);
+    if (int rc = check_launch(ctx, "head_kernel")) return rc;
+    if (int rc = fetch_state(ctx)) return rc;
+    if (first_index) *first_index = ctx->st_host->head_idx;
+    if (first_tts) *first_tts = ctx->st_host->head_tts;
+    ctx->last_nb_mfp = nb; // block minima stay valid for a following photon_event
+    return device_error(ctx);
+}
+
+__global__ void reset_loop_kernel(DevCtx d, int set_times, double time_now, double remaining, long long max_iters)
+{
+    LoopState &st = *d.st;
+    st.done = 0;
+    st.pause_cs = 0;
+    st.iters_done = 0;
+    st.max_iters = max_iters;
+    if (set_times) {
+        st.time_now = time_now;
+        st.remaining_time = remaining;
+    }
+}
+
+static int reset_loop(mcrat_b200_ctx *ctx, int set_times, double time_now, double remaining, long long max_iters)
+{
+    reset_loop_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d, set_times, time_now, remaining, max_iters);
+    return check_launch(ctx, "reset_loop_kernel");
+}
+
+API int mcrat_b200_photon_event(mcrat_b200_ctx *ctx, double dt_max, double *time_step, int *scattered_ph_index,
+                                int *frame_scatt_cnt, int *frame_abs_cnt)
+{
+    (void)frame_abs_cnt; // the reference never touches it either (Src/mclib.c:1107-1356)
+    if (!ctx) return MCRAT_B200_ERR_ARG;
+    if (int rc = need_ready(ctx)) return rc;
+    if (ctx->last_nb_mfp <= 0) return fail(ctx, MCRAT_B200_ERR_STATE, "photon_event needs a preceding calc_mean_free_path");
+    if (int rc = reset_loop(ctx, 0, 0, 0, -1)) return rc;
+    if (int rc = fetch_state(ctx)) return rc;
+    const long long before = ctx->st_host->scatt_cnt;
+    {
+        Timed t(ctx, KC_EVENT);
+        event_kernel<<<1, EVT_THREADS, 0, ctx->stream>>>(ctx->d, ctx->last_nb_mfp, 0, 1, dt_max);
+        if (int rc = check_launch(ctx, "event_kernel")) return rc;
+    }
+    if (int rc = fetch_state(ctx)) return rc;
+    if (time_step) *time_step = ctx->st_host->last_time_step;
+    if (scattered_ph_index) *scattered_ph_index = ctx->st_host->last_scattered_idx;
+    if (frame_scatt_cnt) *frame_scatt_cnt += (int)(ctx->st_host->scatt_cnt - before);
+    ctx->last_nb_mfp = 0;
+    return device_error(ctx);
+}
+
+API int mcrat_b200_update_photon_position(mcrat_b200_ctx *ctx, double t)
+{
+    if (!ctx) return MCRAT_B200_ERR_ARG;
+    if (!ctx->have_photons) return fail(ctx, MCRAT_B200_ERR_STATE, "no photon list loaded");
+    if (int rc = flush_pushes(ctx)) return rc;
+    set_push_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d, t);
+    Timed tm(ctx, KC_PASS);
+    return flush_pushes(ctx);
+}
+
+__global__ void clear_abs_kernel(DevCtx d)
+{
+    d.st->abs_count = 0;
+    d.st->cs_scatt_count = 0;
+    d.st->abs_weight = 0;
+}
+
+API int mcrat_b200_ph_abs_cyclosynch(mcrat_b200_ctx *ctx, int *num_abs_ph, int *scatt_cyclosynch_num_ph, double *absorbed_weight)
+{
+    if (!ctx) return MCRAT_B200_ERR_ARG;
+    if (int rc = need_ready(ctx)) return rc;
+    if (int rc = flush_pushes(ctx)) return rc;
+    clear_abs_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d);
+    cs_absorb_kernel<<<grid_for(ctx, ctx->d.cap, 256, 8), 256, 0, ctx->stream>>>(ctx->d);
+    if (int rc = check_launch(ctx, "cs_absorb_kernel")) return rc;
+    if (int rc = fetch_state(ctx)) return rc;
+    if (num_abs_ph) *num_abs_ph = ctx->st_host->abs_count;
+    if (scatt_cyclosynch_num_ph) *scatt_cyclosynch_num_ph = ctx->st_host->cs_scatt_count;
+    if (absorbed_weight) *absorbed_weight = ctx->st_host->abs_weight;
+    return MCRAT_B200_OK;
+}
+
+static int run_stats(mcrat_b200_ctx *ctx, StatPartial &tot)
+{
+    if (!ctx->have_photons) return fail(ctx, MCRAT_B200_ERR_STATE, "no photon list loaded");
+    if (int rc = flush_pushes(ctx)) return rc;
+    int g = grid_for(ctx, ctx->d.cap, 256, 4);
+    if (g > 1024) g = 1024;
+    stats_kernel<<<g, 256, 0, ctx->stream>>>(ctx->d, ctx->stat_dev);
+    if (int rc = check_launch(ctx, "stats_kernel")) return rc;
+    std::vector<StatPartial> h(g);
+    CK(cudaMemcpyAsync(h.data(), ctx->stat_dev, g * sizeof(StatPartial), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    tot = h[0];
+    for (int k = 1; k < g; ++k) {
+        tot.e_sum += h[k].e_sum; tot.w_sum += h[k].w_sum; tot.ns_sum += h[k].ns_sum; tot.r_sum += h[k].r_sum;
+        tot.r_min = std::fmin(tot.r_min, h[k].r_min); tot.r_max = std::fmax(tot.r_max, h[k].r_max);
+        tot.th_min = std::fmin(tot.th_min, h[k].th_min); tot.th_max = std::fmax(tot.th_max, h[k].th_max);
+        tot.count += h[k].count;
+        tot.ns_max = h[k].ns_max > tot.ns_max ? h[k].ns_max : tot.ns_max;
+        tot.ns_min = h[k].ns_min < tot.ns_min ? h[k].ns_min : tot.ns_min;
+    }
+    return MCRAT_B200_OK;
+}
+
+API int mcrat_b200_ph_min_max(mcrat_b200_ctx *ctx, double *min_r, double *max_r, double *min_theta, double *max_theta)
+{
+    if (!ctx) return MCRAT_B200_ERR_ARG;
+    StatPartial t;
+    if (int rc = run_stats(ctx, t)) return rc;
+    if (min_r) *min_r = t.r_min;
+    if (max_r) *max_r = t.r_max;
+    if (min_theta) *min_theta = t.th_min;
+    if (max_theta) *max_theta = t.th_max;
+    return MCRAT_B200_OK;
+}
+
+API int mcrat_b200_ph_scatt_stats(mcrat_b200_ctx *ctx, int *max_scatt, int *min_scatt, double *avg_scatt, double *avg_r)
+{
+    if (!ctx) return MCRAT_B200_ERR_ARG;
+    StatPartial t;
+    if (int rc = run_stats(ctx, t)) return rc;
+    if (max_scatt) *max_scatt = t.ns_max;
+    if (min_scatt) *min_scatt = t.ns_min;
+    if (avg_scatt) *avg_scatt = t.ns_sum / (double)t.count;
+    if (avg_r) *avg_r = t.r_sum / (double)t.count;
+    return MCRAT_B200_OK;
+}
+
+API int mcrat_b200_average_photon_energy(mcrat_b200_ctx *ctx, double *avg_energy)
+{
+    if (!ctx) return MCRAT_B200_ERR_ARG;
+    StatPartial t;
+    if (int rc = run_stats(ctx, t)) return rc;
+    if (avg_energy) *avg_energy = (t.e_sum * 2.99792458e10) / t.w_sum;
+    return MCRAT_B200_OK;
+}
+
+// ---- the device-resident frame loop, Src/mcrat.c:761-851 ---------------------------------------------
+API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remaining_time, long long max_iters, int sw,
+                             mcrat_b200_frame_stats *stats)
+{
+    if (!ctx || !stats) return ctx ? fail(ctx, MCRAT_B200_ERR_ARG, "run_frame: null stats") : MCRAT_B200_ERR_ARG;
+    if (int rc = need_ready(ctx)) return rc;
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (int rc = fetch_state(ctx)) return rc;
+    const LoopState before = *ctx->st_host;
+    if (int rc = reset_loop(ctx, 1, time_now, remaining_time, max_iters)) return rc;
+    sw = sw ? 1 : 0;
+    const bool fused = !ctx->d.replay;
+    long long launched = 0;
+    // iterations are enqueued in batches; kernels past the stop condition return immediately
+    int batch = 1;
+    for (;;) {
+        for (int b = 0; b < batch; ++b) {
+            int nbp = 0, nbf = 0;
+            if (fused) {
+                if (int rc = launch_locate<true>(ctx, sw, nbp, nbf)) return rc;
+            } else {
+                if (int rc = launch_locate<false>(ctx, sw, nbp, nbf)) return rc;
+                if (int rc = launch_mfp_unfused(ctx, nbp)) return rc;
+                nbf = 0;
+            }
+            {
+                Timed t(ctx, KC_EVENT);
+                event_kernel<<<1, EVT_THREADS, 0, ctx->stream>>>(ctx->d, nbp, nbf, 0, 0.0);
+                if (int rc = check_launch(ctx, "event_kernel")) return rc;
+            }
+            sw = 0; // Src/mcrat.c:773
+            launched++;
+        }
+        if (int rc = fetch_state(ctx)) return rc;
+        const LoopState &s = *ctx->st_host;
+        if (s.done || s.pause_cs || s.error || (max_iters >= 0 && s.iters_done >= max_iters)) break;
+        if (batch < 64) batch *= 2;
+        if (max_iters >= 0 && s.iters_done + batch > max_iters) batch = (int)(max_iters - s.iters_done);
+        if (batch < 1) batch = 1;
+    }
+    const LoopState &s = *ctx->st_host;
+    stats->iterations = s.iters_done;
+    stats->scatterings = s.scatt_cnt - before.scatt_cnt;
+    stats->relocations = s.reloc_total - before.reloc_total;
+    stats->photon_slots = s.slots - before.slots;
+    stats->cell_evals = s.cell_evals - before.cell_evals;
+    stats->time_now = s.time_now;
+    stats->last_time_step = s.last_time_step;
+    stats->last_scattered_index = s.last_scattered_idx;
+    stats->not_found = s.not_found - before.not_found;
+    stats->cs_host_pending = s.pause_cs;
+    stats->error = s.error;
+    ctx->last_nb_mfp = 0;
+    return device_error(ctx);
+}
+
+// ---- measurement -------------------------------------------------------------------------------------
+API int mcrat_b200_get_kernel_times(mcrat_b200_ctx *ctx, mcrat_b200_kernel_times *out, int reset)
+{
+    if (!ctx || !out) return MCRAT_B200_ERR_ARG;
+    *out = ctx->times;
+    if (reset) memset(&ctx->times, 0, sizeof(ctx->times));
+    return MCRAT_B200_OK;
+}
+
+API int mcrat_b200_rescan_all(mcrat_b200_ctx *ctx, long long *cell_evals, float *elapsed_ms)
+{
+    if (!ctx) return MCRAT_B200_ERR_ARG;
+    if (int rc = need_ready(ctx)) return rc;
+    if (int rc = flush_pushes(ctx)) return rc;
+    if (int rc = reset_loop(ctx, 0, 0, 0, -1)) return rc;
+    if (int rc = fetch_state(ctx)) return rc;
+    const long long before = ctx->st_host->cell_evals;
+    const int parity = ctx->pass_parity;
+    ctx->pass_parity ^= 1;
+    const int nbp = grid_for(ctx, ctx->d.cap, PASS_THREADS, 8);
+    pass_kernel<false><<<nbp, PASS_THREADS, 0, ctx->stream>>>(ctx->d, 1, parity);
+    if (int rc = check_launch(ctx, "pass_kernel")) return rc;
+    dim3 grid;
+    int tpc;
+    scan_grid(ctx, ctx->d.cap, grid, tpc);
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (ctx->d.dims == D_THREE)
+        scan_kernel<1><<<grid, SCAN_THREADS, scan_smem_bytes(1), ctx->stream>>>(ctx->d, parity, tpc, -1);
+    else
+        scan_kernel<0><<<grid, SCAN_THREADS, scan_smem_bytes(0), ctx->stream>>>(ctx->d, parity, tpc, -1);
+    if (int rc = check_launch(ctx, "scan_kernel")) return rc;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    const int nbf = grid_for(ctx, ctx->d.cap, FIN_THREADS, 8);
+    finish_kernel<false><<<nbf, FIN_THREADS, 0, ctx->stream>>>(ctx->d, 1, parity);
+    if (int rc = check_launch(ctx, "finish_kernel")) return rc;
+    if (int rc = fetch_state(ctx)) return rc;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (elapsed_ms) *elapsed_ms = ms;
+    if (cell_evals) *cell_evals = ctx->st_host->cell_evals - before;
+    ctx->times.scan_ms += ms;
+    ctx->times.scan_launches++;
+    return device_error(ctx);
+}
+
+API int mcrat_b200_measure_fp64_peak(mcrat_b200_ctx *ctx, double *ginstr_per_s)
+{
+    if (!ctx || !ginstr_per_s) return MCRAT_B200_ERR_ARG;
+    double *out = nullptr;
+    CK(cudaMalloc((void **)&out, sizeof(double)));
+    const int iters = 8192, blocks = ctx->num_sms * 8, threads = 256;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(out, iters, 1.000001 + rep);
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaFree(out);
+    // per thread and iteration: 8 x (DADD + DSETP) FP64-pipe instructions
+    double instr = (double)blocks * threads * (double)iters * 16.0;
+    *ginstr_per_s = instr / (best * 1e-3) / 1e9;
+    return MCRAT_B200_OK;
+}
+
+API int mcrat_b200_measure_hbm_peak(mcrat_b200_ctx *ctx, double *gb_per_s)
+{
+    if (!ctx || !gb_per_s) return MCRAT_B200_ERR_ARG;
+    const size_t n = (size_t)1 << 26; // 2 GiB per buffer of double4: larger than L2
+    double4 *a = nullptr, *b = nullptr;
+    CK(cudaMalloc((void **)&a, n * sizeof(double4)));
+    if (cudaMalloc((void **)&b, n * sizeof(double4)) != cudaSuccess) {
+        cudaFree(a);
+        return fail(ctx, MCRAT_B200_ERR_CUDA, "cudaMalloc (hbm probe)");
+    }
+    CK(cudaMemsetAsync(a, 0, n * sizeof(double4), ctx->stream));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        copy_kernel<<<ctx->num_sms * 16, 256, 0, ctx->stream>>>(a, b, n);
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaFree(a);
+    cudaFree(b);
+    *gb_per_s = 2.0 * (double)n * sizeof(double4) / (best * 1e-3) / 1e9;
+    return MCRAT_B200_OK;
+}

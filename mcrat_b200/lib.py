@@ -1,0 +1,269 @@
+"""ctypes binding of libmcrat_b200.so (the C ABI declared in include/mcrat_b200.h).
+
+This is plumbing for the Python test / benchmark harness; the product boundary is
+the C ABI itself (the host program is C).  Nothing here
+computes: a missing or unloadable library is an error, there is no fallback.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from .synth import PHOTON_DTYPE
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libmcrat_b200.so")
+DROPIN_PATH = os.path.join(CSRC, "libmcrat_b200_dropin.so")
+
+HYDRO_FIELDS = ["r0", "r1", "r2", "r0_size", "r1_size", "r2_size", "r", "theta", "v0", "v1", "v2",
+                "dens", "dens_lab", "pres", "temp", "gamma", "B0", "B1", "B2"]
+
+ABI_VERSION = 1
+RNG_PHILOX, RNG_REPLAY = 0, 1
+
+ERRORS = {-1: "ERR_CUDA", -2: "ERR_ARG", -3: "ERR_STATE", -4: "ERR_REPLAY", -5: "ERR_TABLE"}
+
+
+class McratB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s (%d): %s" % (ERRORS.get(code, "ERR"), code, msg))
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("abi_version", C.c_int), ("dimensions", C.c_int), ("geometry", C.c_int), ("stokes_switch", C.c_int),
+                ("tau_calculation", C.c_int), ("cyclosynch_switch", C.c_int), ("b_field_calc", C.c_int),
+                ("epsilon_b", C.c_double), ("device", C.c_int), ("rng_mode", C.c_int), ("seed", C.c_uint64),
+                ("shard", C.c_uint32), ("profile", C.c_int), ("stream", C.c_void_p)]
+
+
+class FrameStats(C.Structure):
+    _fields_ = [("iterations", C.c_longlong), ("scatterings", C.c_longlong), ("relocations", C.c_longlong),
+                ("photon_slots", C.c_longlong), ("cell_evals", C.c_longlong), ("time_now", C.c_double),
+                ("last_time_step", C.c_double), ("last_scattered_index", C.c_int), ("not_found", C.c_int),
+                ("cs_host_pending", C.c_int), ("error", C.c_int)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class KernelTimes(C.Structure):
+    _fields_ = [("scan_ms", C.c_double), ("scan_launches", C.c_longlong), ("pass_ms", C.c_double),
+                ("pass_launches", C.c_longlong), ("event_ms", C.c_double), ("event_launches", C.c_longlong),
+                ("other_ms", C.c_double), ("other_launches", C.c_longlong)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+EXPORTS = [
+    "mcrat_b200_abi_version", "mcrat_b200_device_count", "mcrat_b200_create", "mcrat_b200_destroy",
+    "mcrat_b200_last_error", "mcrat_b200_synchronize", "mcrat_b200_set_hydro", "mcrat_b200_set_thermal_table",
+    "mcrat_b200_set_photons", "mcrat_b200_get_photons", "mcrat_b200_get_photon", "mcrat_b200_list_capacity",
+    "mcrat_b200_set_replay_uniforms", "mcrat_b200_replay_consumed", "mcrat_b200_find_containing_hydro_cell",
+    "mcrat_b200_calc_mean_free_path", "mcrat_b200_photon_event", "mcrat_b200_update_photon_position",
+    "mcrat_b200_ph_abs_cyclosynch", "mcrat_b200_ph_min_max", "mcrat_b200_ph_scatt_stats",
+    "mcrat_b200_average_photon_energy", "mcrat_b200_run_frame", "mcrat_b200_get_kernel_times",
+    "mcrat_b200_rescan_all", "mcrat_b200_measure_fp64_peak", "mcrat_b200_measure_hbm_peak",
+]
+
+
+def build(force=False):
+    """Compile the CUDA library in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in ("mcrat_b200.cu", "device_math.cuh", "dropin.c", "Makefile")]
+    srcs += [os.path.join(HERE, "..", "include", f) for f in ("mcrat_b200.h", "mcrat_b200_dropin.h")]
+    srcs = [s for s in srcs if os.path.exists(s)]
+    stale = force or not os.path.exists(LIB_PATH) or not os.path.exists(DROPIN_PATH) or \
+        any(os.path.getmtime(s) > min(os.path.getmtime(LIB_PATH), os.path.getmtime(DROPIN_PATH)) for s in srcs)
+    if stale:
+        subprocess.check_call(["make", "-C", CSRC, "-s", "all"])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """dlopen the library; raises if it is not built (no fallback of any kind)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError("%s is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                    "(there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        L.mcrat_b200_last_error.restype = C.c_char_p
+        L.mcrat_b200_last_error.argtypes = [C.c_void_p]
+        L.mcrat_b200_replay_consumed.restype = C.c_longlong
+        L.mcrat_b200_replay_consumed.argtypes = [C.c_void_p]
+        L.mcrat_b200_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+        L.mcrat_b200_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class HotPath:
+    """Host-side mirror of the reference's function surface for one shard (one GPU).
+
+    Method names follow the reference (findContainingHydroCell, calcMeanFreePath,
+    photonEvent, updatePhotonPosition, phAbsCyclosynch, ...; Src/mclib.h:8-23,
+    Src/mc_cyclosynch.h:84-92); each forwards to the C ABI.
+    """
+
+    def __init__(self, cfg, device=0, rng_mode=RNG_PHILOX, seed=0, shard=0, profile=False, stream=None):
+        self.L = load()
+        c = Config(ABI_VERSION, cfg["dimensions"], cfg["geometry"], cfg["stokes"], cfg["tau_calculation"],
+                   cfg["cyclosynch"], cfg["b_field_calc"], cfg["epsilon_b"], device, rng_mode, seed, shard,
+                   1 if profile else 0, stream)
+        self.ctx = C.c_void_p()
+        rc = self.L.mcrat_b200_create(C.byref(c), C.byref(self.ctx))
+        if rc != 0:
+            raise McratB200Error(rc, self.L.mcrat_b200_last_error(None).decode())
+        self.cfg = dict(cfg)
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None and self.ctx:
+            self.L.mcrat_b200_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise McratB200Error(rc, self.L.mcrat_b200_last_error(self.ctx).decode())
+
+    # ---- inputs -----------------------------------------------------------------------
+    def set_hydro(self, hydro):
+        n = int(hydro["num_elements"])
+        ptrs = (C.POINTER(C.c_double) * 19)()
+        keep = []
+        for i, f in enumerate(HYDRO_FIELDS):
+            if f in hydro:
+                a = np.ascontiguousarray(hydro[f], dtype=np.float64)
+                if a.size != n:
+                    raise ValueError("hydro field %s has %d elements, expected %d" % (f, a.size, n))
+                keep.append(a)
+                ptrs[i] = _dp(a)
+            else:
+                ptrs[i] = None
+        dom = np.array(list(hydro.get("r0_domain", (0, 0))) + list(hydro.get("r1_domain", (0, 0))) +
+                       list(hydro.get("r2_domain", (0, 0))), dtype=np.float64)
+        self._ck(self.L.mcrat_b200_set_hydro(self.ctx, C.c_int(n), ptrs, _dp(dom), C.c_double(hydro.get("fps", 5.0)),
+                                             C.c_int(hydro.get("scatt_frame_number", 0)),
+                                             C.c_int(hydro.get("inj_frame_number", 0))))
+
+    def set_thermal_table(self, table):
+        t = np.ascontiguousarray(table, dtype=np.float64)
+        assert t.shape == (221, 81)
+        self._ck(self.L.mcrat_b200_set_thermal_table(self.ctx, _dp(t)))
+
+    def set_photons(self, photons):
+        ph = np.ascontiguousarray(photons, dtype=PHOTON_DTYPE)
+        self._ck(self.L.mcrat_b200_set_photons(self.ctx, ph.ctypes.data_as(C.c_void_p), C.c_int(ph.size)))
+
+    def set_photons_ptr(self, ptr, n):
+        """Upload from a raw host pointer (e.g. pinned memory owned by the caller)."""
+        self._ck(self.L.mcrat_b200_set_photons(self.ctx, C.c_void_p(ptr), C.c_int(n)))
+
+    def get_photons(self, out=None):
+        n = self.L.mcrat_b200_list_capacity(self.ctx)
+        if out is None:
+            out = np.zeros(n, dtype=PHOTON_DTYPE)
+        self._ck(self.L.mcrat_b200_get_photons(self.ctx, out.ctypes.data_as(C.c_void_p), C.c_int(n)))
+        return out
+
+    def get_photons_ptr(self, ptr, n):
+        self._ck(self.L.mcrat_b200_get_photons(self.ctx, C.c_void_p(ptr), C.c_int(n)))
+
+    def get_photon(self, index):
+        out = np.zeros(1, dtype=PHOTON_DTYPE)
+        self._ck(self.L.mcrat_b200_get_photon(self.ctx, C.c_int(index), out.ctypes.data_as(C.c_void_p)))
+        return out[0]
+
+    def set_replay_uniforms(self, u):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        self._ck(self.L.mcrat_b200_set_replay_uniforms(self.ctx, _dp(u), C.c_size_t(u.size)))
+
+    def replay_consumed(self):
+        return int(self.L.mcrat_b200_replay_consumed(self.ctx))
+
+    # ---- the reference's function surface -----------------------------------------------
+    def findContainingHydroCell(self, find_nearest_block_switch):
+        n = C.c_int(0)
+        self._ck(self.L.mcrat_b200_find_containing_hydro_cell(self.ctx, C.c_int(find_nearest_block_switch), C.byref(n)))
+        return n.value
+
+    def calcMeanFreePath(self):
+        i, t = C.c_int(0), C.c_double(0)
+        self._ck(self.L.mcrat_b200_calc_mean_free_path(self.ctx, C.byref(i), C.byref(t)))
+        return i.value, t.value
+
+    def photonEvent(self, dt_max):
+        ts, idx, sc, ab = C.c_double(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        self._ck(self.L.mcrat_b200_photon_event(self.ctx, C.c_double(dt_max), C.byref(ts), C.byref(idx), C.byref(sc),
+                                                C.byref(ab)))
+        return ts.value, idx.value, sc.value
+
+    def updatePhotonPosition(self, t):
+        self._ck(self.L.mcrat_b200_update_photon_position(self.ctx, C.c_double(t)))
+
+    def phAbsCyclosynch(self):
+        na, ns, w = C.c_int(0), C.c_int(0), C.c_double(0)
+        self._ck(self.L.mcrat_b200_ph_abs_cyclosynch(self.ctx, C.byref(na), C.byref(ns), C.byref(w)))
+        return w.value, na.value, ns.value
+
+    def phMinMax(self):
+        v = [C.c_double(0) for _ in range(4)]
+        self._ck(self.L.mcrat_b200_ph_min_max(self.ctx, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    def phScattStats(self):
+        mx, mn, avg, ravg = C.c_int(0), C.c_int(0), C.c_double(0), C.c_double(0)
+        self._ck(self.L.mcrat_b200_ph_scatt_stats(self.ctx, C.byref(mx), C.byref(mn), C.byref(avg), C.byref(ravg)))
+        return mx.value, mn.value, avg.value, ravg.value
+
+    def averagePhotonEnergy(self):
+        e = C.c_double(0)
+        self._ck(self.L.mcrat_b200_average_photon_energy(self.ctx, C.byref(e)))
+        return e.value
+
+    # ---- device-resident frame loop ---------------------------------------------------------
+    def run_frame(self, time_now, remaining_time, max_iters=-1, switch=1):
+        st = FrameStats()
+        self._ck(self.L.mcrat_b200_run_frame(self.ctx, C.c_double(time_now), C.c_double(remaining_time),
+                                             C.c_longlong(max_iters), C.c_int(switch), C.byref(st)))
+        return st.as_dict()
+
+    # ---- measurement -----------------------------------------------------------------------------
+    def synchronize(self):
+        self._ck(self.L.mcrat_b200_synchronize(self.ctx))
+
+    def kernel_times(self, reset=False):
+        t = KernelTimes()
+        self._ck(self.L.mcrat_b200_get_kernel_times(self.ctx, C.byref(t), C.c_int(1 if reset else 0)))
+        return t.as_dict()
+
+    def rescan_all(self):
+        ev, ms = C.c_longlong(0), C.c_float(0)
+        self._ck(self.L.mcrat_b200_rescan_all(self.ctx, C.byref(ev), C.byref(ms)))
+        return ev.value, ms.value
+
+    def measure_fp64_peak(self):
+        v = C.c_double(0)
+        self._ck(self.L.mcrat_b200_measure_fp64_peak(self.ctx, C.byref(v)))
+        return v.value
+
+    def measure_hbm_peak(self):
+        v = C.c_double(0)
+        self._ck(self.L.mcrat_b200_measure_hbm_peak(self.ctx, C.byref(v)))
+        return v.value
