@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- MCRaT hot path on B200: scatterings/s and photon-cell evals/s vs roofline.
+
+A *step* is one scatter-frame slice of the reference's driver loop (Src/mcrat.c:754-851) over
+one shard: a new hydro frame arrives, so every photon is re-located by the full photon x cell
+containment scan (find_nearest_grid_switch = 1, Src/mcrat.c:756), then ``--iters`` iterations of
+the while-loop run (each: fused push / re-check / free-path draw / arg-min pass over all photons,
+then one scattering event).  Steps continue the same simulation, frame after frame.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
+  python bench.py --impl reference [...]                         the reference's own CPU code
+
+Workload at N=1: BASELINE.json configs[1] -- 2-D cylindrical FLASH-shape jet, 1024x1024 cells,
+1e5 photons, polarisation on.  With N>1 every rank owns an independent shard of that size
+(the reference's MPI decomposition: no exchange inside the frame loop), scaling = weak.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "scatterings/sec"
+UNIT = "scatterings/s"
+WORKLOAD = "C2: 2-D cylindrical FLASH-shape GRB jet, 1024x1024 cells, 1e5 photons/shard, Stokes on"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--iters", type=int, default=5000, help="while-loop iterations per step (frame slice)")
+    ap.add_argument("--photons", type=int, default=100000)
+    ap.add_argument("--scale", type=float, default=1.0, help="grid scale (1.0 = 1024x1024 cells)")
+    ap.add_argument("--cpu-iters", type=int, default=0, help="iterations per CPU rank and step (0: same as --iters)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pass-roofline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own sources (oracle/_ref) or, if absent, the oracle port
+# ------------------------------------------------------------------------------------------------
+def _cpu_rank(rank, nranks, cfg, hydro, photons, frame, iters, steps, warmup, kind, barrier, out):
+    from oracle import api
+    sl = slice(rank * photons.size // nranks, (rank + 1) * photons.size // nranks)
+    ph = photons[sl]
+    if kind == "reference":
+        eng = api.RefLib("c2_2d_cyl_stokes")
+        eng.set_hydro(hydro)
+        eng.set_photons(ph)
+        rng, _ = eng.new_rng(seed=rank + 1)
+    else:
+        eng = api.Oracle(cfg)
+        eng.set_hydro(hydro)
+        eng.set_photons(ph)
+        rng = api.OracleRng("ranlxs0", seed=rank + 1)
+    time_now = frame["time_now"]
+    scatt = 0
+    t_steps = []
+    for s in range(warmup + steps):
+        barrier.wait()
+        t0 = time.perf_counter()
+        st = eng.run_frame(rng, time_now, 1.0 / frame["fps"], max_iters=iters, switch=1)
+        t1 = time.perf_counter()
+        time_now = st["time_now"]
+        if s >= warmup:
+            t_steps.append(t1 - t0)
+            scatt += st["scatterings"]
+    out.put((rank, scatt, t_steps))
+
+
+def run_cpu_arm(cfg, hydro, photons, frame, iters, steps, warmup):
+    """R independent ranks (one per host core), each owning a contiguous slice of the photons --
+    the reference's own way of using more cores (no exchange inside the frame loop)."""
+    from oracle import api
+    kind = "reference" if api.ref_available("c2_2d_cyl_stokes") else "port"
+    if kind == "port":
+        api.build_oracle()
+    ncores = len(os.sched_getaffinity(0))
+    nranks = max(1, min(ncores, photons.size // 256))
+    ctx = mp.get_context("fork")
+    barrier = ctx.Barrier(nranks)
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_cpu_rank, args=(r, nranks, cfg, hydro, photons, frame, iters, steps, warmup, kind,
+                                                 barrier, out)) for r in range(nranks)]
+    for p in procs:
+        p.start()
+    res = [out.get() for _ in procs]
+    for p in procs:
+        p.join()
+    scatt = sum(r[1] for r in res)
+    # per step the job takes as long as its slowest rank
+    per_step = [max(r[2][k] for r in res) for k in range(steps)]
+    total = sum(per_step)
+    return dict(value=scatt / total, unit=UNIT, cores=nranks, kind=kind, seconds=total, ms_per_step=1e3 * total / steps,
+                sample="%d ranks x %d photons, full rescan + %d loop iterations per rank and step, %d step(s)"
+                       % (nranks, photons.size // nranks, iters, steps))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from mcrat_b200 import synth
+    cfg, hydro, photons, frame = synth.workload("C2", scale=args.scale, n_photons=args.photons, seed=1234 + rank)
+    config = {"workload": WORKLOAD if (args.scale == 1.0 and args.photons == 100000) else
+              "C2 reduced: scale=%g, %d photons/shard" % (args.scale, args.photons),
+              "cells": int(hydro["num_elements"]), "photons_per_shard": int(photons.size),
+              "loop_iterations_per_step": args.iters, "shards": world,
+              "step": "full photon x cell rescan (new hydro frame) + loop iterations; steps continue one simulation",
+              "l2": "flushed between timed steps (256 MiB write)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cpu_iters = args.cpu_iters or args.iters
+        res = run_cpu_arm(cfg, hydro, photons, frame, cpu_iters, args.steps, args.warmup)
+        config["loop_iterations_per_step"] = cpu_iters
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
+                                 "sample": res["sample"]},
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ---------------- our arm ----------------
+    import torch
+    import torch.distributed as dist
+    from mcrat_b200 import HotPath
+    from mcrat_b200.lib import PHOTON_DTYPE
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream().cuda_stream
+    hp = HotPath(cfg, device=local_rank, seed=20261018, shard=rank, stream=stream)
+    hp.set_hydro(hydro)
+    hp.set_photons(photons)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    dt_frame = 1.0 / frame["fps"]
+
+    # ---- device-resident arm: `value` ----
+    time_now = frame["time_now"]
+    for _ in range(args.warmup):
+        st = hp.run_frame(time_now, dt_frame, max_iters=args.iters, switch=1)
+        time_now = st["time_now"]
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = hp.launch_count()
+    tot_ms = 0.0
+    scatt = evals = slots = 0
+    barrier()
+    for _ in range(args.steps):
+        flush_buf.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        st = hp.run_frame(time_now, dt_frame, max_iters=args.iters, switch=1)
+        e1.record()
+        torch.cuda.synchronize()
+        tot_ms += e0.elapsed_time(e1)
+        time_now = st["time_now"]
+        scatt += st["scatterings"]
+        evals += st["cell_evals"]
+        slots += st["photon_slots"]
+    barrier()
+    launches = hp.launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel (K1 scan), timed alone with CUDA events on its stream ----
+    scan_ms, scan_evals = [], 0
+    for _ in range(3):
+        flush_buf.fill_(1)
+        ev, ms = hp.rescan_all()
+        scan_ms.append(ms)
+        scan_evals = ev
+    scan_ms_avg = float(np.mean(scan_ms))
+    fp64_peak = hp.measure_fp64_peak()  # Ginstr/s, DADD+DSETP mix, same GPU, same run
+    instr_per_eval = 6 if cfg["dimensions"] == 2 else 4  # one DADD + one DSETP per dimension
+    achieved = scan_evals * instr_per_eval / (scan_ms_avg * 1e-3) / 1e9
+    roofline = {"kernel": "scan_kernel (K1 photon x cell containment scan)", "bound": "fp64",
+                "achieved": achieved, "peak": fp64_peak, "unit": "G FP64-pipe instr/s",
+                "frac": achieved / fp64_peak, "traffic": None,
+                "peak_source": "measured in this run (mcrat_b200_measure_fp64_peak: DADD+DSETP chains, all SMs); "
+                               "MEASURED_PEAKS.json holds no FP64 figure",
+                "algorithmic": "%d FP64-pipe instr per photon-cell eval x %d evals per launch" % (instr_per_eval, scan_evals),
+                "evals_per_s": scan_evals / (scan_ms_avg * 1e-3), "ms_per_launch": scan_ms_avg}
+
+    # ---- e2e: the same step through the C ABI with host buffers (H2D + D2H inside the timed region) ----
+    host_ph = torch.empty(photons.size * PHOTON_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    host_np = host_ph.numpy().view(PHOTON_DTYPE)
+    host_np[:] = hp.get_photons()
+    h2d = sum(np.asarray(hydro[f]).nbytes for f in ("r0", "r1", "r2", "r0_size", "r1_size", "r2_size", "r", "theta",
+                                                   "v0", "v1", "v2", "dens", "dens_lab", "pres", "temp", "gamma",
+                                                   "B0", "B1", "B2")) + host_ph.numel()
+    d2h = host_ph.numel()
+    e2e_scatt = 0
+    for k in range(1 + args.steps):
+        if k == 1:
+            barrier()
+            t0 = time.perf_counter()
+        hp.set_hydro(hydro)                                   # the frame the driver just read (Src/mcrat.c:721)
+        hp.set_photons_ptr(host_ph.data_ptr(), photons.size)  # host list -> device
+        st = hp.run_frame(time_now, dt_frame, max_iters=args.iters, switch=1)
+        hp.get_photons_ptr(host_ph.data_ptr(), photons.size)  # device -> host list (checkpoint / mc_proc output)
+        time_now = st["time_now"]
+        if k >= 1:
+            e2e_scatt += st["scatterings"]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- secondary roofline: the fused pass at a list larger than L2 (HBM-bound regime) ----
+    pass_roofline = None
+    if not args.no_pass_roofline and rank == 0:
+        try:
+            nbig = 4_000_000
+            rep = np.resize(photons, nbig)
+            hpb = HotPath(cfg, device=local_rank, seed=7, shard=rank, profile=True)
+            hpb.set_hydro(hydro)
+            hpb.set_photons(rep)
+            hpb.run_frame(time_now, dt_frame, max_iters=1, switch=1)
+            hpb.kernel_times(reset=True)
+            hpb.run_frame(time_now, dt_frame, max_iters=24, switch=0)
+            kt = hpb.kernel_times()
+            ms = kt["pass_ms"] / max(kt["pass_launches"], 1)
+            gbs = nbig * 100.0 / (ms * 1e-3) / 1e9
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+                os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+            peak = peaks.get("hbm_gbs", 6650.0)
+            pass_roofline = {"kernel": "pass_kernel<fused> (K4+K2) at %d photons" % nbig, "bound": "hbm",
+                             "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
+                             "algorithmic": "100 B per photon-iteration x %d photons" % nbig, "ms_per_launch": ms}
+            hpb.close()
+        except Exception as exc:  # measurement extra; never fail the bench line over it
+            pass_roofline = {"error": str(exc)}
+
+    # ---- aggregate over ranks ----
+    t_max, scatt_all, evals_all, slots_all, e2e_max, e2e_all = tot_ms, scatt, evals, slots, e2e_s, e2e_scatt
+    if world > 1:
+        t = torch.tensor([tot_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c = torch.tensor([scatt, evals, slots, e2e_scatt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        t_max, e2e_max = float(t[0]), float(t[1])
+        scatt_all, evals_all, slots_all, e2e_all = [float(x) for x in c]
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cpu_iters = args.cpu_iters or args.iters
+            r = run_cpu_arm(cfg, hydro, photons, frame, cpu_iters, 1, 0)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        line = {"metric": METRIC, "value": scatt_all / (t_max * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_max / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config,
+                "photon_cell_evals_per_sec": roofline["evals_per_s"] * world,
+                "photon_iterations_per_sec": slots_all / (t_max * 1e-3),
+                "scan_share_of_step": scan_ms_avg / (t_max / args.steps),
+                "roofline": roofline, "pass_roofline": pass_roofline, "cpu_baseline": cpu,
+                "e2e": {"value": e2e_all / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_max / args.steps},
+                "gpu_launches": int(launches), "clocks": clk}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

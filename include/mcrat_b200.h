@@ -160,6 +160,8 @@ int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remaining_
 
 /* ---- measurement ------------------------------------------------------------------------------ */
 int mcrat_b200_get_kernel_times(mcrat_b200_ctx *ctx, mcrat_b200_kernel_times *out, int reset);
+/* number of kernels launched through this context so far */
+long long mcrat_b200_launch_count(const mcrat_b200_ctx *ctx);
 /* full photon x cell rescan only (the K1 kernel on the current list), for roofline timing */
 int mcrat_b200_rescan_all(mcrat_b200_ctx *ctx, long long *cell_evals, float *elapsed_ms);
 /* sustained FP64-pipe instruction rate of this GPU (DADD+DSETP mix of the scan), Ginstr/s */

@@ -1135,6 +1135,7 @@ struct mcrat_b200_ctx {
     bool have_hydro, have_photons;
     int pass_parity;
     int last_nb_mfp;
+    long long launches; // kernels launched through this context
     LoopState *st_host; // pinned
     double *replay_dev;
     size_t replay_cap;
@@ -1257,6 +1258,7 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
     ctx->have_hydro = ctx->have_photons = false;
     ctx->pass_parity = 0;
     ctx->last_nb_mfp = 0;
+    ctx->launches = 0;
     ctx->replay_dev = nullptr;
     ctx->replay_cap = 0;
     ctx->table_dev = nullptr;
@@ -1352,8 +1354,9 @@ static int fetch_state(mcrat_b200_ctx *ctx)
     return MCRAT_B200_OK;
 }
 
-static int check_launch(mcrat_b200_ctx *ctx, const char *what)
+static int check_launch(mcrat_b200_ctx *ctx, const char *what, int n = 1)
 {
+    ctx->launches += n;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -1463,6 +1466,7 @@ API int mcrat_b200_set_photons(mcrat_b200_ctx *ctx, const mcrat_photon *photons,
         if (int rc = check_launch(ctx, "unpack_kernel")) return rc;
     }
     clear_push_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d);
+    if (int rc = check_launch(ctx, "clear_push_kernel")) return rc;
     ctx->have_photons = true;
     return MCRAT_B200_OK;
 }
@@ -1624,6 +1628,7 @@ static int launch_mfp_unfused(mcrat_b200_ctx *ctx, int &nb)
     if (ctx->d.replay) {
         mfp_count_kernel<<<nblocks, 256, 0, ctx->stream>>>(ctx->d);
         mfp_scan_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d, nblocks);
+        if (int rc = check_launch(ctx, "mfp_scan_kernel", 2)) return rc;
     }
     mfp_kernel<<<nblocks, 256, 0, ctx->stream>>>(ctx->d);
     if (int rc = check_launch(ctx, "mfp_kernel")) return rc;
@@ -1657,6 +1662,7 @@ API int mcrat_b200_find_containing_hydro_cell(mcrat_b200_ctx *ctx, int sw, int *
     int nbp, nbf;
     if (int rc = launch_locate<false>(ctx, sw ? 1 : 0, nbp, nbf)) return rc;
     clear_push_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d); // the pass consumed the pending pushes
+    if (int rc = check_launch(ctx, "clear_push_kernel")) return rc;
     if (int rc = fetch_state(ctx)) return rc;
     if (num_relocated) *num_relocated = (int)(ctx->st_host->reloc_total - before);
     return device_error(ctx);
@@ -1726,6 +1732,7 @@ API int mcrat_b200_update_photon_position(mcrat_b200_ctx *ctx, double t)
     if (!ctx->have_photons) return fail(ctx, MCRAT_B200_ERR_STATE, "no photon list loaded");
     if (int rc = flush_pushes(ctx)) return rc;
     set_push_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d, t);
+    if (int rc = check_launch(ctx, "set_push_kernel")) return rc;
     Timed tm(ctx, KC_PASS);
     return flush_pushes(ctx);
 }
@@ -1743,6 +1750,7 @@ API int mcrat_b200_ph_abs_cyclosynch(mcrat_b200_ctx *ctx, int *num_abs_ph, int *
     if (int rc = need_ready(ctx)) return rc;
     if (int rc = flush_pushes(ctx)) return rc;
     clear_abs_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d);
+    if (int rc = check_launch(ctx, "clear_abs_kernel")) return rc;
     cs_absorb_kernel<<<grid_for(ctx, ctx->d.cap, 256, 8), 256, 0, ctx->stream>>>(ctx->d);
     if (int rc = check_launch(ctx, "cs_absorb_kernel")) return rc;
     if (int rc = fetch_state(ctx)) return rc;
@@ -1872,6 +1880,8 @@ API int mcrat_b200_get_kernel_times(mcrat_b200_ctx *ctx, mcrat_b200_kernel_times
     if (reset) memset(&ctx->times, 0, sizeof(ctx->times));
     return MCRAT_B200_OK;
 }
+
+API long long mcrat_b200_launch_count(const mcrat_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 API int mcrat_b200_rescan_all(mcrat_b200_ctx *ctx, long long *cell_evals, float *elapsed_ms)
 {

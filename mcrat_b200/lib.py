@@ -66,7 +66,7 @@ EXPORTS = [
     "mcrat_b200_calc_mean_free_path", "mcrat_b200_photon_event", "mcrat_b200_update_photon_position",
     "mcrat_b200_ph_abs_cyclosynch", "mcrat_b200_ph_min_max", "mcrat_b200_ph_scatt_stats",
     "mcrat_b200_average_photon_energy", "mcrat_b200_run_frame", "mcrat_b200_get_kernel_times",
-    "mcrat_b200_rescan_all", "mcrat_b200_measure_fp64_peak", "mcrat_b200_measure_hbm_peak",
+    "mcrat_b200_launch_count", "mcrat_b200_rescan_all", "mcrat_b200_measure_fp64_peak", "mcrat_b200_measure_hbm_peak",
 ]
 
 
@@ -99,6 +99,8 @@ def load():
         L.mcrat_b200_replay_consumed.argtypes = [C.c_void_p]
         L.mcrat_b200_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
         L.mcrat_b200_destroy.argtypes = [C.c_void_p]
+        L.mcrat_b200_launch_count.restype = C.c_longlong
+        L.mcrat_b200_launch_count.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -247,6 +249,9 @@ class HotPath:
     # ---- measurement -----------------------------------------------------------------------------
     def synchronize(self):
         self._ck(self.L.mcrat_b200_synchronize(self.ctx))
+
+    def launch_count(self):
+        return int(self.L.mcrat_b200_launch_count(self.ctx))
 
     def kernel_times(self, reset=False):
         t = KernelTimes()

@@ -40,7 +40,7 @@ def test_frame_philox_parity(wl, refname, scale, nph, iters):
     for k in ("iterations", "scatterings", "relocations", "photon_slots"):
         assert st[k] == ost[k], (k, st, ost)
     assert abs(st["time_now"] - ost["time_now"]) <= 1e-12 * abs(ost["time_now"])
-    errs = compare_photons(got, o.photons(), label=wl, stokes_tol=1e-9)
+    errs = compare_photons(got, o.photons(), label=wl, stokes_tol=1e-9, hydro=hydro)
     print(wl, "max rel errors", {k: "%.1e" % v for k, v in errs.items()})
 
 
@@ -64,5 +64,5 @@ def test_frame_replay_parity(wl, refname, scale, nph, iters):
     assert hp.replay_consumed() == u.size, (hp.replay_consumed(), u.size)
     for k in ("iterations", "scatterings", "relocations"):
         assert st[k] == ost[k], (k, st, ost)
-    errs = compare_photons(got, o.photons(), label=wl, stokes_tol=1e-9)
+    errs = compare_photons(got, o.photons(), label=wl, stokes_tol=1e-9, hydro=hydro)
     print(wl, "max rel errors", {k: "%.1e" % v for k, v in errs.items()})
