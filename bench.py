@@ -33,6 +33,13 @@ UNIT = "scatterings/s"
 WORKLOAD = "C2: 2-D cylindrical FLASH-shape GRB jet, 1024x1024 cells, 1e5 photons/shard, Stokes on"
 
 
+_T0 = time.time()
+
+
+def log(msg):
+    print("[bench %6.1fs] %s" % (time.time() - _T0, msg), file=sys.stderr, flush=True)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,6 +171,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     from mcrat_b200 import synth
+    log("building workload")
     cfg, hydro, photons, frame = synth.workload("C2", scale=args.scale, n_photons=args.photons, seed=1234 + rank)
     config = {"workload": WORKLOAD if (args.scale == 1.0 and args.photons == 100000) else
               "C2 reduced: scale=%g, %d photons/shard" % (args.scale, args.photons),
@@ -212,11 +220,13 @@ def main():
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     dt_frame = 1.0 / frame["fps"]
 
+    log("context ready; warm-up")
     # ---- device-resident arm: `value` ----
     time_now = frame["time_now"]
     for _ in range(args.warmup):
         st = hp.run_frame(time_now, dt_frame, max_iters=args.iters, switch=1)
         time_now = st["time_now"]
+    log("timed steps")
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -241,6 +251,7 @@ def main():
     launches = hp.launch_count() - launches0
     clk = clocks.stop() if rank == 0 else None
 
+    log("timed steps done: %.1f ms/step; scan roofline" % (tot_ms / args.steps))
     # ---- roofline of the dominant kernel (K1 scan), timed alone with CUDA events on its stream ----
     scan_ms, scan_evals = [], 0
     for _ in range(3):
@@ -249,17 +260,18 @@ def main():
         scan_ms.append(ms)
         scan_evals = ev
     scan_ms_avg = float(np.mean(scan_ms))
-    fp64_peak = hp.measure_fp64_peak()  # Ginstr/s, DADD+DSETP mix, same GPU, same run
+    fp64_peak = hp.measure_fp64_peak()  # G FP64-pipe instr/s (DFMA issue rate), same GPU, same run
     instr_per_eval = 6 if cfg["dimensions"] == 2 else 4  # one DADD + one DSETP per dimension
     achieved = scan_evals * instr_per_eval / (scan_ms_avg * 1e-3) / 1e9
     roofline = {"kernel": "scan_kernel (K1 photon x cell containment scan)", "bound": "fp64",
                 "achieved": achieved, "peak": fp64_peak, "unit": "G FP64-pipe instr/s",
                 "frac": achieved / fp64_peak, "traffic": None,
-                "peak_source": "measured in this run (mcrat_b200_measure_fp64_peak: DADD+DSETP chains, all SMs); "
+                "peak_source": "measured in this run (mcrat_b200_measure_fp64_peak: 16 independent DFMA chains/thread, all SMs); "
                                "MEASURED_PEAKS.json holds no FP64 figure",
                 "algorithmic": "%d FP64-pipe instr per photon-cell eval x %d evals per launch" % (instr_per_eval, scan_evals),
                 "evals_per_s": scan_evals / (scan_ms_avg * 1e-3), "ms_per_launch": scan_ms_avg}
 
+    log("scan %.2f ms, fp64 peak %.0f Ginstr/s; e2e" % (scan_ms_avg, fp64_peak))
     # ---- e2e: the same step through the C ABI with host buffers (H2D + D2H inside the timed region) ----
     host_ph = torch.empty(photons.size * PHOTON_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
     host_np = host_ph.numpy().view(PHOTON_DTYPE)
@@ -283,6 +295,7 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    log("e2e done; pass roofline")
     # ---- secondary roofline: the fused pass at a list larger than L2 (HBM-bound regime) ----
     pass_roofline = None
     if not args.no_pass_roofline and rank == 0:
@@ -321,6 +334,7 @@ def main():
 
     if rank == 0:
         cpu = None
+        log("cpu baseline")
         if not args.no_cpu_baseline and world == 1:
             cpu_iters = args.cpu_iters or args.iters
             r = run_cpu_arm(cfg, hydro, photons, frame, cpu_iters, 1, 0)

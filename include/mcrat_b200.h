@@ -164,7 +164,8 @@ int mcrat_b200_get_kernel_times(mcrat_b200_ctx *ctx, mcrat_b200_kernel_times *ou
 long long mcrat_b200_launch_count(const mcrat_b200_ctx *ctx);
 /* full photon x cell rescan only (the K1 kernel on the current list), for roofline timing */
 int mcrat_b200_rescan_all(mcrat_b200_ctx *ctx, long long *cell_evals, float *elapsed_ms);
-/* sustained FP64-pipe instruction rate of this GPU (DADD+DSETP mix of the scan), Ginstr/s */
+/* sustained FP64-pipe instruction issue rate of this GPU (independent DFMA chains on all SMs),
+ * G thread-instructions/s; x2 = DFMA GFLOP/s */
 int mcrat_b200_measure_fp64_peak(mcrat_b200_ctx *ctx, double *ginstr_per_s);
 /* streaming copy bandwidth of this GPU, GB/s (read+write bytes) */
 int mcrat_b200_measure_hbm_peak(mcrat_b200_ctx *ctx, double *gb_per_s);

@@ -1091,23 +1091,19 @@ __global__ void __launch_bounds__(256) stats_kernel(DevCtx d, StatPartial *out)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double seed)
 {
-    // the scan's instruction mix: one DADD + one DSETP per dimension; 8 independent chains
-    double x[8], c = seed + threadIdx.x * 1e-9, h = 0.25;
-    int hits = 0;
+    // FP64-pipe issue rate: 16 independent DFMA chains per thread, 64 warps per SM
+    double x[16];
+    const double a = 1.0 + seed * 1e-9, b = seed * 1e-12;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = seed * (k + 1);
+    for (int k = 0; k < 16; ++k) x[k] = seed + k + threadIdx.x * 1e-6;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            double dd = x[k] - c;
-            hits += (fabs(dd) <= h) ? 1 : 0;
-            x[k] = dd;
-        }
+        for (int k = 0; k < 16; ++k) x[k] = fma(x[k], a, b);
     }
     double s = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += x[k];
-    if (hits == -1 || s == 12345.678) out[0] = s + hits;
+    for (int k = 0; k < 16; ++k) s += x[k];
+    if (s == 12345.678) out[0] = s;
 }
 
 __global__ void __launch_bounds__(256) copy_kernel(const double4 *__restrict__ a, double4 *__restrict__ b, size_t n)
@@ -1936,7 +1932,7 @@ API int mcrat_b200_measure_fp64_peak(mcrat_b200_ctx *ctx, double *ginstr_per_s)
         if (rep > 0 && ms < best) best = ms;
     }
     cudaFree(out);
-    // per thread and iteration: 8 x (DADD + DSETP) FP64-pipe instructions
+    // per thread and iteration: 16 DFMA (one FP64-pipe instruction each)
     double instr = (double)blocks * threads * (double)iters * 16.0;
     *ginstr_per_s = instr / (best * 1e-3) / 1e9;
     return MCRAT_B200_OK;

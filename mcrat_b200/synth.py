@@ -83,6 +83,13 @@ def make_grid(dimensions, geometry, shape, extent, log_r=False, flash_blocks=Fal
              r2_size=z2.copy(), fps=fps, dimensions=dimensions, geometry=geometry,
              r0_domain=tuple(extent[0]), r1_domain=tuple(extent[1]),
              r2_domain=tuple(extent[2]) if nd == 3 else (0.0, 0.0))
+    h["_edges"] = [np.concatenate([a[0] - 0.5 * a[1], [a[0][-1] + 0.5 * a[1][-1]]]) for a in axes]
+    h["_shape"] = tuple(shape[:nd])
+    h["_inv_perm"] = None
+    if nd == 2 and flash_blocks:
+        inv = np.empty(n, dtype=np.int64)
+        inv[p] = np.arange(n)
+        h["_inv_perm"] = inv
     h["r"], h["theta"] = hydro_to_spherical(dimensions, geometry, h["r0"], h["r1"], h["r2"])
     for f in ("v0", "v1", "v2", "dens", "dens_lab", "pres", "temp", "gamma", "B0", "B1", "B2"):
         h[f] = np.zeros(n)
@@ -225,6 +232,25 @@ def _boost(beta, p):
     return out
 
 
+def locate_cells(h, hc0, hc1, hc2):
+    """Containing cell on the structured grids built by make_grid (for building inputs only)."""
+    if "_edges" not in h:
+        return locate_cells_bruteforce(h, hc0, hc1, hc2)
+    e = h["_edges"]
+    shape = h["_shape"]
+    coords = (hc0, hc1, hc2)[:len(shape)]
+    idx = []
+    ok = np.ones(hc0.size, dtype=bool)
+    for d, c in enumerate(coords):
+        i = np.searchsorted(e[d], c, side="right") - 1
+        ok &= (i >= 0) & (i < shape[d]) & (c <= e[d][-1])
+        idx.append(np.clip(i, 0, shape[d] - 1))
+    flat = idx[0] + shape[0] * idx[1] if len(shape) == 2 else idx[0] + shape[0] * (idx[1] + shape[1] * idx[2])
+    if h.get("_inv_perm") is not None:
+        flat = h["_inv_perm"][flat]
+    return np.where(ok, flat, -1)
+
+
 def locate_cells_bruteforce(h, hc0, hc1, hc2, chunk=256):
     """First-match containing cell (numpy; for building inputs only)."""
     nd3 = h["dimensions"] == THREE
@@ -256,7 +282,7 @@ def make_photons(h, n, r_range, theta_range, seed=1234, weight=1e50, phi_range=(
     ph = phi_range[0] + rng.random(n) * (phi_range[1] - phi_range[0])
     x, y, z = r * np.sin(th) * np.cos(ph), r * np.sin(th) * np.sin(ph), r * np.cos(th)
     hc0, hc1, hc2 = mcrat_to_hydro(dims, g, x, y, z)
-    cell = locate_cells_bruteforce(h, hc0, hc1, hc2)
+    cell = locate_cells(h, hc0, hc1, hc2)
     ok = cell >= 0
     c = np.where(ok, cell, 0)
     temp = h["temp"][c]

@@ -1,0 +1,25 @@
+#!/usr/bin/env python
+"""Short driver for ncu captures: one C2 frame slice (full rescan + a few loop iterations),
+then a few fused passes over a photon list larger than L2.  Run plainly first, then under ncu
+(see profiles/README.md for the exact commands)."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mcrat_b200 import HotPath, synth  # noqa: E402
+
+iters = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+big = int(sys.argv[2]) if len(sys.argv) > 2 else 4_000_000
+
+cfg, hydro, photons, frame = synth.workload("C2")
+hp = HotPath(cfg, seed=1)
+hp.set_hydro(hydro)
+hp.set_photons(photons)
+st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=iters, switch=1)
+print("C2 slice:", st)
+if big > 0:
+    hp.set_photons(np.resize(photons, big))
+    st = hp.run_frame(st["time_now"], 1.0 / frame["fps"], max_iters=6, switch=0)
+    print("big list:", st)
