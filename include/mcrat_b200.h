@@ -85,12 +85,12 @@ typedef struct mcrat_b200_ctx mcrat_b200_ctx;
 
 /* what one call of the device-resident frame loop did */
 typedef struct mcrat_b200_frame_stats {
-    long long iterations;   /* while-loop iterations executed, Src/mcrat.c:761 */
+    long long iterations;   /* while-loop iterations executed, Src/mcrat.c:761 (max over sub-shards) */
     long long scatterings;  /* frame_scatt_cnt, Src/mclib.c:1318 */
     long long relocations;  /* num_photons_find_new_element, Src/mcrat.c:768 */
     long long photon_slots; /* sum over iterations of list_capacity (photon-iterations) */
     long long cell_evals;   /* photon-cell containment tests executed by the scan kernels */
-    double time_now;
+    double time_now;        /* clock of sub-shard 0 */
     double last_time_step;
     int last_scattered_index;
     int not_found;          /* photons for which no containing cell exists (Src/mclib.c:583) */
@@ -127,6 +127,16 @@ int mcrat_b200_set_photons(mcrat_b200_ctx *ctx, const mcrat_photon *photons, int
 int mcrat_b200_get_photons(mcrat_b200_ctx *ctx, mcrat_photon *photons, int list_capacity);
 int mcrat_b200_get_photon(mcrat_b200_ctx *ctx, int index, mcrat_photon *out);
 int mcrat_b200_list_capacity(const mcrat_b200_ctx *ctx);
+/* Sub-shards per context.  The reference decomposes a run into independent ranks, each with its
+ * own photon list, clock and time-ordered scatter sequence (Src/mcrat.c:139-164, 457-479; no
+ * exchange inside the frame loop).  A context can hold `num_shards` such ranks at once: the next
+ * mcrat_b200_set_photons() splits the list into that many contiguous, equal slot ranges, and the
+ * frame loop then advances every sub-shard concurrently (one scattering event per sub-shard and
+ * iteration).  Sub-shard s behaves exactly like a stand-alone context created with
+ * shard = cfg.shard + s whose list is that slot range (same Philox streams, same results).
+ * Default 1.  The step-by-step surface and the replay harness need num_shards == 1. */
+int mcrat_b200_set_num_shards(mcrat_b200_ctx *ctx, int num_shards);
+int mcrat_b200_num_shards(const mcrat_b200_ctx *ctx);
 /* parity harness: the uniform stream the reference's gsl_rng would hand out */
 int mcrat_b200_set_replay_uniforms(mcrat_b200_ctx *ctx, const double *u, size_t n);
 long long mcrat_b200_replay_consumed(mcrat_b200_ctx *ctx);
@@ -157,6 +167,10 @@ int mcrat_b200_average_photon_energy(mcrat_b200_ctx *ctx, double *avg_energy);
  * or when the host must act (stats->cs_host_pending, stats->error). */
 int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remaining_time, long long max_iters,
                          int find_nearest_grid_switch, mcrat_b200_frame_stats *stats);
+
+/* per-sub-shard view of the counters (cumulative since the shard layout was set) and its slot range */
+int mcrat_b200_get_shard_stats(mcrat_b200_ctx *ctx, int shard, mcrat_b200_frame_stats *stats, int *first_slot,
+                               int *num_slots);
 
 /* ---- measurement ------------------------------------------------------------------------------ */
 int mcrat_b200_get_kernel_times(mcrat_b200_ctx *ctx, mcrat_b200_kernel_times *out, int reset);

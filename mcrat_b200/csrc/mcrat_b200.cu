@@ -41,12 +41,14 @@ static_assert(sizeof(mcrat_photon) == 176, "struct photon layout (Src/mcrat.h:14
 // ------------------------------------------------------------------------------------------
 enum : unsigned char { F_MOVABLE = 1, F_RECALC = 2 };
 
-constexpr int MAX_DT = 64;         // pushes recorded by one event (1 + Klein-Nishina rejections)
+constexpr int MAX_DT = 16;         // pushes recorded by one event (1 + Klein-Nishina rejections)
 constexpr int BLOCKMIN_CAP = 4096; // per-block arg-min slots
+constexpr int MAX_SHARDS = 1024;
 constexpr int SCAN_THREADS = 128;
 constexpr int SCAN_P = 8;      // photons per thread held in registers
 constexpr int SCAN_TILE = 512; // cells per shared-memory stage
 constexpr int FEW_RMAX = 128;  // relocating photons handled per pass of the cell-parallel scan
+constexpr int RELOC_LIST_SCAN_MAX = 2048;
 
 struct PhotonCols {
     double *r0, *r1, *r2, *p0, *p1, *p2, *p3, *c0, *c1, *c2, *c3, *s0, *s1, *s2, *s3, *nscatt, *weight, *tau, *tts;
@@ -63,18 +65,25 @@ struct CellCols {
     double dom[6];
 };
 
-struct LoopState {
+// One sub-shard = one "rank" of the reference: a contiguous range of photon slots with its own
+// clock, its own time-ordered event sequence (shard-local arg-min, exactly as per MPI rank,
+// Src/mcrat.c:139-164) and its own Philox streams.
+struct ShardState {
     double time_now, remaining_time, last_time_step;
     double dt_list[MAX_DT];
-    int n_dt;
-    int pushed_slot;
-    int reloc_count[2];
-    unsigned long long iter;
-    long long scatt_cnt, reloc_total, slots, cell_evals, iters_done, max_iters;
-    int done, pause_cs, error, not_found;
-    int last_scattered_idx;
-    int head_idx;
     double head_tts;
+    unsigned long long iter;
+    long long scatt_cnt, reloc_total, slots, iters_done;
+    int n_dt, pushed_slot; // pushed_slot: global slot index
+    int done, pause_cs, counted_stopped;
+    int last_scattered_idx, head_idx; // global slot indices
+    int first, count;                 // slot range
+};
+
+struct GlobalState {
+    int reloc_count[2];
+    int error, not_found, n_stopped;
+    long long cell_evals, max_iters;
     unsigned long long replay_cursor, replay_base, replay_n;
     int abs_count, cs_scatt_count;
     double abs_weight;
@@ -83,35 +92,40 @@ struct LoopState {
 struct DevCtx {
     int dims, geom, stokes, tau_calc, cs, b_calc;
     double epsilon_b;
-    uint32_t k0, k1;
+    uint32_t k0, k1; // k1 is XORed with the sub-shard's global id
+    uint32_t shard_base;
     int replay;
     int cap;
+    int nshards, shard_size, blocks_per_shard;
     PhotonCols ph;
     CellCols cells;
     HotTable table;
-    LoopState *st;
+    ShardState *sh;
+    GlobalState *gs;
     // relocation scratch
     int *reloc_slot;
     double *reloc_h0, *reloc_h1, *reloc_h2;
     int *reloc_best;
-    int reloc_cap; // padded
-    // arg-min scratch: [0,BLOCKMIN_CAP) pass blocks, [BLOCKMIN_CAP, 2*BLOCKMIN_CAP) finish blocks
+    int reloc_cap;
+    // arg-min scratch, one entry per pass block
     double *bm_t;
     int *bm_i;
     // replay
     const double *replay_buf;
-    int *prefix_block; // per-256-block counts / offsets
+    int *prefix_block;
 };
 
 // ------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------
-// every kernel of the frame loop evaluates the same stop condition, so one iteration is
-// either executed completely or not at all
-__device__ __forceinline__ bool loop_stopped(const LoopState &st)
+// every kernel of the frame loop evaluates the same stop condition, so one iteration of a shard
+// is either executed completely or not at all
+__device__ __forceinline__ bool loop_stopped(const GlobalState &gs, const ShardState &sh)
 {
-    return st.done | st.pause_cs | (st.error != 0) | (st.max_iters >= 0 && st.iters_done >= st.max_iters);
+    return (gs.error != 0) | sh.done | sh.pause_cs | (gs.max_iters >= 0 && sh.iters_done >= gs.max_iters);
 }
+
+__device__ __forceinline__ int shard_of(const DevCtx &d, int slot) { return slot / d.shard_size; }
 
 __device__ __forceinline__ bool lex_less(double ta, int ia, double tb, int ib) { return (ta < tb) || (ta == tb && ia < ib); }
 
@@ -196,6 +210,20 @@ __device__ __forceinline__ double free_path_time(double tau, double xi)
     return mfp / C_LIGHT;
 }
 
+// pending pushes of a shard's last event, applied one by one: the reference pushes once per
+// candidate it tries (Src/mclib.c:1138, 1332) and FP addition is not associative
+__device__ __forceinline__ void apply_pushes(const ShardState &sh, int n_dt, double p0, double p1, double p2, double p3,
+                                             double &r0, double &r1, double &r2)
+{
+    double div = 1.0 / p0; // Src/mclib.c:1074-1080
+    for (int k = 0; k < n_dt; ++k) {
+        double t = sh.dt_list[k];
+        r0 += p1 * div * C_LIGHT * t;
+        r1 += p2 * div * C_LIGHT * t;
+        r2 += p3 * div * C_LIGHT * t;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // AoS <-> SoA (the boundary: `struct photon` records <-> device columns)
 // ------------------------------------------------------------------------------------------
@@ -262,96 +290,93 @@ __global__ void build_geo_kernel(int ndim3, int n, int n_padded, const double *c
 }
 
 // ------------------------------------------------------------------------------------------
-// K4+K2: fused push + locate re-check + free-path draw + block arg-min
+// K4+K2: fused push + locate re-check + free-path draw + block arg-min.
+// Grid = nshards x blocks_per_shard: a block never straddles two sub-shards.
 // ------------------------------------------------------------------------------------------
 constexpr int PASS_THREADS = 256;
 
 template <bool FUSE_MFP>
 __global__ void __launch_bounds__(PASS_THREADS) pass_kernel(DevCtx d, int sw, int parity)
 {
-    const LoopState &st = *d.st;
-    if (loop_stopped(st)) return;
-    const int n_dt = st.n_dt;
-    const int pushed = st.pushed_slot;
-    const unsigned long long iter = st.iter;
-    const int ndim3 = (d.dims == D_THREE);
-    if (blockIdx.x == 0 && threadIdx.x == 0) d.st->reloc_count[parity ^ 1] = 0;
-
+    const int s = blockIdx.x / d.blocks_per_shard;
+    const int b = blockIdx.x - s * d.blocks_per_shard;
+    const ShardState &sh = d.sh[s];
+    const GlobalState &gs = *d.gs;
+    if (blockIdx.x == 0 && threadIdx.x == 0) d.gs->reloc_count[parity ^ 1] = 0;
     double best_t = DBL_MAX;
     int best_i = INT_MAX;
-    const double default_t = 1e12 / C_LIGHT; // Src/mclib.c:620, 684-687
+    if (!loop_stopped(gs, sh)) {
+        const int n_dt = sh.n_dt;
+        const int pushed = sh.pushed_slot;
+        const unsigned long long iter = sh.iter;
+        const uint32_t k1 = d.k1 ^ (d.shard_base + (uint32_t)s);
+        const int ndim3 = (d.dims == D_THREE);
+        const double default_t = 1e12 / C_LIGHT; // Src/mclib.c:620, 684-687
 
-    for (int i = blockIdx.x * PASS_THREADS + threadIdx.x; i < d.cap; i += gridDim.x * PASS_THREADS) {
-        unsigned char flags = d.ph.flags[i];
-        int idx = d.ph.idx[i];
-        double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
-        // pending pushes of the previous event, Src/mclib.c:1054-1100 (applied one by one: the
-        // reference pushes once per candidate it tries, Src/mclib.c:1138, 1332)
-        if (n_dt > 0 && (flags & F_MOVABLE) && i != pushed) {
-            double p0 = d.ph.p0[i], p1 = d.ph.p1[i], p2 = d.ph.p2[i], p3 = d.ph.p3[i];
-            double div = 1.0 / p0;
-            for (int k = 0; k < n_dt; ++k) {
-                double t = st.dt_list[k];
-                r0 += p1 * div * C_LIGHT * t;
-                r1 += p2 * div * C_LIGHT * t;
-                r2 += p3 * div * C_LIGHT * t;
+        for (int j = b * PASS_THREADS + threadIdx.x; j < sh.count; j += d.blocks_per_shard * PASS_THREADS) {
+            const int i = sh.first + j;
+            unsigned char flags = d.ph.flags[i];
+            int idx = d.ph.idx[i];
+            double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
+            if (n_dt > 0 && (flags & F_MOVABLE) && i != pushed) {
+                apply_pushes(sh, n_dt, d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i], r0, r1, r2);
+                d.ph.r0[i] = r0;
+                d.ph.r1[i] = r1;
+                d.ph.r2[i] = r2;
             }
-            d.ph.r0[i] = r0;
-            d.ph.r1[i] = r1;
-            d.ph.r2[i] = r2;
-        }
-        // findContainingHydroCell, Src/mclib.c:469-597
-        double h0, h1, h2;
-        coord_to_hydro(d.dims, d.geom, r0, r1, r2, h0, h1, h2);
-        bool in_domain;
-        if (!ndim3)
-            in_domain = ((h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) && (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0])) &&
-                        (idx != -1);
-        else
-            in_domain = ((h2 < d.cells.dom[5]) && (h2 > d.cells.dom[4]) && (h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) &&
-                         (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0])) &&
-                        (idx != -1);
-        double t = default_t;
-        bool have_t = true;
-        if (in_domain) {
-            int blk = (sw == 0) ? idx : 0;
-            bool inb = in_cell(ndim3, d.cells, blk, h0, h1, h2);
-            if (d.cs && blk == 0) { // Src/mclib.c:510-515
-                if ((d.ph.c0[i]) + (d.ph.c1[i]) + (d.ph.c2[i]) + (d.ph.c3[i]) == 0) inb = false;
-            }
-            if (sw == 1 || !inb) {
-                int pos = atomicAdd(&d.st->reloc_count[parity], 1);
-                d.reloc_slot[pos] = i;
-                d.reloc_h0[pos] = h0;
-                d.reloc_h1[pos] = h1;
-                d.reloc_h2[pos] = h2;
-                d.reloc_best[pos] = INT_MAX;
-                have_t = false; // finish_kernel completes this photon
-            } else if (FUSE_MFP) {
-                // calcMeanFreePath, Src/mclib.c:657-687
-                double tau;
-                if (flags & F_RECALC) {
-                    CellState c = load_cell_state(d.cells, idx);
-                    int terr = 0;
-                    tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, d.ph.p1[i], d.ph.p2[i], d.ph.p3[i],
-                                        d.ph.c0[i], &terr);
-                    if (terr) d.st->error = MCRAT_B200_ERR_TABLE;
-                    d.ph.tau[i] = tau;
-                    d.ph.flags[i] = flags & ~F_RECALC;
-                } else {
-                    tau = d.ph.tau[i];
+            // findContainingHydroCell, Src/mclib.c:469-597
+            double h0, h1, h2;
+            coord_to_hydro(d.dims, d.geom, r0, r1, r2, h0, h1, h2);
+            bool in_domain;
+            if (!ndim3)
+                in_domain = ((h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) && (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0])) &&
+                            (idx != -1);
+            else
+                in_domain = ((h2 < d.cells.dom[5]) && (h2 > d.cells.dom[4]) && (h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) &&
+                             (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0])) &&
+                            (idx != -1);
+            double t = default_t;
+            bool have_t = true;
+            if (in_domain) {
+                int blk = (sw == 0) ? idx : 0;
+                bool inb = in_cell(ndim3, d.cells, blk, h0, h1, h2);
+                if (d.cs && blk == 0) { // Src/mclib.c:510-515
+                    if ((d.ph.c0[i]) + (d.ph.c1[i]) + (d.ph.c2[i]) + (d.ph.c3[i]) == 0) inb = false;
                 }
-                double xi = philox_mfp_uniform(d.k0, d.k1, iter, (uint32_t)i);
-                t = free_path_time(tau, xi);
+                if (sw == 1 || !inb) {
+                    int pos = atomicAdd(&d.gs->reloc_count[parity], 1);
+                    d.reloc_slot[pos] = i;
+                    d.reloc_h0[pos] = h0;
+                    d.reloc_h1[pos] = h1;
+                    d.reloc_h2[pos] = h2;
+                    d.reloc_best[pos] = INT_MAX;
+                    have_t = false; // finish_kernel completes this photon
+                } else if (FUSE_MFP) {
+                    // calcMeanFreePath, Src/mclib.c:657-687
+                    double tau;
+                    if (flags & F_RECALC) {
+                        CellState c = load_cell_state(d.cells, idx);
+                        int terr = 0;
+                        tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, d.ph.p1[i], d.ph.p2[i],
+                                            d.ph.p3[i], d.ph.c0[i], &terr);
+                        if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
+                        d.ph.tau[i] = tau;
+                        d.ph.flags[i] = flags & ~F_RECALC;
+                    } else {
+                        tau = d.ph.tau[i];
+                    }
+                    double xi = philox_mfp_uniform(d.k0, k1, iter, (uint32_t)j);
+                    t = free_path_time(tau, xi);
+                }
+            } else {
+                if (idx != -1) d.ph.idx[i] = -1; // Src/mclib.c:589-595
             }
-        } else {
-            if (idx != -1) d.ph.idx[i] = -1; // Src/mclib.c:589-595
-        }
-        if (FUSE_MFP && have_t) {
-            d.ph.tts[i] = t;
-            if (lex_less(t, i, best_t, best_i)) {
-                best_t = t;
-                best_i = i;
+            if (FUSE_MFP && have_t) {
+                d.ph.tts[i] = t;
+                if (lex_less(t, i, best_t, best_i)) {
+                    best_t = t;
+                    best_i = i;
+                }
             }
         }
     }
@@ -368,22 +393,14 @@ __global__ void __launch_bounds__(PASS_THREADS) pass_kernel(DevCtx d, int sw, in
 // materialisation of pending event pushes before a download
 __global__ void __launch_bounds__(PASS_THREADS) flush_push_kernel(DevCtx d)
 {
-    const LoopState &st = *d.st;
-    const int n_dt = st.n_dt;
-    const int pushed = st.pushed_slot;
-    if (n_dt == 0) return;
     for (int i = blockIdx.x * PASS_THREADS + threadIdx.x; i < d.cap; i += gridDim.x * PASS_THREADS) {
+        const ShardState &sh = d.sh[shard_of(d, i)];
+        const int n_dt = sh.n_dt;
+        if (n_dt == 0) continue;
         unsigned char flags = d.ph.flags[i];
-        if ((flags & F_MOVABLE) && i != pushed) {
-            double p0 = d.ph.p0[i], p1 = d.ph.p1[i], p2 = d.ph.p2[i], p3 = d.ph.p3[i];
+        if ((flags & F_MOVABLE) && i != sh.pushed_slot) {
             double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
-            double div = 1.0 / p0;
-            for (int k = 0; k < n_dt; ++k) {
-                double t = st.dt_list[k];
-                r0 += p1 * div * C_LIGHT * t;
-                r1 += p2 * div * C_LIGHT * t;
-                r2 += p3 * div * C_LIGHT * t;
-            }
+            apply_pushes(sh, n_dt, d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i], r0, r1, r2);
             d.ph.r0[i] = r0;
             d.ph.r1[i] = r1;
             d.ph.r2[i] = r2;
@@ -393,15 +410,19 @@ __global__ void __launch_bounds__(PASS_THREADS) flush_push_kernel(DevCtx d)
 
 __global__ void clear_push_kernel(DevCtx d)
 {
-    d.st->n_dt = 0;
-    d.st->pushed_slot = -1;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < d.nshards; s += gridDim.x * blockDim.x) {
+        d.sh[s].n_dt = 0;
+        d.sh[s].pushed_slot = -1;
+    }
 }
 
 __global__ void set_push_kernel(DevCtx d, double t)
 {
-    d.st->dt_list[0] = t;
-    d.st->n_dt = 1;
-    d.st->pushed_slot = -1;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < d.nshards; s += gridDim.x * blockDim.x) {
+        d.sh[s].dt_list[0] = t;
+        d.sh[s].n_dt = 1;
+        d.sh[s].pushed_slot = -1;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -442,11 +463,11 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 }
 
 template <int NDIM3>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(DevCtx d, int parity, int tiles_per_chunk, int count_override)
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(DevCtx d, int parity, int tiles_per_chunk)
 {
-    const LoopState &st = *d.st;
-    if (loop_stopped(st)) return;
-    const int count = (count_override >= 0) ? count_override : st.reloc_count[parity];
+    const GlobalState &gs = *d.gs;
+    if (gs.error != 0) return;
+    const int count = gs.reloc_count[parity];
     const int pbase = blockIdx.x * (SCAN_THREADS * SCAN_P);
     if (pbase >= count) return;
 
@@ -524,7 +545,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(DevCtx d, int parity
     }
     if (threadIdx.x == 0 && blockIdx.y == 0) {
         int nph = min(count - pbase, SCAN_THREADS * SCAN_P);
-        atomicAdd((unsigned long long *)&d.st->cell_evals, (unsigned long long)nph * (unsigned long long)d.cells.n);
+        atomicAdd((unsigned long long *)&d.gs->cell_evals, (unsigned long long)nph * (unsigned long long)d.cells.n);
     }
 }
 
@@ -532,9 +553,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(DevCtx d, int parity
 template <int NDIM3>
 __global__ void __launch_bounds__(256) scan_few_kernel(DevCtx d, int parity)
 {
-    const LoopState &st = *d.st;
-    if (loop_stopped(st)) return;
-    const int count = st.reloc_count[parity];
+    const GlobalState &gs = *d.gs;
+    if (gs.error != 0) return;
+    const int count = gs.reloc_count[parity];
     if (count == 0) return;
     __shared__ double sx0[FEW_RMAX], sx1[FEW_RMAX], sx2[FEW_RMAX];
     __shared__ int sbest[FEW_RMAX];
@@ -566,7 +587,7 @@ __global__ void __launch_bounds__(256) scan_few_kernel(DevCtx d, int parity)
             if (sbest[j] != INT_MAX) atomicMin(&d.reloc_best[base + j], sbest[j]);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
-        atomicAdd((unsigned long long *)&d.st->cell_evals, (unsigned long long)count * (unsigned long long)d.cells.n);
+        atomicAdd((unsigned long long *)&d.gs->cell_evals, (unsigned long long)count * (unsigned long long)d.cells.n);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -578,16 +599,15 @@ constexpr int FIN_THREADS = 128;
 template <bool FUSE_MFP>
 __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(DevCtx d, int sw, int parity)
 {
-    const LoopState &st = *d.st;
-    if (loop_stopped(st)) return;
-    const int count = st.reloc_count[parity];
-    const unsigned long long iter = st.iter;
-    double best_t = DBL_MAX;
-    int best_i = INT_MAX;
-    int found = 0, missing = 0;
+    const GlobalState &gs = *d.gs;
+    if (gs.error != 0) return;
+    const int count = gs.reloc_count[parity];
+    int missing = 0;
     for (int j = blockIdx.x * FIN_THREADS + threadIdx.x; j < count; j += gridDim.x * FIN_THREADS) {
         const int i = d.reloc_slot[j];
         const int b = d.reloc_best[j];
+        const int s = shard_of(d, i);
+        ShardState &sh = d.sh[s];
         double t = 1e12 / C_LIGHT;
         if (b == INT_MAX) {
             d.ph.idx[i] = -1; // Src/mclib.c:536, 581-584
@@ -606,36 +626,23 @@ __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(DevCtx d, int sw, i
             d.ph.c3[i] = pc[3];
             int terr = 0;
             double tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, p[1], p[2], p[3], pc[0], &terr);
-            if (terr) d.st->error = MCRAT_B200_ERR_TABLE;
+            if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
             d.ph.tau[i] = tau;
             d.ph.flags[i] = d.ph.flags[i] & ~F_RECALC;
-            found++;
+            if (sw == 0) atomicAdd((unsigned long long *)&sh.reloc_total, 1ull); // Src/mclib.c:579, 608-611
             if (FUSE_MFP) {
-                double xi = philox_mfp_uniform(d.k0, d.k1, iter, (uint32_t)i);
+                const uint32_t k1 = d.k1 ^ (d.shard_base + (uint32_t)s);
+                double xi = philox_mfp_uniform(d.k0, k1, sh.iter, (uint32_t)(i - sh.first));
                 t = free_path_time(tau, xi);
             }
         }
-        if (FUSE_MFP) {
-            d.ph.tts[i] = t;
-            if (lex_less(t, i, best_t, best_i)) {
-                best_t = t;
-                best_i = i;
-            }
-        }
+        if (FUSE_MFP) d.ph.tts[i] = t;
     }
-    if (found && sw == 0) atomicAdd((unsigned long long *)&d.st->reloc_total, (unsigned long long)found); // :608-611
-    if (missing) atomicAdd(&d.st->not_found, missing);
-    if (FUSE_MFP) {
-        block_argmin<FIN_THREADS>(best_t, best_i);
-        if (threadIdx.x == 0) {
-            d.bm_t[BLOCKMIN_CAP + blockIdx.x] = best_t;
-            d.bm_i[BLOCKMIN_CAP + blockIdx.x] = best_i;
-        }
-    }
+    if (missing) atomicAdd(&d.gs->not_found, missing);
 }
 
 // ------------------------------------------------------------------------------------------
-// unfused calcMeanFreePath (step API and replay harness), Src/mclib.c:617-714
+// unfused calcMeanFreePath (step API and replay harness; single shard), Src/mclib.c:617-714
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mfp_count_kernel(DevCtx d)
 {
@@ -655,16 +662,17 @@ __global__ void mfp_scan_kernel(DevCtx d, int nblocks)
             d.prefix_block[b] = (int)run;
             run += (unsigned long long)c;
         }
-        d.st->replay_base = d.st->replay_cursor;
-        d.st->replay_cursor += run;
-        if (d.st->replay_cursor > d.st->replay_n) d.st->error = MCRAT_B200_ERR_REPLAY;
+        d.gs->replay_base = d.gs->replay_cursor;
+        d.gs->replay_cursor += run;
+        if (d.gs->replay_cursor > d.gs->replay_n) d.gs->error = MCRAT_B200_ERR_REPLAY;
     }
 }
 
-__global__ void __launch_bounds__(256) mfp_kernel(DevCtx d)
+__global__ void __launch_bounds__(256) mfp_kernel(DevCtx d, int write_blockmin)
 {
-    const LoopState &st = *d.st;
-    if (st.error != 0) return;
+    const GlobalState &gs = *d.gs;
+    const ShardState &sh = d.sh[0];
+    if (gs.error != 0) return;
     __shared__ int warp_off[8];
     const int i = blockIdx.x * 256 + threadIdx.x;
     const bool valid = i < d.cap;
@@ -687,7 +695,7 @@ __global__ void __launch_bounds__(256) mfp_kernel(DevCtx d)
             int terr = 0;
             tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, d.ph.r0[i], d.ph.r1[i], d.ph.p1[i], d.ph.p2[i],
                                 d.ph.p3[i], d.ph.c0[i], &terr);
-            if (terr) d.st->error = MCRAT_B200_ERR_TABLE;
+            if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
             d.ph.tau[i] = tau;
             d.ph.flags[i] = flags & ~F_RECALC;
         } else {
@@ -695,18 +703,18 @@ __global__ void __launch_bounds__(256) mfp_kernel(DevCtx d)
         }
         double xi;
         if (d.replay)
-            xi = d.replay_buf[st.replay_base + (unsigned long long)d.prefix_block[blockIdx.x] + (unsigned long long)off];
+            xi = d.replay_buf[gs.replay_base + (unsigned long long)d.prefix_block[blockIdx.x] + (unsigned long long)off];
         else
-            xi = philox_mfp_uniform(d.k0, d.k1, st.iter, (uint32_t)i);
+            xi = philox_mfp_uniform(d.k0, d.k1 ^ d.shard_base, sh.iter, (uint32_t)i);
         t = free_path_time(tau, xi);
     }
     int bi = valid ? i : INT_MAX;
     double bt = valid ? t : DBL_MAX;
     if (valid) d.ph.tts[i] = t;
     block_argmin<256>(bt, bi);
-    if (threadIdx.x == 0) {
-        d.bm_t[blockIdx.x % BLOCKMIN_CAP] = bt; // (callers keep nblocks <= BLOCKMIN_CAP or reduce in rounds)
-        d.bm_i[blockIdx.x % BLOCKMIN_CAP] = bi;
+    if (threadIdx.x == 0 && write_blockmin) {
+        d.bm_t[blockIdx.x] = bt;
+        d.bm_i[blockIdx.x] = bi;
     }
 }
 
@@ -730,33 +738,18 @@ __global__ void __launch_bounds__(256) argmin_all_kernel(DevCtx d)
 }
 
 // ------------------------------------------------------------------------------------------
-// K3: event kernel -- global arg-min, then photonEvent (Src/mclib.c:1107-1356) and the driver's
-// bookkeeping (Src/mcrat.c:777-846).  One block; lane 0 runs the serial scatter.
+// K3: event kernel -- shard-local arg-min, then photonEvent (Src/mclib.c:1107-1356) and the
+// driver's bookkeeping (Src/mcrat.c:777-846).  One block per sub-shard; lane 0 runs the scatter.
 // ------------------------------------------------------------------------------------------
-constexpr int EVT_THREADS = 256;
+constexpr int EVT_THREADS = 128;
 
-struct EventShared {
-    double cand_t;
-    int cand_i;
-    int need_next;
-    int finished;
-};
-
-__device__ void scatter_candidate(DevCtx &d, LoopState &st, EventRng &rng, int i, int n_dt, bool &event_did_occur)
+__device__ void scatter_candidate(DevCtx &d, ShardState &st, EventRng &rng, int i, int n_dt, bool &event_did_occur)
 {
     // the candidate's own position after every push of this event so far (Src/mclib.c:1138)
     const unsigned char flags = d.ph.flags[i];
     double p[4] = {d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i]};
     double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
-    if (flags & F_MOVABLE) {
-        double div = 1.0 / p[0];
-        for (int k = 0; k < n_dt; ++k) {
-            double t = st.dt_list[k];
-            r0 += p[1] * div * C_LIGHT * t;
-            r1 += p[2] * div * C_LIGHT * t;
-            r2 += p[3] * div * C_LIGHT * t;
-        }
-    }
+    if (flags & F_MOVABLE) apply_pushes(st, n_dt, p[0], p[1], p[2], p[3], r0, r1, r2);
     const int index = d.ph.idx[i];
     CellState c = load_cell_state(d.cells, index);
     double fb[3];
@@ -792,36 +785,70 @@ __device__ void scatter_candidate(DevCtx &d, LoopState &st, EventRng &rng, int i
 }
 
 // step_mode 0: frame loop (driver bookkeeping included); 1: photonEvent only (dt_max given)
-__global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int nb_pass, int nb_fin, int step_mode,
+// blockmin_valid: the pass wrote per-block minima for this iteration (fused path / step API)
+__global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int parity, int nb_per_shard, int step_mode,
                                                             double dt_max_arg)
 {
-    LoopState &st = *d.st;
-    if (loop_stopped(st)) return;
+    const int s = blockIdx.x;
+    ShardState &st = d.sh[s];
+    GlobalState &gs = *d.gs;
+    if (loop_stopped(gs, st)) return;
 
-    __shared__ EventShared sh;
-    // ---- head of the time order: reduce the per-block minima ----
+    __shared__ double sh_cand_t;
+    __shared__ int sh_cand_i, sh_finished;
+    // ---- head of this shard's time order ----
     double bt = DBL_MAX;
     int bi = INT_MAX;
-    for (int k = threadIdx.x; k < nb_pass; k += EVT_THREADS)
-        if (lex_less(d.bm_t[k], d.bm_i[k], bt, bi)) {
-            bt = d.bm_t[k];
-            bi = d.bm_i[k];
+    if (nb_per_shard > 0) {
+        for (int k = threadIdx.x; k < nb_per_shard; k += EVT_THREADS) {
+            const int q = s * nb_per_shard + k;
+            if (lex_less(d.bm_t[q], d.bm_i[q], bt, bi)) {
+                bt = d.bm_t[q];
+                bi = d.bm_i[q];
+            }
         }
-    for (int k = threadIdx.x; k < nb_fin; k += EVT_THREADS)
-        if (lex_less(d.bm_t[BLOCKMIN_CAP + k], d.bm_i[BLOCKMIN_CAP + k], bt, bi)) {
-            bt = d.bm_t[BLOCKMIN_CAP + k];
-            bi = d.bm_i[BLOCKMIN_CAP + k];
+        // photons relocated in this iteration got their time in finish_kernel
+        const int R = gs.reloc_count[parity];
+        if (R > 0 && R <= RELOC_LIST_SCAN_MAX) {
+            for (int j = threadIdx.x; j < R; j += EVT_THREADS) {
+                const int i = d.reloc_slot[j];
+                if (i >= st.first && i < st.first + st.count) {
+                    double t = d.ph.tts[i];
+                    if (lex_less(t, i, bt, bi)) {
+                        bt = t;
+                        bi = i;
+                    }
+                }
+            }
+        } else if (R > 0) {
+            for (int j = threadIdx.x; j < st.count; j += EVT_THREADS) {
+                const int i = st.first + j;
+                double t = d.ph.tts[i];
+                if (lex_less(t, i, bt, bi)) {
+                    bt = t;
+                    bi = i;
+                }
+            }
         }
+    } else {
+        for (int j = threadIdx.x; j < st.count; j += EVT_THREADS) {
+            const int i = st.first + j;
+            double t = d.ph.tts[i];
+            if (lex_less(t, i, bt, bi)) {
+                bt = t;
+                bi = i;
+            }
+        }
+    }
     block_argmin<EVT_THREADS>(bt, bi);
 
     __shared__ EventRng rng_sh;
     __shared__ double old_scatt_time, scatt_time, dt_max;
     __shared__ int n_dt, ph_index;
     if (threadIdx.x == 0) {
-        sh.cand_t = bt;
-        sh.cand_i = bi;
-        sh.finished = 0;
-        sh.need_next = 0;
+        sh_cand_t = bt;
+        sh_cand_i = bi;
+        sh_finished = 0;
         st.head_idx = bi;
         st.head_tts = bt;
         dt_max = (step_mode == 0) ? st.remaining_time : dt_max_arg;
@@ -833,14 +860,14 @@ __global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int nb_pas
         st.pushed_slot = -1;
         rng_sh.replay = d.replay;
         rng_sh.k0 = d.k0;
-        rng_sh.k1 = d.k1;
+        rng_sh.k1 = d.k1 ^ (d.shard_base + (uint32_t)s);
         rng_sh.iter = st.iter;
         rng_sh.draw = 0;
         rng_sh.buf = d.replay_buf;
-        rng_sh.pos = st.replay_cursor;
-        rng_sh.n = st.replay_n;
+        rng_sh.pos = gs.replay_cursor;
+        rng_sh.n = gs.replay_n;
         rng_sh.exhausted = 0;
-        if (step_mode == 0) st.slots += d.cap;
+        if (step_mode == 0) st.slots += st.count;
         if (step_mode == 0 && !(bt < dt_max)) {
             // Src/mcrat.c:834-846: nothing scatters before the next hydro frame
             st.time_now += st.remaining_time;
@@ -851,17 +878,21 @@ __global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int nb_pas
             st.done = 1;
             st.iter += 1;
             st.iters_done += 1;
-            sh.finished = 1;
+            if (!st.counted_stopped) {
+                st.counted_stopped = 1;
+                atomicAdd(&gs.n_stopped, 1);
+            }
+            sh_finished = 1;
         }
     }
     __syncthreads();
-    if (sh.finished) return;
+    if (sh_finished) return;
 
     // ---- photonEvent: walk candidates in ascending time, Src/mclib.c:1128-1339 ----
     while (true) {
         if (threadIdx.x == 0) {
-            const int i = sh.cand_i;
-            const double t = sh.cand_t;
+            const int i = sh_cand_i;
+            const double t = sh_cand_t;
             bool event = false;
             ph_index = i;
             scatt_time = t;
@@ -870,7 +901,7 @@ __global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int nb_pas
                     st.dt_list[n_dt] = t - old_scatt_time;
                     n_dt++;
                 } else {
-                    st.error = MCRAT_B200_ERR_STATE;
+                    gs.error = MCRAT_B200_ERR_STATE;
                     event = true;
                 }
                 if (!event) {
@@ -885,18 +916,18 @@ __global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int nb_pas
                 event = true;
             }
             old_scatt_time = scatt_time;
-            sh.need_next = event ? 0 : 1;
-            sh.finished = event ? 1 : 0;
+            sh_finished = event ? 1 : 0;
         }
         __syncthreads();
-        if (sh.finished) break;
-        // Klein-Nishina rejection (rare): next entry of the time order after (cand_t, cand_i)
+        if (sh_finished) break;
+        // Klein-Nishina rejection (rare): next entry of this shard's time order after (cand_t, cand_i)
         {
-            const double pt = sh.cand_t;
-            const int pi = sh.cand_i;
+            const double pt = sh_cand_t;
+            const int pi = sh_cand_i;
             double nt = DBL_MAX;
             int ni = INT_MAX;
-            for (int k = threadIdx.x; k < d.cap; k += EVT_THREADS) {
+            for (int j = threadIdx.x; j < st.count; j += EVT_THREADS) {
+                const int k = st.first + j;
                 double t = d.ph.tts[k];
                 if (lex_less(pt, pi, t, k) && lex_less(t, k, nt, ni)) {
                     nt = t;
@@ -906,14 +937,14 @@ __global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int nb_pas
             block_argmin<EVT_THREADS>(nt, ni);
             if (threadIdx.x == 0) {
                 if (ni == INT_MAX) { // list exhausted (Src/mclib.c:1128 loop bound)
-                    sh.finished = 1;
+                    sh_finished = 1;
                 } else {
-                    sh.cand_t = nt;
-                    sh.cand_i = ni;
+                    sh_cand_t = nt;
+                    sh_cand_i = ni;
                 }
             }
             __syncthreads();
-            if (sh.finished) break;
+            if (sh_finished) break;
         }
     }
 
@@ -922,9 +953,11 @@ __global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int nb_pas
         st.last_scattered_idx = ph_index;
         st.last_time_step = scatt_time;
         if (d.replay) {
-            st.replay_cursor = rng_sh.pos;
-            if (rng_sh.exhausted) st.error = MCRAT_B200_ERR_REPLAY;
+            gs.replay_cursor = rng_sh.pos;
+            if (rng_sh.exhausted) gs.error = MCRAT_B200_ERR_REPLAY;
         }
+        st.iter += 1;
+        st.iters_done += 1;
         if (step_mode == 0) {
             st.time_now += scatt_time;
             st.remaining_time -= scatt_time;
@@ -934,13 +967,15 @@ __global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int nb_pas
                 if (d.ph.weight[ph_index] != 0) d.ph.flags[ph_index] |= F_MOVABLE;
                 st.pause_cs = 1;
             }
+            if ((st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters)) && !st.counted_stopped) {
+                st.counted_stopped = 1;
+                atomicAdd(&gs.n_stopped, 1);
+            }
         }
-        st.iter += 1;
-        st.iters_done += 1;
     }
 }
 
-// head of the time order only (step API calcMeanFreePath)
+// head of the time order only (step API calcMeanFreePath; single shard)
 __global__ void __launch_bounds__(EVT_THREADS) head_kernel(DevCtx d, int nb)
 {
     double bt = DBL_MAX;
@@ -952,8 +987,8 @@ __global__ void __launch_bounds__(EVT_THREADS) head_kernel(DevCtx d, int nb)
         }
     block_argmin<EVT_THREADS>(bt, bi);
     if (threadIdx.x == 0) {
-        d.st->head_idx = bi;
-        d.st->head_tts = bt;
+        d.sh[0].head_idx = bi;
+        d.sh[0].head_tts = bt;
     }
 }
 
@@ -1024,9 +1059,9 @@ __global__ void __launch_bounds__(256) cs_absorb_kernel(DevCtx d)
             s += s_sc[k];
             w += s_w[k];
         }
-        if (a) atomicAdd(&d.st->abs_count, a);
-        if (s) atomicAdd(&d.st->cs_scatt_count, s);
-        if (w != 0) atomicAdd(&d.st->abs_weight, w);
+        if (a) atomicAdd(&d.gs->abs_count, a);
+        if (s) atomicAdd(&d.gs->cs_scatt_count, s);
+        if (w != 0) atomicAdd(&d.gs->abs_weight, w);
     }
 }
 
@@ -1131,8 +1166,10 @@ struct mcrat_b200_ctx {
     bool have_hydro, have_photons;
     int pass_parity;
     int last_nb_mfp;
+    int want_shards;    // sub-shards requested for the next set_photons
     long long launches; // kernels launched through this context
-    LoopState *st_host; // pinned
+    GlobalState *gs_host;          // pinned
+    std::vector<ShardState> sh_host;
     double *replay_dev;
     size_t replay_cap;
     double *table_dev;
@@ -1211,6 +1248,11 @@ API int mcrat_b200_device_count(void)
 
 API const char *mcrat_b200_last_error(const mcrat_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+static size_t scan_smem_bytes(int ndim3)
+{
+    return 2 * SCAN_TILE * sizeof(double4) + (ndim3 ? 2 * SCAN_TILE * sizeof(double2) : 0) + 2 * sizeof(uint64_t);
+}
+
 API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
 {
     if (!cfg || !out) {
@@ -1254,11 +1296,13 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
     ctx->have_hydro = ctx->have_photons = false;
     ctx->pass_parity = 0;
     ctx->last_nb_mfp = 0;
+    ctx->want_shards = 1;
     ctx->launches = 0;
     ctx->replay_dev = nullptr;
     ctx->replay_cap = 0;
     ctx->table_dev = nullptr;
     ctx->stat_dev = nullptr;
+    ctx->gs_host = nullptr;
     auto bail = [&](cudaError_t err, const char *what) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
         delete ctx;
@@ -1277,7 +1321,7 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
     }
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
-    if ((e = cudaMallocHost((void **)&ctx->st_host, sizeof(LoopState))) != cudaSuccess) return bail(e, "cudaMallocHost");
+    if ((e = cudaMallocHost((void **)&ctx->gs_host, sizeof(GlobalState))) != cudaSuccess) return bail(e, "cudaMallocHost");
     DevCtx &d = ctx->d;
     d.dims = cfg->dimensions;
     d.geom = cfg->geometry;
@@ -1287,12 +1331,20 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
     d.b_calc = cfg->b_field_calc;
     d.epsilon_b = cfg->epsilon_b;
     d.k0 = (uint32_t)cfg->seed ^ 0x4D435261u;
-    d.k1 = (uint32_t)(cfg->seed >> 32) ^ cfg->shard;
+    d.k1 = (uint32_t)(cfg->seed >> 32);
+    d.shard_base = cfg->shard;
     d.replay = cfg->rng_mode == MCRAT_RNG_REPLAY ? 1 : 0;
-    if ((e = dev_alloc(ctx->misc_allocs, &d.st, 1)) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMemsetAsync(d.st, 0, sizeof(LoopState), ctx->stream)) != cudaSuccess) return bail(e, "cudaMemset");
-    if ((e = dev_alloc(ctx->misc_allocs, &d.bm_t, 2 * BLOCKMIN_CAP)) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = dev_alloc(ctx->misc_allocs, &d.bm_i, 2 * BLOCKMIN_CAP)) != cudaSuccess) return bail(e, "cudaMalloc");
+    d.nshards = 1;
+    d.shard_size = 1;
+    d.blocks_per_shard = 1;
+    if ((e = dev_alloc(ctx->misc_allocs, &d.gs, 1)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMemsetAsync(d.gs, 0, sizeof(GlobalState), ctx->stream)) != cudaSuccess) return bail(e, "cudaMemset");
+    if ((e = dev_alloc(ctx->misc_allocs, &d.sh, MAX_SHARDS)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMemsetAsync(d.sh, 0, sizeof(ShardState) * MAX_SHARDS, ctx->stream)) != cudaSuccess) return bail(e, "cudaMemset");
+    ctx->sh_host.assign(MAX_SHARDS, ShardState());
+    memset(ctx->sh_host.data(), 0, sizeof(ShardState) * MAX_SHARDS);
+    if ((e = dev_alloc(ctx->misc_allocs, &d.bm_t, BLOCKMIN_CAP)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = dev_alloc(ctx->misc_allocs, &d.bm_i, BLOCKMIN_CAP)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = dev_alloc(ctx->misc_allocs, &ctx->stat_dev, 1024)) != cudaSuccess) return bail(e, "cudaMalloc");
     // interpolation grids, Src/hot_x_section.c:470-480
     {
@@ -1311,11 +1363,9 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
         d.table.za = g + N_PH_E + 1 + N_T + 1;
         ctx->table_dev = g + N_PH_E + 1 + N_T + 1;
     }
-    if ((e = cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(2 * SCAN_TILE * sizeof(double4) + 16))) != cudaSuccess)
+    if ((e = cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(0))) != cudaSuccess)
         return bail(e, "cudaFuncSetAttribute");
-    if ((e = cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(2 * SCAN_TILE * (sizeof(double4) + sizeof(double2)) + 16))) != cudaSuccess)
+    if ((e = cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(1))) != cudaSuccess)
         return bail(e, "cudaFuncSetAttribute");
     *out = ctx;
     return MCRAT_B200_OK;
@@ -1330,7 +1380,7 @@ API void mcrat_b200_destroy(mcrat_b200_ctx *ctx)
     free_pool(ctx->misc_allocs);
     if (ctx->aos_dev) cudaFree(ctx->aos_dev);
     if (ctx->replay_dev) cudaFree(ctx->replay_dev);
-    if (ctx->st_host) cudaFreeHost(ctx->st_host);
+    if (ctx->gs_host) cudaFreeHost(ctx->gs_host);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -1343,9 +1393,17 @@ API int mcrat_b200_synchronize(mcrat_b200_ctx *ctx)
     return MCRAT_B200_OK;
 }
 
+static int fetch_global(mcrat_b200_ctx *ctx)
+{
+    CK(cudaMemcpyAsync(ctx->gs_host, ctx->d.gs, sizeof(GlobalState), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MCRAT_B200_OK;
+}
+
 static int fetch_state(mcrat_b200_ctx *ctx)
 {
-    CK(cudaMemcpyAsync(ctx->st_host, ctx->d.st, sizeof(LoopState), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->gs_host, ctx->d.gs, sizeof(GlobalState), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->sh_host.data(), ctx->d.sh, sizeof(ShardState) * ctx->d.nshards, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return MCRAT_B200_OK;
 }
@@ -1377,15 +1435,26 @@ API int mcrat_b200_set_hydro(mcrat_b200_ctx *ctx, int n, const double *const *fi
     if (!ctx || !fields || !domains || n < 0) return ctx ? fail(ctx, MCRAT_B200_ERR_ARG, "set_hydro: bad argument") : MCRAT_B200_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     CK(cudaStreamSynchronize(ctx->stream));
-    free_pool(ctx->cell_allocs);
     CellCols &c = ctx->d.cells;
     const int ndim3 = ctx->d.dims == D_THREE;
+    const int n_padded = n > 0 ? ((n + SCAN_TILE - 1) / SCAN_TILE) * SCAN_TILE : SCAN_TILE;
+    // a frame with the same number of cells reuses the device arrays (one frame per step in the driver)
+    if (!ctx->have_hydro || c.n != n) {
+        free_pool(ctx->cell_allocs);
+        double *cols[19];
+        for (int f = 0; f < 19; ++f) CK(dev_alloc(ctx->cell_allocs, &cols[f], (size_t)n));
+        double4 *geoA = nullptr;
+        double2 *geoB = nullptr;
+        CK(dev_alloc(ctx->cell_allocs, &geoA, (size_t)n_padded));
+        CK(dev_alloc(ctx->cell_allocs, &geoB, (size_t)(ndim3 ? n_padded : 1)));
+        c.geoA = geoA;
+        c.geoB = geoB;
+    }
     c.n = n;
-    c.n_padded = ((n + SCAN_TILE - 1) / SCAN_TILE) * SCAN_TILE;
-    if (c.n_padded == 0) c.n_padded = SCAN_TILE;
+    c.n_padded = n_padded;
     double *cols[19];
     for (int f = 0; f < 19; ++f) {
-        CK(dev_alloc(ctx->cell_allocs, &cols[f], (size_t)n));
+        cols[f] = (double *)ctx->cell_allocs[f];
         if (fields[f])
             CK(cudaMemcpyAsync(cols[f], fields[f], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         else
@@ -1395,15 +1464,9 @@ API int mcrat_b200_set_hydro(mcrat_b200_ctx *ctx, int n, const double *const *fi
     c.v0 = cols[8]; c.v1 = cols[9]; c.v2 = cols[10];
     c.dens = cols[11]; c.dens_lab = cols[12]; c.temp = cols[14]; c.gamma = cols[15];
     c.B0 = cols[16]; c.B1 = cols[17]; c.B2 = cols[18];
-    double4 *geoA = nullptr;
-    double2 *geoB = nullptr;
-    CK(dev_alloc(ctx->cell_allocs, &geoA, (size_t)c.n_padded));
-    CK(dev_alloc(ctx->cell_allocs, &geoB, (size_t)(ndim3 ? c.n_padded : 1)));
-    build_geo_kernel<<<grid_for(ctx, c.n_padded, 256, 8), 256, 0, ctx->stream>>>(ndim3, n, c.n_padded, cols[0], cols[1], cols[2],
-                                                                               cols[3], cols[4], cols[5], geoA, geoB);
+    build_geo_kernel<<<grid_for(ctx, c.n_padded, 256, 8), 256, 0, ctx->stream>>>(
+        ndim3, n, c.n_padded, cols[0], cols[1], cols[2], cols[3], cols[4], cols[5], (double4 *)c.geoA, (double2 *)c.geoB);
     if (int rc = check_launch(ctx, "build_geo_kernel")) return rc;
-    c.geoA = geoA;
-    c.geoB = geoB;
     for (int k = 0; k < 6; ++k) c.dom[k] = domains[k];
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_hydro = true;
@@ -1450,19 +1513,67 @@ static int ensure_photon_capacity(mcrat_b200_ctx *ctx, int n)
     return MCRAT_B200_OK;
 }
 
+API int mcrat_b200_set_num_shards(mcrat_b200_ctx *ctx, int num_shards)
+{
+    if (!ctx) return MCRAT_B200_ERR_ARG;
+    if (num_shards < 1 || num_shards > MAX_SHARDS) return fail(ctx, MCRAT_B200_ERR_ARG, "set_num_shards: 1..1024 sub-shards");
+    if (num_shards > 1 && ctx->d.replay) return fail(ctx, MCRAT_B200_ERR_ARG, "the replay harness drives a single shard");
+    if (num_shards > 1 && ctx->d.cs)
+        return fail(ctx, MCRAT_B200_ERR_ARG, "sub-shards need CYCLOSYNCHROTRON_SWITCH OFF (host-side emission re-packs the list)");
+    ctx->want_shards = num_shards;
+    return MCRAT_B200_OK;
+}
+
+API int mcrat_b200_num_shards(const mcrat_b200_ctx *ctx) { return ctx ? ctx->d.nshards : 0; }
+
+// slot ranges of the sub-shards: contiguous, equal size (the last one may be shorter)
+static int layout_shards(mcrat_b200_ctx *ctx, int n)
+{
+    DevCtx &d = ctx->d;
+    int S = ctx->want_shards;
+    if (S > n) S = n > 0 ? n : 1;
+    const int size = n > 0 ? (n + S - 1) / S : 1;
+    S = n > 0 ? (n + size - 1) / size : 1;
+    if (int rc = fetch_state(ctx)) return rc; // keep per-shard iteration counters (RNG stream positions)
+    const bool relayout = (S != d.nshards) || (size != d.shard_size);
+    d.nshards = S;
+    d.shard_size = size;
+    int bps = (size + PASS_THREADS - 1) / PASS_THREADS;
+    int cap_sm = (ctx->num_sms * 8) / S;
+    if (cap_sm < 1) cap_sm = 1;
+    if (bps > cap_sm) bps = cap_sm;
+    if (bps > BLOCKMIN_CAP / S) bps = BLOCKMIN_CAP / S;
+    if (bps < 1) bps = 1;
+    d.blocks_per_shard = bps;
+    for (int s = 0; s < S; ++s) {
+        ShardState &sh = ctx->sh_host[s];
+        if (relayout) {
+            unsigned long long it = (s == 0) ? sh.iter : 0;
+            memset(&sh, 0, sizeof(sh));
+            sh.iter = it;
+        }
+        sh.first = s * size;
+        sh.count = (s * size + size <= n) ? size : (n - s * size);
+        if (sh.count < 0) sh.count = 0;
+        sh.n_dt = 0;
+        sh.pushed_slot = -1;
+    }
+    CK(cudaMemcpyAsync(d.sh, ctx->sh_host.data(), sizeof(ShardState) * S, cudaMemcpyHostToDevice, ctx->stream));
+    return MCRAT_B200_OK;
+}
+
 API int mcrat_b200_set_photons(mcrat_b200_ctx *ctx, const mcrat_photon *photons, int n)
 {
     if (!ctx || n < 0 || (n > 0 && !photons)) return ctx ? fail(ctx, MCRAT_B200_ERR_ARG, "set_photons: bad argument") : MCRAT_B200_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     if (int rc = ensure_photon_capacity(ctx, n)) return rc;
     ctx->d.cap = n;
+    if (int rc = layout_shards(ctx, n)) return rc;
     if (n > 0) {
         CK(cudaMemcpyAsync(ctx->aos_dev, photons, (size_t)n * sizeof(mcrat_photon), cudaMemcpyHostToDevice, ctx->stream));
         unpack_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->d, ctx->aos_dev, n);
         if (int rc = check_launch(ctx, "unpack_kernel")) return rc;
     }
-    clear_push_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d);
-    if (int rc = check_launch(ctx, "clear_push_kernel")) return rc;
     ctx->have_photons = true;
     return MCRAT_B200_OK;
 }
@@ -1473,7 +1584,7 @@ static int flush_pushes(mcrat_b200_ctx *ctx)
         flush_push_kernel<<<grid_for(ctx, ctx->d.cap, PASS_THREADS, 8), PASS_THREADS, 0, ctx->stream>>>(ctx->d);
         if (int rc = check_launch(ctx, "flush_push_kernel")) return rc;
     }
-    clear_push_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d);
+    clear_push_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d);
     return check_launch(ctx, "clear_push_kernel");
 }
 
@@ -1518,11 +1629,11 @@ API int mcrat_b200_set_replay_uniforms(mcrat_b200_ctx *ctx, const double *u, siz
     }
     CK(cudaMemcpyAsync(ctx->replay_dev, u, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     ctx->d.replay_buf = ctx->replay_dev;
-    if (int rc = fetch_state(ctx)) return rc;
-    ctx->st_host->replay_cursor = 0;
-    ctx->st_host->replay_base = 0;
-    ctx->st_host->replay_n = n;
-    CK(cudaMemcpyAsync(ctx->d.st, ctx->st_host, sizeof(LoopState), cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = fetch_global(ctx)) return rc;
+    ctx->gs_host->replay_cursor = 0;
+    ctx->gs_host->replay_base = 0;
+    ctx->gs_host->replay_n = n;
+    CK(cudaMemcpyAsync(ctx->d.gs, ctx->gs_host, sizeof(GlobalState), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return MCRAT_B200_OK;
 }
@@ -1530,8 +1641,8 @@ API int mcrat_b200_set_replay_uniforms(mcrat_b200_ctx *ctx, const double *u, siz
 API long long mcrat_b200_replay_consumed(mcrat_b200_ctx *ctx)
 {
     if (!ctx) return -1;
-    if (fetch_state(ctx)) return -1;
-    return (long long)ctx->st_host->replay_cursor;
+    if (fetch_global(ctx)) return -1;
+    return (long long)ctx->gs_host->replay_cursor;
 }
 
 // ---- launch helpers ---------------------------------------------------------------------------
@@ -1540,12 +1651,17 @@ static int need_ready(mcrat_b200_ctx *ctx)
     if (!ctx->have_hydro) return fail(ctx, MCRAT_B200_ERR_STATE, "no hydro frame loaded (mcrat_b200_set_hydro)");
     if (!ctx->have_photons) return fail(ctx, MCRAT_B200_ERR_STATE, "no photon list loaded (mcrat_b200_set_photons)");
     if (ctx->d.cells.n <= 0) return fail(ctx, MCRAT_B200_ERR_STATE, "hydro frame has no cells");
+    if (ctx->d.cap <= 0) return fail(ctx, MCRAT_B200_ERR_STATE, "photon list is empty");
     return MCRAT_B200_OK;
 }
 
-static size_t scan_smem_bytes(int ndim3)
+static int need_single_shard(mcrat_b200_ctx *ctx, const char *what)
 {
-    return 2 * SCAN_TILE * sizeof(double4) + (ndim3 ? 2 * SCAN_TILE * sizeof(double2) : 0) + 2 * sizeof(uint64_t);
+    if (ctx->d.nshards != 1) {
+        ctx->err = std::string(what) + ": the step-by-step surface works on one shard (set_num_shards(1))";
+        return MCRAT_B200_ERR_STATE;
+    }
+    return MCRAT_B200_OK;
 }
 
 static void scan_grid(mcrat_b200_ctx *ctx, int nphot, dim3 &grid, int &tiles_per_chunk)
@@ -1566,16 +1682,16 @@ static void scan_grid(mcrat_b200_ctx *ctx, int nphot, dim3 &grid, int &tiles_per
 }
 
 // full scan of the current relocation list with K1 (count known only on the device: sized for cap)
-static int launch_scan_full(mcrat_b200_ctx *ctx, int parity, int nphot_bound, int count_override)
+static int launch_scan_full(mcrat_b200_ctx *ctx, int parity, int nphot_bound)
 {
     dim3 grid;
     int tpc;
     scan_grid(ctx, nphot_bound, grid, tpc);
     Timed t(ctx, KC_SCAN);
     if (ctx->d.dims == D_THREE)
-        scan_kernel<1><<<grid, SCAN_THREADS, scan_smem_bytes(1), ctx->stream>>>(ctx->d, parity, tpc, count_override);
+        scan_kernel<1><<<grid, SCAN_THREADS, scan_smem_bytes(1), ctx->stream>>>(ctx->d, parity, tpc);
     else
-        scan_kernel<0><<<grid, SCAN_THREADS, scan_smem_bytes(0), ctx->stream>>>(ctx->d, parity, tpc, count_override);
+        scan_kernel<0><<<grid, SCAN_THREADS, scan_smem_bytes(0), ctx->stream>>>(ctx->d, parity, tpc);
     return check_launch(ctx, "scan_kernel");
 }
 
@@ -1590,20 +1706,22 @@ static int launch_scan_few(mcrat_b200_ctx *ctx, int parity)
     return check_launch(ctx, "scan_few_kernel");
 }
 
-// one locate step: pass (+ optional fused free-path draw), scan, finish.  Returns block counts.
+// one locate step: pass (+ optional fused free-path draw), scan, finish.  Returns the parity used.
 template <bool FUSE>
-static int launch_locate(mcrat_b200_ctx *ctx, int sw, int &nb_pass, int &nb_fin)
+static int launch_locate(mcrat_b200_ctx *ctx, int sw, int &parity_out)
 {
     const int parity = ctx->pass_parity;
     ctx->pass_parity ^= 1;
-    nb_pass = grid_for(ctx, ctx->d.cap, PASS_THREADS, 8);
+    parity_out = parity;
+    const int nb_pass = ctx->d.nshards * ctx->d.blocks_per_shard;
     {
         Timed t(ctx, KC_PASS);
         pass_kernel<FUSE><<<nb_pass, PASS_THREADS, 0, ctx->stream>>>(ctx->d, sw, parity);
         if (int rc = check_launch(ctx, "pass_kernel")) return rc;
     }
+    int nb_fin;
     if (sw == 1) {
-        if (int rc = launch_scan_full(ctx, parity, ctx->d.cap, -1)) return rc;
+        if (int rc = launch_scan_full(ctx, parity, ctx->d.cap)) return rc;
         nb_fin = grid_for(ctx, ctx->d.cap, FIN_THREADS, 8);
     } else {
         if (int rc = launch_scan_few(ctx, parity)) return rc;
@@ -1626,7 +1744,7 @@ static int launch_mfp_unfused(mcrat_b200_ctx *ctx, int &nb)
         mfp_scan_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d, nblocks);
         if (int rc = check_launch(ctx, "mfp_scan_kernel", 2)) return rc;
     }
-    mfp_kernel<<<nblocks, 256, 0, ctx->stream>>>(ctx->d);
+    mfp_kernel<<<nblocks, 256, 0, ctx->stream>>>(ctx->d, nblocks <= BLOCKMIN_CAP ? 1 : 0);
     if (int rc = check_launch(ctx, "mfp_kernel")) return rc;
     if (nblocks > BLOCKMIN_CAP) {
         nb = grid_for(ctx, ctx->d.cap, 256, 8);
@@ -1640,7 +1758,7 @@ static int launch_mfp_unfused(mcrat_b200_ctx *ctx, int &nb)
 
 static int device_error(mcrat_b200_ctx *ctx)
 {
-    int e = ctx->st_host->error;
+    int e = ctx->gs_host->error;
     if (e == MCRAT_B200_ERR_REPLAY) return fail(ctx, e, "replay uniform stream exhausted");
     if (e == MCRAT_B200_ERR_TABLE)
         return fail(ctx, e, "hot cross-section lookup outside the table (the reference would integrate by Monte Carlo here)");
@@ -1648,19 +1766,46 @@ static int device_error(mcrat_b200_ctx *ctx)
     return MCRAT_B200_OK;
 }
 
+__global__ void reset_loop_kernel(DevCtx d, int set_times, double time_now, double remaining, long long max_iters)
+{
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < d.nshards; s += gridDim.x * blockDim.x) {
+        ShardState &st = d.sh[s];
+        st.done = 0;
+        st.pause_cs = 0;
+        st.counted_stopped = 0;
+        st.iters_done = 0;
+        if (set_times) {
+            st.time_now = time_now;
+            st.remaining_time = remaining;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        d.gs->max_iters = max_iters;
+        d.gs->n_stopped = 0;
+    }
+}
+
+static int reset_loop(mcrat_b200_ctx *ctx, int set_times, double time_now, double remaining, long long max_iters)
+{
+    reset_loop_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d, set_times, time_now, remaining, max_iters);
+    return check_launch(ctx, "reset_loop_kernel");
+}
+
 // ---- reference function surface ------------------------------------------------------------------
 API int mcrat_b200_find_containing_hydro_cell(mcrat_b200_ctx *ctx, int sw, int *num_relocated)
 {
     if (!ctx) return MCRAT_B200_ERR_ARG;
     if (int rc = need_ready(ctx)) return rc;
+    if (int rc = need_single_shard(ctx, "find_containing_hydro_cell")) return rc;
+    if (int rc = reset_loop(ctx, 0, 0, 0, -1)) return rc;
     if (int rc = fetch_state(ctx)) return rc;
-    const long long before = ctx->st_host->reloc_total;
-    int nbp, nbf;
-    if (int rc = launch_locate<false>(ctx, sw ? 1 : 0, nbp, nbf)) return rc;
-    clear_push_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d); // the pass consumed the pending pushes
+    const long long before = ctx->sh_host[0].reloc_total;
+    int parity;
+    if (int rc = launch_locate<false>(ctx, sw ? 1 : 0, parity)) return rc;
+    clear_push_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d); // the pass consumed the pending pushes
     if (int rc = check_launch(ctx, "clear_push_kernel")) return rc;
     if (int rc = fetch_state(ctx)) return rc;
-    if (num_relocated) *num_relocated = (int)(ctx->st_host->reloc_total - before);
+    if (num_relocated) *num_relocated = (int)(ctx->sh_host[0].reloc_total - before);
     return device_error(ctx);
 }
 
@@ -1668,35 +1813,17 @@ API int mcrat_b200_calc_mean_free_path(mcrat_b200_ctx *ctx, int *first_index, do
 {
     if (!ctx) return MCRAT_B200_ERR_ARG;
     if (int rc = need_ready(ctx)) return rc;
+    if (int rc = need_single_shard(ctx, "calc_mean_free_path")) return rc;
     if (int rc = flush_pushes(ctx)) return rc;
     int nb;
     if (int rc = launch_mfp_unfused(ctx, nb)) return rc;
     head_kernel<<<1, EVT_THREADS, 0, ctx->stream>>>(ctx->d, nb);
     if (int rc = check_launch(ctx, "head_kernel")) return rc;
     if (int rc = fetch_state(ctx)) return rc;
-    if (first_index) *first_index = ctx->st_host->head_idx;
-    if (first_tts) *first_tts = ctx->st_host->head_tts;
+    if (first_index) *first_index = ctx->sh_host[0].head_idx;
+    if (first_tts) *first_tts = ctx->sh_host[0].head_tts;
     ctx->last_nb_mfp = nb; // block minima stay valid for a following photon_event
     return device_error(ctx);
-}
-
-__global__ void reset_loop_kernel(DevCtx d, int set_times, double time_now, double remaining, long long max_iters)
-{
-    LoopState &st = *d.st;
-    st.done = 0;
-    st.pause_cs = 0;
-    st.iters_done = 0;
-    st.max_iters = max_iters;
-    if (set_times) {
-        st.time_now = time_now;
-        st.remaining_time = remaining;
-    }
-}
-
-static int reset_loop(mcrat_b200_ctx *ctx, int set_times, double time_now, double remaining, long long max_iters)
-{
-    reset_loop_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d, set_times, time_now, remaining, max_iters);
-    return check_launch(ctx, "reset_loop_kernel");
 }
 
 API int mcrat_b200_photon_event(mcrat_b200_ctx *ctx, double dt_max, double *time_step, int *scattered_ph_index,
@@ -1705,19 +1832,20 @@ API int mcrat_b200_photon_event(mcrat_b200_ctx *ctx, double dt_max, double *time
     (void)frame_abs_cnt; // the reference never touches it either (Src/mclib.c:1107-1356)
     if (!ctx) return MCRAT_B200_ERR_ARG;
     if (int rc = need_ready(ctx)) return rc;
+    if (int rc = need_single_shard(ctx, "photon_event")) return rc;
     if (ctx->last_nb_mfp <= 0) return fail(ctx, MCRAT_B200_ERR_STATE, "photon_event needs a preceding calc_mean_free_path");
     if (int rc = reset_loop(ctx, 0, 0, 0, -1)) return rc;
     if (int rc = fetch_state(ctx)) return rc;
-    const long long before = ctx->st_host->scatt_cnt;
+    const long long before = ctx->sh_host[0].scatt_cnt;
     {
         Timed t(ctx, KC_EVENT);
-        event_kernel<<<1, EVT_THREADS, 0, ctx->stream>>>(ctx->d, ctx->last_nb_mfp, 0, 1, dt_max);
+        event_kernel<<<1, EVT_THREADS, 0, ctx->stream>>>(ctx->d, 0, ctx->last_nb_mfp, 1, dt_max);
         if (int rc = check_launch(ctx, "event_kernel")) return rc;
     }
     if (int rc = fetch_state(ctx)) return rc;
-    if (time_step) *time_step = ctx->st_host->last_time_step;
-    if (scattered_ph_index) *scattered_ph_index = ctx->st_host->last_scattered_idx;
-    if (frame_scatt_cnt) *frame_scatt_cnt += (int)(ctx->st_host->scatt_cnt - before);
+    if (time_step) *time_step = ctx->sh_host[0].last_time_step;
+    if (scattered_ph_index) *scattered_ph_index = ctx->sh_host[0].last_scattered_idx;
+    if (frame_scatt_cnt) *frame_scatt_cnt += (int)(ctx->sh_host[0].scatt_cnt - before);
     ctx->last_nb_mfp = 0;
     return device_error(ctx);
 }
@@ -1727,7 +1855,7 @@ API int mcrat_b200_update_photon_position(mcrat_b200_ctx *ctx, double t)
     if (!ctx) return MCRAT_B200_ERR_ARG;
     if (!ctx->have_photons) return fail(ctx, MCRAT_B200_ERR_STATE, "no photon list loaded");
     if (int rc = flush_pushes(ctx)) return rc;
-    set_push_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d, t);
+    set_push_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d, t);
     if (int rc = check_launch(ctx, "set_push_kernel")) return rc;
     Timed tm(ctx, KC_PASS);
     return flush_pushes(ctx);
@@ -1735,9 +1863,9 @@ API int mcrat_b200_update_photon_position(mcrat_b200_ctx *ctx, double t)
 
 __global__ void clear_abs_kernel(DevCtx d)
 {
-    d.st->abs_count = 0;
-    d.st->cs_scatt_count = 0;
-    d.st->abs_weight = 0;
+    d.gs->abs_count = 0;
+    d.gs->cs_scatt_count = 0;
+    d.gs->abs_weight = 0;
 }
 
 API int mcrat_b200_ph_abs_cyclosynch(mcrat_b200_ctx *ctx, int *num_abs_ph, int *scatt_cyclosynch_num_ph, double *absorbed_weight)
@@ -1749,10 +1877,10 @@ API int mcrat_b200_ph_abs_cyclosynch(mcrat_b200_ctx *ctx, int *num_abs_ph, int *
     if (int rc = check_launch(ctx, "clear_abs_kernel")) return rc;
     cs_absorb_kernel<<<grid_for(ctx, ctx->d.cap, 256, 8), 256, 0, ctx->stream>>>(ctx->d);
     if (int rc = check_launch(ctx, "cs_absorb_kernel")) return rc;
-    if (int rc = fetch_state(ctx)) return rc;
-    if (num_abs_ph) *num_abs_ph = ctx->st_host->abs_count;
-    if (scatt_cyclosynch_num_ph) *scatt_cyclosynch_num_ph = ctx->st_host->cs_scatt_count;
-    if (absorbed_weight) *absorbed_weight = ctx->st_host->abs_weight;
+    if (int rc = fetch_global(ctx)) return rc;
+    if (num_abs_ph) *num_abs_ph = ctx->gs_host->abs_count;
+    if (scatt_cyclosynch_num_ph) *scatt_cyclosynch_num_ph = ctx->gs_host->cs_scatt_count;
+    if (absorbed_weight) *absorbed_weight = ctx->gs_host->abs_weight;
     return MCRAT_B200_OK;
 }
 
@@ -1813,6 +1941,21 @@ API int mcrat_b200_average_photon_energy(mcrat_b200_ctx *ctx, double *avg_energy
 }
 
 // ---- the device-resident frame loop, Src/mcrat.c:761-851 ---------------------------------------------
+static void fill_stats(const ShardState &s, const ShardState &b, mcrat_b200_frame_stats *o)
+{
+    o->iterations = s.iters_done;
+    o->scatterings = s.scatt_cnt - b.scatt_cnt;
+    o->relocations = s.reloc_total - b.reloc_total;
+    o->photon_slots = s.slots - b.slots;
+    o->cell_evals = 0;
+    o->time_now = s.time_now;
+    o->last_time_step = s.last_time_step;
+    o->last_scattered_index = s.last_scattered_idx;
+    o->not_found = 0;
+    o->cs_host_pending = s.pause_cs;
+    o->error = 0;
+}
+
 API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remaining_time, long long max_iters, int sw,
                              mcrat_b200_frame_stats *stats)
 {
@@ -1820,52 +1963,69 @@ API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remain
     if (int rc = need_ready(ctx)) return rc;
     CK(cudaSetDevice(ctx->cfg.device));
     if (int rc = fetch_state(ctx)) return rc;
-    const LoopState before = *ctx->st_host;
+    const int S = ctx->d.nshards;
+    std::vector<ShardState> before(ctx->sh_host.begin(), ctx->sh_host.begin() + S);
+    const GlobalState gbefore = *ctx->gs_host;
     if (int rc = reset_loop(ctx, 1, time_now, remaining_time, max_iters)) return rc;
     sw = sw ? 1 : 0;
     const bool fused = !ctx->d.replay;
-    long long launched = 0;
-    // iterations are enqueued in batches; kernels past the stop condition return immediately
+    // iterations are enqueued in batches; kernels of a shard past its stop condition return at once
     int batch = 1;
+    long long launched = 0;
     for (;;) {
         for (int b = 0; b < batch; ++b) {
-            int nbp = 0, nbf = 0;
+            int parity = 0, nb = ctx->d.blocks_per_shard;
             if (fused) {
-                if (int rc = launch_locate<true>(ctx, sw, nbp, nbf)) return rc;
+                if (int rc = launch_locate<true>(ctx, sw, parity)) return rc;
             } else {
-                if (int rc = launch_locate<false>(ctx, sw, nbp, nbf)) return rc;
-                if (int rc = launch_mfp_unfused(ctx, nbp)) return rc;
-                nbf = 0;
+                if (int rc = launch_locate<false>(ctx, sw, parity)) return rc;
+                if (int rc = launch_mfp_unfused(ctx, nb)) return rc;
             }
             {
                 Timed t(ctx, KC_EVENT);
-                event_kernel<<<1, EVT_THREADS, 0, ctx->stream>>>(ctx->d, nbp, nbf, 0, 0.0);
+                event_kernel<<<S, EVT_THREADS, 0, ctx->stream>>>(ctx->d, parity, nb, 0, 0.0);
                 if (int rc = check_launch(ctx, "event_kernel")) return rc;
             }
             sw = 0; // Src/mcrat.c:773
             launched++;
         }
-        if (int rc = fetch_state(ctx)) return rc;
-        const LoopState &s = *ctx->st_host;
-        if (s.done || s.pause_cs || s.error || (max_iters >= 0 && s.iters_done >= max_iters)) break;
+        if (int rc = fetch_global(ctx)) return rc;
+        const GlobalState &g = *ctx->gs_host;
+        if (g.error || g.n_stopped >= S) break;
         if (batch < 64) batch *= 2;
-        if (max_iters >= 0 && s.iters_done + batch > max_iters) batch = (int)(max_iters - s.iters_done);
+        if (max_iters >= 0 && launched + batch > max_iters) batch = (int)(max_iters - launched);
         if (batch < 1) batch = 1;
     }
-    const LoopState &s = *ctx->st_host;
-    stats->iterations = s.iters_done;
-    stats->scatterings = s.scatt_cnt - before.scatt_cnt;
-    stats->relocations = s.reloc_total - before.reloc_total;
-    stats->photon_slots = s.slots - before.slots;
-    stats->cell_evals = s.cell_evals - before.cell_evals;
-    stats->time_now = s.time_now;
-    stats->last_time_step = s.last_time_step;
-    stats->last_scattered_index = s.last_scattered_idx;
-    stats->not_found = s.not_found - before.not_found;
-    stats->cs_host_pending = s.pause_cs;
-    stats->error = s.error;
+    if (int rc = fetch_state(ctx)) return rc;
+    // aggregate over the sub-shards: counters add up, the clock reported is shard 0's
+    fill_stats(ctx->sh_host[0], before[0], stats);
+    for (int s = 1; s < S; ++s) {
+        mcrat_b200_frame_stats t;
+        fill_stats(ctx->sh_host[s], before[s], &t);
+        if (t.iterations > stats->iterations) stats->iterations = t.iterations;
+        stats->scatterings += t.scatterings;
+        stats->relocations += t.relocations;
+        stats->photon_slots += t.photon_slots;
+        stats->cs_host_pending |= t.cs_host_pending;
+    }
+    stats->cell_evals = ctx->gs_host->cell_evals - gbefore.cell_evals;
+    stats->not_found = ctx->gs_host->not_found - gbefore.not_found;
+    stats->error = ctx->gs_host->error;
     ctx->last_nb_mfp = 0;
     return device_error(ctx);
+}
+
+API int mcrat_b200_get_shard_stats(mcrat_b200_ctx *ctx, int shard, mcrat_b200_frame_stats *stats, int *first_slot,
+                                   int *num_slots)
+{
+    if (!ctx || !stats || shard < 0 || shard >= ctx->d.nshards) return ctx ? fail(ctx, MCRAT_B200_ERR_ARG, "get_shard_stats: bad shard") : MCRAT_B200_ERR_ARG;
+    if (int rc = fetch_state(ctx)) return rc;
+    ShardState zero;
+    memset(&zero, 0, sizeof(zero));
+    fill_stats(ctx->sh_host[shard], zero, stats);
+    if (first_slot) *first_slot = ctx->sh_host[shard].first;
+    if (num_slots) *num_slots = ctx->sh_host[shard].count;
+    return MCRAT_B200_OK;
 }
 
 // ---- measurement -------------------------------------------------------------------------------------
@@ -1885,11 +2045,11 @@ API int mcrat_b200_rescan_all(mcrat_b200_ctx *ctx, long long *cell_evals, float 
     if (int rc = need_ready(ctx)) return rc;
     if (int rc = flush_pushes(ctx)) return rc;
     if (int rc = reset_loop(ctx, 0, 0, 0, -1)) return rc;
-    if (int rc = fetch_state(ctx)) return rc;
-    const long long before = ctx->st_host->cell_evals;
+    if (int rc = fetch_global(ctx)) return rc;
+    const long long before = ctx->gs_host->cell_evals;
     const int parity = ctx->pass_parity;
     ctx->pass_parity ^= 1;
-    const int nbp = grid_for(ctx, ctx->d.cap, PASS_THREADS, 8);
+    const int nbp = ctx->d.nshards * ctx->d.blocks_per_shard;
     pass_kernel<false><<<nbp, PASS_THREADS, 0, ctx->stream>>>(ctx->d, 1, parity);
     if (int rc = check_launch(ctx, "pass_kernel")) return rc;
     dim3 grid;
@@ -1897,19 +2057,19 @@ API int mcrat_b200_rescan_all(mcrat_b200_ctx *ctx, long long *cell_evals, float 
     scan_grid(ctx, ctx->d.cap, grid, tpc);
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     if (ctx->d.dims == D_THREE)
-        scan_kernel<1><<<grid, SCAN_THREADS, scan_smem_bytes(1), ctx->stream>>>(ctx->d, parity, tpc, -1);
+        scan_kernel<1><<<grid, SCAN_THREADS, scan_smem_bytes(1), ctx->stream>>>(ctx->d, parity, tpc);
     else
-        scan_kernel<0><<<grid, SCAN_THREADS, scan_smem_bytes(0), ctx->stream>>>(ctx->d, parity, tpc, -1);
+        scan_kernel<0><<<grid, SCAN_THREADS, scan_smem_bytes(0), ctx->stream>>>(ctx->d, parity, tpc);
     if (int rc = check_launch(ctx, "scan_kernel")) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     const int nbf = grid_for(ctx, ctx->d.cap, FIN_THREADS, 8);
     finish_kernel<false><<<nbf, FIN_THREADS, 0, ctx->stream>>>(ctx->d, 1, parity);
     if (int rc = check_launch(ctx, "finish_kernel")) return rc;
-    if (int rc = fetch_state(ctx)) return rc;
+    if (int rc = fetch_global(ctx)) return rc;
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (elapsed_ms) *elapsed_ms = ms;
-    if (cell_evals) *cell_evals = ctx->st_host->cell_evals - before;
+    if (cell_evals) *cell_evals = ctx->gs_host->cell_evals - before;
     ctx->times.scan_ms += ms;
     ctx->times.scan_launches++;
     return device_error(ctx);

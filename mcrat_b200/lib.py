@@ -62,6 +62,7 @@ EXPORTS = [
     "mcrat_b200_abi_version", "mcrat_b200_device_count", "mcrat_b200_create", "mcrat_b200_destroy",
     "mcrat_b200_last_error", "mcrat_b200_synchronize", "mcrat_b200_set_hydro", "mcrat_b200_set_thermal_table",
     "mcrat_b200_set_photons", "mcrat_b200_get_photons", "mcrat_b200_get_photon", "mcrat_b200_list_capacity",
+    "mcrat_b200_set_num_shards", "mcrat_b200_num_shards", "mcrat_b200_get_shard_stats",
     "mcrat_b200_set_replay_uniforms", "mcrat_b200_replay_consumed", "mcrat_b200_find_containing_hydro_cell",
     "mcrat_b200_calc_mean_free_path", "mcrat_b200_photon_event", "mcrat_b200_update_photon_position",
     "mcrat_b200_ph_abs_cyclosynch", "mcrat_b200_ph_min_max", "mcrat_b200_ph_scatt_stats",
@@ -117,7 +118,8 @@ class HotPath:
     Src/mc_cyclosynch.h:84-92); each forwards to the C ABI.
     """
 
-    def __init__(self, cfg, device=0, rng_mode=RNG_PHILOX, seed=0, shard=0, profile=False, stream=None):
+    def __init__(self, cfg, device=0, rng_mode=RNG_PHILOX, seed=0, shard=0, profile=False, stream=None,
+                 num_shards=1):
         self.L = load()
         c = Config(ABI_VERSION, cfg["dimensions"], cfg["geometry"], cfg["stokes"], cfg["tau_calculation"],
                    cfg["cyclosynch"], cfg["b_field_calc"], cfg["epsilon_b"], device, rng_mode, seed, shard,
@@ -128,6 +130,8 @@ class HotPath:
             raise McratB200Error(rc, self.L.mcrat_b200_last_error(None).decode())
         self.cfg = dict(cfg)
         self._keep = []
+        if num_shards != 1:
+            self.set_num_shards(num_shards)
 
     def close(self):
         if getattr(self, "ctx", None) is not None and self.ctx:
@@ -191,6 +195,20 @@ class HotPath:
         out = np.zeros(1, dtype=PHOTON_DTYPE)
         self._ck(self.L.mcrat_b200_get_photon(self.ctx, C.c_int(index), out.ctypes.data_as(C.c_void_p)))
         return out[0]
+
+    def set_num_shards(self, n):
+        """Sub-shards (independent reference 'ranks') the next set_photons() splits the list into."""
+        self._ck(self.L.mcrat_b200_set_num_shards(self.ctx, C.c_int(n)))
+
+    def num_shards(self):
+        return int(self.L.mcrat_b200_num_shards(self.ctx))
+
+    def shard_stats(self, shard):
+        st, first, count = FrameStats(), C.c_int(0), C.c_int(0)
+        self._ck(self.L.mcrat_b200_get_shard_stats(self.ctx, C.c_int(shard), C.byref(st), C.byref(first), C.byref(count)))
+        d = st.as_dict()
+        d.update(first_slot=first.value, num_slots=count.value)
+        return d
 
     def set_replay_uniforms(self, u):
         u = np.ascontiguousarray(u, dtype=np.float64)

@@ -66,3 +66,28 @@ def test_frame_replay_parity(wl, refname, scale, nph, iters):
         assert st[k] == ost[k], (k, st, ost)
     errs = compare_photons(got, o.photons(), label=wl, stokes_tol=1e-9, hydro=hydro)
     print(wl, "max rel errors", {k: "%.1e" % v for k, v in errs.items()})
+
+
+@pytest.mark.parametrize("wl,nph,shards,iters", [("C2", 1500, 6, 120), ("C5", 1000, 7, 100), ("C1", 640, 64, 40)])
+def test_sub_shards_equal_independent_ranks(wl, nph, shards, iters):
+    """S sub-shards in one context == S stand-alone oracle ranks, each with its slot range and its
+    own Philox shard key (the reference's rank decomposition: shard-local arg-min, no exchange)."""
+    scale = {"C1": 1.0 / 8, "C2": 1.0 / 16, "C5": 1.0 / 8}[wl]
+    cfg, hydro, photons, frame = synth.workload(wl, scale=scale, n_photons=nph, seed=31)
+    hp = HotPath(cfg, seed=77, shard=100, num_shards=shards)
+    hp.set_hydro(hydro)
+    hp.set_photons(photons)
+    assert hp.num_shards() == shards or nph % shards
+    st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=iters, switch=1)
+    got = hp.get_photons()
+    total_scatt = 0
+    for s in range(hp.num_shards()):
+        ss = hp.shard_stats(s)
+        sl = slice(ss["first_slot"], ss["first_slot"] + ss["num_slots"])
+        rng = api.OracleRng("philox", seed=77, shard=100 + s)
+        o, ost = _oracle_frame(cfg, hydro, photons[sl], frame, rng, iters)
+        assert ss["iterations"] == ost["iterations"] and ss["scatterings"] == ost["scatterings"], (s, ss, ost)
+        assert abs(ss["time_now"] - ost["time_now"]) <= 1e-12 * ost["time_now"]
+        compare_photons(got[sl], o.photons(), label="%s shard %d" % (wl, s), stokes_tol=1e-9, hydro=hydro)
+        total_scatt += ost["scatterings"]
+    assert st["scatterings"] == total_scatt
