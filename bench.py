@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--iters", type=int, default=5000, help="while-loop iterations per step (frame slice)")
     ap.add_argument("--photons", type=int, default=100000)
     ap.add_argument("--scale", type=float, default=1.0, help="grid scale (1.0 = 1024x1024 cells)")
+    ap.add_argument("--shards", type=int, default=0,
+                    help="sub-shards (independent reference ranks) per GPU; 0 = one per host core, the "
+                         "decomposition the reference arm uses")
     ap.add_argument("--cpu-iters", type=int, default=0, help="iterations per CPU rank and step (0: same as --iters)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pass-roofline", action="store_true")
@@ -173,10 +176,14 @@ def main():
     from mcrat_b200 import synth
     log("building workload")
     cfg, hydro, photons, frame = synth.workload("C2", scale=args.scale, n_photons=args.photons, seed=1234 + rank)
+    ncores = len(os.sched_getaffinity(0))
+    shards = args.shards if args.shards > 0 else max(1, min(ncores, args.photons // 256))
     config = {"workload": WORKLOAD if (args.scale == 1.0 and args.photons == 100000) else
               "C2 reduced: scale=%g, %d photons/shard" % (args.scale, args.photons),
               "cells": int(hydro["num_elements"]), "photons_per_shard": int(photons.size),
-              "loop_iterations_per_step": args.iters, "shards": world,
+              "loop_iterations_per_step": args.iters, "gpu_ranks": world, "shards_per_gpu": shards,
+              "decomposition": "%d independent shards (reference ranks) of %d photons per GPU, each advancing "
+                               "its own time-ordered scatter sequence" % (shards, photons.size // shards),
               "step": "full photon x cell rescan (new hydro frame) + loop iterations; steps continue one simulation",
               "l2": "flushed between timed steps (256 MiB write)"}
 
@@ -214,7 +221,7 @@ def main():
         torch.cuda.synchronize()
 
     stream = torch.cuda.current_stream().cuda_stream
-    hp = HotPath(cfg, device=local_rank, seed=20261018, shard=rank, stream=stream)
+    hp = HotPath(cfg, device=local_rank, seed=20261018, shard=rank * shards, stream=stream, num_shards=shards)
     hp.set_hydro(hydro)
     hp.set_photons(photons)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -302,7 +309,7 @@ def main():
         try:
             nbig = 4_000_000
             rep = np.resize(photons, nbig)
-            hpb = HotPath(cfg, device=local_rank, seed=7, shard=rank, profile=True)
+            hpb = HotPath(cfg, device=local_rank, seed=7, shard=0, profile=True)
             hpb.set_hydro(hydro)
             hpb.set_photons(rep)
             hpb.run_frame(time_now, dt_frame, max_iters=1, switch=1)

@@ -194,39 +194,35 @@ __device__ inline void hydro_vector_to_cartesian(int dims, int g, double *out, d
 {
     double t0 = 0, t1 = 0, t2 = 0;
     (void)x0;
-    if (dims == D_TWO) {
-        if (g == G_CARTESIAN || g == G_CYLINDRICAL) {
-            t0 = v0 * cos(x2);
-            t1 = v0 * sin(x2);
-            t2 = v1;
-        } else if (g == G_SPHERICAL) {
-            v2 = 0;
-            t0 = v0 * sin(x1) * cos(x2) + v1 * cos(x1) * cos(x2) - v2 * sin(x2);
-            t1 = v0 * sin(x1) * sin(x2) + v1 * cos(x1) * sin(x2) + v2 * cos(x2);
-            t2 = v0 * cos(x1) - v1 * sin(x1);
-        }
-    } else if (dims == D_TWO_POINT_FIVE) {
-        if (g == G_CARTESIAN || g == G_CYLINDRICAL) {
-            t0 = v0 * cos(x2) - v2 * sin(x2);
-            t1 = v0 * sin(x2) + v2 * cos(x2);
-            t2 = v1;
-        } else if (g == G_SPHERICAL) {
-            t0 = v0 * sin(x1) * cos(x2) + v1 * cos(x1) * cos(x2) - v2 * sin(x2);
-            t1 = v0 * sin(x1) * sin(x2) + v1 * cos(x1) * sin(x2) + v2 * cos(x2);
-            t2 = v0 * cos(x1) - v1 * sin(x1);
-        }
-    } else {
-        if (g == G_CARTESIAN) {
-            t0 = v0; t1 = v1; t2 = v2;
-        } else if (g == G_SPHERICAL) {
-            t0 = v0 * sin(x1) * cos(x2) + v1 * cos(x1) * cos(x2) - v2 * sin(x2);
-            t1 = v0 * sin(x1) * sin(x2) + v1 * cos(x1) * sin(x2) + v2 * cos(x2);
-            t2 = v0 * cos(x1) - v1 * sin(x1);
-        } else if (g == G_POLAR) {
-            t0 = v0 * cos(x1) - v1 * sin(x1);
-            t1 = v0 * sin(x1) + v1 * cos(x1);
-            t2 = v2;
-        }
+    const bool planar = (g == G_CARTESIAN || g == G_CYLINDRICAL);
+    if (dims == D_THREE && g == G_CARTESIAN) {
+        t0 = v0; t1 = v1; t2 = v2;
+    } else if (dims == D_THREE && g == G_POLAR) {
+        double s1, c1;
+        sincos(x1, &s1, &c1);
+        t0 = v0 * c1 - v1 * s1;
+        t1 = v0 * s1 + v1 * c1;
+        t2 = v2;
+    } else if (dims == D_TWO && planar) {
+        double s2, c2;
+        sincos(x2, &s2, &c2);
+        t0 = v0 * c2;
+        t1 = v0 * s2;
+        t2 = v1;
+    } else if (dims == D_TWO_POINT_FIVE && planar) {
+        double s2, c2;
+        sincos(x2, &s2, &c2);
+        t0 = v0 * c2 - v2 * s2;
+        t1 = v0 * s2 + v2 * c2;
+        t2 = v1;
+    } else if (g == G_SPHERICAL) {
+        if (dims == D_TWO) v2 = 0;
+        double s1, c1, s2, c2;
+        sincos(x1, &s1, &c1);
+        sincos(x2, &s2, &c2);
+        t0 = v0 * s1 * c2 + v1 * c1 * c2 - v2 * s2;
+        t1 = v0 * s1 * s2 + v1 * c1 * s2 + v2 * c2;
+        t2 = v0 * c1 - v1 * s1;
     }
     out[0] = t0; out[1] = t1; out[2] = t2;
 }
@@ -454,21 +450,20 @@ __device__ inline double optical_depth(int dims, int g, int tau_calc, const HotT
 // ----------------------------------------------------------------------------------------
 // Stokes-plane rotations (Src/mcrat_scattering.c:10-149)
 // ----------------------------------------------------------------------------------------
-// Src/mcrat_scattering.c:10-39 mullerMatrixRotation
+// Src/mcrat_scattering.c:10-39 mullerMatrixRotation.  The 4x4 dgemv of the reference reduces to
+// the two middle rows (rows 0 and 3 are unit rows; the zero products add exactly 0 for finite s)
 __device__ inline void muller_rotation(double theta, double *s)
 {
-    double M[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) M[i] = 0;
-    M[0] = 1;
-    M[15] = 1;
-    M[5] = cos(2 * theta);
-    M[10] = cos(2 * theta);
-    M[6] = -1 * sin(2 * theta);
-    M[9] = sin(2 * theta);
-    double r[4];
-    dgemv<4>(M, s, r);
-    s[0] = r[0]; s[1] = r[1]; s[2] = r[2]; s[3] = r[3];
+    double sn, cs;
+    sincos(2 * theta, &sn, &cs);
+    double r1 = 0.0;
+    r1 += s[1] * cs;
+    r1 += s[2] * (-1 * sn);
+    double r2 = 0.0;
+    r2 += s[1] * sn;
+    r2 += s[2] * cs;
+    s[1] = r1;
+    s[2] = r2;
 }
 
 // Src/mcrat_scattering.c:41-65 findXY
@@ -514,7 +509,8 @@ __device__ inline void stokes_rotation(const double *v, const double *v_ph, cons
 // ----------------------------------------------------------------------------------------
 // Klein-Nishina scatter (Src/mcrat_scattering.c:151-595)
 // ----------------------------------------------------------------------------------------
-// Src/mcrat_scattering.c:509-595 kleinNishinaScatter
+// Src/mcrat_scattering.c:509-595 kleinNishinaScatter.  The reference's pow(m, -1/-2/-3) are written
+// as reciprocals of products (<= 2 ulp apart; pow is several hundred instructions in FP64).
 __device__ inline int kn_scatter(int stokes, double &theta, double &phi, double p0, double q, double u, EventRng &rng)
 {
     double er = p0 / (M_EL * C_LIGHT);
@@ -526,23 +522,28 @@ __device__ inline int kn_scatter(int stokes, double &theta, double &phi, double 
         cty = rng.uniform() * 2;
         ct = rng.uniform() * 2 - 1;
         double m1 = (1 + er * (1 - ct));
-        fct = pow(m1, -2.0) * (er * (1 - ct) + (1 / (1 + er * (1 - ct))) + ct * ct);
+        fct = (1.0 / (m1 * m1)) * (er * (1 - ct) + (1 / m1) + ct * ct);
     }
     theta = acos(ct);
-    double mu = 1 + er * (1 - cos(theta));
-    double st = sin(theta);
-    double f_theta = (pow(mu, -1.0) + pow(mu, -3.0) - pow(mu, -2.0) * st * st) * st;
+    double st, ctheta;
+    sincos(theta, &st, &ctheta);
+    double mu = 1 + er * (1 - ctheta);
+    double imu2 = 1.0 / (mu * mu);
+    double f_theta = ((1.0 / mu) + (1.0 / (mu * mu * mu)) - imu2 * st * st) * st;
     double phi_y = 1, f_phi = 0, phi_dum = 0;
-    while (phi_y > f_phi && !rng.exhausted) {
-        if (!stokes || (u == 0 && q == 0)) {
-            phi_dum = rng.uniform() * 2 * PI;
-            phi_y = -1;
-        } else {
-            double phi_max = fabs(atan2(-u, q)) / 2.0;
-            double norm = (f_theta + pow(mu, -2.0) * st * st * st * (q * cos(2 * phi_max) - u * sin(2 * phi_max)));
+    if (!stokes || (u == 0 && q == 0)) {
+        phi_dum = rng.uniform() * 2 * PI;
+    } else {
+        double phi_max = fabs(atan2(-u, q)) / 2.0;
+        double s2m, c2m;
+        sincos(2 * phi_max, &s2m, &c2m);
+        double norm = (f_theta + imu2 * st * st * st * (q * c2m - u * s2m));
+        while (phi_y > f_phi && !rng.exhausted) {
             phi_y = rng.uniform();
             phi_dum = rng.uniform() * 2 * PI;
-            f_phi = (f_theta + pow(mu, -2.0) * st * st * st * (q * cos(2 * phi_dum) - u * sin(2 * phi_dum))) / norm;
+            double s2, c2;
+            sincos(2 * phi_dum, &s2, &c2);
+            f_phi = (f_theta + imu2 * st * st * st * (q * c2 - u * s2)) / norm;
         }
     }
     phi = phi_dum;
@@ -569,26 +570,30 @@ __device__ inline int single_scatter(int stokes, double *el_comov, double *ph_co
     orig[0] = php[0]; orig[1] = php[1]; orig[2] = php[2]; orig[3] = php[3];
 
     double phi0 = atan2(php[2], php[1]);
+    double s0m, c0m; // sin(-phi0), cos(-phi0)
+    sincos(-phi0, &s0m, &c0m);
 #pragma unroll
     for (int i = 0; i < 9; i++) rot[i] = 0;
     rot[8] = 1;
-    rot[0] = cos(-phi0);
-    rot[4] = cos(-phi0);
-    rot[1] = -sin(-phi0);
-    rot[3] = sin(-phi0);
+    rot[0] = c0m;
+    rot[4] = c0m;
+    rot[1] = -s0m;
+    rot[3] = s0m;
     dgemv<3>(rot, ph_p, result0);
     php[1] = result0[0];
     php[2] = 0;
     php[3] = result0[2];
 
     double phi1 = atan2(result0[2], result0[0]);
+    double s1m, c1m; // sin(-phi1), cos(-phi1)
+    sincos(-phi1, &s1m, &c1m);
 #pragma unroll
     for (int i = 0; i < 9; i++) rot[i] = 0;
     rot[4] = 1;
-    rot[0] = cos(-phi1);
-    rot[8] = cos(-phi1);
-    rot[2] = -sin(-phi1);
-    rot[6] = sin(-phi1);
+    rot[0] = c1m;
+    rot[8] = c1m;
+    rot[2] = -s1m;
+    rot[6] = s1m;
     dgemv<3>(rot, ph_p, result1);
     php[1] = php[0];
     php[2] = result1[1];
@@ -597,28 +602,31 @@ __device__ inline int single_scatter(int stokes, double *el_comov, double *ph_co
     double theta = 0, phi = 0;
     int occurred = kn_scatter(stokes, theta, phi, php[0], s[1], s[2], rng);
     if (occurred == 1) {
-        result[0] = (php[0]) / (1 + (((php[0]) * (1 - cos(theta))) / (M_EL * C_LIGHT)));
-        result[1] = result[0] * cos(theta);
-        result[2] = result[0] * sin(theta) * sin(phi);
-        result[3] = result[0] * sin(theta) * cos(phi);
+        double sth, cth, sph, cph;
+        sincos(theta, &sth, &cth);
+        sincos(phi, &sph, &cph);
+        result[0] = (php[0]) / (1 + (((php[0]) * (1 - cth)) / (M_EL * C_LIGHT)));
+        result[1] = result[0] * cth;
+        result[2] = result[0] * sth * sph;
+        result[3] = result[0] * sth * cph;
 
         php[0] = result[0]; php[1] = result[1]; php[2] = result[2]; php[3] = result[3];
 #pragma unroll
         for (int i = 0; i < 9; i++) rot[i] = 0;
         rot[4] = 1;
-        rot[0] = cos(-phi1);
-        rot[8] = cos(-phi1);
-        rot[2] = sin(-phi1);
-        rot[6] = -sin(-phi1);
+        rot[0] = c1m;
+        rot[8] = c1m;
+        rot[2] = s1m;
+        rot[6] = -s1m;
         dgemv<3>(rot, ph_p, result1);
         php[1] = result1[0]; php[2] = result1[1]; php[3] = result1[2];
 #pragma unroll
         for (int i = 0; i < 9; i++) rot[i] = 0;
         rot[8] = 1;
-        rot[0] = cos(-phi0);
-        rot[4] = cos(-phi0);
-        rot[1] = sin(-phi0);
-        rot[3] = -sin(-phi0);
+        rot[0] = c0m;
+        rot[4] = c0m;
+        rot[1] = s0m;
+        rot[3] = -s0m;
         dgemv<3>(rot, ph_p, result0);
 
         if (stokes) {
@@ -629,11 +637,12 @@ __device__ inline int single_scatter(int stokes, double *el_comov, double *ph_co
             muller_rotation(ph, s);
 
             double th = acos((orig[1] * result0[0] + orig[2] * result0[1] + orig[3] * result0[2]) / (orig[0] * (php[0])));
-            double ct = cos(th), sn = sin(th);
+            double ct, sn;
+            sincos(th, &sn, &ct);
             double scatt[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) scatt[i] = 0;
-            scatt[0] = 1.0 + pow(ct, 2.0) + ((1 - ct) * (orig[0] - result[0]) / (M_EL * C_LIGHT));
+            scatt[0] = 1.0 + ct * ct + ((1 - ct) * (orig[0] - result[0]) / (M_EL * C_LIGHT));
             scatt[1] = sn * sn;
             scatt[4] = sn * sn;
             scatt[5] = 1.0 + ct * ct;
@@ -699,19 +708,22 @@ __device__ inline void rotate_electron(double *el_p, const double *ph_p)
     double ph_theta = atan2(sqrt(ph_p[2] * ph_p[2] + ph_p[3] * ph_p[3]), ph_p[1]);
 #pragma unroll
     for (int i = 0; i < 9; i++) rot[i] = 0;
+    double stt, ctt, spm, cpm;
+    sincos(ph_theta, &stt, &ctt);
+    sincos(-ph_phi, &spm, &cpm);
     rot[4] = 1;
-    rot[8] = cos(ph_theta);
-    rot[0] = cos(ph_theta);
-    rot[2] = -sin(ph_theta);
-    rot[6] = sin(ph_theta);
+    rot[8] = ctt;
+    rot[0] = ctt;
+    rot[2] = -stt;
+    rot[6] = stt;
     dgemv<3>(rot, e, result);
 #pragma unroll
     for (int i = 0; i < 9; i++) rot[i] = 0;
     rot[0] = 1;
-    rot[4] = cos(-ph_phi);
-    rot[8] = cos(-ph_phi);
-    rot[5] = -sin(-ph_phi);
-    rot[7] = sin(-ph_phi);
+    rot[4] = cpm;
+    rot[8] = cpm;
+    rot[5] = -spm;
+    rot[7] = spm;
     double out[3];
     dgemv<3>(rot, result, out);
     e[0] = out[0]; e[1] = out[1]; e[2] = out[2];
@@ -724,10 +736,13 @@ __device__ inline void single_thermal_electron(double *el_p, double temp, const 
     double beta = sqrt(1 - (1 / (gamma * gamma)));
     double phi = rng.uniform() * 2 * PI;
     double theta = acos((1 - sqrt(1 + beta * beta + 2 * beta - 4 * beta * rng.uniform())) / beta);
+    double sth, cth, sph, cph;
+    sincos(theta, &sth, &cth);
+    sincos(phi, &sph, &cph);
     el_p[0] = gamma * (M_EL) * (C_LIGHT);
-    el_p[1] = gamma * (M_EL) * (C_LIGHT)*beta * cos(theta);
-    el_p[2] = gamma * (M_EL) * (C_LIGHT)*beta * sin(theta) * sin(phi);
-    el_p[3] = gamma * (M_EL) * (C_LIGHT)*beta * sin(theta) * cos(phi);
+    el_p[1] = gamma * (M_EL) * (C_LIGHT)*beta * cth;
+    el_p[2] = gamma * (M_EL) * (C_LIGHT)*beta * sth * sph;
+    el_p[3] = gamma * (M_EL) * (C_LIGHT)*beta * sth * cph;
     rotate_electron(el_p, ph_p);
 }
 

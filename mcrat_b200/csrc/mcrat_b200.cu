@@ -43,7 +43,7 @@ enum : unsigned char { F_MOVABLE = 1, F_RECALC = 2 };
 
 constexpr int MAX_DT = 16;         // pushes recorded by one event (1 + Klein-Nishina rejections)
 constexpr int BLOCKMIN_CAP = 4096; // per-block arg-min slots
-constexpr int MAX_SHARDS = 1024;
+constexpr int MAX_SHARDS = 4096;
 constexpr int SCAN_THREADS = 128;
 constexpr int SCAN_P = 8;      // photons per thread held in registers
 constexpr int SCAN_TILE = 512; // cells per shared-memory stage
@@ -741,7 +741,8 @@ __global__ void __launch_bounds__(256) argmin_all_kernel(DevCtx d)
 // K3: event kernel -- shard-local arg-min, then photonEvent (Src/mclib.c:1107-1356) and the
 // driver's bookkeeping (Src/mcrat.c:777-846).  One block per sub-shard; lane 0 runs the scatter.
 // ------------------------------------------------------------------------------------------
-constexpr int EVT_THREADS = 128;
+constexpr int EVT_THREADS = 256;   // one shard / few shards: wide block for the list scans
+constexpr int EVT_THREADS_MANY = 32; // many sub-shards: one warp per event, 16+ events resident per SM
 
 __device__ void scatter_candidate(DevCtx &d, ShardState &st, EventRng &rng, int i, int n_dt, bool &event_did_occur)
 {
@@ -786,6 +787,7 @@ __device__ void scatter_candidate(DevCtx &d, ShardState &st, EventRng &rng, int 
 
 // step_mode 0: frame loop (driver bookkeeping included); 1: photonEvent only (dt_max given)
 // blockmin_valid: the pass wrote per-block minima for this iteration (fused path / step API)
+template <int EVT_THREADS>
 __global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int parity, int nb_per_shard, int step_mode,
                                                             double dt_max_arg)
 {
@@ -1516,7 +1518,7 @@ static int ensure_photon_capacity(mcrat_b200_ctx *ctx, int n)
 API int mcrat_b200_set_num_shards(mcrat_b200_ctx *ctx, int num_shards)
 {
     if (!ctx) return MCRAT_B200_ERR_ARG;
-    if (num_shards < 1 || num_shards > MAX_SHARDS) return fail(ctx, MCRAT_B200_ERR_ARG, "set_num_shards: 1..1024 sub-shards");
+    if (num_shards < 1 || num_shards > MAX_SHARDS) return fail(ctx, MCRAT_B200_ERR_ARG, "set_num_shards: 1..4096 sub-shards");
     if (num_shards > 1 && ctx->d.replay) return fail(ctx, MCRAT_B200_ERR_ARG, "the replay harness drives a single shard");
     if (num_shards > 1 && ctx->d.cs)
         return fail(ctx, MCRAT_B200_ERR_ARG, "sub-shards need CYCLOSYNCHROTRON_SWITCH OFF (host-side emission re-packs the list)");
@@ -1839,7 +1841,7 @@ API int mcrat_b200_photon_event(mcrat_b200_ctx *ctx, double dt_max, double *time
     const long long before = ctx->sh_host[0].scatt_cnt;
     {
         Timed t(ctx, KC_EVENT);
-        event_kernel<<<1, EVT_THREADS, 0, ctx->stream>>>(ctx->d, 0, ctx->last_nb_mfp, 1, dt_max);
+        event_kernel<EVT_THREADS><<<1, EVT_THREADS, 0, ctx->stream>>>(ctx->d, 0, ctx->last_nb_mfp, 1, dt_max);
         if (int rc = check_launch(ctx, "event_kernel")) return rc;
     }
     if (int rc = fetch_state(ctx)) return rc;
@@ -1983,7 +1985,10 @@ API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remain
             }
             {
                 Timed t(ctx, KC_EVENT);
-                event_kernel<<<S, EVT_THREADS, 0, ctx->stream>>>(ctx->d, parity, nb, 0, 0.0);
+                if (S >= 64)
+                    event_kernel<EVT_THREADS_MANY><<<S, EVT_THREADS_MANY, 0, ctx->stream>>>(ctx->d, parity, nb, 0, 0.0);
+                else
+                    event_kernel<EVT_THREADS><<<S, EVT_THREADS, 0, ctx->stream>>>(ctx->d, parity, nb, 0, 0.0);
                 if (int rc = check_launch(ctx, "event_kernel")) return rc;
             }
             sw = 0; // Src/mcrat.c:773

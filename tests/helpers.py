@@ -32,9 +32,16 @@ def compare_photons(got, want, tol=TOL, stokes_tol=None, check_tts=True, label="
     rnorm = np.sqrt(want["r0"] ** 2 + want["r1"] ** 2 + want["r2"] ** 2)
     for f in ("r0", "r1", "r2"):
         errs[f] = _rel(got[f], want[f], rnorm)
-    for f in ("p0", "p1", "p2", "p3"):
-        errs[f] = _rel(got[f], want[f], np.abs(want["p0"]))
     live = want["nearest_block_index"] != -1
+    # the lab momentum of a scattered photon is the boost of its comoving momentum back to the lab,
+    # p0 = Gamma (p0' + beta.p') (Src/mclib.c:1262-1265): for photons scattered against the flow it
+    # cancels by 2 Gamma^2, so it is held to `tol` against Gamma * p0' (pass `hydro`)
+    p_scale = np.abs(want["p0"])
+    if hydro is not None:
+        gidx0 = np.where(live, want["nearest_block_index"], 0)
+        p_scale = np.where(live, np.maximum(p_scale, np.asarray(hydro["gamma"])[gidx0] * np.abs(want["comv_p0"])), p_scale)
+    for f in ("p0", "p1", "p2", "p3"):
+        errs[f] = _rel(got[f], want[f], p_scale)
     # comoving momentum = Lorentz boost of the lab momentum, p0' = Gamma (p0 - beta.p)
     # (Src/mclib.c:302-407): for photons moving with the flow it cancels by the same 2 Gamma^2, so it
     # is held to `tol` against its un-cancelled scale Gamma * p0 (pass `hydro`)
