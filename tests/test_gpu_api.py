@@ -1,0 +1,266 @@
+"""GPU tests of the remaining C-ABI surface: golden fixtures, step-by-step calls, TABLE cross
+section, cyclo-synchrotron absorption, statistics readers, the drop-in library, and size-independent
+properties at BASELINE sizes."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from mcrat_b200 import HotPath, lib, synth
+from mcrat_b200.lib import RNG_REPLAY
+from oracle import api, configs
+
+from helpers import compare_photons
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _cfg_from_ref(name):
+    c = configs.CONFIGS[name]
+    return dict(dimensions=c["dimensions"], geometry=c["geometry"], stokes=c["stokes"],
+                tau_calculation=c["tau_calculation"], cyclosynch=c["cyclosynch"], b_field_calc=c["b_field_calc"],
+                epsilon_b=c["epsilon_b"])
+
+
+def _table():
+    return np.load(os.path.join(GOLDEN, "thermal_table.npy"))
+
+
+@pytest.mark.parametrize("name", ["c1_2d_cart", "c2_2d_cyl_stokes", "c3_2d_cyl_table", "c5_3d_sph"])
+def test_golden_fixture_replay(name):
+    """Fixtures produced by the reference's own sources (tests/golden/make_golden.py)."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=True)
+    hydro = {k: g[k] for k in api.HYDRO_FIELDS}
+    hydro.update(num_elements=int(g["num_elements"]), fps=float(g["fps"]), r0_domain=tuple(g["r0_domain"]),
+                 r1_domain=tuple(g["r1_domain"]), r2_domain=tuple(g["r2_domain"]))
+    cfg = _cfg_from_ref(name)
+    hp = HotPath(cfg, rng_mode=RNG_REPLAY)
+    if cfg["tau_calculation"] == configs.TABLE:
+        hp.set_thermal_table(_table())
+    hp.set_hydro(hydro)
+    hp.set_photons(g["photons_in"])
+    hp.set_replay_uniforms(g["uniforms"])
+    st = hp.run_frame(float(g["time_now"]), float(g["dt"]), max_iters=int(g["iters"]), switch=1)
+    assert hp.replay_consumed() == g["uniforms"].size
+    assert st["scatterings"] == dict(g["stats"])["scatterings"]
+    errs = compare_photons(hp.get_photons(), g["photons_out"], label=name, stokes_tol=1e-9, hydro=hydro)
+    print(name, {k: "%.1e" % v for k, v in errs.items()})
+
+
+def test_hot_electron_table_philox_parity():
+    """C3: Maxwell-Juttner electrons + tabulated thermal Klein-Nishina cross section."""
+    cfg, hydro, photons, frame = synth.workload("C3", scale=1.0 / 16, n_photons=600, seed=17)
+    tab = _table()
+    hp = HotPath(cfg, seed=5, shard=1)
+    hp.set_thermal_table(tab)
+    hp.set_hydro(hydro)
+    hp.set_photons(photons)
+    st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=250, switch=1)
+    o = api.Oracle(cfg, table=tab)
+    o.set_hydro(hydro)
+    o.set_photons(photons)
+    ost = o.run_frame(api.OracleRng("philox", seed=5, shard=1), frame["time_now"], 1.0 / frame["fps"], max_iters=250)
+    assert st["scatterings"] == ost["scatterings"] and st["iterations"] == ost["iterations"]
+    compare_photons(hp.get_photons(), o.photons(), label="C3", stokes_tol=1e-9, hydro=hydro)
+
+
+def test_step_by_step_surface_matches_oracle():
+    """findContainingHydroCell / calcMeanFreePath / photonEvent / updatePhotonPosition one call at a
+    time, driven like Src/mcrat.c:761-851, against the oracle consuming the same uniform stream."""
+    cfg, hydro, photons, frame = synth.workload("C2", scale=1.0 / 16, n_photons=300, seed=3)
+    iters = 40
+    for seed in range(1, 50):
+        src = api.OracleRng("ranlxs0", seed=seed)
+        src.tee(1_000_000)
+        o = api.Oracle(cfg)
+        o.set_hydro(hydro)
+        o.set_photons(photons)
+        trace = []
+        remaining, sw = 1.0 / frame["fps"], 1
+        for _ in range(iters):
+            nrel = o.find_containing_hydro_cell(sw, src)
+            o.calc_mean_free_path(src)
+            head = int(o.sorted_indexes()[0])
+            t_head = float(o.photons()["time_to_scatter"][head])
+            dt, idx, sc = o.photon_event(remaining, src)
+            remaining -= dt
+            sw = 0
+            trace.append((nrel, head, t_head, dt, idx, sc))
+        o.update_photon_position(1e-3)
+        u = src.tee_values()
+        if not np.any(u == 0.0):
+            break
+    hp = HotPath(cfg, rng_mode=RNG_REPLAY)
+    hp.set_hydro(hydro)
+    hp.set_photons(photons)
+    hp.set_replay_uniforms(u)
+    remaining, sw = 1.0 / frame["fps"], 1
+    for k in range(iters):
+        nrel = hp.findContainingHydroCell(sw)
+        head, t_head = hp.calcMeanFreePath()
+        dt, idx, sc = hp.photonEvent(remaining)
+        remaining -= dt
+        sw = 0
+        w = trace[k]
+        assert (nrel, head, idx, sc) == (w[0], w[1], w[4], w[5]), (k, (nrel, head, idx, sc), w)
+        assert abs(t_head - w[2]) <= 1e-9 * w[2] and abs(dt - w[3]) <= 1e-9 * w[3]
+    hp.updatePhotonPosition(1e-3)
+    assert hp.replay_consumed() == u.size
+    compare_photons(hp.get_photons(), o.photons(), label="step API", stokes_tol=1e-9, hydro=hydro)
+    # one record through get_photon == the same slot of the full download
+    full = hp.get_photons()
+    one = hp.get_photon(7)
+    assert one.tobytes() == full[7].tobytes()
+
+
+def test_statistics_readers():
+    cfg, hydro, photons, frame = synth.workload("C2", scale=1.0 / 16, n_photons=2000, seed=9)
+    hp = HotPath(cfg, seed=1)
+    hp.set_hydro(hydro)
+    hp.set_photons(photons)
+    hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=100, switch=1)
+    ph = hp.get_photons()
+    r = np.sqrt(ph["r0"] ** 2 + ph["r1"] ** 2 + ph["r2"] ** 2)
+    th = np.arccos(ph["r2"] / r)
+    rmin, rmax, tmin, tmax = hp.phMinMax()
+    assert (rmin, rmax) == (r.min(), r.max()) and abs(tmin - th.min()) < 1e-15 and abs(tmax - th.max()) < 1e-15
+    mx, mn, avg, ravg = hp.phScattStats()
+    assert (mx, mn) == (int(ph["num_scatt"].max()), int(ph["num_scatt"].min()))
+    assert abs(avg - ph["num_scatt"].mean()) < 1e-12 and abs(ravg / r.mean() - 1) < 1e-12
+    e = hp.averagePhotonEnergy()
+    assert abs(e / ((ph["p0"] * ph["weight"]).sum() * synth.C_LIGHT / ph["weight"].sum()) - 1) < 1e-12
+
+
+@pytest.mark.parametrize("refname", ["c4_3d_sph_cs", "c4b_3d_sph_cs_tote"])
+def test_cyclosynchrotron_absorption(refname):
+    cfg = _cfg_from_ref(refname)
+    _, hydro, photons, frame = synth.workload("C4", scale=1.0 / 16, n_photons=1500, seed=12)
+    o = api.Oracle(configs.CONFIGS[refname])
+    o.set_hydro(hydro)
+    o.set_photons(photons)
+    o.find_containing_hydro_cell(1, api.OracleRng("ranlxs0", seed=1))
+    ph = o.photons()
+    ph["comv_p0"][::3] *= 1e-12
+    ph["type"][1::7] = b"k"
+    ph["type"][2::11] = b"p"
+    o.set_photons(ph)
+    want = o.ph_abs_cyclosynch()
+    hp = HotPath(cfg)
+    hp.set_hydro(hydro)
+    hp.set_photons(ph)
+    got = hp.phAbsCyclosynch()
+    assert got[1:] == want[1:] and abs(got[0] - want[0]) <= 1e-12 * abs(want[0])
+    a, b = hp.get_photons(), o.photons()
+    for f in a.dtype.names:
+        assert np.array_equal(a[f], b[f]), f
+
+
+def test_dropin_library_drives_a_frame():
+    """The reference-signature wrappers (libmcrat_b200_dropin.so) called the way mcrat.c calls them."""
+    D = C.CDLL(lib.DROPIN_PATH)
+    D.__wrap_photonEvent.restype = C.c_double
+    D.__wrap_averagePhotonEnergy.restype = C.c_double
+
+    class PhotonList(C.Structure):
+        _fields_ = [("photons", C.c_void_p), ("sorted_indexes", C.POINTER(C.c_int)), ("num_photons", C.c_int),
+                    ("num_null_photons", C.c_int), ("list_capacity", C.c_int)]
+
+    class Hydro(C.Structure):
+        _fields_ = ([("num_elements", C.c_int)] + [(f, C.POINTER(C.c_double)) for f in api.HYDRO_FIELDS] +
+                    [("r0_domain", C.c_double * 2), ("r1_domain", C.c_double * 2), ("r2_domain", C.c_double * 2),
+                     ("fps", C.c_double), ("scatt_frame_number", C.c_int), ("inj_frame_number", C.c_int),
+                     ("last_frame", C.c_int), ("increment_inj_frame", C.c_int), ("increment_scatt_frame", C.c_int),
+                     ("grid", C.c_void_p)])
+
+    cfg, hydro, photons, frame = synth.workload("C2", scale=1.0 / 16, n_photons=500, seed=4)
+    c = lib.Config(lib.ABI_VERSION, cfg["dimensions"], cfg["geometry"], cfg["stokes"], cfg["tau_calculation"],
+                   cfg["cyclosynch"], cfg["b_field_calc"], cfg["epsilon_b"], 0, 0, 99, 2, 0, None)
+    assert D.mcrat_b200_dropin_configure(C.byref(c)) == 0
+    ph = np.ascontiguousarray(photons.copy())
+    sorted_idx = np.zeros(ph.size, dtype=np.int32)
+    pl = PhotonList(ph.ctypes.data, sorted_idx.ctypes.data_as(C.POINTER(C.c_int)), ph.size, 0, ph.size)
+    h = Hydro()
+    keep = []
+    h.num_elements = hydro["num_elements"]
+    for f in api.HYDRO_FIELDS:
+        a = np.ascontiguousarray(hydro[f], dtype=np.float64)
+        keep.append(a)
+        setattr(h, f, a.ctypes.data_as(C.POINTER(C.c_double)))
+    for k in ("r0_domain", "r1_domain", "r2_domain"):
+        getattr(h, k)[0], getattr(h, k)[1] = hydro[k]
+    h.fps = hydro["fps"]
+    # Src/mcrat.c:754-851
+    remaining, sw, scatt = 3e-5, 1, C.c_int(0)
+    absn, idx = C.c_int(0), C.c_int(0)
+    iters = 0
+    while remaining > 0 and iters < 400:
+        D.__wrap_findContainingHydroCell(C.byref(pl), C.byref(h), C.c_int(sw), None, None)
+        D.__wrap_calcMeanFreePath(C.byref(pl), C.byref(h), None, None)
+        sw = 0
+        if ph["time_to_scatter"][sorted_idx[0]] < remaining:
+            dt = D.__wrap_photonEvent(C.byref(pl), C.c_double(remaining), C.byref(h), C.byref(idx), C.byref(scatt),
+                                      C.byref(absn), None, None)
+            remaining -= dt
+            assert ph["type"][idx.value] == b"i"
+        else:
+            D.__wrap_updatePhotonPosition(C.byref(pl), C.c_double(remaining), None)
+            remaining = 0
+        iters += 1
+    assert remaining == 0 and scatt.value > 10
+    # the same frame through the oracle with the same Philox streams
+    o = api.Oracle(cfg)
+    o.set_hydro(hydro)
+    o.set_photons(photons)
+    ost = o.run_frame(api.OracleRng("philox", seed=99, shard=2), frame["time_now"], 3e-5, max_iters=-1)
+    assert ost["scatterings"] == scatt.value and ost["iterations"] == iters
+    compare_photons(ph, o.photons(), label="drop-in", stokes_tol=1e-9, hydro=hydro)
+    e = D.__wrap_averagePhotonEnergy(C.byref(pl))
+    assert abs(e / ((ph["p0"] * ph["weight"]).sum() * synth.C_LIGHT / ph["weight"].sum()) - 1) < 1e-12
+    D.mcrat_b200_dropin_shutdown()
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] at full size (1e5 photons x 1,048,576 cells): properties that do not need
+    the oracle -- containment of every located photon, first-match on a sample, null 4-vectors,
+    Stokes bounds, idempotence of the rescan, bookkeeping identities."""
+    cfg, hydro, photons, frame = synth.workload("C2")
+    hp = HotPath(cfg, seed=42, num_shards=16)
+    hp.set_hydro(hydro)
+    hp.set_photons(photons)
+    st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=300, switch=1)
+    assert st["cell_evals"] >= photons.size * hydro["num_elements"] * 0.99
+    assert st["scatterings"] == 300 * 16 and st["photon_slots"] == 300 * photons.size
+    ph = hp.get_photons()
+    assert ph["num_scatt"].sum() == st["scatterings"]
+    idx = ph["nearest_block_index"]
+    live = idx >= 0
+    assert live.mean() > 0.99
+    h0, h1, _ = synth.mcrat_to_hydro(cfg["dimensions"], cfg["geometry"], ph["r0"], ph["r1"], ph["r2"])
+    i = idx[live]
+    # every located photon is inside its cell (checkInBlock, Src/geometry.c:401) ...
+    inside = (2 * np.abs(h0[live] - hydro["r0"][i]) - hydro["r0_size"][i] <= 0) & \
+             (2 * np.abs(h1[live] - hydro["r1"][i]) - hydro["r1_size"][i] <= 0)
+    moved = ph["num_scatt"][live] >= 0
+    # (photons pushed after their last locate may have left the cell; re-locate first)
+    ev, ms = hp.rescan_all()
+    ph2 = hp.get_photons()
+    i2 = ph2["nearest_block_index"]
+    live2 = i2 >= 0
+    inside2 = (2 * np.abs(h0[live2] - hydro["r0"][i2[live2]]) - hydro["r0_size"][i2[live2]] <= 0) & \
+              (2 * np.abs(h1[live2] - hydro["r1"][i2[live2]]) - hydro["r1_size"][i2[live2]] <= 0)
+    assert inside2.all()
+    # ... and it is the lowest-index containing cell (first match) on a sample, by brute force
+    samp = np.nonzero(live2)[0][:: max(1, live2.sum() // 200)]
+    want = synth.locate_cells_bruteforce(hydro, h0[samp], h1[samp], np.zeros(samp.size))
+    assert np.array_equal(want, i2[samp])
+    # the rescan is idempotent
+    ev, ms = hp.rescan_all()
+    assert np.array_equal(hp.get_photons()["nearest_block_index"], i2)
+    assert ev == live2.sum() * hydro["num_elements"]
+    # photons stay on the light cone; Stokes vectors stay normalised and physical
+    pn = np.sqrt(ph["p1"] ** 2 + ph["p2"] ** 2 + ph["p3"] ** 2)
+    assert np.max(np.abs(pn / ph["p0"] - 1)) < 4e-16
+    assert np.all(ph["s0"] == 1.0) and np.all(ph["s1"] ** 2 + ph["s2"] ** 2 + ph["s3"] ** 2 <= 1 + 1e-9)
+    assert np.isfinite(ph["time_to_scatter"]).all() and (ph["time_to_scatter"] > 0).all()
