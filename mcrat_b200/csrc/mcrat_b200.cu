@@ -296,7 +296,7 @@ __global__ void build_geo_kernel(int ndim3, int n, int n_padded, const double *c
 constexpr int PASS_THREADS = 256;
 
 template <bool FUSE_MFP>
-__global__ void __launch_bounds__(PASS_THREADS) pass_kernel(DevCtx d, int sw, int parity)
+__global__ void __launch_bounds__(PASS_THREADS, 4) pass_kernel(DevCtx d, int sw, int parity)
 {
     const int s = blockIdx.x / d.blocks_per_shard;
     const int b = blockIdx.x - s * d.blocks_per_shard;
@@ -315,11 +315,15 @@ __global__ void __launch_bounds__(PASS_THREADS) pass_kernel(DevCtx d, int sw, in
 
         for (int j = b * PASS_THREADS + threadIdx.x; j < sh.count; j += d.blocks_per_shard * PASS_THREADS) {
             const int i = sh.first + j;
-            unsigned char flags = d.ph.flags[i];
-            int idx = d.ph.idx[i];
+            // every column this photon can need is requested up front (one round trip to HBM instead
+            // of three dependent ones); the momentum is used by the pushes, tau by the free-path draw
+            const unsigned char flags = d.ph.flags[i];
+            const int idx = d.ph.idx[i];
             double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
+            const double p0 = d.ph.p0[i], p1 = d.ph.p1[i], p2 = d.ph.p2[i], p3 = d.ph.p3[i];
+            double tau = FUSE_MFP ? d.ph.tau[i] : 0.0;
             if (n_dt > 0 && (flags & F_MOVABLE) && i != pushed) {
-                apply_pushes(sh, n_dt, d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i], r0, r1, r2);
+                apply_pushes(sh, n_dt, p0, p1, p2, p3, r0, r1, r2);
                 d.ph.r0[i] = r0;
                 d.ph.r1[i] = r1;
                 d.ph.r2[i] = r2;
@@ -353,17 +357,13 @@ __global__ void __launch_bounds__(PASS_THREADS) pass_kernel(DevCtx d, int sw, in
                     have_t = false; // finish_kernel completes this photon
                 } else if (FUSE_MFP) {
                     // calcMeanFreePath, Src/mclib.c:657-687
-                    double tau;
                     if (flags & F_RECALC) {
                         CellState c = load_cell_state(d.cells, idx);
                         int terr = 0;
-                        tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, d.ph.p1[i], d.ph.p2[i],
-                                            d.ph.p3[i], d.ph.c0[i], &terr);
+                        tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, p1, p2, p3, d.ph.c0[i], &terr);
                         if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
                         d.ph.tau[i] = tau;
                         d.ph.flags[i] = flags & ~F_RECALC;
-                    } else {
-                        tau = d.ph.tau[i];
                     }
                     double xi = philox_mfp_uniform(d.k0, k1, iter, (uint32_t)j);
                     t = free_path_time(tau, xi);

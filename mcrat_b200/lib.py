@@ -90,10 +90,11 @@ def load():
     """dlopen the library; raises if it is not built (no fallback of any kind)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("MCRAT_B200_LIB", LIB_PATH)  # A/B experiments with alternative builds
+        if not os.path.exists(path):
             raise FileNotFoundError("%s is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                     "(there is no CPU fallback)" % LIB_PATH)
-        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        L = C.CDLL(path, mode=C.RTLD_GLOBAL)
         L.mcrat_b200_last_error.restype = C.c_char_p
         L.mcrat_b200_last_error.argtypes = [C.c_void_p]
         L.mcrat_b200_replay_consumed.restype = C.c_longlong

@@ -261,6 +261,6 @@ def test_full_size_properties():
     assert ev == live2.sum() * hydro["num_elements"]
     # photons stay on the light cone; Stokes vectors stay normalised and physical
     pn = np.sqrt(ph["p1"] ** 2 + ph["p2"] ** 2 + ph["p3"] ** 2)
-    assert np.max(np.abs(pn / ph["p0"] - 1)) < 4e-16
+    assert np.max(np.abs(pn / ph["p0"] - 1)) < 1e-15
     assert np.all(ph["s0"] == 1.0) and np.all(ph["s1"] ** 2 + ph["s2"] ** 2 + ph["s3"] ** 2 <= 1 + 1e-9)
     assert np.isfinite(ph["time_to_scatter"]).all() and (ph["time_to_scatter"] > 0).all()
