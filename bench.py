@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "scatterings/sec"
 UNIT = "scatterings/s"
-WORKLOAD = "C2: 2-D cylindrical FLASH-shape GRB jet, 1024x1024 cells, 1e5 photons/shard, Stokes on"
+WORKLOAD = "C2: 2-D cylindrical FLASH-shape GRB jet, 1024x1024 cells, 1e5 photons per GPU, Stokes on"
 
 
 _T0 = time.time()
@@ -109,61 +109,68 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own sources (oracle/_ref) or, if absent, the oracle port
 # ------------------------------------------------------------------------------------------------
-def _cpu_rank(rank, nranks, cfg, hydro, photons, frame, iters, steps, warmup, kind, barrier, out):
+def _cpu_rank(rank, nranks, shards, cfg, hydro, photons, frame, iters, steps, warmup, kind, barrier, out):
+    """One host core: runs its share of the shards (rank, rank + nranks, ...) one after the other."""
     from oracle import api
-    sl = slice(rank * photons.size // nranks, (rank + 1) * photons.size // nranks)
-    ph = photons[sl]
+    from mcrat_b200 import shard as shardlib
+    ranges = shardlib.sub_shard_ranges(photons.size, shards)
+    mine = list(range(rank, len(ranges), nranks))
     if kind == "reference":
         eng = api.RefLib("c2_2d_cyl_stokes")
         eng.set_hydro(hydro)
-        eng.set_photons(ph)
-        rng, _ = eng.new_rng(seed=rank + 1)
     else:
         eng = api.Oracle(cfg)
         eng.set_hydro(hydro)
-        eng.set_photons(ph)
-        rng = api.OracleRng("ranlxs0", seed=rank + 1)
-    time_now = frame["time_now"]
+    lists = {s: photons[ranges[s][0]:ranges[s][0] + ranges[s][1]].copy() for s in mine}
+    clocks = {s: frame["time_now"] for s in mine}
+    rngs = {}
+    for s in mine:
+        rngs[s] = eng.new_rng(seed=s + 1)[0] if kind == "reference" else api.OracleRng("ranlxs0", seed=s + 1)
     scatt = 0
     t_steps = []
-    for s in range(warmup + steps):
+    for k in range(warmup + steps):
         barrier.wait()
         t0 = time.perf_counter()
-        st = eng.run_frame(rng, time_now, 1.0 / frame["fps"], max_iters=iters, switch=1)
+        for s in mine:
+            eng.set_photons(lists[s])
+            st = eng.run_frame(rngs[s], clocks[s], 1.0 / frame["fps"], max_iters=iters, switch=1)
+            lists[s] = eng.photons()
+            clocks[s] = st["time_now"]
+            if k >= warmup:
+                scatt += st["scatterings"]
         t1 = time.perf_counter()
-        time_now = st["time_now"]
-        if s >= warmup:
+        if k >= warmup:
             t_steps.append(t1 - t0)
-            scatt += st["scatterings"]
     out.put((rank, scatt, t_steps))
 
 
-def run_cpu_arm(cfg, hydro, photons, frame, iters, steps, warmup):
-    """R independent ranks (one per host core), each owning a contiguous slice of the photons --
-    the reference's own way of using more cores (no exchange inside the frame loop)."""
+def run_cpu_arm(cfg, hydro, photons, frame, iters, steps, warmup, shards):
+    """The reference's own CPU code on all host cores.  The job is decomposed into `shards`
+    independent ranks -- the reference's own way of using more cores, no exchange inside the frame
+    loop -- exactly as on the GPU arm; each core runs its share of them one after the other."""
     from oracle import api
     kind = "reference" if api.ref_available("c2_2d_cyl_stokes") else "port"
     if kind == "port":
         api.build_oracle()
     ncores = len(os.sched_getaffinity(0))
-    nranks = max(1, min(ncores, photons.size // 256))
+    nranks = max(1, min(ncores, shards))
     ctx = mp.get_context("fork")
     barrier = ctx.Barrier(nranks)
     out = ctx.Queue()
-    procs = [ctx.Process(target=_cpu_rank, args=(r, nranks, cfg, hydro, photons, frame, iters, steps, warmup, kind,
-                                                 barrier, out)) for r in range(nranks)]
+    procs = [ctx.Process(target=_cpu_rank, args=(r, nranks, shards, cfg, hydro, photons, frame, iters, steps, warmup,
+                                                 kind, barrier, out)) for r in range(nranks)]
     for p in procs:
         p.start()
     res = [out.get() for _ in procs]
     for p in procs:
         p.join()
     scatt = sum(r[1] for r in res)
-    # per step the job takes as long as its slowest rank
+    # per step the job takes as long as its slowest core
     per_step = [max(r[2][k] for r in res) for k in range(steps)]
     total = sum(per_step)
     return dict(value=scatt / total, unit=UNIT, cores=nranks, kind=kind, seconds=total, ms_per_step=1e3 * total / steps,
-                sample="%d ranks x %d photons, full rescan + %d loop iterations per rank and step, %d step(s)"
-                       % (nranks, photons.size // nranks, iters, steps))
+                sample="%d shards x %d photons on %d cores, full rescan + %d loop iterations per shard and step, "
+                       "%d step(s)" % (shards, photons.size // shards, nranks, iters, steps))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -179,8 +186,8 @@ def main():
     ncores = len(os.sched_getaffinity(0))
     shards = args.shards if args.shards > 0 else max(1, min(ncores, args.photons // 256))
     config = {"workload": WORKLOAD if (args.scale == 1.0 and args.photons == 100000) else
-              "C2 reduced: scale=%g, %d photons/shard" % (args.scale, args.photons),
-              "cells": int(hydro["num_elements"]), "photons_per_shard": int(photons.size),
+              "C2 reduced: scale=%g, %d photons/GPU" % (args.scale, args.photons),
+              "cells": int(hydro["num_elements"]), "photons_per_gpu": int(photons.size),
               "loop_iterations_per_step": args.iters, "gpu_ranks": world, "shards_per_gpu": shards,
               "decomposition": "%d independent shards (reference ranks) of %d photons per GPU, each advancing "
                                "its own time-ordered scatter sequence" % (shards, photons.size // shards),
@@ -191,7 +198,7 @@ def main():
         if rank != 0:
             return 0
         cpu_iters = args.cpu_iters or args.iters
-        res = run_cpu_arm(cfg, hydro, photons, frame, cpu_iters, args.steps, args.warmup)
+        res = run_cpu_arm(cfg, hydro, photons, frame, cpu_iters, args.steps, args.warmup, shards)
         config["loop_iterations_per_step"] = cpu_iters
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
@@ -344,7 +351,7 @@ def main():
         log("cpu baseline")
         if not args.no_cpu_baseline and world == 1:
             cpu_iters = args.cpu_iters or args.iters
-            r = run_cpu_arm(cfg, hydro, photons, frame, cpu_iters, 1, 0)
+            r = run_cpu_arm(cfg, hydro, photons, frame, cpu_iters, 1, 0, shards)
             cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
         line = {"metric": METRIC, "value": scatt_all / (t_max * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_max / args.steps,
