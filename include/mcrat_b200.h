@@ -122,6 +122,13 @@ int mcrat_b200_set_hydro(mcrat_b200_ctx *ctx, int num_elements, const double *co
                          double fps, int scatt_frame_number, int inj_frame_number);
 /* thermal_table[N_PH_E+1][N_T+1] of Src/hot_x_section.c:15 (221 x 81, log10 sigma/sigma_T) */
 int mcrat_b200_set_thermal_table(mcrat_b200_ctx *ctx, const double *table);
+/* createHotCrossSection (Src/hot_x_section.c:82-206) on the device: every table point is the
+ * reference's plain Monte Carlo integral with `calls` samples (the reference uses 500000,
+ * :348) from a Philox stream keyed by the point; the table is installed in the context and, if
+ * table_out != NULL, copied out in the reference's [N_PH_E+1][N_T+1] order (write it with the
+ * layout of Src/hot_x_section.c:116-131 to interoperate with thermal_hot_x_section.dat). */
+int mcrat_b200_build_thermal_table(mcrat_b200_ctx *ctx, long long calls, uint64_t seed, double *table_out,
+                                   float *elapsed_ms);
 /* Upload / download the photon list (`struct photonList`.photons, Src/mcrat.h:173-180). */
 int mcrat_b200_set_photons(mcrat_b200_ctx *ctx, const mcrat_photon *photons, int list_capacity);
 int mcrat_b200_get_photons(mcrat_b200_ctx *ctx, mcrat_photon *photons, int list_capacity);

@@ -1067,6 +1067,68 @@ __global__ void __launch_bounds__(256) cs_absorb_kernel(DevCtx d)
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// K7: thermal (hot) Klein-Nishina cross-section table, Src/hot_x_section.c:82-206.
+// One block per table point (221 x 81); each point is the reference's plain Monte Carlo estimate
+// (Src/hot_x_section.c:324-357: `calls` uniform samples of (gamma, mu) over
+// [1, 1 + 12 theta] x [-1, 1], integrand = Maxwell-Juttner pdf x boosted KN cross section,
+// result = 0.5 * volume * mean), drawn from a Philox stream keyed by the point.
+// ------------------------------------------------------------------------------------------
+__device__ inline double maxwell_juttner_pdf(double gamma, double theta, double normalization)
+{
+    // Src/electron.c:538-560 singleMaxwellJuttner (normalization computed once per point)
+    return ((gamma * sqrt(gamma * gamma - 1.) / (theta * normalization)) * exp(-(gamma - 1.) / theta));
+}
+
+__device__ inline double boosted_cross_section(double norm_ph_comv, double mu, double gamma)
+{
+    // Src/hot_x_section.c:369-400 boostedCrossSection
+    double beta = sqrt(gamma * gamma - 1.) / gamma;
+    double norm_ph_e = norm_ph_comv * gamma * (1. - mu * beta);
+    return kn_cross_section(norm_ph_e) * (1. - mu * beta);
+}
+
+__global__ void __launch_bounds__(256) hot_table_kernel(double *table, long long calls, uint32_t k0, uint32_t k1)
+{
+    const int point = blockIdx.x; // i * (N_T + 1) + j, the reference's loop order (:90-105)
+    const int i = point / (N_T + 1), j = point - i * (N_T + 1);
+    const double dt = (LOG_T_MAX - LOG_T_MIN) / N_T, dph_e = (LOG_PH_E_MAX - LOG_PH_E_MIN) / N_PH_E;
+    const double comv_ph_e = pow(10., LOG_PH_E_MIN + i * dph_e);
+    const double theta = pow(10., LOG_T_MIN + j * dt);
+    double result;
+    if (theta < pow(10., LOG_T_MIN) && comv_ph_e < pow(10., LOG_PH_E_MIN)) {
+        result = 1; // :336-337
+    } else if (theta < pow(10., LOG_T_MIN)) {
+        result = kn_cross_section(comv_ph_e); // :338-339
+    } else {
+        double normalization;
+        if (theta > 1.e-2)
+            normalization = bessel_K2(1. / theta) * exp(1. / theta);
+        else
+            normalization = sqrt(PI * theta / 2.);
+        const double xl0 = 1, xu0 = 1. + 12 * theta;
+        double sum = 0;
+        for (long long n = threadIdx.x; n < calls; n += 256) {
+            double u1, u2;
+            philox_doubles((uint32_t)n, (uint32_t)(n >> 32), (uint32_t)point, 2u, k0, k1, u1, u2);
+            double gamma = xl0 + u1 * (xu0 - xl0);
+            double mu = -1 + u2 * (1 - (-1));
+            sum += maxwell_juttner_pdf(gamma, theta, normalization) * boosted_cross_section(comv_ph_e, mu, gamma);
+        }
+        __shared__ double red[8];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+        __syncthreads();
+        double tot = 0;
+        for (int k = 0; k < 8; ++k) tot += red[k];
+        const double vol = (xu0 - xl0) * (1 - (-1));
+        result = 0.5 * (vol * (tot / (double)calls));
+    }
+    if (threadIdx.x == 0) table[point] = log10(result);
+}
+
 // ------------------------------------------------------------------------------------------
 // photon statistics (Src/mclib.c:1358-1515): per-block partials, finished on the host
 // ------------------------------------------------------------------------------------------
@@ -2078,6 +2140,36 @@ API int mcrat_b200_rescan_all(mcrat_b200_ctx *ctx, long long *cell_evals, float 
     ctx->times.scan_ms += ms;
     ctx->times.scan_launches++;
     return device_error(ctx);
+}
+
+// createHotCrossSection, Src/hot_x_section.c:82-206, on the device; the table is also installed
+// in the context (as mcrat_b200_set_thermal_table would)
+API int mcrat_b200_build_thermal_table(mcrat_b200_ctx *ctx, long long calls, uint64_t seed, double *table_out,
+                                       float *elapsed_ms)
+{
+    if (!ctx || calls < 1) return ctx ? fail(ctx, MCRAT_B200_ERR_ARG, "build_thermal_table: calls >= 1") : MCRAT_B200_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int npts = (N_PH_E + 1) * (N_T + 1);
+    double *tab = nullptr;
+    CK(cudaMalloc((void **)&tab, npts * sizeof(double)));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    hot_table_kernel<<<npts, 256, 0, ctx->stream>>>(tab, calls, (uint32_t)seed ^ 0x4D435261u, (uint32_t)(seed >> 32));
+    if (int rc = check_launch(ctx, "hot_table_kernel")) {
+        cudaFree(tab);
+        return rc;
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    std::vector<double> host(npts);
+    CK(cudaMemcpyAsync(host.data(), tab, npts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(tab);
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (elapsed_ms) *elapsed_ms = ms;
+    for (int k = 0; k < npts; ++k)
+        if (host[k] != host[k]) return fail(ctx, MCRAT_B200_ERR_STATE, "NaN in the hot cross-section table (Src/hot_x_section.c:97-103)");
+    if (table_out) memcpy(table_out, host.data(), npts * sizeof(double));
+    return mcrat_b200_set_thermal_table(ctx, host.data());
 }
 
 API int mcrat_b200_measure_fp64_peak(mcrat_b200_ctx *ctx, double *ginstr_per_s)

@@ -61,7 +61,7 @@ class KernelTimes(C.Structure):
 EXPORTS = [
     "mcrat_b200_abi_version", "mcrat_b200_device_count", "mcrat_b200_create", "mcrat_b200_destroy",
     "mcrat_b200_last_error", "mcrat_b200_synchronize", "mcrat_b200_set_hydro", "mcrat_b200_set_thermal_table",
-    "mcrat_b200_set_photons", "mcrat_b200_get_photons", "mcrat_b200_get_photon", "mcrat_b200_list_capacity",
+    "mcrat_b200_build_thermal_table", "mcrat_b200_set_photons", "mcrat_b200_get_photons", "mcrat_b200_get_photon", "mcrat_b200_list_capacity",
     "mcrat_b200_set_num_shards", "mcrat_b200_num_shards", "mcrat_b200_get_shard_stats",
     "mcrat_b200_set_replay_uniforms", "mcrat_b200_replay_consumed", "mcrat_b200_find_containing_hydro_cell",
     "mcrat_b200_calc_mean_free_path", "mcrat_b200_photon_event", "mcrat_b200_update_photon_position",
@@ -173,6 +173,13 @@ class HotPath:
         t = np.ascontiguousarray(table, dtype=np.float64)
         assert t.shape == (221, 81)
         self._ck(self.L.mcrat_b200_set_thermal_table(self.ctx, _dp(t)))
+
+    def build_thermal_table(self, calls=500000, seed=1):
+        """Hot cross-section table built on the device (returns the 221 x 81 table and the kernel time in ms)."""
+        t = np.zeros((221, 81), dtype=np.float64)
+        ms = C.c_float(0)
+        self._ck(self.L.mcrat_b200_build_thermal_table(self.ctx, C.c_longlong(calls), C.c_uint64(seed), _dp(t), C.byref(ms)))
+        return t, ms.value
 
     def set_photons(self, photons):
         ph = np.ascontiguousarray(photons, dtype=PHOTON_DTYPE)
