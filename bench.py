@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--shards", type=int, default=0,
                     help="sub-shards (independent reference ranks) per GPU; 0 = one per host core, the "
                          "decomposition the reference arm uses")
+    ap.add_argument("--full-scan", action="store_true",
+                    help="re-locate with the full photon x cell scan (K1) instead of the bounding-box index")
     ap.add_argument("--cpu-iters", type=int, default=0, help="iterations per CPU rank and step (0: same as --iters)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pass-roofline", action="store_true")
@@ -192,7 +194,10 @@ def main():
               "decomposition": "%d independent shards (reference ranks) of %d photons per GPU, each advancing "
                                "its own time-ordered scatter sequence" % (shards, photons.size // shards),
               "step": "full photon x cell rescan (new hydro frame) + loop iterations; steps continue one simulation",
-              "l2": "flushed between timed steps (256 MiB write)"}
+              "l2": "flushed between timed steps (256 MiB write)",
+              "relocation": "full photon x cell scan (K1)" if args.full_scan else
+              "bounding-box index over the cells in array order (identical first-match results; K1 timed "
+              "separately for the roofline)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -228,7 +233,8 @@ def main():
         torch.cuda.synchronize()
 
     stream = torch.cuda.current_stream().cuda_stream
-    hp = HotPath(cfg, device=local_rank, seed=20261018, shard=rank * shards, stream=stream, num_shards=shards)
+    hp = HotPath(cfg, device=local_rank, seed=20261018, shard=rank * shards, stream=stream, num_shards=shards,
+                 scan_index=not args.full_scan)
     hp.set_hydro(hydro)
     hp.set_photons(photons)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")

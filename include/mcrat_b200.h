@@ -79,6 +79,9 @@ typedef struct mcrat_b200_config {
     uint32_t shard;        /* shard (rank) id mixed into the Philox key */
     int profile;           /* 1: time each kernel class with CUDA events (see kernel_times) */
     void *stream;          /* cudaStream_t to run on, or NULL to let the library create one */
+    int scan_index;        /* 0: every re-location is the full photon x cell scan of the reference (K1);
+                            * 1: the same first-match search through a bounding-box index over the
+                            *    cells in array order (identical results, far fewer tests) */
 } mcrat_b200_config;
 
 typedef struct mcrat_b200_ctx mcrat_b200_ctx;
@@ -90,6 +93,7 @@ typedef struct mcrat_b200_frame_stats {
     long long relocations;  /* num_photons_find_new_element, Src/mcrat.c:768 */
     long long photon_slots; /* sum over iterations of list_capacity (photon-iterations) */
     long long cell_evals;   /* photon-cell containment tests executed by the scan kernels */
+    long long box_evals;    /* photon-box tests executed by the bounding-box index (scan_index = 1) */
     double time_now;        /* clock of sub-shard 0 */
     double last_time_step;
     int last_scattered_index;

@@ -63,7 +63,13 @@ struct CellCols {
     const double2 *geoB; // 3-D: (h1, h2)
     const double *r0, *r1, *r2, *v0, *v1, *v2, *dens, *dens_lab, *temp, *gamma, *B0, *B1, *B2;
     double dom[6];
+    // optional two-level bounding-box index over consecutive cells (BOX_T cells per level-1 box,
+    // BOX_T level-1 boxes per level-2 box): 2 doubles (lo, hi) per dimension, 3 dimensions stored
+    const double *box1, *box2;
+    int nbox1, nbox2;
 };
+
+constexpr int BOX_T = 32;
 
 // One sub-shard = one "rank" of the reference: a contiguous range of photon slots with its own
 // clock, its own time-ordered event sequence (shard-local arg-min, exactly as per MPI rank,
@@ -83,7 +89,7 @@ struct ShardState {
 struct GlobalState {
     int reloc_count[2];
     int error, not_found, n_stopped;
-    long long cell_evals, max_iters;
+    long long cell_evals, box_evals, max_iters;
     unsigned long long replay_cursor, replay_base, replay_n;
     int abs_count, cs_scatt_count;
     double abs_weight;
@@ -588,6 +594,104 @@ __global__ void __launch_bounds__(256) scan_few_kernel(DevCtx d, int parity)
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd((unsigned long long *)&d.gs->cell_evals, (unsigned long long)count * (unsigned long long)d.cells.n);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1c: the same first-match search through a two-level bounding-box index (opt-in,
+// mcrat_b200_config.scan_index).  The reference carries a disabled uniform-bucket accelerator
+// (Src/geometry.c:423-676, switched off at Src/mcrat_io.c:1985); this index is built over the
+// cells *in array order*, so walking boxes and cells in ascending index and stopping at the
+// first hit returns exactly the cell findContainingBlock returns (lowest containing index).
+// A box is padded outward by a few ulps so that every cell test that can succeed is reached.
+// ------------------------------------------------------------------------------------------
+__global__ void build_box1_kernel(int ndim3, int n, const double4 *geoA, const double2 *geoB, double *box1, int nbox1)
+{
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nbox1; b += gridDim.x * blockDim.x) {
+        double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+        for (int c = b * BOX_T; c < min(n, b * BOX_T + BOX_T); ++c) {
+            double4 a = geoA[c];
+            double cc[3], hh[3];
+            if (!ndim3) {
+                cc[0] = a.x; cc[1] = a.y; cc[2] = 0; hh[0] = a.z; hh[1] = a.w; hh[2] = 0;
+            } else {
+                double2 q = geoB[c];
+                cc[0] = a.x; cc[1] = a.y; cc[2] = a.z; hh[0] = a.w; hh[1] = q.x; hh[2] = q.y;
+            }
+            for (int k = 0; k < 3; ++k) {
+                double pad = 8.0 * 2.220446049250313e-16 * (fabs(cc[k]) + fabs(hh[k]));
+                lo[k] = fmin(lo[k], cc[k] - hh[k] - pad);
+                hi[k] = fmax(hi[k], cc[k] + hh[k] + pad);
+            }
+        }
+        for (int k = 0; k < 3; ++k) {
+            box1[6 * b + 2 * k] = lo[k];
+            box1[6 * b + 2 * k + 1] = hi[k];
+        }
+    }
+}
+
+__global__ void build_box2_kernel(const double *box1, int nbox1, double *box2, int nbox2)
+{
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nbox2; b += gridDim.x * blockDim.x) {
+        double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+        for (int c = b * BOX_T; c < min(nbox1, b * BOX_T + BOX_T); ++c)
+            for (int k = 0; k < 3; ++k) {
+                lo[k] = fmin(lo[k], box1[6 * c + 2 * k]);
+                hi[k] = fmax(hi[k], box1[6 * c + 2 * k + 1]);
+            }
+        for (int k = 0; k < 3; ++k) {
+            box2[6 * b + 2 * k] = lo[k];
+            box2[6 * b + 2 * k + 1] = hi[k];
+        }
+    }
+}
+
+__device__ __forceinline__ bool in_box(int ndim3, const double *bx, double x0, double x1, double x2)
+{
+    bool in = (x0 >= bx[0]) & (x0 <= bx[1]) & (x1 >= bx[2]) & (x1 <= bx[3]);
+    if (ndim3) in = in & (x2 >= bx[4]) & (x2 <= bx[5]);
+    return in;
+}
+
+__global__ void __launch_bounds__(128) scan_index_kernel(DevCtx d, int parity)
+{
+    const GlobalState &gs = *d.gs;
+    if (gs.error != 0) return;
+    const int count = gs.reloc_count[parity];
+    const int ndim3 = (d.dims == D_THREE);
+    long long cells_tested = 0, boxes_tested = 0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
+        const double x0 = d.reloc_h0[j], x1 = d.reloc_h1[j], x2 = d.reloc_h2[j];
+        int best = INT_MAX;
+        for (int b2 = 0; b2 < d.cells.nbox2 && best == INT_MAX; ++b2) {
+            boxes_tested++;
+            if (!in_box(ndim3, d.cells.box2 + 6 * b2, x0, x1, x2)) continue;
+            const int e1 = min(d.cells.nbox1, b2 * BOX_T + BOX_T);
+            for (int b1 = b2 * BOX_T; b1 < e1 && best == INT_MAX; ++b1) {
+                boxes_tested++;
+                if (!in_box(ndim3, d.cells.box1 + 6 * b1, x0, x1, x2)) continue;
+                const int ec = min(d.cells.n, b1 * BOX_T + BOX_T);
+                for (int c = b1 * BOX_T; c < ec; ++c) {
+                    cells_tested++;
+                    if (in_cell(ndim3, d.cells, c, x0, x1, x2)) {
+                        best = c;
+                        break;
+                    }
+                }
+            }
+        }
+        d.reloc_best[j] = best;
+    }
+    // one atomic pair per warp
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        cells_tested += __shfl_xor_sync(0xffffffffu, cells_tested, off);
+        boxes_tested += __shfl_xor_sync(0xffffffffu, boxes_tested, off);
+    }
+    if ((threadIdx.x & 31) == 0 && (cells_tested | boxes_tested)) {
+        atomicAdd((unsigned long long *)&d.gs->cell_evals, (unsigned long long)cells_tested);
+        atomicAdd((unsigned long long *)&d.gs->box_evals, (unsigned long long)boxes_tested);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1513,6 +1617,13 @@ API int mcrat_b200_set_hydro(mcrat_b200_ctx *ctx, int n, const double *const *fi
         CK(dev_alloc(ctx->cell_allocs, &geoB, (size_t)(ndim3 ? n_padded : 1)));
         c.geoA = geoA;
         c.geoB = geoB;
+        c.nbox1 = (n + BOX_T - 1) / BOX_T;
+        c.nbox2 = (c.nbox1 + BOX_T - 1) / BOX_T;
+        double *b1 = nullptr, *b2 = nullptr;
+        CK(dev_alloc(ctx->cell_allocs, &b1, (size_t)6 * (c.nbox1 ? c.nbox1 : 1)));
+        CK(dev_alloc(ctx->cell_allocs, &b2, (size_t)6 * (c.nbox2 ? c.nbox2 : 1)));
+        c.box1 = b1;
+        c.box2 = b2;
     }
     c.n = n;
     c.n_padded = n_padded;
@@ -1531,6 +1642,11 @@ API int mcrat_b200_set_hydro(mcrat_b200_ctx *ctx, int n, const double *const *fi
     build_geo_kernel<<<grid_for(ctx, c.n_padded, 256, 8), 256, 0, ctx->stream>>>(
         ndim3, n, c.n_padded, cols[0], cols[1], cols[2], cols[3], cols[4], cols[5], (double4 *)c.geoA, (double2 *)c.geoB);
     if (int rc = check_launch(ctx, "build_geo_kernel")) return rc;
+    if (ctx->cfg.scan_index) {
+        build_box1_kernel<<<grid_for(ctx, c.nbox1, 128, 8), 128, 0, ctx->stream>>>(ndim3, n, c.geoA, c.geoB, (double *)c.box1, c.nbox1);
+        build_box2_kernel<<<grid_for(ctx, c.nbox2, 128, 8), 128, 0, ctx->stream>>>(c.box1, c.nbox1, (double *)c.box2, c.nbox2);
+        if (int rc = check_launch(ctx, "build_box_kernels", 2)) return rc;
+    }
     for (int k = 0; k < 6; ++k) c.dom[k] = domains[k];
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_hydro = true;
@@ -1784,7 +1900,13 @@ static int launch_locate(mcrat_b200_ctx *ctx, int sw, int &parity_out)
         if (int rc = check_launch(ctx, "pass_kernel")) return rc;
     }
     int nb_fin;
-    if (sw == 1) {
+    if (ctx->cfg.scan_index) {
+        Timed t(ctx, KC_SCAN);
+        const int g = (sw == 1) ? grid_for(ctx, ctx->d.cap, 128, 16) : 8;
+        scan_index_kernel<<<g, 128, 0, ctx->stream>>>(ctx->d, parity);
+        if (int rc = check_launch(ctx, "scan_index_kernel")) return rc;
+        nb_fin = (sw == 1) ? grid_for(ctx, ctx->d.cap, FIN_THREADS, 8) : 8;
+    } else if (sw == 1) {
         if (int rc = launch_scan_full(ctx, parity, ctx->d.cap)) return rc;
         nb_fin = grid_for(ctx, ctx->d.cap, FIN_THREADS, 8);
     } else {
@@ -2012,6 +2134,7 @@ static void fill_stats(const ShardState &s, const ShardState &b, mcrat_b200_fram
     o->relocations = s.reloc_total - b.reloc_total;
     o->photon_slots = s.slots - b.slots;
     o->cell_evals = 0;
+    o->box_evals = 0;
     o->time_now = s.time_now;
     o->last_time_step = s.last_time_step;
     o->last_scattered_index = s.last_scattered_idx;
@@ -2076,6 +2199,7 @@ API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remain
         stats->cs_host_pending |= t.cs_host_pending;
     }
     stats->cell_evals = ctx->gs_host->cell_evals - gbefore.cell_evals;
+    stats->box_evals = ctx->gs_host->box_evals - gbefore.box_evals;
     stats->not_found = ctx->gs_host->not_found - gbefore.not_found;
     stats->error = ctx->gs_host->error;
     ctx->last_nb_mfp = 0;

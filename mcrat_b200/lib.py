@@ -36,12 +36,13 @@ class Config(C.Structure):
     _fields_ = [("abi_version", C.c_int), ("dimensions", C.c_int), ("geometry", C.c_int), ("stokes_switch", C.c_int),
                 ("tau_calculation", C.c_int), ("cyclosynch_switch", C.c_int), ("b_field_calc", C.c_int),
                 ("epsilon_b", C.c_double), ("device", C.c_int), ("rng_mode", C.c_int), ("seed", C.c_uint64),
-                ("shard", C.c_uint32), ("profile", C.c_int), ("stream", C.c_void_p)]
+                ("shard", C.c_uint32), ("profile", C.c_int), ("stream", C.c_void_p), ("scan_index", C.c_int)]
 
 
 class FrameStats(C.Structure):
     _fields_ = [("iterations", C.c_longlong), ("scatterings", C.c_longlong), ("relocations", C.c_longlong),
-                ("photon_slots", C.c_longlong), ("cell_evals", C.c_longlong), ("time_now", C.c_double),
+                ("photon_slots", C.c_longlong), ("cell_evals", C.c_longlong), ("box_evals", C.c_longlong),
+                ("time_now", C.c_double),
                 ("last_time_step", C.c_double), ("last_scattered_index", C.c_int), ("not_found", C.c_int),
                 ("cs_host_pending", C.c_int), ("error", C.c_int)]
 
@@ -120,11 +121,11 @@ class HotPath:
     """
 
     def __init__(self, cfg, device=0, rng_mode=RNG_PHILOX, seed=0, shard=0, profile=False, stream=None,
-                 num_shards=1):
+                 num_shards=1, scan_index=False):
         self.L = load()
         c = Config(ABI_VERSION, cfg["dimensions"], cfg["geometry"], cfg["stokes"], cfg["tau_calculation"],
                    cfg["cyclosynch"], cfg["b_field_calc"], cfg["epsilon_b"], device, rng_mode, seed, shard,
-                   1 if profile else 0, stream)
+                   1 if profile else 0, stream, 1 if scan_index else 0)
         self.ctx = C.c_void_p()
         rc = self.L.mcrat_b200_create(C.byref(c), C.byref(self.ctx))
         if rc != 0:

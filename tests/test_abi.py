@@ -67,10 +67,10 @@ def test_no_gpu_means_loud_failure_not_fallback():
 
 def test_config_validation():
     L = lib.load()
-    bad = lib.Config(lib.ABI_VERSION + 1, 0, 0, 0, 1, 0, 1, 0.5, 0, 0, 0, 0, 0, None)
+    bad = lib.Config(lib.ABI_VERSION + 1, 0, 0, 0, 1, 0, 1, 0.5, 0, 0, 0, 0, 0, None, 0)
     ctx = C.c_void_p()
     assert L.mcrat_b200_create(C.byref(bad), C.byref(ctx)) == -2
-    polar2d = lib.Config(lib.ABI_VERSION, 0, 3, 0, 1, 0, 1, 0.5, 0, 0, 0, 0, 0, None)
+    polar2d = lib.Config(lib.ABI_VERSION, 0, 3, 0, 1, 0, 1, 0.5, 0, 0, 0, 0, 0, None, 0)
     assert L.mcrat_b200_create(C.byref(polar2d), C.byref(ctx)) == -2
 
 

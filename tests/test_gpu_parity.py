@@ -26,11 +26,13 @@ def _oracle_frame(cfg, hydro, photons, frame, rng, iters, switch=1):
     return o, st
 
 
+@pytest.mark.parametrize("scan_index", [False, True])
 @pytest.mark.parametrize("wl,refname,scale,nph,iters", CASES)
-def test_frame_philox_parity(wl, refname, scale, nph, iters):
-    """Fused production path (Philox streams) vs the oracle drawing from the same keyed streams."""
+def test_frame_philox_parity(wl, refname, scale, nph, iters, scan_index):
+    """Fused production path (Philox streams) vs the oracle drawing from the same keyed streams,
+    with the full photon x cell scan and with the bounding-box index."""
     cfg, hydro, photons, frame = synth.workload(wl, scale=scale, n_photons=nph, seed=11)
-    hp = HotPath(cfg, seed=2024, shard=3)
+    hp = HotPath(cfg, seed=2024, shard=3, scan_index=scan_index)
     hp.set_hydro(hydro)
     hp.set_photons(photons)
     st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=iters, switch=1)
