@@ -365,7 +365,7 @@ def main():
                 "config": config,
                 "photon_cell_evals_per_sec": roofline["evals_per_s"] * world,
                 "photon_iterations_per_sec": slots_all / (t_max * 1e-3),
-                "scan_share_of_step": scan_ms_avg / (t_max / args.steps),
+                "k1_full_scan_ms": scan_ms_avg,
                 "roofline": roofline, "pass_roofline": pass_roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_all / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_max / args.steps},

@@ -44,9 +44,26 @@ enum : unsigned char { F_MOVABLE = 1, F_RECALC = 2 };
 constexpr int MAX_DT = 16;         // pushes recorded by one event (1 + Klein-Nishina rejections)
 constexpr int BLOCKMIN_CAP = 4096; // per-block arg-min slots
 constexpr int MAX_SHARDS = 4096;
-constexpr int SCAN_THREADS = 128;
-constexpr int SCAN_P = 8;      // photons per thread held in registers
-constexpr int SCAN_TILE = 512; // cells per shared-memory stage
+#ifndef MCRAT_SCAN_THREADS
+#define MCRAT_SCAN_THREADS 128
+#endif
+#ifndef MCRAT_SCAN_P
+#define MCRAT_SCAN_P 8
+#endif
+#ifndef MCRAT_SCAN_TILE
+#define MCRAT_SCAN_TILE 512
+#endif
+#ifndef MCRAT_SCAN_UNROLL
+#define MCRAT_SCAN_UNROLL 4
+#endif
+#ifndef MCRAT_SCAN_CTAS_PER_SM
+#define MCRAT_SCAN_CTAS_PER_SM 32
+#endif
+#define MCRAT_PRAGMA_STR2(x) #x
+#define MCRAT_PRAGMA_STR(x) MCRAT_PRAGMA_STR2(x)
+constexpr int SCAN_THREADS = MCRAT_SCAN_THREADS;
+constexpr int SCAN_P = MCRAT_SCAN_P;       // photons per thread held in registers
+constexpr int SCAN_TILE = MCRAT_SCAN_TILE; // cells per shared-memory stage
 constexpr int FEW_RMAX = 128;  // relocating photons handled per pass of the cell-parallel scan
 constexpr int RELOC_LIST_SCAN_MAX = 2048;
 
@@ -524,7 +541,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(DevCtx d, int parity
         }
         mbar_wait(&bar[s], (uint32_t)((t >> 1) & 1));
         const int cbase = (tile0 + t) * SCAN_TILE;
-#pragma unroll 4
+_Pragma(MCRAT_PRAGMA_STR(unroll MCRAT_SCAN_UNROLL))
         for (int c = 0; c < SCAN_TILE; ++c) {
             const double4 a = sA[s][c];
             if (!NDIM3) {
@@ -1849,8 +1866,9 @@ static void scan_grid(mcrat_b200_ctx *ctx, int nphot, dim3 &grid, int &tiles_per
     const int ntiles = ctx->d.cells.n_padded / SCAN_TILE;
     int pchunks = (nphot + SCAN_THREADS * SCAN_P - 1) / (SCAN_THREADS * SCAN_P);
     if (pchunks < 1) pchunks = 1;
-    // enough cell chunks that the grid is ~8 CTAs per SM, each with >= 4 tiles
-    int want = (ctx->num_sms * 8 + pchunks - 1) / pchunks;
+    // enough cell chunks for ~32 CTAs per SM over the launch (measured best: short CTAs balance the
+    // 148 SMs better than long ones), each with >= 4 tiles
+    int want = (ctx->num_sms * MCRAT_SCAN_CTAS_PER_SM + pchunks - 1) / pchunks;
     int maxc = ntiles / 4;
     if (maxc < 1) maxc = 1;
     int cchunks = want < maxc ? want : maxc;
