@@ -98,8 +98,12 @@ typedef struct mcrat_b200_frame_stats {
     double last_time_step;
     int last_scattered_index;
     int not_found;          /* photons for which no containing cell exists (Src/mclib.c:583) */
-    int cs_host_pending;    /* loop paused: a pool photon scattered, host must emit (Src/mcrat.c:792-807) */
+    int cs_host_pending;    /* loop paused for the host: 1 = a pool photon scattered and the list has no null slot
+                             * left (host grows the list and emits, Src/mcrat.c:792-807); 2 = rebin due (:820-830) */
     int error;              /* 0 or MCRAT_B200_ERR_* raised on the device */
+    int cs_emitted;         /* pool photons replaced on the device (photonEmitCyclosynch, single mode) */
+    int scatt_cyclosynch_num_ph;      /* running scatt_cyclosynch_num_ph, Src/mcrat.c:803 */
+    double cs_comptonized_weight;     /* n_comptonized added in this call, Src/mcrat.c:794 */
 } mcrat_b200_frame_stats;
 
 typedef struct mcrat_b200_kernel_times {
@@ -167,6 +171,14 @@ int mcrat_b200_update_photon_position(mcrat_b200_ctx *ctx, double t);
 /* phAbsCyclosynch, Src/mc_cyclosynch.h:92, Src/mc_cyclosynch.c:1571 */
 int mcrat_b200_ph_abs_cyclosynch(mcrat_b200_ctx *ctx, int *num_abs_ph, int *scatt_cyclosynch_num_ph,
                                  double *absorbed_weight);
+/* calcCyclosynchRLimits, Src/mc_cyclosynch.h:84, Src/mc_cyclosynch.c:225; min_or_max is "min" or "max" */
+double mcrat_b200_calc_cyclosynch_r_limits(int frame_scatt, int frame_inj, double fps, double r_inj,
+                                           const char *min_or_max);
+/* rebin threshold (mc.par max_photons) and the running scatt_cyclosynch_num_ph of the driver
+ * (Src/mcrat.c:803, 820): with CYCLOSYNCHROTRON_SWITCH ON the frame loop replaces scattered pool
+ * photons on the device (photonEmitCyclosynch in single mode, Src/mc_cyclosynch.c:1465-1555) and
+ * pauses for the host only to grow the list or to rebin */
+int mcrat_b200_set_cs_limits(mcrat_b200_ctx *ctx, int max_photons, int scatt_cyclosynch_num_ph);
 /* phMinMax / phScattStats / averagePhotonEnergy, Src/mclib.c:1465 / 1385 / 1358 */
 int mcrat_b200_ph_min_max(mcrat_b200_ctx *ctx, double *min_r, double *max_r, double *min_theta, double *max_theta);
 int mcrat_b200_ph_scatt_stats(mcrat_b200_ctx *ctx, int *max_scatt, int *min_scatt, double *avg_scatt, double *avg_r);

@@ -188,6 +188,29 @@ __device__ inline void coord_to_hydro(int dims, int g, double x, double y, doubl
     }
 }
 
+// Src/geometry.c:108-154 hydroCoordinateToMcratCoordinate
+__device__ inline void hydro_coord_to_mcrat(int dims, int g, double *out, double h0, double h1, double h2)
+{
+    double x = 0, y = 0, z = 0;
+    const bool planar = (g == G_CARTESIAN || g == G_CYLINDRICAL);
+    if (dims != D_THREE && planar) {
+        x = h0 * cos(h2);
+        y = h0 * sin(h2);
+        z = h1;
+    } else if (g == G_SPHERICAL) {
+        x = h0 * sin(h1) * cos(h2);
+        y = h0 * sin(h1) * sin(h2);
+        z = h0 * cos(h1);
+    } else if (dims == D_THREE && g == G_CARTESIAN) {
+        x = h0; y = h1; z = h2;
+    } else if (dims == D_THREE && g == G_POLAR) {
+        x = h0 * cos(h1);
+        y = h0 * sin(h1);
+        z = h2;
+    }
+    out[0] = x; out[1] = y; out[2] = z;
+}
+
 // Src/geometry.c:189-253 hydroVectorToCartesian
 __device__ inline void hydro_vector_to_cartesian(int dims, int g, double *out, double v0, double v1, double v2,
                                                  double x0, double x1, double x2)

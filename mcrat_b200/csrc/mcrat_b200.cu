@@ -110,6 +110,11 @@ struct GlobalState {
     unsigned long long replay_cursor, replay_base, replay_n;
     int abs_count, cs_scatt_count;
     double abs_weight;
+    // cyclo-synchrotron bookkeeping of the driver, Src/mcrat.c:792-831
+    int cs_max_photons;        // rebin threshold (max_photons of mc.par); INT_MAX: never
+    int cs_scatt_num;          // scatt_cyclosynch_num_ph
+    int cs_emitted;            // pool photons replaced on the device
+    double cs_comptonized_w;   // n_comptonized
 };
 
 struct DevCtx {
@@ -906,6 +911,91 @@ __device__ void scatter_candidate(DevCtx &d, ShardState &st, EventRng &rng, int 
     }
 }
 
+// getMagneticFieldMagnitude, Src/mc_cyclosynch.c:78-92
+__device__ __forceinline__ double cell_b_field(const DevCtx &d, int idx)
+{
+    if (d.b_calc == B_TOTAL_E || d.b_calc == B_INTERNAL_E) {
+        double el_dens = d.cells.dens[idx] / M_P;
+        return calc_b(d.b_calc, d.epsilon_b, el_dens, d.cells.temp[idx]);
+    }
+    if (d.dims == D_TWO) {
+        double b0 = d.cells.B0[idx], b1 = d.cells.B1[idx];
+        return sqrt(b0 * b0 + b1 * b1);
+    }
+    double b0 = d.cells.B0[idx], b1 = d.cells.B1[idx], b2 = d.cells.B2[idx];
+    return sqrt(b0 * b0 + b1 * b1 + b2 * b2);
+}
+
+// photonEmitCyclosynch with inject_single_switch == 1 (Src/mc_cyclosynch.c:1465-1555): a pool
+// photon that scattered is replaced by a fresh one at the cyclotron frequency of its cell, placed
+// into the first null slot of the list (addToPhotonList, Src/photons.c:132-160), and the scattered
+// photon is re-positioned at random inside the cell (:1541-1553).
+__device__ void cs_emit_single(DevCtx &d, EventRng &rng, int scatt, int slot)
+{
+    const int i = d.ph.idx[scatt];
+    const int ndim3 = (d.dims == D_THREE);
+    const double nu_c = calc_cyclotron_freq(cell_b_field(d, i));
+    const double fr_dum = nu_c;
+    double position_phi = 0;
+    if (!ndim3) position_phi = rng.uniform() * 2 * PI;
+    const double com_v_phi = rng.uniform() * 2 * PI;
+    const double com_v_theta = rng.uniform() * PI;
+    double p_comv[4], boost[3], l_boost[4], pos[3];
+    p_comv[0] = PL_CONST * fr_dum / C_LIGHT;
+    p_comv[1] = (PL_CONST * fr_dum / C_LIGHT) * sin(com_v_theta) * cos(com_v_phi);
+    p_comv[2] = (PL_CONST * fr_dum / C_LIGHT) * sin(com_v_theta) * sin(com_v_phi);
+    p_comv[3] = (PL_CONST * fr_dum / C_LIGHT) * cos(com_v_theta);
+    const double cr0 = d.cells.r0[i], cr1 = d.cells.r1[i], cr2 = d.cells.r2[i];
+    if (ndim3)
+        hydro_vector_to_cartesian(d.dims, d.geom, boost, d.cells.v0[i], d.cells.v1[i], d.cells.v2[i], cr0, cr1, cr2);
+    else if (d.dims == D_TWO_POINT_FIVE)
+        hydro_vector_to_cartesian(d.dims, d.geom, boost, d.cells.v0[i], d.cells.v1[i], d.cells.v2[i], cr0, cr1, position_phi);
+    else
+        hydro_vector_to_cartesian(d.dims, d.geom, boost, d.cells.v0[i], d.cells.v1[i], 0, cr0, cr1, position_phi);
+    boost[0] *= -1;
+    boost[1] *= -1;
+    boost[2] *= -1;
+    lorentz_boost(boost, p_comv, l_boost, true);
+    if (ndim3)
+        hydro_coord_to_mcrat(d.dims, d.geom, pos, cr0, cr1, cr2);
+    else
+        hydro_coord_to_mcrat(d.dims, d.geom, pos, cr0, cr1, position_phi);
+    d.ph.p0[slot] = l_boost[0]; d.ph.p1[slot] = l_boost[1]; d.ph.p2[slot] = l_boost[2]; d.ph.p3[slot] = l_boost[3];
+    d.ph.c0[slot] = p_comv[0]; d.ph.c1[slot] = p_comv[1]; d.ph.c2[slot] = p_comv[2]; d.ph.c3[slot] = p_comv[3];
+    d.ph.r0[slot] = pos[0]; d.ph.r1[slot] = pos[1]; d.ph.r2[slot] = pos[2];
+    d.ph.s0[slot] = 1; d.ph.s1[slot] = 0; d.ph.s2[slot] = 0; d.ph.s3[slot] = 0;
+    d.ph.nscatt[slot] = 0;
+    d.ph.weight[slot] = d.ph.weight[scatt];
+    d.ph.idx[slot] = i;
+    d.ph.type[slot] = 'p';
+    d.ph.flags[slot] = F_RECALC; // pool photons do not move (Src/mclib.c:1070)
+    d.ph.tts[slot] = 0;
+    d.ph.tau[slot] = 0;
+    // new random position of the scattered photon inside its cell
+    const double4 a = d.cells.geoA[i];
+    double size0, size1, size2 = 0;
+    if (!ndim3) {
+        size0 = 2 * a.z;
+        size1 = 2 * a.w;
+    } else {
+        const double2 b = d.cells.geoB[i];
+        size0 = 2 * a.w;
+        size1 = 2 * b.x;
+        size2 = 2 * b.y;
+    }
+    const double pr = rng.uniform_pos() * (size0) - (size0) / 2.0;
+    const double pr2 = rng.uniform_pos() * (size1) - (size1) / 2.0;
+    if (ndim3) {
+        const double pr3 = rng.uniform_pos() * (size2) - (size2) / 2.0;
+        hydro_coord_to_mcrat(d.dims, d.geom, pos, cr0 + pr, cr1 + pr2, cr2 + pr3);
+    } else {
+        hydro_coord_to_mcrat(d.dims, d.geom, pos, cr0 + pr, cr1 + pr2, position_phi);
+    }
+    d.ph.r0[scatt] = pos[0];
+    d.ph.r1[scatt] = pos[1];
+    d.ph.r2[scatt] = pos[2];
+}
+
 // step_mode 0: frame loop (driver bookkeeping included); 1: photonEvent only (dt_max given)
 // blockmin_valid: the pass wrote per-block minima for this iteration (fused path / step API)
 template <int EVT_THREADS>
@@ -1071,29 +1161,63 @@ __global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int parity
         }
     }
 
+    // ---- cyclo-synchrotron pool replacement, Src/mcrat.c:791-808 (the list is one shard here) ----
+    __shared__ int cs_need, cs_slot;
+    if (threadIdx.x == 0) {
+        cs_need = 0;
+        if (step_mode == 0 && d.cs && d.ph.type[ph_index] == 'p') cs_need = 1;
+    }
+    __syncthreads();
+    if (cs_need) {
+        // first null slot of the list (Src/photons.c:143-150)
+        int first_null = INT_MAX;
+        for (int j = threadIdx.x; j < st.count; j += EVT_THREADS)
+            if (d.ph.type[st.first + j] == 'N') {
+                first_null = st.first + j;
+                break;
+            }
+        double dummy = 0;
+        block_argmin<EVT_THREADS>(dummy, first_null);
+        if (threadIdx.x == 0) cs_slot = first_null;
+        __syncthreads();
+    }
+
     if (threadIdx.x == 0) {
         st.n_dt = n_dt;
         st.last_scattered_idx = ph_index;
         st.last_time_step = scatt_time;
-        if (d.replay) {
-            gs.replay_cursor = rng_sh.pos;
-            if (rng_sh.exhausted) gs.error = MCRAT_B200_ERR_REPLAY;
-        }
         st.iter += 1;
         st.iters_done += 1;
         if (step_mode == 0) {
             st.time_now += scatt_time;
             st.remaining_time -= scatt_time;
             if (!(st.remaining_time > 0)) st.done = 1;
-            if (d.cs && d.ph.type[ph_index] == 'p') { // Src/mcrat.c:792-807: host replenishes the pool
-                d.ph.type[ph_index] = 'k';
+            if (cs_need) {
+                gs.cs_comptonized_w += d.ph.weight[ph_index];
+                d.ph.type[ph_index] = 'k'; // COMPTONIZED_PHOTON
                 if (d.ph.weight[ph_index] != 0) d.ph.flags[ph_index] |= F_MOVABLE;
-                st.pause_cs = 1;
+                if (cs_slot == INT_MAX) {
+                    // no null slot: the host must grow the list and emit (Src/photons.c:117-129)
+                    st.pause_cs = 1;
+                } else {
+                    EventRng rng = rng_sh;
+                    cs_emit_single(d, rng, ph_index, cs_slot);
+                    rng_sh = rng;
+                    gs.cs_emitted += 1;
+                    gs.cs_scatt_num += 1;
+                }
             }
+            // Src/mcrat.c:810-831: every 1000 scatterings the driver may have to rebin on the host
+            if (d.cs && !st.pause_cs && (st.scatt_cnt % 1000 == 0) && (st.scatt_cnt != 0) && gs.cs_scatt_num > gs.cs_max_photons)
+                st.pause_cs = 2;
             if ((st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters)) && !st.counted_stopped) {
                 st.counted_stopped = 1;
                 atomicAdd(&gs.n_stopped, 1);
             }
+        }
+        if (d.replay) {
+            gs.replay_cursor = rng_sh.pos;
+            if (rng_sh.exhausted) gs.error = MCRAT_B200_ERR_REPLAY;
         }
     }
 }
@@ -1523,7 +1647,10 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
     d.shard_size = 1;
     d.blocks_per_shard = 1;
     if ((e = dev_alloc(ctx->misc_allocs, &d.gs, 1)) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMemsetAsync(d.gs, 0, sizeof(GlobalState), ctx->stream)) != cudaSuccess) return bail(e, "cudaMemset");
+    memset(ctx->gs_host, 0, sizeof(GlobalState));
+    ctx->gs_host->cs_max_photons = INT_MAX;
+    if ((e = cudaMemcpyAsync(d.gs, ctx->gs_host, sizeof(GlobalState), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+        return bail(e, "cudaMemcpy");
     if ((e = dev_alloc(ctx->misc_allocs, &d.sh, MAX_SHARDS)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemsetAsync(d.sh, 0, sizeof(ShardState) * MAX_SHARDS, ctx->stream)) != cudaSuccess) return bail(e, "cudaMemset");
     ctx->sh_host.assign(MAX_SHARDS, ShardState());
@@ -2159,6 +2286,9 @@ static void fill_stats(const ShardState &s, const ShardState &b, mcrat_b200_fram
     o->not_found = 0;
     o->cs_host_pending = s.pause_cs;
     o->error = 0;
+    o->cs_emitted = 0;
+    o->scatt_cyclosynch_num_ph = 0;
+    o->cs_comptonized_weight = 0;
 }
 
 API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remaining_time, long long max_iters, int sw,
@@ -2220,8 +2350,36 @@ API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remain
     stats->box_evals = ctx->gs_host->box_evals - gbefore.box_evals;
     stats->not_found = ctx->gs_host->not_found - gbefore.not_found;
     stats->error = ctx->gs_host->error;
+    stats->cs_emitted = ctx->gs_host->cs_emitted - gbefore.cs_emitted;
+    stats->scatt_cyclosynch_num_ph = ctx->gs_host->cs_scatt_num;
+    stats->cs_comptonized_weight = ctx->gs_host->cs_comptonized_w - gbefore.cs_comptonized_w;
     ctx->last_nb_mfp = 0;
     return device_error(ctx);
+}
+
+// the driver's cyclo-synchrotron counters (Src/mcrat.c:803, 820, 857): rebin threshold and the running
+// number of scattered pool photons; the loop pauses with cs_host_pending == 2 when a rebin is due
+API int mcrat_b200_set_cs_limits(mcrat_b200_ctx *ctx, int max_photons, int scatt_cyclosynch_num_ph)
+{
+    if (!ctx) return MCRAT_B200_ERR_ARG;
+    if (int rc = fetch_global(ctx)) return rc;
+    ctx->gs_host->cs_max_photons = max_photons;
+    ctx->gs_host->cs_scatt_num = scatt_cyclosynch_num_ph;
+    CK(cudaMemcpyAsync(ctx->d.gs, ctx->gs_host, sizeof(GlobalState), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MCRAT_B200_OK;
+}
+
+// calcCyclosynchRLimits, Src/mc_cyclosynch.h:84, Src/mc_cyclosynch.c:225-242 (pure host arithmetic)
+API double mcrat_b200_calc_cyclosynch_r_limits(int frame_scatt, int frame_inj, double fps, double r_inj, const char *min_or_max)
+{
+    const double c_light = 2.99792458e10;
+    double val = r_inj;
+    if (min_or_max && strcmp(min_or_max, "min") == 0)
+        val += (c_light * (frame_scatt - frame_inj) / fps - 0.5 * c_light / fps);
+    else
+        val += (c_light * (frame_scatt - frame_inj) / fps + 0.5 * c_light / fps);
+    return val;
 }
 
 API int mcrat_b200_get_shard_stats(mcrat_b200_ctx *ctx, int shard, mcrat_b200_frame_stats *stats, int *first_slot,

@@ -44,7 +44,8 @@ class FrameStats(C.Structure):
                 ("photon_slots", C.c_longlong), ("cell_evals", C.c_longlong), ("box_evals", C.c_longlong),
                 ("time_now", C.c_double),
                 ("last_time_step", C.c_double), ("last_scattered_index", C.c_int), ("not_found", C.c_int),
-                ("cs_host_pending", C.c_int), ("error", C.c_int)]
+                ("cs_host_pending", C.c_int), ("error", C.c_int), ("cs_emitted", C.c_int),
+                ("scatt_cyclosynch_num_ph", C.c_int), ("cs_comptonized_weight", C.c_double)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -66,7 +67,7 @@ EXPORTS = [
     "mcrat_b200_set_num_shards", "mcrat_b200_num_shards", "mcrat_b200_get_shard_stats",
     "mcrat_b200_set_replay_uniforms", "mcrat_b200_replay_consumed", "mcrat_b200_find_containing_hydro_cell",
     "mcrat_b200_calc_mean_free_path", "mcrat_b200_photon_event", "mcrat_b200_update_photon_position",
-    "mcrat_b200_ph_abs_cyclosynch", "mcrat_b200_ph_min_max", "mcrat_b200_ph_scatt_stats",
+    "mcrat_b200_ph_abs_cyclosynch", "mcrat_b200_calc_cyclosynch_r_limits", "mcrat_b200_set_cs_limits", "mcrat_b200_ph_min_max", "mcrat_b200_ph_scatt_stats",
     "mcrat_b200_average_photon_energy", "mcrat_b200_run_frame", "mcrat_b200_get_kernel_times",
     "mcrat_b200_launch_count", "mcrat_b200_rescan_all", "mcrat_b200_measure_fp64_peak", "mcrat_b200_measure_hbm_peak",
 ]
@@ -250,6 +251,14 @@ class HotPath:
         na, ns, w = C.c_int(0), C.c_int(0), C.c_double(0)
         self._ck(self.L.mcrat_b200_ph_abs_cyclosynch(self.ctx, C.byref(na), C.byref(ns), C.byref(w)))
         return w.value, na.value, ns.value
+
+    def set_cs_limits(self, max_photons, scatt_cyclosynch_num_ph=0):
+        self._ck(self.L.mcrat_b200_set_cs_limits(self.ctx, C.c_int(max_photons), C.c_int(scatt_cyclosynch_num_ph)))
+
+    def calcCyclosynchRLimits(self, frame_scatt, frame_inj, fps, r_inj, which):
+        self.L.mcrat_b200_calc_cyclosynch_r_limits.restype = C.c_double
+        return self.L.mcrat_b200_calc_cyclosynch_r_limits(C.c_int(frame_scatt), C.c_int(frame_inj), C.c_double(fps),
+                                                          C.c_double(r_inj), which.encode())
 
     def phMinMax(self):
         v = [C.c_double(0) for _ in range(4)]

@@ -324,3 +324,63 @@ def test_bounding_box_index_returns_the_first_match(wl):
     assert sb["cell_evals"] + sb["box_evals"] < sa["cell_evals"] / 20
     print("%s: full scan %d evals %.1f ms; index %d cell + %d box evals %.1f ms" %
           (wl, sa["cell_evals"], 1e3 * out[False][2], sb["cell_evals"], sb["box_evals"], 1e3 * out[True][2]))
+
+
+@pytest.mark.parametrize("refname", ["c4_3d_sph_cs", "g_2d_cyl_cs"])
+def test_cyclosynchrotron_frame_with_pool_replacement(refname):
+    """C4: a frame with CYCLOSYNCHROTRON_SWITCH ON.  Pool photons ('p') that scatter are retagged and
+    replaced on the device (photonEmitCyclosynch single mode, Src/mc_cyclosynch.c:1465-1555), drawing
+    from the event's own stream -- same draws as the oracle's loop (Src/mcrat.c:791-808)."""
+    c = configs.CONFIGS[refname]
+    cfg = _cfg_from_ref(refname)
+    if c["dimensions"] == configs.THREE:
+        _, hydro, photons, frame = synth.workload("C4", scale=1.0 / 16, n_photons=300, seed=21)
+        r_inj = 1e12
+    else:
+        _, hydro, photons, frame = synth.workload("C2", scale=1.0 / 32, n_photons=300, seed=21)
+        synth.toroidal_b_field(hydro, r_ref=2e12)
+        r_inj = 2e12
+    hydro["scatt_frame_number"], hydro["inj_frame_number"] = 3, 2
+    o = api.Oracle(c)
+    o.set_hydro(hydro)
+    o.set_photons(photons)
+    seed_rng = api.OracleRng("ranlxs0", seed=2)
+    o.find_containing_hydro_cell(1, seed_rng)
+    n_emit = o.photon_emit_cyclosynch(seed_rng, r_inj=r_inj - synth.C_LIGHT / 5, ph_weight=1e36, max_photons=3000,
+                                      theta_min=0.0, theta_max=0.2)
+    start = o.photons()
+    assert n_emit > 20 and (start["type"] == b"p").sum() == n_emit and (start["type"] == b"N").sum() > 10
+    start["time_to_scatter"] = 0.0
+    start["total_optical_depth"] = np.where(start["type"] == b"p", 0.0, start["total_optical_depth"])
+    hp = HotPath(cfg, seed=31, shard=4)
+    hp.set_hydro(hydro)
+    hp.set_photons(start)
+    hp.set_cs_limits(10 ** 9, 0)
+    iters = 250
+    st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=iters, switch=1)
+    got = hp.get_photons()
+    ost = o.run_frame(api.OracleRng("philox", seed=31, shard=4), frame["time_now"], 1.0 / frame["fps"], max_iters=iters,
+                      switch=1, cs=dict(r_inj=r_inj, ph_weight=1e48, max_photons=10 ** 9, theta_min=0.0, theta_max=0.2))
+    want = o.photons()
+    assert st["cs_host_pending"] == 0 and st["error"] == 0
+    assert st["iterations"] == ost["iterations"] == iters and st["scatterings"] == ost["scatterings"]
+    assert st["cs_emitted"] == ost["cs_emitted"] and st["cs_emitted"] > 3, (st, ost)
+    assert st["scatt_cyclosynch_num_ph"] == ost["scatt_cyclosynch_num_ph"]
+    assert (got["type"] == b"k").sum() == st["cs_emitted"]
+    # freshly emitted records carry no time_to_scatter / tau in the reference (uninitialised malloc)
+    fresh = (want["type"] == b"p") & (want["recalc_properties"] == 1)
+    for a in (got, want):
+        a["time_to_scatter"][fresh] = 0
+        a["total_optical_depth"][fresh] = 0
+    compare_photons(got, want, label=refname, stokes_tol=1e-9, hydro=hydro, check_tts=False)
+
+
+def test_calc_cyclosynch_r_limits():
+    cfg, hydro, photons, frame = synth.workload("C2", scale=1.0 / 64, n_photons=8)
+    hp = HotPath(cfg)
+    o = api.oracle_lib()
+    o.mc_cyclosynch_r_limits.restype = C.c_double
+    for which in ("min", "max"):
+        a = hp.calcCyclosynchRLimits(205, 200, 5.0, 1e12, which)
+        b = o.mc_cyclosynch_r_limits(C.c_int(205), C.c_int(200), C.c_double(5.0), C.c_double(1e12), which.encode())
+        assert a == b
