@@ -9,8 +9,9 @@ from mcrat_b200 import HotPath, synth  # noqa: E402
 
 nph = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 300
-cfg, hydro, photons, frame = synth.workload("C2", n_photons=nph)
-for S in [1, 4, 16, 64, 148, 296, 592, 1024]:
+wl = sys.argv[3] if len(sys.argv) > 3 else "C2"
+cfg, hydro, photons, frame = synth.workload(wl, n_photons=nph)
+for S in [int(x) for x in (sys.argv[4] if len(sys.argv) > 4 else "1,4,16,64,148,296,592,1024").split(",")]:
     hp = HotPath(cfg, seed=1, num_shards=S)
     hp.set_hydro(hydro)
     hp.set_photons(photons)
