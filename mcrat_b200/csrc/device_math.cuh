@@ -514,6 +514,40 @@ __device__ inline double find_phi(const double *x_old, const double *y_old, cons
     return -1 * factor * acos(dot);
 }
 
+// One half of stokesRotation: the angle between the polarisation bases (k, a) and (k, b),
+// Src/mcrat_scattering.c:115-123 / :133-141.  The angle depends on momenta only -- never on the
+// Stokes vector -- which is what lets the event kernel evaluate all of them on a second warp.
+__device__ inline double stokes_angle(const double *k, const double *a, const double *b)
+{
+    double x[3], y[3], xn[3], yn[3];
+    find_xy(k, a, x, y);
+    find_xy(k, b, xn, yn);
+    return find_phi(x, y, yn);
+}
+
+// general form: first basis from (k1, a), second from (k2, b) -- the scattering-plane rotation of
+// singleScatter pairs two different wave vectors (Src/mcrat_scattering.c:402-405)
+__device__ inline double stokes_angle4(const double *k1, const double *a, const double *k2, const double *b)
+{
+    double x[3], y[3], xn[3], yn[3];
+    find_xy(k1, a, x, y);
+    find_xy(k2, b, xn, yn);
+    return find_phi(x, y, yn);
+}
+
+// mullerMatrixRotation with sin(2 theta), cos(2 theta) already evaluated (same products, same order)
+__device__ inline void muller_rotation_sc(double sn, double cs, double *s)
+{
+    double r1 = 0.0;
+    r1 += s[1] * cs;
+    r1 += s[2] * (-1 * sn);
+    double r2 = 0.0;
+    r2 += s[1] * sn;
+    r2 += s[2] * cs;
+    s[1] = r1;
+    s[2] = r2;
+}
+
 // Src/mcrat_scattering.c:103-149 stokesRotation
 __device__ inline void stokes_rotation(const double *v, const double *v_ph, const double *v_ph_boosted, double *s)
 {
@@ -534,7 +568,12 @@ __device__ inline void stokes_rotation(const double *v, const double *v_ph, cons
 // ----------------------------------------------------------------------------------------
 // Src/mcrat_scattering.c:509-595 kleinNishinaScatter.  The reference's pow(m, -1/-2/-3) are written
 // as reciprocals of products (<= 2 ulp apart; pow is several hundred instructions in FP64).
-__device__ inline int kn_scatter(int stokes, double &theta, double &phi, double p0, double q, double u, EventRng &rng)
+struct KnTheta {
+    double er, st, imu2, f_theta;
+};
+
+// first half: accept / reject and the polar angle (Src/mcrat_scattering.c:519-553)
+__device__ inline int kn_accept_theta(double &theta, double p0, KnTheta &k, EventRng &rng)
 {
     double er = p0 / (M_EL * C_LIGHT);
     double kn = kn_cross_section(er);
@@ -552,7 +591,18 @@ __device__ inline int kn_scatter(int stokes, double &theta, double &phi, double 
     sincos(theta, &st, &ctheta);
     double mu = 1 + er * (1 - ctheta);
     double imu2 = 1.0 / (mu * mu);
-    double f_theta = ((1.0 / mu) + (1.0 / (mu * mu * mu)) - imu2 * st * st) * st;
+    k.er = er;
+    k.st = st;
+    k.imu2 = imu2;
+    k.f_theta = ((1.0 / mu) + (1.0 / (mu * mu * mu)) - imu2 * st * st) * st;
+    return 1;
+}
+
+// second half: the azimuth, which is the only place the Stokes vector (q, u) enters the
+// kinematics (Src/mcrat_scattering.c:555-585)
+__device__ inline double kn_phi(int stokes, const KnTheta &k, double q, double u, EventRng &rng)
+{
+    const double st = k.st, imu2 = k.imu2, f_theta = k.f_theta;
     double phi_y = 1, f_phi = 0, phi_dum = 0;
     if (!stokes || (u == 0 && q == 0)) {
         phi_dum = rng.uniform() * 2 * PI;
@@ -569,7 +619,14 @@ __device__ inline int kn_scatter(int stokes, double &theta, double &phi, double 
             f_phi = (f_theta + imu2 * st * st * st * (q * c2 - u * s2)) / norm;
         }
     }
-    phi = phi_dum;
+    return phi_dum;
+}
+
+__device__ inline int kn_scatter(int stokes, double &theta, double &phi, double p0, double q, double u, EventRng &rng)
+{
+    KnTheta k;
+    if (!kn_accept_theta(theta, p0, k, rng)) return 0;
+    phi = kn_phi(stokes, k, q, u, rng);
     return 1;
 }
 
@@ -691,6 +748,108 @@ __device__ inline int single_scatter(int stokes, double *el_comov, double *ph_co
         if (stokes) stokes_rotation(neg_el_v, php + 1, ph_comov + 1, s);
     }
     return occurred;
+}
+
+// ----------------------------------------------------------------------------------------
+// singleScatter cut into stages for the two-warp event (mcrat_b200.cu, scatter_candidate_2w):
+// warp 0 runs the momentum chain below, warp 1 evaluates the Stokes-plane angles, which depend on
+// momenta only.  Every stage is the corresponding statement block of single_scatter above,
+// operation for operation, so both paths give bit-identical results.
+// ----------------------------------------------------------------------------------------
+struct ScatterRot {
+    double s0m, c0m, s1m, c1m; // sin/cos of -phi0 and -phi1 (Src/mcrat_scattering.c:262-296)
+};
+
+// Src/mcrat_scattering.c:216-240: electron velocity, photon into the electron rest frame
+__device__ inline void scatter_stage_boost(double *el_comov, double *ph_comov, double *el_v, double *php)
+{
+    el_v[0] = el_comov[1] / el_comov[0];
+    el_v[1] = el_comov[2] / el_comov[0];
+    el_v[2] = el_comov[3] / el_comov[0];
+    lorentz_boost(el_v, ph_comov, php, true);
+}
+
+// Src/mcrat_scattering.c:262-296: rotate the photon onto +x; returns its energy (p0 is unchanged)
+__device__ inline void scatter_stage_align(const double *php, ScatterRot &r)
+{
+    double rot[9], result0[3], tmp[3];
+    double phi0 = atan2(php[2], php[1]);
+    sincos(-phi0, &r.s0m, &r.c0m);
+#pragma unroll
+    for (int i = 0; i < 9; i++) rot[i] = 0;
+    rot[8] = 1;
+    rot[0] = r.c0m;
+    rot[4] = r.c0m;
+    rot[1] = -r.s0m;
+    rot[3] = r.s0m;
+    tmp[0] = php[1]; tmp[1] = php[2]; tmp[2] = php[3];
+    dgemv<3>(rot, tmp, result0);
+    double phi1 = atan2(result0[2], result0[0]);
+    sincos(-phi1, &r.s1m, &r.c1m);
+}
+
+// Src/mcrat_scattering.c:318-386: scattered photon in the electron rest frame, original axes
+__device__ inline void scatter_stage_out(double e_in, double theta, double phi, const ScatterRot &r, double *out)
+{
+    double rot[9], result[4], v[3], result1[3], result0[3];
+    double sth, cth, sph, cph;
+    sincos(theta, &sth, &cth);
+    sincos(phi, &sph, &cph);
+    result[0] = (e_in) / (1 + (((e_in) * (1 - cth)) / (M_EL * C_LIGHT)));
+    result[1] = result[0] * cth;
+    result[2] = result[0] * sth * sph;
+    result[3] = result[0] * sth * cph;
+    v[0] = result[1]; v[1] = result[2]; v[2] = result[3];
+#pragma unroll
+    for (int i = 0; i < 9; i++) rot[i] = 0;
+    rot[4] = 1;
+    rot[0] = r.c1m;
+    rot[8] = r.c1m;
+    rot[2] = r.s1m;
+    rot[6] = -r.s1m;
+    dgemv<3>(rot, v, result1);
+#pragma unroll
+    for (int i = 0; i < 9; i++) rot[i] = 0;
+    rot[8] = 1;
+    rot[0] = r.c0m;
+    rot[4] = r.c0m;
+    rot[1] = r.s0m;
+    rot[3] = -r.s0m;
+    dgemv<3>(rot, result1, result0);
+    out[0] = result[0]; out[1] = result0[0]; out[2] = result0[1]; out[3] = result0[2];
+}
+
+// Src/mcrat_scattering.c:408-416: scattering angle and the non-zero entries of the Fano matrix
+__device__ inline void scatter_stage_fano(const double *orig, const double *out, double *f)
+{
+    double th = acos((orig[1] * out[1] + orig[2] * out[2] + orig[3] * out[3]) / (orig[0] * (out[0])));
+    double ct, sn;
+    sincos(th, &sn, &ct);
+    f[0] = 1.0 + ct * ct + ((1 - ct) * (orig[0] - out[0]) / (M_EL * C_LIGHT));
+    f[1] = sn * sn;
+    f[2] = 1.0 + ct * ct;
+    f[3] = 2.0 * ct;
+    f[4] = 2.0 * ct + ((ct) * (1 - ct) * (orig[0] - out[0]) / (M_EL * C_LIGHT));
+}
+
+// Src/mcrat_scattering.c:418-433: s <- T s / (T s)_0 with the full 4x4 product of the reference
+__device__ inline void fano_apply(const double *f, double *s)
+{
+    double scatt[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) scatt[i] = 0;
+    scatt[0] = f[0];
+    scatt[1] = f[1];
+    scatt[4] = f[1];
+    scatt[5] = f[2];
+    scatt[10] = f[3];
+    scatt[15] = f[4];
+    double sr[4];
+    dgemv<4>(scatt, s, sr);
+    s[0] = sr[0] / sr[0];
+    s[1] = sr[1] / sr[0];
+    s[2] = sr[2] / sr[0];
+    s[3] = sr[3] / sr[0];
 }
 
 // ----------------------------------------------------------------------------------------

@@ -868,7 +868,233 @@ __global__ void __launch_bounds__(256) argmin_all_kernel(DevCtx d)
 // driver's bookkeeping (Src/mcrat.c:777-846).  One block per sub-shard; lane 0 runs the scatter.
 // ------------------------------------------------------------------------------------------
 constexpr int EVT_THREADS = 256;   // one shard / few shards: wide block for the list scans
-constexpr int EVT_THREADS_MANY = 32; // many sub-shards: one warp per event, 16+ events resident per SM
+constexpr int EVT_THREADS_MANY = 64; // many sub-shards: two warps per event, 16 events resident per SM
+
+// Mailbox of the two-warp scattering event (shared memory).  Warp 0 = momentum chain (the only
+// consumer of random numbers), warp 1 = Stokes chain.  Every rotation angle of stokesRotation
+// (Src/mcrat_scattering.c:103-149) is a function of momenta only, so warp 1 evaluates them -- two
+// or three at a time, one per lane, same instruction stream -- while warp 0 is already working on
+// the next stage; the Stokes vector itself only enters warp 0 through (q, u) in the azimuth draw.
+struct ScatterMail {
+    double zhat[3];
+    double fb[3], nfb[3];   // fluid velocity (Src/mclib.c:1151-1174) and its negative
+    double p[4];            // lab 4-momentum of the candidate
+    double pc[4];           // fluid-frame 4-momentum (photon.comv_p*)
+    double pcb[4];          // the same after lorentzBoost had it as input (renormalised in place if beta = 0)
+    double el_v[3], nel_v[3];
+    double php[4];          // electron rest frame, before the scatter (`orig`)
+    double out[4];          // electron rest frame, after
+    double outb[4];         // `out` after lorentzBoost had it as input
+    double pc_new[4];       // fluid frame, after (as the last stokesRotation of singleScatter sees it)
+    double pc_fin[4];       // fluid frame, after the lab boost had it as input
+    double p_new[4];        // lab frame, after
+    double fano[5];
+    double q, u;
+    int occurred;
+};
+
+__device__ __forceinline__ void pair_bar() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
+// up to three Stokes angles at once, one per lane; returns sin/cos(2 phi) of this lane's angle
+__device__ __forceinline__ void lane_angle(const double *k1, const double *a, const double *k2, const double *b, bool active,
+                                           double &sn, double &cs)
+{
+    sn = 0;
+    cs = 1;
+    if (active) {
+        double phi = stokes_angle4(k1, a, k2, b);
+        sincos(2 * phi, &sn, &cs);
+    }
+}
+
+__device__ __forceinline__ void rot_from_lane(double sn, double cs, int src, double *s)
+{
+    double a = __shfl_sync(0xffffffffu, sn, src), c = __shfl_sync(0xffffffffu, cs, src);
+    muller_rotation_sc(a, c, s);
+}
+
+// photonEvent's body for one candidate (Src/mclib.c:1138-1333) on two warps (threads 0..63 of the
+// block call this together; STOKES_SWITCH ON).  Results are bit-identical to scatter_candidate.
+__device__ void scatter_candidate_2w(DevCtx &d, ShardState &st, EventRng &rng_sh, ScatterMail &m, int i, int n_dt,
+                                     int *event_did_occur)
+{
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp-0 lane-0 state carried across stages
+    unsigned char flags = 0;
+    double r0 = 0, r1 = 0, r2 = 0, theta = 0;
+    CellState c;
+    KnTheta kn;
+    ScatterRot rot;
+    EventRng rng;
+    double s[4] = {0, 0, 0, 0}; // warp 1, replicated in its lanes
+    double sn = 0, cs = 1;
+
+    // ---- stage A: candidate position after this event's pushes, fluid velocity ----
+    if (w == 0) {
+        if (lane == 0) {
+            rng = rng_sh;
+            flags = d.ph.flags[i];
+            double p[4] = {d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i]};
+            r0 = d.ph.r0[i]; r1 = d.ph.r1[i]; r2 = d.ph.r2[i];
+            if (flags & F_MOVABLE) apply_pushes(st, n_dt, p[0], p[1], p[2], p[3], r0, r1, r2);
+            c = load_cell_state(d.cells, d.ph.idx[i]);
+            double fb[3];
+            fluid_beta_of(d, c, r0, r1, fb);
+            m.zhat[0] = 0; m.zhat[1] = 0; m.zhat[2] = 1;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                m.fb[k] = fb[k];
+                m.nfb[k] = -1 * fb[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) m.p[k] = p[k];
+            m.pc[0] = d.ph.c0[i]; m.pc[1] = d.ph.c1[i]; m.pc[2] = d.ph.c2[i]; m.pc[3] = d.ph.c3[i];
+        }
+        __syncwarp();
+    } else {
+        s[0] = d.ph.s0[i]; s[1] = d.ph.s1[i]; s[2] = d.ph.s2[i]; s[3] = d.ph.s3[i];
+    }
+    pair_bar();
+    // ---- stage B: electron + boost into its rest frame | lab -> fluid Stokes rotation ----
+    if (w == 0) {
+        if (lane == 0) {
+            double pc[4] = {m.pc[0], m.pc[1], m.pc[2], m.pc[3]};
+            double el[4], el_v[3], php[4];
+            single_thermal_electron(el, c.temp, pc, rng);
+            scatter_stage_boost(el, pc, el_v, php);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                m.el_v[k] = el_v[k];
+                m.nel_v[k] = (-1 * el_v[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                m.pcb[k] = pc[k];
+                m.php[k] = php[k];
+            }
+        }
+        __syncwarp();
+    } else {
+        // stokesRotation(fluid_beta, p, comv_p), Src/mclib.c:1190-1196
+        lane_angle(lane == 0 ? m.p + 1 : m.pc + 1, lane == 0 ? m.zhat : m.fb, lane == 0 ? m.p + 1 : m.pc + 1,
+                   lane == 0 ? m.fb : m.zhat, lane < 2, sn, cs);
+        rot_from_lane(sn, cs, 0, s);
+        rot_from_lane(sn, cs, 1, s);
+    }
+    pair_bar();
+    // ---- stage C: align + Klein-Nishina accept / polar angle | fluid -> electron-frame rotation ----
+    if (w == 0) {
+        if (lane == 0) {
+            double php[4] = {m.php[0], m.php[1], m.php[2], m.php[3]};
+            scatter_stage_align(php, rot);
+            m.occurred = kn_accept_theta(theta, php[0], kn, rng);
+        }
+        __syncwarp();
+    } else {
+        // stokesRotation(el_v, ph_comov, ph_p_prime), Src/mcrat_scattering.c:245-253
+        lane_angle(lane == 0 ? m.pcb + 1 : m.php + 1, lane == 0 ? m.zhat : m.el_v, lane == 0 ? m.pcb + 1 : m.php + 1,
+                   lane == 0 ? m.el_v : m.zhat, lane < 2, sn, cs);
+        rot_from_lane(sn, cs, 0, s);
+        rot_from_lane(sn, cs, 1, s);
+        if (lane == 0) {
+            m.q = s[1];
+            m.u = s[2];
+        }
+    }
+    pair_bar();
+    if (!m.occurred) { // Klein-Nishina rejection: the draws are spent, nothing else changes
+        if (w == 0 && lane == 0) rng_sh = rng;
+        return;
+    }
+    // ---- stage D: azimuth + outgoing photon ----
+    if (w == 0) {
+        if (lane == 0) {
+            double phi = kn_phi(1, kn, m.q, m.u, rng);
+            double out[4];
+            scatter_stage_out(m.php[0], theta, phi, rot, out);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) m.out[k] = out[k];
+        }
+        __syncwarp();
+    }
+    pair_bar();
+    // ---- stage E: boosts back to the fluid and lab frames | scattering-plane angles ----
+    if (w == 0) {
+        if (lane == 0) {
+            double out[4] = {m.out[0], m.out[1], m.out[2], m.out[3]};
+            double nel_v[3] = {m.nel_v[0], m.nel_v[1], m.nel_v[2]};
+            double nfb[3] = {m.nfb[0], m.nfb[1], m.nfb[2]};
+            double pcn[4], pn[4];
+            lorentz_boost(nel_v, out, pcn, true); // Src/mcrat_scattering.c:455-463
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                m.outb[k] = out[k];
+                m.pc_new[k] = pcn[k];
+            }
+            lorentz_boost(nfb, pcn, pn, true); // Src/mclib.c:1262-1265
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                m.pc_fin[k] = pcn[k];
+                m.p_new[k] = pn[k];
+            }
+        }
+        __syncwarp();
+    } else {
+        // lane 0: into the scattering plane (Src/mcrat_scattering.c:402-405); lane 1: back out of it (:438-447)
+        lane_angle(lane == 0 ? m.php + 1 : m.out + 1, lane == 0 ? m.zhat : m.php + 1, m.out + 1,
+                   lane == 0 ? m.php + 1 : m.zhat, lane < 2, sn, cs);
+    }
+    pair_bar();
+    // ---- stage F: Fano matrix | remaining angles ----
+    double sn2 = 0, cs2 = 1;
+    if (w == 0) {
+        if (lane == 0) {
+            double f[5];
+            scatter_stage_fano(m.php, m.out, f);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) m.fano[k] = f[k];
+        }
+        __syncwarp();
+    } else {
+        // lane 0: stokesRotation(-el_v, out, pc_new) first half uses `out` as lorentzBoost left it;
+        // lane 1: its second half; lane 2 / 3: stokesRotation(-fluid_beta, pc_fin, p_new), Src/mclib.c:1267-1287
+        const double *k = lane == 0 ? m.outb + 1 : (lane == 1 ? m.pc_new + 1 : (lane == 2 ? m.pc_fin + 1 : m.p_new + 1));
+        const double *a = lane == 0 ? m.zhat : (lane == 1 ? m.nel_v : (lane == 2 ? m.zhat : m.nfb));
+        const double *b = lane == 0 ? m.nel_v : (lane == 1 ? m.zhat : (lane == 2 ? m.nfb : m.zhat));
+        lane_angle(k, a, k, b, lane < 4, sn2, cs2);
+    }
+    pair_bar();
+    if (w == 1) {
+        rot_from_lane(sn, cs, 0, s);
+        {
+            double f[5] = {m.fano[0], m.fano[1], m.fano[2], m.fano[3], m.fano[4]};
+            fano_apply(f, s);
+        }
+        rot_from_lane(sn, cs, 1, s);
+        rot_from_lane(sn2, cs2, 0, s);
+        rot_from_lane(sn2, cs2, 1, s);
+        rot_from_lane(sn2, cs2, 2, s);
+        rot_from_lane(sn2, cs2, 3, s);
+        if (lane == 0) {
+            d.ph.s0[i] = s[0];
+            d.ph.s1[i] = s[1];
+            d.ph.s2[i] = s[2];
+            d.ph.s3[i] = s[3];
+        }
+    } else if (lane == 0) {
+        d.ph.p0[i] = m.p_new[0]; d.ph.p1[i] = m.p_new[1]; d.ph.p2[i] = m.p_new[2]; d.ph.p3[i] = m.p_new[3];
+        d.ph.c0[i] = m.pc_fin[0]; d.ph.c1[i] = m.pc_fin[1]; d.ph.c2[i] = m.pc_fin[2]; d.ph.c3[i] = m.pc_fin[3];
+        d.ph.nscatt[i] = d.ph.nscatt[i] + 1;
+        d.ph.flags[i] = flags | F_RECALC;
+        d.ph.r0[i] = r0;
+        d.ph.r1[i] = r1;
+        d.ph.r2[i] = r2;
+        st.pushed_slot = i;
+        st.scatt_cnt += 1;
+        *event_did_occur = 1;
+        rng_sh = rng;
+    }
+}
 
 __device__ void scatter_candidate(DevCtx &d, ShardState &st, EventRng &rng, int i, int n_dt, bool &event_did_occur)
 {
@@ -999,13 +1225,11 @@ __device__ void cs_emit_single(DevCtx &d, EventRng &rng, int scatt, int slot)
 // step_mode 0: frame loop (driver bookkeeping included); 1: photonEvent only (dt_max given)
 // blockmin_valid: the pass wrote per-block minima for this iteration (fused path / step API)
 template <int EVT_THREADS>
-__global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int parity, int nb_per_shard, int step_mode,
-                                                            double dt_max_arg)
+__device__ __forceinline__ void event_body(DevCtx &d, const int s, int parity, int nb_per_shard, int step_mode,
+                                           double dt_max_arg)
 {
-    const int s = blockIdx.x;
     ShardState &st = d.sh[s];
     GlobalState &gs = *d.gs;
-    if (loop_stopped(gs, st)) return;
 
     __shared__ double sh_cand_t;
     __shared__ int sh_cand_i, sh_finished;
@@ -1056,8 +1280,9 @@ __global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int parity
     block_argmin<EVT_THREADS>(bt, bi);
 
     __shared__ EventRng rng_sh;
+    __shared__ ScatterMail mail;
     __shared__ double old_scatt_time, scatt_time, dt_max;
-    __shared__ int n_dt, ph_index;
+    __shared__ int n_dt, ph_index, sh_try, sh_event;
     if (threadIdx.x == 0) {
         sh_cand_t = bt;
         sh_cand_i = bi;
@@ -1106,21 +1331,17 @@ __global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int parity
         if (threadIdx.x == 0) {
             const int i = sh_cand_i;
             const double t = sh_cand_t;
-            bool event = false;
+            bool event = false, attempt = false;
             ph_index = i;
             scatt_time = t;
             if (t < dt_max) {
                 if (n_dt < MAX_DT) {
                     st.dt_list[n_dt] = t - old_scatt_time;
                     n_dt++;
+                    attempt = true;
                 } else {
                     gs.error = MCRAT_B200_ERR_STATE;
                     event = true;
-                }
-                if (!event) {
-                    EventRng rng = rng_sh;
-                    scatter_candidate(d, st, rng, i, n_dt, event);
-                    rng_sh = rng;
                 }
             } else {
                 scatt_time = dt_max;
@@ -1129,8 +1350,24 @@ __global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int parity
                 event = true;
             }
             old_scatt_time = scatt_time;
-            sh_finished = event ? 1 : 0;
+            sh_try = attempt ? 1 : 0;
+            sh_event = event ? 1 : 0;
         }
+        __syncthreads();
+        if (sh_try) {
+            if (d.stokes) {
+                // two warps: momentum chain | Stokes chain
+                if (threadIdx.x < 64) scatter_candidate_2w(d, st, rng_sh, mail, sh_cand_i, n_dt, &sh_event);
+            } else if (threadIdx.x == 0) {
+                EventRng rng = rng_sh;
+                bool event = false;
+                scatter_candidate(d, st, rng, sh_cand_i, n_dt, event);
+                rng_sh = rng;
+                if (event) sh_event = 1;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) sh_finished = sh_event;
         __syncthreads();
         if (sh_finished) break;
         // Klein-Nishina rejection (rare): next entry of this shard's time order after (cand_t, cand_i)
@@ -1220,6 +1457,15 @@ __global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int parity
             if (rng_sh.exhausted) gs.error = MCRAT_B200_ERR_REPLAY;
         }
     }
+}
+
+template <int EVT_THREADS>
+__global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int parity, int nb_per_shard, int step_mode,
+                                                            double dt_max_arg)
+{
+    const int s = blockIdx.x;
+    if (loop_stopped(*d.gs, d.sh[s])) return;
+    event_body<EVT_THREADS>(d, s, parity, nb_per_shard, step_mode, dt_max_arg);
 }
 
 // head of the time order only (step API calcMeanFreePath; single shard)
