@@ -79,9 +79,12 @@ typedef struct mcrat_b200_config {
     uint32_t shard;        /* shard (rank) id mixed into the Philox key */
     int profile;           /* 1: time each kernel class with CUDA events (see kernel_times) */
     void *stream;          /* cudaStream_t to run on, or NULL to let the library create one */
-    int scan_index;        /* 0: every re-location is the full photon x cell scan of the reference (K1);
+    int scan_index;        /* 0: the rescan of a new hydro frame (find_nearest_grid_switch = 1) and the streamed
+                            *    loop re-locate with the full photon x cell scan of the reference (K1 / K1b);
                             * 1: the same first-match search through a bounding-box index over the
-                            *    cells in array order (identical results, far fewer tests) */
+                            *    cells in array order (identical results, far fewer tests).
+                            * The persistent loop always re-locates the few photons that change cell in a
+                            * steady-state iteration through the index (one warp per photon). */
 } mcrat_b200_config;
 
 typedef struct mcrat_b200_ctx mcrat_b200_ctx;
@@ -190,6 +193,17 @@ int mcrat_b200_average_photon_energy(mcrat_b200_ctx *ctx, double *avg_energy);
  * or when the host must act (stats->cs_host_pending, stats->error). */
 int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remaining_time, long long max_iters,
                          int find_nearest_grid_switch, mcrat_b200_frame_stats *stats);
+
+/* How the loop is driven.  STREAMED: four stream-ordered kernel launches per iteration (pass, re-locate,
+ * finish, event), enqueued in growing batches.  PERSISTENT: one cooperative launch per frame; every
+ * sub-shard is iterated by resident blocks that hand over through a generation word in global memory
+ * (no launch boundary inside the loop; sub-shards advance independently, like MPI ranks).  AUTO
+ * (default): PERSISTENT while the list fits in L2 (<= 2^21 photons), STREAMED above.  Both give
+ * bit-identical photons; the replay harness and profile = 1 always use STREAMED. */
+#define MCRAT_B200_LOOP_AUTO 0
+#define MCRAT_B200_LOOP_STREAMED 1
+#define MCRAT_B200_LOOP_PERSISTENT 2
+int mcrat_b200_set_loop_mode(mcrat_b200_ctx *ctx, int mode);
 
 /* per-sub-shard view of the counters (cumulative since the shard layout was set) and its slot range */
 int mcrat_b200_get_shard_stats(mcrat_b200_ctx *ctx, int shard, mcrat_b200_frame_stats *stats, int *first_slot,

@@ -101,6 +101,12 @@ struct ShardState {
     int done, pause_cs, counted_stopped;
     int last_scattered_idx, head_idx; // global slot indices
     int first, count;                 // slot range
+    // persistent frame loop (frame_loop_kernel): inter-block protocol of the blocks that share this shard
+    unsigned int arrive;              // tickets drawn by blocks that finished a phase (monotonic)
+    unsigned int gen;                 // phases completed, published by the last arriver (monotonic)
+    int reloc_n;                      // entries of this shard's region of the relocation list
+    int halt;                         // loop_stopped() as evaluated by the publishing block
+    int reloc_heavy;                  // the last iteration re-located many photons: better served by K1/K1b
 };
 
 struct GlobalState {
@@ -323,91 +329,100 @@ __global__ void build_geo_kernel(int ndim3, int n, int n_padded, const double *c
 // ------------------------------------------------------------------------------------------
 constexpr int PASS_THREADS = 256;
 
+// One block's share of a shard: photons j = b*THREADS + tid, stride nblk*THREADS.
+// LOCAL_RELOC = false: relocating photons go to the global list (gs.reloc_count[parity]) that
+// K1/K1b/K1c + finish_kernel work off; true: to the shard's own region [first, first+count) of the
+// list (persistent loop: shards advance independently of each other).
+template <bool FUSE_MFP, bool LOCAL_RELOC, int THREADS>
+__device__ __forceinline__ void pass_body(DevCtx &d, const int s, const int b, const int nblk, const int sw, const int parity,
+                                          double &best_t, int &best_i)
+{
+    ShardState &sh = d.sh[s];
+    const int n_dt = sh.n_dt;
+    const int pushed = sh.pushed_slot;
+    const unsigned long long iter = sh.iter;
+    const uint32_t k1 = d.k1 ^ (d.shard_base + (uint32_t)s);
+    const int ndim3 = (d.dims == D_THREE);
+    const double default_t = 1e12 / C_LIGHT; // Src/mclib.c:620, 684-687
+    const int first = sh.first, count = sh.count;
+
+    for (int j = b * THREADS + threadIdx.x; j < count; j += nblk * THREADS) {
+        const int i = first + j;
+        // every column this photon can need is requested up front (one round trip to HBM instead
+        // of three dependent ones); the momentum is used by the pushes, tau by the free-path draw
+        const unsigned char flags = d.ph.flags[i];
+        const int idx = d.ph.idx[i];
+        double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
+        const double p0 = d.ph.p0[i], p1 = d.ph.p1[i], p2 = d.ph.p2[i], p3 = d.ph.p3[i];
+        double tau = FUSE_MFP ? d.ph.tau[i] : 0.0;
+        if (n_dt > 0 && (flags & F_MOVABLE) && i != pushed) {
+            apply_pushes(sh, n_dt, p0, p1, p2, p3, r0, r1, r2);
+            d.ph.r0[i] = r0;
+            d.ph.r1[i] = r1;
+            d.ph.r2[i] = r2;
+        }
+        // findContainingHydroCell, Src/mclib.c:469-597
+        double h0, h1, h2;
+        coord_to_hydro(d.dims, d.geom, r0, r1, r2, h0, h1, h2);
+        bool in_domain;
+        if (!ndim3)
+            in_domain = ((h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) && (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0])) &&
+                        (idx != -1);
+        else
+            in_domain = ((h2 < d.cells.dom[5]) && (h2 > d.cells.dom[4]) && (h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) &&
+                         (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0])) &&
+                        (idx != -1);
+        double t = default_t;
+        bool have_t = true;
+        if (in_domain) {
+            int blk = (sw == 0) ? idx : 0;
+            bool inb = in_cell(ndim3, d.cells, blk, h0, h1, h2);
+            if (d.cs && blk == 0) { // Src/mclib.c:510-515
+                if ((d.ph.c0[i]) + (d.ph.c1[i]) + (d.ph.c2[i]) + (d.ph.c3[i]) == 0) inb = false;
+            }
+            if (sw == 1 || !inb) {
+                int pos = LOCAL_RELOC ? first + atomicAdd(&sh.reloc_n, 1) : atomicAdd(&d.gs->reloc_count[parity], 1);
+                d.reloc_slot[pos] = i;
+                d.reloc_h0[pos] = h0;
+                d.reloc_h1[pos] = h1;
+                d.reloc_h2[pos] = h2;
+                d.reloc_best[pos] = INT_MAX;
+                have_t = false; // finish completes this photon
+            } else if (FUSE_MFP) {
+                // calcMeanFreePath, Src/mclib.c:657-687
+                if (flags & F_RECALC) {
+                    CellState c = load_cell_state(d.cells, idx);
+                    int terr = 0;
+                    tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, p1, p2, p3, d.ph.c0[i], &terr);
+                    if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
+                    d.ph.tau[i] = tau;
+                    d.ph.flags[i] = flags & ~F_RECALC;
+                }
+                double xi = philox_mfp_uniform(d.k0, k1, iter, (uint32_t)j);
+                t = free_path_time(tau, xi);
+            }
+        } else {
+            if (idx != -1) d.ph.idx[i] = -1; // Src/mclib.c:589-595
+        }
+        if (FUSE_MFP && have_t) {
+            d.ph.tts[i] = t;
+            if (lex_less(t, i, best_t, best_i)) {
+                best_t = t;
+                best_i = i;
+            }
+        }
+    }
+}
+
 template <bool FUSE_MFP>
 __global__ void __launch_bounds__(PASS_THREADS, 4) pass_kernel(DevCtx d, int sw, int parity)
 {
     const int s = blockIdx.x / d.blocks_per_shard;
     const int b = blockIdx.x - s * d.blocks_per_shard;
-    const ShardState &sh = d.sh[s];
-    const GlobalState &gs = *d.gs;
     if (blockIdx.x == 0 && threadIdx.x == 0) d.gs->reloc_count[parity ^ 1] = 0;
     double best_t = DBL_MAX;
     int best_i = INT_MAX;
-    if (!loop_stopped(gs, sh)) {
-        const int n_dt = sh.n_dt;
-        const int pushed = sh.pushed_slot;
-        const unsigned long long iter = sh.iter;
-        const uint32_t k1 = d.k1 ^ (d.shard_base + (uint32_t)s);
-        const int ndim3 = (d.dims == D_THREE);
-        const double default_t = 1e12 / C_LIGHT; // Src/mclib.c:620, 684-687
-
-        for (int j = b * PASS_THREADS + threadIdx.x; j < sh.count; j += d.blocks_per_shard * PASS_THREADS) {
-            const int i = sh.first + j;
-            // every column this photon can need is requested up front (one round trip to HBM instead
-            // of three dependent ones); the momentum is used by the pushes, tau by the free-path draw
-            const unsigned char flags = d.ph.flags[i];
-            const int idx = d.ph.idx[i];
-            double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
-            const double p0 = d.ph.p0[i], p1 = d.ph.p1[i], p2 = d.ph.p2[i], p3 = d.ph.p3[i];
-            double tau = FUSE_MFP ? d.ph.tau[i] : 0.0;
-            if (n_dt > 0 && (flags & F_MOVABLE) && i != pushed) {
-                apply_pushes(sh, n_dt, p0, p1, p2, p3, r0, r1, r2);
-                d.ph.r0[i] = r0;
-                d.ph.r1[i] = r1;
-                d.ph.r2[i] = r2;
-            }
-            // findContainingHydroCell, Src/mclib.c:469-597
-            double h0, h1, h2;
-            coord_to_hydro(d.dims, d.geom, r0, r1, r2, h0, h1, h2);
-            bool in_domain;
-            if (!ndim3)
-                in_domain = ((h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) && (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0])) &&
-                            (idx != -1);
-            else
-                in_domain = ((h2 < d.cells.dom[5]) && (h2 > d.cells.dom[4]) && (h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) &&
-                             (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0])) &&
-                            (idx != -1);
-            double t = default_t;
-            bool have_t = true;
-            if (in_domain) {
-                int blk = (sw == 0) ? idx : 0;
-                bool inb = in_cell(ndim3, d.cells, blk, h0, h1, h2);
-                if (d.cs && blk == 0) { // Src/mclib.c:510-515
-                    if ((d.ph.c0[i]) + (d.ph.c1[i]) + (d.ph.c2[i]) + (d.ph.c3[i]) == 0) inb = false;
-                }
-                if (sw == 1 || !inb) {
-                    int pos = atomicAdd(&d.gs->reloc_count[parity], 1);
-                    d.reloc_slot[pos] = i;
-                    d.reloc_h0[pos] = h0;
-                    d.reloc_h1[pos] = h1;
-                    d.reloc_h2[pos] = h2;
-                    d.reloc_best[pos] = INT_MAX;
-                    have_t = false; // finish_kernel completes this photon
-                } else if (FUSE_MFP) {
-                    // calcMeanFreePath, Src/mclib.c:657-687
-                    if (flags & F_RECALC) {
-                        CellState c = load_cell_state(d.cells, idx);
-                        int terr = 0;
-                        tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, p1, p2, p3, d.ph.c0[i], &terr);
-                        if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
-                        d.ph.tau[i] = tau;
-                        d.ph.flags[i] = flags & ~F_RECALC;
-                    }
-                    double xi = philox_mfp_uniform(d.k0, k1, iter, (uint32_t)j);
-                    t = free_path_time(tau, xi);
-                }
-            } else {
-                if (idx != -1) d.ph.idx[i] = -1; // Src/mclib.c:589-595
-            }
-            if (FUSE_MFP && have_t) {
-                d.ph.tts[i] = t;
-                if (lex_less(t, i, best_t, best_i)) {
-                    best_t = t;
-                    best_i = i;
-                }
-            }
-        }
-    }
+    if (!loop_stopped(*d.gs, d.sh[s])) pass_body<FUSE_MFP, false, PASS_THREADS>(d, s, b, d.blocks_per_shard, sw, parity, best_t, best_i);
     if (FUSE_MFP) {
         block_argmin<PASS_THREADS>(best_t, best_i);
         if (threadIdx.x == 0) {
@@ -675,40 +690,59 @@ __device__ __forceinline__ bool in_box(int ndim3, const double *bx, double x0, d
     return in;
 }
 
+// One warp locates one photon.  Level-2 boxes are all tested first (independent loads, 32 per
+// round, hits kept as one bit per round and lane), then the hits are descended in ascending order:
+// 32 level-1 boxes per level-2 box and 32 cells per level-1 box, one per lane; the lowest lane of
+// the first ballot with a containing cell is the lowest containing index = findContainingBlock's answer.
+__device__ __forceinline__ int warp_locate_indexed(const DevCtx &d, const double x0, const double x1, const double x2,
+                                                   long long &cells_tested, long long &boxes_tested)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int ndim3 = (d.dims == D_THREE);
+    const CellCols &c = d.cells;
+    int best = INT_MAX;
+    for (int chunk = 0; chunk < c.nbox2 && best == INT_MAX; chunk += 2048) {
+        const int rounds = min(64, (c.nbox2 - chunk + 31) / 32);
+        unsigned long long mine = 0;
+#pragma unroll 4
+        for (int r = 0; r < rounds; ++r) {
+            const int b2 = chunk + r * 32 + lane;
+            if (b2 < c.nbox2 && in_box(ndim3, c.box2 + 6 * b2, x0, x1, x2)) mine |= 1ull << r;
+        }
+        boxes_tested += min(c.nbox2 - chunk, 2048);
+        for (int r = 0; r < rounds && best == INT_MAX; ++r) {
+            unsigned m2 = __ballot_sync(full, (mine >> r) & 1ull);
+            while (m2 && best == INT_MAX) {
+                const int B2 = chunk + r * 32 + (__ffs(m2) - 1);
+                m2 &= m2 - 1;
+                const int b1 = B2 * BOX_T + lane;
+                unsigned m1 = __ballot_sync(full, b1 < c.nbox1 && in_box(ndim3, c.box1 + 6 * b1, x0, x1, x2));
+                boxes_tested += min(BOX_T, c.nbox1 - B2 * BOX_T);
+                while (m1 && best == INT_MAX) {
+                    const int B1 = B2 * BOX_T + (__ffs(m1) - 1);
+                    m1 &= m1 - 1;
+                    const int cell = B1 * BOX_T + lane;
+                    const unsigned mc = __ballot_sync(full, cell < c.n && in_cell(ndim3, c, cell, x0, x1, x2));
+                    cells_tested += min(BOX_T, c.n - B1 * BOX_T);
+                    if (mc) best = B1 * BOX_T + (__ffs(mc) - 1);
+                }
+            }
+        }
+    }
+    return best;
+}
+
 __global__ void __launch_bounds__(128) scan_index_kernel(DevCtx d, int parity)
 {
     const GlobalState &gs = *d.gs;
     if (gs.error != 0) return;
     const int count = gs.reloc_count[parity];
-    const int ndim3 = (d.dims == D_THREE);
     long long cells_tested = 0, boxes_tested = 0;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
-        const double x0 = d.reloc_h0[j], x1 = d.reloc_h1[j], x2 = d.reloc_h2[j];
-        int best = INT_MAX;
-        for (int b2 = 0; b2 < d.cells.nbox2 && best == INT_MAX; ++b2) {
-            boxes_tested++;
-            if (!in_box(ndim3, d.cells.box2 + 6 * b2, x0, x1, x2)) continue;
-            const int e1 = min(d.cells.nbox1, b2 * BOX_T + BOX_T);
-            for (int b1 = b2 * BOX_T; b1 < e1 && best == INT_MAX; ++b1) {
-                boxes_tested++;
-                if (!in_box(ndim3, d.cells.box1 + 6 * b1, x0, x1, x2)) continue;
-                const int ec = min(d.cells.n, b1 * BOX_T + BOX_T);
-                for (int c = b1 * BOX_T; c < ec; ++c) {
-                    cells_tested++;
-                    if (in_cell(ndim3, d.cells, c, x0, x1, x2)) {
-                        best = c;
-                        break;
-                    }
-                }
-            }
-        }
-        d.reloc_best[j] = best;
-    }
-    // one atomic pair per warp
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        cells_tested += __shfl_xor_sync(0xffffffffu, cells_tested, off);
-        boxes_tested += __shfl_xor_sync(0xffffffffu, boxes_tested, off);
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int j = warp; j < count; j += nwarps) {
+        const int best = warp_locate_indexed(d, d.reloc_h0[j], d.reloc_h1[j], d.reloc_h2[j], cells_tested, boxes_tested);
+        if ((threadIdx.x & 31) == 0) d.reloc_best[j] = best;
     }
     if ((threadIdx.x & 31) == 0 && (cells_tested | boxes_tested)) {
         atomicAdd((unsigned long long *)&d.gs->cell_evals, (unsigned long long)cells_tested);
@@ -722,6 +756,45 @@ __global__ void __launch_bounds__(128) scan_index_kernel(DevCtx d, int parity)
 // ------------------------------------------------------------------------------------------
 constexpr int FIN_THREADS = 128;
 
+// one relocated photon: new cell (or -1), comoving 4-momentum, optical depth, free-path draw
+template <bool FUSE_MFP>
+__device__ __forceinline__ bool finish_one(DevCtx &d, const int i, const int b, const int sw)
+{
+    const int s = shard_of(d, i);
+    ShardState &sh = d.sh[s];
+    double t = 1e12 / C_LIGHT;
+    bool missing = false;
+    if (b == INT_MAX) {
+        d.ph.idx[i] = -1; // Src/mclib.c:536, 581-584
+        missing = true;
+    } else {
+        d.ph.idx[i] = b;
+        double p[4] = {d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i]};
+        double r0 = d.ph.r0[i], r1 = d.ph.r1[i];
+        CellState c = load_cell_state(d.cells, b);
+        double fb[3], pc[4];
+        fluid_beta_of(d, c, r0, r1, fb);
+        lorentz_boost(fb, p, pc, true);
+        d.ph.c0[i] = pc[0];
+        d.ph.c1[i] = pc[1];
+        d.ph.c2[i] = pc[2];
+        d.ph.c3[i] = pc[3];
+        int terr = 0;
+        double tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, p[1], p[2], p[3], pc[0], &terr);
+        if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
+        d.ph.tau[i] = tau;
+        d.ph.flags[i] = d.ph.flags[i] & ~F_RECALC;
+        if (sw == 0) atomicAdd((unsigned long long *)&sh.reloc_total, 1ull); // Src/mclib.c:579, 608-611
+        if (FUSE_MFP) {
+            const uint32_t k1 = d.k1 ^ (d.shard_base + (uint32_t)s);
+            double xi = philox_mfp_uniform(d.k0, k1, sh.iter, (uint32_t)(i - sh.first));
+            t = free_path_time(tau, xi);
+        }
+    }
+    if (FUSE_MFP) d.ph.tts[i] = t;
+    return missing;
+}
+
 template <bool FUSE_MFP>
 __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(DevCtx d, int sw, int parity)
 {
@@ -729,41 +802,8 @@ __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(DevCtx d, int sw, i
     if (gs.error != 0) return;
     const int count = gs.reloc_count[parity];
     int missing = 0;
-    for (int j = blockIdx.x * FIN_THREADS + threadIdx.x; j < count; j += gridDim.x * FIN_THREADS) {
-        const int i = d.reloc_slot[j];
-        const int b = d.reloc_best[j];
-        const int s = shard_of(d, i);
-        ShardState &sh = d.sh[s];
-        double t = 1e12 / C_LIGHT;
-        if (b == INT_MAX) {
-            d.ph.idx[i] = -1; // Src/mclib.c:536, 581-584
-            missing++;
-        } else {
-            d.ph.idx[i] = b;
-            double p[4] = {d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i]};
-            double r0 = d.ph.r0[i], r1 = d.ph.r1[i];
-            CellState c = load_cell_state(d.cells, b);
-            double fb[3], pc[4];
-            fluid_beta_of(d, c, r0, r1, fb);
-            lorentz_boost(fb, p, pc, true);
-            d.ph.c0[i] = pc[0];
-            d.ph.c1[i] = pc[1];
-            d.ph.c2[i] = pc[2];
-            d.ph.c3[i] = pc[3];
-            int terr = 0;
-            double tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, p[1], p[2], p[3], pc[0], &terr);
-            if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
-            d.ph.tau[i] = tau;
-            d.ph.flags[i] = d.ph.flags[i] & ~F_RECALC;
-            if (sw == 0) atomicAdd((unsigned long long *)&sh.reloc_total, 1ull); // Src/mclib.c:579, 608-611
-            if (FUSE_MFP) {
-                const uint32_t k1 = d.k1 ^ (d.shard_base + (uint32_t)s);
-                double xi = philox_mfp_uniform(d.k0, k1, sh.iter, (uint32_t)(i - sh.first));
-                t = free_path_time(tau, xi);
-            }
-        }
-        if (FUSE_MFP) d.ph.tts[i] = t;
-    }
+    for (int j = blockIdx.x * FIN_THREADS + threadIdx.x; j < count; j += gridDim.x * FIN_THREADS)
+        if (finish_one<FUSE_MFP>(d, d.reloc_slot[j], d.reloc_best[j], sw)) missing++;
     if (missing) atomicAdd(&d.gs->not_found, missing);
 }
 
@@ -1225,8 +1265,8 @@ __device__ void cs_emit_single(DevCtx &d, EventRng &rng, int scatt, int slot)
 // step_mode 0: frame loop (driver bookkeeping included); 1: photonEvent only (dt_max given)
 // blockmin_valid: the pass wrote per-block minima for this iteration (fused path / step API)
 template <int EVT_THREADS>
-__device__ __forceinline__ void event_body(DevCtx &d, const int s, int parity, int nb_per_shard, int step_mode,
-                                           double dt_max_arg)
+__device__ __forceinline__ void event_body(DevCtx &d, const int s, const int reloc_base, const int R, int nb_per_shard,
+                                           int step_mode, double dt_max_arg)
 {
     ShardState &st = d.sh[s];
     GlobalState &gs = *d.gs;
@@ -1244,11 +1284,10 @@ __device__ __forceinline__ void event_body(DevCtx &d, const int s, int parity, i
                 bi = d.bm_i[q];
             }
         }
-        // photons relocated in this iteration got their time in finish_kernel
-        const int R = gs.reloc_count[parity];
+        // photons relocated in this iteration got their time in finish
         if (R > 0 && R <= RELOC_LIST_SCAN_MAX) {
             for (int j = threadIdx.x; j < R; j += EVT_THREADS) {
-                const int i = d.reloc_slot[j];
+                const int i = d.reloc_slot[reloc_base + j];
                 if (i >= st.first && i < st.first + st.count) {
                     double t = d.ph.tts[i];
                     if (lex_less(t, i, bt, bi)) {
@@ -1465,7 +1504,154 @@ __global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int parity
 {
     const int s = blockIdx.x;
     if (loop_stopped(*d.gs, d.sh[s])) return;
-    event_body<EVT_THREADS>(d, s, parity, nb_per_shard, step_mode, dt_max_arg);
+    event_body<EVT_THREADS>(d, s, 0, d.gs->reloc_count[parity], nb_per_shard, step_mode, dt_max_arg);
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent frame loop: the whole while-loop of Src/mcrat.c:761-851 in ONE launch.
+//
+// The streamed loop above costs four dependent kernel launches per scattering; for lists that fit
+// in L2 the launch boundaries, not the work, set the iteration time.  Here every sub-shard (one
+// reference "rank") is owned by `bps` resident blocks that iterate on their own:
+//   pass (push + re-check + free-path draw + block arg-min)  ->  arrive
+//   last arriver: re-locate the few photons that left their cell (one warp per photon through the
+//                 bounding-box index), shard arg-min, scattering event, publish the new clock /
+//                 push list                                  ->  release
+//   the other blocks spin on the shard's generation word (ld.acquire.gpu) and start the next pass.
+// Shards never wait for each other (exactly like MPI ranks), so a rank that finishes its frame or
+// rejects a Klein-Nishina candidate does not hold the others up.  All blocks are co-resident
+// (cooperative launch); with one block per shard a block walks through its shards one after the other.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+constexpr int RELOC_HEAVY = 64; // re-locations per shard and iteration above which the grid-wide K1b / K1c serve better
+
+// relocated photons of this iteration: new cell, comoving momentum, tau', free-path draw
+template <int THREADS>
+__device__ __forceinline__ void finish_reloc(DevCtx &d, ShardState &st, const int R)
+{
+    int missing = 0;
+    for (int j = threadIdx.x; j < R; j += THREADS)
+        if (finish_one<true>(d, d.reloc_slot[st.first + j], d.reloc_best[st.first + j], 0)) missing++;
+    if (missing) atomicAdd(&d.gs->not_found, missing);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st.reloc_n = 0;
+        if (R > RELOC_HEAVY) st.reloc_heavy = 1;
+    }
+}
+
+// the shard's relocation entries [first, first+R): one warp per photon through the bounding-box index
+template <int THREADS>
+__device__ __forceinline__ void relocate_shard(DevCtx &d, ShardState &st, const int R)
+{
+    long long cells_tested = 0, boxes_tested = 0;
+    for (int j = threadIdx.x >> 5; j < R; j += THREADS / 32) {
+        const int q = st.first + j;
+        const int best = warp_locate_indexed(d, d.reloc_h0[q], d.reloc_h1[q], d.reloc_h2[q], cells_tested, boxes_tested);
+        if ((threadIdx.x & 31) == 0) d.reloc_best[q] = best;
+    }
+    if ((threadIdx.x & 31) == 0 && (cells_tested | boxes_tested)) {
+        atomicAdd((unsigned long long *)&d.gs->cell_evals, (unsigned long long)cells_tested);
+        atomicAdd((unsigned long long *)&d.gs->box_evals, (unsigned long long)boxes_tested);
+    }
+    __syncthreads();
+    finish_reloc<THREADS>(d, st, R);
+    __syncthreads();
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 8) frame_loop_kernel(DevCtx d, const int bps)
+{
+    __shared__ int sh_last, sh_halt;
+    GlobalState &gs = *d.gs;
+    const int groups = gridDim.x / bps;
+    const int g = blockIdx.x / bps, b = blockIdx.x - g * bps;
+    if (g >= groups) return;
+
+    for (int s = g; s < d.nshards; s += groups) {
+        ShardState &st = d.sh[s];
+        unsigned phase = 0; // phases this block has been through; arrive / gen were zeroed before the launch
+        // stop test at entry: shard state only, so that all blocks of the shard decide alike
+        bool halt = st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters);
+
+        // the last arriver of a phase returns true
+        auto arrive = [&]() -> bool {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                ++phase;
+                if (bps == 1) {
+                    sh_last = 1;
+                } else {
+                    __threadfence();
+                    const unsigned ticket = atomicAdd(&st.arrive, 1u);
+                    sh_last = (ticket == phase * (unsigned)bps - 1u) ? 1 : 0;
+                    if (sh_last) __threadfence();
+                }
+            }
+            __syncthreads();
+            return sh_last != 0;
+        };
+        // last arriver: hand the shard back to its blocks
+        auto publish = [&]() {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                st.halt = (loop_stopped(gs, st) || st.reloc_heavy) ? 1 : 0;
+                sh_halt = st.halt;
+                if (bps > 1) {
+                    __threadfence();
+                    st_release_u32(&st.gen, phase);
+                }
+            }
+            __syncthreads();
+        };
+        auto wait = [&]() {
+            if (threadIdx.x == 0) {
+                unsigned spins = 0;
+                bool ok = true;
+                while (ld_acquire_u32(&st.gen) < phase) {
+                    __nanosleep(40);
+                    if (++spins > (1u << 24)) { // ~1 s: never in a healthy run; refuse to hang the GPU
+                        gs.error = MCRAT_B200_ERR_STATE;
+                        ok = false;
+                        break;
+                    }
+                }
+                sh_halt = ok ? *(volatile int *)&st.halt : 1;
+            }
+            __syncthreads();
+        };
+        while (!halt) {
+            // ---- pass ----
+            double best_t = DBL_MAX;
+            int best_i = INT_MAX;
+            pass_body<true, true, THREADS>(d, s, b, bps, 0, 0, best_t, best_i);
+            block_argmin<THREADS>(best_t, best_i);
+            if (threadIdx.x == 0) {
+                d.bm_t[s * bps + b] = best_t;
+                d.bm_i[s * bps + b] = best_i;
+            }
+            if (arrive()) {
+                const int R = *(volatile int *)&st.reloc_n;
+                if (R > 0) relocate_shard<THREADS>(d, st, R);
+                event_body<THREADS>(d, s, st.first, R, bps, 0, 0.0);
+                publish();
+            } else {
+                wait();
+            }
+            halt = sh_halt != 0;
+            __syncthreads();
+        }
+    }
 }
 
 // head of the time order only (step API calcMeanFreePath; single shard)
@@ -1722,6 +1908,8 @@ struct mcrat_b200_ctx {
     int pass_parity;
     int last_nb_mfp;
     int want_shards;    // sub-shards requested for the next set_photons
+    int loop_mode;      // MCRAT_B200_LOOP_AUTO / _STREAMED / _PERSISTENT
+    int occ_loop256, occ_loop64; // resident blocks per SM of frame_loop_kernel<256> / <64>
     long long launches; // kernels launched through this context
     GlobalState *gs_host;          // pinned
     std::vector<ShardState> sh_host;
@@ -1852,6 +2040,8 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
     ctx->pass_parity = 0;
     ctx->last_nb_mfp = 0;
     ctx->want_shards = 1;
+    ctx->loop_mode = MCRAT_B200_LOOP_AUTO;
+    ctx->occ_loop256 = ctx->occ_loop64 = 0;
     ctx->launches = 0;
     ctx->replay_dev = nullptr;
     ctx->replay_cap = 0;
@@ -1925,6 +2115,10 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
         return bail(e, "cudaFuncSetAttribute");
     if ((e = cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(1))) != cudaSuccess)
         return bail(e, "cudaFuncSetAttribute");
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_loop256, frame_loop_kernel<256>, 256, 0)) != cudaSuccess)
+        return bail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_loop64, frame_loop_kernel<64>, 64, 0)) != cudaSuccess)
+        return bail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     *out = ctx;
     return MCRAT_B200_OK;
 }
@@ -2032,7 +2226,8 @@ API int mcrat_b200_set_hydro(mcrat_b200_ctx *ctx, int n, const double *const *fi
     build_geo_kernel<<<grid_for(ctx, c.n_padded, 256, 8), 256, 0, ctx->stream>>>(
         ndim3, n, c.n_padded, cols[0], cols[1], cols[2], cols[3], cols[4], cols[5], (double4 *)c.geoA, (double2 *)c.geoB);
     if (int rc = check_launch(ctx, "build_geo_kernel")) return rc;
-    if (ctx->cfg.scan_index) {
+    {   // the index is always built (two tiny kernels): the persistent loop re-locates through it;
+        // cfg.scan_index only decides whether the *streamed* path and the full rescan use it
         build_box1_kernel<<<grid_for(ctx, c.nbox1, 128, 8), 128, 0, ctx->stream>>>(ndim3, n, c.geoA, c.geoB, (double *)c.box1, c.nbox1);
         build_box2_kernel<<<grid_for(ctx, c.nbox2, 128, 8), 128, 0, ctx->stream>>>(c.box1, c.nbox1, (double *)c.box2, c.nbox2);
         if (int rc = check_launch(ctx, "build_box_kernels", 2)) return rc;
@@ -2293,7 +2488,8 @@ static int launch_locate(mcrat_b200_ctx *ctx, int sw, int &parity_out)
     int nb_fin;
     if (ctx->cfg.scan_index) {
         Timed t(ctx, KC_SCAN);
-        const int g = (sw == 1) ? grid_for(ctx, ctx->d.cap, 128, 16) : 8;
+        // one warp per photon
+        const int g = (sw == 1) ? grid_for(ctx, ctx->d.cap > (INT_MAX >> 5) ? INT_MAX : ctx->d.cap * 32, 128, 16) : 32;
         scan_index_kernel<<<g, 128, 0, ctx->stream>>>(ctx->d, parity);
         if (int rc = check_launch(ctx, "scan_index_kernel")) return rc;
         nb_fin = (sw == 1) ? grid_for(ctx, ctx->d.cap, FIN_THREADS, 8) : 8;
@@ -2351,6 +2547,11 @@ __global__ void reset_loop_kernel(DevCtx d, int set_times, double time_now, doub
         st.pause_cs = 0;
         st.counted_stopped = 0;
         st.iters_done = 0;
+        st.arrive = 0;
+        st.gen = 0;
+        st.reloc_n = 0;
+        st.halt = 0;
+        st.reloc_heavy = 0;
         if (set_times) {
             st.time_now = time_now;
             st.remaining_time = remaining;
@@ -2518,6 +2719,76 @@ API int mcrat_b200_average_photon_energy(mcrat_b200_ctx *ctx, double *avg_energy
 }
 
 // ---- the device-resident frame loop, Src/mcrat.c:761-851 ---------------------------------------------
+constexpr int PERSISTENT_MAX_PHOTONS = 1 << 21; // above this the pass is HBM-bound and wants the leaner pass_kernel
+
+__global__ void reset_protocol_kernel(DevCtx d)
+{
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < d.nshards; s += gridDim.x * blockDim.x) {
+        ShardState &st = d.sh[s];
+        st.arrive = 0;
+        st.gen = 0;
+        st.reloc_n = 0;
+        st.halt = 0;
+        st.reloc_heavy = 0;
+    }
+}
+
+static int reset_protocol(mcrat_b200_ctx *ctx)
+{
+    reset_protocol_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d);
+    return check_launch(ctx, "reset_protocol_kernel");
+}
+
+// geometry of the persistent launch: `bps` blocks per shard, all blocks resident
+static void frame_loop_grid(const mcrat_b200_ctx *ctx, int &threads, int &bps, int &grid)
+{
+    const int S = ctx->d.nshards;
+    const int cap256 = ctx->num_sms * ctx->occ_loop256;
+    if (S > cap256) {
+        // more shards than wide blocks fit: two-warp blocks (pass + two-warp event), a block walks
+        // through its shards one after the other if there are more shards than resident blocks
+        threads = 64;
+        bps = 1;
+        const int cap = ctx->num_sms * ctx->occ_loop64;
+        grid = S < cap ? S : cap;
+    } else {
+        threads = 256;
+        bps = (ctx->d.shard_size + 255) / 256;
+        if (bps > cap256 / S) bps = cap256 / S;
+        if (bps > BLOCKMIN_CAP / S) bps = BLOCKMIN_CAP / S;
+        if (bps < 1) bps = 1;
+        grid = S * bps;
+    }
+}
+
+static int launch_frame_loop(mcrat_b200_ctx *ctx)
+{
+    int threads, bps, grid;
+    frame_loop_grid(ctx, threads, bps, grid);
+    if (grid < 1) return fail(ctx, MCRAT_B200_ERR_STATE, "frame_loop_kernel does not fit on this device");
+    void *args[2] = {(void *)&ctx->d, (void *)&bps};
+    Timed t(ctx, KC_EVENT);
+    cudaError_t e;
+    if (threads == 64)
+        e = cudaLaunchCooperativeKernel((const void *)frame_loop_kernel<64>, dim3(grid), dim3(64), args, 0, ctx->stream);
+    else
+        e = cudaLaunchCooperativeKernel((const void *)frame_loop_kernel<256>, dim3(grid), dim3(256), args, 0, ctx->stream);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("frame_loop_kernel: ") + cudaGetErrorString(e);
+        return MCRAT_B200_ERR_CUDA;
+    }
+    return check_launch(ctx, "frame_loop_kernel");
+}
+
+API int mcrat_b200_set_loop_mode(mcrat_b200_ctx *ctx, int mode)
+{
+    if (!ctx) return MCRAT_B200_ERR_ARG;
+    if (mode != MCRAT_B200_LOOP_AUTO && mode != MCRAT_B200_LOOP_STREAMED && mode != MCRAT_B200_LOOP_PERSISTENT)
+        return fail(ctx, MCRAT_B200_ERR_ARG, "set_loop_mode: unknown mode");
+    ctx->loop_mode = mode;
+    return MCRAT_B200_OK;
+}
+
 static void fill_stats(const ShardState &s, const ShardState &b, mcrat_b200_frame_stats *o)
 {
     o->iterations = s.iters_done;
@@ -2550,35 +2821,71 @@ API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remain
     if (int rc = reset_loop(ctx, 1, time_now, remaining_time, max_iters)) return rc;
     sw = sw ? 1 : 0;
     const bool fused = !ctx->d.replay;
-    // iterations are enqueued in batches; kernels of a shard past its stop condition return at once
-    int batch = 1;
-    long long launched = 0;
-    for (;;) {
-        for (int b = 0; b < batch; ++b) {
-            int parity = 0, nb = ctx->d.blocks_per_shard;
-            if (fused) {
-                if (int rc = launch_locate<true>(ctx, sw, parity)) return rc;
-            } else {
-                if (int rc = launch_locate<false>(ctx, sw, parity)) return rc;
-                if (int rc = launch_mfp_unfused(ctx, nb)) return rc;
-            }
-            {
-                Timed t(ctx, KC_EVENT);
-                if (S >= 64)
-                    event_kernel<EVT_THREADS_MANY><<<S, EVT_THREADS_MANY, 0, ctx->stream>>>(ctx->d, parity, nb, 0, 0.0);
-                else
-                    event_kernel<EVT_THREADS><<<S, EVT_THREADS, 0, ctx->stream>>>(ctx->d, parity, nb, 0, 0.0);
-                if (int rc = check_launch(ctx, "event_kernel")) return rc;
-            }
-            sw = 0; // Src/mcrat.c:773
+    // one iteration of every running shard as four stream-ordered launches
+    auto streamed_iteration = [&]() -> int {
+        int parity = 0, nb = ctx->d.blocks_per_shard;
+        if (fused) {
+            if (int rc = launch_locate<true>(ctx, sw, parity)) return rc;
+        } else {
+            if (int rc = launch_locate<false>(ctx, sw, parity)) return rc;
+            if (int rc = launch_mfp_unfused(ctx, nb)) return rc;
+        }
+        {
+            Timed t(ctx, KC_EVENT);
+            if (S >= 64)
+                event_kernel<EVT_THREADS_MANY><<<S, EVT_THREADS_MANY, 0, ctx->stream>>>(ctx->d, parity, nb, 0, 0.0);
+            else
+                event_kernel<EVT_THREADS><<<S, EVT_THREADS, 0, ctx->stream>>>(ctx->d, parity, nb, 0, 0.0);
+            if (int rc = check_launch(ctx, "event_kernel")) return rc;
+        }
+        sw = 0; // Src/mcrat.c:773
+        return MCRAT_B200_OK;
+    };
+    const bool persistent = fused && !ctx->cfg.profile &&
+                            (ctx->loop_mode == MCRAT_B200_LOOP_PERSISTENT ||
+                             (ctx->loop_mode == MCRAT_B200_LOOP_AUTO && ctx->d.cap <= PERSISTENT_MAX_PHOTONS));
+    if (persistent) {
+        // the first iteration of a new hydro frame re-locates every photon: that is K1's job
+        long long launched = 0;
+        if (sw == 1 && max_iters != 0) {
+            if (int rc = streamed_iteration()) return rc;
             launched++;
         }
-        if (int rc = fetch_global(ctx)) return rc;
-        const GlobalState &g = *ctx->gs_host;
-        if (g.error || g.n_stopped >= S) break;
-        if (batch < 64) batch *= 2;
-        if (max_iters >= 0 && launched + batch > max_iters) batch = (int)(max_iters - launched);
-        if (batch < 1) batch = 1;
+        for (;;) {
+            if (int rc = launch_frame_loop(ctx)) return rc;
+            if (int rc = fetch_state(ctx)) return rc;
+            if (ctx->gs_host->error) break;
+            bool heavy = false, running = false;
+            for (int k = 0; k < S; ++k) {
+                const ShardState &h = ctx->sh_host[k];
+                const bool stopped = h.done || h.pause_cs || (max_iters >= 0 && h.iters_done >= max_iters);
+                if (!stopped) running = true;
+                if (!stopped && h.reloc_heavy) heavy = true;
+            }
+            if (!running) break;
+            if (!heavy) return fail(ctx, MCRAT_B200_ERR_STATE, "frame_loop_kernel returned with running shards");
+            // many photons change cell per iteration (optically thin flow): K1b / K1c serve that better
+            for (int b = 0; b < 32; ++b)
+                if (int rc = streamed_iteration()) return rc;
+            if (int rc = reset_protocol(ctx)) return rc;
+            (void)launched;
+        }
+    } else {
+        // iterations are enqueued in batches; kernels of a shard past its stop condition return at once
+        int batch = 1;
+        long long launched = 0;
+        for (;;) {
+            for (int b = 0; b < batch; ++b) {
+                if (int rc = streamed_iteration()) return rc;
+                launched++;
+            }
+            if (int rc = fetch_global(ctx)) return rc;
+            const GlobalState &g = *ctx->gs_host;
+            if (g.error || g.n_stopped >= S) break;
+            if (batch < 64) batch *= 2;
+            if (max_iters >= 0 && launched + batch > max_iters) batch = (int)(max_iters - launched);
+            if (batch < 1) batch = 1;
+        }
     }
     if (int rc = fetch_state(ctx)) return rc;
     // aggregate over the sub-shards: counters add up, the clock reported is shard 0's

@@ -22,6 +22,7 @@ HYDRO_FIELDS = ["r0", "r1", "r2", "r0_size", "r1_size", "r2_size", "r", "theta",
 
 ABI_VERSION = 1
 RNG_PHILOX, RNG_REPLAY = 0, 1
+LOOP_MODES = {"auto": 0, "streamed": 1, "persistent": 2}
 
 ERRORS = {-1: "ERR_CUDA", -2: "ERR_ARG", -3: "ERR_STATE", -4: "ERR_REPLAY", -5: "ERR_TABLE"}
 
@@ -68,7 +69,7 @@ EXPORTS = [
     "mcrat_b200_set_replay_uniforms", "mcrat_b200_replay_consumed", "mcrat_b200_find_containing_hydro_cell",
     "mcrat_b200_calc_mean_free_path", "mcrat_b200_photon_event", "mcrat_b200_update_photon_position",
     "mcrat_b200_ph_abs_cyclosynch", "mcrat_b200_calc_cyclosynch_r_limits", "mcrat_b200_set_cs_limits", "mcrat_b200_ph_min_max", "mcrat_b200_ph_scatt_stats",
-    "mcrat_b200_average_photon_energy", "mcrat_b200_run_frame", "mcrat_b200_get_kernel_times",
+    "mcrat_b200_average_photon_energy", "mcrat_b200_run_frame", "mcrat_b200_set_loop_mode", "mcrat_b200_get_kernel_times",
     "mcrat_b200_launch_count", "mcrat_b200_rescan_all", "mcrat_b200_measure_fp64_peak", "mcrat_b200_measure_hbm_peak",
 ]
 
@@ -122,7 +123,7 @@ class HotPath:
     """
 
     def __init__(self, cfg, device=0, rng_mode=RNG_PHILOX, seed=0, shard=0, profile=False, stream=None,
-                 num_shards=1, scan_index=False):
+                 num_shards=1, scan_index=False, loop_mode=None):
         self.L = load()
         c = Config(ABI_VERSION, cfg["dimensions"], cfg["geometry"], cfg["stokes"], cfg["tau_calculation"],
                    cfg["cyclosynch"], cfg["b_field_calc"], cfg["epsilon_b"], device, rng_mode, seed, shard,
@@ -135,6 +136,8 @@ class HotPath:
         self._keep = []
         if num_shards != 1:
             self.set_num_shards(num_shards)
+        if loop_mode is not None:
+            self.set_loop_mode(loop_mode)
 
     def close(self):
         if getattr(self, "ctx", None) is not None and self.ctx:
@@ -212,6 +215,10 @@ class HotPath:
 
     def num_shards(self):
         return int(self.L.mcrat_b200_num_shards(self.ctx))
+
+    def set_loop_mode(self, mode):
+        """'auto' | 'streamed' (four launches per iteration) | 'persistent' (one cooperative launch per frame)."""
+        self._ck(self.L.mcrat_b200_set_loop_mode(self.ctx, C.c_int(LOOP_MODES[mode] if isinstance(mode, str) else mode)))
 
     def shard_stats(self, shard):
         st, first, count = FrameStats(), C.c_int(0), C.c_int(0)

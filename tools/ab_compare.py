@@ -2,7 +2,7 @@
 """A/B harness: run the same frames through two builds of the library (MCRAT_B200_LIB) and compare
 the photon lists bit for bit, plus the loop time per iteration.
 
-  python tools/ab_compare.py libA.so libB.so [workload] [photons] [shards] [iters]
+  python tools/ab_compare.py libA.so[:loop_mode] libB.so[:loop_mode] [workload] [photons] [shards] [iters] [scale]
 """
 import os
 import subprocess
@@ -17,7 +17,8 @@ def child(out, wl, nph, shards, iters, scale):
     import numpy as np
     from mcrat_b200 import HotPath, synth
     cfg, hydro, photons, frame = synth.workload(wl, scale=scale, n_photons=nph, seed=5)
-    hp = HotPath(cfg, seed=99, num_shards=shards, scan_index=True)
+    mode = os.environ.get("MCRAT_LOOP_MODE")
+    hp = HotPath(cfg, seed=99, num_shards=shards, scan_index=True, loop_mode=mode or None)
     hp.set_hydro(hydro)
     hp.set_photons(photons)
     st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=50, switch=1)
@@ -27,8 +28,8 @@ def child(out, wl, nph, shards, iters, scale):
     hp.synchronize()
     dt = time.perf_counter() - t0
     np.save(out, hp.get_photons())
-    print("%s: %d iterations %d scatterings  %.2f us/iteration  %.3e scatterings/s  launches %d" %
-          (os.environ.get("MCRAT_B200_LIB", "default"), st2["iterations"], st2["scatterings"],
+    print("%s[%s]: %d iterations %d scatterings  %.2f us/iteration  %.3e scatterings/s  launches %d" %
+          (os.path.basename(os.environ.get("MCRAT_B200_LIB", "default")), os.environ.get("MCRAT_LOOP_MODE", "-"), st2["iterations"], st2["scatterings"],
            1e6 * dt / max(st2["iterations"], 1), st2["scatterings"] / dt, hp.launch_count()), flush=True)
 
 
@@ -46,7 +47,10 @@ if __name__ == "__main__":
     outs = []
     for k, lib in enumerate(libs):
         out = "/tmp/ab_%d.npy" % k
+        lib, _, mode = lib.partition(":")
         env = dict(os.environ, MCRAT_B200_LIB=os.path.abspath(lib))
+        if mode:
+            env["MCRAT_LOOP_MODE"] = mode
         subprocess.check_call([sys.executable, os.path.abspath(__file__), "--child", out, wl, nph, shards, iters, scale], env=env)
         outs.append(np.load(out))
     a, b = outs
