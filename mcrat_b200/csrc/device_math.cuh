@@ -76,9 +76,14 @@ struct EventRng {
     const double *buf;
     unsigned long long pos, n;
     int exhausted;
+    // first `npre` uniforms of this event's Philox stream, evaluated lane-parallel up front
+    // (same counters, same values; only the latency moves off the scattering lane)
+    const double *pre;
+    int npre;
 
     __device__ double uniform()
     {
+        if (!replay && draw < (uint64_t)npre) return pre[draw++];
         if (replay) {
             if (pos >= n) {
                 exhausted = 1;
@@ -261,6 +266,49 @@ __device__ inline void zero_norm(double *p)
         p[1] = (p[1] / nrm) * p[0];
         p[2] = (p[2] / nrm) * p[0];
         p[3] = (p[3] / nrm) * p[0];
+    }
+}
+
+// lorentzBoost in two halves: the matrix depends on the velocity only, so the event kernel builds
+// it on a helper warp while the scattering lane is still busy (Src/mclib.c:311-347 / :348-405)
+struct BoostMat {
+    double L[16];
+    int moving; // beta > 0
+};
+
+__device__ inline void boost_matrix(const double *b, BoostMat &M)
+{
+    double beta = dnrm2_3(b);
+    M.moving = (beta > 0) ? 1 : 0;
+    if (beta > 0) {
+        double gamma = 1.0 / sqrt(1 - beta * beta);
+        double *L = M.L;
+        double bb = beta * beta;
+        L[0] = gamma;
+        L[1] = -1 * b[0] * gamma;
+        L[2] = -1 * b[1] * gamma;
+        L[3] = -1 * b[2] * gamma;
+        L[5] = 1 + ((gamma - 1) * (b[0] * b[0]) / bb);
+        L[6] = ((gamma - 1) * (b[0] * b[1] / bb));
+        L[7] = ((gamma - 1) * (b[0] * b[2] / bb));
+        L[10] = 1 + ((gamma - 1) * (b[1] * b[1]) / bb);
+        L[11] = ((gamma - 1) * (b[1] * b[2]) / bb);
+        L[15] = 1 + ((gamma - 1) * (b[2] * b[2]) / bb);
+        L[4] = L[1]; L[8] = L[2]; L[12] = L[3];
+        L[9] = L[6]; L[13] = L[7]; L[14] = L[11];
+    }
+}
+
+__device__ inline void boost_apply(const BoostMat &M, double *p_in, double *result, bool photon)
+{
+    if (M.moving) {
+        double pp[4];
+        dgemv<4>(M.L, p_in, pp);
+        if (photon) zero_norm(pp);
+        result[0] = pp[0]; result[1] = pp[1]; result[2] = pp[2]; result[3] = pp[3];
+    } else {
+        if (photon) zero_norm(p_in);
+        result[0] = p_in[0]; result[1] = p_in[1]; result[2] = p_in[2]; result[3] = p_in[3];
     }
 }
 

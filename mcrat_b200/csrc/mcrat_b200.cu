@@ -121,7 +121,23 @@ struct GlobalState {
     int cs_scatt_num;          // scatt_cyclosynch_num_ph
     int cs_emitted;            // pool photons replaced on the device
     double cs_comptonized_w;   // n_comptonized
+#ifdef MCRAT_TIMING
+    long long dbg[32];         // SM-cycle accumulators of shard 0 (tools/loop_timing.py; not in the product build)
+#endif
 };
+
+#ifdef MCRAT_TIMING
+#define TSTAMP_DECL long long t_last__ = clock64()
+#define TSTAMP(gsref, k)                                 \
+    do {                                                 \
+        long long now__ = clock64();                     \
+        (gsref).dbg[k] += now__ - t_last__;              \
+        t_last__ = now__;                                \
+    } while (0)
+#else
+#define TSTAMP_DECL
+#define TSTAMP(gsref, k)
+#endif
 
 struct DevCtx {
     int dims, geom, stokes, tau_calc, cs, b_calc;
@@ -908,16 +924,26 @@ __global__ void __launch_bounds__(256) argmin_all_kernel(DevCtx d)
 // driver's bookkeeping (Src/mcrat.c:777-846).  One block per sub-shard; lane 0 runs the scatter.
 // ------------------------------------------------------------------------------------------
 constexpr int EVT_THREADS = 256;   // one shard / few shards: wide block for the list scans
-constexpr int EVT_THREADS_MANY = 64; // many sub-shards: two warps per event, 16 events resident per SM
+constexpr int EVT_THREADS_MANY = 128; // many sub-shards: the three event warps + one, 4 events resident per SM
 
-// Mailbox of the two-warp scattering event (shared memory).  Warp 0 = momentum chain (the only
-// consumer of random numbers), warp 1 = Stokes chain.  Every rotation angle of stokesRotation
-// (Src/mcrat_scattering.c:103-149) is a function of momenta only, so warp 1 evaluates them -- two
-// or three at a time, one per lane, same instruction stream -- while warp 0 is already working on
-// the next stage; the Stokes vector itself only enters warp 0 through (q, u) in the azimuth draw.
+// Mailbox of the three-warp scattering event (shared memory).
+//   warp 0 = the scattering lane: electron sampling, Klein-Nishina draws, the boosts -- the only
+//            consumer of random numbers and the critical path;
+//   warp 1 = Stokes chain: every rotation angle of stokesRotation (Src/mcrat_scattering.c:103-149)
+//            is a function of momenta only, so they are evaluated here, two to four at a time, one
+//            per lane on the same instruction stream; the Stokes vector itself enters warp 0 only
+//            through (q, u) in the azimuth draw;
+//   warp 2 = helper: everything that depends on velocities alone and would otherwise sit on the
+//            critical path -- the candidate's pushed position and fluid velocity, the Lorentz
+//            matrices of the boosts back (lorentzBoost's matrix depends on beta only), the
+//            alignment rotation and the Fano matrix.
+// Each piece is the reference's statement block, operation for operation: results are
+// bit-identical to the single-lane scatter_candidate below.
 struct ScatterMail {
+    double pre[64];         // first 64 uniforms of the event's Philox stream
     double zhat[3];
     double fb[3], nfb[3];   // fluid velocity (Src/mclib.c:1151-1174) and its negative
+    double r[3];            // candidate position after this event's pushes
     double p[4];            // lab 4-momentum of the candidate
     double pc[4];           // fluid-frame 4-momentum (photon.comv_p*)
     double pcb[4];          // the same after lorentzBoost had it as input (renormalised in place if beta = 0)
@@ -930,12 +956,18 @@ struct ScatterMail {
     double p_new[4];        // lab frame, after
     double fano[5];
     double q, u;
+    BoostMat Lf, Le;        // boosts by -fluid_beta and by -el_v
+    ScatterRot rot;
     int occurred;
+    unsigned char flags;
 };
 
-__device__ __forceinline__ void pair_bar() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+constexpr int SCATTER_THREADS = 96; // warps 0..2 of the event block
 
-// up to three Stokes angles at once, one per lane; returns sin/cos(2 phi) of this lane's angle
+__device__ __forceinline__ void trio_bar() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
+__device__ __forceinline__ void duo_bar() { asm volatile("bar.sync 2, 64;" ::: "memory"); } // warps 1 and 2
+
+// up to four Stokes angles at once, one per lane; returns sin/cos(2 phi) of this lane's angle
 __device__ __forceinline__ void lane_angle(const double *k1, const double *a, const double *k2, const double *b, bool active,
                                            double &sn, double &cs)
 {
@@ -953,54 +985,46 @@ __device__ __forceinline__ void rot_from_lane(double sn, double cs, int src, dou
     muller_rotation_sc(a, c, s);
 }
 
-// photonEvent's body for one candidate (Src/mclib.c:1138-1333) on two warps (threads 0..63 of the
-// block call this together; STOKES_SWITCH ON).  Results are bit-identical to scatter_candidate.
-__device__ void scatter_candidate_2w(DevCtx &d, ShardState &st, EventRng &rng_sh, ScatterMail &m, int i, int n_dt,
+// photonEvent's body for one candidate (Src/mclib.c:1138-1333); threads 0..95 of the block call
+// this together (STOKES_SWITCH ON).
+__device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh, ScatterMail &m, int i, int n_dt,
                                      int *event_did_occur)
 {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // warp-0 lane-0 state carried across stages
-    unsigned char flags = 0;
-    double r0 = 0, r1 = 0, r2 = 0, theta = 0;
-    CellState c;
+    double theta = 0;
     KnTheta kn;
-    ScatterRot rot;
     EventRng rng;
     double s[4] = {0, 0, 0, 0}; // warp 1, replicated in its lanes
     double sn = 0, cs = 1;
+#ifdef MCRAT_TIMING
+    const bool tm__ = (w == 0 && lane == 0 && st.first == 0);
+    GlobalState &gsr__ = *d.gs;
+#define T2W(k) if (tm__) TSTAMP(gsr__, k)
+#else
+#define T2W(k)
+#endif
+    TSTAMP_DECL;
 
-    // ---- stage A: candidate position after this event's pushes, fluid velocity ----
+    // ---- stage A/B: electron + boost into its rest frame | position, fluid velocity, lab -> fluid rotation ----
     if (w == 0) {
-        if (lane == 0) {
-            rng = rng_sh;
-            flags = d.ph.flags[i];
-            double p[4] = {d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i]};
-            r0 = d.ph.r0[i]; r1 = d.ph.r1[i]; r2 = d.ph.r2[i];
-            if (flags & F_MOVABLE) apply_pushes(st, n_dt, p[0], p[1], p[2], p[3], r0, r1, r2);
-            c = load_cell_state(d.cells, d.ph.idx[i]);
-            double fb[3];
-            fluid_beta_of(d, c, r0, r1, fb);
-            m.zhat[0] = 0; m.zhat[1] = 0; m.zhat[2] = 1;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                m.fb[k] = fb[k];
-                m.nfb[k] = -1 * fb[k];
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) m.p[k] = p[k];
-            m.pc[0] = d.ph.c0[i]; m.pc[1] = d.ph.c1[i]; m.pc[2] = d.ph.c2[i]; m.pc[3] = d.ph.c3[i];
+        if (!rng_sh.replay) {
+            double a, b;
+            philox_doubles((uint32_t)lane, (uint32_t)rng_sh.iter, (uint32_t)(rng_sh.iter >> 32), 1u, rng_sh.k0, rng_sh.k1, a, b);
+            m.pre[2 * lane] = a;
+            m.pre[2 * lane + 1] = b;
         }
         __syncwarp();
-    } else {
-        s[0] = d.ph.s0[i]; s[1] = d.ph.s1[i]; s[2] = d.ph.s2[i]; s[3] = d.ph.s3[i];
-    }
-    pair_bar();
-    // ---- stage B: electron + boost into its rest frame | lab -> fluid Stokes rotation ----
-    if (w == 0) {
         if (lane == 0) {
-            double pc[4] = {m.pc[0], m.pc[1], m.pc[2], m.pc[3]};
+            rng = rng_sh;
+            rng.pre = m.pre;
+            rng.npre = rng_sh.replay ? 0 : 64;
+            const double temp = d.cells.temp[d.ph.idx[i]];
+            double pc[4] = {d.ph.c0[i], d.ph.c1[i], d.ph.c2[i], d.ph.c3[i]};
+            T2W(8);
             double el[4], el_v[3], php[4];
-            single_thermal_electron(el, c.temp, pc, rng);
+            single_thermal_electron(el, temp, pc, rng);
+            T2W(9);
             scatter_stage_boost(el, pc, el_v, php);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -1014,23 +1038,51 @@ __device__ void scatter_candidate_2w(DevCtx &d, ShardState &st, EventRng &rng_sh
             }
         }
         __syncwarp();
+    } else if (w == 2) {
+        if (lane == 0) {
+            const unsigned char flags = d.ph.flags[i];
+            double p[4] = {d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i]};
+            double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
+            if (flags & F_MOVABLE) apply_pushes(st, n_dt, p[0], p[1], p[2], p[3], r0, r1, r2);
+            CellState c = load_cell_state(d.cells, d.ph.idx[i]);
+            double fb[3];
+            fluid_beta_of(d, c, r0, r1, fb);
+            m.zhat[0] = 0; m.zhat[1] = 0; m.zhat[2] = 1;
+            m.r[0] = r0; m.r[1] = r1; m.r[2] = r2;
+            m.flags = flags;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                m.fb[k] = fb[k];
+                m.nfb[k] = -1 * fb[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) m.p[k] = p[k];
+            m.pc[0] = d.ph.c0[i]; m.pc[1] = d.ph.c1[i]; m.pc[2] = d.ph.c2[i]; m.pc[3] = d.ph.c3[i];
+        }
+        __syncwarp();
+        duo_bar();
+        if (lane == 0) {
+            double nfb[3] = {m.nfb[0], m.nfb[1], m.nfb[2]};
+            boost_matrix(nfb, m.Lf);
+        }
+        __syncwarp();
     } else {
+        s[0] = d.ph.s0[i]; s[1] = d.ph.s1[i]; s[2] = d.ph.s2[i]; s[3] = d.ph.s3[i];
+        duo_bar();
         // stokesRotation(fluid_beta, p, comv_p), Src/mclib.c:1190-1196
         lane_angle(lane == 0 ? m.p + 1 : m.pc + 1, lane == 0 ? m.zhat : m.fb, lane == 0 ? m.p + 1 : m.pc + 1,
                    lane == 0 ? m.fb : m.zhat, lane < 2, sn, cs);
         rot_from_lane(sn, cs, 0, s);
         rot_from_lane(sn, cs, 1, s);
     }
-    pair_bar();
-    // ---- stage C: align + Klein-Nishina accept / polar angle | fluid -> electron-frame rotation ----
+    T2W(10);
+    trio_bar();
+    T2W(11);
+    // ---- stage C: Klein-Nishina accept / polar angle | fluid -> electron-frame rotation | alignment, boost matrix ----
     if (w == 0) {
-        if (lane == 0) {
-            double php[4] = {m.php[0], m.php[1], m.php[2], m.php[3]};
-            scatter_stage_align(php, rot);
-            m.occurred = kn_accept_theta(theta, php[0], kn, rng);
-        }
+        if (lane == 0) m.occurred = kn_accept_theta(theta, m.php[0], kn, rng);
         __syncwarp();
-    } else {
+    } else if (w == 1) {
         // stokesRotation(el_v, ph_comov, ph_p_prime), Src/mcrat_scattering.c:245-253
         lane_angle(lane == 0 ? m.pcb + 1 : m.php + 1, lane == 0 ? m.zhat : m.el_v, lane == 0 ? m.pcb + 1 : m.php + 1,
                    lane == 0 ? m.el_v : m.zhat, lane < 2, sn, cs);
@@ -1040,10 +1092,26 @@ __device__ void scatter_candidate_2w(DevCtx &d, ShardState &st, EventRng &rng_sh
             m.q = s[1];
             m.u = s[2];
         }
+    } else {
+        if (lane == 0) {
+            double php[4] = {m.php[0], m.php[1], m.php[2], m.php[3]};
+            ScatterRot rot;
+            scatter_stage_align(php, rot);
+            m.rot = rot;
+            double nel_v[3] = {m.nel_v[0], m.nel_v[1], m.nel_v[2]};
+            boost_matrix(nel_v, m.Le);
+        }
+        __syncwarp();
     }
-    pair_bar();
+    T2W(12);
+    trio_bar();
+    T2W(13);
     if (!m.occurred) { // Klein-Nishina rejection: the draws are spent, nothing else changes
-        if (w == 0 && lane == 0) rng_sh = rng;
+        if (w == 0 && lane == 0) {
+            rng.pre = nullptr;
+            rng.npre = 0;
+            rng_sh = rng;
+        }
         return;
     }
     // ---- stage D: azimuth + outgoing photon ----
@@ -1051,27 +1119,28 @@ __device__ void scatter_candidate_2w(DevCtx &d, ShardState &st, EventRng &rng_sh
         if (lane == 0) {
             double phi = kn_phi(1, kn, m.q, m.u, rng);
             double out[4];
+            ScatterRot rot = m.rot;
             scatter_stage_out(m.php[0], theta, phi, rot, out);
 #pragma unroll
             for (int k = 0; k < 4; ++k) m.out[k] = out[k];
         }
         __syncwarp();
     }
-    pair_bar();
-    // ---- stage E: boosts back to the fluid and lab frames | scattering-plane angles ----
+    T2W(14);
+    trio_bar();
+    T2W(15);
+    // ---- stage E: boosts back to the fluid and lab frames | scattering-plane angles | Fano matrix ----
     if (w == 0) {
         if (lane == 0) {
             double out[4] = {m.out[0], m.out[1], m.out[2], m.out[3]};
-            double nel_v[3] = {m.nel_v[0], m.nel_v[1], m.nel_v[2]};
-            double nfb[3] = {m.nfb[0], m.nfb[1], m.nfb[2]};
             double pcn[4], pn[4];
-            lorentz_boost(nel_v, out, pcn, true); // Src/mcrat_scattering.c:455-463
+            boost_apply(m.Le, out, pcn, true); // Src/mcrat_scattering.c:455-463
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 m.outb[k] = out[k];
                 m.pc_new[k] = pcn[k];
             }
-            lorentz_boost(nfb, pcn, pn, true); // Src/mclib.c:1262-1265
+            boost_apply(m.Lf, pcn, pn, true); // Src/mclib.c:1262-1265
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 m.pc_fin[k] = pcn[k];
@@ -1079,15 +1148,11 @@ __device__ void scatter_candidate_2w(DevCtx &d, ShardState &st, EventRng &rng_sh
             }
         }
         __syncwarp();
-    } else {
+    } else if (w == 1) {
         // lane 0: into the scattering plane (Src/mcrat_scattering.c:402-405); lane 1: back out of it (:438-447)
         lane_angle(lane == 0 ? m.php + 1 : m.out + 1, lane == 0 ? m.zhat : m.php + 1, m.out + 1,
                    lane == 0 ? m.php + 1 : m.zhat, lane < 2, sn, cs);
-    }
-    pair_bar();
-    // ---- stage F: Fano matrix | remaining angles ----
-    double sn2 = 0, cs2 = 1;
-    if (w == 0) {
+    } else {
         if (lane == 0) {
             double f[5];
             scatter_stage_fano(m.php, m.out, f);
@@ -1095,16 +1160,19 @@ __device__ void scatter_candidate_2w(DevCtx &d, ShardState &st, EventRng &rng_sh
             for (int k = 0; k < 5; ++k) m.fano[k] = f[k];
         }
         __syncwarp();
-    } else {
-        // lane 0: stokesRotation(-el_v, out, pc_new) first half uses `out` as lorentzBoost left it;
-        // lane 1: its second half; lane 2 / 3: stokesRotation(-fluid_beta, pc_fin, p_new), Src/mclib.c:1267-1287
+    }
+    T2W(16);
+    trio_bar();
+    T2W(17);
+    // ---- stage F: the remaining angles, the Stokes chain applied in order, write-back ----
+    if (w == 1) {
+        // lane 0 / 1: stokesRotation(-el_v, out, pc_new), Src/mcrat_scattering.c:465-473 (`out` as lorentzBoost
+        // left it); lane 2 / 3: stokesRotation(-fluid_beta, pc_fin, p_new), Src/mclib.c:1267-1287
+        double sn2, cs2;
         const double *k = lane == 0 ? m.outb + 1 : (lane == 1 ? m.pc_new + 1 : (lane == 2 ? m.pc_fin + 1 : m.p_new + 1));
         const double *a = lane == 0 ? m.zhat : (lane == 1 ? m.nel_v : (lane == 2 ? m.zhat : m.nfb));
         const double *b = lane == 0 ? m.nel_v : (lane == 1 ? m.zhat : (lane == 2 ? m.nfb : m.zhat));
         lane_angle(k, a, k, b, lane < 4, sn2, cs2);
-    }
-    pair_bar();
-    if (w == 1) {
         rot_from_lane(sn, cs, 0, s);
         {
             double f[5] = {m.fano[0], m.fano[1], m.fano[2], m.fano[3], m.fano[4]};
@@ -1121,18 +1189,22 @@ __device__ void scatter_candidate_2w(DevCtx &d, ShardState &st, EventRng &rng_sh
             d.ph.s2[i] = s[2];
             d.ph.s3[i] = s[3];
         }
-    } else if (lane == 0) {
+    } else if (w == 0 && lane == 0) {
         d.ph.p0[i] = m.p_new[0]; d.ph.p1[i] = m.p_new[1]; d.ph.p2[i] = m.p_new[2]; d.ph.p3[i] = m.p_new[3];
         d.ph.c0[i] = m.pc_fin[0]; d.ph.c1[i] = m.pc_fin[1]; d.ph.c2[i] = m.pc_fin[2]; d.ph.c3[i] = m.pc_fin[3];
         d.ph.nscatt[i] = d.ph.nscatt[i] + 1;
-        d.ph.flags[i] = flags | F_RECALC;
-        d.ph.r0[i] = r0;
-        d.ph.r1[i] = r1;
-        d.ph.r2[i] = r2;
+        d.ph.flags[i] = m.flags | F_RECALC;
+        // this photon is already at its pushed position: the next pass must not push it again
+        d.ph.r0[i] = m.r[0];
+        d.ph.r1[i] = m.r[1];
+        d.ph.r2[i] = m.r[2];
         st.pushed_slot = i;
         st.scatt_cnt += 1;
         *event_did_occur = 1;
+        rng.pre = nullptr;
+        rng.npre = 0;
         rng_sh = rng;
+        T2W(18);
     }
 }
 
@@ -1344,6 +1416,8 @@ __device__ __forceinline__ void event_body(DevCtx &d, const int s, const int rel
         rng_sh.pos = gs.replay_cursor;
         rng_sh.n = gs.replay_n;
         rng_sh.exhausted = 0;
+        rng_sh.pre = nullptr;
+        rng_sh.npre = 0;
         if (step_mode == 0) st.slots += st.count;
         if (step_mode == 0 && !(bt < dt_max)) {
             // Src/mcrat.c:834-846: nothing scatters before the next hydro frame
@@ -1395,8 +1469,8 @@ __device__ __forceinline__ void event_body(DevCtx &d, const int s, const int rel
         __syncthreads();
         if (sh_try) {
             if (d.stokes) {
-                // two warps: momentum chain | Stokes chain
-                if (threadIdx.x < 64) scatter_candidate_2w(d, st, rng_sh, mail, sh_cand_i, n_dt, &sh_event);
+                // three warps: scattering lane | Stokes chain | helper
+                if (threadIdx.x < SCATTER_THREADS) scatter_candidate_3w(d, st, rng_sh, mail, sh_cand_i, n_dt, &sh_event);
             } else if (threadIdx.x == 0) {
                 EventRng rng = rng_sh;
                 bool event = false;
@@ -1570,7 +1644,7 @@ __device__ __forceinline__ void relocate_shard(DevCtx &d, ShardState &st, const 
 }
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 8) frame_loop_kernel(DevCtx d, const int bps)
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_kernel(DevCtx d, const int bps)
 {
     __shared__ int sh_last, sh_halt;
     GlobalState &gs = *d.gs;
@@ -1630,8 +1704,16 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 8) frame_loop_ke
             }
             __syncthreads();
         };
+#ifdef MCRAT_TIMING
+        const bool tm__ = (threadIdx.x == 0 && s == 0);
+#define TLOOP(k) if (tm__) TSTAMP(gs, k)
+#else
+#define TLOOP(k)
+#endif
+        TSTAMP_DECL;
         while (!halt) {
             // ---- pass ----
+            TLOOP(0);
             double best_t = DBL_MAX;
             int best_i = INT_MAX;
             pass_body<true, true, THREADS>(d, s, b, bps, 0, 0, best_t, best_i);
@@ -1640,13 +1722,22 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 8) frame_loop_ke
                 d.bm_t[s * bps + b] = best_t;
                 d.bm_i[s * bps + b] = best_i;
             }
+            TLOOP(1); // pass + block arg-min
             if (arrive()) {
+                TLOOP(2); // waiting for the other blocks of the shard
                 const int R = *(volatile int *)&st.reloc_n;
                 if (R > 0) relocate_shard<THREADS>(d, st, R);
+                TLOOP(3); // re-location
                 event_body<THREADS>(d, s, st.first, R, bps, 0, 0.0);
+                TLOOP(4); // event
                 publish();
+                TLOOP(5);
+#ifdef MCRAT_TIMING
+                if (tm__) gs.dbg[7] += 1;
+#endif
             } else {
                 wait();
+                TLOOP(6); // spinning on the generation word
             }
             halt = sh_halt != 0;
             __syncthreads();
@@ -1909,7 +2000,7 @@ struct mcrat_b200_ctx {
     int last_nb_mfp;
     int want_shards;    // sub-shards requested for the next set_photons
     int loop_mode;      // MCRAT_B200_LOOP_AUTO / _STREAMED / _PERSISTENT
-    int occ_loop256, occ_loop64; // resident blocks per SM of frame_loop_kernel<256> / <64>
+    int occ_loop256, occ_loop128; // resident blocks per SM of frame_loop_kernel<256> / <128>
     long long launches; // kernels launched through this context
     GlobalState *gs_host;          // pinned
     std::vector<ShardState> sh_host;
@@ -2041,7 +2132,7 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
     ctx->last_nb_mfp = 0;
     ctx->want_shards = 1;
     ctx->loop_mode = MCRAT_B200_LOOP_AUTO;
-    ctx->occ_loop256 = ctx->occ_loop64 = 0;
+    ctx->occ_loop256 = ctx->occ_loop128 = 0;
     ctx->launches = 0;
     ctx->replay_dev = nullptr;
     ctx->replay_cap = 0;
@@ -2117,7 +2208,7 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
         return bail(e, "cudaFuncSetAttribute");
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_loop256, frame_loop_kernel<256>, 256, 0)) != cudaSuccess)
         return bail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_loop64, frame_loop_kernel<64>, 64, 0)) != cudaSuccess)
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_loop128, frame_loop_kernel<128>, 128, 0)) != cudaSuccess)
         return bail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     *out = ctx;
     return MCRAT_B200_OK;
@@ -2745,11 +2836,11 @@ static void frame_loop_grid(const mcrat_b200_ctx *ctx, int &threads, int &bps, i
     const int S = ctx->d.nshards;
     const int cap256 = ctx->num_sms * ctx->occ_loop256;
     if (S > cap256) {
-        // more shards than wide blocks fit: two-warp blocks (pass + two-warp event), a block walks
+        // more shards than wide blocks fit: four-warp blocks (pass + three-warp event), a block walks
         // through its shards one after the other if there are more shards than resident blocks
-        threads = 64;
+        threads = 128;
         bps = 1;
-        const int cap = ctx->num_sms * ctx->occ_loop64;
+        const int cap = ctx->num_sms * ctx->occ_loop128;
         grid = S < cap ? S : cap;
     } else {
         threads = 256;
@@ -2769,8 +2860,8 @@ static int launch_frame_loop(mcrat_b200_ctx *ctx)
     void *args[2] = {(void *)&ctx->d, (void *)&bps};
     Timed t(ctx, KC_EVENT);
     cudaError_t e;
-    if (threads == 64)
-        e = cudaLaunchCooperativeKernel((const void *)frame_loop_kernel<64>, dim3(grid), dim3(64), args, 0, ctx->stream);
+    if (threads == 128)
+        e = cudaLaunchCooperativeKernel((const void *)frame_loop_kernel<128>, dim3(grid), dim3(128), args, 0, ctx->stream);
     else
         e = cudaLaunchCooperativeKernel((const void *)frame_loop_kernel<256>, dim3(grid), dim3(256), args, 0, ctx->stream);
     if (e != cudaSuccess) {
@@ -2956,6 +3047,20 @@ API int mcrat_b200_get_kernel_times(mcrat_b200_ctx *ctx, mcrat_b200_kernel_times
     if (reset) memset(&ctx->times, 0, sizeof(ctx->times));
     return MCRAT_B200_OK;
 }
+
+#ifdef MCRAT_TIMING
+API int mcrat_b200_debug_counters(mcrat_b200_ctx *ctx, long long *out32, int reset)
+{
+    if (int rc = fetch_global(ctx)) return rc;
+    memcpy(out32, ctx->gs_host->dbg, sizeof(long long) * 32);
+    if (reset) {
+        memset(ctx->gs_host->dbg, 0, sizeof(long long) * 32);
+        CK(cudaMemcpyAsync(ctx->d.gs, ctx->gs_host, sizeof(GlobalState), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return MCRAT_B200_OK;
+}
+#endif
 
 API long long mcrat_b200_launch_count(const mcrat_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 

@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""Where one iteration of the persistent loop spends its time (SM cycles, shard 0): needs the
+instrumented build  make -C mcrat_b200/csrc libmcrat_b200_timing.so
+
+  python tools/loop_timing.py [workload] [photons] [shards] [iters]
+"""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ["MCRAT_B200_LIB"] = os.path.join(ROOT, "mcrat_b200", "csrc", "libmcrat_b200_timing.so")
+from mcrat_b200 import HotPath, synth  # noqa: E402
+
+wl = sys.argv[1] if len(sys.argv) > 1 else "C2"
+nph = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
+shards = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+iters = int(sys.argv[4]) if len(sys.argv) > 4 else 2000
+cfg, hydro, photons, frame = synth.workload(wl, n_photons=nph, seed=5)
+hp = HotPath(cfg, seed=99, num_shards=shards, scan_index=True, loop_mode="persistent")
+hp.set_hydro(hydro)
+hp.set_photons(photons)
+st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=50, switch=1)
+buf = (C.c_longlong * 32)()
+hp.L.mcrat_b200_debug_counters(hp.ctx, buf, 1)
+st = hp.run_frame(st["time_now"], 1.0 / frame["fps"], max_iters=iters, switch=0)
+hp.L.mcrat_b200_debug_counters(hp.ctx, buf, 0)
+n = max(buf[7], 1)
+names = {0: "loop top", 1: "pass + block arg-min", 2: "arrive (last block)", 3: "re-location", 4: "event (all)", 5: "publish",
+         6: "spin (not last)", 8: "3w A: loads (idx, temp, comv p)", 9: "3w B1: electron", 10: "3w B2: boost to e- frame",
+         11: "3w wait", 12: "3w C: KN accept/theta", 13: "3w wait (Stokes q,u; alignment)", 14: "3w D: azimuth + outgoing",
+         15: "3w wait", 16: "3w E: boosts back", 17: "3w wait (angles, Fano)", 18: "3w write-back"}
+print("%s %d photons %d shards: %d events of shard 0 seen by the stamping thread" % (wl, nph, shards, buf[7]))
+for k in sorted(names):
+    print("  %-34s %9.0f cycles / iteration  (%.2f us at 1.965 GHz)" % (names[k], buf[k] / n, buf[k] / n / 1965.0))
