@@ -617,7 +617,7 @@ __device__ inline void stokes_rotation(const double *v, const double *v_ph, cons
 // Src/mcrat_scattering.c:509-595 kleinNishinaScatter.  The reference's pow(m, -1/-2/-3) are written
 // as reciprocals of products (<= 2 ulp apart; pow is several hundred instructions in FP64).
 struct KnTheta {
-    double er, st, imu2, f_theta;
+    double er, st, ct, imu2, f_theta; // st, ct = sin / cos of the polar angle
 };
 
 // first half: accept / reject and the polar angle (Src/mcrat_scattering.c:519-553)
@@ -641,6 +641,7 @@ __device__ inline int kn_accept_theta(double &theta, double p0, KnTheta &k, Even
     double imu2 = 1.0 / (mu * mu);
     k.er = er;
     k.st = st;
+    k.ct = ctheta;
     k.imu2 = imu2;
     k.f_theta = ((1.0 / mu) + (1.0 / (mu * mu * mu)) - imu2 * st * st) * st;
     return 1;
@@ -837,11 +838,11 @@ __device__ inline void scatter_stage_align(const double *php, ScatterRot &r)
 }
 
 // Src/mcrat_scattering.c:318-386: scattered photon in the electron rest frame, original axes
-__device__ inline void scatter_stage_out(double e_in, double theta, double phi, const ScatterRot &r, double *out)
+// (sth, cth) = sincos(theta) as kn_accept_theta already evaluated it
+__device__ inline void scatter_stage_out(double e_in, double sth, double cth, double phi, const ScatterRot &r, double *out)
 {
     double rot[9], result[4], v[3], result1[3], result0[3];
-    double sth, cth, sph, cph;
-    sincos(theta, &sth, &cth);
+    double sph, cph;
     sincos(phi, &sph, &cph);
     result[0] = (e_in) / (1 + (((e_in) * (1 - cth)) / (M_EL * C_LIGHT)));
     result[1] = result[0] * cth;
@@ -929,18 +930,26 @@ __device__ inline double sample_thermal_electron(double temp, EventRng &rng)
     return gamma;
 }
 
-// Src/electron.c:126-175 rotateElectron
-__device__ inline void rotate_electron(double *el_p, const double *ph_p)
+// Src/electron.c:126-175 rotateElectron; the two rotation angles depend on the photon only
+struct ElRot {
+    double stt, ctt, spm, cpm; // sin / cos of ph_theta and of -ph_phi
+};
+
+__device__ inline void electron_rot_angles(const double *ph_p, ElRot &r)
+{
+    double ph_phi = atan2(ph_p[2], ph_p[3]);
+    double ph_theta = atan2(sqrt(ph_p[2] * ph_p[2] + ph_p[3] * ph_p[3]), ph_p[1]);
+    sincos(ph_theta, &r.stt, &r.ctt);
+    sincos(-ph_phi, &r.spm, &r.cpm);
+}
+
+__device__ inline void rotate_electron_sc(double *el_p, const ElRot &r)
 {
     double rot[9], result[3];
     double *e = el_p + 1;
-    double ph_phi = atan2(ph_p[2], ph_p[3]);
-    double ph_theta = atan2(sqrt(ph_p[2] * ph_p[2] + ph_p[3] * ph_p[3]), ph_p[1]);
+    const double stt = r.stt, ctt = r.ctt, spm = r.spm, cpm = r.cpm;
 #pragma unroll
     for (int i = 0; i < 9; i++) rot[i] = 0;
-    double stt, ctt, spm, cpm;
-    sincos(ph_theta, &stt, &ctt);
-    sincos(-ph_phi, &spm, &cpm);
     rot[4] = 1;
     rot[8] = ctt;
     rot[0] = ctt;
@@ -957,6 +966,66 @@ __device__ inline void rotate_electron(double *el_p, const double *ph_p)
     double out[3];
     dgemv<3>(rot, result, out);
     e[0] = out[0]; e[1] = out[1]; e[2] = out[2];
+}
+
+__device__ inline void rotate_electron(double *el_p, const double *ph_p)
+{
+    ElRot r;
+    electron_rot_angles(ph_p, r);
+    rotate_electron_sc(el_p, r);
+}
+
+// the three polar Box-Muller samples of the Maxwellian branch (Src/electron.c:231-233) evaluated by a
+// whole warp: lane j works out candidate pair j of the prefetched Philox stream, the first three
+// accepted candidates are the three gaussians the sequential loop would have produced (a candidate
+// always costs exactly two draws: Philox doubles are never 0).  Returns the number of draws
+// consumed, or 0 if the window held fewer than three accepted pairs (caller falls back).
+__device__ inline int warp_gaussians3(const double *pre, int npre, uint64_t draw0, double sigma, double *g)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t k = draw0 + 2ull * (uint64_t)lane;
+    const bool valid = (k + 1 < (uint64_t)npre);
+    double x = 2, y = 2;
+    if (valid) {
+        x = -1 + 2 * pre[k];
+        y = -1 + 2 * pre[k + 1];
+    }
+    const double r2 = x * x + y * y;
+    const bool ok = valid && !(r2 > 1.0 || r2 == 0);
+    const double val = sigma * y * sqrt(-2.0 * log(ok ? r2 : 0.5) / (ok ? r2 : 0.5));
+    unsigned mask = __ballot_sync(0xffffffffu, ok);
+    if (__popc(mask) < 3) return 0;
+    int j = 0;
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+        j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        g[n] = __shfl_sync(0xffffffffu, val, j);
+    }
+    return 2 * (j + 1);
+}
+
+// gamma of a Maxwellian electron from its three velocity components, Src/electron.c:231-236
+__device__ inline double maxwellian_gamma(const double *g)
+{
+    double a = g[0] / C_LIGHT, b = g[1] / C_LIGHT, c = g[2] / C_LIGHT;
+    return 1.0 / sqrt(1 - (a * a + b * b + c * c));
+}
+
+// singleThermalElectron after the Lorentz factor is known: direction draws, 4-momentum, rotation
+__device__ inline void thermal_electron_from_gamma(double *el_p, double gamma, const ElRot &er, EventRng &rng)
+{
+    double beta = sqrt(1 - (1 / (gamma * gamma)));
+    double phi = rng.uniform() * 2 * PI;
+    double theta = acos((1 - sqrt(1 + beta * beta + 2 * beta - 4 * beta * rng.uniform())) / beta);
+    double sth, cth, sph, cph;
+    sincos(theta, &sth, &cth);
+    sincos(phi, &sph, &cph);
+    el_p[0] = gamma * (M_EL) * (C_LIGHT);
+    el_p[1] = gamma * (M_EL) * (C_LIGHT)*beta * cth;
+    el_p[2] = gamma * (M_EL) * (C_LIGHT)*beta * sth * sph;
+    el_p[3] = gamma * (M_EL) * (C_LIGHT)*beta * sth * cph;
+    rotate_electron_sc(el_p, er);
 }
 
 // Src/electron.c:70-94 singleThermalElectron (+ :177-200 sampleElectronTheta)

@@ -101,13 +101,18 @@ struct ShardState {
     int done, pause_cs, counted_stopped;
     int last_scattered_idx, head_idx; // global slot indices
     int first, count;                 // slot range
-    // persistent frame loop (frame_loop_kernel): inter-block protocol of the blocks that share this shard
-    unsigned int arrive;              // tickets drawn by blocks that finished a phase (monotonic)
-    unsigned int gen;                 // phases completed, published by the last arriver (monotonic)
+    int halt;                         // persistent loop: loop_stopped() as evaluated by the publishing block
+    int reloc_heavy;                  // the last iteration re-located many photons: better served by K1b / K1c
+    int pad0_;
+    // ---- everything above is the shard's state proper (the persistent loop keeps a shared-memory copy of it
+    // and writes it back once per iteration); below: words other blocks update with atomics, never copied ----
+    unsigned int arrive;              // tickets drawn by blocks that finished their pass (monotonic)
+    unsigned int gen;                 // iterations completed, published by the last arriver (monotonic)
     int reloc_n;                      // entries of this shard's region of the relocation list
-    int halt;                         // loop_stopped() as evaluated by the publishing block
-    int reloc_heavy;                  // the last iteration re-located many photons: better served by K1/K1b
+    int pad_;
 };
+constexpr int SHARD_STATE_WORDS = offsetof(ShardState, arrive) / 8; // 8-byte words of the copied part
+static_assert(offsetof(ShardState, arrive) % 8 == 0, "ShardState: copied part must be a whole number of 8-byte words");
 
 struct GlobalState {
     int reloc_count[2];
@@ -350,10 +355,9 @@ constexpr int PASS_THREADS = 256;
 // K1/K1b/K1c + finish_kernel work off; true: to the shard's own region [first, first+count) of the
 // list (persistent loop: shards advance independently of each other).
 template <bool FUSE_MFP, bool LOCAL_RELOC, int THREADS>
-__device__ __forceinline__ void pass_body(DevCtx &d, const int s, const int b, const int nblk, const int sw, const int parity,
-                                          double &best_t, int &best_i)
+__device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const int s, const int b, const int nblk,
+                                          const int sw, const int parity, double &best_t, int &best_i)
 {
-    ShardState &sh = d.sh[s];
     const int n_dt = sh.n_dt;
     const int pushed = sh.pushed_slot;
     const unsigned long long iter = sh.iter;
@@ -397,7 +401,7 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const int s, const int b, c
                 if ((d.ph.c0[i]) + (d.ph.c1[i]) + (d.ph.c2[i]) + (d.ph.c3[i]) == 0) inb = false;
             }
             if (sw == 1 || !inb) {
-                int pos = LOCAL_RELOC ? first + atomicAdd(&sh.reloc_n, 1) : atomicAdd(&d.gs->reloc_count[parity], 1);
+                int pos = LOCAL_RELOC ? first + atomicAdd(&d.sh[s].reloc_n, 1) : atomicAdd(&d.gs->reloc_count[parity], 1);
                 d.reloc_slot[pos] = i;
                 d.reloc_h0[pos] = h0;
                 d.reloc_h1[pos] = h1;
@@ -438,7 +442,8 @@ __global__ void __launch_bounds__(PASS_THREADS, 4) pass_kernel(DevCtx d, int sw,
     if (blockIdx.x == 0 && threadIdx.x == 0) d.gs->reloc_count[parity ^ 1] = 0;
     double best_t = DBL_MAX;
     int best_i = INT_MAX;
-    if (!loop_stopped(*d.gs, d.sh[s])) pass_body<FUSE_MFP, false, PASS_THREADS>(d, s, b, d.blocks_per_shard, sw, parity, best_t, best_i);
+    if (!loop_stopped(*d.gs, d.sh[s]))
+        pass_body<FUSE_MFP, false, PASS_THREADS>(d, d.sh[s], s, b, d.blocks_per_shard, sw, parity, best_t, best_i);
     if (FUSE_MFP) {
         block_argmin<PASS_THREADS>(best_t, best_i);
         if (threadIdx.x == 0) {
@@ -774,10 +779,8 @@ constexpr int FIN_THREADS = 128;
 
 // one relocated photon: new cell (or -1), comoving 4-momentum, optical depth, free-path draw
 template <bool FUSE_MFP>
-__device__ __forceinline__ bool finish_one(DevCtx &d, const int i, const int b, const int sw)
+__device__ __forceinline__ bool finish_one(DevCtx &d, ShardState &sh, const int s, const int i, const int b, const int sw)
 {
-    const int s = shard_of(d, i);
-    ShardState &sh = d.sh[s];
     double t = 1e12 / C_LIGHT;
     bool missing = false;
     if (b == INT_MAX) {
@@ -819,7 +822,10 @@ __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(DevCtx d, int sw, i
     const int count = gs.reloc_count[parity];
     int missing = 0;
     for (int j = blockIdx.x * FIN_THREADS + threadIdx.x; j < count; j += gridDim.x * FIN_THREADS)
-        if (finish_one<FUSE_MFP>(d, d.reloc_slot[j], d.reloc_best[j], sw)) missing++;
+    {
+        const int i = d.reloc_slot[j], s = shard_of(d, i);
+        if (finish_one<FUSE_MFP>(d, d.sh[s], s, i, d.reloc_best[j], sw)) missing++;
+    }
     if (missing) atomicAdd(&d.gs->not_found, missing);
 }
 
@@ -958,6 +964,7 @@ struct ScatterMail {
     double q, u;
     BoostMat Lf, Le;        // boosts by -fluid_beta and by -el_v
     ScatterRot rot;
+    ElRot erot;             // rotateElectron's angles (functions of the comoving photon only)
     int occurred;
     unsigned char flags;
 };
@@ -966,6 +973,9 @@ constexpr int SCATTER_THREADS = 96; // warps 0..2 of the event block
 
 __device__ __forceinline__ void trio_bar() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
 __device__ __forceinline__ void duo_bar() { asm volatile("bar.sync 2, 64;" ::: "memory"); } // warps 1 and 2
+// warp 1 hands rotateElectron's angles to warp 0 without waiting for it
+__device__ __forceinline__ void erot_arrive() { asm volatile("bar.arrive 3, 64;" ::: "memory"); }
+__device__ __forceinline__ void erot_wait() { asm volatile("bar.sync 3, 64;" ::: "memory"); }
 
 // up to four Stokes angles at once, one per lane; returns sin/cos(2 phi) of this lane's angle
 __device__ __forceinline__ void lane_angle(const double *k1, const double *a, const double *k2, const double *b, bool active,
@@ -1015,15 +1025,31 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
             m.pre[2 * lane + 1] = b;
         }
         __syncwarp();
+        // Maxwellian branch: the three gaussians at once, one candidate pair per lane
+        double temp = 0;
+        if (lane == 0) temp = d.cells.temp[d.ph.idx[i]];
+        temp = __shfl_sync(0xffffffffu, temp, 0);
+        double g3[3] = {0, 0, 0};
+        int used = 0;
+        if (!rng_sh.replay && temp < 1e7) used = warp_gaussians3(m.pre, 64, rng_sh.draw, sqrt(K_B * temp / M_EL), g3);
+        double gamma = 1;
         if (lane == 0) {
             rng = rng_sh;
             rng.pre = m.pre;
             rng.npre = rng_sh.replay ? 0 : 64;
-            const double temp = d.cells.temp[d.ph.idx[i]];
-            double pc[4] = {d.ph.c0[i], d.ph.c1[i], d.ph.c2[i], d.ph.c3[i]};
             T2W(8);
+            if (used) {
+                rng.draw += (uint64_t)used;
+                gamma = maxwellian_gamma(g3);
+            } else {
+                gamma = sample_thermal_electron(temp, rng);
+            }
+        }
+        erot_wait(); // warp 1 has the rotation angles ready long before
+        if (lane == 0) {
+            double pc[4] = {d.ph.c0[i], d.ph.c1[i], d.ph.c2[i], d.ph.c3[i]};
             double el[4], el_v[3], php[4];
-            single_thermal_electron(el, temp, pc, rng);
+            thermal_electron_from_gamma(el, gamma, m.erot, rng);
             T2W(9);
             scatter_stage_boost(el, pc, el_v, php);
 #pragma unroll
@@ -1067,6 +1093,14 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
         }
         __syncwarp();
     } else {
+        if (lane == 0) {
+            double pc[4] = {d.ph.c0[i], d.ph.c1[i], d.ph.c2[i], d.ph.c3[i]};
+            ElRot er;
+            electron_rot_angles(pc, er);
+            m.erot = er;
+        }
+        __syncwarp();
+        erot_arrive();
         s[0] = d.ph.s0[i]; s[1] = d.ph.s1[i]; s[2] = d.ph.s2[i]; s[3] = d.ph.s3[i];
         duo_bar();
         // stokesRotation(fluid_beta, p, comv_p), Src/mclib.c:1190-1196
@@ -1120,7 +1154,7 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
             double phi = kn_phi(1, kn, m.q, m.u, rng);
             double out[4];
             ScatterRot rot = m.rot;
-            scatter_stage_out(m.php[0], theta, phi, rot, out);
+            scatter_stage_out(m.php[0], kn.st, kn.ct, phi, rot, out);
 #pragma unroll
             for (int k = 0; k < 4; ++k) m.out[k] = out[k];
         }
@@ -1338,9 +1372,8 @@ __device__ void cs_emit_single(DevCtx &d, EventRng &rng, int scatt, int slot)
 // blockmin_valid: the pass wrote per-block minima for this iteration (fused path / step API)
 template <int EVT_THREADS>
 __device__ __forceinline__ void event_body(DevCtx &d, const int s, const int reloc_base, const int R, int nb_per_shard,
-                                           int step_mode, double dt_max_arg)
+                                           int step_mode, double dt_max_arg, ShardState &st)
 {
-    ShardState &st = d.sh[s];
     GlobalState &gs = *d.gs;
 
     __shared__ double sh_cand_t;
@@ -1480,9 +1513,7 @@ __device__ __forceinline__ void event_body(DevCtx &d, const int s, const int rel
             }
             __syncthreads();
         }
-        if (threadIdx.x == 0) sh_finished = sh_event;
-        __syncthreads();
-        if (sh_finished) break;
+        if (sh_event) break;
         // Klein-Nishina rejection (rare): next entry of this shard's time order after (cand_t, cand_i)
         {
             const double pt = sh_cand_t;
@@ -1513,12 +1544,13 @@ __device__ __forceinline__ void event_body(DevCtx &d, const int s, const int rel
 
     // ---- cyclo-synchrotron pool replacement, Src/mcrat.c:791-808 (the list is one shard here) ----
     __shared__ int cs_need, cs_slot;
-    if (threadIdx.x == 0) {
+    if (d.cs) {
+        if (threadIdx.x == 0) cs_need = (step_mode == 0 && d.ph.type[ph_index] == 'p') ? 1 : 0;
+        __syncthreads();
+    } else if (threadIdx.x == 0) {
         cs_need = 0;
-        if (step_mode == 0 && d.cs && d.ph.type[ph_index] == 'p') cs_need = 1;
     }
-    __syncthreads();
-    if (cs_need) {
+    if (d.cs && cs_need) {
         // first null slot of the list (Src/photons.c:143-150)
         int first_null = INT_MAX;
         for (int j = threadIdx.x; j < st.count; j += EVT_THREADS)
@@ -1578,7 +1610,7 @@ __global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int parity
 {
     const int s = blockIdx.x;
     if (loop_stopped(*d.gs, d.sh[s])) return;
-    event_body<EVT_THREADS>(d, s, 0, d.gs->reloc_count[parity], nb_per_shard, step_mode, dt_max_arg);
+    event_body<EVT_THREADS>(d, s, 0, d.gs->reloc_count[parity], nb_per_shard, step_mode, dt_max_arg, d.sh[s]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1611,22 +1643,22 @@ constexpr int RELOC_HEAVY = 64; // re-locations per shard and iteration above wh
 
 // relocated photons of this iteration: new cell, comoving momentum, tau', free-path draw
 template <int THREADS>
-__device__ __forceinline__ void finish_reloc(DevCtx &d, ShardState &st, const int R)
+__device__ __forceinline__ void finish_reloc(DevCtx &d, ShardState &st, const int s, const int R)
 {
     int missing = 0;
     for (int j = threadIdx.x; j < R; j += THREADS)
-        if (finish_one<true>(d, d.reloc_slot[st.first + j], d.reloc_best[st.first + j], 0)) missing++;
+        if (finish_one<true>(d, st, s, d.reloc_slot[st.first + j], d.reloc_best[st.first + j], 0)) missing++;
     if (missing) atomicAdd(&d.gs->not_found, missing);
     __syncthreads();
     if (threadIdx.x == 0) {
-        st.reloc_n = 0;
+        d.sh[s].reloc_n = 0;
         if (R > RELOC_HEAVY) st.reloc_heavy = 1;
     }
 }
 
 // the shard's relocation entries [first, first+R): one warp per photon through the bounding-box index
 template <int THREADS>
-__device__ __forceinline__ void relocate_shard(DevCtx &d, ShardState &st, const int R)
+__device__ __forceinline__ void relocate_shard(DevCtx &d, ShardState &st, const int s, const int R)
 {
     long long cells_tested = 0, boxes_tested = 0;
     for (int j = threadIdx.x >> 5; j < R; j += THREADS / 32) {
@@ -1639,26 +1671,35 @@ __device__ __forceinline__ void relocate_shard(DevCtx &d, ShardState &st, const 
         atomicAdd((unsigned long long *)&d.gs->box_evals, (unsigned long long)boxes_tested);
     }
     __syncthreads();
-    finish_reloc<THREADS>(d, st, R);
+    finish_reloc<THREADS>(d, st, s, R);
     __syncthreads();
 }
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_kernel(DevCtx d, const int bps)
 {
-    __shared__ int sh_last, sh_halt;
+    __shared__ int sh_last;
+    __shared__ ShardState st; // this block's copy of the shard's state; the publisher writes it back
     GlobalState &gs = *d.gs;
     const int groups = gridDim.x / bps;
     const int g = blockIdx.x / bps, b = blockIdx.x - g * bps;
     if (g >= groups) return;
 
     for (int s = g; s < d.nshards; s += groups) {
-        ShardState &st = d.sh[s];
-        unsigned phase = 0; // phases this block has been through; arrive / gen were zeroed before the launch
+        ShardState &gst = d.sh[s];
+        // global -> shared (the copied part only; the protocol words live in global memory)
+        auto pull = [&]() {
+            if (threadIdx.x < SHARD_STATE_WORDS)
+                reinterpret_cast<unsigned long long *>(&st)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&gst)[threadIdx.x];
+            __syncthreads();
+        };
+        __syncthreads();
+        pull();
+        unsigned phase = 0; // iterations this block has been through; arrive / gen were zeroed before the launch
         // stop test at entry: shard state only, so that all blocks of the shard decide alike
         bool halt = st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters);
 
-        // the last arriver of a phase returns true
+        // the last arriver of an iteration returns true
         auto arrive = [&]() -> bool {
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -1667,7 +1708,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
                     sh_last = 1;
                 } else {
                     __threadfence();
-                    const unsigned ticket = atomicAdd(&st.arrive, 1u);
+                    const unsigned ticket = atomicAdd(&gst.arrive, 1u);
                     sh_last = (ticket == phase * (unsigned)bps - 1u) ? 1 : 0;
                     if (sh_last) __threadfence();
                 }
@@ -1675,37 +1716,38 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
             __syncthreads();
             return sh_last != 0;
         };
-        // last arriver: hand the shard back to its blocks
+        // last arriver: write the state back and hand the shard to its blocks
         auto publish = [&]() {
+            if (threadIdx.x == 0) st.halt = (loop_stopped(gs, st) || st.reloc_heavy) ? 1 : 0;
             __syncthreads();
-            if (threadIdx.x == 0) {
-                st.halt = (loop_stopped(gs, st) || st.reloc_heavy) ? 1 : 0;
-                sh_halt = st.halt;
-                if (bps > 1) {
+            if (threadIdx.x < SHARD_STATE_WORDS)
+                reinterpret_cast<unsigned long long *>(&gst)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&st)[threadIdx.x];
+            if (bps > 1) {
+                __syncthreads();
+                if (threadIdx.x == 0) {
                     __threadfence();
-                    st_release_u32(&st.gen, phase);
+                    st_release_u32(&gst.gen, phase);
                 }
             }
-            __syncthreads();
         };
         auto wait = [&]() {
             if (threadIdx.x == 0) {
                 unsigned spins = 0;
-                bool ok = true;
-                while (ld_acquire_u32(&st.gen) < phase) {
+                while (ld_acquire_u32(&gst.gen) < phase) {
                     __nanosleep(40);
                     if (++spins > (1u << 24)) { // ~1 s: never in a healthy run; refuse to hang the GPU
                         gs.error = MCRAT_B200_ERR_STATE;
-                        ok = false;
                         break;
                     }
                 }
-                sh_halt = ok ? *(volatile int *)&st.halt : 1;
             }
+            __syncthreads();
+            pull();
+            if (gs.error == MCRAT_B200_ERR_STATE) st.halt = 1; // benign race: every thread stores the same value
             __syncthreads();
         };
 #ifdef MCRAT_TIMING
-        const bool tm__ = (threadIdx.x == 0 && s == 0);
+        const bool tm__ = (threadIdx.x == 0 && s == 0 && b == 0);
 #define TLOOP(k) if (tm__) TSTAMP(gs, k)
 #else
 #define TLOOP(k)
@@ -1716,7 +1758,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
             TLOOP(0);
             double best_t = DBL_MAX;
             int best_i = INT_MAX;
-            pass_body<true, true, THREADS>(d, s, b, bps, 0, 0, best_t, best_i);
+            pass_body<true, true, THREADS>(d, st, s, b, bps, 0, 0, best_t, best_i);
             block_argmin<THREADS>(best_t, best_i);
             if (threadIdx.x == 0) {
                 d.bm_t[s * bps + b] = best_t;
@@ -1725,10 +1767,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
             TLOOP(1); // pass + block arg-min
             if (arrive()) {
                 TLOOP(2); // waiting for the other blocks of the shard
-                const int R = *(volatile int *)&st.reloc_n;
-                if (R > 0) relocate_shard<THREADS>(d, st, R);
+                const int R = *(volatile int *)&gst.reloc_n;
+                if (R > 0) relocate_shard<THREADS>(d, st, s, R);
                 TLOOP(3); // re-location
-                event_body<THREADS>(d, s, st.first, R, bps, 0, 0.0);
+                event_body<THREADS>(d, s, st.first, R, bps, 0, 0.0, st);
                 TLOOP(4); // event
                 publish();
                 TLOOP(5);
@@ -1739,8 +1781,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
                 wait();
                 TLOOP(6); // spinning on the generation word
             }
-            halt = sh_halt != 0;
             __syncthreads();
+            halt = st.halt != 0;
         }
     }
 }
