@@ -51,10 +51,10 @@ constexpr int MAX_SHARDS = 4096;
 #define MCRAT_SCAN_P 8
 #endif
 #ifndef MCRAT_SCAN_TILE
-#define MCRAT_SCAN_TILE 512
+#define MCRAT_SCAN_TILE 256
 #endif
 #ifndef MCRAT_SCAN_UNROLL
-#define MCRAT_SCAN_UNROLL 4
+#define MCRAT_SCAN_UNROLL 8
 #endif
 #ifndef MCRAT_SCAN_CTAS_PER_SM
 #define MCRAT_SCAN_CTAS_PER_SM 32
@@ -348,7 +348,19 @@ __global__ void build_geo_kernel(int ndim3, int n, int n_padded, const double *c
 // K4+K2: fused push + locate re-check + free-path draw + block arg-min.
 // Grid = nshards x blocks_per_shard: a block never straddles two sub-shards.
 // ------------------------------------------------------------------------------------------
-constexpr int PASS_THREADS = 256;
+#ifndef MCRAT_PASS_THREADS
+#define MCRAT_PASS_THREADS 256
+#endif
+#ifndef MCRAT_PASS_MINB
+#define MCRAT_PASS_MINB 4
+#endif
+#ifndef MCRAT_PASS_PREFETCH
+#define MCRAT_PASS_PREFETCH 0
+#endif
+#ifndef MCRAT_PASS_CTAS_PER_SM
+#define MCRAT_PASS_CTAS_PER_SM 8
+#endif
+constexpr int PASS_THREADS = MCRAT_PASS_THREADS;
 
 // One block's share of a shard: photons j = b*THREADS + tid, stride nblk*THREADS.
 // LOCAL_RELOC = false: relocating photons go to the global list (gs.reloc_count[parity]) that
@@ -366,6 +378,37 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
     const double default_t = 1e12 / C_LIGHT; // Src/mclib.c:620, 684-687
     const int first = sh.first, count = sh.count;
 
+#if MCRAT_PASS_PREFETCH
+    // Software pipeline: the columns of the photon this thread handles NEXT are requested before the
+    // current one is worked on, so every thread keeps two photons' loads in flight (the pass is
+    // latency-bound on HBM otherwise: one dependent round trip per photon and thread).
+    struct In {
+        unsigned char flags;
+        int idx;
+        double r0, r1, r2, p0, p1, p2, p3, tau;
+    };
+    auto fetch = [&](int jj, In &x) {
+        if (jj < count) {
+            const int ii = first + jj;
+            x.flags = d.ph.flags[ii];
+            x.idx = d.ph.idx[ii];
+            x.r0 = d.ph.r0[ii]; x.r1 = d.ph.r1[ii]; x.r2 = d.ph.r2[ii];
+            x.p0 = d.ph.p0[ii]; x.p1 = d.ph.p1[ii]; x.p2 = d.ph.p2[ii]; x.p3 = d.ph.p3[ii];
+            x.tau = FUSE_MFP ? d.ph.tau[ii] : 0.0;
+        }
+    };
+    const int stride = nblk * THREADS;
+    In cur, nxt;
+    fetch(b * THREADS + threadIdx.x, cur);
+    for (int j = b * THREADS + threadIdx.x; j < count; j += stride) {
+        fetch(j + stride, nxt);
+        const int i = first + j;
+        const unsigned char flags = cur.flags;
+        const int idx = cur.idx;
+        double r0 = cur.r0, r1 = cur.r1, r2 = cur.r2;
+        const double p0 = cur.p0, p1 = cur.p1, p2 = cur.p2, p3 = cur.p3;
+        double tau = cur.tau;
+#else
     for (int j = b * THREADS + threadIdx.x; j < count; j += nblk * THREADS) {
         const int i = first + j;
         // every column this photon can need is requested up front (one round trip to HBM instead
@@ -375,6 +418,7 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
         double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
         const double p0 = d.ph.p0[i], p1 = d.ph.p1[i], p2 = d.ph.p2[i], p3 = d.ph.p3[i];
         double tau = FUSE_MFP ? d.ph.tau[i] : 0.0;
+#endif
         if (n_dt > 0 && (flags & F_MOVABLE) && i != pushed) {
             apply_pushes(sh, n_dt, p0, p1, p2, p3, r0, r1, r2);
             d.ph.r0[i] = r0;
@@ -396,7 +440,11 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
         bool have_t = true;
         if (in_domain) {
             int blk = (sw == 0) ? idx : 0;
+#if defined(MCRAT_EXP_NOGATHER)
+            bool inb = true; // experiment: no cell-geometry gather
+#else
             bool inb = in_cell(ndim3, d.cells, blk, h0, h1, h2);
+#endif
             if (d.cs && blk == 0) { // Src/mclib.c:510-515
                 if ((d.ph.c0[i]) + (d.ph.c1[i]) + (d.ph.c2[i]) + (d.ph.c3[i]) == 0) inb = false;
             }
@@ -418,8 +466,12 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
                     d.ph.tau[i] = tau;
                     d.ph.flags[i] = flags & ~F_RECALC;
                 }
+#if defined(MCRAT_EXP_NOCOMPUTE)
+                t = tau * (double)j; // experiment: memory pattern without Philox / log / divisions
+#else
                 double xi = philox_mfp_uniform(d.k0, k1, iter, (uint32_t)j);
                 t = free_path_time(tau, xi);
+#endif
             }
         } else {
             if (idx != -1) d.ph.idx[i] = -1; // Src/mclib.c:589-595
@@ -431,11 +483,14 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
                 best_i = i;
             }
         }
+#if MCRAT_PASS_PREFETCH
+        cur = nxt;
+#endif
     }
 }
 
 template <bool FUSE_MFP>
-__global__ void __launch_bounds__(PASS_THREADS, 4) pass_kernel(DevCtx d, int sw, int parity)
+__global__ void __launch_bounds__(PASS_THREADS, MCRAT_PASS_MINB) pass_kernel(DevCtx d, int sw, int parity)
 {
     const int s = blockIdx.x / d.blocks_per_shard;
     const int b = blockIdx.x - s * d.blocks_per_shard;
@@ -2437,7 +2492,7 @@ static int layout_shards(mcrat_b200_ctx *ctx, int n)
     d.nshards = S;
     d.shard_size = size;
     int bps = (size + PASS_THREADS - 1) / PASS_THREADS;
-    int cap_sm = (ctx->num_sms * 8) / S;
+    int cap_sm = (ctx->num_sms * MCRAT_PASS_CTAS_PER_SM) / S;
     if (cap_sm < 1) cap_sm = 1;
     if (bps > cap_sm) bps = cap_sm;
     if (bps > BLOCKMIN_CAP / S) bps = BLOCKMIN_CAP / S;
