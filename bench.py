@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--full-scan", action="store_true",
                     help="re-locate with the full photon x cell scan (K1) instead of the bounding-box index")
     ap.add_argument("--cpu-iters", type=int, default=0, help="iterations per CPU rank and step (0: same as --iters)")
+    ap.add_argument("--loop", default="auto", choices=["auto", "streamed", "persistent"],
+                    help="frame-loop driver: one cooperative launch per frame (persistent) or four launches per iteration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pass-roofline", action="store_true")
     return ap.parse_args()
@@ -195,6 +197,8 @@ def main():
                                "its own time-ordered scatter sequence" % (shards, photons.size // shards),
               "step": "full photon x cell rescan (new hydro frame) + loop iterations; steps continue one simulation",
               "l2": "flushed between timed steps (256 MiB write)",
+              "loop": args.loop + " (auto = persistent frame_loop_kernel: one cooperative launch per frame; lists > 2^21 "
+                      "photons use the streamed loop)",
               "relocation": "full photon x cell scan (K1)" if args.full_scan else
               "bounding-box index over the cells in array order (identical first-match results; K1 timed "
               "separately for the roofline)"}
@@ -234,7 +238,7 @@ def main():
 
     stream = torch.cuda.current_stream().cuda_stream
     hp = HotPath(cfg, device=local_rank, seed=20261018, shard=rank * shards, stream=stream, num_shards=shards,
-                 scan_index=not args.full_scan)
+                 scan_index=not args.full_scan, loop_mode=args.loop)
     hp.set_hydro(hydro)
     hp.set_photons(photons)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -283,9 +287,15 @@ def main():
     fp64_peak = hp.measure_fp64_peak()  # G FP64-pipe instr/s (DFMA issue rate), same GPU, same run
     instr_per_eval = 6 if cfg["dimensions"] == 2 else 4  # one DADD + one DSETP per dimension
     achieved = scan_evals * instr_per_eval / (scan_ms_avg * 1e-3) / 1e9
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch, from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and args.scale == 1.0 and args.photons == 100000:
+        traffic = json.load(open(tpath)).get("scan_kernel_C2_bytes")
     roofline = {"kernel": "scan_kernel (K1 photon x cell containment scan)", "bound": "fp64",
                 "achieved": achieved, "peak": fp64_peak, "unit": "G FP64-pipe instr/s",
-                "frac": achieved / fp64_peak, "traffic": None,
+                "frac": achieved / fp64_peak, "traffic": traffic,
+                "traffic_note": "bytes per launch (ncu --set full, profiles/ncu_traffic.json); algorithmic minimum "
+                                "32 B x cells + 28 B x photons = %d" % (32 * int(hydro["num_elements"]) + 28 * photons.size),
                 "peak_source": "measured in this run (mcrat_b200_measure_fp64_peak: 16 independent DFMA chains/thread, all SMs); "
                                "MEASURED_PEAKS.json holds no FP64 figure",
                 "algorithmic": "%d FP64-pipe instr per photon-cell eval x %d evals per launch" % (instr_per_eval, scan_evals),
@@ -335,7 +345,8 @@ def main():
                 os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
             peak = peaks.get("hbm_gbs", 6650.0)
             pass_roofline = {"kernel": "pass_kernel<fused> (K4+K2) at %d photons" % nbig, "bound": "hbm",
-                             "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                             "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                             "traffic": (json.load(open(tpath)).get("pass_kernel_4e6_bytes") if os.path.exists(tpath) else None),
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
                              "algorithmic": "100 B per photon-iteration x %d photons" % nbig, "ms_per_launch": ms}
             hpb.close()
@@ -366,6 +377,7 @@ def main():
                 "photon_cell_evals_per_sec": roofline["evals_per_s"] * world,
                 "photon_iterations_per_sec": slots_all / (t_max * 1e-3),
                 "k1_full_scan_ms": scan_ms_avg,
+                "loop_us_per_iteration": 1e3 * t_max / args.steps / args.iters,
                 "roofline": roofline, "pass_roofline": pass_roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_all / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_max / args.steps},

@@ -12,9 +12,11 @@ from mcrat_b200 import HotPath, synth  # noqa: E402
 
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 big = int(sys.argv[2]) if len(sys.argv) > 2 else 4_000_000
+shards = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+loop = sys.argv[4] if len(sys.argv) > 4 else "auto"
 
 cfg, hydro, photons, frame = synth.workload("C2")
-hp = HotPath(cfg, seed=1)
+hp = HotPath(cfg, seed=1, num_shards=shards, loop_mode=loop)
 hp.set_hydro(hydro)
 hp.set_photons(photons)
 st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=iters, switch=1)
