@@ -47,13 +47,19 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--iters", type=int, default=5000, help="while-loop iterations per step (frame slice)")
-    ap.add_argument("--photons", type=int, default=100000)
+    ap.add_argument("--workload", default="C2", choices=["C2", "C5"],
+                    help="C2 = BASELINE configs[1] (default, the config the metric is quoted on); C5 = 3-D spherical "
+                         "PLUTO-shape jet of the photon-count scaling sweep (use with --photons 1e5 .. 1e7)")
+    ap.add_argument("--photons", type=float, default=100000)
     ap.add_argument("--scale", type=float, default=1.0, help="grid scale (1.0 = 1024x1024 cells)")
-    ap.add_argument("--shards", type=int, default=0,
-                    help="sub-shards (independent reference ranks) per GPU; 0 = one per host core, the "
-                         "decomposition the reference arm uses")
-    ap.add_argument("--full-scan", action="store_true",
-                    help="re-locate with the full photon x cell scan (K1) instead of the bounding-box index")
+    ap.add_argument("--shards", type=int, default=16,
+                    help="sub-shards (independent reference ranks, each with its own list, clock and scatter sequence) "
+                         "per GPU; both arms use the same decomposition.  Fixed at 16 by default so that the metric does "
+                         "not depend on the host's core count (the reference arm runs them on min(cores, shards) cores)")
+    ap.add_argument("--index", action="store_true",
+                    help="re-locate a new hydro frame through the bounding-box index (K1c: same cells, ~2000x fewer "
+                         "tests) instead of the reference's full photon x cell scan (K1, the default and the kernel "
+                         "the roofline is quoted on)")
     ap.add_argument("--cpu-iters", type=int, default=0, help="iterations per CPU rank and step (0: same as --iters)")
     ap.add_argument("--loop", default="auto", choices=["auto", "streamed", "persistent"],
                     help="frame-loop driver: one cooperative launch per frame (persistent) or four launches per iteration")
@@ -113,14 +119,14 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own sources (oracle/_ref) or, if absent, the oracle port
 # ------------------------------------------------------------------------------------------------
-def _cpu_rank(rank, nranks, shards, cfg, hydro, photons, frame, iters, steps, warmup, kind, barrier, out):
+def _cpu_rank(rank, nranks, shards, cfg, hydro, photons, frame, iters, steps, warmup, kind, barrier, out, refname):
     """One host core: runs its share of the shards (rank, rank + nranks, ...) one after the other."""
     from oracle import api
     from mcrat_b200 import shard as shardlib
     ranges = shardlib.sub_shard_ranges(photons.size, shards)
     mine = list(range(rank, len(ranges), nranks))
     if kind == "reference":
-        eng = api.RefLib("c2_2d_cyl_stokes")
+        eng = api.RefLib(refname)
         eng.set_hydro(hydro)
     else:
         eng = api.Oracle(cfg)
@@ -148,12 +154,12 @@ def _cpu_rank(rank, nranks, shards, cfg, hydro, photons, frame, iters, steps, wa
     out.put((rank, scatt, t_steps))
 
 
-def run_cpu_arm(cfg, hydro, photons, frame, iters, steps, warmup, shards):
+def run_cpu_arm(cfg, hydro, photons, frame, iters, steps, warmup, shards, refname="c2_2d_cyl_stokes"):
     """The reference's own CPU code on all host cores.  The job is decomposed into `shards`
     independent ranks -- the reference's own way of using more cores, no exchange inside the frame
     loop -- exactly as on the GPU arm; each core runs its share of them one after the other."""
     from oracle import api
-    kind = "reference" if api.ref_available("c2_2d_cyl_stokes") else "port"
+    kind = "reference" if api.ref_available(refname) else "port"
     if kind == "port":
         api.build_oracle()
     ncores = len(os.sched_getaffinity(0))
@@ -162,7 +168,7 @@ def run_cpu_arm(cfg, hydro, photons, frame, iters, steps, warmup, shards):
     barrier = ctx.Barrier(nranks)
     out = ctx.Queue()
     procs = [ctx.Process(target=_cpu_rank, args=(r, nranks, shards, cfg, hydro, photons, frame, iters, steps, warmup,
-                                                 kind, barrier, out)) for r in range(nranks)]
+                                                 kind, barrier, out, refname)) for r in range(nranks)]
     for p in procs:
         p.start()
     res = [out.get() for _ in procs]
@@ -177,20 +183,34 @@ def run_cpu_arm(cfg, hydro, photons, frame, iters, steps, warmup, shards):
                        "%d step(s)" % (shards, photons.size // shards, nranks, iters, steps))
 
 
+def cpu_sample_iters(args, shards):
+    """Loop iterations per CPU rank and step: the bounded sample of the same workload.  One iteration costs the
+    reference O(N log N) in the list length (push + draw + qsort), so the count shrinks with the list to keep the
+    CPU arm at tens of seconds; the metric is a rate, the sample size does not enter it."""
+    if args.cpu_iters:
+        return args.cpu_iters
+    per_rank = max(args.photons // shards, 1)
+    return int(max(10, min(args.iters, args.iters * 6250 // per_rank)))
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
+    args.photons = int(args.photons)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     from mcrat_b200 import synth
     log("building workload")
-    cfg, hydro, photons, frame = synth.workload("C2", scale=args.scale, n_photons=args.photons, seed=1234 + rank)
+    cfg, hydro, photons, frame = synth.workload(args.workload, scale=args.scale, n_photons=args.photons, seed=1234 + rank)
+    refname = {"C2": "c2_2d_cyl_stokes", "C5": "c5_3d_sph"}[args.workload]
+    wl_name = WORKLOAD if args.workload == "C2" else \
+        "C5: 3-D spherical PLUTO-shape jet, 256x64x64 cells, %d photons per GPU, Stokes on" % args.photons
     ncores = len(os.sched_getaffinity(0))
-    shards = args.shards if args.shards > 0 else max(1, min(ncores, args.photons // 256))
-    config = {"workload": WORKLOAD if (args.scale == 1.0 and args.photons == 100000) else
-              "C2 reduced: scale=%g, %d photons/GPU" % (args.scale, args.photons),
+    shards = max(1, min(args.shards, args.photons // 256))
+    config = {"workload": wl_name if (args.scale == 1.0 and (args.photons == 100000 or args.workload == "C5")) else
+              "%s reduced: scale=%g, %d photons/GPU" % (args.workload, args.scale, args.photons),
               "cells": int(hydro["num_elements"]), "photons_per_gpu": int(photons.size),
               "loop_iterations_per_step": args.iters, "gpu_ranks": world, "shards_per_gpu": shards,
               "decomposition": "%d independent shards (reference ranks) of %d photons per GPU, each advancing "
@@ -199,15 +219,15 @@ def main():
               "l2": "flushed between timed steps (256 MiB write)",
               "loop": args.loop + " (auto = persistent frame_loop_kernel: one cooperative launch per frame; lists > 2^21 "
                       "photons use the streamed loop)",
-              "relocation": "full photon x cell scan (K1)" if args.full_scan else
-              "bounding-box index over the cells in array order (identical first-match results; K1 timed "
-              "separately for the roofline)"}
+              "relocation": "bounding-box index over the cells in array order (K1c, identical first-match results)"
+              if args.index else "full photon x cell scan of every new hydro frame (K1), as the reference does; "
+              "steady-state re-locations inside the loop go through the bounding-box index"}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cpu_iters = args.cpu_iters or args.iters
-        res = run_cpu_arm(cfg, hydro, photons, frame, cpu_iters, args.steps, args.warmup, shards)
+        cpu_iters = cpu_sample_iters(args, shards)
+        res = run_cpu_arm(cfg, hydro, photons, frame, cpu_iters, args.steps, args.warmup, shards, refname)
         config["loop_iterations_per_step"] = cpu_iters
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
@@ -238,7 +258,7 @@ def main():
 
     stream = torch.cuda.current_stream().cuda_stream
     hp = HotPath(cfg, device=local_rank, seed=20261018, shard=rank * shards, stream=stream, num_shards=shards,
-                 scan_index=not args.full_scan, loop_mode=args.loop)
+                 scan_index=args.index, loop_mode=args.loop)
     hp.set_hydro(hydro)
     hp.set_photons(photons)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -289,7 +309,7 @@ def main():
     achieved = scan_evals * instr_per_eval / (scan_ms_avg * 1e-3) / 1e9
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch, from the committed ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath) and args.scale == 1.0 and args.photons == 100000:
+    if os.path.exists(tpath) and args.scale == 1.0 and args.photons == 100000 and args.workload == "C2":
         traffic = json.load(open(tpath)).get("scan_kernel_C2_bytes")
     roofline = {"kernel": "scan_kernel (K1 photon x cell containment scan)", "bound": "fp64",
                 "achieved": achieved, "peak": fp64_peak, "unit": "G FP64-pipe instr/s",
@@ -367,8 +387,8 @@ def main():
         cpu = None
         log("cpu baseline")
         if not args.no_cpu_baseline and world == 1:
-            cpu_iters = args.cpu_iters or args.iters
-            r = run_cpu_arm(cfg, hydro, photons, frame, cpu_iters, 1, 0, shards)
+            cpu_iters = cpu_sample_iters(args, shards)
+            r = run_cpu_arm(cfg, hydro, photons, frame, cpu_iters, 1, 0, shards, refname)
             cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
         line = {"metric": METRIC, "value": scatt_all / (t_max * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_max / args.steps,

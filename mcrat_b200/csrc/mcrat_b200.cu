@@ -354,9 +354,6 @@ __global__ void build_geo_kernel(int ndim3, int n, int n_padded, const double *c
 #ifndef MCRAT_PASS_MINB
 #define MCRAT_PASS_MINB 4
 #endif
-#ifndef MCRAT_PASS_PREFETCH
-#define MCRAT_PASS_PREFETCH 0
-#endif
 #ifndef MCRAT_PASS_CTAS_PER_SM
 #define MCRAT_PASS_CTAS_PER_SM 8
 #endif
@@ -378,37 +375,6 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
     const double default_t = 1e12 / C_LIGHT; // Src/mclib.c:620, 684-687
     const int first = sh.first, count = sh.count;
 
-#if MCRAT_PASS_PREFETCH
-    // Software pipeline: the columns of the photon this thread handles NEXT are requested before the
-    // current one is worked on, so every thread keeps two photons' loads in flight (the pass is
-    // latency-bound on HBM otherwise: one dependent round trip per photon and thread).
-    struct In {
-        unsigned char flags;
-        int idx;
-        double r0, r1, r2, p0, p1, p2, p3, tau;
-    };
-    auto fetch = [&](int jj, In &x) {
-        if (jj < count) {
-            const int ii = first + jj;
-            x.flags = d.ph.flags[ii];
-            x.idx = d.ph.idx[ii];
-            x.r0 = d.ph.r0[ii]; x.r1 = d.ph.r1[ii]; x.r2 = d.ph.r2[ii];
-            x.p0 = d.ph.p0[ii]; x.p1 = d.ph.p1[ii]; x.p2 = d.ph.p2[ii]; x.p3 = d.ph.p3[ii];
-            x.tau = FUSE_MFP ? d.ph.tau[ii] : 0.0;
-        }
-    };
-    const int stride = nblk * THREADS;
-    In cur, nxt;
-    fetch(b * THREADS + threadIdx.x, cur);
-    for (int j = b * THREADS + threadIdx.x; j < count; j += stride) {
-        fetch(j + stride, nxt);
-        const int i = first + j;
-        const unsigned char flags = cur.flags;
-        const int idx = cur.idx;
-        double r0 = cur.r0, r1 = cur.r1, r2 = cur.r2;
-        const double p0 = cur.p0, p1 = cur.p1, p2 = cur.p2, p3 = cur.p3;
-        double tau = cur.tau;
-#else
     for (int j = b * THREADS + threadIdx.x; j < count; j += nblk * THREADS) {
         const int i = first + j;
         // every column this photon can need is requested up front (one round trip to HBM instead
@@ -418,7 +384,6 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
         double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
         const double p0 = d.ph.p0[i], p1 = d.ph.p1[i], p2 = d.ph.p2[i], p3 = d.ph.p3[i];
         double tau = FUSE_MFP ? d.ph.tau[i] : 0.0;
-#endif
         if (n_dt > 0 && (flags & F_MOVABLE) && i != pushed) {
             apply_pushes(sh, n_dt, p0, p1, p2, p3, r0, r1, r2);
             d.ph.r0[i] = r0;
@@ -441,7 +406,7 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
         if (in_domain) {
             int blk = (sw == 0) ? idx : 0;
 #if defined(MCRAT_EXP_NOGATHER)
-            bool inb = true; // experiment: no cell-geometry gather
+            bool inb = true; // ablation build: no cell-geometry gather (see MCRAT_EXP_NOCOMPUTE)
 #else
             bool inb = in_cell(ndim3, d.cells, blk, h0, h1, h2);
 #endif
@@ -467,7 +432,9 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
                     d.ph.flags[i] = flags & ~F_RECALC;
                 }
 #if defined(MCRAT_EXP_NOCOMPUTE)
-                t = tau * (double)j; // experiment: memory pattern without Philox / log / divisions
+                // ablation build (profiles/ncu_r01_summary.md, "pass kernel: where the time goes"): the memory
+                // pattern alone, without Philox / log / divisions.  Never defined in the product build.
+                t = tau * (double)j;
 #else
                 double xi = philox_mfp_uniform(d.k0, k1, iter, (uint32_t)j);
                 t = free_path_time(tau, xi);
@@ -483,9 +450,6 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
                 best_i = i;
             }
         }
-#if MCRAT_PASS_PREFETCH
-        cur = nxt;
-#endif
     }
 }
 
