@@ -3008,16 +3008,18 @@ API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remain
             if (int rc = fetch_state(ctx)) return rc;
             if (ctx->gs_host->error) break;
             bool heavy = false, running = false;
+            long long batch = 32; // iterations the slowest running shard may still do, capped
             for (int k = 0; k < S; ++k) {
                 const ShardState &h = ctx->sh_host[k];
                 const bool stopped = h.done || h.pause_cs || (max_iters >= 0 && h.iters_done >= max_iters);
                 if (!stopped) running = true;
                 if (!stopped && h.reloc_heavy) heavy = true;
+                if (!stopped && max_iters >= 0 && max_iters - h.iters_done < batch) batch = max_iters - h.iters_done;
             }
             if (!running) break;
             if (!heavy) return fail(ctx, MCRAT_B200_ERR_STATE, "frame_loop_kernel returned with running shards");
             // many photons change cell per iteration (optically thin flow): K1b / K1c serve that better
-            for (int b = 0; b < 32; ++b)
+            for (long long b = 0; b < batch; ++b)
                 if (int rc = streamed_iteration()) return rc;
             if (int rc = reset_protocol(ctx)) return rc;
             (void)launched;

@@ -93,3 +93,88 @@ def test_sub_shards_equal_independent_ranks(wl, nph, shards, iters):
         compare_photons(got[sl], o.photons(), label="%s shard %d" % (wl, s), stokes_tol=1e-9, hydro=hydro)
         total_scatt += ost["scatterings"]
     assert st["scatterings"] == total_scatt
+
+
+def _thin(hydro, factor):
+    """The same flow, `factor` times more dilute: free paths and therefore event time steps grow by 1/factor, so
+    that many photons change cell in every loop iteration (the regime the persistent loop hands back to K1b / K1c)."""
+    h = dict(hydro)
+    h["dens"] = np.asarray(hydro["dens"]) * factor
+    h["dens_lab"] = np.asarray(hydro["dens_lab"]) * factor
+    return h
+
+
+LOOP_CASES = [
+    # workload, grid scale, photons, sub-shards, iterations, dilution, scan_index
+    ("C2", 1.0 / 16, 3000, 1, 150, 1.0, False),
+    ("C2", 1.0 / 16, 3000, 5, 150, 1.0, True),
+    ("C5", 1.0 / 8, 4000, 40, 60, 1.0, False),
+    ("C1", 1.0 / 8, 2000, 3, 120, 1.0, False),
+    ("C2", 1.0 / 4, 3000, 2, 30, 5e-6, False),     # optically thin: ~100 re-locations per shard and iteration
+    ("C5", 1.0 / 8, 20000, 320, 30, 1.0, True),     # more shards than resident wide blocks: four-warp blocks
+]
+
+
+@pytest.mark.parametrize("wl,scale,nph,shards,iters,dilute,scan_index", LOOP_CASES)
+def test_persistent_loop_is_bit_identical_to_streamed_loop_and_matches_oracle(wl, scale, nph, shards, iters, dilute, scan_index):
+    """One cooperative launch per frame (frame_loop_kernel) vs four launches per iteration: same photons bit for bit,
+    same counters; and sub-shard 0 against the oracle.  Covers the hand-back to the streamed loop when a shard
+    re-locates more than RELOC_HEAVY photons per iteration, frames that end inside the call, and max_iters stops."""
+    cfg, hydro, photons, frame = synth.workload(wl, scale=scale, n_photons=nph, seed=41)
+    if dilute != 1.0:
+        hydro = _thin(hydro, dilute)
+    out = {}
+    for mode in ("streamed", "persistent"):
+        hp = HotPath(cfg, seed=5150, shard=7, num_shards=shards, scan_index=scan_index, loop_mode=mode)
+        hp.set_hydro(hydro)
+        hp.set_photons(photons)
+        st1 = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=iters, switch=1)
+        st2 = hp.run_frame(st1["time_now"], 1.0 / frame["fps"] - (st1["time_now"] - frame["time_now"]), max_iters=iters // 2,
+                           switch=0)
+        out[mode] = (st1, st2, hp.get_photons(), [hp.shard_stats(s) for s in range(hp.num_shards())], hp.launch_count())
+        hp.close()
+    a, b = out["streamed"], out["persistent"]
+    for k in ("iterations", "scatterings", "relocations", "photon_slots", "not_found", "time_now", "last_time_step",
+              "last_scattered_index"):
+        assert a[0][k] == b[0][k] and a[1][k] == b[1][k], (k, a[0], b[0], a[1], b[1])
+    for f in a[2].dtype.names:
+        assert np.array_equal(a[2][f], b[2][f], equal_nan=(a[2].dtype[f].kind == "f")), "field %s differs" % f
+    for sa, sb in zip(a[3], b[3]):
+        for k in ("iterations", "scatterings", "relocations", "time_now"):
+            assert sa[k] == sb[k], (k, sa, sb)
+    if dilute == 1.0:
+        assert b[4] < a[4]  # far fewer launches
+    else:
+        assert a[0]["relocations"] > 64 * iters / 4, "the thin case must actually exercise heavy re-location: %s" % a[0]
+    # sub-shard 0 against the oracle (two consecutive calls, the second continuing the frame)
+    ss = b[3][0]
+    sl = slice(ss["first_slot"], ss["first_slot"] + ss["num_slots"])
+    o = api.Oracle(cfg)
+    o.set_hydro(hydro)
+    o.set_photons(photons[sl])
+    rng = api.OracleRng("philox", seed=5150, shard=7)
+    o1 = o.run_frame(rng, frame["time_now"], 1.0 / frame["fps"], max_iters=iters, switch=1)
+    o2 = o.run_frame(rng, o1["time_now"], 1.0 / frame["fps"] - (o1["time_now"] - frame["time_now"]), max_iters=iters // 2, switch=0)
+    assert ss["scatterings"] == o1["scatterings"] + o2["scatterings"]
+    compare_photons(b[2][sl], o.photons(), label="%s persistent shard 0" % wl, stokes_tol=1e-9, hydro=hydro)
+
+
+def test_persistent_loop_runs_a_frame_to_its_end():
+    """No iteration cap: every shard stops when its own clock reaches the next hydro frame (Src/mcrat.c:834-846)."""
+    cfg, hydro, photons, frame = synth.workload("C2", scale=1.0 / 16, n_photons=600, seed=43)
+    hydro = _thin(hydro, 3e-4)  # a few hundred scatterings per shard and frame instead of millions
+    res = {}
+    for mode in ("streamed", "persistent"):
+        hp = HotPath(cfg, seed=99, num_shards=4, loop_mode=mode)
+        hp.set_hydro(hydro)
+        hp.set_photons(photons)
+        st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=-1, switch=1)
+        res[mode] = (st, hp.get_photons(), [hp.shard_stats(s) for s in range(4)])
+        hp.close()
+    st, ph, shards = res["persistent"]
+    assert st["scatterings"] > 50
+    for s in shards:
+        assert abs(s["time_now"] - (frame["time_now"] + 1.0 / frame["fps"])) <= 1e-9 * s["time_now"], s
+    assert res["streamed"][0]["scatterings"] == st["scatterings"] and res["streamed"][0]["iterations"] == st["iterations"]
+    for f in ph.dtype.names:
+        assert np.array_equal(ph[f], res["streamed"][1][f], equal_nan=(ph.dtype[f].kind == "f")), f
