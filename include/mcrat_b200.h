@@ -182,6 +182,16 @@ double mcrat_b200_calc_cyclosynch_r_limits(int frame_scatt, int frame_inj, doubl
  * photons on the device (photonEmitCyclosynch in single mode, Src/mc_cyclosynch.c:1465-1555) and
  * pauses for the host only to grow the list or to rebin */
 int mcrat_b200_set_cs_limits(mcrat_b200_ctx *ctx, int max_photons, int scatt_cyclosynch_num_ph);
+/* rebinCyclosynchCompPhotons, Src/mc_cyclosynch.h:86, Src/mc_cyclosynch.c:600-710, on the device: every 'k' / 'c' photon
+ * is replaced by the weighted-mean photon of its (log E, theta[, phi]) bin, placed into the null slots of the list in slot
+ * order (addToPhotonList, Src/photons.c:167-205).  The counters are the ones the reference updates (:680-684); the return
+ * value is MCRAT_B200_OK or an error (the reference returns the number of empty bins, given here through
+ * num_null_rebin_ph).  If the list has fewer null slots than bins the call fails with MCRAT_B200_ERR_STATE and the host
+ * must grow the list.  Single shard only (CYCLOSYNCHROTRON_SWITCH ON). */
+int mcrat_b200_rebin_cyclosynch_comp_photons(mcrat_b200_ctx *ctx, int max_photons, int *num_cyclosynch_ph_emit,
+                                             int *scatt_cyclosynch_num_ph, int *num_null_rebin_ph);
+/* CYCLOSYNCHROTRON_REBIN_E_PERC, _REBIN_ANG (degrees), _REBIN_ANG_PHI (degrees); defaults 0.1, 0.5, 10 (Src/mcrat.h:308-322) */
+int mcrat_b200_set_cs_rebin_params(mcrat_b200_ctx *ctx, double rebin_e_perc, double rebin_ang_deg, double rebin_ang_phi_deg);
 /* phMinMax / phScattStats / averagePhotonEnergy, Src/mclib.c:1465 / 1385 / 1358 */
 int mcrat_b200_ph_min_max(mcrat_b200_ctx *ctx, double *min_r, double *max_r, double *min_theta, double *max_theta);
 int mcrat_b200_ph_scatt_stats(mcrat_b200_ctx *ctx, int *max_scatt, int *min_scatt, double *avg_scatt, double *avg_r);

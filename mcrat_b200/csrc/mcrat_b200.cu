@@ -2015,6 +2015,301 @@ __global__ void __launch_bounds__(256) stats_kernel(DevCtx d, StatPartial *out)
 }
 
 // ------------------------------------------------------------------------------------------
+// K8: rebinCyclosynchCompPhotons, Src/mc_cyclosynch.c:244-710, on the device.  The (log E, theta[, phi])
+// binning of the reference, including gsl_histogram2d's uniform ranges and its find() (linear guess,
+// then bisection); every bin's weighted sums are accumulated in slot order, as the reference's one
+// sequential loop does, so the rebinned photons agree with the CPU's to rounding of acos / atan2 / sincos.
+// ------------------------------------------------------------------------------------------
+constexpr double RAD_TO_DEG = 180.0 / PI, DEG_TO_RAD = PI / 180.0; // Src/mcrat.h:80-81
+
+struct RebinRange { // struct PhotonRangeInfo, Src/mc_cyclosynch.h
+    double p0_min, p0_max, theta_min, theta_max, phi_min, phi_max;
+    int valid_photon_count, synch_photon_count;
+};
+
+struct RebinParams { // struct BinningParams + the histogram ranges
+    int num_bins, num_bins_theta, num_bins_phi, total_bins;
+    const double *range_e, *range_theta, *range_phi; // num_bins+1, num_bins_theta+1, num_bins_phi+1 edges
+};
+
+struct RebinBin { // struct BinStats
+    double weighted_r, weighted_theta, weighted_phi_offset, weighted_stokes[4], weighted_scatt_count, total_weight;
+    double weighted_phi_dir, weighted_theta_dir, weighted_energy, weighted_phi_pos;
+};
+
+__device__ __forceinline__ bool rebin_eligible(char type) { return (type != 'N') && (type != 'p') && (type != 'i'); }
+
+// calculate_photon_position, Src/mc_cyclosynch.c:246-270
+__device__ __forceinline__ void rebin_position(int ndim3, double x, double y, double z, double &r, double &theta, double &phi)
+{
+    r = sqrt(x * x + y * y + z * z);
+    if (r < DBL_MIN) {
+        theta = 0.0;
+        phi = 0.0;
+    } else {
+        theta = acos(z / r);
+        if (ndim3) {
+            double phi_rad = atan2(y, x);
+            phi = fmod(phi_rad * RAD_TO_DEG + 360.0, 360.0);
+        } else {
+            phi = 0;
+        }
+    }
+}
+
+// collect_photon_statistics, Src/mc_cyclosynch.c:273-322 (per-block partials; min / max are exact in any order)
+__global__ void __launch_bounds__(256) rebin_range_kernel(DevCtx d, RebinRange *out)
+{
+    const int ndim3 = (d.dims == D_THREE);
+    RebinRange a;
+    a.p0_min = DBL_MAX; a.p0_max = 0.0; a.theta_min = DBL_MAX; a.theta_max = 0.0; a.phi_min = DBL_MAX; a.phi_max = 0.0;
+    a.valid_photon_count = 0; a.synch_photon_count = 0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < d.cap; i += gridDim.x * 256) {
+        const char type = d.ph.type[i];
+        if (rebin_eligible(type)) {
+            const double p0 = d.ph.p0[i];
+            if (p0 > 0) {
+                a.p0_min = fmin(a.p0_min, p0);
+                a.p0_max = fmax(a.p0_max, p0);
+                a.valid_photon_count++;
+            }
+            double r, theta, phi;
+            rebin_position(ndim3, d.ph.r0[i], d.ph.r1[i], d.ph.r2[i], r, theta, phi);
+            a.theta_min = fmin(a.theta_min, theta);
+            a.theta_max = fmax(a.theta_max, theta);
+            if (ndim3) {
+                a.phi_min = fmin(a.phi_min, phi);
+                a.phi_max = fmax(a.phi_max, phi);
+            }
+        }
+        if (type == 'p') a.synch_photon_count++;
+    }
+    __shared__ RebinRange sh[256];
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            RebinRange &x = sh[threadIdx.x];
+            const RebinRange &y = sh[threadIdx.x + s];
+            x.p0_min = fmin(x.p0_min, y.p0_min); x.p0_max = fmax(x.p0_max, y.p0_max);
+            x.theta_min = fmin(x.theta_min, y.theta_min); x.theta_max = fmax(x.theta_max, y.theta_max);
+            x.phi_min = fmin(x.phi_min, y.phi_min); x.phi_max = fmax(x.phi_max, y.phi_max);
+            x.valid_photon_count += y.valid_photon_count; x.synch_photon_count += y.synch_photon_count;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+
+// gsl_histogram find(): 0 on success (histogram/find.c: linear guess, then bisection)
+__device__ __forceinline__ int hist_find(int n, const double *range, double x, int &i)
+{
+    if (x < range[0] || x >= range[n]) return 1;
+    {
+        double u = (x - range[0]) / (range[n] - range[0]);
+        size_t g = (size_t)(u * n);
+        if (g < (size_t)n && x >= range[g] && x < range[g + 1]) {
+            i = (int)g;
+            return 0;
+        }
+    }
+    int lower = 0, upper = n;
+    while (upper - lower > 1) {
+        int mid = (upper + lower) / 2;
+        if (x >= range[mid])
+            lower = mid;
+        else
+            upper = mid;
+    }
+    i = lower;
+    return 0;
+}
+
+// bin index of every slot (or -1), Src/mc_cyclosynch.c:453-472
+__global__ void __launch_bounds__(256) rebin_index_kernel(DevCtx d, RebinParams p, int *bin_of)
+{
+    const int ndim3 = (d.dims == D_THREE);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < d.cap; i += gridDim.x * 256) {
+        int b = -1;
+        if (rebin_eligible(d.ph.type[i])) {
+            double r, theta, phi;
+            rebin_position(ndim3, d.ph.r0[i], d.ph.r1[i], d.ph.r2[i], r, theta, phi);
+            const double le = log10(d.ph.p0[i]);
+            int ix = 0, iy = 0, iz = 0;
+            // gsl_histogram2d_find(h_energy_theta, ...): the second index is only written if the first was found
+            if (hist_find(p.num_bins, p.range_e, le, ix) == 0) hist_find(p.num_bins_theta, p.range_theta, theta, iy);
+            if (ndim3) {
+                if (hist_find(p.num_bins, p.range_e, le, ix) == 0) hist_find(p.num_bins_phi, p.range_phi, phi, iz);
+                if (hist_find(p.num_bins_theta, p.range_theta, theta, iy) == 0) hist_find(p.num_bins_phi, p.range_phi, phi, iz);
+            }
+            // calculate_bin_index, :432-446
+            if (ix < 0 || ix >= p.num_bins || iy < 0 || iy >= p.num_bins_theta)
+                b = -2;
+            else if (ndim3)
+                b = (iz < 0 || iz >= p.num_bins_phi) ? -2 : iz * p.num_bins * p.num_bins_theta + ix * p.num_bins_theta + iy;
+            else
+                b = ix * p.num_bins_theta + iy;
+            if (b == -2 || b >= p.total_bins) {
+                d.gs->error = MCRAT_B200_ERR_STATE; // the reference exits here (:469-472)
+                b = -1;
+            }
+        }
+        bin_of[i] = b;
+    }
+}
+
+// accumulate_bin_statistics + create_rebinned_photons (:448-585): one thread per bin walks the list in slot
+// order (warp-uniform reads of bin_of[]), which keeps the reference's order of additions inside every bin
+__global__ void __launch_bounds__(128) rebin_accumulate_kernel(DevCtx d, RebinParams p, const int *bin_of, mcrat_photon *out)
+{
+    const int ndim3 = (d.dims == D_THREE);
+    const int b = blockIdx.x * 128 + threadIdx.x;
+    RebinBin s;
+    memset(&s, 0, sizeof(s));
+    for (int i = 0; i < d.cap; ++i) {
+        if (bin_of[i] != b || b >= p.total_bins) continue;
+        const double w = d.ph.weight[i];
+        const double x = d.ph.r0[i], y = d.ph.r1[i], z = d.ph.r2[i];
+        const double p0 = d.ph.p0[i], p1 = d.ph.p1[i], p2 = d.ph.p2[i], p3 = d.ph.p3[i];
+        double r, theta, phi;
+        rebin_position(ndim3, x, y, z, r, theta, phi);
+        s.weighted_r += r * w;
+        s.weighted_theta += theta * w;
+        s.weighted_phi_offset += (atan2(p2, p1) - atan2(y, x)) * RAD_TO_DEG * w;
+        s.weighted_stokes[0] += d.ph.s0[i] * w;
+        s.weighted_stokes[1] += d.ph.s1[i] * w;
+        s.weighted_stokes[2] += d.ph.s2[i] * w;
+        s.weighted_stokes[3] += d.ph.s3[i] * w;
+        s.weighted_scatt_count += d.ph.nscatt[i] * w;
+        s.total_weight += w;
+        double phi_dir = fmod(atan2(p2, p1) * RAD_TO_DEG + 360.0, 360.0);
+        double theta_dir = acos(p3 / p0) * RAD_TO_DEG;
+        s.weighted_phi_dir += phi_dir * w;
+        s.weighted_theta_dir += theta_dir * w;
+        s.weighted_energy += p0 * w;
+        if (ndim3) s.weighted_phi_pos += phi * w;
+    }
+    if (b >= p.total_bins) return;
+    mcrat_photon q;
+    memset(&q, 0, sizeof(q)); // calloc'ed in the reference (:505)
+    if (s.total_weight <= 0) {
+        q.type = 'N';
+        q.weight = 0;
+        q.nearest_block_index = -1;
+        q.recalc_properties = 0;
+    } else {
+        q.type = 'k';
+        q.weight = s.total_weight;
+        double avg_energy = s.weighted_energy / s.total_weight;
+        double avg_phi_dir = s.weighted_phi_dir / s.total_weight;
+        double avg_theta_dir = s.weighted_theta_dir / s.total_weight;
+        double avg_r = s.weighted_r / s.total_weight;
+        double avg_theta_pos = s.weighted_theta / s.total_weight;
+        q.p0 = avg_energy;
+        q.p1 = avg_energy * sin(avg_theta_dir * DEG_TO_RAD) * cos(avg_phi_dir * DEG_TO_RAD);
+        q.p2 = avg_energy * sin(avg_theta_dir * DEG_TO_RAD) * sin(avg_phi_dir * DEG_TO_RAD);
+        q.p3 = avg_energy * cos(avg_theta_dir * DEG_TO_RAD);
+        double pos_phi;
+        if (ndim3) {
+            double avg_phi_pos = s.weighted_phi_pos / s.total_weight;
+            pos_phi = avg_phi_pos * DEG_TO_RAD;
+        } else {
+            double avg_phi_offset = s.weighted_phi_offset / s.total_weight;
+            pos_phi = (avg_phi_dir - avg_phi_offset) * DEG_TO_RAD;
+        }
+        q.r0 = avg_r * sin(avg_theta_pos) * cos(pos_phi);
+        q.r1 = avg_r * sin(avg_theta_pos) * sin(pos_phi);
+        q.r2 = avg_r * cos(avg_theta_pos);
+        q.s0 = s.weighted_stokes[0] / s.total_weight;
+        q.s1 = s.weighted_stokes[1] / s.total_weight;
+        q.s2 = s.weighted_stokes[2] / s.total_weight;
+        q.s3 = s.weighted_stokes[3] / s.total_weight;
+        q.num_scatt = (int)(s.weighted_scatt_count / s.total_weight + 0.5);
+        q.nearest_block_index = 0;
+        q.recalc_properties = 1;
+    }
+    out[b] = q;
+}
+
+__device__ __forceinline__ void set_null_photon(DevCtx &d, int i) // setNullPhoton, Src/photons.c:208-251
+{
+    d.ph.type[i] = 'N';
+    d.ph.weight[i] = 0;
+    d.ph.idx[i] = -1;
+    d.ph.flags[i] = 0;
+    d.ph.p0[i] = 0; d.ph.p1[i] = 0; d.ph.p2[i] = 0; d.ph.p3[i] = 0;
+    d.ph.c0[i] = 0; d.ph.c1[i] = 0; d.ph.c2[i] = 0; d.ph.c3[i] = 0;
+    d.ph.r0[i] = 0; d.ph.r1[i] = 0; d.ph.r2[i] = 0;
+    d.ph.s0[i] = 0; d.ph.s1[i] = 0; d.ph.s2[i] = 0; d.ph.s3[i] = 0;
+    d.ph.nscatt[i] = 0;
+    d.ph.tau[i] = 0;
+}
+
+// :588-596 null every 'k' / 'c' photon, then count the null slots of each 256-slot block
+__global__ void __launch_bounds__(256) rebin_null_kernel(DevCtx d)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    int is_null = 0;
+    if (i < d.cap) {
+        const char t = d.ph.type[i];
+        if (t == 'c' || t == 'k') set_null_photon(d, i);
+        is_null = (t == 'c' || t == 'k' || t == 'N');
+    }
+    const int c = __syncthreads_count(is_null);
+    if (threadIdx.x == 0) d.prefix_block[blockIdx.x] = c;
+}
+
+__global__ void rebin_scan_kernel(DevCtx d, int nblocks, int *total_null)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int run = 0;
+        for (int b = 0; b < nblocks; ++b) {
+            int c = d.prefix_block[b];
+            d.prefix_block[b] = run;
+            run += c;
+        }
+        *total_null = run;
+    }
+}
+
+// addToPhotonList (Src/photons.c:167-205): rebinned photon k goes to the k-th null slot of the list
+__global__ void __launch_bounds__(256) rebin_place_kernel(DevCtx d, const mcrat_photon *rebinned, int total_bins)
+{
+    __shared__ int warp_off[8];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const bool is_null = (i < d.cap) && (d.ph.type[i] == 'N');
+    const unsigned ball = __ballot_sync(0xffffffffu, is_null);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) warp_off[w] = __popc(ball);
+    __syncthreads();
+    int k = d.prefix_block[blockIdx.x];
+    for (int q = 0; q < w; ++q) k += warp_off[q];
+    k += __popc(ball & ((1u << lane) - 1u));
+    if (!is_null || k >= total_bins) return;
+    const mcrat_photon p = rebinned[k];
+    if (p.type == 'N') return; // only the non-null rebinned photons are copied (:190-199)
+    d.ph.type[i] = p.type;
+    d.ph.p0[i] = p.p0; d.ph.p1[i] = p.p1; d.ph.p2[i] = p.p2; d.ph.p3[i] = p.p3;
+    d.ph.c0[i] = 0; d.ph.c1[i] = 0; d.ph.c2[i] = 0; d.ph.c3[i] = 0;
+    d.ph.r0[i] = p.r0; d.ph.r1[i] = p.r1; d.ph.r2[i] = p.r2;
+    d.ph.s0[i] = p.s0; d.ph.s1[i] = p.s1; d.ph.s2[i] = p.s2; d.ph.s3[i] = p.s3;
+    d.ph.nscatt[i] = p.num_scatt;
+    d.ph.weight[i] = p.weight;
+    d.ph.idx[i] = p.nearest_block_index;
+    d.ph.tts[i] = 0;
+    d.ph.tau[i] = 0;
+    d.ph.flags[i] = (unsigned char)(((p.weight != 0) ? F_MOVABLE : 0) | F_RECALC);
+}
+
+__global__ void rebin_count_kernel(const mcrat_photon *rebinned, int total_bins, int *null_bins)
+{
+    int c = 0;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < total_bins; b += gridDim.x * blockDim.x)
+        if (rebinned[b].type == 'N') c++;
+    if (c) atomicAdd(null_bins, c);
+}
+
+// ------------------------------------------------------------------------------------------
 // peak probes (roofline denominators measured on the same GPU, same run)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double seed)
@@ -2061,6 +2356,7 @@ struct mcrat_b200_ctx {
     int last_nb_mfp;
     int want_shards;    // sub-shards requested for the next set_photons
     int loop_mode;      // MCRAT_B200_LOOP_AUTO / _STREAMED / _PERSISTENT
+    double cs_rebin_e_perc, cs_rebin_ang, cs_rebin_ang_phi; // CYCLOSYNCHROTRON_REBIN_E_PERC / _ANG / _ANG_PHI, Src/mcrat.h:308-322
     int occ_loop256, occ_loop128; // resident blocks per SM of frame_loop_kernel<256> / <128>
     long long launches; // kernels launched through this context
     GlobalState *gs_host;          // pinned
@@ -2193,6 +2489,9 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
     ctx->last_nb_mfp = 0;
     ctx->want_shards = 1;
     ctx->loop_mode = MCRAT_B200_LOOP_AUTO;
+    ctx->cs_rebin_e_perc = 0.1;
+    ctx->cs_rebin_ang = 0.5;
+    ctx->cs_rebin_ang_phi = 10;
     ctx->occ_loop256 = ctx->occ_loop128 = 0;
     ctx->launches = 0;
     ctx->replay_dev = nullptr;
@@ -2867,6 +3166,131 @@ API int mcrat_b200_average_photon_energy(mcrat_b200_ctx *ctx, double *avg_energy
     StatPartial t;
     if (int rc = run_stats(ctx, t)) return rc;
     if (avg_energy) *avg_energy = (t.e_sum * 2.99792458e10) / t.w_sum;
+    return MCRAT_B200_OK;
+}
+
+// rebinCyclosynchCompPhotons (Src/mc_cyclosynch.h:86, Src/mc_cyclosynch.c:600-710) without the list leaving the device.
+// The host only sizes the histograms (calculate_binning_params, :325-347, and GSL's uniform ranges).
+API int mcrat_b200_rebin_cyclosynch_comp_photons(mcrat_b200_ctx *ctx, int max_photons, int *num_cyclosynch_ph_emit,
+                                                 int *scatt_cyclosynch_num_ph, int *num_null_rebin_ph)
+{
+    if (!ctx) return MCRAT_B200_ERR_ARG;
+    if (int rc = need_ready(ctx)) return rc;
+    if (int rc = need_single_shard(ctx, "rebin_cyclosynch_comp_photons")) return rc;
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (int rc = flush_pushes(ctx)) return rc;
+    DevCtx &d = ctx->d;
+    const int ndim3 = (d.dims == D_THREE);
+    // ---- phase 1: ranges ----
+    int g = grid_for(ctx, d.cap, 256, 4);
+    if (g > 1024) g = 1024;
+    RebinRange *part = nullptr;
+    CK(cudaMalloc((void **)&part, sizeof(RebinRange) * g));
+    rebin_range_kernel<<<g, 256, 0, ctx->stream>>>(d, part);
+    if (int rc = check_launch(ctx, "rebin_range_kernel")) { cudaFree(part); return rc; }
+    std::vector<RebinRange> hp(g);
+    CK(cudaMemcpyAsync(hp.data(), part, sizeof(RebinRange) * g, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(part);
+    RebinRange info = hp[0];
+    for (int k = 1; k < g; ++k) {
+        info.p0_min = std::fmin(info.p0_min, hp[k].p0_min); info.p0_max = std::fmax(info.p0_max, hp[k].p0_max);
+        info.theta_min = std::fmin(info.theta_min, hp[k].theta_min); info.theta_max = std::fmax(info.theta_max, hp[k].theta_max);
+        info.phi_min = std::fmin(info.phi_min, hp[k].phi_min); info.phi_max = std::fmax(info.phi_max, hp[k].phi_max);
+        info.valid_photon_count += hp[k].valid_photon_count; info.synch_photon_count += hp[k].synch_photon_count;
+    }
+    if (info.valid_photon_count <= 0) return fail(ctx, MCRAT_B200_ERR_STATE, "rebin: no valid photons found for rebinning (Src/mc_cyclosynch.c:613)");
+    const double log_p0_min = (info.p0_min > 0 && info.p0_max > 0) ? log10(info.p0_min) : 0.0;
+    const double log_p0_max = (info.p0_min > 0 && info.p0_max > 0) ? log10(info.p0_max) : 1.0;
+    // ---- phase 2: binning parameters, :325-347 ----
+    const double rebin_e_perc = ctx->cs_rebin_e_perc, rebin_ang = ctx->cs_rebin_ang, rebin_ang_phi = ctx->cs_rebin_ang_phi;
+    const double deg_to_rad = 3.14159265358979323846 / 180.0;
+    RebinParams p;
+    p.num_bins = (int)(rebin_e_perc * max_photons);
+    p.num_bins_theta = (int)ceil((info.theta_max - info.theta_min) / (rebin_ang * deg_to_rad));
+    p.num_bins_phi = 1;
+    if (ndim3) p.num_bins_phi = (int)ceil((info.phi_max - info.phi_min) / rebin_ang_phi);
+    p.total_bins = p.num_bins_theta * p.num_bins;
+    if (ndim3) p.total_bins *= p.num_bins_phi;
+    if (p.total_bins > max_photons) return fail(ctx, MCRAT_B200_ERR_STATE, "rebin: would create more photons than max_photons (Src/mc_cyclosynch.c:637)");
+    if (p.num_bins <= 0 || p.num_bins_theta <= 0 || p.num_bins_phi <= 0) return fail(ctx, MCRAT_B200_ERR_STATE, "rebin: invalid histogram dimensions (Src/mc_cyclosynch.c:352)");
+    // gsl_histogram2d_set_ranges_uniform with the reference's epsilons (:363-390)
+    auto uniform = [](std::vector<double> &r, int n, double lo, double hi) {
+        r.resize((size_t)n + 1);
+        for (int i = 0; i <= n; i++) {
+            double f1 = ((double)(n - i) / (double)n);
+            double f2 = ((double)i / (double)n);
+            r[(size_t)i] = f1 * lo + f2 * hi;
+        }
+    };
+    const double e_eps = (log_p0_max - log_p0_min) * 1e-6, t_eps = (info.theta_max - info.theta_min) * 1e-6;
+    const double p_eps = (info.phi_max - info.phi_min) * 1e-6;
+    std::vector<double> re, rt, rp;
+    uniform(re, p.num_bins, log_p0_min, log_p0_max + e_eps);
+    uniform(rt, p.num_bins_theta, info.theta_min, info.theta_max + t_eps);
+    if (ndim3) uniform(rp, p.num_bins_phi, info.phi_min, info.phi_max + p_eps); else rp.assign(2, 0.0);
+    double *ranges = nullptr;
+    int *bin_of = nullptr, *counters = nullptr;
+    mcrat_photon *rebinned = nullptr;
+    auto cleanup = [&]() {
+        if (ranges) cudaFree(ranges);
+        if (bin_of) cudaFree(bin_of);
+        if (counters) cudaFree(counters);
+        if (rebinned) cudaFree(rebinned);
+    };
+    const size_t nr = re.size() + rt.size() + rp.size();
+    if (cudaMalloc((void **)&ranges, nr * sizeof(double)) != cudaSuccess || cudaMalloc((void **)&bin_of, (size_t)d.cap * sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void **)&counters, 2 * sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void **)&rebinned, (size_t)p.total_bins * sizeof(mcrat_photon)) != cudaSuccess) {
+        cleanup();
+        return fail(ctx, MCRAT_B200_ERR_CUDA, "rebin: cudaMalloc");
+    }
+    cudaMemcpyAsync(ranges, re.data(), re.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(ranges + re.size(), rt.data(), rt.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(ranges + re.size() + rt.size(), rp.data(), rp.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemsetAsync(counters, 0, 2 * sizeof(int), ctx->stream);
+    p.range_e = ranges;
+    p.range_theta = ranges + re.size();
+    p.range_phi = ranges + re.size() + rt.size();
+    // ---- phases 4-5 ----
+    const int nblocks = (d.cap + 255) / 256;
+    rebin_index_kernel<<<grid_for(ctx, d.cap, 256, 8), 256, 0, ctx->stream>>>(d, p, bin_of);
+    rebin_accumulate_kernel<<<(p.total_bins + 127) / 128, 128, 0, ctx->stream>>>(d, p, bin_of, rebinned);
+    rebin_null_kernel<<<nblocks, 256, 0, ctx->stream>>>(d);
+    rebin_scan_kernel<<<1, 32, 0, ctx->stream>>>(d, nblocks, counters);
+    rebin_count_kernel<<<grid_for(ctx, p.total_bins, 256, 4), 256, 0, ctx->stream>>>(rebinned, p.total_bins, counters + 1);
+    if (int rc = check_launch(ctx, "rebin kernels", 5)) { cleanup(); return rc; }
+    int hc[2] = {0, 0};
+    cudaMemcpyAsync(hc, counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cleanup(); return fail(ctx, MCRAT_B200_ERR_CUDA, "rebin: synchronize"); }
+    if (hc[0] < p.total_bins) {
+        // addToPhotonList would have to grow the list (Src/photons.c:117-129): that is the host's job.  The
+        // 'k' / 'c' photons are already nulled, exactly as the reference has done at this point (:588-596).
+        cleanup();
+        return fail(ctx, MCRAT_B200_ERR_STATE, "rebin: fewer null slots than rebinned photons; download, grow the list (addToPhotonList) and upload");
+    }
+    rebin_place_kernel<<<nblocks, 256, 0, ctx->stream>>>(d, rebinned, p.total_bins);
+    if (int rc = check_launch(ctx, "rebin_place_kernel")) { cleanup(); return rc; }
+    const int null_count = hc[1];
+    // counters of the driver, :680-684
+    const int scatt = p.total_bins - null_count;
+    if (scatt_cyclosynch_num_ph) *scatt_cyclosynch_num_ph = scatt;
+    if (num_cyclosynch_ph_emit) *num_cyclosynch_ph_emit = p.total_bins + info.synch_photon_count - null_count;
+    if (num_null_rebin_ph) *num_null_rebin_ph = null_count;
+    if (int rc = fetch_global(ctx)) { cleanup(); return rc; }
+    ctx->gs_host->cs_scatt_num = scatt;
+    CK(cudaMemcpyAsync(ctx->d.gs, ctx->gs_host, sizeof(GlobalState), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cleanup();
+    return device_error(ctx);
+}
+
+API int mcrat_b200_set_cs_rebin_params(mcrat_b200_ctx *ctx, double rebin_e_perc, double rebin_ang_deg, double rebin_ang_phi_deg)
+{
+    if (!ctx || !(rebin_e_perc > 0) || !(rebin_ang_deg > 0) || !(rebin_ang_phi_deg > 0)) return ctx ? fail(ctx, MCRAT_B200_ERR_ARG, "set_cs_rebin_params: values must be positive") : MCRAT_B200_ERR_ARG;
+    ctx->cs_rebin_e_perc = rebin_e_perc;
+    ctx->cs_rebin_ang = rebin_ang_deg;
+    ctx->cs_rebin_ang_phi = rebin_ang_phi_deg;
     return MCRAT_B200_OK;
 }
 

@@ -69,7 +69,8 @@ EXPORTS = [
     "mcrat_b200_set_replay_uniforms", "mcrat_b200_replay_consumed", "mcrat_b200_find_containing_hydro_cell",
     "mcrat_b200_calc_mean_free_path", "mcrat_b200_photon_event", "mcrat_b200_update_photon_position",
     "mcrat_b200_ph_abs_cyclosynch", "mcrat_b200_calc_cyclosynch_r_limits", "mcrat_b200_set_cs_limits", "mcrat_b200_ph_min_max", "mcrat_b200_ph_scatt_stats",
-    "mcrat_b200_average_photon_energy", "mcrat_b200_run_frame", "mcrat_b200_set_loop_mode", "mcrat_b200_get_kernel_times",
+    "mcrat_b200_average_photon_energy", "mcrat_b200_run_frame", "mcrat_b200_set_loop_mode",
+    "mcrat_b200_rebin_cyclosynch_comp_photons", "mcrat_b200_set_cs_rebin_params", "mcrat_b200_get_kernel_times",
     "mcrat_b200_launch_count", "mcrat_b200_rescan_all", "mcrat_b200_measure_fp64_peak", "mcrat_b200_measure_hbm_peak",
 ]
 
@@ -258,6 +259,16 @@ class HotPath:
         na, ns, w = C.c_int(0), C.c_int(0), C.c_double(0)
         self._ck(self.L.mcrat_b200_ph_abs_cyclosynch(self.ctx, C.byref(na), C.byref(ns), C.byref(w)))
         return w.value, na.value, ns.value
+
+    def rebinCyclosynchCompPhotons(self, max_photons):
+        """-> (number of empty bins, num_cyclosynch_ph_emit, scatt_cyclosynch_num_ph), Src/mc_cyclosynch.c:600-710"""
+        emit, scatt, nnull = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._ck(self.L.mcrat_b200_rebin_cyclosynch_comp_photons(self.ctx, C.c_int(max_photons), C.byref(emit), C.byref(scatt),
+                                                                 C.byref(nnull)))
+        return nnull.value, emit.value, scatt.value
+
+    def set_cs_rebin_params(self, e_perc=0.1, ang=0.5, ang_phi=10.0):
+        self._ck(self.L.mcrat_b200_set_cs_rebin_params(self.ctx, C.c_double(e_perc), C.c_double(ang), C.c_double(ang_phi)))
 
     def set_cs_limits(self, max_photons, scatt_cyclosynch_num_ph=0):
         self._ck(self.L.mcrat_b200_set_cs_limits(self.ctx, C.c_int(max_photons), C.c_int(scatt_cyclosynch_num_ph)))

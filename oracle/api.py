@@ -484,6 +484,13 @@ class RefLib:
                                                C.c_int(max_photons), C.c_double(theta_min), C.c_double(theta_max),
                                                self.hydro, rng, C.c_int(single), C.c_int(scatt_idx))
 
+    def rebin_cyclosynch_comp_photons(self, max_photons, theta_min=0.0, theta_max=0.0, rng=None):
+        """rebinCyclosynchCompPhotons (Src/mc_cyclosynch.c:600-710) -> (return value, num_cyclosynch_ph_emit, scatt_cyclosynch_num_ph)"""
+        emit, scatt = C.c_int(0), C.c_int(0)
+        rc = self.L.ref_rebinCyclosynchCompPhotons(self.list, C.byref(emit), C.byref(scatt), C.c_int(max_photons),
+                                                   C.c_double(theta_min), C.c_double(theta_max), rng)
+        return rc, emit.value, scatt.value
+
     def photon_injection(self, rng, r_inj, ph_weight, min_photons, max_photons, spect, theta_min, theta_max):
         if not self.list:
             self.list = C.c_void_p(self.L.ref_list_new(None, C.c_int(0)))

@@ -384,3 +384,73 @@ def test_calc_cyclosynch_r_limits():
         a = hp.calcCyclosynchRLimits(205, 200, 5.0, 1e12, which)
         b = o.mc_cyclosynch_r_limits(C.c_int(205), C.c_int(200), C.c_double(5.0), C.c_double(1e12), which.encode())
         assert a == b
+
+
+@pytest.mark.parametrize("refname,wl", [("c4_3d_sph_cs", "C4"), ("g_2d_cyl_cs", "C2")])
+def test_cyclosynchrotron_rebin_on_the_device(refname, wl):
+    """K8 vs the reference's own rebinCyclosynchCompPhotons (Src/mc_cyclosynch.c:600-710): same bins, same
+    placement into the list's null slots (addToPhotonList), weighted means to 1e-12."""
+    if not api.ref_available(refname):
+        pytest.skip("reference build %s not available" % refname)
+    cfg = _cfg_from_ref(refname)
+    _, hydro, photons, frame = synth.workload(wl, scale=1.0 / 32, n_photons=20000, seed=77)
+    rng = np.random.default_rng(5)
+    n = photons.size
+    # a list in the middle of a CS run: injected, comptonised, unabsorbed, pool and null photons
+    kinds = rng.choice(np.frombuffer(b"ikcpN", dtype="S1"), n, p=[0.15, 0.35, 0.2, 0.1, 0.2])
+    photons["type"] = kinds
+    photons["num_scatt"] = rng.integers(0, 40, n)
+    photons["weight"] = 10 ** rng.uniform(48, 50, n)
+    f = 10 ** rng.uniform(-2, 2, n)
+    for k in ("p0", "p1", "p2", "p3"):
+        photons[k] *= f
+    ang = rng.uniform(0, 2 * np.pi, n)
+    photons["s1"], photons["s2"] = 0.3 * np.cos(ang), 0.3 * np.sin(ang)
+    # total_bins = 0.1 max_photons x n_theta (x n_phi) must not exceed max_photons (Src/mc_cyclosynch.c:637): the
+    # photons are squeezed into an 18-degree wedge in azimuth, and only those inside a 1.7-degree cone take part (the
+    # others become 'injected' photons, which the rebin leaves alone)
+    rho, phi = np.hypot(photons["r0"], photons["r1"]), np.arctan2(photons["r1"], photons["r0"]) % (2 * np.pi)
+    photons["r0"], photons["r1"] = rho * np.cos(phi / 20.0), rho * np.sin(phi / 20.0)
+    rr = np.sqrt(photons["r0"] ** 2 + photons["r1"] ** 2 + photons["r2"] ** 2)
+    th = np.degrees(np.arccos(photons["r2"] / rr))
+    inside = th < th.min() + 1.7
+    kinds = np.where(~inside & ((kinds == b"k") | (kinds == b"c")), b"i", kinds)
+    photons["type"] = kinds
+    null = kinds == b"N"
+    for k in photons.dtype.names:
+        if k != "type":
+            photons[k][null] = 0
+    photons["nearest_block_index"][null] = -1
+    max_photons = 3000
+    ref = api.RefLib(refname)
+    ref.set_hydro(hydro)
+    ref.set_photons(photons)
+    rc, emit, scatt = ref.rebin_cyclosynch_comp_photons(max_photons)
+    want = ref.photons()
+    assert rc >= 0, "the reference refused to rebin this list"
+    hp = HotPath(cfg, seed=1)
+    hp.set_hydro(hydro)
+    hp.set_photons(photons)
+    nnull, emit_d, scatt_d = hp.rebinCyclosynchCompPhotons(max_photons)
+    got = hp.get_photons()
+    assert (nnull, emit_d, scatt_d) == (rc, emit, scatt)
+    assert got.size == want.size
+    assert np.array_equal(got["type"], want["type"]), np.nonzero(got["type"] != want["type"])[0][:10]
+    assert np.array_equal(got["nearest_block_index"], want["nearest_block_index"])
+    assert np.array_equal(got["num_scatt"], want["num_scatt"])
+    assert np.array_equal(got["recalc_properties"] != 0, want["recalc_properties"] != 0)
+    new = want["type"] == b"k"
+    assert new.sum() == scatt and new.sum() > 50
+    scale = dict(p0="p0", p1="p0", p2="p0", p3="p0", r0=None, r1=None, r2=None, s0=1, s1=1, s2=1, s3=1, weight="weight")
+    rn = np.sqrt(want["r0"] ** 2 + want["r1"] ** 2 + want["r2"] ** 2)
+    worst = {}
+    for k, sc in scale.items():
+        den = rn if sc is None else (np.ones(n) if sc == 1 else np.abs(want[sc]))
+        err = np.abs(got[k] - want[k])[new] / np.maximum(den[new], 1e-300)
+        worst[k] = float(err.max())
+        assert err.max() < 1e-12, (k, err.max())
+    # everything that was not rebinned is untouched
+    old = ~new
+    for k in ("p0", "r0", "weight", "s1", "comv_p0"):
+        assert np.array_equal(got[k][old], want[k][old]), k
+    print(refname, "rebinned", int(new.sum()), "photons; worst relative errors", {k: "%.1e" % v for k, v in worst.items()})
