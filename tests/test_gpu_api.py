@@ -454,3 +454,64 @@ def test_cyclosynchrotron_rebin_on_the_device(refname, wl):
     for k in ("p0", "r0", "weight", "s1", "comv_p0"):
         assert np.array_equal(got[k][old], want[k][old]), k
     print(refname, "rebinned", int(new.sum()), "photons; worst relative errors", {k: "%.1e" % v for k, v in worst.items()})
+
+
+def test_c_host_drives_frames_and_writes_the_reference_output(tmp_path):
+    """examples/host_frame.c: a C program (gcc, no Python, no torch) reads mcrat_input.h + mc.par, runs two hydro
+    frames through the C ABI and writes mc_proc_0.h5 / mcdata_<frame>.h5; the same calls through ctypes must give
+    the same photons, and the files must hold them under the reference's dataset names."""
+    import os
+    import subprocess
+    from mcrat_b200 import io as mio
+    from mcrat_b200.lib import CSRC, HYDRO_FIELDS
+    from h5spec import H5File
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_frame")
+    subprocess.check_call(["gcc", "-O2", "-std=gnu11", os.path.join(root, "examples", "host_frame.c"), "-I" + os.path.join(root, "include"),
+                           "-L" + CSRC, "-lmcrat_b200", "-lmcrat_b200_io", "-Wl,-rpath," + CSRC, "-o", exe])
+    cfg, hydro, photons, frame = synth.workload("C2", scale=1.0 / 16, n_photons=1500, seed=61)
+    d = str(tmp_path)
+    open(os.path.join(d, "mcrat_input.h"), "w").write(
+        '#define SIMULATION_TYPE SCIENCE\n#define FILEPATH "./"\n#define FILEROOT "synthetic_"\n#define MC_PATH "./"\n'
+        "#define SIM_SWITCH FLASH\n#define GEOMETRY CYLINDRICAL\n#define DIMENSIONS TWO\n#define HYDRO_L_SCALE 1.0\n"
+        "#define HYDRO_D_SCALE 1.0\n#define STOKES_SWITCH ON\n#define COMV_SWITCH ON\n#define SAVE_TYPE ON\n"
+        '#define CYCLOSYNCHROTRON_SWITCH OFF\n#define MCPAR "mc.par"\n')
+    frame0 = 10
+    time0 = frame0 / 5.0
+    open(os.path.join(d, "mc.par"), "w").write(
+        "[Hydro/MHD Simulation Block]\n\n5.  # fps\n3000 # last frame\n%r %r # r0\n%r %r # r1\n0 0 # r2\n\n"
+        "[MCRaT Injection Angles Block]\n\n0. #\n6. #\n1. #\n%d #\n2 #\n2e12 #\n\n[MCRaT Photon Block]\n\nb #\n1000 #\n5000 #\n\n"
+        "[Initialization/Continuation Block]\n\ni #\n" % (hydro["r0_domain"][0], hydro["r0_domain"][1], hydro["r1_domain"][0],
+                                                           hydro["r1_domain"][1], frame0))
+    n = int(hydro["num_elements"])
+    with open(os.path.join(d, "hydro.bin"), "wb") as f:
+        f.write(np.array([n, 0], dtype=np.int32).tobytes())
+        for name in HYDRO_FIELDS:
+            f.write(np.ascontiguousarray(hydro.get(name, np.zeros(n)), dtype=np.float64).tobytes())
+    with open(os.path.join(d, "photons.bin"), "wb") as f:
+        f.write(np.array([photons.size, 0], dtype=np.int32).tobytes())
+        f.write(photons.tobytes())
+    out = subprocess.check_output([exe, d, "2", "150"], text=True)
+    lines = [l.split() for l in out.strip().splitlines()]
+    assert len(lines) == 2 and lines[0][1] == str(frame0) and lines[1][1] == str(frame0 + 1)
+    # the same two frames through the ctypes binding
+    hp = HotPath(cfg, seed=20261018, shard=0)
+    hp.set_photons(photons)
+    t = time0
+    for k, fr in enumerate((frame0, frame0 + 1)):
+        hp.set_hydro(hydro)
+        st = hp.run_frame(t, (fr + 1) / 5.0 - t, max_iters=150, switch=1)
+        t = st["time_now"]
+        got = hp.get_photons()
+        assert int(lines[k][3]) == st["iterations"] and int(lines[k][5]) == st["scatterings"]
+        assert float(lines[k][9]) == st["time_now"]
+        live = got[got["weight"] != 0]
+        tree = H5File(os.path.join(d, "mcdata_%d.h5" % fr)).tree()
+        proc = H5File(os.path.join(d, "mc_proc_0.h5")).tree()[str(fr)]
+        for name, field in (("P0", "p0"), ("P3", "p3"), ("COMV_P0", "comv_p0"), ("R0", "r0"), ("R2", "r2"), ("S1", "s1"),
+                            ("NS", "num_scatt"), ("PW", "weight")):
+            assert np.array_equal(tree[name], live[field].astype(np.float64)), (fr, name)
+            assert np.array_equal(proc[name], tree[name])
+        assert np.array_equal(tree["PT"], np.frombuffer(live["type"].tobytes(), dtype=np.int8))
+        assert sorted(tree) == sorted(["P0", "P1", "P2", "P3", "COMV_P0", "COMV_P1", "COMV_P2", "COMV_P3", "R0", "R1", "R2",
+                                       "S0", "S1", "S2", "S3", "NS", "PW", "PT"])
