@@ -330,12 +330,21 @@ def main():
                                                    "v0", "v1", "v2", "dens", "dens_lab", "pres", "temp", "gamma",
                                                    "B0", "B1", "B2")) + host_ph.numel()
     d2h = host_ph.numel()
+    # the hydro frame sits in pinned host memory, as a reader that fills the device-bound arrays directly would leave it
+    from mcrat_b200.lib import HYDRO_FIELDS
+    hydro_pinned = dict(hydro)
+    pinned_keep = []
+    for f in HYDRO_FIELDS:
+        if f in hydro:
+            t = torch.from_numpy(np.ascontiguousarray(hydro[f], dtype=np.float64)).pin_memory()
+            pinned_keep.append(t)
+            hydro_pinned[f] = t.numpy()
     e2e_scatt = 0
     for k in range(1 + args.steps):
         if k == 1:
             barrier()
             t0 = time.perf_counter()
-        hp.set_hydro(hydro)                                   # the frame the driver just read (Src/mcrat.c:721)
+        hp.set_hydro(hydro_pinned)                            # the frame the driver just read (Src/mcrat.c:721)
         hp.set_photons_ptr(host_ph.data_ptr(), photons.size)  # host list -> device
         st = hp.run_frame(time_now, dt_frame, max_iters=args.iters, switch=1)
         hp.get_photons_ptr(host_ph.data_ptr(), photons.size)  # device -> host list (checkpoint / mc_proc output)

@@ -1653,6 +1653,12 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -1752,13 +1758,15 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
         auto wait = [&]() {
             if (threadIdx.x == 0) {
                 unsigned spins = 0;
-                while (ld_acquire_u32(&gst.gen) < phase) {
+                // poll with relaxed loads (L2-coherent, no L1 invalidation per poll); one acquire once the word moved
+                while (ld_relaxed_u32(&gst.gen) < phase) {
                     __nanosleep(40);
                     if (++spins > (1u << 24)) { // ~1 s: never in a healthy run; refuse to hang the GPU
                         gs.error = MCRAT_B200_ERR_STATE;
                         break;
                     }
                 }
+                (void)ld_acquire_u32(&gst.gen);
             }
             __syncthreads();
             pull();
