@@ -3303,6 +3303,7 @@ API int mcrat_b200_set_cs_rebin_params(mcrat_b200_ctx *ctx, double rebin_e_perc,
 }
 
 // ---- the device-resident frame loop, Src/mcrat.c:761-851 ---------------------------------------------
+constexpr int MCRAT_B200_LOOP_FALLBACK = 1000; // internal: cooperative launch refused, use the streamed loop
 constexpr int PERSISTENT_MAX_PHOTONS = 1 << 21; // above this the pass is HBM-bound and wants the leaner pass_kernel
 
 __global__ void reset_protocol_kernel(DevCtx d)
@@ -3351,12 +3352,18 @@ static int launch_frame_loop(mcrat_b200_ctx *ctx)
     frame_loop_grid(ctx, threads, bps, grid);
     if (grid < 1) return fail(ctx, MCRAT_B200_ERR_STATE, "frame_loop_kernel does not fit on this device");
     void *args[2] = {(void *)&ctx->d, (void *)&bps};
+    if (getenv("MCRAT_B200_REFUSE_COOPERATIVE")) return MCRAT_B200_LOOP_FALLBACK; // test hook for the hand-over below
     Timed t(ctx, KC_EVENT);
     cudaError_t e;
     if (threads == 128)
         e = cudaLaunchCooperativeKernel((const void *)frame_loop_kernel<128>, dim3(grid), dim3(128), args, 0, ctx->stream);
     else
         e = cudaLaunchCooperativeKernel((const void *)frame_loop_kernel<256>, dim3(grid), dim3(256), args, 0, ctx->stream);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported || e == cudaErrorLaunchOutOfResources) {
+        // the device cannot hold the grid (MPS share, another tenant, no cooperative launch): the streamed loop needs nothing special
+        (void)cudaGetLastError();
+        return MCRAT_B200_LOOP_FALLBACK;
+    }
     if (e != cudaSuccess) {
         ctx->err = std::string("frame_loop_kernel: ") + cudaGetErrorString(e);
         return MCRAT_B200_ERR_CUDA;
@@ -3425,9 +3432,10 @@ API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remain
         sw = 0; // Src/mcrat.c:773
         return MCRAT_B200_OK;
     };
-    const bool persistent = fused && !ctx->cfg.profile &&
-                            (ctx->loop_mode == MCRAT_B200_LOOP_PERSISTENT ||
-                             (ctx->loop_mode == MCRAT_B200_LOOP_AUTO && ctx->d.cap <= PERSISTENT_MAX_PHOTONS));
+    bool persistent = fused && !ctx->cfg.profile &&
+                      (ctx->loop_mode == MCRAT_B200_LOOP_PERSISTENT ||
+                       (ctx->loop_mode == MCRAT_B200_LOOP_AUTO && ctx->d.cap <= PERSISTENT_MAX_PHOTONS));
+    long long streamed_done = 0; // iterations already launched when the persistent loop hands over for good
     if (persistent) {
         // the first iteration of a new hydro frame re-locates every photon: that is K1's job
         long long launched = 0;
@@ -3436,7 +3444,13 @@ API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remain
             launched++;
         }
         for (;;) {
-            if (int rc = launch_frame_loop(ctx)) return rc;
+            if (int rc = launch_frame_loop(ctx)) {
+                if (rc != MCRAT_B200_LOOP_FALLBACK) return rc;
+                ctx->loop_mode = MCRAT_B200_LOOP_STREAMED; // for the rest of this context's life
+                persistent = false;
+                streamed_done = launched;
+                break;
+            }
             if (int rc = fetch_state(ctx)) return rc;
             if (ctx->gs_host->error) break;
             bool heavy = false, running = false;
@@ -3456,10 +3470,11 @@ API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remain
             if (int rc = reset_protocol(ctx)) return rc;
             (void)launched;
         }
-    } else {
+    }
+    if (!persistent) {
         // iterations are enqueued in batches; kernels of a shard past its stop condition return at once
         int batch = 1;
-        long long launched = 0;
+        long long launched = streamed_done;
         for (;;) {
             for (int b = 0; b < batch; ++b) {
                 if (int rc = streamed_iteration()) return rc;

@@ -178,3 +178,24 @@ def test_persistent_loop_runs_a_frame_to_its_end():
     assert res["streamed"][0]["scatterings"] == st["scatterings"] and res["streamed"][0]["iterations"] == st["iterations"]
     for f in ph.dtype.names:
         assert np.array_equal(ph[f], res["streamed"][1][f], equal_nan=(ph.dtype[f].kind == "f")), f
+
+
+def test_refused_cooperative_launch_falls_back_to_the_streamed_loop(monkeypatch):
+    """If the device cannot hold the persistent grid (MPS share, no cooperative launch) the frame still runs --
+    streamed, same photons -- and the context stays on the streamed loop."""
+    cfg, hydro, photons, frame = synth.workload("C2", scale=1.0 / 16, n_photons=1200, seed=47)
+    out = []
+    for refuse in (False, True):
+        if refuse:
+            monkeypatch.setenv("MCRAT_B200_REFUSE_COOPERATIVE", "1")
+        hp = HotPath(cfg, seed=3, num_shards=3, loop_mode="persistent")
+        hp.set_hydro(hydro)
+        hp.set_photons(photons)
+        st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=90, switch=1)
+        out.append((st, hp.get_photons(), hp.launch_count()))
+        hp.close()
+    (sa, pa, la), (sb, pb, lb) = out
+    assert sa["iterations"] == sb["iterations"] == 90 and sa["scatterings"] == sb["scatterings"]
+    assert lb > la + 200  # four launches per iteration instead of one per frame
+    for f in pa.dtype.names:
+        assert np.array_equal(pa[f], pb[f], equal_nan=(pa.dtype[f].kind == "f")), f
