@@ -359,6 +359,36 @@ def workload(name, scale=1.0, n_photons=None, seed=1234):
         n = n_photons or 100000
         ph = make_photons(h, n, (1e12 - 0.5 * C_LIGHT / 5, 1e12 + 0.5 * C_LIGHT / 5), (1e-3, np.deg2rad(10.0)), seed)
         frame = dict(fps=5.0, time_now=1e12 / C_LIGHT)
+    elif name in ("G25", "G2S", "G3C", "G3P"):
+        # geometry coverage (Src/geometry.c:15-253): the other coordinate systems the reference supports
+        stokes = 0 if name == "G3C" else 1
+        if name == "G25":    # 2.5-D cylindrical (PLUTO): (R, z) grid with an azimuthal velocity component
+            dims, geom = TWO_POINT_FIVE, CYLINDRICAL
+            n0 = n1 = max(8, int(512 * scale))
+            h = make_grid(dims, geom, (n0, n1), ((0.0, 2.5e11), (1.0e12, 3.0e12)))
+        elif name == "G2S":  # 2-D spherical (PLUTO-CHOMBO): (r, theta)
+            dims, geom = TWO, SPHERICAL
+            n0, n1 = max(8, int(512 * scale)), max(8, int(256 * scale))
+            h = make_grid(dims, geom, (n0, n1), ((1.0e12, 3.0e12), (0.0, np.pi / 16)))
+        elif name == "G3C":  # 3-D Cartesian (PLUTO): (x, y, z) box around the axis
+            dims, geom = THREE, CARTESIAN
+            n0 = n1 = max(4, int(64 * scale))
+            n2 = max(4, int(256 * scale))
+            h = make_grid(dims, geom, (n0, n1, n2), ((-2.5e11, 2.5e11), (-2.5e11, 2.5e11), (1.0e12, 3.0e12)))
+        else:                # 3-D polar (PLUTO): (R, phi, z)
+            dims, geom = THREE, POLAR
+            n0, n1, n2 = max(4, int(128 * scale)), max(4, int(32 * scale)), max(4, int(256 * scale))
+            h = make_grid(dims, geom, (n0, n1, n2), ((0.0, 2.5e11), (0.0, 2 * np.pi), (1.0e12, 3.0e12)))
+        structured_jet(h, theta_j=0.05)
+        if name == "G25":  # part of the speed goes into rotation about the axis
+            vel = np.sqrt(h["v0"] ** 2 + h["v1"] ** 2)
+            h["v2"] = 0.02 * vel
+            h["v0"] *= np.sqrt(1 - 0.02 ** 2)
+            h["v1"] *= np.sqrt(1 - 0.02 ** 2)
+        cfg = dict(dimensions=dims, geometry=geom, stokes=stokes, tau_calculation=1, cyclosynch=0, b_field_calc=1, epsilon_b=0.5)
+        n = n_photons or 10000
+        ph = make_photons(h, n, (2e12 - 0.5 * C_LIGHT / 5, 2e12 + 0.5 * C_LIGHT / 5), (1e-3, np.deg2rad(5.0)), seed)
+        frame = dict(fps=5.0, time_now=2e12 / C_LIGHT)
     else:
         raise ValueError(name)
     h["fps"] = frame["fps"]

@@ -15,6 +15,11 @@ CASES = [
     ("C1", "c1_2d_cart", 1.0 / 8, 400, 300),
     ("C2", "c2_2d_cyl_stokes", 1.0 / 16, 400, 300),
     ("C5", "c5_3d_sph", 1.0 / 8, 400, 300),
+    # the other coordinate systems of Src/geometry.c: 2.5-D cylindrical, 2-D spherical, 3-D Cartesian, 3-D polar
+    ("G25", "g_25d_cyl", 1.0 / 8, 400, 300),
+    ("G2S", "g_2d_sph", 1.0 / 8, 400, 300),
+    ("G3C", "g_3d_cart", 1.0 / 4, 400, 300),
+    ("G3P", "g_3d_polar", 1.0 / 4, 400, 300),
 ]
 
 

@@ -15,6 +15,11 @@ FRAME_CASES = [
     ("C2", "c2_2d_cyl_stokes", 1.0 / 32, 200, 150),
     ("C3", "c3_2d_cyl_table", 1.0 / 32, 150, 100),
     ("C5", "c5_3d_sph", 1.0 / 8, 200, 150),
+    # the remaining coordinate systems of Src/geometry.c
+    ("G25", "g_25d_cyl", 1.0 / 8, 200, 150),
+    ("G2S", "g_2d_sph", 1.0 / 8, 200, 150),
+    ("G3C", "g_3d_cart", 1.0 / 4, 200, 150),
+    ("G3P", "g_3d_polar", 1.0 / 4, 200, 150),
 ]
 
 
