@@ -236,3 +236,85 @@ def test_many_frames_in_one_file(tmp_path):
     tree = f.tree()
     assert len(tree) == 150 and f.leaf_k >= 75
     assert np.array_equal(tree["349"]["PW"], _expect(ph, "PW"))
+
+
+def _hand_built_chunked_file(path, values, chunk):
+    """A minimal HDF5 file with one 1-D *chunked*, extendible F64 dataset "PW" at the root, laid out by hand from the
+    format specification (layout message v3 class 2, B-tree v1 node type 1) -- the storage the reference's per-rank
+    files use (H5Pset_chunk + H5S_UNLIMITED, Src/mcrat_io.c:253-262)."""
+    import struct
+    UNDEF = 0xFFFFFFFFFFFFFFFF
+    n = len(values)
+    nchunks = (n + chunk - 1) // chunk
+    K = 4
+    # addresses
+    a_root_ohdr = 96
+    a_heap = a_root_ohdr + 16 + 24 + 8
+    a_heap_data = a_heap + 32
+    heap_size = 8 + 8 + 32
+    a_btree = a_heap_data + heap_size
+    a_snod = a_btree + 24 + 33 * 8 + 32 * 8
+    a_dset = a_snod + 8 + 2 * K * 40
+    dset_msgs = (8 + 8) + (8 + 24) + (8 + 24) + (8 + 24)
+    a_cbtree = a_dset + 16 + dset_msgs
+    a_chunks = a_cbtree + 24 + (2 * 32 + 1) * 24 + 2 * 32 * 8
+    eof = a_chunks + nchunks * chunk * 8
+    b = bytearray(eof)
+    b[0:8] = b"\x89HDF\r\n\x1a\n"
+    b[13], b[14] = 8, 8
+    struct.pack_into("<HH", b, 16, K, 16)
+    struct.pack_into("<4Q", b, 24, 0, UNDEF, eof, UNDEF)
+    struct.pack_into("<QQIIQQ", b, 56, 0, a_root_ohdr, 1, 0, a_btree, a_heap)
+    # root group
+    struct.pack_into("<BBHII", b, a_root_ohdr, 1, 0, 2, 1, 32)
+    struct.pack_into("<HHB3xQQ", b, a_root_ohdr + 16, 0x11, 16, 0, a_btree, a_heap)
+    b[a_heap:a_heap + 4] = b"HEAP"
+    struct.pack_into("<QQQ", b, a_heap + 8, heap_size, 16, a_heap_data)
+    b[a_heap_data + 8:a_heap_data + 10] = b"PW"
+    struct.pack_into("<QQ", b, a_heap_data + 16, 1, 32)
+    b[a_btree:a_btree + 4] = b"TREE"
+    struct.pack_into("<BBHQQ", b, a_btree + 4, 0, 0, 1, UNDEF, UNDEF)
+    struct.pack_into("<QQQ", b, a_btree + 24, 0, a_snod, 8)
+    b[a_snod:a_snod + 4] = b"SNOD"
+    struct.pack_into("<BBH", b, a_snod + 4, 1, 0, 1)
+    struct.pack_into("<QQII", b, a_snod + 8, 8, a_dset, 0, 0)
+    # dataset header: fill value, datatype, dataspace (with maximum = unlimited), chunked layout
+    struct.pack_into("<BBHII", b, a_dset, 1, 0, 4, 1, dset_msgs)
+    m = a_dset + 16
+    struct.pack_into("<HHB3x", b, m, 0x05, 8, 1)
+    b[m + 8:m + 12] = bytes([1, 1, 2, 1])
+    m += 16
+    struct.pack_into("<HHB3x", b, m, 0x03, 24, 1)
+    b[m + 8:m + 12] = bytes([0x11, 0x20, 0x3F, 0])
+    struct.pack_into("<IHHBBBBI", b, m + 12, 8, 0, 64, 52, 11, 0, 52, 1023)
+    m += 32
+    struct.pack_into("<HHB3x", b, m, 0x01, 24, 0)
+    b[m + 8:m + 11] = bytes([1, 1, 1])                      # version 1, rank 1, flags: maximum dimensions present
+    struct.pack_into("<QQ", b, m + 16, n, UNDEF)
+    m += 32
+    struct.pack_into("<HHB3x", b, m, 0x08, 24, 0)
+    b[m + 8:m + 11] = bytes([3, 2, 2])                      # version 3, chunked, dimensionality = rank + 1
+    struct.pack_into("<QII", b, m + 11, a_cbtree, chunk, 8)  # B-tree address, chunk dims (elements), element size
+    # chunk B-tree: node type 1, leaf
+    b[a_cbtree:a_cbtree + 4] = b"TREE"
+    struct.pack_into("<BBHQQ", b, a_cbtree + 4, 1, 0, nchunks, UNDEF, UNDEF)
+    p = a_cbtree + 24
+    data = np.zeros(nchunks * chunk)
+    data[:n] = values
+    for c in range(nchunks):
+        struct.pack_into("<IIQQ", b, p, chunk * 8, 0, c * chunk, 0)  # key: chunk bytes, filter mask, offsets (dim 0, element)
+        struct.pack_into("<Q", b, p + 24, a_chunks + c * chunk * 8)
+        p += 32
+    struct.pack_into("<IIQQ", b, p, 0, 0, nchunks * chunk, 0)        # final key
+    b[a_chunks:eof] = data.astype("<f8").tobytes()
+    open(path, "wb").write(bytes(b))
+
+
+def test_reader_takes_chunked_extendible_datasets(tmp_path):
+    """The reference's own mc_proc files store every dataset chunked (Src/mcrat_io.c:253-262); the C reader must take
+    that layout (un-filtered), including a last chunk that extends past the dataset."""
+    vals = np.linspace(1e48, 3e50, 1234)
+    path = str(tmp_path / "chunked.h5")
+    _hand_built_chunked_file(path, vals, chunk=500)
+    assert mio.h5_list(path) == ["PW"]
+    assert np.array_equal(mio.h5_read(path, "PW"), vals)
