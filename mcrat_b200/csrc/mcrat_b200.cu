@@ -2948,10 +2948,16 @@ static int launch_locate(mcrat_b200_ctx *ctx, int sw, int &parity_out)
     if (ctx->cfg.scan_index) {
         Timed t(ctx, KC_SCAN);
         // one warp per photon
-        const int g = (sw == 1) ? grid_for(ctx, ctx->d.cap > (INT_MAX >> 5) ? INT_MAX : ctx->d.cap * 32, 128, 16) : 32;
+        // one warp per photon; in a steady-state iteration a few in every 10^4 photons change cell
+        int g = grid_for(ctx, ctx->d.cap > (INT_MAX >> 5) ? INT_MAX : ctx->d.cap * 32, 128, 16);
+        if (sw == 0) {
+            g = ctx->d.cap / 2048;
+            if (g < 32) g = 32;
+            if (g > ctx->num_sms * 16) g = ctx->num_sms * 16;
+        }
         scan_index_kernel<<<g, 128, 0, ctx->stream>>>(ctx->d, parity);
         if (int rc = check_launch(ctx, "scan_index_kernel")) return rc;
-        nb_fin = (sw == 1) ? grid_for(ctx, ctx->d.cap, FIN_THREADS, 8) : 8;
+        nb_fin = (sw == 1) ? grid_for(ctx, ctx->d.cap, FIN_THREADS, 8) : (g / 4 < 8 ? 8 : g / 4);
     } else if (sw == 1) {
         if (int rc = launch_scan_full(ctx, parity, ctx->d.cap)) return rc;
         nb_fin = grid_for(ctx, ctx->d.cap, FIN_THREADS, 8);
