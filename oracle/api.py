@@ -234,6 +234,15 @@ class Oracle:
             self.list = McPhotonList()
             self.L.mc_list_init(C.byref(self.list))
         self.L.mc_list_set(C.byref(self.list), ph.ctypes.data_as(C.c_void_p), C.c_int(ph.size))
+        # setPhotonList (Src/photons.c:83-108) leaves num_photons at n even if the array holds null photons; the
+        # driver never gives it such an array, the tests do: restore the invariant verifyPhotonNum checks
+        self.list.num_photons = ph.size - self.list.num_null_photons
+
+    def rebin_cyclosynch_comp_photons(self, max_photons):
+        """-> (return value, num_cyclosynch_ph_emit, scatt_cyclosynch_num_ph), Src/mc_cyclosynch.c:600-710"""
+        emit, scatt = C.c_int(0), C.c_int(0)
+        rc = self.L.mc_rebin_cyclosynch_comp_photons(self.o, C.byref(self.list), C.byref(emit), C.byref(scatt), C.c_int(max_photons))
+        return rc, emit.value, scatt.value
 
     def photons(self):
         n = self.list.list_capacity

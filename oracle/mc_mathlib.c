@@ -623,3 +623,40 @@ int mc_integrate_adaptive(mc_quad_fn f, void *params, double a, double b, double
     free(s);
     return status;
 }
+
+/* ---- gsl_histogram: uniform ranges and find ------------------------------------------------ */
+void mc_hist_uniform_ranges(double *range, size_t n, double xmin, double xmax)
+{
+    size_t i;
+    for (i = 0; i <= n; i++) {
+        double f1 = ((double)(n - i) / (double)n);
+        double f2 = ((double)i / (double)n);
+        range[i] = f1 * xmin + f2 * xmax;
+    }
+}
+
+int mc_hist_find(size_t n, const double *range, double x, size_t *i)
+{
+    size_t i_linear, lower, upper, mid;
+    if (x < range[0]) return 1;
+    if (x >= range[n]) return 1;
+    {
+        double u = (x - range[0]) / (range[n] - range[0]);
+        i_linear = (size_t)(u * n);
+    }
+    if (i_linear < n && x >= range[i_linear] && x < range[i_linear + 1]) {
+        *i = i_linear;
+        return 0;
+    }
+    upper = n;
+    lower = 0;
+    while (upper - lower > 1) {
+        mid = (upper + lower) / 2;
+        if (x >= range[mid])
+            lower = mid;
+        else
+            upper = mid;
+    }
+    *i = lower;
+    return 0;
+}

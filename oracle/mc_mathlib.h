@@ -120,4 +120,9 @@ int mc_integrate_adaptive(mc_quad_fn f, void *params, double a, double b, double
 #ifdef __cplusplus
 }
 #endif
+/* gsl_histogram2d_set_ranges_uniform's edges (histogram/init.c make_uniform) and gsl_histogram find()
+ * (histogram/find.c: linear guess, then bisection); find returns 0 and writes *i on success, 1 outside the range */
+void mc_hist_uniform_ranges(double *range, size_t n, double xmin, double xmax);
+int mc_hist_find(size_t n, const double *range, double x, size_t *i);
+
 #endif

@@ -1458,9 +1458,188 @@ double mc_ph_abs_cyclosynch(mc_oracle *o, mc_photon_list *l, int *num_abs_ph, in
 }
 
 /* ============================================================================ */
+/* rebinCyclosynchCompPhotons, Src/mc_cyclosynch.c:244-710                          */
+/* ============================================================================ */
+#define MC_RAD_TO_DEG (180.0 / M_PI) /* Src/mcrat.h:80-81 */
+#define MC_DEG_TO_RAD (M_PI / 180.0)
+#define MC_REBIN_ANG 0.5             /* CYCLOSYNCHROTRON_REBIN_ANG, Src/mcrat.h:313-316 */
+#define MC_REBIN_ANG_PHI 10.0        /* CYCLOSYNCHROTRON_REBIN_ANG_PHI, :318-321 */
+
+/* calculate_photon_position, :246-270 */
+static void rebin_position(const mc_oracle *o, const mc_photon *ph, double *r, double *theta, double *phi)
+{
+    double x = ph->r0, y = ph->r1, z = ph->r2;
+    *r = sqrt(x * x + y * y + z * z);
+    if (*r < DBL_MIN) {
+        *theta = 0.0;
+        *phi = 0.0;
+    } else {
+        *theta = acos(z / *r);
+        if (o->cfg.dimensions == MC_THREE) {
+            double phi_rad = atan2(y, x);
+            *phi = fmod(phi_rad * MC_RAD_TO_DEG + 360.0, 360.0);
+        } else {
+            *phi = 0;
+        }
+    }
+}
+
+static int rebin_eligible(const mc_photon *ph)
+{
+    return (ph->type != MC_NULL_PHOTON) && (ph->type != MC_CS_POOL_PHOTON) && (ph->type != MC_INJECTED_PHOTON);
+}
+
+int mc_rebin_cyclosynch_comp_photons(mc_oracle *o, mc_photon_list *l, int *num_cyclosynch_ph_emit,
+                                     int *scatt_cyclosynch_num_ph, int max_photons)
+{
+    const int three = (o->cfg.dimensions == MC_THREE);
+    int i, valid = 0, synch = 0, null_count = 0;
+    double p0_min = DBL_MAX, p0_max = 0.0, th_min = DBL_MAX, th_max = 0.0, ph_min = DBL_MAX, ph_max = 0.0;
+    /* collect_photon_statistics, :273-322 */
+    for (i = 0; i < l->list_capacity; i++) {
+        const mc_photon *ph = &l->photons[i];
+        if (rebin_eligible(ph)) {
+            double r, theta, phi = 0.0;
+            if (ph->p0 > 0) {
+                p0_min = fmin(p0_min, ph->p0);
+                p0_max = fmax(p0_max, ph->p0);
+                valid++;
+            }
+            rebin_position(o, ph, &r, &theta, &phi);
+            th_min = fmin(th_min, theta);
+            th_max = fmax(th_max, theta);
+            if (three) {
+                ph_min = fmin(ph_min, phi);
+                ph_max = fmax(ph_max, phi);
+            }
+        }
+        if (ph->type == MC_CS_POOL_PHOTON) synch++;
+    }
+    if (valid <= 0) return -1;
+    {
+        const double log_p0_min = (p0_min > 0 && p0_max > 0) ? log10(p0_min) : 0.0;
+        const double log_p0_max = (p0_min > 0 && p0_max > 0) ? log10(p0_max) : 1.0;
+        /* calculate_binning_params, :325-347 */
+        const int num_bins = (int)(o->cfg.cs_rebin_e_perc * max_photons);
+        const int num_bins_theta = (int)ceil((th_max - th_min) / (MC_REBIN_ANG * MC_DEG_TO_RAD));
+        const int num_bins_phi = three ? (int)ceil((ph_max - ph_min) / MC_REBIN_ANG_PHI) : 1;
+        int total_bins = num_bins_theta * num_bins;
+        double *re, *rt, *rp;
+        double (*st)[14];
+        mc_photon *rebin_ph;
+        if (three) total_bins *= num_bins_phi;
+        if (total_bins > max_photons) return -1; /* :637-642 */
+        if (num_bins <= 0 || num_bins_theta <= 0 || num_bins_phi <= 0) return -1; /* :352-355 */
+        /* allocate_histograms, :350-392: uniform ranges with the upper edge nudged outward */
+        re = (double *)malloc((size_t)(num_bins + 1) * sizeof(double));
+        rt = (double *)malloc((size_t)(num_bins_theta + 1) * sizeof(double));
+        rp = (double *)malloc((size_t)(num_bins_phi + 1) * sizeof(double));
+        mc_hist_uniform_ranges(re, (size_t)num_bins, log_p0_min, log_p0_max + (log_p0_max - log_p0_min) * 1e-6);
+        mc_hist_uniform_ranges(rt, (size_t)num_bins_theta, th_min, th_max + (th_max - th_min) * 1e-6);
+        if (three) mc_hist_uniform_ranges(rp, (size_t)num_bins_phi, ph_min, ph_max + (ph_max - ph_min) * 1e-6);
+        /* accumulate_bin_statistics, :448-500.  Columns: r, theta, phi_offset, s0..s3, scatt, weight, phi_dir,
+         * theta_dir, energy, phi_pos */
+        st = (double (*)[14])calloc((size_t)total_bins, sizeof(*st));
+        for (i = 0; i < l->list_capacity; i++) {
+            const mc_photon *ph = &l->photons[i];
+            double r, theta, phi = 0.0, phi_dir, theta_dir, le;
+            size_t ix = 0, iy = 0, iz = 0;
+            long bin;
+            if (!rebin_eligible(ph)) continue;
+            rebin_position(o, ph, &r, &theta, &phi);
+            le = log10(ph->p0);
+            if (mc_hist_find((size_t)num_bins, re, le, &ix) == 0) mc_hist_find((size_t)num_bins_theta, rt, theta, &iy);
+            if (three) {
+                if (mc_hist_find((size_t)num_bins, re, le, &ix) == 0) mc_hist_find((size_t)num_bins_phi, rp, phi, &iz);
+                if (mc_hist_find((size_t)num_bins_theta, rt, theta, &iy) == 0) mc_hist_find((size_t)num_bins_phi, rp, phi, &iz);
+            }
+            /* calculate_bin_index, :432-446 */
+            if ((int)ix >= num_bins || (int)iy >= num_bins_theta)
+                bin = -1;
+            else if (three)
+                bin = ((int)iz >= num_bins_phi) ? -1 : (long)iz * num_bins * num_bins_theta + (long)ix * num_bins_theta + (long)iy;
+            else
+                bin = (long)ix * num_bins_theta + (long)iy;
+            if (bin < 0 || bin >= total_bins) {
+                fprintf(stderr, "oracle rebin: photon %d maps to invalid bin index %ld\n", i, bin);
+                exit(1); /* :469-472 */
+            }
+            st[bin][0] += r * ph->weight;
+            st[bin][1] += theta * ph->weight;
+            st[bin][2] += (atan2(ph->p2, ph->p1) - atan2(ph->r1, ph->r0)) * MC_RAD_TO_DEG * ph->weight;
+            st[bin][3] += ph->s0 * ph->weight;
+            st[bin][4] += ph->s1 * ph->weight;
+            st[bin][5] += ph->s2 * ph->weight;
+            st[bin][6] += ph->s3 * ph->weight;
+            st[bin][7] += ph->num_scatt * ph->weight;
+            st[bin][8] += ph->weight;
+            phi_dir = fmod(atan2(ph->p2, ph->p1) * MC_RAD_TO_DEG + 360.0, 360.0);
+            theta_dir = acos(ph->p3 / ph->p0) * MC_RAD_TO_DEG;
+            st[bin][9] += phi_dir * ph->weight;
+            st[bin][10] += theta_dir * ph->weight;
+            st[bin][11] += ph->p0 * ph->weight;
+            if (three) st[bin][12] += phi * ph->weight;
+        }
+        /* create_rebinned_photons, :503-598 */
+        rebin_ph = (mc_photon *)calloc((size_t)total_bins, sizeof(mc_photon));
+        for (i = 0; i < total_bins; i++) {
+            const double *s = st[i];
+            mc_photon *q = &rebin_ph[i];
+            if (s[8] <= 0) {
+                q->type = MC_NULL_PHOTON;
+                q->weight = 0;
+                q->nearest_block_index = -1;
+                q->recalc_properties = 0;
+                null_count++;
+            } else {
+                double avg_energy = s[11] / s[8], avg_phi_dir = s[9] / s[8], avg_theta_dir = s[10] / s[8];
+                double avg_r = s[0] / s[8], avg_theta_pos = s[1] / s[8], pos_phi;
+                q->type = MC_COMPTONIZED_PHOTON;
+                q->weight = s[8];
+                q->p0 = avg_energy;
+                q->p1 = avg_energy * sin(avg_theta_dir * MC_DEG_TO_RAD) * cos(avg_phi_dir * MC_DEG_TO_RAD);
+                q->p2 = avg_energy * sin(avg_theta_dir * MC_DEG_TO_RAD) * sin(avg_phi_dir * MC_DEG_TO_RAD);
+                q->p3 = avg_energy * cos(avg_theta_dir * MC_DEG_TO_RAD);
+                if (three) {
+                    double avg_phi_pos = s[12] / s[8];
+                    pos_phi = avg_phi_pos * MC_DEG_TO_RAD;
+                } else {
+                    double avg_phi_offset = s[2] / s[8];
+                    pos_phi = (avg_phi_dir - avg_phi_offset) * MC_DEG_TO_RAD;
+                }
+                q->r0 = avg_r * sin(avg_theta_pos) * cos(pos_phi);
+                q->r1 = avg_r * sin(avg_theta_pos) * sin(pos_phi);
+                q->r2 = avg_r * cos(avg_theta_pos);
+                q->s0 = s[3] / s[8];
+                q->s1 = s[4] / s[8];
+                q->s2 = s[5] / s[8];
+                q->s3 = s[6] / s[8];
+                q->num_scatt = (int)(s[7] / s[8] + 0.5);
+                q->nearest_block_index = 0;
+                q->recalc_properties = 1;
+            }
+        }
+        for (i = 0; i < l->list_capacity; i++) {
+            mc_photon *ph = &l->photons[i];
+            if (ph->type == MC_UNABSORBED_CS_PHOTON || ph->type == MC_COMPTONIZED_PHOTON) mc_list_set_null(l, i);
+        }
+        mc_list_add(l, rebin_ph, (size_t)total_bins);
+        free(rebin_ph);
+        free(st);
+        free(re);
+        free(rt);
+        free(rp);
+        /* :680-684 */
+        *scatt_cyclosynch_num_ph = total_bins - null_count;
+        *num_cyclosynch_ph_emit = total_bins + synch - null_count;
+    }
+    return null_count;
+}
+
+/* ============================================================================ */
 /* the scatter-frame while-loop, Src/mcrat.c:754-851                               */
-/* (rebinCyclosynchCompPhotons, :820-830, is not restated: the loop stops with     */
-/*  st->iterations < 0 if a rebin would be required)                               */
+/* (the rebin of :820-830 is mc_rebin_cyclosynch_comp_photons above; the loop stops */
+/*  with st->iterations < 0 where the driver would call it)                        */
 /* ============================================================================ */
 void mc_run_frame(mc_oracle *o, mc_photon_list *l, const mc_hydro *h, mc_rng *rng, double time_now,
                   double remaining_time, long long max_iters, int find_nearest_grid_switch, double cs_r_inj,

@@ -175,6 +175,10 @@ double mc_cyclosynch_r_limits(int frame_scatt, int frame_inj, double fps, double
 int mc_photon_emit_cyclosynch(mc_oracle *o, mc_photon_list *l, double r_inj, double ph_weight, int maximum_photons,
                               double theta_min, double theta_max, const mc_hydro *h, mc_rng *rng,
                               int inject_single_switch, int scatt_ph_index);
+/* rebinCyclosynchCompPhotons, Src/mc_cyclosynch.c:600-710 (+ static helpers :244-598); returns the number of empty
+ * bins or -1 */
+int mc_rebin_cyclosynch_comp_photons(mc_oracle *o, mc_photon_list *l, int *num_cyclosynch_ph_emit,
+                                     int *scatt_cyclosynch_num_ph, int max_photons);
 double mc_ph_abs_cyclosynch(mc_oracle *o, mc_photon_list *l, int *num_abs_ph, int *scatt_cyclosynch_num_ph,
                             const mc_hydro *h);
 

@@ -257,3 +257,54 @@ def test_cyclosynchrotron_absorb_and_emit(refname):
         eng.set_photons(ph)
     assert ref.ph_abs_cyclosynch() == o.ph_abs_cyclosynch()
     assert _bitwise(ref.photons(), o.photons()) == []
+
+
+def _cs_list_for_rebin(wl, seed=77, n_photons=20000):
+    """A list in the middle of a cyclo-synchrotron run: injected, comptonised, unabsorbed, pool and null photons, the
+    rebinnable ones inside a narrow cone (total bins = 0.1 max_photons x n_theta x n_phi must stay <= max_photons)."""
+    cfg, hydro, photons, frame = synth.workload(wl, scale=1.0 / 32, n_photons=n_photons, seed=seed)
+    rng = np.random.default_rng(5)
+    n = photons.size
+    kinds = rng.choice(np.frombuffer(b"ikcpN", dtype="S1"), n, p=[0.15, 0.35, 0.2, 0.1, 0.2])
+    photons["num_scatt"] = rng.integers(0, 40, n)
+    photons["weight"] = 10 ** rng.uniform(48, 50, n)
+    f = 10 ** rng.uniform(-2, 2, n)
+    for k in ("p0", "p1", "p2", "p3"):
+        photons[k] *= f
+    ang = rng.uniform(0, 2 * np.pi, n)
+    photons["s1"], photons["s2"] = 0.3 * np.cos(ang), 0.3 * np.sin(ang)
+    rho, phi = np.hypot(photons["r0"], photons["r1"]), np.arctan2(photons["r1"], photons["r0"]) % (2 * np.pi)
+    photons["r0"], photons["r1"] = rho * np.cos(phi / 20.0), rho * np.sin(phi / 20.0)
+    rr = np.sqrt(photons["r0"] ** 2 + photons["r1"] ** 2 + photons["r2"] ** 2)
+    th = np.degrees(np.arccos(photons["r2"] / rr))
+    inside = th < th.min() + 1.7
+    kinds = np.where(~inside & ((kinds == b"k") | (kinds == b"c")), b"i", kinds)
+    photons["type"] = kinds
+    null = kinds == b"N"
+    for k in photons.dtype.names:
+        if k != "type":
+            photons[k][null] = 0
+    photons["nearest_block_index"][null] = -1
+    return hydro, photons
+
+
+@pytest.mark.parametrize("refname,wl", [("c4_3d_sph_cs", "C4"), ("g_2d_cyl_cs", "C2")])
+def test_cyclosynchrotron_rebin_bit_identical(refname, wl):
+    """rebinCyclosynchCompPhotons (Src/mc_cyclosynch.c:600-710): the restatement against the reference's own function."""
+    _need_ref(refname)
+    hydro, photons = _cs_list_for_rebin(wl)
+    ref = api.RefLib(refname)
+    ref.set_hydro(hydro)
+    ref.set_photons(photons)
+    want_rc = ref.rebin_cyclosynch_comp_photons(3000)
+    o = api.Oracle(configs.CONFIGS[refname])
+    o.set_hydro(hydro)
+    o.set_photons(photons)
+    got_rc = o.rebin_cyclosynch_comp_photons(3000)
+    assert want_rc[0] >= 0 and got_rc == want_rc
+    assert (ref.photons()["type"] == b"k").sum() == want_rc[2] > 50
+    assert _bitwise(ref.photons(), o.photons(), skip=("time_to_scatter", "total_optical_depth")) == []
+    # no energy bins at all (0.1 x max_photons < 1): both refuse (:352-355)
+    ref.set_photons(photons)
+    o.set_photons(photons)
+    assert ref.rebin_cyclosynch_comp_photons(5)[0] == -1 and o.rebin_cyclosynch_comp_photons(5)[0] == -1
