@@ -42,7 +42,7 @@ static_assert(sizeof(mcrat_photon) == 176, "struct photon layout (Src/mcrat.h:14
 enum : unsigned char { F_MOVABLE = 1, F_RECALC = 2 };
 
 constexpr int MAX_DT = 16;         // pushes recorded by one event (1 + Klein-Nishina rejections)
-constexpr int BLOCKMIN_CAP = 4096; // per-block arg-min slots
+constexpr int BLOCKMIN_CAP = 8192; // per-block arg-min slots (persistent loop: two per sub-shard at 4096 sub-shards)
 constexpr int MAX_SHARDS = 4096;
 #ifndef MCRAT_SCAN_THREADS
 #define MCRAT_SCAN_THREADS 128
@@ -101,6 +101,8 @@ struct ShardState {
     int done, pause_cs, counted_stopped;
     int last_scattered_idx, head_idx; // global slot indices
     int first, count;                 // slot range
+    int mini_slot;                    // persistent loop: the photon whose next pass the event block does itself, or -1
+    int pad1_;
     int halt;                         // persistent loop: loop_stopped() as evaluated by the publishing block
     int reloc_heavy;                  // the last iteration re-located many photons: better served by K1b / K1c
     int pad0_;
@@ -375,8 +377,10 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
     const double default_t = 1e12 / C_LIGHT; // Src/mclib.c:620, 684-687
     const int first = sh.first, count = sh.count;
 
+    const int mini = LOCAL_RELOC ? sh.mini_slot : -1;
     for (int j = b * THREADS + threadIdx.x; j < count; j += nblk * THREADS) {
         const int i = first + j;
+        if (i == mini) continue; // the event block runs this photon's pass itself (persistent loop)
         // every column this photon can need is requested up front (one round trip to HBM instead
         // of three dependent ones); the momentum is used by the pushes, tau by the free-path draw
         const unsigned char flags = d.ph.flags[i];
@@ -990,6 +994,48 @@ struct ScatterMail {
 
 constexpr int SCATTER_THREADS = 96; // warps 0..2 of the event block
 
+// Early hand-over (persistent loop): once a candidate is accepted by the Klein-Nishina test, everything the
+// other photons' next pass needs -- the pushes of this event, the new clock, the iteration number -- is final,
+// while half of the event (azimuth, outgoing photon, boosts back, Stokes chain) still lies ahead and touches only
+// the scattered photon.  The helper warp therefore does the driver's bookkeeping (Src/mcrat.c:781-846) right there,
+// publishes the shard state and releases the pass blocks; the event block finishes the scatter and runs the
+// scattered photon's next pass itself ("mini-pass").
+struct EarlyRelease {
+    int enabled;        // set by thread 0 before the scatter
+    ShardState *gst;    // global copy of the shard state
+    unsigned gen_value; // value to release on gst->gen
+    int bm_index;       // slot of d.bm_t / d.bm_i that receives the mini-pass result
+    int step_mode;
+    int n_dt, ph_index;
+    double scatt_time;
+    int released;       // out: the state has been published
+};
+
+// the driver's bookkeeping after photonEvent returned (Src/mcrat.c:783-787, 834-846), without the cyclo-synchrotron part
+__device__ __forceinline__ void event_bookkeeping(ShardState &st, int n_dt, int ph_index, double scatt_time, int step_mode)
+{
+    st.n_dt = n_dt;
+    st.last_scattered_idx = ph_index;
+    st.last_time_step = scatt_time;
+    st.iter += 1;
+    st.iters_done += 1;
+    if (step_mode == 0) {
+        st.time_now += scatt_time;
+        st.remaining_time -= scatt_time;
+        if (!(st.remaining_time > 0)) st.done = 1;
+    }
+}
+
+__device__ __forceinline__ void event_count_stopped(GlobalState &gs, ShardState &st)
+{
+    if ((st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters)) && !st.counted_stopped) {
+        st.counted_stopped = 1;
+        atomicAdd(&gs.n_stopped, 1);
+    }
+}
+
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v);
+
 __device__ __forceinline__ void trio_bar() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
 __device__ __forceinline__ void duo_bar() { asm volatile("bar.sync 2, 64;" ::: "memory"); } // warps 1 and 2
 // warp 1 hands rotateElectron's angles to warp 0 without waiting for it
@@ -1017,7 +1063,7 @@ __device__ __forceinline__ void rot_from_lane(double sn, double cs, int src, dou
 // photonEvent's body for one candidate (Src/mclib.c:1138-1333); threads 0..95 of the block call
 // this together (STOKES_SWITCH ON).
 __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh, ScatterMail &m, int i, int n_dt,
-                                     int *event_did_occur)
+                                     int *event_did_occur, EarlyRelease &early)
 {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // warp-0 lane-0 state carried across stages
@@ -1026,6 +1072,9 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
     EventRng rng;
     double s[4] = {0, 0, 0, 0}; // warp 1, replicated in its lanes
     double sn = 0, cs = 1;
+    CellState cell; // warp 2 lane 0: the candidate's cell, kept for the mini-pass
+    cell.v0 = cell.v1 = cell.v2 = cell.r0 = cell.r1 = cell.r2 = cell.gamma = cell.dens_lab = cell.temp = 0;
+    int cell_idx = -1;
 #ifdef MCRAT_TIMING
     const bool tm__ = (w == 0 && lane == 0 && st.first == 0);
     GlobalState &gsr__ = *d.gs;
@@ -1089,9 +1138,10 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
             double p[4] = {d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i]};
             double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
             if (flags & F_MOVABLE) apply_pushes(st, n_dt, p[0], p[1], p[2], p[3], r0, r1, r2);
-            CellState c = load_cell_state(d.cells, d.ph.idx[i]);
+            cell_idx = d.ph.idx[i];
+            cell = load_cell_state(d.cells, cell_idx);
             double fb[3];
-            fluid_beta_of(d, c, r0, r1, fb);
+            fluid_beta_of(d, cell, r0, r1, fb);
             m.zhat[0] = 0; m.zhat[1] = 0; m.zhat[2] = 1;
             m.r[0] = r0; m.r[1] = r1; m.r[2] = r2;
             m.flags = flags;
@@ -1167,7 +1217,7 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
         }
         return;
     }
-    // ---- stage D: azimuth + outgoing photon ----
+    // ---- stage D: azimuth + outgoing photon | -- | bookkeeping and early release of the pass blocks ----
     if (w == 0) {
         if (lane == 0) {
             double phi = kn_phi(1, kn, m.q, m.u, rng);
@@ -1176,6 +1226,25 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
             scatter_stage_out(m.php[0], kn.st, kn.ct, phi, rot, out);
 #pragma unroll
             for (int k = 0; k < 4; ++k) m.out[k] = out[k];
+        }
+        __syncwarp();
+    } else if (w == 2 && early.enabled) {
+        if (lane == 0) {
+            st.pushed_slot = i; // the accepted candidate is at its pushed position already (Src/mclib.c:1138)
+            st.scatt_cnt += 1;
+            event_bookkeeping(st, early.n_dt, early.ph_index, early.scatt_time, early.step_mode);
+            event_count_stopped(*d.gs, st);
+            st.halt = (loop_stopped(*d.gs, st) || st.reloc_heavy) ? 1 : 0;
+            st.mini_slot = st.halt ? -1 : i; // a halted shard leaves the photon as photonEvent left it
+        }
+        __syncwarp();
+        for (int k = lane; k < SHARD_STATE_WORDS; k += 32)
+            reinterpret_cast<unsigned long long *>(early.gst)[k] = reinterpret_cast<const unsigned long long *>(&st)[k];
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            st_release_u32(&early.gst->gen, early.gen_value);
+            early.released = 1;
         }
         __syncwarp();
     }
@@ -1251,13 +1320,70 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
         d.ph.r0[i] = m.r[0];
         d.ph.r1[i] = m.r[1];
         d.ph.r2[i] = m.r[2];
-        st.pushed_slot = i;
-        st.scatt_cnt += 1;
+        if (!early.released) {
+            st.pushed_slot = i;
+            st.scatt_cnt += 1;
+        }
         *event_did_occur = 1;
         rng.pre = nullptr;
         rng.npre = 0;
         rng_sh = rng;
         T2W(18);
+    }
+    // ---- mini-pass: the scattered photon's share of the next pass (pass_body for one photon), by the helper warp ----
+    if (early.released && st.mini_slot == i) {
+        double t_next = 1e12 / C_LIGHT, tau_next = 0, h0 = 0, h1 = 0, h2 = 0;
+        int state = 0; // 0: out of the domain, 1: still in its cell (t_next, tau_next valid), 2: left its cell
+        if (w == 2 && lane == 0) {
+            const int ndim3 = (d.dims == D_THREE);
+            coord_to_hydro(d.dims, d.geom, m.r[0], m.r[1], m.r[2], h0, h1, h2);
+            bool in_domain;
+            if (!ndim3)
+                in_domain = ((h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) && (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0]));
+            else
+                in_domain = ((h2 < d.cells.dom[5]) && (h2 > d.cells.dom[4]) && (h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) &&
+                             (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0]));
+            if (in_domain) {
+                if (in_cell(ndim3, d.cells, cell_idx, h0, h1, h2)) {
+                    int terr = 0;
+                    tau_next = optical_depth(d.dims, d.geom, d.tau_calc, d.table, cell, m.r[0], m.r[1], m.p_new[1], m.p_new[2],
+                                             m.p_new[3], m.pc_fin[0], &terr);
+                    if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
+                    const uint32_t k1 = d.k1 ^ (d.shard_base + (uint32_t)(early.gst - d.sh));
+                    const double xi = philox_mfp_uniform(d.k0, k1, st.iter, (uint32_t)(i - st.first));
+                    t_next = free_path_time(tau_next, xi);
+                    state = 1;
+                } else {
+                    state = 2;
+                }
+            }
+        }
+        trio_bar(); // warp 0 has written the photon's new columns
+        if (w == 2 && lane == 0) {
+            double bt = DBL_MAX;
+            int bi = INT_MAX;
+            if (state == 1) {
+                d.ph.tau[i] = tau_next;
+                d.ph.flags[i] = m.flags & ~F_RECALC;
+                d.ph.tts[i] = t_next;
+                bt = t_next;
+                bi = i;
+            } else if (state == 2) {
+                const int pos = st.first + atomicAdd(&early.gst->reloc_n, 1);
+                d.reloc_slot[pos] = i;
+                d.reloc_h0[pos] = h0;
+                d.reloc_h1[pos] = h1;
+                d.reloc_h2[pos] = h2;
+                d.reloc_best[pos] = INT_MAX;
+            } else {
+                d.ph.idx[i] = -1; // Src/mclib.c:589-595
+                d.ph.tts[i] = t_next;
+                bt = t_next;
+                bi = i;
+            }
+            d.bm_t[early.bm_index] = bt;
+            d.bm_i[early.bm_index] = bi;
+        }
     }
 }
 
@@ -1389,11 +1515,16 @@ __device__ void cs_emit_single(DevCtx &d, EventRng &rng, int scatt, int slot)
 
 // step_mode 0: frame loop (driver bookkeeping included); 1: photonEvent only (dt_max given)
 // blockmin_valid: the pass wrote per-block minima for this iteration (fused path / step API)
+// `early_gst` != nullptr (persistent loop): publish the state to *early_gst and release `early_gen` on its generation
+// word as soon as a candidate is accepted; d.bm_*[early_bm] receives the scattered photon's mini-pass.  Returns
+// whether that happened (else the caller publishes after the event).
 template <int EVT_THREADS>
-__device__ __forceinline__ void event_body(DevCtx &d, const int s, const int reloc_base, const int R, int nb_per_shard,
-                                           int step_mode, double dt_max_arg, ShardState &st)
+__device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int reloc_base, const int R, int nb_per_shard,
+                                           int step_mode, double dt_max_arg, ShardState &st, ShardState *early_gst = nullptr,
+                                           unsigned early_gen = 0, int early_bm = 0)
 {
     GlobalState &gs = *d.gs;
+    __shared__ EarlyRelease early;
 
     __shared__ double sh_cand_t;
     __shared__ int sh_cand_i, sh_finished;
@@ -1459,6 +1590,12 @@ __device__ __forceinline__ void event_body(DevCtx &d, const int s, const int rel
         ph_index = bi;
         st.n_dt = 0;
         st.pushed_slot = -1;
+        early.enabled = 0;
+        early.released = 0;
+        early.gst = early_gst;
+        early.gen_value = early_gen;
+        early.bm_index = early_bm;
+        early.step_mode = step_mode;
         rng_sh.replay = d.replay;
         rng_sh.k0 = d.k0;
         rng_sh.k1 = d.k1 ^ (d.shard_base + (uint32_t)s);
@@ -1489,7 +1626,7 @@ __device__ __forceinline__ void event_body(DevCtx &d, const int s, const int rel
         }
     }
     __syncthreads();
-    if (sh_finished) return;
+    if (sh_finished) return false;
 
     // ---- photonEvent: walk candidates in ascending time, Src/mclib.c:1128-1339 ----
     while (true) {
@@ -1517,12 +1654,17 @@ __device__ __forceinline__ void event_body(DevCtx &d, const int s, const int rel
             old_scatt_time = scatt_time;
             sh_try = attempt ? 1 : 0;
             sh_event = event ? 1 : 0;
+            // if this candidate is accepted, these are the event's final numbers
+            early.enabled = (early_gst != nullptr && attempt && !d.cs && step_mode == 0 && !d.replay) ? 1 : 0;
+            early.n_dt = n_dt;
+            early.ph_index = i;
+            early.scatt_time = scatt_time;
         }
         __syncthreads();
         if (sh_try) {
             if (d.stokes) {
                 // three warps: scattering lane | Stokes chain | helper
-                if (threadIdx.x < SCATTER_THREADS) scatter_candidate_3w(d, st, rng_sh, mail, sh_cand_i, n_dt, &sh_event);
+                if (threadIdx.x < SCATTER_THREADS) scatter_candidate_3w(d, st, rng_sh, mail, sh_cand_i, n_dt, &sh_event, early);
             } else if (threadIdx.x == 0) {
                 EventRng rng = rng_sh;
                 bool event = false;
@@ -1583,16 +1725,9 @@ __device__ __forceinline__ void event_body(DevCtx &d, const int s, const int rel
         __syncthreads();
     }
 
-    if (threadIdx.x == 0) {
-        st.n_dt = n_dt;
-        st.last_scattered_idx = ph_index;
-        st.last_time_step = scatt_time;
-        st.iter += 1;
-        st.iters_done += 1;
+    if (threadIdx.x == 0 && !early.released) {
+        event_bookkeeping(st, n_dt, ph_index, scatt_time, step_mode);
         if (step_mode == 0) {
-            st.time_now += scatt_time;
-            st.remaining_time -= scatt_time;
-            if (!(st.remaining_time > 0)) st.done = 1;
             if (cs_need) {
                 gs.cs_comptonized_w += d.ph.weight[ph_index];
                 d.ph.type[ph_index] = 'k'; // COMPTONIZED_PHOTON
@@ -1611,16 +1746,15 @@ __device__ __forceinline__ void event_body(DevCtx &d, const int s, const int rel
             // Src/mcrat.c:810-831: every 1000 scatterings the driver may have to rebin on the host
             if (d.cs && !st.pause_cs && (st.scatt_cnt % 1000 == 0) && (st.scatt_cnt != 0) && gs.cs_scatt_num > gs.cs_max_photons)
                 st.pause_cs = 2;
-            if ((st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters)) && !st.counted_stopped) {
-                st.counted_stopped = 1;
-                atomicAdd(&gs.n_stopped, 1);
-            }
+            event_count_stopped(gs, st);
         }
         if (d.replay) {
             gs.replay_cursor = rng_sh.pos;
             if (rng_sh.exhausted) gs.error = MCRAT_B200_ERR_REPLAY;
         }
     }
+    __syncthreads();
+    return early.released != 0;
 }
 
 template <int EVT_THREADS>
@@ -1700,15 +1834,23 @@ __device__ __forceinline__ void relocate_shard(DevCtx &d, ShardState &st, const 
     __syncthreads();
 }
 
+// A sub-shard is run by a team of `bps` pass blocks and one event block, all resident:
+//   pass block b:  pass over its slice -> ticket on gst.arrive -> spin on gst.gen -> pull the state -> next pass
+//   event block:   spin until all bps tickets of the iteration are drawn -> re-locate -> shard arg-min -> event;
+//                  the state is published (gst.gen released) the moment a candidate is accepted, so the pass blocks
+//                  run the next pass while the event block is still busy with the second half of the scatter; the
+//                  scattered photon's own next pass is done by the event block (mini-pass, slot `bps` of the minima).
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_kernel(DevCtx d, const int bps)
 {
-    __shared__ int sh_last;
-    __shared__ ShardState st; // this block's copy of the shard's state; the publisher writes it back
+    __shared__ ShardState st; // this block's copy of the shard's state
+    __shared__ int sh_flag;
     GlobalState &gs = *d.gs;
-    const int groups = gridDim.x / bps;
-    const int g = blockIdx.x / bps, b = blockIdx.x - g * bps;
+    const int team = bps + 1;
+    const int groups = gridDim.x / team;
+    const int g = blockIdx.x / team, role = blockIdx.x - g * team;
     if (g >= groups) return;
+    const bool is_event_block = (role == bps);
 
     for (int s = g; s < d.nshards; s += groups) {
         ShardState &gst = d.sh[s];
@@ -1718,99 +1860,128 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
                 reinterpret_cast<unsigned long long *>(&st)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&gst)[threadIdx.x];
             __syncthreads();
         };
-        __syncthreads();
-        pull();
-        unsigned phase = 0; // iterations this block has been through; arrive / gen were zeroed before the launch
-        // stop test at entry: shard state only, so that all blocks of the shard decide alike
-        bool halt = st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters);
-
-        // the last arriver of an iteration returns true
-        auto arrive = [&]() -> bool {
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                ++phase;
-                if (bps == 1) {
-                    sh_last = 1;
-                } else {
-                    __threadfence();
-                    const unsigned ticket = atomicAdd(&gst.arrive, 1u);
-                    sh_last = (ticket == phase * (unsigned)bps - 1u) ? 1 : 0;
-                    if (sh_last) __threadfence();
-                }
-            }
-            __syncthreads();
-            return sh_last != 0;
-        };
-        // last arriver: write the state back and hand the shard to its blocks
-        auto publish = [&]() {
-            if (threadIdx.x == 0) st.halt = (loop_stopped(gs, st) || st.reloc_heavy) ? 1 : 0;
-            __syncthreads();
-            if (threadIdx.x < SHARD_STATE_WORDS)
-                reinterpret_cast<unsigned long long *>(&gst)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&st)[threadIdx.x];
-            if (bps > 1) {
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    __threadfence();
-                    st_release_u32(&gst.gen, phase);
-                }
-            }
-        };
-        auto wait = [&]() {
+        // thread 0 spins until *word >= target (relaxed polls, one acquire at the end); false after ~1 s
+        auto spin_until = [&](const unsigned *word, unsigned target) -> bool {
             if (threadIdx.x == 0) {
                 unsigned spins = 0;
-                // poll with relaxed loads (L2-coherent, no L1 invalidation per poll); one acquire once the word moved
-                while (ld_relaxed_u32(&gst.gen) < phase) {
+                int ok = 1;
+                while (ld_relaxed_u32(word) < target) {
                     __nanosleep(40);
-                    if (++spins > (1u << 24)) { // ~1 s: never in a healthy run; refuse to hang the GPU
+                    if (++spins > (1u << 24)) { // never in a healthy run; refuse to hang the GPU
                         gs.error = MCRAT_B200_ERR_STATE;
+                        ok = 0;
                         break;
                     }
                 }
-                (void)ld_acquire_u32(&gst.gen);
+                (void)ld_acquire_u32(word);
+                sh_flag = ok;
             }
             __syncthreads();
-            pull();
-            if (gs.error == MCRAT_B200_ERR_STATE) st.halt = 1; // benign race: every thread stores the same value
-            __syncthreads();
+            return sh_flag != 0;
         };
-#ifdef MCRAT_TIMING
-        const bool tm__ = (threadIdx.x == 0 && s == 0 && b == 0);
-#define TLOOP(k) if (tm__) TSTAMP(gs, k)
-#else
-#define TLOOP(k)
-#endif
-        TSTAMP_DECL;
-        while (!halt) {
-            // ---- pass ----
-            TLOOP(0);
-            double best_t = DBL_MAX;
-            int best_i = INT_MAX;
-            pass_body<true, true, THREADS>(d, st, s, b, bps, 0, 0, best_t, best_i);
-            block_argmin<THREADS>(best_t, best_i);
-            if (threadIdx.x == 0) {
-                d.bm_t[s * bps + b] = best_t;
-                d.bm_i[s * bps + b] = best_i;
+        __syncthreads();
+        pull();
+        // stop test at entry: shard state only, so that all blocks of the team decide alike
+        bool halt = st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters);
+        unsigned k = 0; // iterations of this launch; gst.arrive / gst.gen were zeroed before it
+
+        if (!is_event_block) {
+            // ---------------- pass block ----------------
+            const int b = role;
+            while (!halt) {
+                double best_t = DBL_MAX;
+                int best_i = INT_MAX;
+                pass_body<true, true, THREADS>(d, st, s, b, bps, 0, 0, best_t, best_i);
+                block_argmin<THREADS>(best_t, best_i);
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    d.bm_t[s * team + b] = best_t;
+                    d.bm_i[s * team + b] = best_i;
+                    __threadfence();
+                    atomicAdd(&gst.arrive, 1u);
+                }
+                ++k;
+                if (!spin_until(&gst.gen, k)) break;
+                pull();
+                halt = st.halt != 0;
+                __syncthreads();
             }
-            TLOOP(1); // pass + block arg-min
-            if (arrive()) {
-                TLOOP(2); // waiting for the other blocks of the shard
+        } else {
+            // ---------------- event block ----------------
+            if (threadIdx.x == 0) {
+                d.bm_t[s * team + bps] = DBL_MAX;
+                d.bm_i[s * team + bps] = INT_MAX;
+                st.mini_slot = -1;
+            }
+            __syncthreads();
+            while (!halt) {
+                if (!spin_until(&gst.arrive, (k + 1) * (unsigned)bps)) break;
+                ++k;
                 const int R = *(volatile int *)&gst.reloc_n;
                 if (R > 0) relocate_shard<THREADS>(d, st, s, R);
-                TLOOP(3); // re-location
-                event_body<THREADS>(d, s, st.first, R, bps, 0, 0.0, st);
-                TLOOP(4); // event
-                publish();
-                TLOOP(5);
-#ifdef MCRAT_TIMING
-                if (tm__) gs.dbg[7] += 1;
-#endif
-            } else {
-                wait();
-                TLOOP(6); // spinning on the generation word
+                const bool released = event_body<THREADS>(d, s, st.first, R, team, 0, 0.0, st, &gst, k, s * team + bps);
+                if (!released) {
+                    // frame end, Klein-Nishina walk exhausted, cyclo-synchrotron run, unpolarised run: publish now
+                    if (threadIdx.x == 0) {
+                        st.halt = (loop_stopped(gs, st) || st.reloc_heavy) ? 1 : 0;
+                        st.mini_slot = -1;
+                        d.bm_t[s * team + bps] = DBL_MAX;
+                        d.bm_i[s * team + bps] = INT_MAX;
+                    }
+                    __syncthreads();
+                    if (threadIdx.x < SHARD_STATE_WORDS)
+                        reinterpret_cast<unsigned long long *>(&gst)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&st)[threadIdx.x];
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        __threadfence();
+                        st_release_u32(&gst.gen, k);
+                    }
+                } else if (threadIdx.x == 0 && st.mini_slot < 0) {
+                    d.bm_t[s * team + bps] = DBL_MAX; // released with a halt: no mini-pass ran
+                    d.bm_i[s * team + bps] = INT_MAX;
+                }
+                __syncthreads();
+                halt = st.halt != 0;
             }
+            // the state proper is current in global memory (published with every release)
+        }
+    }
+}
+
+// With more sub-shards than resident teams the GPU is busy anyway (many events in flight per SM) and throughput,
+// not the latency of one shard, is what counts: one block per sub-shard does pass and event in turn, and walks through
+// its shards one after the other if there are more shards than resident blocks.  No inter-block protocol at all.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_solo_kernel(DevCtx d)
+{
+    __shared__ ShardState st;
+    GlobalState &gs = *d.gs;
+    for (int s = blockIdx.x; s < d.nshards; s += gridDim.x) {
+        ShardState &gst = d.sh[s];
+        __syncthreads();
+        if (threadIdx.x < SHARD_STATE_WORDS)
+            reinterpret_cast<unsigned long long *>(&st)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&gst)[threadIdx.x];
+        __syncthreads();
+        bool halt = st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters);
+        while (!halt) {
+            double best_t = DBL_MAX;
+            int best_i = INT_MAX;
+            pass_body<true, true, THREADS>(d, st, s, 0, 1, 0, 0, best_t, best_i);
+            block_argmin<THREADS>(best_t, best_i);
+            if (threadIdx.x == 0) {
+                d.bm_t[s] = best_t;
+                d.bm_i[s] = best_i;
+            }
+            __syncthreads();
+            const int R = *(volatile int *)&gst.reloc_n;
+            if (R > 0) relocate_shard<THREADS>(d, st, s, R);
+            event_body<THREADS>(d, s, st.first, R, 1, 0, 0.0, st);
+            if (threadIdx.x == 0) st.halt = (loop_stopped(gs, st) || st.reloc_heavy) ? 1 : 0;
             __syncthreads();
             halt = st.halt != 0;
         }
+        if (threadIdx.x < SHARD_STATE_WORDS)
+            reinterpret_cast<unsigned long long *>(&gst)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&st)[threadIdx.x];
     }
 }
 
@@ -2365,7 +2536,7 @@ struct mcrat_b200_ctx {
     int want_shards;    // sub-shards requested for the next set_photons
     int loop_mode;      // MCRAT_B200_LOOP_AUTO / _STREAMED / _PERSISTENT
     double cs_rebin_e_perc, cs_rebin_ang, cs_rebin_ang_phi; // CYCLOSYNCHROTRON_REBIN_E_PERC / _ANG / _ANG_PHI, Src/mcrat.h:308-322
-    int occ_loop256, occ_loop128; // resident blocks per SM of frame_loop_kernel<256> / <128>
+    int occ_loop256, occ_loop128; // resident blocks per SM of frame_loop_kernel<256>, frame_loop_solo_kernel<256> / <128>
     long long launches; // kernels launched through this context
     GlobalState *gs_host;          // pinned
     std::vector<ShardState> sh_host;
@@ -2576,8 +2747,14 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
         return bail(e, "cudaFuncSetAttribute");
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_loop256, frame_loop_kernel<256>, 256, 0)) != cudaSuccess)
         return bail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_loop128, frame_loop_kernel<128>, 128, 0)) != cudaSuccess)
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_loop128, frame_loop_solo_kernel<128>, 128, 0)) != cudaSuccess)
         return bail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    {
+        int occ_solo256 = 0;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_solo256, frame_loop_solo_kernel<256>, 256, 0)) != cudaSuccess)
+            return bail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+        if (occ_solo256 < ctx->occ_loop256) ctx->occ_loop256 = occ_solo256;
+    }
     *out = ctx;
     return MCRAT_B200_OK;
 }
@@ -3017,6 +3194,7 @@ __global__ void reset_loop_kernel(DevCtx d, int set_times, double time_now, doub
         st.reloc_n = 0;
         st.halt = 0;
         st.reloc_heavy = 0;
+        st.mini_slot = -1;
         if (set_times) {
             st.time_now = time_now;
             st.remaining_time = remaining;
@@ -3335,20 +3513,21 @@ static void frame_loop_grid(const mcrat_b200_ctx *ctx, int &threads, int &bps, i
 {
     const int S = ctx->d.nshards;
     const int cap256 = ctx->num_sms * ctx->occ_loop256;
-    if (S > cap256) {
-        // more shards than wide blocks fit: four-warp blocks (pass + three-warp event), a block walks
-        // through its shards one after the other if there are more shards than resident blocks
-        threads = 128;
-        bps = 1;
-        const int cap = ctx->num_sms * ctx->occ_loop128;
-        grid = S < cap ? S : cap;
-    } else {
+    if (3 * S <= cap256) {
+        // latency regime (room for at least two pass blocks per shard): a team of bps pass blocks + 1 event block
+        // per sub-shard (frame_loop_kernel)
         threads = 256;
         bps = (ctx->d.shard_size + 255) / 256;
-        if (bps > cap256 / S) bps = cap256 / S;
-        if (bps > BLOCKMIN_CAP / S) bps = BLOCKMIN_CAP / S;
+        if (bps > cap256 / S - 1) bps = cap256 / S - 1;
+        if (bps > BLOCKMIN_CAP / S - 1) bps = BLOCKMIN_CAP / S - 1;
         if (bps < 1) bps = 1;
-        grid = S * bps;
+        grid = S * (bps + 1);
+    } else {
+        // throughput regime: one block per sub-shard (frame_loop_solo_kernel), bps = 0 marks it
+        bps = 0;
+        threads = (S <= cap256) ? 256 : 128;
+        const int cap = (threads == 256) ? cap256 : ctx->num_sms * ctx->occ_loop128;
+        grid = S < cap ? S : cap;
     }
 }
 
@@ -3361,10 +3540,14 @@ static int launch_frame_loop(mcrat_b200_ctx *ctx)
     if (getenv("MCRAT_B200_REFUSE_COOPERATIVE")) return MCRAT_B200_LOOP_FALLBACK; // test hook for the hand-over below
     Timed t(ctx, KC_EVENT);
     cudaError_t e;
-    if (threads == 128)
-        e = cudaLaunchCooperativeKernel((const void *)frame_loop_kernel<128>, dim3(grid), dim3(128), args, 0, ctx->stream);
-    else
-        e = cudaLaunchCooperativeKernel((const void *)frame_loop_kernel<256>, dim3(grid), dim3(256), args, 0, ctx->stream);
+    if (bps == 0) { // independent blocks: an ordinary launch
+        if (threads == 128)
+            frame_loop_solo_kernel<128><<<grid, 128, 0, ctx->stream>>>(ctx->d);
+        else
+            frame_loop_solo_kernel<256><<<grid, 256, 0, ctx->stream>>>(ctx->d);
+        return check_launch(ctx, "frame_loop_solo_kernel");
+    }
+    e = cudaLaunchCooperativeKernel((const void *)frame_loop_kernel<256>, dim3(grid), dim3(256), args, 0, ctx->stream);
     if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported || e == cudaErrorLaunchOutOfResources) {
         // the device cannot hold the grid (MPS share, another tenant, no cooperative launch): the streamed loop needs nothing special
         (void)cudaGetLastError();
