@@ -13,5 +13,5 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:"sca
 timeout 120 python tools/prof_driver.py 50 0 16 auto C5 > gpurun_out/prof_plain_c5.log 2>&1 && \
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"scan_kernel" -c 1 \
     -f -o gpurun_out/prof_full_c5 python tools/prof_driver.py 50 0 16 auto C5 > gpurun_out/ncu_full_c5.log 2>&1
-timeout 200 python tools/loop_timing.py C2 100000 296 1000 > gpurun_out/loop_timing.log 2>&1
+timeout 200 python tools/loop_timing.py C2 100000 16 2000 > gpurun_out/loop_timing.log 2>&1
 ls -la gpurun_out | tail -12

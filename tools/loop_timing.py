@@ -24,13 +24,19 @@ hp.set_photons(photons)
 st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=50, switch=1)
 buf = (C.c_longlong * 32)()
 hp.L.mcrat_b200_debug_counters(hp.ctx, buf, 1)
+import time
+hp.synchronize()
+t0 = time.perf_counter()
 st = hp.run_frame(st["time_now"], 1.0 / frame["fps"], max_iters=iters, switch=0)
+hp.synchronize()
+wall = time.perf_counter() - t0
 hp.L.mcrat_b200_debug_counters(hp.ctx, buf, 0)
-n = max(buf[7], 1)
-names = {0: "loop top", 1: "pass + block arg-min", 2: "arrive (last block)", 3: "re-location", 4: "event (all)", 5: "publish",
-         6: "spin (not last)", 8: "3w A: loads (idx, temp, comv p)", 9: "3w B1: electron", 10: "3w B2: boost to e- frame",
-         11: "3w wait", 12: "3w C: KN accept/theta", 13: "3w wait (Stokes q,u; alignment)", 14: "3w D: azimuth + outgoing",
-         15: "3w wait", 16: "3w E: boosts back", 17: "3w wait (angles, Fano)", 18: "3w write-back"}
-print("%s %d photons %d shards: %d events of shard 0 seen by the stamping thread" % (wl, nph, shards, buf[7]))
+n = max(st["iterations"], 1)
+print("%.2f us per iteration end to end (instrumented build)" % (1e6 * wall / n))
+names = {8: "scattering lane: loads (idx, temp, comv p), Philox prefetch, warp-wide Box-Muller", 9: "electron direction + rotation",
+         10: "boost into the electron frame", 11: "wait (helper / Stokes warps)", 12: "Klein-Nishina accept + polar angle",
+         13: "wait (Stokes q,u; alignment)", 14: "azimuth + outgoing photon", 15: "wait", 16: "boosts back",
+         17: "wait (angles, Fano)", 18: "write-back"}
+print("%s %d photons %d shards: SM-cycle stamps of shard 0's scattering lane, per iteration" % (wl, nph, shards))
 for k in sorted(names):
-    print("  %-34s %9.0f cycles / iteration  (%.2f us at 1.965 GHz)" % (names[k], buf[k] / n, buf[k] / n / 1965.0))
+    print("  %-86s %9.0f cycles / iteration  (%.2f us at 1.965 GHz)" % (names[k], buf[k] / n, buf[k] / n / 1965.0))
