@@ -1062,8 +1062,8 @@ __device__ __forceinline__ void rot_from_lane(double sn, double cs, int src, dou
 
 // photonEvent's body for one candidate (Src/mclib.c:1138-1333); threads 0..95 of the block call
 // this together (STOKES_SWITCH ON).
-__device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh, ScatterMail &m, int i, int n_dt,
-                                     int *event_did_occur, EarlyRelease &early)
+__device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh, ScatterMail &m, const int i, const int cand_idx,
+                                     int n_dt, int *event_did_occur, EarlyRelease &early)
 {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // warp-0 lane-0 state carried across stages
@@ -1095,7 +1095,7 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
         __syncwarp();
         // Maxwellian branch: the three gaussians at once, one candidate pair per lane
         double temp = 0;
-        if (lane == 0) temp = d.cells.temp[d.ph.idx[i]];
+        if (lane == 0) temp = d.cells.temp[cand_idx];
         temp = __shfl_sync(0xffffffffu, temp, 0);
         double g3[3] = {0, 0, 0};
         int used = 0;
@@ -1138,7 +1138,7 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
             double p[4] = {d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i]};
             double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
             if (flags & F_MOVABLE) apply_pushes(st, n_dt, p[0], p[1], p[2], p[3], r0, r1, r2);
-            cell_idx = d.ph.idx[i];
+            cell_idx = cand_idx;
             cell = load_cell_state(d.cells, cell_idx);
             double fb[3];
             fluid_beta_of(d, cell, r0, r1, fb);
@@ -1521,22 +1521,28 @@ __device__ void cs_emit_single(DevCtx &d, EventRng &rng, int scatt, int slot)
 template <int EVT_THREADS>
 __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int reloc_base, const int R, int nb_per_shard,
                                            int step_mode, double dt_max_arg, ShardState &st, ShardState *early_gst = nullptr,
-                                           unsigned early_gen = 0, int early_bm = 0)
+                                           unsigned early_gen = 0, int early_bm = 0, const bool have_pre = false,
+                                           const double pre_t = DBL_MAX, const int pre_i = INT_MAX)
 {
     GlobalState &gs = *d.gs;
     __shared__ EarlyRelease early;
 
     __shared__ double sh_cand_t;
-    __shared__ int sh_cand_i, sh_finished;
+    __shared__ int sh_cand_i, sh_cand_idx, sh_finished;
     // ---- head of this shard's time order ----
     double bt = DBL_MAX;
     int bi = INT_MAX;
     if (nb_per_shard > 0) {
-        for (int k = threadIdx.x; k < nb_per_shard; k += EVT_THREADS) {
-            const int q = s * nb_per_shard + k;
-            if (lex_less(d.bm_t[q], d.bm_i[q], bt, bi)) {
-                bt = d.bm_t[q];
-                bi = d.bm_i[q];
+        if (have_pre) { // the caller requested this thread's entry of the block minima together with other loads
+            bt = pre_t;
+            bi = pre_i;
+        } else {
+            for (int k = threadIdx.x; k < nb_per_shard; k += EVT_THREADS) {
+                const int q = s * nb_per_shard + k;
+                if (lex_less(d.bm_t[q], d.bm_i[q], bt, bi)) {
+                    bt = d.bm_t[q];
+                    bi = d.bm_i[q];
+                }
             }
         }
         // photons relocated in this iteration got their time in finish
@@ -1578,6 +1584,8 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
     __shared__ double old_scatt_time, scatt_time, dt_max;
     __shared__ int n_dt, ph_index, sh_try, sh_event;
     if (threadIdx.x == 0) {
+        // the candidate's cell index is requested first: the loads of the set-up below travel with it
+        sh_cand_idx = (bi != INT_MAX) ? d.ph.idx[bi] : -1;
         sh_cand_t = bt;
         sh_cand_i = bi;
         sh_finished = 0;
@@ -1602,8 +1610,8 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
         rng_sh.iter = st.iter;
         rng_sh.draw = 0;
         rng_sh.buf = d.replay_buf;
-        rng_sh.pos = gs.replay_cursor;
-        rng_sh.n = gs.replay_n;
+        rng_sh.pos = d.replay ? gs.replay_cursor : 0; // global loads only the parity harness needs
+        rng_sh.n = d.replay ? gs.replay_n : 0;
         rng_sh.exhausted = 0;
         rng_sh.pre = nullptr;
         rng_sh.npre = 0;
@@ -1664,7 +1672,8 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
         if (sh_try) {
             if (d.stokes) {
                 // three warps: scattering lane | Stokes chain | helper
-                if (threadIdx.x < SCATTER_THREADS) scatter_candidate_3w(d, st, rng_sh, mail, sh_cand_i, n_dt, &sh_event, early);
+                if (threadIdx.x < SCATTER_THREADS)
+                    scatter_candidate_3w(d, st, rng_sh, mail, sh_cand_i, sh_cand_idx, n_dt, &sh_event, early);
             } else if (threadIdx.x == 0) {
                 EventRng rng = rng_sh;
                 bool event = false;
@@ -1696,6 +1705,7 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
                 } else {
                     sh_cand_t = nt;
                     sh_cand_i = ni;
+                    sh_cand_idx = d.ph.idx[ni];
                 }
             }
             __syncthreads();
@@ -1917,9 +1927,18 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
             while (!halt) {
                 if (!spin_until(&gst.arrive, (k + 1) * (unsigned)bps)) break;
                 ++k;
+                // this thread's entry of the block minima and the relocation count: one round trip
+                double pre_t = DBL_MAX;
+                int pre_i = INT_MAX;
+                const bool have_pre = (team <= THREADS);
+                if (have_pre && (int)threadIdx.x < team) {
+                    pre_t = *(volatile double *)&d.bm_t[s * team + threadIdx.x];
+                    pre_i = *(volatile int *)&d.bm_i[s * team + threadIdx.x];
+                }
                 const int R = *(volatile int *)&gst.reloc_n;
                 if (R > 0) relocate_shard<THREADS>(d, st, s, R);
-                const bool released = event_body<THREADS>(d, s, st.first, R, team, 0, 0.0, st, &gst, k, s * team + bps);
+                const bool released = event_body<THREADS>(d, s, st.first, R, team, 0, 0.0, st, &gst, k, s * team + bps, have_pre,
+                                                          pre_t, pre_i);
                 if (!released) {
                     // frame end, Klein-Nishina walk exhausted, cyclo-synchrotron run, unpolarised run: publish now
                     if (threadIdx.x == 0) {
