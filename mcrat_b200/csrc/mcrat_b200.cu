@@ -1875,15 +1875,17 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
             if (threadIdx.x == 0) {
                 unsigned spins = 0;
                 int ok = 1;
-                while (ld_relaxed_u32(word) < target) {
-                    __nanosleep(40);
-                    if (++spins > (1u << 24)) { // never in a healthy run; refuse to hang the GPU
-                        gs.error = MCRAT_B200_ERR_STATE;
-                        ok = 0;
-                        break;
+                if (ld_acquire_u32(word) < target) { // fast path: already there, one round trip
+                    while (ld_relaxed_u32(word) < target) {
+                        __nanosleep(40);
+                        if (++spins > (1u << 24)) { // never in a healthy run; refuse to hang the GPU
+                            gs.error = MCRAT_B200_ERR_STATE;
+                            ok = 0;
+                            break;
+                        }
                     }
+                    (void)ld_acquire_u32(word);
                 }
-                (void)ld_acquire_u32(word);
                 sh_flag = ok;
             }
             __syncthreads();
