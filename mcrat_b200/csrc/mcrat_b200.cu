@@ -167,6 +167,10 @@ struct DevCtx {
     // arg-min scratch, one entry per pass block
     double *bm_t;
     int *bm_i;
+    // team kernel: cell index and cell temperature of the block's best candidate, so that the event block gets
+    // what the scattering lane needs first together with the minima (the pass blocks' time is hidden, the event's is not)
+    int *bm_idx;
+    double *bm_temp;
     // replay
     const double *replay_buf;
     int *prefix_block;
@@ -1062,8 +1066,9 @@ __device__ __forceinline__ void rot_from_lane(double sn, double cs, int src, dou
 
 // photonEvent's body for one candidate (Src/mclib.c:1138-1333); threads 0..95 of the block call
 // this together (STOKES_SWITCH ON).
-__device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh, ScatterMail &m, const int i, const int cand_idx,
-                                     int n_dt, int *event_did_occur, EarlyRelease &early)
+// cand_idx: the candidate's cell (-2: not known yet); cand_temp: that cell's temperature (< 0: not known yet)
+__device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh, ScatterMail &m, const int i, int cand_idx,
+                                     const double cand_temp, int n_dt, int *event_did_occur, EarlyRelease &early)
 {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // warp-0 lane-0 state carried across stages
@@ -1095,7 +1100,7 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
         __syncwarp();
         // Maxwellian branch: the three gaussians at once, one candidate pair per lane
         double temp = 0;
-        if (lane == 0) temp = d.cells.temp[cand_idx];
+        if (lane == 0) temp = (cand_temp >= 0) ? cand_temp : d.cells.temp[cand_idx == -2 ? d.ph.idx[i] : cand_idx];
         temp = __shfl_sync(0xffffffffu, temp, 0);
         double g3[3] = {0, 0, 0};
         int used = 0;
@@ -1138,7 +1143,7 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
             double p[4] = {d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i]};
             double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
             if (flags & F_MOVABLE) apply_pushes(st, n_dt, p[0], p[1], p[2], p[3], r0, r1, r2);
-            cell_idx = cand_idx;
+            cell_idx = (cand_idx == -2) ? d.ph.idx[i] : cand_idx;
             cell = load_cell_state(d.cells, cell_idx);
             double fb[3];
             fluid_beta_of(d, cell, r0, r1, fb);
@@ -1383,6 +1388,8 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
             }
             d.bm_t[early.bm_index] = bt;
             d.bm_i[early.bm_index] = bi;
+            d.bm_idx[early.bm_index] = (state == 1) ? cell_idx : -1;
+            d.bm_temp[early.bm_index] = cell.temp;
         }
     }
 }
@@ -1522,13 +1529,15 @@ template <int EVT_THREADS>
 __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int reloc_base, const int R, int nb_per_shard,
                                            int step_mode, double dt_max_arg, ShardState &st, ShardState *early_gst = nullptr,
                                            unsigned early_gen = 0, int early_bm = 0, const bool have_pre = false,
-                                           const double pre_t = DBL_MAX, const int pre_i = INT_MAX)
+                                           const double pre_t = DBL_MAX, const int pre_i = INT_MAX, const int pre_idx = -2,
+                                           const double pre_temp = 0)
 {
     GlobalState &gs = *d.gs;
     __shared__ EarlyRelease early;
 
     __shared__ double sh_cand_t;
-    __shared__ int sh_cand_i, sh_cand_idx, sh_finished;
+    __shared__ double sh_cand_temp;
+    __shared__ int sh_cand_i, sh_cand_idx, sh_cand_known, sh_finished; // sh_cand_known: idx and temperature are in shared memory
     // ---- head of this shard's time order ----
     double bt = DBL_MAX;
     int bi = INT_MAX;
@@ -1584,8 +1593,10 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
     __shared__ double old_scatt_time, scatt_time, dt_max;
     __shared__ int n_dt, ph_index, sh_try, sh_event;
     if (threadIdx.x == 0) {
-        // the candidate's cell index is requested first: the loads of the set-up below travel with it
-        sh_cand_idx = (bi != INT_MAX) ? d.ph.idx[bi] : -1;
+        // the candidate's cell index: delivered with the block minima (team kernel), else requested first so that
+        // the loads of the set-up below travel with it
+        sh_cand_known = 0;
+        sh_cand_idx = have_pre ? -2 : ((bi != INT_MAX) ? d.ph.idx[bi] : -1);
         sh_cand_t = bt;
         sh_cand_i = bi;
         sh_finished = 0;
@@ -1635,6 +1646,11 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
     }
     __syncthreads();
     if (sh_finished) return false;
+    if (have_pre && pre_i == sh_cand_i && pre_idx >= 0) { // the thread whose entry won hands over what came with it
+        sh_cand_idx = pre_idx;
+        sh_cand_temp = pre_temp;
+        sh_cand_known = 1;
+    }
 
     // ---- photonEvent: walk candidates in ascending time, Src/mclib.c:1128-1339 ----
     while (true) {
@@ -1673,7 +1689,8 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
             if (d.stokes) {
                 // three warps: scattering lane | Stokes chain | helper
                 if (threadIdx.x < SCATTER_THREADS)
-                    scatter_candidate_3w(d, st, rng_sh, mail, sh_cand_i, sh_cand_idx, n_dt, &sh_event, early);
+                    scatter_candidate_3w(d, st, rng_sh, mail, sh_cand_i, sh_cand_idx, sh_cand_known ? sh_cand_temp : -1.0, n_dt,
+                                         &sh_event, early);
             } else if (threadIdx.x == 0) {
                 EventRng rng = rng_sh;
                 bool event = false;
@@ -1706,6 +1723,7 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
                     sh_cand_t = nt;
                     sh_cand_i = ni;
                     sh_cand_idx = d.ph.idx[ni];
+                    sh_cand_known = 0;
                 }
             }
             __syncthreads();
@@ -1907,8 +1925,16 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
                 block_argmin<THREADS>(best_t, best_i);
                 __syncthreads();
                 if (threadIdx.x == 0) {
+                    int bidx = -1;
+                    double btemp = 0;
+                    if (best_i != INT_MAX) {
+                        bidx = d.ph.idx[best_i];
+                        if (bidx >= 0) btemp = d.cells.temp[bidx];
+                    }
                     d.bm_t[s * team + b] = best_t;
                     d.bm_i[s * team + b] = best_i;
+                    d.bm_idx[s * team + b] = bidx;
+                    d.bm_temp[s * team + b] = btemp;
                     __threadfence();
                     atomicAdd(&gst.arrive, 1u);
                 }
@@ -1933,14 +1959,18 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
                 double pre_t = DBL_MAX;
                 int pre_i = INT_MAX;
                 const bool have_pre = (team <= THREADS);
+                int pre_idx = -2;
+                double pre_temp = 0;
                 if (have_pre && (int)threadIdx.x < team) {
                     pre_t = *(volatile double *)&d.bm_t[s * team + threadIdx.x];
                     pre_i = *(volatile int *)&d.bm_i[s * team + threadIdx.x];
+                    pre_idx = *(volatile int *)&d.bm_idx[s * team + threadIdx.x];
+                    pre_temp = *(volatile double *)&d.bm_temp[s * team + threadIdx.x];
                 }
                 const int R = *(volatile int *)&gst.reloc_n;
                 if (R > 0) relocate_shard<THREADS>(d, st, s, R);
                 const bool released = event_body<THREADS>(d, s, st.first, R, team, 0, 0.0, st, &gst, k, s * team + bps, have_pre,
-                                                          pre_t, pre_i);
+                                                          pre_t, pre_i, pre_idx, pre_temp);
                 if (!released) {
                     // frame end, Klein-Nishina walk exhausted, cyclo-synchrotron run, unpolarised run: publish now
                     if (threadIdx.x == 0) {
@@ -2744,6 +2774,8 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
     memset(ctx->sh_host.data(), 0, sizeof(ShardState) * MAX_SHARDS);
     if ((e = dev_alloc(ctx->misc_allocs, &d.bm_t, BLOCKMIN_CAP)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = dev_alloc(ctx->misc_allocs, &d.bm_i, BLOCKMIN_CAP)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = dev_alloc(ctx->misc_allocs, &d.bm_idx, BLOCKMIN_CAP)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = dev_alloc(ctx->misc_allocs, &d.bm_temp, BLOCKMIN_CAP)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = dev_alloc(ctx->misc_allocs, &ctx->stat_dev, 1024)) != cudaSuccess) return bail(e, "cudaMalloc");
     // interpolation grids, Src/hot_x_section.c:470-480
     {
