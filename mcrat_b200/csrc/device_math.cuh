@@ -424,12 +424,14 @@ struct HotTable {
     const double *za; // za[j*(N_PH_E+1)+i]
 };
 
+// The table (221 x 81 doubles + the two grids, 145 KB) is immutable while a kernel runs: every access goes through the
+// read-only data cache (ld.global.nc, SASS LDG.E.CONSTANT), which the acquire loads of the persistent loop do not invalidate.
 __device__ inline int interp_bsearch(const double *xa, double x, int lo, int hi)
 {
     int ilo = lo, ihi = hi;
     while (ihi > ilo + 1) {
         int i = (ihi + ilo) / 2;
-        if (xa[i] > x)
+        if (__ldg(xa + i) > x)
             ihi = i;
         else
             ilo = i;
@@ -441,16 +443,16 @@ __device__ inline int interp_bsearch(const double *xa, double x, int lo, int hi)
 __device__ inline bool bilinear_eval(const HotTable &t, double x, double y, double &z)
 {
     const int nx = N_PH_E + 1, ny = N_T + 1;
-    if (x < t.xa[0] || x > t.xa[nx - 1]) return false;
-    if (y < t.ya[0] || y > t.ya[ny - 1]) return false;
+    if (x < __ldg(t.xa) || x > __ldg(t.xa + nx - 1)) return false;
+    if (y < __ldg(t.ya) || y > __ldg(t.ya + ny - 1)) return false;
     int xi = interp_bsearch(t.xa, x, 0, nx - 1);
     int yi = interp_bsearch(t.ya, y, 0, ny - 1);
-    double xmin = t.xa[xi], xmax = t.xa[xi + 1];
-    double ymin = t.ya[yi], ymax = t.ya[yi + 1];
-    double zminmin = t.za[yi * nx + xi];
-    double zminmax = t.za[(yi + 1) * nx + xi];
-    double zmaxmin = t.za[yi * nx + xi + 1];
-    double zmaxmax = t.za[(yi + 1) * nx + xi + 1];
+    double xmin = __ldg(t.xa + xi), xmax = __ldg(t.xa + xi + 1);
+    double ymin = __ldg(t.ya + yi), ymax = __ldg(t.ya + yi + 1);
+    double zminmin = __ldg(t.za + yi * nx + xi);
+    double zminmax = __ldg(t.za + (yi + 1) * nx + xi);
+    double zmaxmin = __ldg(t.za + yi * nx + xi + 1);
+    double zmaxmax = __ldg(t.za + (yi + 1) * nx + xi + 1);
     double dx = xmax - xmin, dy = ymax - ymin;
     double tt = (x - xmin) / dx;
     double u = (y - ymin) / dy;
