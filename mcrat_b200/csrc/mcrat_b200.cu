@@ -44,6 +44,7 @@ enum : unsigned char { F_MOVABLE = 1, F_RECALC = 2 };
 constexpr int MAX_DT = 16;         // pushes recorded by one event (1 + Klein-Nishina rejections)
 constexpr int BLOCKMIN_CAP = 8192; // per-block arg-min slots (persistent loop: two per sub-shard at 4096 sub-shards)
 constexpr int MAX_SHARDS = 4096;
+constexpr int PERSISTENT_MAX_PHOTONS = 1 << 21; // above this the list no longer fits in L2: streamed loop, streaming cache hints
 #ifndef MCRAT_SCAN_THREADS
 #define MCRAT_SCAN_THREADS 128
 #endif
@@ -154,6 +155,8 @@ struct DevCtx {
     int replay;
     int cap;
     int nshards, shard_size, blocks_per_shard;
+    int stream_hints; // the list is larger than L2: photon columns are streamed past it (ld/st.global.cs) so that the
+                      // cell geometry the pass gathers from stays resident
     PhotonCols ph;
     CellCols cells;
     HotTable table;
@@ -387,16 +390,33 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
         if (i == mini) continue; // the event block runs this photon's pass itself (persistent loop)
         // every column this photon can need is requested up front (one round trip to HBM instead
         // of three dependent ones); the momentum is used by the pushes, tau by the free-path draw
-        const unsigned char flags = d.ph.flags[i];
-        const int idx = d.ph.idx[i];
-        double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
-        const double p0 = d.ph.p0[i], p1 = d.ph.p1[i], p2 = d.ph.p2[i], p3 = d.ph.p3[i];
-        double tau = FUSE_MFP ? d.ph.tau[i] : 0.0;
+        unsigned char flags;
+        int idx;
+        double r0, r1, r2, p0, p1, p2, p3, tau;
+        if (!LOCAL_RELOC && d.stream_hints) {
+            flags = __ldcs(d.ph.flags + i);
+            idx = __ldcs(d.ph.idx + i);
+            r0 = __ldcs(d.ph.r0 + i); r1 = __ldcs(d.ph.r1 + i); r2 = __ldcs(d.ph.r2 + i);
+            p0 = __ldcs(d.ph.p0 + i); p1 = __ldcs(d.ph.p1 + i); p2 = __ldcs(d.ph.p2 + i); p3 = __ldcs(d.ph.p3 + i);
+            tau = FUSE_MFP ? __ldcs(d.ph.tau + i) : 0.0;
+        } else {
+            flags = d.ph.flags[i];
+            idx = d.ph.idx[i];
+            r0 = d.ph.r0[i]; r1 = d.ph.r1[i]; r2 = d.ph.r2[i];
+            p0 = d.ph.p0[i]; p1 = d.ph.p1[i]; p2 = d.ph.p2[i]; p3 = d.ph.p3[i];
+            tau = FUSE_MFP ? d.ph.tau[i] : 0.0;
+        }
         if (n_dt > 0 && (flags & F_MOVABLE) && i != pushed) {
             apply_pushes(sh, n_dt, p0, p1, p2, p3, r0, r1, r2);
-            d.ph.r0[i] = r0;
-            d.ph.r1[i] = r1;
-            d.ph.r2[i] = r2;
+            if (!LOCAL_RELOC && d.stream_hints) {
+                __stcs(d.ph.r0 + i, r0);
+                __stcs(d.ph.r1 + i, r1);
+                __stcs(d.ph.r2 + i, r2);
+            } else {
+                d.ph.r0[i] = r0;
+                d.ph.r1[i] = r1;
+                d.ph.r2[i] = r2;
+            }
         }
         // findContainingHydroCell, Src/mclib.c:469-597
         double h0, h1, h2;
@@ -452,7 +472,10 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
             if (idx != -1) d.ph.idx[i] = -1; // Src/mclib.c:589-595
         }
         if (FUSE_MFP && have_t) {
-            d.ph.tts[i] = t;
+            if (!LOCAL_RELOC && d.stream_hints)
+                __stcs(d.ph.tts + i, t);
+            else
+                d.ph.tts[i] = t;
             if (lex_less(t, i, best_t, best_i)) {
                 best_t = t;
                 best_i = i;
@@ -3022,6 +3045,7 @@ API int mcrat_b200_set_photons(mcrat_b200_ctx *ctx, const mcrat_photon *photons,
     CK(cudaSetDevice(ctx->cfg.device));
     if (int rc = ensure_photon_capacity(ctx, n)) return rc;
     ctx->d.cap = n;
+    ctx->d.stream_hints = (getenv("MCRAT_B200_NO_STREAM_HINTS") == nullptr && n > PERSISTENT_MAX_PHOTONS) ? 1 : 0;
     if (int rc = layout_shards(ctx, n)) return rc;
     if (n > 0) {
         CK(cudaMemcpyAsync(ctx->aos_dev, photons, (size_t)n * sizeof(mcrat_photon), cudaMemcpyHostToDevice, ctx->stream));
@@ -3541,7 +3565,6 @@ API int mcrat_b200_set_cs_rebin_params(mcrat_b200_ctx *ctx, double rebin_e_perc,
 
 // ---- the device-resident frame loop, Src/mcrat.c:761-851 ---------------------------------------------
 constexpr int MCRAT_B200_LOOP_FALLBACK = 1000; // internal: cooperative launch refused, use the streamed loop
-constexpr int PERSISTENT_MAX_PHOTONS = 1 << 21; // above this the pass is HBM-bound and wants the leaner pass_kernel
 
 __global__ void reset_protocol_kernel(DevCtx d)
 {

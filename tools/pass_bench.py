@@ -10,10 +10,11 @@ from mcrat_b200 import HotPath, synth  # noqa: E402
 
 nbig = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
 shards = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-cfg, hydro, photons, frame = synth.workload("C2")
+distinct = len(sys.argv) > 3 and sys.argv[3] == "distinct"  # nbig different photons (cells spread) instead of 1e5 repeated
+cfg, hydro, photons, frame = synth.workload("C2", n_photons=nbig if distinct else None)
 hp = HotPath(cfg, seed=7, profile=True, num_shards=shards)
 hp.set_hydro(hydro)
-hp.set_photons(np.resize(photons, nbig))
+hp.set_photons(photons if distinct else np.resize(photons, nbig))
 st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=1, switch=1)
 hp.kernel_times(reset=True)
 st = hp.run_frame(st["time_now"], 1.0 / frame["fps"], max_iters=24, switch=0)
