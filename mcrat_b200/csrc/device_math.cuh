@@ -681,7 +681,9 @@ __device__ inline int kn_scatter(int stokes, double &theta, double &phi, double 
     return 1;
 }
 
-// Src/mcrat_scattering.c:151-485 singleScatter
+// Src/mcrat_scattering.c:151-485 singleScatter in one piece.  The kernels use the staged form below
+// (scatter_stage_*), which is this function cut at its data dependencies; it stays here as the readable statement
+// of the whole scatter in the reference's order.
 __device__ inline int single_scatter(int stokes, double *el_comov, double *ph_comov, double *s, EventRng &rng)
 {
     const double z_axis[3] = {0, 0, 1};

@@ -994,7 +994,8 @@ constexpr int EVT_THREADS_MANY = 128; // many sub-shards: the three event warps 
 //            matrices of the boosts back (lorentzBoost's matrix depends on beta only), the
 //            alignment rotation and the Fano matrix.
 // Each piece is the reference's statement block, operation for operation: results are
-// bit-identical to the single-lane scatter_candidate below.
+// bit-identical to the single-lane form (single_scatter in device_math.cuh; the round-1 single-lane event is the
+// reference build of the A/B harness, tools/ab_compare.py).
 struct ScatterMail {
     double pre[64];         // first 64 uniforms of the event's Philox stream
     double zhat[3];
@@ -1094,6 +1095,7 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
                                      const double cand_temp, int n_dt, int *event_did_occur, EarlyRelease &early)
 {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stokes = d.stokes;
     // warp-0 lane-0 state carried across stages
     double theta = 0;
     KnTheta kn;
@@ -1198,13 +1200,15 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
         }
         __syncwarp();
         erot_arrive();
-        s[0] = d.ph.s0[i]; s[1] = d.ph.s1[i]; s[2] = d.ph.s2[i]; s[3] = d.ph.s3[i];
+        if (stokes) { s[0] = d.ph.s0[i]; s[1] = d.ph.s1[i]; s[2] = d.ph.s2[i]; s[3] = d.ph.s3[i]; }
         duo_bar();
-        // stokesRotation(fluid_beta, p, comv_p), Src/mclib.c:1190-1196
-        lane_angle(lane == 0 ? m.p + 1 : m.pc + 1, lane == 0 ? m.zhat : m.fb, lane == 0 ? m.p + 1 : m.pc + 1,
-                   lane == 0 ? m.fb : m.zhat, lane < 2, sn, cs);
-        rot_from_lane(sn, cs, 0, s);
-        rot_from_lane(sn, cs, 1, s);
+        if (stokes) {
+            // stokesRotation(fluid_beta, p, comv_p), Src/mclib.c:1190-1196
+            lane_angle(lane == 0 ? m.p + 1 : m.pc + 1, lane == 0 ? m.zhat : m.fb, lane == 0 ? m.p + 1 : m.pc + 1,
+                       lane == 0 ? m.fb : m.zhat, lane < 2, sn, cs);
+            rot_from_lane(sn, cs, 0, s);
+            rot_from_lane(sn, cs, 1, s);
+        }
     }
     T2W(10);
     trio_bar();
@@ -1214,11 +1218,13 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
         if (lane == 0) m.occurred = kn_accept_theta(theta, m.php[0], kn, rng);
         __syncwarp();
     } else if (w == 1) {
-        // stokesRotation(el_v, ph_comov, ph_p_prime), Src/mcrat_scattering.c:245-253
-        lane_angle(lane == 0 ? m.pcb + 1 : m.php + 1, lane == 0 ? m.zhat : m.el_v, lane == 0 ? m.pcb + 1 : m.php + 1,
-                   lane == 0 ? m.el_v : m.zhat, lane < 2, sn, cs);
-        rot_from_lane(sn, cs, 0, s);
-        rot_from_lane(sn, cs, 1, s);
+        if (stokes) {
+            // stokesRotation(el_v, ph_comov, ph_p_prime), Src/mcrat_scattering.c:245-253
+            lane_angle(lane == 0 ? m.pcb + 1 : m.php + 1, lane == 0 ? m.zhat : m.el_v, lane == 0 ? m.pcb + 1 : m.php + 1,
+                       lane == 0 ? m.el_v : m.zhat, lane < 2, sn, cs);
+            rot_from_lane(sn, cs, 0, s);
+            rot_from_lane(sn, cs, 1, s);
+        }
         if (lane == 0) {
             m.q = s[1];
             m.u = s[2];
@@ -1248,7 +1254,7 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
     // ---- stage D: azimuth + outgoing photon | -- | bookkeeping and early release of the pass blocks ----
     if (w == 0) {
         if (lane == 0) {
-            double phi = kn_phi(1, kn, m.q, m.u, rng);
+            double phi = kn_phi(stokes, kn, m.q, m.u, rng);
             double out[4];
             ScatterRot rot = m.rot;
             scatter_stage_out(m.php[0], kn.st, kn.ct, phi, rot, out);
@@ -1300,10 +1306,11 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
         __syncwarp();
     } else if (w == 1) {
         // lane 0: into the scattering plane (Src/mcrat_scattering.c:402-405); lane 1: back out of it (:438-447)
-        lane_angle(lane == 0 ? m.php + 1 : m.out + 1, lane == 0 ? m.zhat : m.php + 1, m.out + 1,
-                   lane == 0 ? m.php + 1 : m.zhat, lane < 2, sn, cs);
+        if (stokes)
+            lane_angle(lane == 0 ? m.php + 1 : m.out + 1, lane == 0 ? m.zhat : m.php + 1, m.out + 1,
+                       lane == 0 ? m.php + 1 : m.zhat, lane < 2, sn, cs);
     } else {
-        if (lane == 0) {
+        if (lane == 0 && stokes) {
             double f[5];
             scatter_stage_fano(m.php, m.out, f);
 #pragma unroll
@@ -1315,7 +1322,9 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
     trio_bar();
     T2W(17);
     // ---- stage F: the remaining angles, the Stokes chain applied in order, write-back ----
-    if (w == 1) {
+    if (w == 1 && !stokes) {
+        // unpolarised run (STOKES_SWITCH OFF): no Stokes chain; warp 1 only supplied rotateElectron's angles
+    } else if (w == 1) {
         // lane 0 / 1: stokesRotation(-el_v, out, pc_new), Src/mcrat_scattering.c:465-473 (`out` as lorentzBoost
         // left it); lane 2 / 3: stokesRotation(-fluid_beta, pc_fin, p_new), Src/mclib.c:1267-1287
         double sn2, cs2;
@@ -1414,47 +1423,6 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
             d.bm_idx[early.bm_index] = (state == 1) ? cell_idx : -1;
             d.bm_temp[early.bm_index] = cell.temp;
         }
-    }
-}
-
-__device__ void scatter_candidate(DevCtx &d, ShardState &st, EventRng &rng, int i, int n_dt, bool &event_did_occur)
-{
-    // the candidate's own position after every push of this event so far (Src/mclib.c:1138)
-    const unsigned char flags = d.ph.flags[i];
-    double p[4] = {d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i]};
-    double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
-    if (flags & F_MOVABLE) apply_pushes(st, n_dt, p[0], p[1], p[2], p[3], r0, r1, r2);
-    const int index = d.ph.idx[i];
-    CellState c = load_cell_state(d.cells, index);
-    double fb[3];
-    fluid_beta_of(d, c, r0, r1, fb); // ph_phi = atan2(r1, r0), Src/mclib.c:1151-1174
-    double pc[4] = {d.ph.c0[i], d.ph.c1[i], d.ph.c2[i], d.ph.c3[i]};
-    double s[4] = {d.ph.s0[i], d.ph.s1[i], d.ph.s2[i], d.ph.s3[i]};
-    if (d.stokes) stokes_rotation(fb, p + 1, pc + 1, s);
-    double el[4];
-    single_thermal_electron(el, c.temp, pc, rng);
-    int occurred = single_scatter(d.stokes, el, pc, s, rng);
-    if (occurred == 1) {
-        double nfb[3] = {-1 * fb[0], -1 * fb[1], -1 * fb[2]};
-        lorentz_boost(nfb, pc, p, true);
-        if (d.stokes) {
-            stokes_rotation(nfb, pc + 1, p + 1, s);
-            d.ph.s0[i] = s[0];
-            d.ph.s1[i] = s[1];
-            d.ph.s2[i] = s[2];
-            d.ph.s3[i] = s[3];
-        }
-        d.ph.p0[i] = p[0]; d.ph.p1[i] = p[1]; d.ph.p2[i] = p[2]; d.ph.p3[i] = p[3];
-        d.ph.c0[i] = pc[0]; d.ph.c1[i] = pc[1]; d.ph.c2[i] = pc[2]; d.ph.c3[i] = pc[3];
-        d.ph.nscatt[i] = d.ph.nscatt[i] + 1;
-        d.ph.flags[i] = flags | F_RECALC;
-        // this photon is already at its pushed position: the next pass must not push it again
-        d.ph.r0[i] = r0;
-        d.ph.r1[i] = r1;
-        d.ph.r2[i] = r2;
-        st.pushed_slot = i;
-        st.scatt_cnt += 1;
-        event_did_occur = true;
     }
 }
 
@@ -1709,18 +1677,10 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
         }
         __syncthreads();
         if (sh_try) {
-            if (d.stokes) {
-                // three warps: scattering lane | Stokes chain | helper
-                if (threadIdx.x < SCATTER_THREADS)
-                    scatter_candidate_3w(d, st, rng_sh, mail, sh_cand_i, sh_cand_idx, sh_cand_known ? sh_cand_temp : -1.0, n_dt,
-                                         &sh_event, early);
-            } else if (threadIdx.x == 0) {
-                EventRng rng = rng_sh;
-                bool event = false;
-                scatter_candidate(d, st, rng, sh_cand_i, n_dt, event);
-                rng_sh = rng;
-                if (event) sh_event = 1;
-            }
+            // three warps: scattering lane | Stokes chain (idle when STOKES_SWITCH is OFF) | helper
+            if (threadIdx.x < SCATTER_THREADS)
+                scatter_candidate_3w(d, st, rng_sh, mail, sh_cand_i, sh_cand_idx, sh_cand_known ? sh_cand_temp : -1.0, n_dt,
+                                     &sh_event, early);
             __syncthreads();
         }
         if (sh_event) break;
@@ -1995,7 +1955,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
                 const bool released = event_body<THREADS>(d, s, st.first, R, team, 0, 0.0, st, &gst, k, s * team + bps, have_pre,
                                                           pre_t, pre_i, pre_idx, pre_temp);
                 if (!released) {
-                    // frame end, Klein-Nishina walk exhausted, cyclo-synchrotron run, unpolarised run: publish now
+                    // frame end, Klein-Nishina walk exhausted, cyclo-synchrotron run: publish now
                     if (threadIdx.x == 0) {
                         st.halt = (loop_stopped(gs, st) || st.reloc_heavy) ? 1 : 0;
                         st.mini_slot = -1;
