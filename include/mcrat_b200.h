@@ -228,6 +228,10 @@ int mcrat_b200_rescan_all(mcrat_b200_ctx *ctx, long long *cell_evals, float *ela
 /* sustained FP64-pipe instruction issue rate of this GPU (independent DFMA chains on all SMs),
  * G thread-instructions/s; x2 = DFMA GFLOP/s */
 int mcrat_b200_measure_fp64_peak(mcrat_b200_ctx *ctx, double *ginstr_per_s);
+/* self-test: the free path divides by C_LIGHT (Src/mclib.c:684) with an FMA-corrected multiplication by the
+ * reciprocal; this compares it bit for bit with the general division on 4 x n doubles and returns the number of
+ * differing results (0 expected) */
+int mcrat_b200_selftest_div_by_c(mcrat_b200_ctx *ctx, long long n, unsigned seed, long long *mismatches);
 /* streaming copy bandwidth of this GPU, GB/s (read+write bytes) */
 int mcrat_b200_measure_hbm_peak(mcrat_b200_ctx *ctx, double *gb_per_s);
 

@@ -70,6 +70,11 @@ constexpr int RELOC_LIST_SCAN_MAX = 2048;
 
 struct PhotonCols {
     double *r0, *r1, *r2, *p0, *p1, *p2, *p3, *c0, *c1, *c2, *c3, *s0, *s1, *s2, *s3, *nscatt, *weight, *tau, *tts;
+    // derived columns, rewritten whenever p / tau are (store_momentum, store_tau): what the pass reads instead of
+    // them.  v_k = (p_k * (1/p0)) * C_LIGHT is the reference's own intermediate of the push (Src/mclib.c:1074-1080),
+    // ntau = -1/tau that of the free path (Src/mclib.c:683): same roundings, one division each per *change* of the
+    // photon instead of per photon-iteration, and 24 + 8 bytes per photon-iteration instead of 32 + 8.
+    double *v0, *v1, *v2, *ntau;
     int *idx;
     unsigned char *flags;
     char *type;
@@ -274,6 +279,55 @@ __device__ __forceinline__ double free_path_time(double tau, double xi)
     return mfp / C_LIGHT;
 }
 
+// x / C_LIGHT, correctly rounded, without the general division: q = RN(x * rc) with rc = RN(1 / C_LIGHT) is within
+// an ulp of the quotient, r = x - q * C_LIGHT is exact in one FMA, and RN(q + r * rc) is the correctly rounded
+// quotient (Markstein's theorem; C_LIGHT's significand is not all ones).  Outside the range where q, r stay normal
+// and finite the true division runs.  tests/test_gpu_parity.py::test_division_by_c_is_exact compares the two bit
+// for bit; tools/div_by_c_check.c does so on the host over 4e9 significands.
+__device__ __forceinline__ double div_by_c(double x)
+{
+    const double rc = 1.0 / C_LIGHT; // folded at compile time, correctly rounded
+    const double ax = fabs(x);
+    if (!(ax > 1e-280 && ax < 1e300)) return x / C_LIGHT;
+    const double q = x * rc;
+    const double r = fma(-q, C_LIGHT, x);
+    return fma(r, rc, q);
+}
+
+// free_path_time with ntau = -1/tau already formed (PhotonCols.ntau): bit-identical to it
+__device__ __forceinline__ double free_path_time_n(double ntau, double xi)
+{
+    double mfp = ntau * log(xi);
+    return div_by_c(mfp);
+}
+
+__device__ __forceinline__ void store_momentum(PhotonCols &ph, int i, double p0, double p1, double p2, double p3)
+{
+    ph.p0[i] = p0; ph.p1[i] = p1; ph.p2[i] = p2; ph.p3[i] = p3;
+    const double div = 1.0 / p0; // Src/mclib.c:1074
+    ph.v0[i] = p1 * div * C_LIGHT;
+    ph.v1[i] = p2 * div * C_LIGHT;
+    ph.v2[i] = p3 * div * C_LIGHT;
+}
+
+__device__ __forceinline__ void store_tau(PhotonCols &ph, int i, double tau)
+{
+    ph.tau[i] = tau;
+    ph.ntau[i] = -1.0 / tau;
+}
+
+// the pushes with v_k = (p_k / p0) * C_LIGHT already formed (PhotonCols.v*): bit-identical to apply_pushes
+__device__ __forceinline__ void apply_pushes_v(const ShardState &sh, int n_dt, double v0, double v1, double v2, double &r0,
+                                               double &r1, double &r2)
+{
+    for (int k = 0; k < n_dt; ++k) {
+        double t = sh.dt_list[k];
+        r0 += v0 * t;
+        r1 += v1 * t;
+        r2 += v2 * t;
+    }
+}
+
 // pending pushes of a shard's last event, applied one by one: the reference pushes once per
 // candidate it tries (Src/mclib.c:1138, 1332) and FP addition is not associative
 __device__ __forceinline__ void apply_pushes(const ShardState &sh, int n_dt, double p0, double p1, double p2, double p3,
@@ -296,7 +350,7 @@ __global__ void unpack_kernel(DevCtx d, const mcrat_photon *aos, int n)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         mcrat_photon p = aos[i];
         d.ph.type[i] = p.type;
-        d.ph.p0[i] = p.p0; d.ph.p1[i] = p.p1; d.ph.p2[i] = p.p2; d.ph.p3[i] = p.p3;
+        store_momentum(d.ph, i, p.p0, p.p1, p.p2, p.p3);
         d.ph.c0[i] = p.comv_p0; d.ph.c1[i] = p.comv_p1; d.ph.c2[i] = p.comv_p2; d.ph.c3[i] = p.comv_p3;
         d.ph.r0[i] = p.r0; d.ph.r1[i] = p.r1; d.ph.r2[i] = p.r2;
         d.ph.s0[i] = p.s0; d.ph.s1[i] = p.s1; d.ph.s2[i] = p.s2; d.ph.s3[i] = p.s3;
@@ -304,7 +358,7 @@ __global__ void unpack_kernel(DevCtx d, const mcrat_photon *aos, int n)
         d.ph.weight[i] = p.weight;
         d.ph.idx[i] = p.nearest_block_index;
         d.ph.tts[i] = p.time_to_scatter;
-        d.ph.tau[i] = p.total_optical_depth;
+        store_tau(d.ph, i, p.total_optical_depth);
         unsigned char f = 0;
         if ((p.type != 'p') && (p.weight != 0)) f |= F_MOVABLE; // Src/mclib.c:1070
         if (p.recalc_properties == 1) f |= F_RECALC;
@@ -392,22 +446,22 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
         // of three dependent ones); the momentum is used by the pushes, tau by the free-path draw
         unsigned char flags;
         int idx;
-        double r0, r1, r2, p0, p1, p2, p3, tau;
+        double r0, r1, r2, v0, v1, v2, ntau;
         if (!LOCAL_RELOC && d.stream_hints) {
             flags = __ldcs(d.ph.flags + i);
             idx = __ldcs(d.ph.idx + i);
             r0 = __ldcs(d.ph.r0 + i); r1 = __ldcs(d.ph.r1 + i); r2 = __ldcs(d.ph.r2 + i);
-            p0 = __ldcs(d.ph.p0 + i); p1 = __ldcs(d.ph.p1 + i); p2 = __ldcs(d.ph.p2 + i); p3 = __ldcs(d.ph.p3 + i);
-            tau = FUSE_MFP ? __ldcs(d.ph.tau + i) : 0.0;
+            v0 = __ldcs(d.ph.v0 + i); v1 = __ldcs(d.ph.v1 + i); v2 = __ldcs(d.ph.v2 + i);
+            ntau = FUSE_MFP ? __ldcs(d.ph.ntau + i) : 0.0;
         } else {
             flags = d.ph.flags[i];
             idx = d.ph.idx[i];
             r0 = d.ph.r0[i]; r1 = d.ph.r1[i]; r2 = d.ph.r2[i];
-            p0 = d.ph.p0[i]; p1 = d.ph.p1[i]; p2 = d.ph.p2[i]; p3 = d.ph.p3[i];
-            tau = FUSE_MFP ? d.ph.tau[i] : 0.0;
+            v0 = d.ph.v0[i]; v1 = d.ph.v1[i]; v2 = d.ph.v2[i];
+            ntau = FUSE_MFP ? d.ph.ntau[i] : 0.0;
         }
         if (n_dt > 0 && (flags & F_MOVABLE) && i != pushed) {
-            apply_pushes(sh, n_dt, p0, p1, p2, p3, r0, r1, r2);
+            apply_pushes_v(sh, n_dt, v0, v1, v2, r0, r1, r2);
             if (!LOCAL_RELOC && d.stream_hints) {
                 __stcs(d.ph.r0 + i, r0);
                 __stcs(d.ph.r1 + i, r1);
@@ -454,18 +508,20 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
                 if (flags & F_RECALC) {
                     CellState c = load_cell_state(d.cells, idx);
                     int terr = 0;
-                    tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, p1, p2, p3, d.ph.c0[i], &terr);
+                    const double tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, d.ph.p1[i], d.ph.p2[i],
+                                                     d.ph.p3[i], d.ph.c0[i], &terr);
                     if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
-                    d.ph.tau[i] = tau;
+                    store_tau(d.ph, i, tau);
+                    ntau = -1.0 / tau;
                     d.ph.flags[i] = flags & ~F_RECALC;
                 }
 #if defined(MCRAT_EXP_NOCOMPUTE)
                 // ablation build (profiles/ncu_r01_summary.md, "pass kernel: where the time goes"): the memory
                 // pattern alone, without Philox / log / divisions.  Never defined in the product build.
-                t = tau * (double)j;
+                t = ntau * (double)j;
 #else
                 double xi = philox_mfp_uniform(d.k0, k1, iter, (uint32_t)j);
-                t = free_path_time(tau, xi);
+                t = free_path_time_n(ntau, xi);
 #endif
             }
         } else {
@@ -514,7 +570,7 @@ __global__ void __launch_bounds__(PASS_THREADS) flush_push_kernel(DevCtx d)
         unsigned char flags = d.ph.flags[i];
         if ((flags & F_MOVABLE) && i != sh.pushed_slot) {
             double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
-            apply_pushes(sh, n_dt, d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i], r0, r1, r2);
+            apply_pushes_v(sh, n_dt, d.ph.v0[i], d.ph.v1[i], d.ph.v2[i], r0, r1, r2);
             d.ph.r0[i] = r0;
             d.ph.r1[i] = r1;
             d.ph.r2[i] = r2;
@@ -851,7 +907,7 @@ __device__ __forceinline__ bool finish_one(DevCtx &d, ShardState &sh, const int 
         int terr = 0;
         double tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, p[1], p[2], p[3], pc[0], &terr);
         if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
-        d.ph.tau[i] = tau;
+        store_tau(d.ph, i, tau);
         d.ph.flags[i] = d.ph.flags[i] & ~F_RECALC;
         if (sw == 0) atomicAdd((unsigned long long *)&sh.reloc_total, 1ull); // Src/mclib.c:579, 608-611
         if (FUSE_MFP) {
@@ -934,7 +990,7 @@ __global__ void __launch_bounds__(256) mfp_kernel(DevCtx d, int write_blockmin)
             tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, d.ph.r0[i], d.ph.r1[i], d.ph.p1[i], d.ph.p2[i],
                                 d.ph.p3[i], d.ph.c0[i], &terr);
             if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
-            d.ph.tau[i] = tau;
+            store_tau(d.ph, i, tau);
             d.ph.flags[i] = flags & ~F_RECALC;
         } else {
             tau = d.ph.tau[i];
@@ -1349,7 +1405,7 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
             d.ph.s3[i] = s[3];
         }
     } else if (w == 0 && lane == 0) {
-        d.ph.p0[i] = m.p_new[0]; d.ph.p1[i] = m.p_new[1]; d.ph.p2[i] = m.p_new[2]; d.ph.p3[i] = m.p_new[3];
+        store_momentum(d.ph, i, m.p_new[0], m.p_new[1], m.p_new[2], m.p_new[3]);
         d.ph.c0[i] = m.pc_fin[0]; d.ph.c1[i] = m.pc_fin[1]; d.ph.c2[i] = m.pc_fin[2]; d.ph.c3[i] = m.pc_fin[3];
         d.ph.nscatt[i] = d.ph.nscatt[i] + 1;
         d.ph.flags[i] = m.flags | F_RECALC;
@@ -1400,7 +1456,7 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
             double bt = DBL_MAX;
             int bi = INT_MAX;
             if (state == 1) {
-                d.ph.tau[i] = tau_next;
+                store_tau(d.ph, i, tau_next);
                 d.ph.flags[i] = m.flags & ~F_RECALC;
                 d.ph.tts[i] = t_next;
                 bt = t_next;
@@ -1475,7 +1531,7 @@ __device__ void cs_emit_single(DevCtx &d, EventRng &rng, int scatt, int slot)
         hydro_coord_to_mcrat(d.dims, d.geom, pos, cr0, cr1, cr2);
     else
         hydro_coord_to_mcrat(d.dims, d.geom, pos, cr0, cr1, position_phi);
-    d.ph.p0[slot] = l_boost[0]; d.ph.p1[slot] = l_boost[1]; d.ph.p2[slot] = l_boost[2]; d.ph.p3[slot] = l_boost[3];
+    store_momentum(d.ph, slot, l_boost[0], l_boost[1], l_boost[2], l_boost[3]);
     d.ph.c0[slot] = p_comv[0]; d.ph.c1[slot] = p_comv[1]; d.ph.c2[slot] = p_comv[2]; d.ph.c3[slot] = p_comv[3];
     d.ph.r0[slot] = pos[0]; d.ph.r1[slot] = pos[1]; d.ph.r2[slot] = pos[2];
     d.ph.s0[slot] = 1; d.ph.s1[slot] = 0; d.ph.s2[slot] = 0; d.ph.s3[slot] = 0;
@@ -1485,7 +1541,7 @@ __device__ void cs_emit_single(DevCtx &d, EventRng &rng, int scatt, int slot)
     d.ph.type[slot] = 'p';
     d.ph.flags[slot] = F_RECALC; // pool photons do not move (Src/mclib.c:1070)
     d.ph.tts[slot] = 0;
-    d.ph.tau[slot] = 0;
+    store_tau(d.ph, slot, 0);
     // new random position of the scattered photon inside its cell
     const double4 a = d.cells.geoA[i];
     double size0, size1, size2 = 0;
@@ -2068,12 +2124,12 @@ __global__ void __launch_bounds__(256) cs_absorb_kernel(DevCtx d)
                 d.ph.weight[i] = 0;
                 d.ph.idx[i] = -1;
                 d.ph.flags[i] = 0;
-                d.ph.p0[i] = 0; d.ph.p1[i] = 0; d.ph.p2[i] = 0; d.ph.p3[i] = 0;
+                store_momentum(d.ph, i, 0, 0, 0, 0);
                 d.ph.c0[i] = 0; d.ph.c1[i] = 0; d.ph.c2[i] = 0; d.ph.c3[i] = 0;
                 d.ph.r0[i] = 0; d.ph.r1[i] = 0; d.ph.r2[i] = 0;
                 d.ph.s0[i] = 0; d.ph.s1[i] = 0; d.ph.s2[i] = 0; d.ph.s3[i] = 0;
                 d.ph.nscatt[i] = 0;
-                d.ph.tau[i] = 0;
+                store_tau(d.ph, i, 0);
             } else if ((type == 'k') || (type == 'c')) {
                 scatt_cnt++;
             }
@@ -2450,12 +2506,12 @@ __device__ __forceinline__ void set_null_photon(DevCtx &d, int i) // setNullPhot
     d.ph.weight[i] = 0;
     d.ph.idx[i] = -1;
     d.ph.flags[i] = 0;
-    d.ph.p0[i] = 0; d.ph.p1[i] = 0; d.ph.p2[i] = 0; d.ph.p3[i] = 0;
+    store_momentum(d.ph, i, 0, 0, 0, 0);
     d.ph.c0[i] = 0; d.ph.c1[i] = 0; d.ph.c2[i] = 0; d.ph.c3[i] = 0;
     d.ph.r0[i] = 0; d.ph.r1[i] = 0; d.ph.r2[i] = 0;
     d.ph.s0[i] = 0; d.ph.s1[i] = 0; d.ph.s2[i] = 0; d.ph.s3[i] = 0;
     d.ph.nscatt[i] = 0;
-    d.ph.tau[i] = 0;
+    store_tau(d.ph, i, 0);
 }
 
 // :588-596 null every 'k' / 'c' photon, then count the null slots of each 256-slot block
@@ -2502,7 +2558,7 @@ __global__ void __launch_bounds__(256) rebin_place_kernel(DevCtx d, const mcrat_
     const mcrat_photon p = rebinned[k];
     if (p.type == 'N') return; // only the non-null rebinned photons are copied (:190-199)
     d.ph.type[i] = p.type;
-    d.ph.p0[i] = p.p0; d.ph.p1[i] = p.p1; d.ph.p2[i] = p.p2; d.ph.p3[i] = p.p3;
+    store_momentum(d.ph, i, p.p0, p.p1, p.p2, p.p3);
     d.ph.c0[i] = 0; d.ph.c1[i] = 0; d.ph.c2[i] = 0; d.ph.c3[i] = 0;
     d.ph.r0[i] = p.r0; d.ph.r1[i] = p.r1; d.ph.r2[i] = p.r2;
     d.ph.s0[i] = p.s0; d.ph.s1[i] = p.s1; d.ph.s2[i] = p.s2; d.ph.s3[i] = p.s3;
@@ -2510,7 +2566,7 @@ __global__ void __launch_bounds__(256) rebin_place_kernel(DevCtx d, const mcrat_
     d.ph.weight[i] = p.weight;
     d.ph.idx[i] = p.nearest_block_index;
     d.ph.tts[i] = 0;
-    d.ph.tau[i] = 0;
+    store_tau(d.ph, i, 0);
     d.ph.flags[i] = (unsigned char)(((p.weight != 0) ? F_MOVABLE : 0) | F_RECALC);
 }
 
@@ -2929,9 +2985,9 @@ static int ensure_photon_capacity(mcrat_b200_ctx *ctx, int n)
     free_pool(ctx->ph_allocs);
     int cap = n + n / 8 + 1024;
     PhotonCols &p = ctx->d.ph;
-    double **cols[19] = {&p.r0, &p.r1, &p.r2, &p.p0, &p.p1, &p.p2, &p.p3, &p.c0, &p.c1, &p.c2,
-                         &p.c3, &p.s0, &p.s1, &p.s2, &p.s3, &p.nscatt, &p.weight, &p.tau, &p.tts};
-    for (int k = 0; k < 19; ++k) CK(dev_alloc(ctx->ph_allocs, cols[k], (size_t)cap));
+    double **cols[23] = {&p.r0, &p.r1, &p.r2, &p.p0, &p.p1, &p.p2, &p.p3, &p.c0, &p.c1, &p.c2, &p.c3, &p.s0,
+                         &p.s1, &p.s2, &p.s3, &p.nscatt, &p.weight, &p.tau, &p.tts, &p.v0, &p.v1, &p.v2, &p.ntau};
+    for (int k = 0; k < 23; ++k) CK(dev_alloc(ctx->ph_allocs, cols[k], (size_t)cap));
     CK(dev_alloc(ctx->ph_allocs, &p.idx, (size_t)cap));
     CK(dev_alloc(ctx->ph_allocs, &p.flags, (size_t)cap));
     CK(dev_alloc(ctx->ph_allocs, &p.type, (size_t)cap));
@@ -3885,6 +3941,40 @@ API int mcrat_b200_measure_fp64_peak(mcrat_b200_ctx *ctx, double *ginstr_per_s)
     // per thread and iteration: 16 DFMA (one FP64-pipe instruction each)
     double instr = (double)blocks * threads * (double)iters * 16.0;
     *ginstr_per_s = instr / (best * 1e-3) / 1e9;
+    return MCRAT_B200_OK;
+}
+
+// self-test of div_by_c against the hardware-rounded division: n Philox-drawn significands at each of the binary
+// exponents -60 ... +60 around 1 (plus the range ends, where the true division is taken anyway)
+__global__ void div_by_c_check_kernel(long long n, uint32_t seed, unsigned long long *bad)
+{
+    unsigned long long mine = 0;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        double a, b;
+        philox_doubles((uint32_t)k, (uint32_t)(k >> 32), 0u, 7u, seed, 0x64697643u, a, b);
+        const int e = (int)(k % 121) - 60;
+        const double xs[4] = {ldexp(1.0 + a, e), -ldexp(1.0 + b, e), ldexp(1.0 + a, 8 * e), ldexp(1.0 + b, -1000 + e)};
+        for (int q = 0; q < 4; ++q) {
+            const double x = xs[q];
+            if (__double_as_longlong(div_by_c(x)) != __double_as_longlong(x / C_LIGHT)) mine++;
+        }
+    }
+    if (mine) atomicAdd(bad, mine);
+}
+
+API int mcrat_b200_selftest_div_by_c(mcrat_b200_ctx *ctx, long long n, unsigned seed, long long *mismatches)
+{
+    if (!ctx || !mismatches || n < 0) return MCRAT_B200_ERR_ARG;
+    unsigned long long *bad = nullptr;
+    CK(cudaMalloc((void **)&bad, sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(bad, 0, sizeof(unsigned long long), ctx->stream));
+    div_by_c_check_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(n, seed, bad);
+    ctx->launches++;
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(bad);
+    *mismatches = (long long)h;
     return MCRAT_B200_OK;
 }
 

@@ -72,6 +72,7 @@ EXPORTS = [
     "mcrat_b200_average_photon_energy", "mcrat_b200_run_frame", "mcrat_b200_set_loop_mode",
     "mcrat_b200_rebin_cyclosynch_comp_photons", "mcrat_b200_set_cs_rebin_params", "mcrat_b200_get_kernel_times",
     "mcrat_b200_launch_count", "mcrat_b200_rescan_all", "mcrat_b200_measure_fp64_peak", "mcrat_b200_measure_hbm_peak",
+    "mcrat_b200_selftest_div_by_c",
 ]
 
 
@@ -320,6 +321,11 @@ class HotPath:
     def measure_fp64_peak(self):
         v = C.c_double(0)
         self._ck(self.L.mcrat_b200_measure_fp64_peak(self.ctx, C.byref(v)))
+        return v.value
+
+    def selftest_div_by_c(self, n, seed=1):
+        v = C.c_longlong(-1)
+        self._ck(self.L.mcrat_b200_selftest_div_by_c(self.ctx, C.c_longlong(n), C.c_uint(seed), C.byref(v)))
         return v.value
 
     def measure_hbm_peak(self):

@@ -204,3 +204,12 @@ def test_refused_cooperative_launch_falls_back_to_the_streamed_loop(monkeypatch)
     assert lb > la + 200  # four launches per iteration instead of one per frame
     for f in pa.dtype.names:
         assert np.array_equal(pa[f], pb[f], equal_nan=(pa.dtype[f].kind == "f")), f
+
+
+def test_division_by_c_is_exact():
+    """The free path's division by C_LIGHT (Src/mclib.c:684) runs as an FMA-corrected multiplication by the reciprocal;
+    it has to return the correctly rounded quotient, bit for bit, for every input (4 x 5e7 doubles here, all binades the
+    free path can reach plus both ends of the double range)."""
+    cfg, hydro, photons, frame = synth.workload("C1", scale=0.25, n_photons=64)
+    hp = HotPath(cfg, seed=3)
+    assert hp.selftest_div_by_c(50_000_000, seed=11) == 0
