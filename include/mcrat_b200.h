@@ -204,6 +204,13 @@ int mcrat_b200_average_photon_energy(mcrat_b200_ctx *ctx, double *avg_energy);
 int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remaining_time, long long max_iters,
                          int find_nearest_grid_switch, mcrat_b200_frame_stats *stats);
 
+/* The reference re-checks every photon's cached cell in every iteration (findContainingHydroCell, Src/mclib.c:469-597).
+ * The pass kernel skips that re-check for a photon while the total length of the pushes since its last re-check is
+ * provably smaller than its distance to the boundary of its cell and of the domain (a per-shard path counter against
+ * a per-photon threshold); a skipped re-check would have succeeded and has no side effect, so results are identical.
+ * mode 0: never skip; 1 (default): skip; 2: decide as in 1 but re-check anyway and fail the frame with
+ * MCRAT_B200_ERR_STATE if a skipped photon had left its cell (test mode). */
+int mcrat_b200_set_recheck_skip(mcrat_b200_ctx *ctx, int mode);
 /* How the loop is driven.  STREAMED: four stream-ordered kernel launches per iteration (pass, re-locate,
  * finish, event), enqueued in growing batches.  PERSISTENT: one cooperative launch per frame; every
  * sub-shard is iterated by resident blocks that hand over through a generation word in global memory

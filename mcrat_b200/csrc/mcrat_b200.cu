@@ -75,6 +75,9 @@ struct PhotonCols {
     // ntau = -1/tau that of the free path (Src/mclib.c:683): same roundings, one division each per *change* of the
     // photon instead of per photon-iteration, and 24 + 8 bytes per photon-iteration instead of 32 + 8.
     double *v0, *v1, *v2, *ntau;
+    // safe[i]: the value of the shard's path counter (ShardState.path) up to which photon i provably cannot have left
+    // its cell or the domain, so that the pass may skip its containment re-check (0: always re-check); see safe_path()
+    unsigned long long *safe;
     int *idx;
     unsigned char *flags;
     char *type;
@@ -102,6 +105,7 @@ struct ShardState {
     double dt_list[MAX_DT];
     double head_tts;
     unsigned long long iter;
+    unsigned long long path; // length of all pushes before the pending ones, in 1/PATH_SCALE cm, rounded up (path_units)
     long long scatt_cnt, reloc_total, slots, iters_done;
     int n_dt, pushed_slot; // pushed_slot: global slot index
     int done, pause_cs, counted_stopped;
@@ -160,6 +164,10 @@ struct DevCtx {
     int replay;
     int cap;
     int nshards, shard_size, blocks_per_shard;
+    int recheck_skip; // 0: every photon re-checks its cell in every pass; 1: skip while provably inside (safe_path);
+                      // 2: decide as in 1 but re-check anyway and raise an error if a skipped photon had left (tests)
+    const double *dom_dev; // cells.dom in global memory, for safe_path()
+    double path_pad;  // bound on the rounding error of one push of a photon inside the domain, cm
     int stream_hints; // the list is larger than L2: photon columns are streamed past it (ld/st.global.cs) so that the
                       // cell geometry the pass gathers from stays resident
     PhotonCols ph;
@@ -197,6 +205,106 @@ __device__ __forceinline__ bool loop_stopped(const GlobalState &gs, const ShardS
 __device__ __forceinline__ int shard_of(const DevCtx &d, int slot) { return slot / d.shard_size; }
 
 __device__ __forceinline__ bool lex_less(double ta, int ia, double tb, int ib) { return (ta < tb) || (ta == tb && ia < ib); }
+
+// ---- skipping the containment re-check while a photon provably cannot have left its cell ------------------------
+// The reference re-checks every photon's cached cell in every iteration (Src/mclib.c:469-597), and almost always
+// finds it unchanged.  A photon that sits at distance >= dist from the boundary of (its cell intersected with the domain)
+// stays inside while the total length of its pushes is < dist, whatever its direction; all movable photons of a
+// shard are pushed by the same times, so one counter per shard (ShardState.path, integer units, every push rounded
+// up, plus a bound on the rounding of the position update) and one threshold per photon (PhotonCols.safe) decide it.
+// The re-check that is skipped has no side effect when it succeeds, so the photons are bit-identical; the margins
+// (safe_distance) are far above the rounding of the reference's coordinate evaluation.
+constexpr double PATH_SCALE = 256.0;
+constexpr unsigned long long PATH_SAT = 1ull << 62;
+
+__device__ __forceinline__ unsigned long long path_units(double dt, double pad)
+{
+    const double x = (C_LIGHT * fabs(dt) * (1.0 + 1e-9) + pad) * PATH_SCALE;
+    if (!(x < 4e18)) return PATH_SAT;
+    return __double2ull_ru(x);
+}
+
+__device__ __forceinline__ unsigned long long path_add(unsigned long long a, unsigned long long b)
+{
+    const unsigned long long c = a + b;
+    return (a >= PATH_SAT || b >= PATH_SAT || c >= PATH_SAT) ? PATH_SAT : c;
+}
+
+// the pending pushes become part of the path; called wherever a shard's push list is replaced or cleared
+__device__ __forceinline__ void fold_path(ShardState &sh, double pad)
+{
+    unsigned long long p = sh.path;
+    for (int k = 0; k < sh.n_dt; ++k) p = path_add(p, path_units(sh.dt_list[k], pad));
+    sh.path = p;
+}
+
+__device__ __forceinline__ unsigned long long path_after_pending(const ShardState &sh, double pad)
+{
+    unsigned long long p = sh.path;
+    for (int k = 0; k < sh.n_dt; ++k) p = path_add(p, path_units(sh.dt_list[k], pad));
+    return p;
+}
+
+// Lower bound (cm) on the Euclidean distance from the photon at hydro coordinates h (inside cell blk and inside the
+// domain) to the nearest point outside either.  Per coordinate the margin m = min(half size - |h - c|, h - dom_lo,
+// dom_hi - h); a length coordinate (x, y, z, cylindrical / spherical radius) is 1-Lipschitz in the position, an
+// angle seen from the origin (axis) changes by at most asin(length / r) (asin(length / rho)), and sin(m) >= 0.8 m
+// on [0, 1].  Margins below 1e-7 of the coordinate's scale (1e-6 rad) give 0: never skipped.  The factor 0.5
+// leaves half of every margin for the rounding of the coordinates themselves.
+__device__ __forceinline__ double margin_length(double h, double c, double hs, double lo, double hi)
+{
+    const double m = fmin(hs - fabs(h - c), fmin(h - lo, hi - h));
+    return (m > 1e-7 * fmax(fabs(h), fabs(c))) ? m : 0.0;
+}
+
+__device__ __forceinline__ double margin_angle(double h, double c, double hs, double lo, double hi, double full, double lever)
+{
+    double m = fmin(hs - fabs(h - c), fmin(h - lo, hi - h));
+    m = fmin(m, fmin(h, full - h)); // the pole / the wrap of the azimuth
+    return (m > 1e-6) ? 0.8 * lever * fmin(m, 1.0) : 0.0;
+}
+
+// not inlined, arguments by value: the pass kernel runs at 64 registers and takes this path for a fraction of a
+// percent of its photons.  dom: the domain bounds in global memory (DevCtx.dom_dev).
+__device__ __noinline__ unsigned long long safe_path(const double4 *geoA, const double2 *geoB, const double *dom, int geom,
+                                                      int ndim3, int blk, double h0, double h1, double h2, double v0,
+                                                      double v1, double v2, int movable, unsigned long long s_now)
+{
+    if (movable) { // |v| <= c up to rounding is what path_units assumes
+        const double b2 = (v0 * v0 + v1 * v1 + v2 * v2) / (C_LIGHT * C_LIGHT);
+        if (!(b2 <= 1.0 + 1e-9)) return 0ull;
+    }
+    const double4 a = geoA[blk];
+    double dist;
+    if (!ndim3) { // (c0, c1, h0, h1)
+        dist = margin_length(h0, a.x, a.z, dom[0], dom[1]);
+        if (geom == G_SPHERICAL)
+            dist = fmin(dist, margin_angle(h1, a.y, a.w, dom[2], dom[3], PI, h0));
+        else
+            dist = fmin(dist, margin_length(h1, a.y, a.w, dom[2], dom[3]));
+    } else { // (c0, c1, c2, h0) + (h1, h2)
+        const double2 b = geoB[blk];
+        if (geom == G_SPHERICAL) {
+            dist = margin_length(h0, a.x, a.w, dom[0], dom[1]);
+            dist = fmin(dist, margin_angle(h1, a.y, b.x, dom[2], dom[3], PI, h0));
+            dist = fmin(dist, margin_angle(h2, a.z, b.y, dom[4], dom[5], 2.0 * PI, h0 * sin(h1)));
+        } else if (geom == G_POLAR) {
+            dist = margin_length(h0, a.x, a.w, dom[0], dom[1]);
+            dist = fmin(dist, margin_angle(h1, a.y, b.x, dom[2], dom[3], 2.0 * PI, h0));
+            dist = fmin(dist, margin_length(h2, a.z, b.y, dom[4], dom[5]));
+        } else {
+            dist = margin_length(h0, a.x, a.w, dom[0], dom[1]);
+            dist = fmin(dist, margin_length(h1, a.y, b.x, dom[2], dom[3]));
+            dist = fmin(dist, margin_length(h2, a.z, b.y, dom[4], dom[5]));
+        }
+    }
+    if (!(dist > 0 && dist < 1e300)) return 0ull; // also NaN
+    const double x = 0.5 * dist * PATH_SCALE;
+    if (!(x >= 1.0)) return 0ull;
+    const unsigned long long u = (x < 4e18) ? __double2ull_rd(x) : PATH_SAT;
+    const unsigned long long t = path_add(s_now, u);
+    return t >= PATH_SAT ? PATH_SAT - 1 : t;
+}
 
 // warp-shuffle + shared-memory arg-min over (time, slot); ties broken by lowest slot
 template <int THREADS>
@@ -359,6 +467,7 @@ __global__ void unpack_kernel(DevCtx d, const mcrat_photon *aos, int n)
         d.ph.idx[i] = p.nearest_block_index;
         d.ph.tts[i] = p.time_to_scatter;
         store_tau(d.ph, i, p.total_optical_depth);
+        d.ph.safe[i] = 0;
         unsigned char f = 0;
         if ((p.type != 'p') && (p.weight != 0)) f |= F_MOVABLE; // Src/mclib.c:1070
         if (p.recalc_properties == 1) f |= F_RECALC;
@@ -437,6 +546,12 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
     const int ndim3 = (d.dims == D_THREE);
     const double default_t = 1e12 / C_LIGHT; // Src/mclib.c:620, 684-687
     const int first = sh.first, count = sh.count;
+    // path counter once the pending pushes are applied (what this pass does), and whether re-checks may be skipped:
+    // never on a new hydro frame (everything re-locates) nor in cyclo-synchrotron runs (Src/mclib.c:510-515 re-locates
+    // by the photon's state, not its position)
+    const unsigned long long s_now = path_after_pending(sh, d.path_pad);
+    const bool may_skip = d.recheck_skip && sw == 0 && !d.cs && s_now < PATH_SAT;
+    const bool verify = d.recheck_skip == 2;
 
     const int mini = LOCAL_RELOC ? sh.mini_slot : -1;
     for (int j = b * THREADS + threadIdx.x; j < count; j += nblk * THREADS) {
@@ -445,17 +560,18 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
         // every column this photon can need is requested up front (one round trip to HBM instead
         // of three dependent ones); the momentum is used by the pushes, tau by the free-path draw
         unsigned char flags;
-        int idx;
+        int idx = 0;
+        unsigned long long safe = 0;
         double r0, r1, r2, v0, v1, v2, ntau;
         if (!LOCAL_RELOC && d.stream_hints) {
             flags = __ldcs(d.ph.flags + i);
-            idx = __ldcs(d.ph.idx + i);
+            if (may_skip) safe = __ldcs(d.ph.safe + i); else idx = __ldcs(d.ph.idx + i);
             r0 = __ldcs(d.ph.r0 + i); r1 = __ldcs(d.ph.r1 + i); r2 = __ldcs(d.ph.r2 + i);
             v0 = __ldcs(d.ph.v0 + i); v1 = __ldcs(d.ph.v1 + i); v2 = __ldcs(d.ph.v2 + i);
             ntau = FUSE_MFP ? __ldcs(d.ph.ntau + i) : 0.0;
         } else {
             flags = d.ph.flags[i];
-            idx = d.ph.idx[i];
+            if (may_skip) safe = d.ph.safe[i]; else idx = d.ph.idx[i];
             r0 = d.ph.r0[i]; r1 = d.ph.r1[i]; r2 = d.ph.r2[i];
             v0 = d.ph.v0[i]; v1 = d.ph.v1[i]; v2 = d.ph.v2[i];
             ntau = FUSE_MFP ? d.ph.ntau[i] : 0.0;
@@ -473,59 +589,73 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
             }
         }
         // findContainingHydroCell, Src/mclib.c:469-597
-        double h0, h1, h2;
-        coord_to_hydro(d.dims, d.geom, r0, r1, r2, h0, h1, h2);
-        bool in_domain;
-        if (!ndim3)
-            in_domain = ((h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) && (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0])) &&
-                        (idx != -1);
-        else
-            in_domain = ((h2 < d.cells.dom[5]) && (h2 > d.cells.dom[4]) && (h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) &&
-                         (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0])) &&
-                        (idx != -1);
+        const bool skip = may_skip && (s_now < safe); // provably still inside its cell and the domain
         double t = default_t;
         bool have_t = true;
-        if (in_domain) {
-            int blk = (sw == 0) ? idx : 0;
+        bool inside = skip;
+        if (!skip || verify) {
+            if (may_skip) idx = d.ph.idx[i];
+            double h0, h1, h2;
+            coord_to_hydro(d.dims, d.geom, r0, r1, r2, h0, h1, h2);
+            bool in_domain;
+            if (!ndim3)
+                in_domain = ((h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) && (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0])) &&
+                            (idx != -1);
+            else
+                in_domain = ((h2 < d.cells.dom[5]) && (h2 > d.cells.dom[4]) && (h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) &&
+                             (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0])) &&
+                            (idx != -1);
+            inside = false;
+            if (in_domain) {
+                int blk = (sw == 0) ? idx : 0;
 #if defined(MCRAT_EXP_NOGATHER)
-            bool inb = true; // ablation build: no cell-geometry gather (see MCRAT_EXP_NOCOMPUTE)
+                bool inb = true; // ablation build: no cell-geometry gather (see MCRAT_EXP_NOCOMPUTE)
 #else
-            bool inb = in_cell(ndim3, d.cells, blk, h0, h1, h2);
+                bool inb = in_cell(ndim3, d.cells, blk, h0, h1, h2);
 #endif
-            if (d.cs && blk == 0) { // Src/mclib.c:510-515
-                if ((d.ph.c0[i]) + (d.ph.c1[i]) + (d.ph.c2[i]) + (d.ph.c3[i]) == 0) inb = false;
-            }
-            if (sw == 1 || !inb) {
-                int pos = LOCAL_RELOC ? first + atomicAdd(&d.sh[s].reloc_n, 1) : atomicAdd(&d.gs->reloc_count[parity], 1);
-                d.reloc_slot[pos] = i;
-                d.reloc_h0[pos] = h0;
-                d.reloc_h1[pos] = h1;
-                d.reloc_h2[pos] = h2;
-                d.reloc_best[pos] = INT_MAX;
-                have_t = false; // finish completes this photon
-            } else if (FUSE_MFP) {
-                // calcMeanFreePath, Src/mclib.c:657-687
-                if (flags & F_RECALC) {
-                    CellState c = load_cell_state(d.cells, idx);
-                    int terr = 0;
-                    const double tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, d.ph.p1[i], d.ph.p2[i],
-                                                     d.ph.p3[i], d.ph.c0[i], &terr);
-                    if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
-                    store_tau(d.ph, i, tau);
-                    ntau = -1.0 / tau;
-                    d.ph.flags[i] = flags & ~F_RECALC;
+                if (d.cs && blk == 0) { // Src/mclib.c:510-515
+                    if ((d.ph.c0[i]) + (d.ph.c1[i]) + (d.ph.c2[i]) + (d.ph.c3[i]) == 0) inb = false;
                 }
-#if defined(MCRAT_EXP_NOCOMPUTE)
-                // ablation build (profiles/ncu_r01_summary.md, "pass kernel: where the time goes"): the memory
-                // pattern alone, without Philox / log / divisions.  Never defined in the product build.
-                t = ntau * (double)j;
-#else
-                double xi = philox_mfp_uniform(d.k0, k1, iter, (uint32_t)j);
-                t = free_path_time_n(ntau, xi);
-#endif
+                if (sw == 1 || !inb) {
+                    int pos = LOCAL_RELOC ? first + atomicAdd(&d.sh[s].reloc_n, 1) : atomicAdd(&d.gs->reloc_count[parity], 1);
+                    d.reloc_slot[pos] = i;
+                    d.reloc_h0[pos] = h0;
+                    d.reloc_h1[pos] = h1;
+                    d.reloc_h2[pos] = h2;
+                    d.reloc_best[pos] = INT_MAX;
+                    have_t = false; // finish completes this photon
+                } else {
+                    inside = true;
+                    if (may_skip && !skip)
+                        d.ph.safe[i] = safe_path(d.cells.geoA, d.cells.geoB, d.dom_dev, d.geom, ndim3, blk, h0, h1, h2, v0, v1, v2,
+                                                 flags & F_MOVABLE, s_now);
+                }
+            } else {
+                if (idx != -1) d.ph.idx[i] = -1; // Src/mclib.c:589-595
             }
-        } else {
-            if (idx != -1) d.ph.idx[i] = -1; // Src/mclib.c:589-595
+            if (skip && !inside) d.gs->error = MCRAT_B200_ERR_STATE; // verify mode: the bound was wrong
+        }
+        if (inside && FUSE_MFP) {
+            // calcMeanFreePath, Src/mclib.c:657-687
+            if (flags & F_RECALC) {
+                if (skip) idx = d.ph.idx[i];
+                CellState c = load_cell_state(d.cells, idx);
+                int terr = 0;
+                const double tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, d.ph.p1[i], d.ph.p2[i],
+                                                 d.ph.p3[i], d.ph.c0[i], &terr);
+                if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
+                store_tau(d.ph, i, tau);
+                ntau = -1.0 / tau;
+                d.ph.flags[i] = flags & ~F_RECALC;
+            }
+#if defined(MCRAT_EXP_NOCOMPUTE)
+            // ablation build (profiles/ncu_r01_summary.md, "pass kernel: where the time goes"): the memory
+            // pattern alone, without Philox / log / divisions.  Never defined in the product build.
+            t = ntau * (double)j;
+#else
+            double xi = philox_mfp_uniform(d.k0, k1, iter, (uint32_t)j);
+            t = free_path_time_n(ntau, xi);
+#endif
         }
         if (FUSE_MFP && have_t) {
             if (!LOCAL_RELOC && d.stream_hints)
@@ -581,6 +711,7 @@ __global__ void __launch_bounds__(PASS_THREADS) flush_push_kernel(DevCtx d)
 __global__ void clear_push_kernel(DevCtx d)
 {
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < d.nshards; s += gridDim.x * blockDim.x) {
+        fold_path(d.sh[s], d.path_pad);
         d.sh[s].n_dt = 0;
         d.sh[s].pushed_slot = -1;
     }
@@ -589,6 +720,7 @@ __global__ void clear_push_kernel(DevCtx d)
 __global__ void set_push_kernel(DevCtx d, double t)
 {
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < d.nshards; s += gridDim.x * blockDim.x) {
+        fold_path(d.sh[s], d.path_pad);
         d.sh[s].dt_list[0] = t;
         d.sh[s].n_dt = 1;
         d.sh[s].pushed_slot = -1;
@@ -891,9 +1023,11 @@ __device__ __forceinline__ bool finish_one(DevCtx &d, ShardState &sh, const int 
     bool missing = false;
     if (b == INT_MAX) {
         d.ph.idx[i] = -1; // Src/mclib.c:536, 581-584
+        d.ph.safe[i] = 0;
         missing = true;
     } else {
         d.ph.idx[i] = b;
+        d.ph.safe[i] = 0; // the next pass re-checks the new cell and sets the threshold
         double p[4] = {d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i]};
         double r0 = d.ph.r0[i], r1 = d.ph.r1[i];
         CellState c = load_cell_state(d.cells, b);
@@ -1413,6 +1547,7 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
         d.ph.r0[i] = m.r[0];
         d.ph.r1[i] = m.r[1];
         d.ph.r2[i] = m.r[2];
+        d.ph.safe[i] = 0;
         if (!early.released) {
             st.pushed_slot = i;
             st.scatt_cnt += 1;
@@ -1469,7 +1604,7 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
                 d.reloc_h2[pos] = h2;
                 d.reloc_best[pos] = INT_MAX;
             } else {
-                d.ph.idx[i] = -1; // Src/mclib.c:589-595
+                d.ph.idx[i] = -1; // Src/mclib.c:589-595 (safe[i] is 0 since the write-back)
                 d.ph.tts[i] = t_next;
                 bt = t_next;
                 bi = i;
@@ -1534,6 +1669,7 @@ __device__ void cs_emit_single(DevCtx &d, EventRng &rng, int scatt, int slot)
     store_momentum(d.ph, slot, l_boost[0], l_boost[1], l_boost[2], l_boost[3]);
     d.ph.c0[slot] = p_comv[0]; d.ph.c1[slot] = p_comv[1]; d.ph.c2[slot] = p_comv[2]; d.ph.c3[slot] = p_comv[3];
     d.ph.r0[slot] = pos[0]; d.ph.r1[slot] = pos[1]; d.ph.r2[slot] = pos[2];
+    d.ph.safe[slot] = 0;
     d.ph.s0[slot] = 1; d.ph.s1[slot] = 0; d.ph.s2[slot] = 0; d.ph.s3[slot] = 0;
     d.ph.nscatt[slot] = 0;
     d.ph.weight[slot] = d.ph.weight[scatt];
@@ -1562,6 +1698,7 @@ __device__ void cs_emit_single(DevCtx &d, EventRng &rng, int scatt, int slot)
     } else {
         hydro_coord_to_mcrat(d.dims, d.geom, pos, cr0 + pr, cr1 + pr2, position_phi);
     }
+    d.ph.safe[scatt] = 0;
     d.ph.r0[scatt] = pos[0];
     d.ph.r1[scatt] = pos[1];
     d.ph.r2[scatt] = pos[2];
@@ -1654,6 +1791,7 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
         scatt_time = 0;
         n_dt = 0;
         ph_index = bi;
+        fold_path(st, d.path_pad); // the pushes of the last event have been applied by the pass that led here
         st.n_dt = 0;
         st.pushed_slot = -1;
         early.enabled = 0;
@@ -2123,6 +2261,7 @@ __global__ void __launch_bounds__(256) cs_absorb_kernel(DevCtx d)
                 d.ph.type[i] = 'N';
                 d.ph.weight[i] = 0;
                 d.ph.idx[i] = -1;
+                d.ph.safe[i] = 0;
                 d.ph.flags[i] = 0;
                 store_momentum(d.ph, i, 0, 0, 0, 0);
                 d.ph.c0[i] = 0; d.ph.c1[i] = 0; d.ph.c2[i] = 0; d.ph.c3[i] = 0;
@@ -2505,6 +2644,7 @@ __device__ __forceinline__ void set_null_photon(DevCtx &d, int i) // setNullPhot
     d.ph.type[i] = 'N';
     d.ph.weight[i] = 0;
     d.ph.idx[i] = -1;
+    d.ph.safe[i] = 0;
     d.ph.flags[i] = 0;
     store_momentum(d.ph, i, 0, 0, 0, 0);
     d.ph.c0[i] = 0; d.ph.c1[i] = 0; d.ph.c2[i] = 0; d.ph.c3[i] = 0;
@@ -2561,6 +2701,7 @@ __global__ void __launch_bounds__(256) rebin_place_kernel(DevCtx d, const mcrat_
     store_momentum(d.ph, i, p.p0, p.p1, p.p2, p.p3);
     d.ph.c0[i] = 0; d.ph.c1[i] = 0; d.ph.c2[i] = 0; d.ph.c3[i] = 0;
     d.ph.r0[i] = p.r0; d.ph.r1[i] = p.r1; d.ph.r2[i] = p.r2;
+    d.ph.safe[i] = 0;
     d.ph.s0[i] = p.s0; d.ph.s1[i] = p.s1; d.ph.s2[i] = p.s2; d.ph.s3[i] = p.s3;
     d.ph.nscatt[i] = p.num_scatt;
     d.ph.weight[i] = p.weight;
@@ -2799,10 +2940,17 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
     d.k1 = (uint32_t)(cfg->seed >> 32);
     d.shard_base = cfg->shard;
     d.replay = cfg->rng_mode == MCRAT_RNG_REPLAY ? 1 : 0;
+    d.recheck_skip = getenv("MCRAT_B200_NO_RECHECK_SKIP") ? 0 : 1;
+    d.path_pad = 0;
     d.nshards = 1;
     d.shard_size = 1;
     d.blocks_per_shard = 1;
     if ((e = dev_alloc(ctx->misc_allocs, &d.gs, 1)) != cudaSuccess) return bail(e, "cudaMalloc");
+    {
+        double *dom = nullptr;
+        if ((e = dev_alloc(ctx->misc_allocs, &dom, 6)) != cudaSuccess) return bail(e, "cudaMalloc");
+        d.dom_dev = dom;
+    }
     memset(ctx->gs_host, 0, sizeof(GlobalState));
     ctx->gs_host->cs_max_photons = INT_MAX;
     if ((e = cudaMemcpyAsync(d.gs, ctx->gs_host, sizeof(GlobalState), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
@@ -2961,6 +3109,17 @@ API int mcrat_b200_set_hydro(mcrat_b200_ctx *ctx, int n, const double *const *fi
         if (int rc = check_launch(ctx, "build_box_kernels", 2)) return rc;
     }
     for (int k = 0; k < 6; ++k) c.dom[k] = domains[k];
+    {   // safe_path(): a photon inside the domain has |position| <= R; one push rounds each component by <= ulp/2
+        double r2sum = 0;
+        for (int k = 0; k < (ndim3 ? 3 : 2); ++k) {
+            const double m = fmax(fabs(domains[2 * k]), fabs(domains[2 * k + 1]));
+            r2sum += m * m;
+        }
+        ctx->d.path_pad = 4e-16 * sqrt(r2sum);
+        CK(cudaMemcpyAsync((void *)ctx->d.dom_dev, domains, 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        // thresholds refer to the cells of the previous frame
+        if (ctx->ph_cap_alloc > 0) CK(cudaMemsetAsync(ctx->d.ph.safe, 0, sizeof(unsigned long long) * (size_t)ctx->ph_cap_alloc, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_hydro = true;
     return MCRAT_B200_OK;
@@ -2988,6 +3147,7 @@ static int ensure_photon_capacity(mcrat_b200_ctx *ctx, int n)
     double **cols[23] = {&p.r0, &p.r1, &p.r2, &p.p0, &p.p1, &p.p2, &p.p3, &p.c0, &p.c1, &p.c2, &p.c3, &p.s0,
                          &p.s1, &p.s2, &p.s3, &p.nscatt, &p.weight, &p.tau, &p.tts, &p.v0, &p.v1, &p.v2, &p.ntau};
     for (int k = 0; k < 23; ++k) CK(dev_alloc(ctx->ph_allocs, cols[k], (size_t)cap));
+    CK(dev_alloc(ctx->ph_allocs, &p.safe, (size_t)cap));
     CK(dev_alloc(ctx->ph_allocs, &p.idx, (size_t)cap));
     CK(dev_alloc(ctx->ph_allocs, &p.flags, (size_t)cap));
     CK(dev_alloc(ctx->ph_allocs, &p.type, (size_t)cap));
@@ -3650,6 +3810,14 @@ static int launch_frame_loop(mcrat_b200_ctx *ctx)
         return MCRAT_B200_ERR_CUDA;
     }
     return check_launch(ctx, "frame_loop_kernel");
+}
+
+API int mcrat_b200_set_recheck_skip(mcrat_b200_ctx *ctx, int mode)
+{
+    if (!ctx) return MCRAT_B200_ERR_ARG;
+    if (mode < 0 || mode > 2) return fail(ctx, MCRAT_B200_ERR_ARG, "set_recheck_skip: 0 (off), 1 (on), 2 (on, verified)");
+    ctx->d.recheck_skip = mode;
+    return MCRAT_B200_OK;
 }
 
 API int mcrat_b200_set_loop_mode(mcrat_b200_ctx *ctx, int mode)

@@ -72,7 +72,7 @@ EXPORTS = [
     "mcrat_b200_average_photon_energy", "mcrat_b200_run_frame", "mcrat_b200_set_loop_mode",
     "mcrat_b200_rebin_cyclosynch_comp_photons", "mcrat_b200_set_cs_rebin_params", "mcrat_b200_get_kernel_times",
     "mcrat_b200_launch_count", "mcrat_b200_rescan_all", "mcrat_b200_measure_fp64_peak", "mcrat_b200_measure_hbm_peak",
-    "mcrat_b200_selftest_div_by_c",
+    "mcrat_b200_selftest_div_by_c", "mcrat_b200_set_recheck_skip",
 ]
 
 
@@ -322,6 +322,9 @@ class HotPath:
         v = C.c_double(0)
         self._ck(self.L.mcrat_b200_measure_fp64_peak(self.ctx, C.byref(v)))
         return v.value
+
+    def set_recheck_skip(self, mode):
+        self._ck(self.L.mcrat_b200_set_recheck_skip(self.ctx, int(mode)))
 
     def selftest_div_by_c(self, n, seed=1):
         v = C.c_longlong(-1)

@@ -213,3 +213,48 @@ def test_division_by_c_is_exact():
     cfg, hydro, photons, frame = synth.workload("C1", scale=0.25, n_photons=64)
     hp = HotPath(cfg, seed=3)
     assert hp.selftest_div_by_c(50_000_000, seed=11) == 0
+
+
+SKIP_CASES = [
+    # workload, grid scale, photons, sub-shards, iterations, dilution, loop
+    ("C1", 1.0 / 8, 3000, 2, 400, 1.0, "persistent"),     # 2-D Cartesian
+    ("C2", 1.0 / 8, 4000, 3, 400, 1.0, "streamed"),       # 2-D cylindrical
+    ("C2", 1.0 / 4, 3000, 2, 60, 5e-6, "persistent"),     # optically thin: long steps, photons cross cells all the time
+    ("C5", 1.0 / 8, 4000, 4, 300, 1.0, "persistent"),     # 3-D spherical
+    ("C5", 1.0 / 8, 4000, 4, 60, 1e-5, "streamed"),
+    ("G2S", 1.0 / 8, 3000, 2, 300, 1.0, "persistent"),    # 2-D spherical
+    ("G3C", 1.0 / 8, 3000, 2, 300, 1.0, "streamed"),      # 3-D Cartesian
+    ("G3P", 1.0 / 8, 3000, 2, 300, 1.0, "persistent"),    # 3-D polar
+    ("G3P", 1.0 / 8, 3000, 2, 60, 1e-5, "persistent"),
+]
+
+
+@pytest.mark.parametrize("wl,scale,nph,shards,iters,dilute,loop", SKIP_CASES)
+def test_skipped_cell_rechecks_change_nothing(wl, scale, nph, shards, iters, dilute, loop):
+    """The pass skips the containment re-check of a photon that provably cannot have left its cell
+    (mcrat_b200_set_recheck_skip).  Mode 2 makes every skipped re-check anyway and fails the frame if one would not
+    have succeeded; modes 0 (the reference's behaviour: re-check everything) and 1 must give the same photons bit for
+    bit.  Several frames' worth of calls, so thresholds survive run_frame boundaries and a new hydro frame."""
+    cfg, hydro, photons, frame = synth.workload(wl, scale=scale, n_photons=nph, seed=77)
+    if dilute != 1.0:
+        hydro = _thin(hydro, dilute)
+    out = {}
+    for mode in (0, 1, 2):
+        hp = HotPath(cfg, seed=808, num_shards=shards, loop_mode=loop)
+        hp.set_recheck_skip(mode)
+        hp.set_hydro(hydro)
+        hp.set_photons(photons)
+        t, stats = frame["time_now"], []
+        for call, sw in enumerate((1, 0, 0, 1, 0)):
+            if sw == 1 and call > 0:
+                hp.set_hydro(hydro)  # "new" hydro frame: thresholds of the old cells must not survive
+            st = hp.run_frame(t, 1.0 / frame["fps"], max_iters=iters, switch=sw)  # raises on MCRAT_B200_ERR_STATE
+            t = st["time_now"]
+            stats.append((st["iterations"], st["scatterings"], st["relocations"]))
+        out[mode] = (hp.get_photons(), stats)
+    for mode in (1, 2):
+        assert out[mode][1] == out[0][1]
+        for f in out[0][0].dtype.names:
+            assert np.array_equal(out[0][0][f], out[mode][0][f], equal_nan=out[0][0].dtype[f].kind == "f"), (mode, f)
+    if dilute != 1.0:
+        assert sum(s[2] for s in out[0][1]) > 100  # photons did change cells

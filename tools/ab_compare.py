@@ -2,7 +2,7 @@
 """A/B harness: run the same frames through two builds of the library (MCRAT_B200_LIB) and compare
 the photon lists bit for bit, plus the loop time per iteration.
 
-  python tools/ab_compare.py libA.so[:loop_mode] libB.so[:loop_mode] [workload] [photons] [shards] [iters] [scale]
+  python tools/ab_compare.py libA.so[:loop_mode[:recheck_skip]] libB.so[:loop_mode[:recheck_skip]] [workload] [photons] [shards] [iters] [scale]
 """
 import os
 import subprocess
@@ -19,6 +19,8 @@ def child(out, wl, nph, shards, iters, scale):
     cfg, hydro, photons, frame = synth.workload(wl, scale=scale, n_photons=nph, seed=5)
     mode = os.environ.get("MCRAT_LOOP_MODE")
     hp = HotPath(cfg, seed=99, num_shards=shards, scan_index=True, loop_mode=mode or None)
+    if os.environ.get("MCRAT_RECHECK_SKIP"):
+        hp.set_recheck_skip(int(os.environ["MCRAT_RECHECK_SKIP"]))
     hp.set_hydro(hydro)
     hp.set_photons(photons)
     st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=50, switch=1)
@@ -29,7 +31,7 @@ def child(out, wl, nph, shards, iters, scale):
     dt = time.perf_counter() - t0
     np.save(out, hp.get_photons())
     print("%s[%s]: %d iterations %d scatterings  %.2f us/iteration  %.3e scatterings/s  launches %d" %
-          (os.path.basename(os.environ.get("MCRAT_B200_LIB", "default")), os.environ.get("MCRAT_LOOP_MODE", "-"), st2["iterations"], st2["scatterings"],
+          (os.path.basename(os.environ.get("MCRAT_B200_LIB", "default")), os.environ.get("MCRAT_LOOP_MODE", "-") + "/" + os.environ.get("MCRAT_RECHECK_SKIP", "-"), st2["iterations"], st2["scatterings"],
            1e6 * dt / max(st2["iterations"], 1), st2["scatterings"] / dt, hp.launch_count()), flush=True)
 
 
@@ -48,9 +50,12 @@ if __name__ == "__main__":
     for k, lib in enumerate(libs):
         out = "/tmp/ab_%d.npy" % k
         lib, _, mode = lib.partition(":")
+        mode, _, skip = mode.partition(":")
         env = dict(os.environ, MCRAT_B200_LIB=os.path.abspath(lib))
         if mode:
             env["MCRAT_LOOP_MODE"] = mode
+        if skip:
+            env["MCRAT_RECHECK_SKIP"] = skip  # 0 / 1 / 2 (mcrat_b200_set_recheck_skip)
         subprocess.check_call([sys.executable, os.path.abspath(__file__), "--child", out, wl, nph, shards, iters, scale], env=env)
         outs.append(np.load(out))
     a, b = outs

@@ -16,7 +16,10 @@ cfg, hydro, photons, frame = synth.workload(wl, n_photons=nbig if distinct else 
 hp = HotPath(cfg, seed=7, profile=True, num_shards=shards)
 hp.set_hydro(hydro)
 hp.set_photons(photons if distinct else np.resize(photons, nbig))
-st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=1, switch=1)
+if os.environ.get("MCRAT_RECHECK_SKIP"):
+    hp.set_recheck_skip(int(os.environ["MCRAT_RECHECK_SKIP"]))
+# the rescan iteration and two more: the pass after a re-location re-checks every photon and sets its skip threshold
+st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=3, switch=1)
 hp.kernel_times(reset=True)
 st = hp.run_frame(st["time_now"], 1.0 / frame["fps"], max_iters=24, switch=0)
 kt = hp.kernel_times()
