@@ -24,5 +24,5 @@ st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=iters, switch
 print(wl, "slice:", st)
 if big > 0:
     hp.set_photons(np.resize(photons, big))
-    st = hp.run_frame(st["time_now"], 1.0 / frame["fps"], max_iters=6, switch=0)
+    st = hp.run_frame(st["time_now"], 1.0 / frame["fps"], max_iters=8, switch=0)
     print("big list:", st)
