@@ -909,12 +909,12 @@ __device__ inline void fano_apply(const double *f, double *s)
 // electron sampling (Src/electron.c:70-237)
 // ----------------------------------------------------------------------------------------
 // Src/electron.c:202-237 sampleThermalElectron
-__device__ inline double sample_thermal_electron(double temp, EventRng &rng)
+__device__ inline double sample_thermal_electron(double temp, EventRng &rng, double k2_known = 0)
 {
     double gamma = 1;
     if (temp >= 1e7) {
         double factor = K_B * temp / (M_EL * C_LIGHT * C_LIGHT);
-        double k2 = bessel_K2(1.0 / factor);
+        double k2 = (k2_known > 0) ? k2_known : bessel_K2(1.0 / factor);
         double y = 1, f = 0, x = 0;
         while (((f != f) || (y > f)) && !rng.exhausted) {
             x = rng.uniform_pos() * (1 + 100 * factor);
@@ -1007,6 +1007,59 @@ __device__ inline int warp_gaussians3(const double *pre, int npre, uint64_t draw
         g[n] = __shfl_sync(0xffffffffu, val, j);
     }
     return 2 * (j + 1);
+}
+
+// The Maxwell-Juttner branch (Src/electron.c:207-226) is a rejection loop over a flat envelope: 50 (theta ~ 1) to
+// 330 (theta ~ 0.002) trials per electron, each two uniforms, a square root, a division and an exponential -- 40 000
+// to 390 000 cycles on one lane.  Here the lanes of the warp evaluate 64 consecutive trials per round from the same Philox
+// counters the sequential loop would reach (a trial always costs exactly two draws: Philox doubles are never 0), and
+// the first accepted trial in stream order wins: same gamma, same number of draws consumed (the return value).
+// 0 = no acceptance within `max_rounds` rounds; the caller then continues sequentially from where this stopped.
+__device__ inline void mj_trial(uint32_t k0, uint32_t k1, uint64_t iter, uint64_t dd, double span, double factor, double k2,
+                                double &x, bool &accepted)
+{
+    double a, b, u1, u2;
+    philox_doubles((uint32_t)(dd >> 1), (uint32_t)iter, (uint32_t)(iter >> 32), 1u, k0, k1, a, b);
+    if (dd & 1ull) {
+        u1 = b;
+        philox_doubles((uint32_t)((dd + 1) >> 1), (uint32_t)iter, (uint32_t)(iter >> 32), 1u, k0, k1, a, b);
+        u2 = a;
+    } else {
+        u1 = a;
+        u2 = b;
+    }
+    x = u1 * span;
+    const double bx = sqrt(1 - (1 / (x * x)));
+    const double y = u2 / 2.0;
+    const double f = x * x * (bx / k2) * exp(-1 * x / factor);
+    accepted = !((f != f) || (y > f));
+}
+
+// one round = 64 consecutive trials: lane j evaluates trials 64 r + j and 64 r + 32 + j (two independent chains)
+__device__ inline uint64_t warp_mj_gamma(uint32_t k0, uint32_t k1, uint64_t iter, uint64_t draw0, double factor, double k2,
+                                         int max_rounds, double &gamma)
+{
+    const int lane = threadIdx.x & 31;
+    const double span = (1 + 100 * factor);
+    for (int r = 0; r < max_rounds; ++r) {
+        double xa, xb;
+        bool acc_a, acc_b;
+        mj_trial(k0, k1, iter, draw0 + 2ull * (uint64_t)(64 * r + lane), span, factor, k2, xa, acc_a);
+        mj_trial(k0, k1, iter, draw0 + 2ull * (uint64_t)(64 * r + 32 + lane), span, factor, k2, xb, acc_b);
+        const unsigned ma = __ballot_sync(0xffffffffu, acc_a);
+        const unsigned mb = __ballot_sync(0xffffffffu, acc_b);
+        if (ma) {
+            const int j = __ffs(ma) - 1;
+            gamma = __shfl_sync(0xffffffffu, xa, j);
+            return 2ull * (uint64_t)(64 * r + j + 1);
+        }
+        if (mb) {
+            const int j = __ffs(mb) - 1;
+            gamma = __shfl_sync(0xffffffffu, xb, j);
+            return 2ull * (uint64_t)(64 * r + 32 + j + 1);
+        }
+    }
+    return 0;
 }
 
 // gamma of a Maxwellian electron from its three velocity components, Src/electron.c:231-236

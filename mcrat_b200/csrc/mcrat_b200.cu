@@ -88,6 +88,7 @@ struct CellCols {
     const double4 *geoA; // 2-D: (c0, c1, h0, h1); 3-D: (c0, c1, c2, h0)     h = 0.5 * size
     const double2 *geoB; // 3-D: (h1, h2)
     const double *r0, *r1, *r2, *v0, *v1, *v2, *dens, *dens_lab, *temp, *gamma, *B0, *B1, *B2;
+    double *k2; // K_2(1/theta) of the cell's temperature (Src/electron.c:215), filled on first use; 0 = not yet
     double dom[6];
     // optional two-level bounding-box index over consecutive cells (BOX_T cells per level-1 box,
     // BOX_T level-1 boxes per level-2 box): 2 doubles (lo, hi) per dimension, 3 dimensions stored
@@ -164,6 +165,7 @@ struct DevCtx {
     int replay;
     int cap;
     int nshards, shard_size, blocks_per_shard;
+    int mj_rounds;    // warp-wide Maxwell-Juttner sampling: rounds of 64 trials before the sequential loop takes over
     int recheck_skip; // 0: every photon re-checks its cell in every pass; 1: skip while provably inside (safe_path);
                       // 2: decide as in 1 but re-check anyway and raise an error if a skipped photon had left (tests)
     const double *dom_dev; // cells.dom in global memory, for safe_path()
@@ -1323,7 +1325,26 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
         double g3[3] = {0, 0, 0};
         int used = 0;
         if (!rng_sh.replay && temp < 1e7) used = warp_gaussians3(m.pre, 64, rng_sh.draw, sqrt(K_B * temp / M_EL), g3);
-        double gamma = 1;
+        // Maxwell-Juttner branch: K_2(1/theta) from the per-cell cache, then 64 rejection trials per round
+        double gamma = 1, k2 = 0;
+        uint64_t used_mj = 0;
+        const int MJ_ROUNDS = d.mj_rounds; // x 64 trials, then sequentially (never in practice; MCRAT_B200_MJ_ROUNDS for tests)
+        if (temp >= 1e7) {
+            const double factor = K_B * temp / (M_EL * C_LIGHT * C_LIGHT);
+            if (lane == 0) {
+                const int cell = (cand_idx == -2) ? d.ph.idx[i] : cand_idx;
+                k2 = d.cells.k2[cell];
+                if (!(k2 > 0)) { // not yet evaluated for this cell in this hydro frame (or underflowed: evaluated again)
+                    k2 = bessel_K2(1.0 / factor);
+                    d.cells.k2[cell] = k2;
+                }
+            }
+            k2 = __shfl_sync(0xffffffffu, k2, 0);
+            if (!rng_sh.replay) {
+                used_mj = warp_mj_gamma(rng_sh.k0, rng_sh.k1, rng_sh.iter, rng_sh.draw, factor, k2, MJ_ROUNDS, gamma);
+                if (!used_mj) gamma = 1;
+            }
+        }
         if (lane == 0) {
             rng = rng_sh;
             rng.pre = m.pre;
@@ -1332,8 +1353,11 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
             if (used) {
                 rng.draw += (uint64_t)used;
                 gamma = maxwellian_gamma(g3);
+            } else if (used_mj) {
+                rng.draw += used_mj;
             } else {
-                gamma = sample_thermal_electron(temp, rng);
+                if (temp >= 1e7 && !rng_sh.replay) rng.draw += 128ull * (uint64_t)MJ_ROUNDS; // those trials were all rejected
+                gamma = sample_thermal_electron(temp, rng, k2);
             }
         }
         erot_wait(); // warp 1 has the rotation angles ready long before
@@ -2945,6 +2969,8 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
     d.replay = cfg->rng_mode == MCRAT_RNG_REPLAY ? 1 : 0;
     d.recheck_skip = getenv("MCRAT_B200_NO_RECHECK_SKIP") ? 0 : 1;
     d.path_pad = 0;
+    d.mj_rounds = getenv("MCRAT_B200_MJ_ROUNDS") ? atoi(getenv("MCRAT_B200_MJ_ROUNDS")) : (1 << 13);
+    if (d.mj_rounds < 0) d.mj_rounds = 0;
     d.nshards = 1;
     d.shard_size = 1;
     d.blocks_per_shard = 1;
@@ -3087,7 +3113,9 @@ API int mcrat_b200_set_hydro(mcrat_b200_ctx *ctx, int n, const double *const *fi
         CK(dev_alloc(ctx->cell_allocs, &b2, (size_t)6 * (c.nbox2 ? c.nbox2 : 1)));
         c.box1 = b1;
         c.box2 = b2;
+        CK(dev_alloc(ctx->cell_allocs, &c.k2, (size_t)n));
     }
+    CK(cudaMemsetAsync(c.k2, 0, (size_t)(n ? n : 1) * sizeof(double), ctx->stream)); // new temperatures
     c.n = n;
     c.n_padded = n_padded;
     double *cols[19];

@@ -258,3 +258,27 @@ def test_skipped_cell_rechecks_change_nothing(wl, scale, nph, shards, iters, dil
             assert np.array_equal(out[0][0][f], out[mode][0][f], equal_nan=out[0][0].dtype[f].kind == "f"), (mode, f)
     if dilute != 1.0:
         assert sum(s[2] for s in out[0][1]) > 100  # photons did change cells
+
+
+def test_warp_wide_maxwell_juttner_sampling_equals_the_sequential_loop(monkeypatch):
+    """Hot electrons (T >= 1e7 K) are drawn by a rejection loop (Src/electron.c:207-226) that the event evaluates 64
+    trials at a time across a warp.  With MCRAT_B200_MJ_ROUNDS = 0 every electron is drawn by the sequential loop, with 1
+    the sequential loop takes over after 64 rejected trials (which happens for most cold-ish cells): all three must give
+    the same photons bit for bit, and the default build must match the oracle's sequential loop."""
+    cfg, hydro, photons, frame = synth.workload("C3", scale=1.0 / 8, n_photons=4000, seed=13)
+    out = {}
+    for rounds in ("0", "1", None):
+        if rounds is None:
+            monkeypatch.delenv("MCRAT_B200_MJ_ROUNDS", raising=False)
+        else:
+            monkeypatch.setenv("MCRAT_B200_MJ_ROUNDS", rounds)
+        hp = HotPath(cfg, seed=4242, num_shards=4)
+        hp.set_hydro(hydro)
+        hp.build_thermal_table(calls=20000, seed=3)
+        hp.set_photons(photons)
+        st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=150, switch=1)
+        out[rounds] = (hp.get_photons(), st["scatterings"])
+    assert out["0"][1] == out["1"][1] == out[None][1] > 300
+    for r in ("0", "1"):
+        for f in out[None][0].dtype.names:
+            assert np.array_equal(out[None][0][f], out[r][0][f], equal_nan=out[None][0].dtype[f].kind == "f"), (r, f)

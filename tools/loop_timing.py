@@ -20,6 +20,8 @@ iters = int(sys.argv[4]) if len(sys.argv) > 4 else 2000
 cfg, hydro, photons, frame = synth.workload(wl, n_photons=nph, seed=5)
 hp = HotPath(cfg, seed=99, num_shards=shards, scan_index=True, loop_mode="persistent")
 hp.set_hydro(hydro)
+if cfg["tau_calculation"] == 2:
+    hp.build_thermal_table(calls=200000, seed=3)
 hp.set_photons(photons)
 st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=50, switch=1)
 buf = (C.c_longlong * 32)()
