@@ -1911,12 +1911,56 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
             const int pi = sh_cand_i;
             double nt = DBL_MAX;
             int ni = INT_MAX;
-            for (int j = threadIdx.x; j < st.count; j += EVT_THREADS) {
-                const int k = st.first + j;
-                double t = d.ph.tts[k];
-                if (lex_less(pt, pi, t, k) && lex_less(t, k, nt, ni)) {
-                    nt = t;
-                    ni = k;
+            // streamed loop: the pass blocks' minima are still there.  A block whose minimum comes after (pt, pi) offers
+            // exactly that minimum; a block whose minimum has been consumed (at most one per rejection) is read again;
+            // photons re-located in this iteration are not in any minimum and come from the re-location list.  Same
+            // result as reading every time of the shard, without the 80 MB read by one block at 10^7 photons.
+            const bool two_level = (early_gst == nullptr) && !have_pre && step_mode == 0 && !d.replay && nb_per_shard > 1 &&
+                                   R <= RELOC_LIST_SCAN_MAX;
+            if (two_level) {
+                for (int k = threadIdx.x; k < nb_per_shard; k += EVT_THREADS) {
+                    const int q = s * nb_per_shard + k;
+                    const double t = d.bm_t[q];
+                    const int ti = d.bm_i[q];
+                    if (lex_less(pt, pi, t, ti) && lex_less(t, ti, nt, ni)) {
+                        nt = t;
+                        ni = ti;
+                    }
+                }
+                for (int k = 0; k < nb_per_shard; ++k) { // uniform over the block
+                    const int q = s * nb_per_shard + k;
+                    if (lex_less(pt, pi, d.bm_t[q], d.bm_i[q])) continue;
+                    // pass block k's photons: j = k * PASS_THREADS + u + m * nb_per_shard * PASS_THREADS (pass_body)
+                    for (int base = k * PASS_THREADS; base < st.count; base += nb_per_shard * PASS_THREADS)
+                        for (int u = threadIdx.x; u < PASS_THREADS; u += EVT_THREADS) {
+                            const int j = base + u;
+                            if (j >= st.count) break;
+                            const int kk = st.first + j;
+                            const double t = d.ph.tts[kk];
+                            if (lex_less(pt, pi, t, kk) && lex_less(t, kk, nt, ni)) {
+                                nt = t;
+                                ni = kk;
+                            }
+                        }
+                }
+                for (int j = threadIdx.x; j < R; j += EVT_THREADS) {
+                    const int kk = d.reloc_slot[reloc_base + j];
+                    if (kk >= st.first && kk < st.first + st.count) {
+                        const double t = d.ph.tts[kk];
+                        if (lex_less(pt, pi, t, kk) && lex_less(t, kk, nt, ni)) {
+                            nt = t;
+                            ni = kk;
+                        }
+                    }
+                }
+            } else {
+                for (int j = threadIdx.x; j < st.count; j += EVT_THREADS) {
+                    const int k = st.first + j;
+                    double t = d.ph.tts[k];
+                    if (lex_less(pt, pi, t, k) && lex_less(t, k, nt, ni)) {
+                        nt = t;
+                        ni = k;
+                    }
                 }
             }
             block_argmin<EVT_THREADS>(nt, ni);

@@ -282,3 +282,25 @@ def test_warp_wide_maxwell_juttner_sampling_equals_the_sequential_loop(monkeypat
     for r in ("0", "1"):
         for f in out[None][0].dtype.names:
             assert np.array_equal(out[None][0][f], out[r][0][f], equal_nan=out[None][0].dtype[f].kind == "f"), (r, f)
+
+
+@pytest.mark.parametrize("nph,shards", [(6000, 2), (9000, 1), (40000, 80)])
+def test_klein_nishina_rejections_streamed_equals_persistent(nph, shards):
+    """C3 (x = h nu / m c^2 up to 10): a third of the candidates is rejected by the Klein-Nishina test and the event
+    moves on to the next entry of the time order (Src/mclib.c:1128-1339).  The streamed loop finds it from the pass
+    blocks' minima plus the slices of the blocks whose minimum is used up, the persistent loop reads the shard's times:
+    same photons bit for bit, and fewer scatterings than shard-iterations would give without rejections' extra pushes."""
+    cfg, hydro, photons, frame = synth.workload("C3", scale=1.0 / 8, n_photons=nph, seed=19)
+    out = {}
+    for mode in ("streamed", "persistent"):
+        hp = HotPath(cfg, seed=777, num_shards=shards, loop_mode=mode)
+        hp.set_hydro(hydro)
+        hp.build_thermal_table(calls=20000, seed=3)
+        hp.set_photons(photons)
+        st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=120, switch=1)
+        st2 = hp.run_frame(st["time_now"], 1.0 / frame["fps"], max_iters=80, switch=0)
+        out[mode] = (hp.get_photons(), st["scatterings"] + st2["scatterings"], st["iterations"] + st2["iterations"])
+    a, b = out["streamed"], out["persistent"]
+    assert a[1] == b[1] and a[2] == b[2] == 200
+    for f in a[0].dtype.names:
+        assert np.array_equal(a[0][f], b[0][f], equal_nan=a[0].dtype[f].kind == "f"), f
