@@ -48,8 +48,13 @@ constexpr int PERSISTENT_MAX_PHOTONS = 1 << 21; // above this the list no longer
 #ifndef MCRAT_SCAN_THREADS
 #define MCRAT_SCAN_THREADS 128
 #endif
+// photons per thread: 7 in 2-D (10^5 photons x 2^20 cells: 24.87 ms = 98.9 % of the measured DFMA issue rate, against
+// 25.84 ms / 95.3 % with 8 and 25.54 ms with 6), 8 in 3-D (41.03 ms; 7: 41.20, 6: 41.52, 10: 41.21)
 #ifndef MCRAT_SCAN_P
-#define MCRAT_SCAN_P 8
+#define MCRAT_SCAN_P 7
+#endif
+#ifndef MCRAT_SCAN_P3
+#define MCRAT_SCAN_P3 8
 #endif
 #ifndef MCRAT_SCAN_TILE
 #define MCRAT_SCAN_TILE 256
@@ -63,7 +68,8 @@ constexpr int PERSISTENT_MAX_PHOTONS = 1 << 21; // above this the list no longer
 #define MCRAT_PRAGMA_STR2(x) #x
 #define MCRAT_PRAGMA_STR(x) MCRAT_PRAGMA_STR2(x)
 constexpr int SCAN_THREADS = MCRAT_SCAN_THREADS;
-constexpr int SCAN_P = MCRAT_SCAN_P;       // photons per thread held in registers
+constexpr int SCAN_P2 = MCRAT_SCAN_P;      // photons per thread held in registers, 2-D
+constexpr int SCAN_P3 = MCRAT_SCAN_P3;     // ... 3-D
 constexpr int SCAN_TILE = MCRAT_SCAN_TILE; // cells per shared-memory stage
 constexpr int FEW_RMAX = 128;  // relocating photons handled per pass of the cell-parallel scan
 constexpr int RELOC_LIST_SCAN_MAX = 2048;
@@ -733,7 +739,7 @@ __global__ void set_push_kernel(DevCtx d, double t)
 }
 
 // ------------------------------------------------------------------------------------------
-// K1: photon x cell containment scan.  Photons in registers (SCAN_P per thread), cells streamed
+// K1: photon x cell containment scan.  Photons in registers (SCAN_P2 / SCAN_P3 per thread), cells streamed
 // through a double-buffered shared-memory tile filled by TMA bulk copies.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -774,6 +780,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(DevCtx d, int parity
 {
     const GlobalState &gs = *d.gs;
     if (gs.error != 0) return;
+    constexpr int SCAN_P = NDIM3 ? SCAN_P3 : SCAN_P2;
     const int count = gs.reloc_count[parity];
     const int pbase = blockIdx.x * (SCAN_THREADS * SCAN_P);
     if (pbase >= count) return;
@@ -3396,6 +3403,7 @@ static int need_single_shard(mcrat_b200_ctx *ctx, const char *what)
 static void scan_grid(mcrat_b200_ctx *ctx, int nphot, dim3 &grid, int &tiles_per_chunk)
 {
     const int ntiles = ctx->d.cells.n_padded / SCAN_TILE;
+    const int SCAN_P = (ctx->d.dims == D_THREE) ? SCAN_P3 : SCAN_P2;
     int pchunks = (nphot + SCAN_THREADS * SCAN_P - 1) / (SCAN_THREADS * SCAN_P);
     if (pchunks < 1) pchunks = 1;
     // enough cell chunks for ~32 CTAs per SM over the launch (measured best: short CTAs balance the
