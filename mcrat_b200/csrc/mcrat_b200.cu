@@ -49,12 +49,13 @@ constexpr int PERSISTENT_MAX_PHOTONS = 1 << 21; // above this the list no longer
 #define MCRAT_SCAN_THREADS 128
 #endif
 // photons per thread: 7 in 2-D (10^5 photons x 2^20 cells: 24.87 ms = 98.9 % of the measured DFMA issue rate, against
-// 25.84 ms / 95.3 % with 8 and 25.54 ms with 6), 8 in 3-D (41.03 ms; 7: 41.20, 6: 41.52, 10: 41.21)
+// 25.84 ms / 95.3 % with 8 and 25.54 ms with 6), 9 in 3-D (39.85 ms = 92.6 %; 6 / 7 / 8 / 10 / 11 / 12 / 13 photons:
+// 41.52 / 41.20 / 41.03 / 41.21 / 40.17 / 41.15 / 40.17 ms -- the grid's last wave decides)
 #ifndef MCRAT_SCAN_P
 #define MCRAT_SCAN_P 7
 #endif
 #ifndef MCRAT_SCAN_P3
-#define MCRAT_SCAN_P3 8
+#define MCRAT_SCAN_P3 9
 #endif
 #ifndef MCRAT_SCAN_TILE
 #define MCRAT_SCAN_TILE 256
