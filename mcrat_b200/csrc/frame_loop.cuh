@@ -1,0 +1,262 @@
+// frame_loop.cuh -- persistent frame loop (team and solo kernels).
+// Part of the single translation unit mcrat_b200.cu (included there, in this order); not a stand-alone header.
+#pragma once
+
+// ------------------------------------------------------------------------------------------
+// Persistent frame loop: the whole while-loop of Src/mcrat.c:761-851 in ONE launch.
+//
+// The streamed loop above costs four dependent kernel launches per scattering; for lists that fit
+// in L2 the launch boundaries, not the work, set the iteration time.  Here every sub-shard (one
+// reference "rank") is owned by `bps` resident blocks that iterate on their own:
+//   pass (push + re-check + free-path draw + block arg-min)  ->  arrive
+//   last arriver: re-locate the few photons that left their cell (one warp per photon through the
+//                 bounding-box index), shard arg-min, scattering event, publish the new clock /
+//                 push list                                  ->  release
+//   the other blocks spin on the shard's generation word (ld.acquire.gpu) and start the next pass.
+// Shards never wait for each other (exactly like MPI ranks), so a rank that finishes its frame or
+// rejects a Klein-Nishina candidate does not hold the others up.  All blocks are co-resident
+// (cooperative launch); with one block per shard a block walks through its shards one after the other.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+constexpr int RELOC_HEAVY = 64; // re-locations per shard and iteration above which the grid-wide K1b / K1c serve better
+
+// relocated photons of this iteration: new cell, comoving momentum, tau', free-path draw
+template <int THREADS>
+__device__ __forceinline__ void finish_reloc(DevCtx &d, ShardState &st, const int s, const int R)
+{
+    int missing = 0;
+    for (int j = threadIdx.x; j < R; j += THREADS)
+        if (finish_one<true>(d, st, s, d.reloc_slot[st.first + j], d.reloc_best[st.first + j], 0)) missing++;
+    if (missing) atomicAdd(&d.gs->not_found, missing);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        d.sh[s].reloc_n = 0;
+        if (R > RELOC_HEAVY) st.reloc_heavy = 1;
+    }
+}
+
+// the shard's relocation entries [first, first+R): one warp per photon through the bounding-box index
+template <int THREADS>
+__device__ __forceinline__ void relocate_shard(DevCtx &d, ShardState &st, const int s, const int R)
+{
+    long long cells_tested = 0, boxes_tested = 0;
+    for (int j = threadIdx.x >> 5; j < R; j += THREADS / 32) {
+        const int q = st.first + j;
+        const int best = warp_locate_indexed(d, d.reloc_h0[q], d.reloc_h1[q], d.reloc_h2[q], cells_tested, boxes_tested);
+        if ((threadIdx.x & 31) == 0) d.reloc_best[q] = best;
+    }
+    if ((threadIdx.x & 31) == 0 && (cells_tested | boxes_tested)) {
+        atomicAdd((unsigned long long *)&d.gs->cell_evals, (unsigned long long)cells_tested);
+        atomicAdd((unsigned long long *)&d.gs->box_evals, (unsigned long long)boxes_tested);
+    }
+    __syncthreads();
+    finish_reloc<THREADS>(d, st, s, R);
+    __syncthreads();
+}
+
+// A sub-shard is run by a team of `bps` pass blocks and one event block, all resident:
+//   pass block b:  pass over its slice -> ticket on gst.arrive -> spin on gst.gen -> pull the state -> next pass
+//   event block:   spin until all bps tickets of the iteration are drawn -> re-locate -> shard arg-min -> event;
+//                  the state is published (gst.gen released) the moment a candidate is accepted, so the pass blocks
+//                  run the next pass while the event block is still busy with the second half of the scatter; the
+//                  scattered photon's own next pass is done by the event block (mini-pass, slot `bps` of the minima).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_kernel(DevCtx d, const int bps)
+{
+    __shared__ ShardState st; // this block's copy of the shard's state
+    __shared__ int sh_flag;
+    GlobalState &gs = *d.gs;
+    const int team = bps + 1;
+    const int groups = gridDim.x / team;
+    const int g = blockIdx.x / team, role = blockIdx.x - g * team;
+    if (g >= groups) return;
+    const bool is_event_block = (role == bps);
+
+    for (int s = g; s < d.nshards; s += groups) {
+        ShardState &gst = d.sh[s];
+        // global -> shared (the copied part only; the protocol words live in global memory)
+        auto pull = [&]() {
+            if (threadIdx.x < SHARD_STATE_WORDS)
+                reinterpret_cast<unsigned long long *>(&st)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&gst)[threadIdx.x];
+            __syncthreads();
+        };
+        // thread 0 spins until *word >= target (relaxed polls, one acquire at the end); false after ~1 s
+        auto spin_until = [&](const unsigned *word, unsigned target) -> bool {
+            if (threadIdx.x == 0) {
+                unsigned spins = 0;
+                int ok = 1;
+                if (ld_acquire_u32(word) < target) { // fast path: already there, one round trip
+                    while (ld_relaxed_u32(word) < target) {
+                        __nanosleep(40);
+                        if (++spins > (1u << 24)) { // never in a healthy run; refuse to hang the GPU
+                            gs.error = MCRAT_B200_ERR_STATE;
+                            ok = 0;
+                            break;
+                        }
+                    }
+                    (void)ld_acquire_u32(word);
+                }
+                sh_flag = ok;
+            }
+            __syncthreads();
+            return sh_flag != 0;
+        };
+        __syncthreads();
+        pull();
+        // stop test at entry: shard state only, so that all blocks of the team decide alike
+        bool halt = st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters);
+        unsigned k = 0; // iterations of this launch; gst.arrive / gst.gen were zeroed before it
+
+        if (!is_event_block) {
+            // ---------------- pass block ----------------
+            const int b = role;
+            while (!halt) {
+                double best_t = DBL_MAX;
+                int best_i = INT_MAX;
+                pass_body<true, true, THREADS>(d, st, s, b, bps, 0, 0, best_t, best_i);
+                block_argmin<THREADS>(best_t, best_i);
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    int bidx = -1;
+                    double btemp = 0;
+                    if (best_i != INT_MAX) {
+                        bidx = d.ph.idx[best_i];
+                        if (bidx >= 0) btemp = d.cells.temp[bidx];
+                    }
+                    d.bm_t[s * team + b] = best_t;
+                    d.bm_i[s * team + b] = best_i;
+                    d.bm_idx[s * team + b] = bidx;
+                    d.bm_temp[s * team + b] = btemp;
+                    __threadfence();
+                    atomicAdd(&gst.arrive, 1u);
+                }
+                ++k;
+                if (!spin_until(&gst.gen, k)) break;
+                pull();
+                halt = st.halt != 0;
+                __syncthreads();
+            }
+        } else {
+            // ---------------- event block ----------------
+            if (threadIdx.x == 0) {
+                d.bm_t[s * team + bps] = DBL_MAX;
+                d.bm_i[s * team + bps] = INT_MAX;
+                st.mini_slot = -1;
+            }
+            __syncthreads();
+            while (!halt) {
+                if (!spin_until(&gst.arrive, (k + 1) * (unsigned)bps)) break;
+                ++k;
+                // this thread's entry of the block minima and the relocation count: one round trip
+                double pre_t = DBL_MAX;
+                int pre_i = INT_MAX;
+                const bool have_pre = (team <= THREADS);
+                int pre_idx = -2;
+                double pre_temp = 0;
+                if (have_pre && (int)threadIdx.x < team) {
+                    pre_t = *(volatile double *)&d.bm_t[s * team + threadIdx.x];
+                    pre_i = *(volatile int *)&d.bm_i[s * team + threadIdx.x];
+                    pre_idx = *(volatile int *)&d.bm_idx[s * team + threadIdx.x];
+                    pre_temp = *(volatile double *)&d.bm_temp[s * team + threadIdx.x];
+                }
+                const int R = *(volatile int *)&gst.reloc_n;
+                if (R > 0) relocate_shard<THREADS>(d, st, s, R);
+                const bool released = event_body<THREADS>(d, s, st.first, R, team, 0, 0.0, st, &gst, k, s * team + bps, have_pre,
+                                                          pre_t, pre_i, pre_idx, pre_temp);
+                if (!released) {
+                    // frame end, Klein-Nishina walk exhausted, cyclo-synchrotron run: publish now
+                    if (threadIdx.x == 0) {
+                        st.halt = (loop_stopped(gs, st) || st.reloc_heavy) ? 1 : 0;
+                        st.mini_slot = -1;
+                        d.bm_t[s * team + bps] = DBL_MAX;
+                        d.bm_i[s * team + bps] = INT_MAX;
+                    }
+                    __syncthreads();
+                    if (threadIdx.x < SHARD_STATE_WORDS)
+                        reinterpret_cast<unsigned long long *>(&gst)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&st)[threadIdx.x];
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        __threadfence();
+                        st_release_u32(&gst.gen, k);
+                    }
+                } else if (threadIdx.x == 0 && st.mini_slot < 0) {
+                    d.bm_t[s * team + bps] = DBL_MAX; // released with a halt: no mini-pass ran
+                    d.bm_i[s * team + bps] = INT_MAX;
+                }
+                __syncthreads();
+                halt = st.halt != 0;
+            }
+            // the state proper is current in global memory (published with every release)
+        }
+    }
+}
+
+// With more sub-shards than resident teams the GPU is busy anyway (many events in flight per SM) and throughput,
+// not the latency of one shard, is what counts: one block per sub-shard does pass and event in turn, and walks through
+// its shards one after the other if there are more shards than resident blocks.  No inter-block protocol at all.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_solo_kernel(DevCtx d)
+{
+    __shared__ ShardState st;
+    GlobalState &gs = *d.gs;
+    for (int s = blockIdx.x; s < d.nshards; s += gridDim.x) {
+        ShardState &gst = d.sh[s];
+        __syncthreads();
+        if (threadIdx.x < SHARD_STATE_WORDS)
+            reinterpret_cast<unsigned long long *>(&st)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&gst)[threadIdx.x];
+        __syncthreads();
+        bool halt = st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters);
+        while (!halt) {
+            double best_t = DBL_MAX;
+            int best_i = INT_MAX;
+            pass_body<true, true, THREADS>(d, st, s, 0, 1, 0, 0, best_t, best_i);
+            block_argmin<THREADS>(best_t, best_i);
+            if (threadIdx.x == 0) {
+                d.bm_t[s] = best_t;
+                d.bm_i[s] = best_i;
+            }
+            __syncthreads();
+            const int R = *(volatile int *)&gst.reloc_n;
+            if (R > 0) relocate_shard<THREADS>(d, st, s, R);
+            event_body<THREADS>(d, s, st.first, R, 1, 0, 0.0, st);
+            if (threadIdx.x == 0) st.halt = (loop_stopped(gs, st) || st.reloc_heavy) ? 1 : 0;
+            __syncthreads();
+            halt = st.halt != 0;
+        }
+        if (threadIdx.x < SHARD_STATE_WORDS)
+            reinterpret_cast<unsigned long long *>(&gst)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&st)[threadIdx.x];
+    }
+}
+
+// head of the time order only (step API calcMeanFreePath; single shard)
+__global__ void __launch_bounds__(EVT_THREADS) head_kernel(DevCtx d, int nb)
+{
+    double bt = DBL_MAX;
+    int bi = INT_MAX;
+    for (int k = threadIdx.x; k < nb; k += EVT_THREADS)
+        if (lex_less(d.bm_t[k], d.bm_i[k], bt, bi)) {
+            bt = d.bm_t[k];
+            bi = d.bm_i[k];
+        }
+    block_argmin<EVT_THREADS>(bt, bi);
+    if (threadIdx.x == 0) {
+        d.sh[0].head_idx = bi;
+        d.sh[0].head_tts = bt;
+    }
+}

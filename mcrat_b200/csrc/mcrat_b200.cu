@@ -17,6 +17,13 @@
 //                          rotations, boost back; plus the driver's bookkeeping of
 //                          Src/mcrat.c:777-846.
 //   K5  cs_absorb_kernel   phAbsCyclosynch, Src/mc_cyclosynch.c:1571-1644.
+//   K7  hot_table_kernel   thermal Klein-Nishina cross-section table, Src/hot_x_section.c:82-206.
+//   K8  rebin_*_kernel     rebinCyclosynchCompPhotons, Src/mc_cyclosynch.c:244-710.
+//       frame_loop_kernel  the whole while-loop of Src/mcrat.c:761-851 in one cooperative launch.
+// Files (one translation unit, included below in this order): state.cuh (loop state, columns, DevCtx),
+// pass_kernels.cuh (helpers, AoS <-> SoA, K4+K2), scan_kernels.cuh (K1 / K1b / K1c, finish, un-fused free path),
+// event.cuh (K3), frame_loop.cuh (persistent loop), aux_kernels.cuh (K5, K7, statistics, K8, peak probes);
+// device_math.cuh holds the physics in the reference's operation order.  This file: the host side and the C ABI.
 // No CPU fallback exists: every entry point fails with MCRAT_B200_ERR_CUDA without a device.
 #include "../../include/mcrat_b200.h"
 #include "device_math.cuh"
@@ -36,2792 +43,13 @@ static_assert(sizeof(mcrat_photon) == 176, "struct photon layout (Src/mcrat.h:14
 
 #define API extern "C" __attribute__((visibility("default")))
 
-// ------------------------------------------------------------------------------------------
-// device-side data
-// ------------------------------------------------------------------------------------------
-enum : unsigned char { F_MOVABLE = 1, F_RECALC = 2 };
-
-constexpr int MAX_DT = 16;         // pushes recorded by one event (1 + Klein-Nishina rejections)
-constexpr int BLOCKMIN_CAP = 8192; // per-block arg-min slots (persistent loop: two per sub-shard at 4096 sub-shards)
-constexpr int MAX_SHARDS = 4096;
-constexpr int PERSISTENT_MAX_PHOTONS = 1 << 21; // above this the list no longer fits in L2: streamed loop, streaming cache hints
-#ifndef MCRAT_SCAN_THREADS
-#define MCRAT_SCAN_THREADS 128
-#endif
-// photons per thread: 7 in 2-D (10^5 photons x 2^20 cells: 24.87 ms = 98.9 % of the measured DFMA issue rate, against
-// 25.84 ms / 95.3 % with 8 and 25.54 ms with 6), 9 in 3-D (39.85 ms = 92.6 %; 6 / 7 / 8 / 10 / 11 / 12 / 13 photons:
-// 41.52 / 41.20 / 41.03 / 41.21 / 40.17 / 41.15 / 40.17 ms -- the grid's last wave decides)
-#ifndef MCRAT_SCAN_P
-#define MCRAT_SCAN_P 7
-#endif
-#ifndef MCRAT_SCAN_P3
-#define MCRAT_SCAN_P3 9
-#endif
-#ifndef MCRAT_SCAN_TILE
-#define MCRAT_SCAN_TILE 256
-#endif
-#ifndef MCRAT_SCAN_UNROLL
-#define MCRAT_SCAN_UNROLL 8
-#endif
-#ifndef MCRAT_SCAN_CTAS_PER_SM
-#define MCRAT_SCAN_CTAS_PER_SM 32
-#endif
-#define MCRAT_PRAGMA_STR2(x) #x
-#define MCRAT_PRAGMA_STR(x) MCRAT_PRAGMA_STR2(x)
-constexpr int SCAN_THREADS = MCRAT_SCAN_THREADS;
-constexpr int SCAN_P2 = MCRAT_SCAN_P;      // photons per thread held in registers, 2-D
-constexpr int SCAN_P3 = MCRAT_SCAN_P3;     // ... 3-D
-constexpr int SCAN_TILE = MCRAT_SCAN_TILE; // cells per shared-memory stage
-constexpr int FEW_RMAX = 128;  // relocating photons handled per pass of the cell-parallel scan
-constexpr int RELOC_LIST_SCAN_MAX = 2048;
-
-struct PhotonCols {
-    double *r0, *r1, *r2, *p0, *p1, *p2, *p3, *c0, *c1, *c2, *c3, *s0, *s1, *s2, *s3, *nscatt, *weight, *tau, *tts;
-    // derived columns, rewritten whenever p / tau are (store_momentum, store_tau): what the pass reads instead of
-    // them.  v_k = (p_k * (1/p0)) * C_LIGHT is the reference's own intermediate of the push (Src/mclib.c:1074-1080),
-    // ntau = -1/tau that of the free path (Src/mclib.c:683): same roundings, one division each per *change* of the
-    // photon instead of per photon-iteration, and 24 + 8 bytes per photon-iteration instead of 32 + 8.
-    double *v0, *v1, *v2, *ntau;
-    // safe[i]: the value of the shard's path counter (ShardState.path) up to which photon i provably cannot have left
-    // its cell or the domain, so that the pass may skip its containment re-check (0: always re-check); see safe_path()
-    unsigned long long *safe;
-    int *idx;
-    unsigned char *flags;
-    char *type;
-};
-
-struct CellCols {
-    int n, n_padded;
-    const double4 *geoA; // 2-D: (c0, c1, h0, h1); 3-D: (c0, c1, c2, h0)     h = 0.5 * size
-    const double2 *geoB; // 3-D: (h1, h2)
-    const double *r0, *r1, *r2, *v0, *v1, *v2, *dens, *dens_lab, *temp, *gamma, *B0, *B1, *B2;
-    double *k2; // K_2(1/theta) of the cell's temperature (Src/electron.c:215), filled on first use; 0 = not yet
-    double dom[6];
-    // optional two-level bounding-box index over consecutive cells (BOX_T cells per level-1 box,
-    // BOX_T level-1 boxes per level-2 box): 2 doubles (lo, hi) per dimension, 3 dimensions stored
-    const double *box1, *box2;
-    int nbox1, nbox2;
-};
-
-constexpr int BOX_T = 32;
-
-// One sub-shard = one "rank" of the reference: a contiguous range of photon slots with its own
-// clock, its own time-ordered event sequence (shard-local arg-min, exactly as per MPI rank,
-// Src/mcrat.c:139-164) and its own Philox streams.
-struct ShardState {
-    double time_now, remaining_time, last_time_step;
-    double dt_list[MAX_DT];
-    double head_tts;
-    unsigned long long iter;
-    unsigned long long path; // length of all pushes before the pending ones, in 1/PATH_SCALE cm, rounded up (path_units)
-    long long scatt_cnt, reloc_total, slots, iters_done;
-    int n_dt, pushed_slot; // pushed_slot: global slot index
-    int done, pause_cs, counted_stopped;
-    int last_scattered_idx, head_idx; // global slot indices
-    int first, count;                 // slot range
-    int mini_slot;                    // persistent loop: the photon whose next pass the event block does itself, or -1
-    int pad1_;
-    int halt;                         // persistent loop: loop_stopped() as evaluated by the publishing block
-    int reloc_heavy;                  // the last iteration re-located many photons: better served by K1b / K1c
-    int pad0_;
-    // ---- everything above is the shard's state proper (the persistent loop keeps a shared-memory copy of it
-    // and writes it back once per iteration); below: words other blocks update with atomics, never copied ----
-    unsigned int arrive;              // tickets drawn by blocks that finished their pass (monotonic)
-    unsigned int gen;                 // iterations completed, published by the last arriver (monotonic)
-    int reloc_n;                      // entries of this shard's region of the relocation list
-    int pad_;
-};
-constexpr int SHARD_STATE_WORDS = offsetof(ShardState, arrive) / 8; // 8-byte words of the copied part
-static_assert(offsetof(ShardState, arrive) % 8 == 0, "ShardState: copied part must be a whole number of 8-byte words");
-
-struct GlobalState {
-    int reloc_count[2];
-    int error, not_found, n_stopped;
-    long long cell_evals, box_evals, max_iters;
-    unsigned long long replay_cursor, replay_base, replay_n;
-    int abs_count, cs_scatt_count;
-    double abs_weight;
-    // cyclo-synchrotron bookkeeping of the driver, Src/mcrat.c:792-831
-    int cs_max_photons;        // rebin threshold (max_photons of mc.par); INT_MAX: never
-    int cs_scatt_num;          // scatt_cyclosynch_num_ph
-    int cs_emitted;            // pool photons replaced on the device
-    double cs_comptonized_w;   // n_comptonized
-#ifdef MCRAT_TIMING
-    long long dbg[32];         // SM-cycle accumulators of shard 0 (tools/loop_timing.py; not in the product build)
-#endif
-};
-
-#ifdef MCRAT_TIMING
-#define TSTAMP_DECL long long t_last__ = clock64()
-#define TSTAMP(gsref, k)                                 \
-    do {                                                 \
-        long long now__ = clock64();                     \
-        (gsref).dbg[k] += now__ - t_last__;              \
-        t_last__ = now__;                                \
-    } while (0)
-#else
-#define TSTAMP_DECL
-#define TSTAMP(gsref, k)
-#endif
-
-struct DevCtx {
-    int dims, geom, stokes, tau_calc, cs, b_calc;
-    double epsilon_b;
-    uint32_t k0, k1; // k1 is XORed with the sub-shard's global id
-    uint32_t shard_base;
-    int replay;
-    int cap;
-    int nshards, shard_size, blocks_per_shard;
-    int mj_rounds;    // warp-wide Maxwell-Juttner sampling: rounds of 64 trials before the sequential loop takes over
-    int recheck_skip; // 0: every photon re-checks its cell in every pass; 1: skip while provably inside (safe_path);
-                      // 2: decide as in 1 but re-check anyway and raise an error if a skipped photon had left (tests)
-    const double *dom_dev; // cells.dom in global memory, for safe_path()
-    double path_pad;  // bound on the rounding error of one push of a photon inside the domain, cm
-    int stream_hints; // the list is larger than L2: photon columns are streamed past it (ld/st.global.cs) so that the
-                      // cell geometry the pass gathers from stays resident
-    PhotonCols ph;
-    CellCols cells;
-    HotTable table;
-    ShardState *sh;
-    GlobalState *gs;
-    // relocation scratch
-    int *reloc_slot;
-    double *reloc_h0, *reloc_h1, *reloc_h2;
-    int *reloc_best;
-    int reloc_cap;
-    // arg-min scratch, one entry per pass block
-    double *bm_t;
-    int *bm_i;
-    // team kernel: cell index and cell temperature of the block's best candidate, so that the event block gets
-    // what the scattering lane needs first together with the minima (the pass blocks' time is hidden, the event's is not)
-    int *bm_idx;
-    double *bm_temp;
-    // replay
-    const double *replay_buf;
-    int *prefix_block;
-};
-
-// ------------------------------------------------------------------------------------------
-// small device helpers
-// ------------------------------------------------------------------------------------------
-// every kernel of the frame loop evaluates the same stop condition, so one iteration of a shard
-// is either executed completely or not at all
-__device__ __forceinline__ bool loop_stopped(const GlobalState &gs, const ShardState &sh)
-{
-    return (gs.error != 0) | sh.done | sh.pause_cs | (gs.max_iters >= 0 && sh.iters_done >= gs.max_iters);
-}
-
-__device__ __forceinline__ int shard_of(const DevCtx &d, int slot) { return slot / d.shard_size; }
-
-__device__ __forceinline__ bool lex_less(double ta, int ia, double tb, int ib) { return (ta < tb) || (ta == tb && ia < ib); }
-
-// ---- skipping the containment re-check while a photon provably cannot have left its cell ------------------------
-// The reference re-checks every photon's cached cell in every iteration (Src/mclib.c:469-597), and almost always
-// finds it unchanged.  A photon that sits at distance >= dist from the boundary of (its cell intersected with the domain)
-// stays inside while the total length of its pushes is < dist, whatever its direction; all movable photons of a
-// shard are pushed by the same times, so one counter per shard (ShardState.path, integer units, every push rounded
-// up, plus a bound on the rounding of the position update) and one threshold per photon (PhotonCols.safe) decide it.
-// The re-check that is skipped has no side effect when it succeeds, so the photons are bit-identical; the margins
-// (safe_distance) are far above the rounding of the reference's coordinate evaluation.
-constexpr double PATH_SCALE = 256.0;
-constexpr unsigned long long PATH_SAT = 1ull << 62;
-
-__device__ __forceinline__ unsigned long long path_units(double dt, double pad)
-{
-    const double x = (C_LIGHT * fabs(dt) * (1.0 + 1e-9) + pad) * PATH_SCALE;
-    if (!(x < 4e18)) return PATH_SAT;
-    return __double2ull_ru(x);
-}
-
-__device__ __forceinline__ unsigned long long path_add(unsigned long long a, unsigned long long b)
-{
-    const unsigned long long c = a + b;
-    return (a >= PATH_SAT || b >= PATH_SAT || c >= PATH_SAT) ? PATH_SAT : c;
-}
-
-// the pending pushes become part of the path; called wherever a shard's push list is replaced or cleared
-__device__ __forceinline__ void fold_path(ShardState &sh, double pad)
-{
-    unsigned long long p = sh.path;
-    for (int k = 0; k < sh.n_dt; ++k) p = path_add(p, path_units(sh.dt_list[k], pad));
-    sh.path = p;
-}
-
-__device__ __forceinline__ unsigned long long path_after_pending(const ShardState &sh, double pad)
-{
-    unsigned long long p = sh.path;
-    for (int k = 0; k < sh.n_dt; ++k) p = path_add(p, path_units(sh.dt_list[k], pad));
-    return p;
-}
-
-// Lower bound (cm) on the Euclidean distance from the photon at hydro coordinates h (inside cell blk and inside the
-// domain) to the nearest point outside either.  Per coordinate the margin m = min(half size - |h - c|, h - dom_lo,
-// dom_hi - h); a length coordinate (x, y, z, cylindrical / spherical radius) is 1-Lipschitz in the position, an
-// angle seen from the origin (axis) changes by at most asin(length / r) (asin(length / rho)), and sin(m) >= 0.8 m
-// on [0, 1].  Margins below 1e-7 of the coordinate's scale (1e-6 rad) give 0: never skipped.  The factor 0.5
-// leaves half of every margin for the rounding of the coordinates themselves.
-__device__ __forceinline__ double margin_length(double h, double c, double hs, double lo, double hi)
-{
-    const double m = fmin(hs - fabs(h - c), fmin(h - lo, hi - h));
-    return (m > 1e-7 * fmax(fabs(h), fabs(c))) ? m : 0.0;
-}
-
-__device__ __forceinline__ double margin_angle(double h, double c, double hs, double lo, double hi, double full, double lever)
-{
-    double m = fmin(hs - fabs(h - c), fmin(h - lo, hi - h));
-    m = fmin(m, fmin(h, full - h)); // the pole / the wrap of the azimuth
-    return (m > 1e-6) ? 0.8 * lever * fmin(m, 1.0) : 0.0;
-}
-
-// not inlined, arguments by value: the pass kernel runs at 64 registers and takes this path for a fraction of a
-// percent of its photons.  dom: the domain bounds in global memory (DevCtx.dom_dev).
-__device__ __noinline__ unsigned long long safe_path(const double4 *geoA, const double2 *geoB, const double *dom, int geom,
-                                                      int ndim3, int blk, double h0, double h1, double h2, double v0,
-                                                      double v1, double v2, int movable, unsigned long long s_now)
-{
-    if (movable) { // |v| <= c up to rounding is what path_units assumes
-        const double b2 = (v0 * v0 + v1 * v1 + v2 * v2) / (C_LIGHT * C_LIGHT);
-        if (!(b2 <= 1.0 + 1e-9)) return 0ull;
-    }
-    const double4 a = geoA[blk];
-    double dist;
-    if (!ndim3) { // (c0, c1, h0, h1)
-        dist = margin_length(h0, a.x, a.z, dom[0], dom[1]);
-        if (geom == G_SPHERICAL)
-            dist = fmin(dist, margin_angle(h1, a.y, a.w, dom[2], dom[3], PI, h0));
-        else
-            dist = fmin(dist, margin_length(h1, a.y, a.w, dom[2], dom[3]));
-    } else { // (c0, c1, c2, h0) + (h1, h2)
-        const double2 b = geoB[blk];
-        if (geom == G_SPHERICAL) {
-            dist = margin_length(h0, a.x, a.w, dom[0], dom[1]);
-            dist = fmin(dist, margin_angle(h1, a.y, b.x, dom[2], dom[3], PI, h0));
-            dist = fmin(dist, margin_angle(h2, a.z, b.y, dom[4], dom[5], 2.0 * PI, h0 * sin(h1)));
-        } else if (geom == G_POLAR) {
-            dist = margin_length(h0, a.x, a.w, dom[0], dom[1]);
-            dist = fmin(dist, margin_angle(h1, a.y, b.x, dom[2], dom[3], 2.0 * PI, h0));
-            dist = fmin(dist, margin_length(h2, a.z, b.y, dom[4], dom[5]));
-        } else {
-            dist = margin_length(h0, a.x, a.w, dom[0], dom[1]);
-            dist = fmin(dist, margin_length(h1, a.y, b.x, dom[2], dom[3]));
-            dist = fmin(dist, margin_length(h2, a.z, b.y, dom[4], dom[5]));
-        }
-    }
-    if (!(dist > 0 && dist < 1e300)) return 0ull; // also NaN
-    const double x = 0.5 * dist * PATH_SCALE;
-    if (!(x >= 1.0)) return 0ull;
-    const unsigned long long u = (x < 4e18) ? __double2ull_rd(x) : PATH_SAT;
-    const unsigned long long t = path_add(s_now, u);
-    return t >= PATH_SAT ? PATH_SAT - 1 : t;
-}
-
-// warp-shuffle + shared-memory arg-min over (time, slot); ties broken by lowest slot
-template <int THREADS>
-__device__ __forceinline__ void block_argmin(double &t, int &i)
-{
-    __shared__ double sh_t[THREADS / 32];
-    __shared__ int sh_i[THREADS / 32];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        double ot = __shfl_xor_sync(0xffffffffu, t, off);
-        int oi = __shfl_xor_sync(0xffffffffu, i, off);
-        if (lex_less(ot, oi, t, i)) {
-            t = ot;
-            i = oi;
-        }
-    }
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) {
-        sh_t[w] = t;
-        sh_i[w] = i;
-    }
-    __syncthreads();
-    if (w == 0) {
-        t = (lane < THREADS / 32) ? sh_t[lane] : DBL_MAX;
-        i = (lane < THREADS / 32) ? sh_i[lane] : INT_MAX;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            double ot = __shfl_xor_sync(0xffffffffu, t, off);
-            int oi = __shfl_xor_sync(0xffffffffu, i, off);
-            if (lex_less(ot, oi, t, i)) {
-                t = ot;
-                i = oi;
-            }
-        }
-    }
-}
-
-__device__ __forceinline__ bool in_cell(int ndim3, const CellCols &c, int blk, double h0, double h1, double h2)
-{
-    // Src/geometry.c:394-417 checkInBlock: 2|x-c| - size <= 0  <=>  |x-c| <= size/2 (both exact scalings)
-    double4 a = c.geoA[blk];
-    if (!ndim3) return (fabs(h0 - a.x) <= a.z) & (fabs(h1 - a.y) <= a.w);
-    double2 b = c.geoB[blk];
-    return (fabs(h0 - a.x) <= a.w) & (fabs(h1 - a.y) <= b.x) & (fabs(h2 - a.z) <= b.y);
-}
-
-__device__ __forceinline__ CellState load_cell_state(const CellCols &c, int i)
-{
-    CellState s;
-    s.v0 = c.v0[i];
-    s.v1 = c.v1[i];
-    s.v2 = c.v2[i];
-    s.r0 = c.r0[i];
-    s.r1 = c.r1[i];
-    s.r2 = c.r2[i];
-    s.gamma = c.gamma[i];
-    s.dens_lab = c.dens_lab[i];
-    s.temp = c.temp[i];
-    return s;
-}
-
-__device__ __forceinline__ void fluid_beta_of(const DevCtx &d, const CellState &c, double ph_r0, double ph_r1, double *fb)
-{
-    if (d.dims == D_THREE) {
-        hydro_vector_to_cartesian(d.dims, d.geom, fb, c.v0, c.v1, c.v2, c.r0, c.r1, c.r2);
-    } else if (d.dims == D_TWO_POINT_FIVE) {
-        double ph_phi = atan2(ph_r1, ph_r0);
-        hydro_vector_to_cartesian(d.dims, d.geom, fb, c.v0, c.v1, c.v2, c.r0, c.r1, ph_phi);
-    } else {
-        double ph_phi = atan2(ph_r1, ph_r0);
-        hydro_vector_to_cartesian(d.dims, d.geom, fb, c.v0, c.v1, 0, c.r0, c.r1, ph_phi);
-    }
-}
-
-// time_to_scatter of an in-domain photon, Src/mclib.c:675-687
-__device__ __forceinline__ double free_path_time(double tau, double xi)
-{
-    double mfp = (-1.0 / tau) * log(xi);
-    return mfp / C_LIGHT;
-}
-
-// x / C_LIGHT, correctly rounded, without the general division: q = RN(x * rc) with rc = RN(1 / C_LIGHT) is within
-// an ulp of the quotient, r = x - q * C_LIGHT is exact in one FMA, and RN(q + r * rc) is the correctly rounded
-// quotient (Markstein's theorem; C_LIGHT's significand is not all ones).  Outside the range where q, r stay normal
-// and finite the true division runs.  tests/test_gpu_parity.py::test_division_by_c_is_exact compares the two bit
-// for bit; tools/div_by_c_check.c does so on the host over 4e9 significands.
-__device__ __forceinline__ double div_by_c(double x)
-{
-    const double rc = 1.0 / C_LIGHT; // folded at compile time, correctly rounded
-    const double ax = fabs(x);
-    if (!(ax > 1e-280 && ax < 1e300)) return x / C_LIGHT;
-    const double q = x * rc;
-    const double r = fma(-q, C_LIGHT, x);
-    return fma(r, rc, q);
-}
-
-// free_path_time with ntau = -1/tau already formed (PhotonCols.ntau): bit-identical to it
-__device__ __forceinline__ double free_path_time_n(double ntau, double xi)
-{
-    double mfp = ntau * log(xi);
-    return div_by_c(mfp);
-}
-
-__device__ __forceinline__ void store_momentum(PhotonCols &ph, int i, double p0, double p1, double p2, double p3)
-{
-    ph.p0[i] = p0; ph.p1[i] = p1; ph.p2[i] = p2; ph.p3[i] = p3;
-    const double div = 1.0 / p0; // Src/mclib.c:1074
-    ph.v0[i] = p1 * div * C_LIGHT;
-    ph.v1[i] = p2 * div * C_LIGHT;
-    ph.v2[i] = p3 * div * C_LIGHT;
-}
-
-__device__ __forceinline__ void store_tau(PhotonCols &ph, int i, double tau)
-{
-    ph.tau[i] = tau;
-    ph.ntau[i] = -1.0 / tau;
-}
-
-// the pushes with v_k = (p_k / p0) * C_LIGHT already formed (PhotonCols.v*): bit-identical to apply_pushes
-__device__ __forceinline__ void apply_pushes_v(const ShardState &sh, int n_dt, double v0, double v1, double v2, double &r0,
-                                               double &r1, double &r2)
-{
-    for (int k = 0; k < n_dt; ++k) {
-        double t = sh.dt_list[k];
-        r0 += v0 * t;
-        r1 += v1 * t;
-        r2 += v2 * t;
-    }
-}
-
-// pending pushes of a shard's last event, applied one by one: the reference pushes once per
-// candidate it tries (Src/mclib.c:1138, 1332) and FP addition is not associative
-__device__ __forceinline__ void apply_pushes(const ShardState &sh, int n_dt, double p0, double p1, double p2, double p3,
-                                             double &r0, double &r1, double &r2)
-{
-    double div = 1.0 / p0; // Src/mclib.c:1074-1080
-    for (int k = 0; k < n_dt; ++k) {
-        double t = sh.dt_list[k];
-        r0 += p1 * div * C_LIGHT * t;
-        r1 += p2 * div * C_LIGHT * t;
-        r2 += p3 * div * C_LIGHT * t;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// AoS <-> SoA (the boundary: `struct photon` records <-> device columns)
-// ------------------------------------------------------------------------------------------
-__global__ void unpack_kernel(DevCtx d, const mcrat_photon *aos, int n)
-{
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        mcrat_photon p = aos[i];
-        d.ph.type[i] = p.type;
-        store_momentum(d.ph, i, p.p0, p.p1, p.p2, p.p3);
-        d.ph.c0[i] = p.comv_p0; d.ph.c1[i] = p.comv_p1; d.ph.c2[i] = p.comv_p2; d.ph.c3[i] = p.comv_p3;
-        d.ph.r0[i] = p.r0; d.ph.r1[i] = p.r1; d.ph.r2[i] = p.r2;
-        d.ph.s0[i] = p.s0; d.ph.s1[i] = p.s1; d.ph.s2[i] = p.s2; d.ph.s3[i] = p.s3;
-        d.ph.nscatt[i] = p.num_scatt;
-        d.ph.weight[i] = p.weight;
-        d.ph.idx[i] = p.nearest_block_index;
-        d.ph.tts[i] = p.time_to_scatter;
-        store_tau(d.ph, i, p.total_optical_depth);
-        d.ph.safe[i] = 0;
-        unsigned char f = 0;
-        if ((p.type != 'p') && (p.weight != 0)) f |= F_MOVABLE; // Src/mclib.c:1070
-        if (p.recalc_properties == 1) f |= F_RECALC;
-        d.ph.flags[i] = f;
-    }
-}
-
-__global__ void pack_kernel(DevCtx d, mcrat_photon *aos, int first, int n)
-{
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        int i = first + j;
-        mcrat_photon p;
-        memset(&p, 0, sizeof(p));
-        p.type = d.ph.type[i];
-        p.p0 = d.ph.p0[i]; p.p1 = d.ph.p1[i]; p.p2 = d.ph.p2[i]; p.p3 = d.ph.p3[i];
-        p.comv_p0 = d.ph.c0[i]; p.comv_p1 = d.ph.c1[i]; p.comv_p2 = d.ph.c2[i]; p.comv_p3 = d.ph.c3[i];
-        p.r0 = d.ph.r0[i]; p.r1 = d.ph.r1[i]; p.r2 = d.ph.r2[i];
-        p.s0 = d.ph.s0[i]; p.s1 = d.ph.s1[i]; p.s2 = d.ph.s2[i]; p.s3 = d.ph.s3[i];
-        p.num_scatt = d.ph.nscatt[i];
-        p.recalc_properties = (d.ph.flags[i] & F_RECALC) ? 1 : 0;
-        p.weight = d.ph.weight[i];
-        p.nearest_block_index = d.ph.idx[i];
-        p.time_to_scatter = d.ph.tts[i];
-        p.total_optical_depth = d.ph.tau[i];
-        aos[j] = p;
-    }
-}
-
-// cell SoA -> scan layout (centres + half sizes), NaN-padded so that padding never matches
-__global__ void build_geo_kernel(int ndim3, int n, int n_padded, const double *c0, const double *c1, const double *c2,
-                                 const double *s0, const double *s1, const double *s2, double4 *geoA, double2 *geoB)
-{
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += gridDim.x * blockDim.x) {
-        const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-        if (i < n) {
-            if (!ndim3) {
-                geoA[i] = make_double4(c0[i], c1[i], 0.5 * s0[i], 0.5 * s1[i]);
-            } else {
-                geoA[i] = make_double4(c0[i], c1[i], c2[i], 0.5 * s0[i]);
-                geoB[i] = make_double2(0.5 * s1[i], 0.5 * s2[i]);
-            }
-        } else {
-            geoA[i] = make_double4(qnan, qnan, qnan, qnan);
-            if (ndim3) geoB[i] = make_double2(qnan, qnan);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// K4+K2: fused push + locate re-check + free-path draw + block arg-min.
-// Grid = nshards x blocks_per_shard: a block never straddles two sub-shards.
-// ------------------------------------------------------------------------------------------
-#ifndef MCRAT_PASS_THREADS
-#define MCRAT_PASS_THREADS 256
-#endif
-// 5 blocks of 256 threads per SM (48 registers; the few spilled words are L1 hits) and a grid of two full waves:
-// 10^7 photons, 2-D: 174.6 us per pass against 187.1 us at 4 blocks / 64 registers and 183.3 us at 6 / 40 -- once
-// the re-check is skipped the kernel is a latency-bound stream and the extra loads in flight pay
-#ifndef MCRAT_PASS_MINB
-#define MCRAT_PASS_MINB 5
-#endif
-#ifndef MCRAT_PASS_CTAS_PER_SM
-#define MCRAT_PASS_CTAS_PER_SM 10
-#endif
-constexpr int PASS_THREADS = MCRAT_PASS_THREADS;
-
-// One block's share of a shard: photons j = b*THREADS + tid, stride nblk*THREADS.
-// LOCAL_RELOC = false: relocating photons go to the global list (gs.reloc_count[parity]) that
-// K1/K1b/K1c + finish_kernel work off; true: to the shard's own region [first, first+count) of the
-// list (persistent loop: shards advance independently of each other).
-template <bool FUSE_MFP, bool LOCAL_RELOC, int THREADS>
-__device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const int s, const int b, const int nblk,
-                                          const int sw, const int parity, double &best_t, int &best_i)
-{
-    const int n_dt = sh.n_dt;
-    const int pushed = sh.pushed_slot;
-    const unsigned long long iter = sh.iter;
-    const uint32_t k1 = d.k1 ^ (d.shard_base + (uint32_t)s);
-    const int ndim3 = (d.dims == D_THREE);
-    const double default_t = 1e12 / C_LIGHT; // Src/mclib.c:620, 684-687
-    const int first = sh.first, count = sh.count;
-    // path counter once the pending pushes are applied (what this pass does), and whether re-checks may be skipped:
-    // never on a new hydro frame (everything re-locates) nor in cyclo-synchrotron runs (Src/mclib.c:510-515 re-locates
-    // by the photon's state, not its position)
-    const unsigned long long s_now = path_after_pending(sh, d.path_pad);
-    const bool may_skip = d.recheck_skip && sw == 0 && !d.cs && s_now < PATH_SAT;
-    const bool verify = d.recheck_skip == 2;
-
-    const int mini = LOCAL_RELOC ? sh.mini_slot : -1;
-    for (int j = b * THREADS + threadIdx.x; j < count; j += nblk * THREADS) {
-        const int i = first + j;
-        if (i == mini) continue; // the event block runs this photon's pass itself (persistent loop)
-        // every column this photon can need is requested up front (one round trip to HBM instead
-        // of three dependent ones); the momentum is used by the pushes, tau by the free-path draw
-        unsigned char flags;
-        int idx = 0;
-        unsigned long long safe = 0;
-        double r0, r1, r2, v0, v1, v2, ntau;
-        if (!LOCAL_RELOC && d.stream_hints) {
-            flags = __ldcs(d.ph.flags + i);
-            if (may_skip) safe = __ldcs(d.ph.safe + i); else idx = __ldcs(d.ph.idx + i);
-            r0 = __ldcs(d.ph.r0 + i); r1 = __ldcs(d.ph.r1 + i); r2 = __ldcs(d.ph.r2 + i);
-            v0 = __ldcs(d.ph.v0 + i); v1 = __ldcs(d.ph.v1 + i); v2 = __ldcs(d.ph.v2 + i);
-            ntau = FUSE_MFP ? __ldcs(d.ph.ntau + i) : 0.0;
-        } else {
-            flags = d.ph.flags[i];
-            if (may_skip) safe = d.ph.safe[i]; else idx = d.ph.idx[i];
-            r0 = d.ph.r0[i]; r1 = d.ph.r1[i]; r2 = d.ph.r2[i];
-            v0 = d.ph.v0[i]; v1 = d.ph.v1[i]; v2 = d.ph.v2[i];
-            ntau = FUSE_MFP ? d.ph.ntau[i] : 0.0;
-        }
-        if (n_dt > 0 && (flags & F_MOVABLE) && i != pushed) {
-            apply_pushes_v(sh, n_dt, v0, v1, v2, r0, r1, r2);
-            if (!LOCAL_RELOC && d.stream_hints) {
-                __stcs(d.ph.r0 + i, r0);
-                __stcs(d.ph.r1 + i, r1);
-                __stcs(d.ph.r2 + i, r2);
-            } else {
-                d.ph.r0[i] = r0;
-                d.ph.r1[i] = r1;
-                d.ph.r2[i] = r2;
-            }
-        }
-        // findContainingHydroCell, Src/mclib.c:469-597
-        const bool skip = may_skip && (s_now < safe); // provably still inside its cell and the domain
-        double t = default_t;
-        bool have_t = true;
-        bool inside = skip;
-        if (!skip || verify) {
-            if (may_skip) idx = d.ph.idx[i];
-            double h0, h1, h2;
-            coord_to_hydro(d.dims, d.geom, r0, r1, r2, h0, h1, h2);
-            bool in_domain;
-            if (!ndim3)
-                in_domain = ((h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) && (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0])) &&
-                            (idx != -1);
-            else
-                in_domain = ((h2 < d.cells.dom[5]) && (h2 > d.cells.dom[4]) && (h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) &&
-                             (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0])) &&
-                            (idx != -1);
-            inside = false;
-            if (in_domain) {
-                int blk = (sw == 0) ? idx : 0;
-#if defined(MCRAT_EXP_NOGATHER)
-                bool inb = true; // ablation build: no cell-geometry gather (see MCRAT_EXP_NOCOMPUTE)
-#else
-                bool inb = in_cell(ndim3, d.cells, blk, h0, h1, h2);
-#endif
-                if (d.cs && blk == 0) { // Src/mclib.c:510-515
-                    if ((d.ph.c0[i]) + (d.ph.c1[i]) + (d.ph.c2[i]) + (d.ph.c3[i]) == 0) inb = false;
-                }
-                if (sw == 1 || !inb) {
-                    int pos = LOCAL_RELOC ? first + atomicAdd(&d.sh[s].reloc_n, 1) : atomicAdd(&d.gs->reloc_count[parity], 1);
-                    d.reloc_slot[pos] = i;
-                    d.reloc_h0[pos] = h0;
-                    d.reloc_h1[pos] = h1;
-                    d.reloc_h2[pos] = h2;
-                    d.reloc_best[pos] = INT_MAX;
-                    have_t = false; // finish completes this photon
-                } else {
-                    inside = true;
-                    if (may_skip && !skip)
-                        d.ph.safe[i] = safe_path(d.cells.geoA, d.cells.geoB, d.dom_dev, d.geom, ndim3, blk, h0, h1, h2, v0, v1, v2,
-                                                 flags & F_MOVABLE, s_now);
-                }
-            } else {
-                if (idx != -1) d.ph.idx[i] = -1; // Src/mclib.c:589-595
-            }
-            if (skip && !inside) d.gs->error = MCRAT_B200_ERR_STATE; // verify mode: the bound was wrong
-        }
-        if (inside && FUSE_MFP) {
-            // calcMeanFreePath, Src/mclib.c:657-687
-            if (flags & F_RECALC) {
-                if (skip) idx = d.ph.idx[i];
-                CellState c = load_cell_state(d.cells, idx);
-                int terr = 0;
-                const double tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, d.ph.p1[i], d.ph.p2[i],
-                                                 d.ph.p3[i], d.ph.c0[i], &terr);
-                if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
-                store_tau(d.ph, i, tau);
-                ntau = -1.0 / tau;
-                d.ph.flags[i] = flags & ~F_RECALC;
-            }
-#if defined(MCRAT_EXP_NOCOMPUTE)
-            // ablation build (profiles/ncu_r01_summary.md, "pass kernel: where the time goes"): the memory
-            // pattern alone, without Philox / log / divisions.  Never defined in the product build.
-            t = ntau * (double)j;
-#else
-            double xi = philox_mfp_uniform(d.k0, k1, iter, (uint32_t)j);
-            t = free_path_time_n(ntau, xi);
-#endif
-        }
-        if (FUSE_MFP && have_t) {
-            if (!LOCAL_RELOC && d.stream_hints)
-                __stcs(d.ph.tts + i, t);
-            else
-                d.ph.tts[i] = t;
-            if (lex_less(t, i, best_t, best_i)) {
-                best_t = t;
-                best_i = i;
-            }
-        }
-    }
-}
-
-template <bool FUSE_MFP>
-__global__ void __launch_bounds__(PASS_THREADS, MCRAT_PASS_MINB) pass_kernel(DevCtx d, int sw, int parity)
-{
-    const int s = blockIdx.x / d.blocks_per_shard;
-    const int b = blockIdx.x - s * d.blocks_per_shard;
-    if (blockIdx.x == 0 && threadIdx.x == 0) d.gs->reloc_count[parity ^ 1] = 0;
-    double best_t = DBL_MAX;
-    int best_i = INT_MAX;
-    if (!loop_stopped(*d.gs, d.sh[s]))
-        pass_body<FUSE_MFP, false, PASS_THREADS>(d, d.sh[s], s, b, d.blocks_per_shard, sw, parity, best_t, best_i);
-    if (FUSE_MFP) {
-        block_argmin<PASS_THREADS>(best_t, best_i);
-        if (threadIdx.x == 0) {
-            d.bm_t[blockIdx.x] = best_t;
-            d.bm_i[blockIdx.x] = best_i;
-        }
-    }
-}
-
-// push only: updatePhotonPosition called directly by the driver (Src/mcrat.c:841), and the
-// materialisation of pending event pushes before a download
-__global__ void __launch_bounds__(PASS_THREADS) flush_push_kernel(DevCtx d)
-{
-    for (int i = blockIdx.x * PASS_THREADS + threadIdx.x; i < d.cap; i += gridDim.x * PASS_THREADS) {
-        const ShardState &sh = d.sh[shard_of(d, i)];
-        const int n_dt = sh.n_dt;
-        if (n_dt == 0) continue;
-        unsigned char flags = d.ph.flags[i];
-        if ((flags & F_MOVABLE) && i != sh.pushed_slot) {
-            double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
-            apply_pushes_v(sh, n_dt, d.ph.v0[i], d.ph.v1[i], d.ph.v2[i], r0, r1, r2);
-            d.ph.r0[i] = r0;
-            d.ph.r1[i] = r1;
-            d.ph.r2[i] = r2;
-        }
-    }
-}
-
-__global__ void clear_push_kernel(DevCtx d)
-{
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < d.nshards; s += gridDim.x * blockDim.x) {
-        fold_path(d.sh[s], d.path_pad);
-        d.sh[s].n_dt = 0;
-        d.sh[s].pushed_slot = -1;
-    }
-}
-
-__global__ void set_push_kernel(DevCtx d, double t)
-{
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < d.nshards; s += gridDim.x * blockDim.x) {
-        fold_path(d.sh[s], d.path_pad);
-        d.sh[s].dt_list[0] = t;
-        d.sh[s].n_dt = 1;
-        d.sh[s].pushed_slot = -1;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// K1: photon x cell containment scan.  Photons in registers (SCAN_P2 / SCAN_P3 per thread), cells streamed
-// through a double-buffered shared-memory tile filled by TMA bulk copies.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-template <int NDIM3>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(DevCtx d, int parity, int tiles_per_chunk)
-{
-    const GlobalState &gs = *d.gs;
-    if (gs.error != 0) return;
-    constexpr int SCAN_P = NDIM3 ? SCAN_P3 : SCAN_P2;
-    const int count = gs.reloc_count[parity];
-    const int pbase = blockIdx.x * (SCAN_THREADS * SCAN_P);
-    if (pbase >= count) return;
-
-    extern __shared__ __align__(128) unsigned char scan_smem[];
-    constexpr uint32_t BYTES_A = SCAN_TILE * sizeof(double4);
-    constexpr uint32_t BYTES_B = NDIM3 ? SCAN_TILE * sizeof(double2) : 0;
-    double4(*sA)[SCAN_TILE] = reinterpret_cast<double4(*)[SCAN_TILE]>(scan_smem);
-    double2(*sB)[SCAN_TILE] = reinterpret_cast<double2(*)[SCAN_TILE]>(scan_smem + 2 * BYTES_A);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(scan_smem + 2 * BYTES_A + 2 * BYTES_B);
-
-    const int ntiles_total = d.cells.n_padded / SCAN_TILE;
-    const int tile0 = blockIdx.y * tiles_per_chunk;
-    const int ntiles = min(tiles_per_chunk, ntiles_total - tile0);
-    if (ntiles <= 0) return;
-
-    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-    double x0[SCAN_P], x1[SCAN_P], x2[SCAN_P];
-    int best[SCAN_P];
-#pragma unroll
-    for (int p = 0; p < SCAN_P; ++p) {
-        int j = pbase + p * SCAN_THREADS + threadIdx.x;
-        bool ok = j < count;
-        x0[p] = ok ? d.reloc_h0[j] : qnan;
-        x1[p] = ok ? d.reloc_h1[j] : qnan;
-        x2[p] = (ok && NDIM3) ? d.reloc_h2[j] : qnan;
-        best[p] = INT_MAX;
-    }
-
-    if (threadIdx.x == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(&bar[0], BYTES_A + BYTES_B);
-        tma_bulk_g2s(&sA[0][0], d.cells.geoA + (size_t)tile0 * SCAN_TILE, BYTES_A, &bar[0]);
-        if (NDIM3) tma_bulk_g2s(&sB[0][0], d.cells.geoB + (size_t)tile0 * SCAN_TILE, BYTES_B, &bar[0]);
-    }
-
-    for (int t = 0; t < ntiles; ++t) {
-        const int s = t & 1;
-        if (threadIdx.x == 0 && t + 1 < ntiles) {
-            mbar_expect_tx(&bar[s ^ 1], BYTES_A + BYTES_B);
-            tma_bulk_g2s(&sA[s ^ 1][0], d.cells.geoA + (size_t)(tile0 + t + 1) * SCAN_TILE, BYTES_A, &bar[s ^ 1]);
-            if (NDIM3)
-                tma_bulk_g2s(&sB[s ^ 1][0], d.cells.geoB + (size_t)(tile0 + t + 1) * SCAN_TILE, BYTES_B, &bar[s ^ 1]);
-        }
-        mbar_wait(&bar[s], (uint32_t)((t >> 1) & 1));
-        const int cbase = (tile0 + t) * SCAN_TILE;
-_Pragma(MCRAT_PRAGMA_STR(unroll MCRAT_SCAN_UNROLL))
-        for (int c = 0; c < SCAN_TILE; ++c) {
-            const double4 a = sA[s][c];
-            if (!NDIM3) {
-#pragma unroll
-                for (int p = 0; p < SCAN_P; ++p) {
-                    bool hit = (fabs(x0[p] - a.x) <= a.z) & (fabs(x1[p] - a.y) <= a.w);
-                    if (hit) best[p] = min(best[p], cbase + c);
-                }
-            } else {
-                const double2 b = sB[s][c];
-#pragma unroll
-                for (int p = 0; p < SCAN_P; ++p) {
-                    bool hit = (fabs(x0[p] - a.x) <= a.w) & (fabs(x1[p] - a.y) <= b.x) & (fabs(x2[p] - a.z) <= b.y);
-                    if (hit) best[p] = min(best[p], cbase + c);
-                }
-            }
-        }
-        __syncthreads(); // everyone is done with stage s before it is refilled at t+2
-    }
-#pragma unroll
-    for (int p = 0; p < SCAN_P; ++p) {
-        int j = pbase + p * SCAN_THREADS + threadIdx.x;
-        if (best[p] != INT_MAX && j < count) atomicMin(&d.reloc_best[j], best[p]);
-    }
-    if (threadIdx.x == 0 && blockIdx.y == 0) {
-        int nph = min(count - pbase, SCAN_THREADS * SCAN_P);
-        atomicAdd((unsigned long long *)&d.gs->cell_evals, (unsigned long long)nph * (unsigned long long)d.cells.n);
-    }
-}
-
-// K1b: the same containment test, cell-parallel, for a short relocation list
-template <int NDIM3>
-__global__ void __launch_bounds__(256) scan_few_kernel(DevCtx d, int parity)
-{
-    const GlobalState &gs = *d.gs;
-    if (gs.error != 0) return;
-    const int count = gs.reloc_count[parity];
-    if (count == 0) return;
-    __shared__ double sx0[FEW_RMAX], sx1[FEW_RMAX], sx2[FEW_RMAX];
-    __shared__ int sbest[FEW_RMAX];
-    for (int base = 0; base < count; base += FEW_RMAX) {
-        const int r = min(FEW_RMAX, count - base);
-        __syncthreads();
-        for (int j = threadIdx.x; j < r; j += blockDim.x) {
-            sx0[j] = d.reloc_h0[base + j];
-            sx1[j] = d.reloc_h1[base + j];
-            sx2[j] = NDIM3 ? d.reloc_h2[base + j] : 0.0;
-            sbest[j] = INT_MAX;
-        }
-        __syncthreads();
-        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < d.cells.n; c += gridDim.x * blockDim.x) {
-            const double4 a = d.cells.geoA[c];
-            double2 b = make_double2(0, 0);
-            if (NDIM3) b = d.cells.geoB[c];
-            for (int j = 0; j < r; ++j) {
-                bool hit;
-                if (!NDIM3)
-                    hit = (fabs(sx0[j] - a.x) <= a.z) & (fabs(sx1[j] - a.y) <= a.w);
-                else
-                    hit = (fabs(sx0[j] - a.x) <= a.w) & (fabs(sx1[j] - a.y) <= b.x) & (fabs(sx2[j] - a.z) <= b.y);
-                if (hit) atomicMin(&sbest[j], c);
-            }
-        }
-        __syncthreads();
-        for (int j = threadIdx.x; j < r; j += blockDim.x)
-            if (sbest[j] != INT_MAX) atomicMin(&d.reloc_best[base + j], sbest[j]);
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-        atomicAdd((unsigned long long *)&d.gs->cell_evals, (unsigned long long)count * (unsigned long long)d.cells.n);
-}
-
-// ------------------------------------------------------------------------------------------
-// K1c: the same first-match search through a two-level bounding-box index (opt-in,
-// mcrat_b200_config.scan_index).  The reference carries a disabled uniform-bucket accelerator
-// (Src/geometry.c:423-676, switched off at Src/mcrat_io.c:1985); this index is built over the
-// cells *in array order*, so walking boxes and cells in ascending index and stopping at the
-// first hit returns exactly the cell findContainingBlock returns (lowest containing index).
-// A box is padded outward by a few ulps so that every cell test that can succeed is reached.
-// ------------------------------------------------------------------------------------------
-__global__ void build_box1_kernel(int ndim3, int n, const double4 *geoA, const double2 *geoB, double *box1, int nbox1)
-{
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nbox1; b += gridDim.x * blockDim.x) {
-        double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
-        for (int c = b * BOX_T; c < min(n, b * BOX_T + BOX_T); ++c) {
-            double4 a = geoA[c];
-            double cc[3], hh[3];
-            if (!ndim3) {
-                cc[0] = a.x; cc[1] = a.y; cc[2] = 0; hh[0] = a.z; hh[1] = a.w; hh[2] = 0;
-            } else {
-                double2 q = geoB[c];
-                cc[0] = a.x; cc[1] = a.y; cc[2] = a.z; hh[0] = a.w; hh[1] = q.x; hh[2] = q.y;
-            }
-            for (int k = 0; k < 3; ++k) {
-                double pad = 8.0 * 2.220446049250313e-16 * (fabs(cc[k]) + fabs(hh[k]));
-                lo[k] = fmin(lo[k], cc[k] - hh[k] - pad);
-                hi[k] = fmax(hi[k], cc[k] + hh[k] + pad);
-            }
-        }
-        for (int k = 0; k < 3; ++k) {
-            box1[6 * b + 2 * k] = lo[k];
-            box1[6 * b + 2 * k + 1] = hi[k];
-        }
-    }
-}
-
-__global__ void build_box2_kernel(const double *box1, int nbox1, double *box2, int nbox2)
-{
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nbox2; b += gridDim.x * blockDim.x) {
-        double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
-        for (int c = b * BOX_T; c < min(nbox1, b * BOX_T + BOX_T); ++c)
-            for (int k = 0; k < 3; ++k) {
-                lo[k] = fmin(lo[k], box1[6 * c + 2 * k]);
-                hi[k] = fmax(hi[k], box1[6 * c + 2 * k + 1]);
-            }
-        for (int k = 0; k < 3; ++k) {
-            box2[6 * b + 2 * k] = lo[k];
-            box2[6 * b + 2 * k + 1] = hi[k];
-        }
-    }
-}
-
-__device__ __forceinline__ bool in_box(int ndim3, const double *bx, double x0, double x1, double x2)
-{
-    bool in = (x0 >= bx[0]) & (x0 <= bx[1]) & (x1 >= bx[2]) & (x1 <= bx[3]);
-    if (ndim3) in = in & (x2 >= bx[4]) & (x2 <= bx[5]);
-    return in;
-}
-
-// One warp locates one photon.  Level-2 boxes are all tested first (independent loads, 32 per
-// round, hits kept as one bit per round and lane), then the hits are descended in ascending order:
-// 32 level-1 boxes per level-2 box and 32 cells per level-1 box, one per lane; the lowest lane of
-// the first ballot with a containing cell is the lowest containing index = findContainingBlock's answer.
-__device__ __forceinline__ int warp_locate_indexed(const DevCtx &d, const double x0, const double x1, const double x2,
-                                                   long long &cells_tested, long long &boxes_tested)
-{
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int ndim3 = (d.dims == D_THREE);
-    const CellCols &c = d.cells;
-    int best = INT_MAX;
-    for (int chunk = 0; chunk < c.nbox2 && best == INT_MAX; chunk += 2048) {
-        const int rounds = min(64, (c.nbox2 - chunk + 31) / 32);
-        unsigned long long mine = 0;
-#pragma unroll 4
-        for (int r = 0; r < rounds; ++r) {
-            const int b2 = chunk + r * 32 + lane;
-            if (b2 < c.nbox2 && in_box(ndim3, c.box2 + 6 * b2, x0, x1, x2)) mine |= 1ull << r;
-        }
-        boxes_tested += min(c.nbox2 - chunk, 2048);
-        for (int r = 0; r < rounds && best == INT_MAX; ++r) {
-            unsigned m2 = __ballot_sync(full, (mine >> r) & 1ull);
-            while (m2 && best == INT_MAX) {
-                const int B2 = chunk + r * 32 + (__ffs(m2) - 1);
-                m2 &= m2 - 1;
-                const int b1 = B2 * BOX_T + lane;
-                unsigned m1 = __ballot_sync(full, b1 < c.nbox1 && in_box(ndim3, c.box1 + 6 * b1, x0, x1, x2));
-                boxes_tested += min(BOX_T, c.nbox1 - B2 * BOX_T);
-                while (m1 && best == INT_MAX) {
-                    const int B1 = B2 * BOX_T + (__ffs(m1) - 1);
-                    m1 &= m1 - 1;
-                    const int cell = B1 * BOX_T + lane;
-                    const unsigned mc = __ballot_sync(full, cell < c.n && in_cell(ndim3, c, cell, x0, x1, x2));
-                    cells_tested += min(BOX_T, c.n - B1 * BOX_T);
-                    if (mc) best = B1 * BOX_T + (__ffs(mc) - 1);
-                }
-            }
-        }
-    }
-    return best;
-}
-
-__global__ void __launch_bounds__(128) scan_index_kernel(DevCtx d, int parity)
-{
-    const GlobalState &gs = *d.gs;
-    if (gs.error != 0) return;
-    const int count = gs.reloc_count[parity];
-    long long cells_tested = 0, boxes_tested = 0;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int j = warp; j < count; j += nwarps) {
-        const int best = warp_locate_indexed(d, d.reloc_h0[j], d.reloc_h1[j], d.reloc_h2[j], cells_tested, boxes_tested);
-        if ((threadIdx.x & 31) == 0) d.reloc_best[j] = best;
-    }
-    if ((threadIdx.x & 31) == 0 && (cells_tested | boxes_tested)) {
-        atomicAdd((unsigned long long *)&d.gs->cell_evals, (unsigned long long)cells_tested);
-        atomicAdd((unsigned long long *)&d.gs->box_evals, (unsigned long long)boxes_tested);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// finish: relocated photons get their new cell, comoving 4-momentum and optical depth
-// (Src/mclib.c:536-584); in the fused loop also their free-path draw
-// ------------------------------------------------------------------------------------------
-constexpr int FIN_THREADS = 128;
-
-// one relocated photon: new cell (or -1), comoving 4-momentum, optical depth, free-path draw
-template <bool FUSE_MFP>
-__device__ __forceinline__ bool finish_one(DevCtx &d, ShardState &sh, const int s, const int i, const int b, const int sw)
-{
-    double t = 1e12 / C_LIGHT;
-    bool missing = false;
-    if (b == INT_MAX) {
-        d.ph.idx[i] = -1; // Src/mclib.c:536, 581-584
-        d.ph.safe[i] = 0;
-        missing = true;
-    } else {
-        d.ph.idx[i] = b;
-        d.ph.safe[i] = 0; // the next pass re-checks the new cell and sets the threshold
-        double p[4] = {d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i]};
-        double r0 = d.ph.r0[i], r1 = d.ph.r1[i];
-        CellState c = load_cell_state(d.cells, b);
-        double fb[3], pc[4];
-        fluid_beta_of(d, c, r0, r1, fb);
-        lorentz_boost(fb, p, pc, true);
-        d.ph.c0[i] = pc[0];
-        d.ph.c1[i] = pc[1];
-        d.ph.c2[i] = pc[2];
-        d.ph.c3[i] = pc[3];
-        int terr = 0;
-        double tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, p[1], p[2], p[3], pc[0], &terr);
-        if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
-        store_tau(d.ph, i, tau);
-        d.ph.flags[i] = d.ph.flags[i] & ~F_RECALC;
-        if (sw == 0) atomicAdd((unsigned long long *)&sh.reloc_total, 1ull); // Src/mclib.c:579, 608-611
-        if (FUSE_MFP) {
-            const uint32_t k1 = d.k1 ^ (d.shard_base + (uint32_t)s);
-            double xi = philox_mfp_uniform(d.k0, k1, sh.iter, (uint32_t)(i - sh.first));
-            t = free_path_time(tau, xi);
-        }
-    }
-    if (FUSE_MFP) d.ph.tts[i] = t;
-    return missing;
-}
-
-template <bool FUSE_MFP>
-__global__ void __launch_bounds__(FIN_THREADS) finish_kernel(DevCtx d, int sw, int parity)
-{
-    const GlobalState &gs = *d.gs;
-    if (gs.error != 0) return;
-    const int count = gs.reloc_count[parity];
-    int missing = 0;
-    for (int j = blockIdx.x * FIN_THREADS + threadIdx.x; j < count; j += gridDim.x * FIN_THREADS)
-    {
-        const int i = d.reloc_slot[j], s = shard_of(d, i);
-        if (finish_one<FUSE_MFP>(d, d.sh[s], s, i, d.reloc_best[j], sw)) missing++;
-    }
-    if (missing) atomicAdd(&d.gs->not_found, missing);
-}
-
-// ------------------------------------------------------------------------------------------
-// unfused calcMeanFreePath (step API and replay harness; single shard), Src/mclib.c:617-714
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) mfp_count_kernel(DevCtx d)
-{
-    int i = blockIdx.x * 256 + threadIdx.x;
-    int in = (i < d.cap) && (d.ph.idx[i] != -1);
-    int c = __syncthreads_count(in);
-    if (threadIdx.x == 0) d.prefix_block[blockIdx.x] = c;
-}
-
-__global__ void mfp_scan_kernel(DevCtx d, int nblocks)
-{
-    // single thread: exclusive scan of per-block counts (replay harness only; small lists)
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        unsigned long long run = 0;
-        for (int b = 0; b < nblocks; ++b) {
-            int c = d.prefix_block[b];
-            d.prefix_block[b] = (int)run;
-            run += (unsigned long long)c;
-        }
-        d.gs->replay_base = d.gs->replay_cursor;
-        d.gs->replay_cursor += run;
-        if (d.gs->replay_cursor > d.gs->replay_n) d.gs->error = MCRAT_B200_ERR_REPLAY;
-    }
-}
-
-__global__ void __launch_bounds__(256) mfp_kernel(DevCtx d, int write_blockmin)
-{
-    const GlobalState &gs = *d.gs;
-    const ShardState &sh = d.sh[0];
-    if (gs.error != 0) return;
-    __shared__ int warp_off[8];
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    const bool valid = i < d.cap;
-    const int idx = valid ? d.ph.idx[i] : -1;
-    const bool in = valid && idx != -1;
-    double t = 1e12 / C_LIGHT;
-    // rank of this photon among the in-domain photons of the block (stream order = slot order)
-    unsigned ball = __ballot_sync(0xffffffffu, in);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) warp_off[w] = __popc(ball);
-    __syncthreads();
-    int off = 0;
-    for (int k = 0; k < w; ++k) off += warp_off[k];
-    off += __popc(ball & ((1u << lane) - 1u));
-    if (in) {
-        unsigned char flags = d.ph.flags[i];
-        double tau;
-        if (flags & F_RECALC) {
-            CellState c = load_cell_state(d.cells, idx);
-            int terr = 0;
-            tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, d.ph.r0[i], d.ph.r1[i], d.ph.p1[i], d.ph.p2[i],
-                                d.ph.p3[i], d.ph.c0[i], &terr);
-            if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
-            store_tau(d.ph, i, tau);
-            d.ph.flags[i] = flags & ~F_RECALC;
-        } else {
-            tau = d.ph.tau[i];
-        }
-        double xi;
-        if (d.replay)
-            xi = d.replay_buf[gs.replay_base + (unsigned long long)d.prefix_block[blockIdx.x] + (unsigned long long)off];
-        else
-            xi = philox_mfp_uniform(d.k0, d.k1 ^ d.shard_base, sh.iter, (uint32_t)i);
-        t = free_path_time(tau, xi);
-    }
-    int bi = valid ? i : INT_MAX;
-    double bt = valid ? t : DBL_MAX;
-    if (valid) d.ph.tts[i] = t;
-    block_argmin<256>(bt, bi);
-    if (threadIdx.x == 0 && write_blockmin) {
-        d.bm_t[blockIdx.x] = bt;
-        d.bm_i[blockIdx.x] = bi;
-    }
-}
-
-// head of the time-ordered list for lists with more than BLOCKMIN_CAP*256 slots in the unfused path
-__global__ void __launch_bounds__(256) argmin_all_kernel(DevCtx d)
-{
-    double bt = DBL_MAX;
-    int bi = INT_MAX;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < d.cap; i += gridDim.x * 256) {
-        double t = d.ph.tts[i];
-        if (lex_less(t, i, bt, bi)) {
-            bt = t;
-            bi = i;
-        }
-    }
-    block_argmin<256>(bt, bi);
-    if (threadIdx.x == 0) {
-        d.bm_t[blockIdx.x] = bt;
-        d.bm_i[blockIdx.x] = bi;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// K3: event kernel -- shard-local arg-min, then photonEvent (Src/mclib.c:1107-1356) and the
-// driver's bookkeeping (Src/mcrat.c:777-846).  One block per sub-shard; lane 0 runs the scatter.
-// ------------------------------------------------------------------------------------------
-constexpr int EVT_THREADS = 256;   // one shard / few shards: wide block for the list scans
-constexpr int EVT_THREADS_MANY = 128; // many sub-shards: the three event warps + one, 4 events resident per SM
-
-// Mailbox of the three-warp scattering event (shared memory).
-//   warp 0 = the scattering lane: electron sampling, Klein-Nishina draws, the boosts -- the only
-//            consumer of random numbers and the critical path;
-//   warp 1 = Stokes chain: every rotation angle of stokesRotation (Src/mcrat_scattering.c:103-149)
-//            is a function of momenta only, so they are evaluated here, two to four at a time, one
-//            per lane on the same instruction stream; the Stokes vector itself enters warp 0 only
-//            through (q, u) in the azimuth draw;
-//   warp 2 = helper: everything that depends on velocities alone and would otherwise sit on the
-//            critical path -- the candidate's pushed position and fluid velocity, the Lorentz
-//            matrices of the boosts back (lorentzBoost's matrix depends on beta only), the
-//            alignment rotation and the Fano matrix.
-// Each piece is the reference's statement block, operation for operation: results are
-// bit-identical to the single-lane form (single_scatter in device_math.cuh; the round-1 single-lane event is the
-// reference build of the A/B harness, tools/ab_compare.py).
-struct ScatterMail {
-    double pre[64];         // first 64 uniforms of the event's Philox stream
-    double zhat[3];
-    double fb[3], nfb[3];   // fluid velocity (Src/mclib.c:1151-1174) and its negative
-    double r[3];            // candidate position after this event's pushes
-    double p[4];            // lab 4-momentum of the candidate
-    double pc[4];           // fluid-frame 4-momentum (photon.comv_p*)
-    double pcb[4];          // the same after lorentzBoost had it as input (renormalised in place if beta = 0)
-    double el_v[3], nel_v[3];
-    double php[4];          // electron rest frame, before the scatter (`orig`)
-    double out[4];          // electron rest frame, after
-    double outb[4];         // `out` after lorentzBoost had it as input
-    double pc_new[4];       // fluid frame, after (as the last stokesRotation of singleScatter sees it)
-    double pc_fin[4];       // fluid frame, after the lab boost had it as input
-    double p_new[4];        // lab frame, after
-    double fano[5];
-    double q, u;
-    BoostMat Lf, Le;        // boosts by -fluid_beta and by -el_v
-    ScatterRot rot;
-    ElRot erot;             // rotateElectron's angles (functions of the comoving photon only)
-    int occurred;
-    unsigned char flags;
-};
-
-constexpr int SCATTER_THREADS = 96; // warps 0..2 of the event block
-
-// Early hand-over (persistent loop): once a candidate is accepted by the Klein-Nishina test, everything the
-// other photons' next pass needs -- the pushes of this event, the new clock, the iteration number -- is final,
-// while half of the event (azimuth, outgoing photon, boosts back, Stokes chain) still lies ahead and touches only
-// the scattered photon.  The helper warp therefore does the driver's bookkeeping (Src/mcrat.c:781-846) right there,
-// publishes the shard state and releases the pass blocks; the event block finishes the scatter and runs the
-// scattered photon's next pass itself ("mini-pass").
-struct EarlyRelease {
-    int enabled;        // set by thread 0 before the scatter
-    ShardState *gst;    // global copy of the shard state
-    unsigned gen_value; // value to release on gst->gen
-    int bm_index;       // slot of d.bm_t / d.bm_i that receives the mini-pass result
-    int step_mode;
-    int n_dt, ph_index;
-    double scatt_time;
-    int released;       // out: the state has been published
-};
-
-// the driver's bookkeeping after photonEvent returned (Src/mcrat.c:783-787, 834-846), without the cyclo-synchrotron part
-__device__ __forceinline__ void event_bookkeeping(ShardState &st, int n_dt, int ph_index, double scatt_time, int step_mode)
-{
-    st.n_dt = n_dt;
-    st.last_scattered_idx = ph_index;
-    st.last_time_step = scatt_time;
-    st.iter += 1;
-    st.iters_done += 1;
-    if (step_mode == 0) {
-        st.time_now += scatt_time;
-        st.remaining_time -= scatt_time;
-        if (!(st.remaining_time > 0)) st.done = 1;
-    }
-}
-
-__device__ __forceinline__ void event_count_stopped(GlobalState &gs, ShardState &st)
-{
-    if ((st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters)) && !st.counted_stopped) {
-        st.counted_stopped = 1;
-        atomicAdd(&gs.n_stopped, 1);
-    }
-}
-
-__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v);
-
-__device__ __forceinline__ void trio_bar() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
-__device__ __forceinline__ void duo_bar() { asm volatile("bar.sync 2, 64;" ::: "memory"); } // warps 1 and 2
-// warp 1 hands rotateElectron's angles to warp 0 without waiting for it
-__device__ __forceinline__ void erot_arrive() { asm volatile("bar.arrive 3, 64;" ::: "memory"); }
-__device__ __forceinline__ void erot_wait() { asm volatile("bar.sync 3, 64;" ::: "memory"); }
-
-// up to four Stokes angles at once, one per lane; returns sin/cos(2 phi) of this lane's angle
-__device__ __forceinline__ void lane_angle(const double *k1, const double *a, const double *k2, const double *b, bool active,
-                                           double &sn, double &cs)
-{
-    sn = 0;
-    cs = 1;
-    if (active) {
-        double phi = stokes_angle4(k1, a, k2, b);
-        sincos(2 * phi, &sn, &cs);
-    }
-}
-
-__device__ __forceinline__ void rot_from_lane(double sn, double cs, int src, double *s)
-{
-    double a = __shfl_sync(0xffffffffu, sn, src), c = __shfl_sync(0xffffffffu, cs, src);
-    muller_rotation_sc(a, c, s);
-}
-
-// photonEvent's body for one candidate (Src/mclib.c:1138-1333); threads 0..95 of the block call
-// this together (STOKES_SWITCH ON).
-// cand_idx: the candidate's cell (-2: not known yet); cand_temp: that cell's temperature (< 0: not known yet)
-__device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh, ScatterMail &m, const int i, int cand_idx,
-                                     const double cand_temp, int n_dt, int *event_did_occur, EarlyRelease &early)
-{
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int stokes = d.stokes;
-    // warp-0 lane-0 state carried across stages
-    double theta = 0;
-    KnTheta kn;
-    EventRng rng;
-    double s[4] = {0, 0, 0, 0}; // warp 1, replicated in its lanes
-    double sn = 0, cs = 1;
-    CellState cell; // warp 2 lane 0: the candidate's cell, kept for the mini-pass
-    cell.v0 = cell.v1 = cell.v2 = cell.r0 = cell.r1 = cell.r2 = cell.gamma = cell.dens_lab = cell.temp = 0;
-    int cell_idx = -1;
-#ifdef MCRAT_TIMING
-    const bool tm__ = (w == 0 && lane == 0 && st.first == 0);
-    GlobalState &gsr__ = *d.gs;
-#define T2W(k) if (tm__) TSTAMP(gsr__, k)
-#else
-#define T2W(k)
-#endif
-    TSTAMP_DECL;
-
-    // ---- stage A/B: electron + boost into its rest frame | position, fluid velocity, lab -> fluid rotation ----
-    if (w == 0) {
-        if (!rng_sh.replay) {
-            double a, b;
-            philox_doubles((uint32_t)lane, (uint32_t)rng_sh.iter, (uint32_t)(rng_sh.iter >> 32), 1u, rng_sh.k0, rng_sh.k1, a, b);
-            m.pre[2 * lane] = a;
-            m.pre[2 * lane + 1] = b;
-        }
-        __syncwarp();
-        // Maxwellian branch: the three gaussians at once, one candidate pair per lane
-        double temp = 0;
-        if (lane == 0) temp = (cand_temp >= 0) ? cand_temp : d.cells.temp[cand_idx == -2 ? d.ph.idx[i] : cand_idx];
-        temp = __shfl_sync(0xffffffffu, temp, 0);
-        double g3[3] = {0, 0, 0};
-        int used = 0;
-        if (!rng_sh.replay && temp < 1e7) used = warp_gaussians3(m.pre, 64, rng_sh.draw, sqrt(K_B * temp / M_EL), g3);
-        // Maxwell-Juttner branch: K_2(1/theta) from the per-cell cache, then 64 rejection trials per round
-        double gamma = 1, k2 = 0;
-        uint64_t used_mj = 0;
-        const int MJ_ROUNDS = d.mj_rounds; // x 64 trials, then sequentially (never in practice; MCRAT_B200_MJ_ROUNDS for tests)
-        if (temp >= 1e7) {
-            const double factor = K_B * temp / (M_EL * C_LIGHT * C_LIGHT);
-            if (lane == 0) {
-                const int cell = (cand_idx == -2) ? d.ph.idx[i] : cand_idx;
-                k2 = d.cells.k2[cell];
-                if (!(k2 > 0)) { // not yet evaluated for this cell in this hydro frame (or underflowed: evaluated again)
-                    k2 = bessel_K2(1.0 / factor);
-                    d.cells.k2[cell] = k2;
-                }
-            }
-            k2 = __shfl_sync(0xffffffffu, k2, 0);
-            if (!rng_sh.replay) {
-                used_mj = warp_mj_gamma(rng_sh.k0, rng_sh.k1, rng_sh.iter, rng_sh.draw, factor, k2, MJ_ROUNDS, gamma);
-                if (!used_mj) gamma = 1;
-            }
-        }
-        if (lane == 0) {
-            rng = rng_sh;
-            rng.pre = m.pre;
-            rng.npre = rng_sh.replay ? 0 : 64;
-            T2W(8);
-            if (used) {
-                rng.draw += (uint64_t)used;
-                gamma = maxwellian_gamma(g3);
-            } else if (used_mj) {
-                rng.draw += used_mj;
-            } else {
-                if (temp >= 1e7 && !rng_sh.replay) rng.draw += 128ull * (uint64_t)MJ_ROUNDS; // those trials were all rejected
-                gamma = sample_thermal_electron(temp, rng, k2);
-            }
-        }
-        erot_wait(); // warp 1 has the rotation angles ready long before
-        if (lane == 0) {
-            double pc[4] = {d.ph.c0[i], d.ph.c1[i], d.ph.c2[i], d.ph.c3[i]};
-            double el[4], el_v[3], php[4];
-            thermal_electron_from_gamma(el, gamma, m.erot, rng);
-            T2W(9);
-            scatter_stage_boost(el, pc, el_v, php);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                m.el_v[k] = el_v[k];
-                m.nel_v[k] = (-1 * el_v[k]);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                m.pcb[k] = pc[k];
-                m.php[k] = php[k];
-            }
-        }
-        __syncwarp();
-    } else if (w == 2) {
-        if (lane == 0) {
-            const unsigned char flags = d.ph.flags[i];
-            double p[4] = {d.ph.p0[i], d.ph.p1[i], d.ph.p2[i], d.ph.p3[i]};
-            double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
-            if (flags & F_MOVABLE) apply_pushes(st, n_dt, p[0], p[1], p[2], p[3], r0, r1, r2);
-            cell_idx = (cand_idx == -2) ? d.ph.idx[i] : cand_idx;
-            cell = load_cell_state(d.cells, cell_idx);
-            double fb[3];
-            fluid_beta_of(d, cell, r0, r1, fb);
-            m.zhat[0] = 0; m.zhat[1] = 0; m.zhat[2] = 1;
-            m.r[0] = r0; m.r[1] = r1; m.r[2] = r2;
-            m.flags = flags;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                m.fb[k] = fb[k];
-                m.nfb[k] = -1 * fb[k];
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) m.p[k] = p[k];
-            m.pc[0] = d.ph.c0[i]; m.pc[1] = d.ph.c1[i]; m.pc[2] = d.ph.c2[i]; m.pc[3] = d.ph.c3[i];
-        }
-        __syncwarp();
-        duo_bar();
-        if (lane == 0) {
-            double nfb[3] = {m.nfb[0], m.nfb[1], m.nfb[2]};
-            boost_matrix(nfb, m.Lf);
-        }
-        __syncwarp();
-    } else {
-        if (lane == 0) {
-            double pc[4] = {d.ph.c0[i], d.ph.c1[i], d.ph.c2[i], d.ph.c3[i]};
-            ElRot er;
-            electron_rot_angles(pc, er);
-            m.erot = er;
-        }
-        __syncwarp();
-        erot_arrive();
-        if (stokes) { s[0] = d.ph.s0[i]; s[1] = d.ph.s1[i]; s[2] = d.ph.s2[i]; s[3] = d.ph.s3[i]; }
-        duo_bar();
-        if (stokes) {
-            // stokesRotation(fluid_beta, p, comv_p), Src/mclib.c:1190-1196
-            lane_angle(lane == 0 ? m.p + 1 : m.pc + 1, lane == 0 ? m.zhat : m.fb, lane == 0 ? m.p + 1 : m.pc + 1,
-                       lane == 0 ? m.fb : m.zhat, lane < 2, sn, cs);
-            rot_from_lane(sn, cs, 0, s);
-            rot_from_lane(sn, cs, 1, s);
-        }
-    }
-    T2W(10);
-    trio_bar();
-    T2W(11);
-    // ---- stage C: Klein-Nishina accept / polar angle | fluid -> electron-frame rotation | alignment, boost matrix ----
-    if (w == 0) {
-        if (lane == 0) m.occurred = kn_accept_theta(theta, m.php[0], kn, rng);
-        __syncwarp();
-    } else if (w == 1) {
-        if (stokes) {
-            // stokesRotation(el_v, ph_comov, ph_p_prime), Src/mcrat_scattering.c:245-253
-            lane_angle(lane == 0 ? m.pcb + 1 : m.php + 1, lane == 0 ? m.zhat : m.el_v, lane == 0 ? m.pcb + 1 : m.php + 1,
-                       lane == 0 ? m.el_v : m.zhat, lane < 2, sn, cs);
-            rot_from_lane(sn, cs, 0, s);
-            rot_from_lane(sn, cs, 1, s);
-        }
-        if (lane == 0) {
-            m.q = s[1];
-            m.u = s[2];
-        }
-    } else {
-        if (lane == 0) {
-            double php[4] = {m.php[0], m.php[1], m.php[2], m.php[3]};
-            ScatterRot rot;
-            scatter_stage_align(php, rot);
-            m.rot = rot;
-            double nel_v[3] = {m.nel_v[0], m.nel_v[1], m.nel_v[2]};
-            boost_matrix(nel_v, m.Le);
-        }
-        __syncwarp();
-    }
-    T2W(12);
-    trio_bar();
-    T2W(13);
-    if (!m.occurred) { // Klein-Nishina rejection: the draws are spent, nothing else changes
-        if (w == 0 && lane == 0) {
-            rng.pre = nullptr;
-            rng.npre = 0;
-            rng_sh = rng;
-        }
-        return;
-    }
-    // ---- stage D: azimuth + outgoing photon | -- | bookkeeping and early release of the pass blocks ----
-    if (w == 0) {
-        if (lane == 0) {
-            double phi = kn_phi(stokes, kn, m.q, m.u, rng);
-            double out[4];
-            ScatterRot rot = m.rot;
-            scatter_stage_out(m.php[0], kn.st, kn.ct, phi, rot, out);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) m.out[k] = out[k];
-        }
-        __syncwarp();
-    } else if (w == 2 && early.enabled) {
-        if (lane == 0) {
-            st.pushed_slot = i; // the accepted candidate is at its pushed position already (Src/mclib.c:1138)
-            st.scatt_cnt += 1;
-            event_bookkeeping(st, early.n_dt, early.ph_index, early.scatt_time, early.step_mode);
-            event_count_stopped(*d.gs, st);
-            st.halt = (loop_stopped(*d.gs, st) || st.reloc_heavy) ? 1 : 0;
-            st.mini_slot = st.halt ? -1 : i; // a halted shard leaves the photon as photonEvent left it
-        }
-        __syncwarp();
-        for (int k = lane; k < SHARD_STATE_WORDS; k += 32)
-            reinterpret_cast<unsigned long long *>(early.gst)[k] = reinterpret_cast<const unsigned long long *>(&st)[k];
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence();
-            st_release_u32(&early.gst->gen, early.gen_value);
-            early.released = 1;
-        }
-        __syncwarp();
-    }
-    T2W(14);
-    trio_bar();
-    T2W(15);
-    // ---- stage E: boosts back to the fluid and lab frames | scattering-plane angles | Fano matrix ----
-    if (w == 0) {
-        if (lane == 0) {
-            double out[4] = {m.out[0], m.out[1], m.out[2], m.out[3]};
-            double pcn[4], pn[4];
-            boost_apply(m.Le, out, pcn, true); // Src/mcrat_scattering.c:455-463
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                m.outb[k] = out[k];
-                m.pc_new[k] = pcn[k];
-            }
-            boost_apply(m.Lf, pcn, pn, true); // Src/mclib.c:1262-1265
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                m.pc_fin[k] = pcn[k];
-                m.p_new[k] = pn[k];
-            }
-        }
-        __syncwarp();
-    } else if (w == 1) {
-        // lane 0: into the scattering plane (Src/mcrat_scattering.c:402-405); lane 1: back out of it (:438-447)
-        if (stokes)
-            lane_angle(lane == 0 ? m.php + 1 : m.out + 1, lane == 0 ? m.zhat : m.php + 1, m.out + 1,
-                       lane == 0 ? m.php + 1 : m.zhat, lane < 2, sn, cs);
-    } else {
-        if (lane == 0 && stokes) {
-            double f[5];
-            scatter_stage_fano(m.php, m.out, f);
-#pragma unroll
-            for (int k = 0; k < 5; ++k) m.fano[k] = f[k];
-        }
-        __syncwarp();
-    }
-    T2W(16);
-    trio_bar();
-    T2W(17);
-    // ---- stage F: the remaining angles, the Stokes chain applied in order, write-back ----
-    if (w == 1 && !stokes) {
-        // unpolarised run (STOKES_SWITCH OFF): no Stokes chain; warp 1 only supplied rotateElectron's angles
-    } else if (w == 1) {
-        // lane 0 / 1: stokesRotation(-el_v, out, pc_new), Src/mcrat_scattering.c:465-473 (`out` as lorentzBoost
-        // left it); lane 2 / 3: stokesRotation(-fluid_beta, pc_fin, p_new), Src/mclib.c:1267-1287
-        double sn2, cs2;
-        const double *k = lane == 0 ? m.outb + 1 : (lane == 1 ? m.pc_new + 1 : (lane == 2 ? m.pc_fin + 1 : m.p_new + 1));
-        const double *a = lane == 0 ? m.zhat : (lane == 1 ? m.nel_v : (lane == 2 ? m.zhat : m.nfb));
-        const double *b = lane == 0 ? m.nel_v : (lane == 1 ? m.zhat : (lane == 2 ? m.nfb : m.zhat));
-        lane_angle(k, a, k, b, lane < 4, sn2, cs2);
-        rot_from_lane(sn, cs, 0, s);
-        {
-            double f[5] = {m.fano[0], m.fano[1], m.fano[2], m.fano[3], m.fano[4]};
-            fano_apply(f, s);
-        }
-        rot_from_lane(sn, cs, 1, s);
-        rot_from_lane(sn2, cs2, 0, s);
-        rot_from_lane(sn2, cs2, 1, s);
-        rot_from_lane(sn2, cs2, 2, s);
-        rot_from_lane(sn2, cs2, 3, s);
-        if (lane == 0) {
-            d.ph.s0[i] = s[0];
-            d.ph.s1[i] = s[1];
-            d.ph.s2[i] = s[2];
-            d.ph.s3[i] = s[3];
-        }
-    } else if (w == 0 && lane == 0) {
-        store_momentum(d.ph, i, m.p_new[0], m.p_new[1], m.p_new[2], m.p_new[3]);
-        d.ph.c0[i] = m.pc_fin[0]; d.ph.c1[i] = m.pc_fin[1]; d.ph.c2[i] = m.pc_fin[2]; d.ph.c3[i] = m.pc_fin[3];
-        d.ph.nscatt[i] = d.ph.nscatt[i] + 1;
-        d.ph.flags[i] = m.flags | F_RECALC;
-        // this photon is already at its pushed position: the next pass must not push it again
-        d.ph.r0[i] = m.r[0];
-        d.ph.r1[i] = m.r[1];
-        d.ph.r2[i] = m.r[2];
-        d.ph.safe[i] = 0;
-        if (!early.released) {
-            st.pushed_slot = i;
-            st.scatt_cnt += 1;
-        }
-        *event_did_occur = 1;
-        rng.pre = nullptr;
-        rng.npre = 0;
-        rng_sh = rng;
-        T2W(18);
-    }
-    // ---- mini-pass: the scattered photon's share of the next pass (pass_body for one photon), by the helper warp ----
-    if (early.released && st.mini_slot == i) {
-        double t_next = 1e12 / C_LIGHT, tau_next = 0, h0 = 0, h1 = 0, h2 = 0;
-        int state = 0; // 0: out of the domain, 1: still in its cell (t_next, tau_next valid), 2: left its cell
-        if (w == 2 && lane == 0) {
-            const int ndim3 = (d.dims == D_THREE);
-            coord_to_hydro(d.dims, d.geom, m.r[0], m.r[1], m.r[2], h0, h1, h2);
-            bool in_domain;
-            if (!ndim3)
-                in_domain = ((h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) && (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0]));
-            else
-                in_domain = ((h2 < d.cells.dom[5]) && (h2 > d.cells.dom[4]) && (h1 < d.cells.dom[3]) && (h1 > d.cells.dom[2]) &&
-                             (h0 < d.cells.dom[1]) && (h0 > d.cells.dom[0]));
-            if (in_domain) {
-                if (in_cell(ndim3, d.cells, cell_idx, h0, h1, h2)) {
-                    int terr = 0;
-                    tau_next = optical_depth(d.dims, d.geom, d.tau_calc, d.table, cell, m.r[0], m.r[1], m.p_new[1], m.p_new[2],
-                                             m.p_new[3], m.pc_fin[0], &terr);
-                    if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
-                    const uint32_t k1 = d.k1 ^ (d.shard_base + (uint32_t)(early.gst - d.sh));
-                    const double xi = philox_mfp_uniform(d.k0, k1, st.iter, (uint32_t)(i - st.first));
-                    t_next = free_path_time(tau_next, xi);
-                    state = 1;
-                } else {
-                    state = 2;
-                }
-            }
-        }
-        trio_bar(); // warp 0 has written the photon's new columns
-        if (w == 2 && lane == 0) {
-            double bt = DBL_MAX;
-            int bi = INT_MAX;
-            if (state == 1) {
-                store_tau(d.ph, i, tau_next);
-                d.ph.flags[i] = m.flags & ~F_RECALC;
-                d.ph.tts[i] = t_next;
-                bt = t_next;
-                bi = i;
-            } else if (state == 2) {
-                const int pos = st.first + atomicAdd(&early.gst->reloc_n, 1);
-                d.reloc_slot[pos] = i;
-                d.reloc_h0[pos] = h0;
-                d.reloc_h1[pos] = h1;
-                d.reloc_h2[pos] = h2;
-                d.reloc_best[pos] = INT_MAX;
-            } else {
-                d.ph.idx[i] = -1; // Src/mclib.c:589-595 (safe[i] is 0 since the write-back)
-                d.ph.tts[i] = t_next;
-                bt = t_next;
-                bi = i;
-            }
-            d.bm_t[early.bm_index] = bt;
-            d.bm_i[early.bm_index] = bi;
-            d.bm_idx[early.bm_index] = (state == 1) ? cell_idx : -1;
-            d.bm_temp[early.bm_index] = cell.temp;
-        }
-    }
-}
-
-// getMagneticFieldMagnitude, Src/mc_cyclosynch.c:78-92
-__device__ __forceinline__ double cell_b_field(const DevCtx &d, int idx)
-{
-    if (d.b_calc == B_TOTAL_E || d.b_calc == B_INTERNAL_E) {
-        double el_dens = d.cells.dens[idx] / M_P;
-        return calc_b(d.b_calc, d.epsilon_b, el_dens, d.cells.temp[idx]);
-    }
-    if (d.dims == D_TWO) {
-        double b0 = d.cells.B0[idx], b1 = d.cells.B1[idx];
-        return sqrt(b0 * b0 + b1 * b1);
-    }
-    double b0 = d.cells.B0[idx], b1 = d.cells.B1[idx], b2 = d.cells.B2[idx];
-    return sqrt(b0 * b0 + b1 * b1 + b2 * b2);
-}
-
-// photonEmitCyclosynch with inject_single_switch == 1 (Src/mc_cyclosynch.c:1465-1555): a pool
-// photon that scattered is replaced by a fresh one at the cyclotron frequency of its cell, placed
-// into the first null slot of the list (addToPhotonList, Src/photons.c:132-160), and the scattered
-// photon is re-positioned at random inside the cell (:1541-1553).
-__device__ void cs_emit_single(DevCtx &d, EventRng &rng, int scatt, int slot)
-{
-    const int i = d.ph.idx[scatt];
-    const int ndim3 = (d.dims == D_THREE);
-    const double nu_c = calc_cyclotron_freq(cell_b_field(d, i));
-    const double fr_dum = nu_c;
-    double position_phi = 0;
-    if (!ndim3) position_phi = rng.uniform() * 2 * PI;
-    const double com_v_phi = rng.uniform() * 2 * PI;
-    const double com_v_theta = rng.uniform() * PI;
-    double p_comv[4], boost[3], l_boost[4], pos[3];
-    p_comv[0] = PL_CONST * fr_dum / C_LIGHT;
-    p_comv[1] = (PL_CONST * fr_dum / C_LIGHT) * sin(com_v_theta) * cos(com_v_phi);
-    p_comv[2] = (PL_CONST * fr_dum / C_LIGHT) * sin(com_v_theta) * sin(com_v_phi);
-    p_comv[3] = (PL_CONST * fr_dum / C_LIGHT) * cos(com_v_theta);
-    const double cr0 = d.cells.r0[i], cr1 = d.cells.r1[i], cr2 = d.cells.r2[i];
-    if (ndim3)
-        hydro_vector_to_cartesian(d.dims, d.geom, boost, d.cells.v0[i], d.cells.v1[i], d.cells.v2[i], cr0, cr1, cr2);
-    else if (d.dims == D_TWO_POINT_FIVE)
-        hydro_vector_to_cartesian(d.dims, d.geom, boost, d.cells.v0[i], d.cells.v1[i], d.cells.v2[i], cr0, cr1, position_phi);
-    else
-        hydro_vector_to_cartesian(d.dims, d.geom, boost, d.cells.v0[i], d.cells.v1[i], 0, cr0, cr1, position_phi);
-    boost[0] *= -1;
-    boost[1] *= -1;
-    boost[2] *= -1;
-    lorentz_boost(boost, p_comv, l_boost, true);
-    if (ndim3)
-        hydro_coord_to_mcrat(d.dims, d.geom, pos, cr0, cr1, cr2);
-    else
-        hydro_coord_to_mcrat(d.dims, d.geom, pos, cr0, cr1, position_phi);
-    store_momentum(d.ph, slot, l_boost[0], l_boost[1], l_boost[2], l_boost[3]);
-    d.ph.c0[slot] = p_comv[0]; d.ph.c1[slot] = p_comv[1]; d.ph.c2[slot] = p_comv[2]; d.ph.c3[slot] = p_comv[3];
-    d.ph.r0[slot] = pos[0]; d.ph.r1[slot] = pos[1]; d.ph.r2[slot] = pos[2];
-    d.ph.safe[slot] = 0;
-    d.ph.s0[slot] = 1; d.ph.s1[slot] = 0; d.ph.s2[slot] = 0; d.ph.s3[slot] = 0;
-    d.ph.nscatt[slot] = 0;
-    d.ph.weight[slot] = d.ph.weight[scatt];
-    d.ph.idx[slot] = i;
-    d.ph.type[slot] = 'p';
-    d.ph.flags[slot] = F_RECALC; // pool photons do not move (Src/mclib.c:1070)
-    d.ph.tts[slot] = 0;
-    store_tau(d.ph, slot, 0);
-    // new random position of the scattered photon inside its cell
-    const double4 a = d.cells.geoA[i];
-    double size0, size1, size2 = 0;
-    if (!ndim3) {
-        size0 = 2 * a.z;
-        size1 = 2 * a.w;
-    } else {
-        const double2 b = d.cells.geoB[i];
-        size0 = 2 * a.w;
-        size1 = 2 * b.x;
-        size2 = 2 * b.y;
-    }
-    const double pr = rng.uniform_pos() * (size0) - (size0) / 2.0;
-    const double pr2 = rng.uniform_pos() * (size1) - (size1) / 2.0;
-    if (ndim3) {
-        const double pr3 = rng.uniform_pos() * (size2) - (size2) / 2.0;
-        hydro_coord_to_mcrat(d.dims, d.geom, pos, cr0 + pr, cr1 + pr2, cr2 + pr3);
-    } else {
-        hydro_coord_to_mcrat(d.dims, d.geom, pos, cr0 + pr, cr1 + pr2, position_phi);
-    }
-    d.ph.safe[scatt] = 0;
-    d.ph.r0[scatt] = pos[0];
-    d.ph.r1[scatt] = pos[1];
-    d.ph.r2[scatt] = pos[2];
-}
-
-// step_mode 0: frame loop (driver bookkeeping included); 1: photonEvent only (dt_max given)
-// blockmin_valid: the pass wrote per-block minima for this iteration (fused path / step API)
-// `early_gst` != nullptr (persistent loop): publish the state to *early_gst and release `early_gen` on its generation
-// word as soon as a candidate is accepted; d.bm_*[early_bm] receives the scattered photon's mini-pass.  Returns
-// whether that happened (else the caller publishes after the event).
-template <int EVT_THREADS>
-__device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int reloc_base, const int R, int nb_per_shard,
-                                           int step_mode, double dt_max_arg, ShardState &st, ShardState *early_gst = nullptr,
-                                           unsigned early_gen = 0, int early_bm = 0, const bool have_pre = false,
-                                           const double pre_t = DBL_MAX, const int pre_i = INT_MAX, const int pre_idx = -2,
-                                           const double pre_temp = 0)
-{
-    GlobalState &gs = *d.gs;
-    __shared__ EarlyRelease early;
-
-    __shared__ double sh_cand_t;
-    __shared__ double sh_cand_temp;
-    __shared__ int sh_cand_i, sh_cand_idx, sh_cand_known, sh_finished; // sh_cand_known: idx and temperature are in shared memory
-    // ---- head of this shard's time order ----
-    double bt = DBL_MAX;
-    int bi = INT_MAX;
-    if (nb_per_shard > 0) {
-        if (have_pre) { // the caller requested this thread's entry of the block minima together with other loads
-            bt = pre_t;
-            bi = pre_i;
-        } else {
-            for (int k = threadIdx.x; k < nb_per_shard; k += EVT_THREADS) {
-                const int q = s * nb_per_shard + k;
-                if (lex_less(d.bm_t[q], d.bm_i[q], bt, bi)) {
-                    bt = d.bm_t[q];
-                    bi = d.bm_i[q];
-                }
-            }
-        }
-        // photons relocated in this iteration got their time in finish
-        if (R > 0 && R <= RELOC_LIST_SCAN_MAX) {
-            for (int j = threadIdx.x; j < R; j += EVT_THREADS) {
-                const int i = d.reloc_slot[reloc_base + j];
-                if (i >= st.first && i < st.first + st.count) {
-                    double t = d.ph.tts[i];
-                    if (lex_less(t, i, bt, bi)) {
-                        bt = t;
-                        bi = i;
-                    }
-                }
-            }
-        } else if (R > 0) {
-            for (int j = threadIdx.x; j < st.count; j += EVT_THREADS) {
-                const int i = st.first + j;
-                double t = d.ph.tts[i];
-                if (lex_less(t, i, bt, bi)) {
-                    bt = t;
-                    bi = i;
-                }
-            }
-        }
-    } else {
-        for (int j = threadIdx.x; j < st.count; j += EVT_THREADS) {
-            const int i = st.first + j;
-            double t = d.ph.tts[i];
-            if (lex_less(t, i, bt, bi)) {
-                bt = t;
-                bi = i;
-            }
-        }
-    }
-    block_argmin<EVT_THREADS>(bt, bi);
-
-    __shared__ EventRng rng_sh;
-    __shared__ ScatterMail mail;
-    __shared__ double old_scatt_time, scatt_time, dt_max;
-    __shared__ int n_dt, ph_index, sh_try, sh_event;
-    if (threadIdx.x == 0) {
-        // the candidate's cell index: delivered with the block minima (team kernel), else requested first so that
-        // the loads of the set-up below travel with it
-        sh_cand_known = 0;
-        sh_cand_idx = have_pre ? -2 : ((bi != INT_MAX) ? d.ph.idx[bi] : -1);
-        sh_cand_t = bt;
-        sh_cand_i = bi;
-        sh_finished = 0;
-        st.head_idx = bi;
-        st.head_tts = bt;
-        dt_max = (step_mode == 0) ? st.remaining_time : dt_max_arg;
-        old_scatt_time = 0;
-        scatt_time = 0;
-        n_dt = 0;
-        ph_index = bi;
-        fold_path(st, d.path_pad); // the pushes of the last event have been applied by the pass that led here
-        st.n_dt = 0;
-        st.pushed_slot = -1;
-        early.enabled = 0;
-        early.released = 0;
-        early.gst = early_gst;
-        early.gen_value = early_gen;
-        early.bm_index = early_bm;
-        early.step_mode = step_mode;
-        rng_sh.replay = d.replay;
-        rng_sh.k0 = d.k0;
-        rng_sh.k1 = d.k1 ^ (d.shard_base + (uint32_t)s);
-        rng_sh.iter = st.iter;
-        rng_sh.draw = 0;
-        rng_sh.buf = d.replay_buf;
-        rng_sh.pos = d.replay ? gs.replay_cursor : 0; // global loads only the parity harness needs
-        rng_sh.n = d.replay ? gs.replay_n : 0;
-        rng_sh.exhausted = 0;
-        rng_sh.pre = nullptr;
-        rng_sh.npre = 0;
-        if (step_mode == 0) st.slots += st.count;
-        if (step_mode == 0 && !(bt < dt_max)) {
-            // Src/mcrat.c:834-846: nothing scatters before the next hydro frame
-            st.time_now += st.remaining_time;
-            st.dt_list[0] = st.remaining_time;
-            st.n_dt = 1;
-            st.last_time_step = st.remaining_time;
-            st.remaining_time = 0;
-            st.done = 1;
-            st.iter += 1;
-            st.iters_done += 1;
-            if (!st.counted_stopped) {
-                st.counted_stopped = 1;
-                atomicAdd(&gs.n_stopped, 1);
-            }
-            sh_finished = 1;
-        }
-    }
-    __syncthreads();
-    if (sh_finished) return false;
-    if (have_pre && pre_i == sh_cand_i && pre_idx >= 0) { // the thread whose entry won hands over what came with it
-        sh_cand_idx = pre_idx;
-        sh_cand_temp = pre_temp;
-        sh_cand_known = 1;
-    }
-
-    // ---- photonEvent: walk candidates in ascending time, Src/mclib.c:1128-1339 ----
-    while (true) {
-        if (threadIdx.x == 0) {
-            const int i = sh_cand_i;
-            const double t = sh_cand_t;
-            bool event = false, attempt = false;
-            ph_index = i;
-            scatt_time = t;
-            if (t < dt_max) {
-                if (n_dt < MAX_DT) {
-                    st.dt_list[n_dt] = t - old_scatt_time;
-                    n_dt++;
-                    attempt = true;
-                } else {
-                    gs.error = MCRAT_B200_ERR_STATE;
-                    event = true;
-                }
-            } else {
-                scatt_time = dt_max;
-                st.dt_list[n_dt < MAX_DT ? n_dt : MAX_DT - 1] = scatt_time - old_scatt_time;
-                n_dt = min(n_dt + 1, MAX_DT);
-                event = true;
-            }
-            old_scatt_time = scatt_time;
-            sh_try = attempt ? 1 : 0;
-            sh_event = event ? 1 : 0;
-            // if this candidate is accepted, these are the event's final numbers
-            early.enabled = (early_gst != nullptr && attempt && !d.cs && step_mode == 0 && !d.replay) ? 1 : 0;
-            early.n_dt = n_dt;
-            early.ph_index = i;
-            early.scatt_time = scatt_time;
-        }
-        __syncthreads();
-        if (sh_try) {
-            // three warps: scattering lane | Stokes chain (idle when STOKES_SWITCH is OFF) | helper
-            if (threadIdx.x < SCATTER_THREADS)
-                scatter_candidate_3w(d, st, rng_sh, mail, sh_cand_i, sh_cand_idx, sh_cand_known ? sh_cand_temp : -1.0, n_dt,
-                                     &sh_event, early);
-            __syncthreads();
-        }
-        if (sh_event) break;
-        // Klein-Nishina rejection (rare): next entry of this shard's time order after (cand_t, cand_i)
-        {
-            const double pt = sh_cand_t;
-            const int pi = sh_cand_i;
-            double nt = DBL_MAX;
-            int ni = INT_MAX;
-            // streamed loop: the pass blocks' minima are still there.  A block whose minimum comes after (pt, pi) offers
-            // exactly that minimum; a block whose minimum has been consumed (at most one per rejection) is read again;
-            // photons re-located in this iteration are not in any minimum and come from the re-location list.  Same
-            // result as reading every time of the shard, without the 80 MB read by one block at 10^7 photons.
-            const bool two_level = (early_gst == nullptr) && !have_pre && step_mode == 0 && !d.replay && nb_per_shard > 1 &&
-                                   R <= RELOC_LIST_SCAN_MAX;
-            if (two_level) {
-                for (int k = threadIdx.x; k < nb_per_shard; k += EVT_THREADS) {
-                    const int q = s * nb_per_shard + k;
-                    const double t = d.bm_t[q];
-                    const int ti = d.bm_i[q];
-                    if (lex_less(pt, pi, t, ti) && lex_less(t, ti, nt, ni)) {
-                        nt = t;
-                        ni = ti;
-                    }
-                }
-                for (int k = 0; k < nb_per_shard; ++k) { // uniform over the block
-                    const int q = s * nb_per_shard + k;
-                    if (lex_less(pt, pi, d.bm_t[q], d.bm_i[q])) continue;
-                    // pass block k's photons: j = k * PASS_THREADS + u + m * nb_per_shard * PASS_THREADS (pass_body)
-                    for (int base = k * PASS_THREADS; base < st.count; base += nb_per_shard * PASS_THREADS)
-                        for (int u = threadIdx.x; u < PASS_THREADS; u += EVT_THREADS) {
-                            const int j = base + u;
-                            if (j >= st.count) break;
-                            const int kk = st.first + j;
-                            const double t = d.ph.tts[kk];
-                            if (lex_less(pt, pi, t, kk) && lex_less(t, kk, nt, ni)) {
-                                nt = t;
-                                ni = kk;
-                            }
-                        }
-                }
-                for (int j = threadIdx.x; j < R; j += EVT_THREADS) {
-                    const int kk = d.reloc_slot[reloc_base + j];
-                    if (kk >= st.first && kk < st.first + st.count) {
-                        const double t = d.ph.tts[kk];
-                        if (lex_less(pt, pi, t, kk) && lex_less(t, kk, nt, ni)) {
-                            nt = t;
-                            ni = kk;
-                        }
-                    }
-                }
-            } else {
-                for (int j = threadIdx.x; j < st.count; j += EVT_THREADS) {
-                    const int k = st.first + j;
-                    double t = d.ph.tts[k];
-                    if (lex_less(pt, pi, t, k) && lex_less(t, k, nt, ni)) {
-                        nt = t;
-                        ni = k;
-                    }
-                }
-            }
-            block_argmin<EVT_THREADS>(nt, ni);
-            if (threadIdx.x == 0) {
-                if (ni == INT_MAX) { // list exhausted (Src/mclib.c:1128 loop bound)
-                    sh_finished = 1;
-                } else {
-                    sh_cand_t = nt;
-                    sh_cand_i = ni;
-                    sh_cand_idx = d.ph.idx[ni];
-                    sh_cand_known = 0;
-                }
-            }
-            __syncthreads();
-            if (sh_finished) break;
-        }
-    }
-
-    // ---- cyclo-synchrotron pool replacement, Src/mcrat.c:791-808 (the list is one shard here) ----
-    __shared__ int cs_need, cs_slot;
-    if (d.cs) {
-        if (threadIdx.x == 0) cs_need = (step_mode == 0 && d.ph.type[ph_index] == 'p') ? 1 : 0;
-        __syncthreads();
-    } else if (threadIdx.x == 0) {
-        cs_need = 0;
-    }
-    if (d.cs && cs_need) {
-        // first null slot of the list (Src/photons.c:143-150)
-        int first_null = INT_MAX;
-        for (int j = threadIdx.x; j < st.count; j += EVT_THREADS)
-            if (d.ph.type[st.first + j] == 'N') {
-                first_null = st.first + j;
-                break;
-            }
-        double dummy = 0;
-        block_argmin<EVT_THREADS>(dummy, first_null);
-        if (threadIdx.x == 0) cs_slot = first_null;
-        __syncthreads();
-    }
-
-    if (threadIdx.x == 0 && !early.released) {
-        event_bookkeeping(st, n_dt, ph_index, scatt_time, step_mode);
-        if (step_mode == 0) {
-            if (cs_need) {
-                gs.cs_comptonized_w += d.ph.weight[ph_index];
-                d.ph.type[ph_index] = 'k'; // COMPTONIZED_PHOTON
-                if (d.ph.weight[ph_index] != 0) d.ph.flags[ph_index] |= F_MOVABLE;
-                if (cs_slot == INT_MAX) {
-                    // no null slot: the host must grow the list and emit (Src/photons.c:117-129)
-                    st.pause_cs = 1;
-                } else {
-                    EventRng rng = rng_sh;
-                    cs_emit_single(d, rng, ph_index, cs_slot);
-                    rng_sh = rng;
-                    gs.cs_emitted += 1;
-                    gs.cs_scatt_num += 1;
-                }
-            }
-            // Src/mcrat.c:810-831: every 1000 scatterings the driver may have to rebin on the host
-            if (d.cs && !st.pause_cs && (st.scatt_cnt % 1000 == 0) && (st.scatt_cnt != 0) && gs.cs_scatt_num > gs.cs_max_photons)
-                st.pause_cs = 2;
-            event_count_stopped(gs, st);
-        }
-        if (d.replay) {
-            gs.replay_cursor = rng_sh.pos;
-            if (rng_sh.exhausted) gs.error = MCRAT_B200_ERR_REPLAY;
-        }
-    }
-    __syncthreads();
-    return early.released != 0;
-}
-
-template <int EVT_THREADS>
-__global__ void __launch_bounds__(EVT_THREADS) event_kernel(DevCtx d, int parity, int nb_per_shard, int step_mode,
-                                                            double dt_max_arg)
-{
-    const int s = blockIdx.x;
-    if (loop_stopped(*d.gs, d.sh[s])) return;
-    event_body<EVT_THREADS>(d, s, 0, d.gs->reloc_count[parity], nb_per_shard, step_mode, dt_max_arg, d.sh[s]);
-}
-
-// ------------------------------------------------------------------------------------------
-// Persistent frame loop: the whole while-loop of Src/mcrat.c:761-851 in ONE launch.
-//
-// The streamed loop above costs four dependent kernel launches per scattering; for lists that fit
-// in L2 the launch boundaries, not the work, set the iteration time.  Here every sub-shard (one
-// reference "rank") is owned by `bps` resident blocks that iterate on their own:
-//   pass (push + re-check + free-path draw + block arg-min)  ->  arrive
-//   last arriver: re-locate the few photons that left their cell (one warp per photon through the
-//                 bounding-box index), shard arg-min, scattering event, publish the new clock /
-//                 push list                                  ->  release
-//   the other blocks spin on the shard's generation word (ld.acquire.gpu) and start the next pass.
-// Shards never wait for each other (exactly like MPI ranks), so a rank that finishes its frame or
-// rejects a Klein-Nishina candidate does not hold the others up.  All blocks are co-resident
-// (cooperative launch); with one block per shard a block walks through its shards one after the other.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
-{
-    unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
-{
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-constexpr int RELOC_HEAVY = 64; // re-locations per shard and iteration above which the grid-wide K1b / K1c serve better
-
-// relocated photons of this iteration: new cell, comoving momentum, tau', free-path draw
-template <int THREADS>
-__device__ __forceinline__ void finish_reloc(DevCtx &d, ShardState &st, const int s, const int R)
-{
-    int missing = 0;
-    for (int j = threadIdx.x; j < R; j += THREADS)
-        if (finish_one<true>(d, st, s, d.reloc_slot[st.first + j], d.reloc_best[st.first + j], 0)) missing++;
-    if (missing) atomicAdd(&d.gs->not_found, missing);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        d.sh[s].reloc_n = 0;
-        if (R > RELOC_HEAVY) st.reloc_heavy = 1;
-    }
-}
-
-// the shard's relocation entries [first, first+R): one warp per photon through the bounding-box index
-template <int THREADS>
-__device__ __forceinline__ void relocate_shard(DevCtx &d, ShardState &st, const int s, const int R)
-{
-    long long cells_tested = 0, boxes_tested = 0;
-    for (int j = threadIdx.x >> 5; j < R; j += THREADS / 32) {
-        const int q = st.first + j;
-        const int best = warp_locate_indexed(d, d.reloc_h0[q], d.reloc_h1[q], d.reloc_h2[q], cells_tested, boxes_tested);
-        if ((threadIdx.x & 31) == 0) d.reloc_best[q] = best;
-    }
-    if ((threadIdx.x & 31) == 0 && (cells_tested | boxes_tested)) {
-        atomicAdd((unsigned long long *)&d.gs->cell_evals, (unsigned long long)cells_tested);
-        atomicAdd((unsigned long long *)&d.gs->box_evals, (unsigned long long)boxes_tested);
-    }
-    __syncthreads();
-    finish_reloc<THREADS>(d, st, s, R);
-    __syncthreads();
-}
-
-// A sub-shard is run by a team of `bps` pass blocks and one event block, all resident:
-//   pass block b:  pass over its slice -> ticket on gst.arrive -> spin on gst.gen -> pull the state -> next pass
-//   event block:   spin until all bps tickets of the iteration are drawn -> re-locate -> shard arg-min -> event;
-//                  the state is published (gst.gen released) the moment a candidate is accepted, so the pass blocks
-//                  run the next pass while the event block is still busy with the second half of the scatter; the
-//                  scattered photon's own next pass is done by the event block (mini-pass, slot `bps` of the minima).
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_kernel(DevCtx d, const int bps)
-{
-    __shared__ ShardState st; // this block's copy of the shard's state
-    __shared__ int sh_flag;
-    GlobalState &gs = *d.gs;
-    const int team = bps + 1;
-    const int groups = gridDim.x / team;
-    const int g = blockIdx.x / team, role = blockIdx.x - g * team;
-    if (g >= groups) return;
-    const bool is_event_block = (role == bps);
-
-    for (int s = g; s < d.nshards; s += groups) {
-        ShardState &gst = d.sh[s];
-        // global -> shared (the copied part only; the protocol words live in global memory)
-        auto pull = [&]() {
-            if (threadIdx.x < SHARD_STATE_WORDS)
-                reinterpret_cast<unsigned long long *>(&st)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&gst)[threadIdx.x];
-            __syncthreads();
-        };
-        // thread 0 spins until *word >= target (relaxed polls, one acquire at the end); false after ~1 s
-        auto spin_until = [&](const unsigned *word, unsigned target) -> bool {
-            if (threadIdx.x == 0) {
-                unsigned spins = 0;
-                int ok = 1;
-                if (ld_acquire_u32(word) < target) { // fast path: already there, one round trip
-                    while (ld_relaxed_u32(word) < target) {
-                        __nanosleep(40);
-                        if (++spins > (1u << 24)) { // never in a healthy run; refuse to hang the GPU
-                            gs.error = MCRAT_B200_ERR_STATE;
-                            ok = 0;
-                            break;
-                        }
-                    }
-                    (void)ld_acquire_u32(word);
-                }
-                sh_flag = ok;
-            }
-            __syncthreads();
-            return sh_flag != 0;
-        };
-        __syncthreads();
-        pull();
-        // stop test at entry: shard state only, so that all blocks of the team decide alike
-        bool halt = st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters);
-        unsigned k = 0; // iterations of this launch; gst.arrive / gst.gen were zeroed before it
-
-        if (!is_event_block) {
-            // ---------------- pass block ----------------
-            const int b = role;
-            while (!halt) {
-                double best_t = DBL_MAX;
-                int best_i = INT_MAX;
-                pass_body<true, true, THREADS>(d, st, s, b, bps, 0, 0, best_t, best_i);
-                block_argmin<THREADS>(best_t, best_i);
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    int bidx = -1;
-                    double btemp = 0;
-                    if (best_i != INT_MAX) {
-                        bidx = d.ph.idx[best_i];
-                        if (bidx >= 0) btemp = d.cells.temp[bidx];
-                    }
-                    d.bm_t[s * team + b] = best_t;
-                    d.bm_i[s * team + b] = best_i;
-                    d.bm_idx[s * team + b] = bidx;
-                    d.bm_temp[s * team + b] = btemp;
-                    __threadfence();
-                    atomicAdd(&gst.arrive, 1u);
-                }
-                ++k;
-                if (!spin_until(&gst.gen, k)) break;
-                pull();
-                halt = st.halt != 0;
-                __syncthreads();
-            }
-        } else {
-            // ---------------- event block ----------------
-            if (threadIdx.x == 0) {
-                d.bm_t[s * team + bps] = DBL_MAX;
-                d.bm_i[s * team + bps] = INT_MAX;
-                st.mini_slot = -1;
-            }
-            __syncthreads();
-            while (!halt) {
-                if (!spin_until(&gst.arrive, (k + 1) * (unsigned)bps)) break;
-                ++k;
-                // this thread's entry of the block minima and the relocation count: one round trip
-                double pre_t = DBL_MAX;
-                int pre_i = INT_MAX;
-                const bool have_pre = (team <= THREADS);
-                int pre_idx = -2;
-                double pre_temp = 0;
-                if (have_pre && (int)threadIdx.x < team) {
-                    pre_t = *(volatile double *)&d.bm_t[s * team + threadIdx.x];
-                    pre_i = *(volatile int *)&d.bm_i[s * team + threadIdx.x];
-                    pre_idx = *(volatile int *)&d.bm_idx[s * team + threadIdx.x];
-                    pre_temp = *(volatile double *)&d.bm_temp[s * team + threadIdx.x];
-                }
-                const int R = *(volatile int *)&gst.reloc_n;
-                if (R > 0) relocate_shard<THREADS>(d, st, s, R);
-                const bool released = event_body<THREADS>(d, s, st.first, R, team, 0, 0.0, st, &gst, k, s * team + bps, have_pre,
-                                                          pre_t, pre_i, pre_idx, pre_temp);
-                if (!released) {
-                    // frame end, Klein-Nishina walk exhausted, cyclo-synchrotron run: publish now
-                    if (threadIdx.x == 0) {
-                        st.halt = (loop_stopped(gs, st) || st.reloc_heavy) ? 1 : 0;
-                        st.mini_slot = -1;
-                        d.bm_t[s * team + bps] = DBL_MAX;
-                        d.bm_i[s * team + bps] = INT_MAX;
-                    }
-                    __syncthreads();
-                    if (threadIdx.x < SHARD_STATE_WORDS)
-                        reinterpret_cast<unsigned long long *>(&gst)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&st)[threadIdx.x];
-                    __syncthreads();
-                    if (threadIdx.x == 0) {
-                        __threadfence();
-                        st_release_u32(&gst.gen, k);
-                    }
-                } else if (threadIdx.x == 0 && st.mini_slot < 0) {
-                    d.bm_t[s * team + bps] = DBL_MAX; // released with a halt: no mini-pass ran
-                    d.bm_i[s * team + bps] = INT_MAX;
-                }
-                __syncthreads();
-                halt = st.halt != 0;
-            }
-            // the state proper is current in global memory (published with every release)
-        }
-    }
-}
-
-// With more sub-shards than resident teams the GPU is busy anyway (many events in flight per SM) and throughput,
-// not the latency of one shard, is what counts: one block per sub-shard does pass and event in turn, and walks through
-// its shards one after the other if there are more shards than resident blocks.  No inter-block protocol at all.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_solo_kernel(DevCtx d)
-{
-    __shared__ ShardState st;
-    GlobalState &gs = *d.gs;
-    for (int s = blockIdx.x; s < d.nshards; s += gridDim.x) {
-        ShardState &gst = d.sh[s];
-        __syncthreads();
-        if (threadIdx.x < SHARD_STATE_WORDS)
-            reinterpret_cast<unsigned long long *>(&st)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&gst)[threadIdx.x];
-        __syncthreads();
-        bool halt = st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters);
-        while (!halt) {
-            double best_t = DBL_MAX;
-            int best_i = INT_MAX;
-            pass_body<true, true, THREADS>(d, st, s, 0, 1, 0, 0, best_t, best_i);
-            block_argmin<THREADS>(best_t, best_i);
-            if (threadIdx.x == 0) {
-                d.bm_t[s] = best_t;
-                d.bm_i[s] = best_i;
-            }
-            __syncthreads();
-            const int R = *(volatile int *)&gst.reloc_n;
-            if (R > 0) relocate_shard<THREADS>(d, st, s, R);
-            event_body<THREADS>(d, s, st.first, R, 1, 0, 0.0, st);
-            if (threadIdx.x == 0) st.halt = (loop_stopped(gs, st) || st.reloc_heavy) ? 1 : 0;
-            __syncthreads();
-            halt = st.halt != 0;
-        }
-        if (threadIdx.x < SHARD_STATE_WORDS)
-            reinterpret_cast<unsigned long long *>(&gst)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&st)[threadIdx.x];
-    }
-}
-
-// head of the time order only (step API calcMeanFreePath; single shard)
-__global__ void __launch_bounds__(EVT_THREADS) head_kernel(DevCtx d, int nb)
-{
-    double bt = DBL_MAX;
-    int bi = INT_MAX;
-    for (int k = threadIdx.x; k < nb; k += EVT_THREADS)
-        if (lex_less(d.bm_t[k], d.bm_i[k], bt, bi)) {
-            bt = d.bm_t[k];
-            bi = d.bm_i[k];
-        }
-    block_argmin<EVT_THREADS>(bt, bi);
-    if (threadIdx.x == 0) {
-        d.sh[0].head_idx = bi;
-        d.sh[0].head_tts = bt;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// K5: phAbsCyclosynch, Src/mc_cyclosynch.c:1571-1644
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) cs_absorb_kernel(DevCtx d)
-{
-    int abs_cnt = 0, scatt_cnt = 0;
-    double abs_w = 0;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < d.cap; i += gridDim.x * 256) {
-        const double w = d.ph.weight[i];
-        const int idx = d.ph.idx[i];
-        if ((w != 0) && (idx != -1)) {
-            double b;
-            if (d.b_calc == B_TOTAL_E || d.b_calc == B_INTERNAL_E) {
-                double el_dens = d.cells.dens[idx] / M_P;
-                b = calc_b(d.b_calc, d.epsilon_b, el_dens, d.cells.temp[idx]);
-            } else if (d.dims == D_TWO) {
-                double b0 = d.cells.B0[idx], b1 = d.cells.B1[idx];
-                b = sqrt(b0 * b0 + b1 * b1);
-            } else {
-                double b0 = d.cells.B0[idx], b1 = d.cells.B1[idx], b2 = d.cells.B2[idx];
-                b = sqrt(b0 * b0 + b1 * b1 + b2 * b2);
-            }
-            const double nu_c = calc_cyclotron_freq(b);
-            const char type = d.ph.type[i];
-            if ((d.ph.c0[i] * C_LIGHT / PL_CONST <= nu_c) || (type == 'p')) {
-                abs_cnt++;
-                if (!((type != 'i') && (type != 'c'))) abs_w += w;
-                // setNullPhoton, Src/photons.c:208-251
-                d.ph.type[i] = 'N';
-                d.ph.weight[i] = 0;
-                d.ph.idx[i] = -1;
-                d.ph.safe[i] = 0;
-                d.ph.flags[i] = 0;
-                store_momentum(d.ph, i, 0, 0, 0, 0);
-                d.ph.c0[i] = 0; d.ph.c1[i] = 0; d.ph.c2[i] = 0; d.ph.c3[i] = 0;
-                d.ph.r0[i] = 0; d.ph.r1[i] = 0; d.ph.r2[i] = 0;
-                d.ph.s0[i] = 0; d.ph.s1[i] = 0; d.ph.s2[i] = 0; d.ph.s3[i] = 0;
-                d.ph.nscatt[i] = 0;
-                store_tau(d.ph, i, 0);
-            } else if ((type == 'k') || (type == 'c')) {
-                scatt_cnt++;
-            }
-        }
-    }
-    // block reduction, then one atomic per block
-    __shared__ int s_abs[8], s_sc[8];
-    __shared__ double s_w[8];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        abs_cnt += __shfl_xor_sync(0xffffffffu, abs_cnt, off);
-        scatt_cnt += __shfl_xor_sync(0xffffffffu, scatt_cnt, off);
-        abs_w += __shfl_xor_sync(0xffffffffu, abs_w, off);
-    }
-    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    if (lane == 0) {
-        s_abs[wp] = abs_cnt;
-        s_sc[wp] = scatt_cnt;
-        s_w[wp] = abs_w;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int a = 0, s = 0;
-        double w = 0;
-        for (int k = 0; k < 8; ++k) {
-            a += s_abs[k];
-            s += s_sc[k];
-            w += s_w[k];
-        }
-        if (a) atomicAdd(&d.gs->abs_count, a);
-        if (s) atomicAdd(&d.gs->cs_scatt_count, s);
-        if (w != 0) atomicAdd(&d.gs->abs_weight, w);
-    }
-}
-
-
-// ------------------------------------------------------------------------------------------
-// K7: thermal (hot) Klein-Nishina cross-section table, Src/hot_x_section.c:82-206.
-// One block per table point (221 x 81); each point is the reference's plain Monte Carlo estimate
-// (Src/hot_x_section.c:324-357: `calls` uniform samples of (gamma, mu) over
-// [1, 1 + 12 theta] x [-1, 1], integrand = Maxwell-Juttner pdf x boosted KN cross section,
-// result = 0.5 * volume * mean), drawn from a Philox stream keyed by the point.
-// ------------------------------------------------------------------------------------------
-__device__ inline double maxwell_juttner_pdf(double gamma, double theta, double normalization)
-{
-    // Src/electron.c:538-560 singleMaxwellJuttner (normalization computed once per point)
-    return ((gamma * sqrt(gamma * gamma - 1.) / (theta * normalization)) * exp(-(gamma - 1.) / theta));
-}
-
-__device__ inline double boosted_cross_section(double norm_ph_comv, double mu, double gamma)
-{
-    // Src/hot_x_section.c:369-400 boostedCrossSection
-    double beta = sqrt(gamma * gamma - 1.) / gamma;
-    double norm_ph_e = norm_ph_comv * gamma * (1. - mu * beta);
-    return kn_cross_section(norm_ph_e) * (1. - mu * beta);
-}
-
-__global__ void __launch_bounds__(256) hot_table_kernel(double *table, long long calls, uint32_t k0, uint32_t k1)
-{
-    const int point = blockIdx.x; // i * (N_T + 1) + j, the reference's loop order (:90-105)
-    const int i = point / (N_T + 1), j = point - i * (N_T + 1);
-    const double dt = (LOG_T_MAX - LOG_T_MIN) / N_T, dph_e = (LOG_PH_E_MAX - LOG_PH_E_MIN) / N_PH_E;
-    const double comv_ph_e = pow(10., LOG_PH_E_MIN + i * dph_e);
-    const double theta = pow(10., LOG_T_MIN + j * dt);
-    double result;
-    if (theta < pow(10., LOG_T_MIN) && comv_ph_e < pow(10., LOG_PH_E_MIN)) {
-        result = 1; // :336-337
-    } else if (theta < pow(10., LOG_T_MIN)) {
-        result = kn_cross_section(comv_ph_e); // :338-339
-    } else {
-        double normalization;
-        if (theta > 1.e-2)
-            normalization = bessel_K2(1. / theta) * exp(1. / theta);
-        else
-            normalization = sqrt(PI * theta / 2.);
-        const double xl0 = 1, xu0 = 1. + 12 * theta;
-        double sum = 0;
-        for (long long n = threadIdx.x; n < calls; n += 256) {
-            double u1, u2;
-            philox_doubles((uint32_t)n, (uint32_t)(n >> 32), (uint32_t)point, 2u, k0, k1, u1, u2);
-            double gamma = xl0 + u1 * (xu0 - xl0);
-            double mu = -1 + u2 * (1 - (-1));
-            sum += maxwell_juttner_pdf(gamma, theta, normalization) * boosted_cross_section(comv_ph_e, mu, gamma);
-        }
-        __shared__ double red[8];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
-        __syncthreads();
-        double tot = 0;
-        for (int k = 0; k < 8; ++k) tot += red[k];
-        const double vol = (xu0 - xl0) * (1 - (-1));
-        result = 0.5 * (vol * (tot / (double)calls));
-    }
-    if (threadIdx.x == 0) table[point] = log10(result);
-}
-
-// ------------------------------------------------------------------------------------------
-// photon statistics (Src/mclib.c:1358-1515): per-block partials, finished on the host
-// ------------------------------------------------------------------------------------------
-struct StatPartial {
-    double e_sum, w_sum, ns_sum, r_sum, r_min, r_max, th_min, th_max;
-    long long count;
-    int ns_max, ns_min;
-};
-
-__global__ void __launch_bounds__(256) stats_kernel(DevCtx d, StatPartial *out)
-{
-    StatPartial a;
-    a.e_sum = a.w_sum = a.ns_sum = a.r_sum = 0;
-    a.r_min = DBL_MAX; a.r_max = 0; a.th_min = DBL_MAX; a.th_max = 0;
-    a.count = 0; a.ns_max = 0; a.ns_min = INT_MAX;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < d.cap; i += gridDim.x * 256) {
-        const double w = d.ph.weight[i];
-        const bool live = (w != 0);
-        if (!d.cs || live) { // Src/mclib.c:1373-1379, 1401-1404
-            a.e_sum += d.ph.p0[i] * w;
-            a.w_sum += w;
-            double ns = d.ph.nscatt[i];
-            double r = sqrt(d.ph.r0[i] * d.ph.r0[i] + d.ph.r1[i] * d.ph.r1[i] + d.ph.r2[i] * d.ph.r2[i]);
-            a.ns_sum += ns;
-            a.r_sum += r;
-            if (ns > a.ns_max) a.ns_max = (int)ns;
-            if (ns < a.ns_min) a.ns_min = (int)ns;
-            a.count++;
-        }
-        if (live) { // Src/mclib.c:1479-1508
-            double r = sqrt(d.ph.r0[i] * d.ph.r0[i] + d.ph.r1[i] * d.ph.r1[i] + d.ph.r2[i] * d.ph.r2[i]);
-            double th = acos(d.ph.r2[i] / r);
-            if (r > a.r_max) a.r_max = r;
-            if (r < a.r_min) a.r_min = r;
-            if (th > a.th_max) a.th_max = th;
-            if (th < a.th_min) a.th_min = th;
-        }
-    }
-    __shared__ StatPartial sh[256];
-    sh[threadIdx.x] = a;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s) {
-            StatPartial &x = sh[threadIdx.x];
-            const StatPartial &y = sh[threadIdx.x + s];
-            x.e_sum += y.e_sum; x.w_sum += y.w_sum; x.ns_sum += y.ns_sum; x.r_sum += y.r_sum;
-            x.r_min = fmin(x.r_min, y.r_min); x.r_max = fmax(x.r_max, y.r_max);
-            x.th_min = fmin(x.th_min, y.th_min); x.th_max = fmax(x.th_max, y.th_max);
-            x.count += y.count;
-            x.ns_max = max(x.ns_max, y.ns_max); x.ns_min = min(x.ns_min, y.ns_min);
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
-}
-
-// ------------------------------------------------------------------------------------------
-// K8: rebinCyclosynchCompPhotons, Src/mc_cyclosynch.c:244-710, on the device.  The (log E, theta[, phi])
-// binning of the reference, including gsl_histogram2d's uniform ranges and its find() (linear guess,
-// then bisection); every bin's weighted sums are accumulated in slot order, as the reference's one
-// sequential loop does, so the rebinned photons agree with the CPU's to rounding of acos / atan2 / sincos.
-// ------------------------------------------------------------------------------------------
-constexpr double RAD_TO_DEG = 180.0 / PI, DEG_TO_RAD = PI / 180.0; // Src/mcrat.h:80-81
-
-struct RebinRange { // struct PhotonRangeInfo, Src/mc_cyclosynch.h
-    double p0_min, p0_max, theta_min, theta_max, phi_min, phi_max;
-    int valid_photon_count, synch_photon_count;
-};
-
-struct RebinParams { // struct BinningParams + the histogram ranges
-    int num_bins, num_bins_theta, num_bins_phi, total_bins;
-    const double *range_e, *range_theta, *range_phi; // num_bins+1, num_bins_theta+1, num_bins_phi+1 edges
-};
-
-struct RebinBin { // struct BinStats
-    double weighted_r, weighted_theta, weighted_phi_offset, weighted_stokes[4], weighted_scatt_count, total_weight;
-    double weighted_phi_dir, weighted_theta_dir, weighted_energy, weighted_phi_pos;
-};
-
-__device__ __forceinline__ bool rebin_eligible(char type) { return (type != 'N') && (type != 'p') && (type != 'i'); }
-
-// calculate_photon_position, Src/mc_cyclosynch.c:246-270
-__device__ __forceinline__ void rebin_position(int ndim3, double x, double y, double z, double &r, double &theta, double &phi)
-{
-    r = sqrt(x * x + y * y + z * z);
-    if (r < DBL_MIN) {
-        theta = 0.0;
-        phi = 0.0;
-    } else {
-        theta = acos(z / r);
-        if (ndim3) {
-            double phi_rad = atan2(y, x);
-            phi = fmod(phi_rad * RAD_TO_DEG + 360.0, 360.0);
-        } else {
-            phi = 0;
-        }
-    }
-}
-
-// collect_photon_statistics, Src/mc_cyclosynch.c:273-322 (per-block partials; min / max are exact in any order)
-__global__ void __launch_bounds__(256) rebin_range_kernel(DevCtx d, RebinRange *out)
-{
-    const int ndim3 = (d.dims == D_THREE);
-    RebinRange a;
-    a.p0_min = DBL_MAX; a.p0_max = 0.0; a.theta_min = DBL_MAX; a.theta_max = 0.0; a.phi_min = DBL_MAX; a.phi_max = 0.0;
-    a.valid_photon_count = 0; a.synch_photon_count = 0;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < d.cap; i += gridDim.x * 256) {
-        const char type = d.ph.type[i];
-        if (rebin_eligible(type)) {
-            const double p0 = d.ph.p0[i];
-            if (p0 > 0) {
-                a.p0_min = fmin(a.p0_min, p0);
-                a.p0_max = fmax(a.p0_max, p0);
-                a.valid_photon_count++;
-            }
-            double r, theta, phi;
-            rebin_position(ndim3, d.ph.r0[i], d.ph.r1[i], d.ph.r2[i], r, theta, phi);
-            a.theta_min = fmin(a.theta_min, theta);
-            a.theta_max = fmax(a.theta_max, theta);
-            if (ndim3) {
-                a.phi_min = fmin(a.phi_min, phi);
-                a.phi_max = fmax(a.phi_max, phi);
-            }
-        }
-        if (type == 'p') a.synch_photon_count++;
-    }
-    __shared__ RebinRange sh[256];
-    sh[threadIdx.x] = a;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s) {
-            RebinRange &x = sh[threadIdx.x];
-            const RebinRange &y = sh[threadIdx.x + s];
-            x.p0_min = fmin(x.p0_min, y.p0_min); x.p0_max = fmax(x.p0_max, y.p0_max);
-            x.theta_min = fmin(x.theta_min, y.theta_min); x.theta_max = fmax(x.theta_max, y.theta_max);
-            x.phi_min = fmin(x.phi_min, y.phi_min); x.phi_max = fmax(x.phi_max, y.phi_max);
-            x.valid_photon_count += y.valid_photon_count; x.synch_photon_count += y.synch_photon_count;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
-}
-
-// gsl_histogram find(): 0 on success (histogram/find.c: linear guess, then bisection)
-__device__ __forceinline__ int hist_find(int n, const double *range, double x, int &i)
-{
-    if (x < range[0] || x >= range[n]) return 1;
-    {
-        double u = (x - range[0]) / (range[n] - range[0]);
-        size_t g = (size_t)(u * n);
-        if (g < (size_t)n && x >= range[g] && x < range[g + 1]) {
-            i = (int)g;
-            return 0;
-        }
-    }
-    int lower = 0, upper = n;
-    while (upper - lower > 1) {
-        int mid = (upper + lower) / 2;
-        if (x >= range[mid])
-            lower = mid;
-        else
-            upper = mid;
-    }
-    i = lower;
-    return 0;
-}
-
-// bin index of every slot (or -1), Src/mc_cyclosynch.c:453-472
-__global__ void __launch_bounds__(256) rebin_index_kernel(DevCtx d, RebinParams p, int *bin_of)
-{
-    const int ndim3 = (d.dims == D_THREE);
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < d.cap; i += gridDim.x * 256) {
-        int b = -1;
-        if (rebin_eligible(d.ph.type[i])) {
-            double r, theta, phi;
-            rebin_position(ndim3, d.ph.r0[i], d.ph.r1[i], d.ph.r2[i], r, theta, phi);
-            const double le = log10(d.ph.p0[i]);
-            int ix = 0, iy = 0, iz = 0;
-            // gsl_histogram2d_find(h_energy_theta, ...): the second index is only written if the first was found
-            if (hist_find(p.num_bins, p.range_e, le, ix) == 0) hist_find(p.num_bins_theta, p.range_theta, theta, iy);
-            if (ndim3) {
-                if (hist_find(p.num_bins, p.range_e, le, ix) == 0) hist_find(p.num_bins_phi, p.range_phi, phi, iz);
-                if (hist_find(p.num_bins_theta, p.range_theta, theta, iy) == 0) hist_find(p.num_bins_phi, p.range_phi, phi, iz);
-            }
-            // calculate_bin_index, :432-446
-            if (ix < 0 || ix >= p.num_bins || iy < 0 || iy >= p.num_bins_theta)
-                b = -2;
-            else if (ndim3)
-                b = (iz < 0 || iz >= p.num_bins_phi) ? -2 : iz * p.num_bins * p.num_bins_theta + ix * p.num_bins_theta + iy;
-            else
-                b = ix * p.num_bins_theta + iy;
-            if (b == -2 || b >= p.total_bins) {
-                d.gs->error = MCRAT_B200_ERR_STATE; // the reference exits here (:469-472)
-                b = -1;
-            }
-        }
-        bin_of[i] = b;
-    }
-}
-
-// accumulate_bin_statistics + create_rebinned_photons (:448-585): one thread per bin walks the list in slot
-// order (warp-uniform reads of bin_of[]), which keeps the reference's order of additions inside every bin
-__global__ void __launch_bounds__(128) rebin_accumulate_kernel(DevCtx d, RebinParams p, const int *bin_of, mcrat_photon *out)
-{
-    const int ndim3 = (d.dims == D_THREE);
-    const int b = blockIdx.x * 128 + threadIdx.x;
-    RebinBin s;
-    memset(&s, 0, sizeof(s));
-    for (int i = 0; i < d.cap; ++i) {
-        if (bin_of[i] != b || b >= p.total_bins) continue;
-        const double w = d.ph.weight[i];
-        const double x = d.ph.r0[i], y = d.ph.r1[i], z = d.ph.r2[i];
-        const double p0 = d.ph.p0[i], p1 = d.ph.p1[i], p2 = d.ph.p2[i], p3 = d.ph.p3[i];
-        double r, theta, phi;
-        rebin_position(ndim3, x, y, z, r, theta, phi);
-        s.weighted_r += r * w;
-        s.weighted_theta += theta * w;
-        s.weighted_phi_offset += (atan2(p2, p1) - atan2(y, x)) * RAD_TO_DEG * w;
-        s.weighted_stokes[0] += d.ph.s0[i] * w;
-        s.weighted_stokes[1] += d.ph.s1[i] * w;
-        s.weighted_stokes[2] += d.ph.s2[i] * w;
-        s.weighted_stokes[3] += d.ph.s3[i] * w;
-        s.weighted_scatt_count += d.ph.nscatt[i] * w;
-        s.total_weight += w;
-        double phi_dir = fmod(atan2(p2, p1) * RAD_TO_DEG + 360.0, 360.0);
-        double theta_dir = acos(p3 / p0) * RAD_TO_DEG;
-        s.weighted_phi_dir += phi_dir * w;
-        s.weighted_theta_dir += theta_dir * w;
-        s.weighted_energy += p0 * w;
-        if (ndim3) s.weighted_phi_pos += phi * w;
-    }
-    if (b >= p.total_bins) return;
-    mcrat_photon q;
-    memset(&q, 0, sizeof(q)); // calloc'ed in the reference (:505)
-    if (s.total_weight <= 0) {
-        q.type = 'N';
-        q.weight = 0;
-        q.nearest_block_index = -1;
-        q.recalc_properties = 0;
-    } else {
-        q.type = 'k';
-        q.weight = s.total_weight;
-        double avg_energy = s.weighted_energy / s.total_weight;
-        double avg_phi_dir = s.weighted_phi_dir / s.total_weight;
-        double avg_theta_dir = s.weighted_theta_dir / s.total_weight;
-        double avg_r = s.weighted_r / s.total_weight;
-        double avg_theta_pos = s.weighted_theta / s.total_weight;
-        q.p0 = avg_energy;
-        q.p1 = avg_energy * sin(avg_theta_dir * DEG_TO_RAD) * cos(avg_phi_dir * DEG_TO_RAD);
-        q.p2 = avg_energy * sin(avg_theta_dir * DEG_TO_RAD) * sin(avg_phi_dir * DEG_TO_RAD);
-        q.p3 = avg_energy * cos(avg_theta_dir * DEG_TO_RAD);
-        double pos_phi;
-        if (ndim3) {
-            double avg_phi_pos = s.weighted_phi_pos / s.total_weight;
-            pos_phi = avg_phi_pos * DEG_TO_RAD;
-        } else {
-            double avg_phi_offset = s.weighted_phi_offset / s.total_weight;
-            pos_phi = (avg_phi_dir - avg_phi_offset) * DEG_TO_RAD;
-        }
-        q.r0 = avg_r * sin(avg_theta_pos) * cos(pos_phi);
-        q.r1 = avg_r * sin(avg_theta_pos) * sin(pos_phi);
-        q.r2 = avg_r * cos(avg_theta_pos);
-        q.s0 = s.weighted_stokes[0] / s.total_weight;
-        q.s1 = s.weighted_stokes[1] / s.total_weight;
-        q.s2 = s.weighted_stokes[2] / s.total_weight;
-        q.s3 = s.weighted_stokes[3] / s.total_weight;
-        q.num_scatt = (int)(s.weighted_scatt_count / s.total_weight + 0.5);
-        q.nearest_block_index = 0;
-        q.recalc_properties = 1;
-    }
-    out[b] = q;
-}
-
-__device__ __forceinline__ void set_null_photon(DevCtx &d, int i) // setNullPhoton, Src/photons.c:208-251
-{
-    d.ph.type[i] = 'N';
-    d.ph.weight[i] = 0;
-    d.ph.idx[i] = -1;
-    d.ph.safe[i] = 0;
-    d.ph.flags[i] = 0;
-    store_momentum(d.ph, i, 0, 0, 0, 0);
-    d.ph.c0[i] = 0; d.ph.c1[i] = 0; d.ph.c2[i] = 0; d.ph.c3[i] = 0;
-    d.ph.r0[i] = 0; d.ph.r1[i] = 0; d.ph.r2[i] = 0;
-    d.ph.s0[i] = 0; d.ph.s1[i] = 0; d.ph.s2[i] = 0; d.ph.s3[i] = 0;
-    d.ph.nscatt[i] = 0;
-    store_tau(d.ph, i, 0);
-}
-
-// :588-596 null every 'k' / 'c' photon, then count the null slots of each 256-slot block
-__global__ void __launch_bounds__(256) rebin_null_kernel(DevCtx d)
-{
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    int is_null = 0;
-    if (i < d.cap) {
-        const char t = d.ph.type[i];
-        if (t == 'c' || t == 'k') set_null_photon(d, i);
-        is_null = (t == 'c' || t == 'k' || t == 'N');
-    }
-    const int c = __syncthreads_count(is_null);
-    if (threadIdx.x == 0) d.prefix_block[blockIdx.x] = c;
-}
-
-__global__ void rebin_scan_kernel(DevCtx d, int nblocks, int *total_null)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        int run = 0;
-        for (int b = 0; b < nblocks; ++b) {
-            int c = d.prefix_block[b];
-            d.prefix_block[b] = run;
-            run += c;
-        }
-        *total_null = run;
-    }
-}
-
-// addToPhotonList (Src/photons.c:167-205): rebinned photon k goes to the k-th null slot of the list
-__global__ void __launch_bounds__(256) rebin_place_kernel(DevCtx d, const mcrat_photon *rebinned, int total_bins)
-{
-    __shared__ int warp_off[8];
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    const bool is_null = (i < d.cap) && (d.ph.type[i] == 'N');
-    const unsigned ball = __ballot_sync(0xffffffffu, is_null);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) warp_off[w] = __popc(ball);
-    __syncthreads();
-    int k = d.prefix_block[blockIdx.x];
-    for (int q = 0; q < w; ++q) k += warp_off[q];
-    k += __popc(ball & ((1u << lane) - 1u));
-    if (!is_null || k >= total_bins) return;
-    const mcrat_photon p = rebinned[k];
-    if (p.type == 'N') return; // only the non-null rebinned photons are copied (:190-199)
-    d.ph.type[i] = p.type;
-    store_momentum(d.ph, i, p.p0, p.p1, p.p2, p.p3);
-    d.ph.c0[i] = 0; d.ph.c1[i] = 0; d.ph.c2[i] = 0; d.ph.c3[i] = 0;
-    d.ph.r0[i] = p.r0; d.ph.r1[i] = p.r1; d.ph.r2[i] = p.r2;
-    d.ph.safe[i] = 0;
-    d.ph.s0[i] = p.s0; d.ph.s1[i] = p.s1; d.ph.s2[i] = p.s2; d.ph.s3[i] = p.s3;
-    d.ph.nscatt[i] = p.num_scatt;
-    d.ph.weight[i] = p.weight;
-    d.ph.idx[i] = p.nearest_block_index;
-    d.ph.tts[i] = 0;
-    store_tau(d.ph, i, 0);
-    d.ph.flags[i] = (unsigned char)(((p.weight != 0) ? F_MOVABLE : 0) | F_RECALC);
-}
-
-__global__ void rebin_count_kernel(const mcrat_photon *rebinned, int total_bins, int *null_bins)
-{
-    int c = 0;
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < total_bins; b += gridDim.x * blockDim.x)
-        if (rebinned[b].type == 'N') c++;
-    if (c) atomicAdd(null_bins, c);
-}
-
-// ------------------------------------------------------------------------------------------
-// peak probes (roofline denominators measured on the same GPU, same run)
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double seed)
-{
-    // FP64-pipe issue rate: 16 independent DFMA chains per thread, 64 warps per SM
-    double x[16];
-    const double a = 1.0 + seed * 1e-9, b = seed * 1e-12;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) x[k] = seed + k + threadIdx.x * 1e-6;
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = fma(x[k], a, b);
-    }
-    double s = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) s += x[k];
-    if (s == 12345.678) out[0] = s;
-}
-
-__global__ void __launch_bounds__(256) copy_kernel(const double4 *__restrict__ a, double4 *__restrict__ b, size_t n)
-{
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
-}
+// the kernels, in dependency order (one translation unit: everything is inlined into the __global__ functions)
+#include "state.cuh"
+#include "pass_kernels.cuh"
+#include "scan_kernels.cuh"
+#include "event.cuh"
+#include "frame_loop.cuh"
+#include "aux_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------
 // host side

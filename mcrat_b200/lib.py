@@ -78,7 +78,7 @@ EXPORTS = [
 
 def build(force=False):
     """Compile the CUDA library in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("mcrat_b200.cu", "device_math.cuh", "dropin.c", "Makefile")]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".c")) or f == "Makefile"]
     srcs += [os.path.join(HERE, "..", "include", f) for f in ("mcrat_b200.h", "mcrat_b200_dropin.h")]
     srcs = [s for s in srcs if os.path.exists(s)]
     stale = force or not os.path.exists(LIB_PATH) or not os.path.exists(DROPIN_PATH) or \

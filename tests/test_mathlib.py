@@ -87,7 +87,7 @@ def test_gaussian_and_poisson_moments():
 
 
 def test_fma_corrected_division_by_c_is_the_ieee_quotient(tmp_path):
-    """div_by_c of the pass kernel (mcrat_b200/csrc/mcrat_b200.cu): q = RN(x * rc), r = fma(-q, c, x), RN(q + r * rc)
+    """div_by_c of the pass kernel (mcrat_b200/csrc/pass_kernels.cuh): q = RN(x * rc), r = fma(-q, c, x), RN(q + r * rc)
     must equal x / C_LIGHT bit for bit.  Host-side brute force (tools/div_by_c_check.c) on 2e8 random significands
     over 41 binades plus structured ones; the device version is compared with the hardware division by
     tests/test_gpu_parity.py::test_division_by_c_is_exact."""

@@ -1,5 +1,5 @@
 """The geometric bound behind the skipped cell re-checks (safe_path / margin_length / margin_angle in
-mcrat_b200/csrc/mcrat_b200.cu), restated in numpy and attacked with random displacements: a photon inside a cell
+mcrat_b200/csrc/pass_kernels.cuh), restated in numpy and attacked with random displacements: a photon inside a cell
 that moves by less than the bound, in any direction, must still be inside the cell and the domain when its new
 position is put through the reference's coordinate transform (Src/geometry.c:15-64) and its cell test
 (Src/geometry.c:394-417).  CPU only; the device side is checked against the real re-check by

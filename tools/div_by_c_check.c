@@ -1,5 +1,5 @@
 /* Host-side brute-force check of the FMA-corrected division by C_LIGHT used by the pass kernel (div_by_c in
- * mcrat_b200/csrc/mcrat_b200.cu): 4e9 random significands over 41 binades, structured significands, and the neighbours
+ * mcrat_b200/csrc/pass_kernels.cuh): 4e9 random significands over 41 binades, structured significands, and the neighbours
  * of exact multiples of C_LIGHT, each compared with the IEEE division.
  *   gcc -O2 -mfma -ffp-contract=off -fopenmp tools/div_by_c_check.c -o /tmp/div_by_c_check -lm && /tmp/div_by_c_check
  * prints "mismatches 0 of 4000000000" and "structured mismatches 0"; an argument sets the number of random samples
