@@ -101,3 +101,27 @@ def test_synthetic_outflows_match_reference_analytic_models():
             if wl == "C2" and f in ("gamma", "v0", "v1", "dens", "dens_lab"):
                 ok |= ref.hydro_field("gamma") < 1.0  # synth clamps the unphysical Gamma < 1 region
             assert ok.all(), (refname, f)
+
+
+def test_every_kernel_source_is_a_build_dependency_and_nothing_imports_the_oracle():
+    """The kernels are one translation unit spread over include files: each must be listed in the Makefile's
+    dependencies (a stale library would silently survive an edit), and be included by mcrat_b200.cu.  And the product
+    package must not reach into oracle/ (test infrastructure only)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "mcrat_b200", "csrc")
+    mk = open(os.path.join(csrc, "Makefile")).read()
+    main = open(os.path.join(csrc, "mcrat_b200.cu")).read()
+    headers = sorted(f for f in os.listdir(csrc) if f.endswith(".cuh"))
+    assert len(headers) >= 7
+    for h in headers:
+        assert re.search(r"KERNEL_SRC\s*=.*\b%s\b" % re.escape(h), mk), h
+        assert ('#include "%s"' % h) in main, h
+    pkg = os.path.join(root, "mcrat_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), os.path.join(dirpath, f)
+                assert '#include "../../oracle' not in text, os.path.join(dirpath, f)
