@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(256) rebin_index_kernel(DevCtx d, RebinParams 
             else
                 b = ix * p.num_bins_theta + iy;
             if (b == -2 || b >= p.total_bins) {
-                d.gs->error = MCRAT_B200_ERR_STATE; // the reference exits here (:469-472)
+                raise_error(d.gs, MCRAT_B200_ERR_STATE, -1, ERR_SITE_REBIN); // the reference exits here (:469-472)
                 b = -1;
             }
         }

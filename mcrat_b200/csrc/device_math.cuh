@@ -46,16 +46,18 @@ __host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// two uniforms strictly inside (0,1): ((53-bit integer) + 0.5) * 2^-53
+// two uniforms strictly inside (0,1): ((52-bit integer) + 0.5) * 2^-52.  x + 0.5 with x < 2^52 needs 53 significand
+// bits, so the sum and the scaling are exact: the values are the odd multiples of 2^-53, from 2^-53 to 1 - 2^-53
+// (with 53 random bits the + 0.5 would be rounded away for x >= 2^52 and x = 2^53 - 1 would give exactly 1.0)
 __host__ __device__ inline void philox_doubles(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                                uint32_t k1, double &a, double &b)
 {
     uint32_t r[4];
     philox4x32_10(c0, c1, c2, c3, k0, k1, r);
-    uint64_t x = (((uint64_t)r[0] << 32) | r[1]) >> 11;
-    uint64_t y = (((uint64_t)r[2] << 32) | r[3]) >> 11;
-    a = ((double)x + 0.5) * (1.0 / 9007199254740992.0);
-    b = ((double)y + 0.5) * (1.0 / 9007199254740992.0);
+    uint64_t x = (((uint64_t)r[0] << 32) | r[1]) >> 12;
+    uint64_t y = (((uint64_t)r[2] << 32) | r[3]) >> 12;
+    a = ((double)x + 0.5) * (1.0 / 4503599627370496.0);
+    b = ((double)y + 0.5) * (1.0 / 4503599627370496.0);
 }
 
 // stream 0: the free-path draw of photon `slot` in while-loop iteration `iter`

@@ -435,7 +435,7 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
                     int terr = 0;
                     tau_next = optical_depth(d.dims, d.geom, d.tau_calc, d.table, cell, m.r[0], m.r[1], m.p_new[1], m.p_new[2],
                                              m.p_new[3], m.pc_fin[0], &terr);
-                    if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
+                    if (terr) raise_error(d.gs, MCRAT_B200_ERR_TABLE, i, ERR_SITE_EVENT_MINIPASS);
                     const uint32_t k1 = d.k1 ^ (d.shard_base + (uint32_t)(early.gst - d.sh));
                     const double xi = philox_mfp_uniform(d.k0, k1, st.iter, (uint32_t)(i - st.first));
                     t_next = free_path_time(tau_next, xi);
@@ -568,6 +568,15 @@ __device__ void cs_emit_single(DevCtx &d, EventRng &rng, int scatt, int slot)
 // `early_gst` != nullptr (persistent loop): publish the state to *early_gst and release `early_gen` on its generation
 // word as soon as a candidate is accepted; d.bm_*[early_bm] receives the scattered photon's mini-pass.  Returns
 // whether that happened (else the caller publishes after the event).
+// R is the relocation count of the whole list in the streamed loop: the entries of this shard are found by reading all
+// R slots (4 B each, L2-resident) -- cheaper than reading the shard's own time column (8 B per photon) unless the list is
+// long compared with the shard.  (A fixed cap of 2048 made every event block of a 10^7-photon list re-read its whole
+// column once 2e-4 of the photons changed cell in an iteration.)
+__device__ __forceinline__ bool reloc_list_cheaper(int R, int shard_count)
+{
+    return R <= RELOC_LIST_SCAN_MAX || R <= shard_count / 2;
+}
+
 template <int EVT_THREADS>
 __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int reloc_base, const int R, int nb_per_shard,
                                            int step_mode, double dt_max_arg, ShardState &st, ShardState *early_gst = nullptr,
@@ -598,7 +607,7 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
             }
         }
         // photons relocated in this iteration got their time in finish
-        if (R > 0 && R <= RELOC_LIST_SCAN_MAX) {
+        if (R > 0 && reloc_list_cheaper(R, st.count)) {
             for (int j = threadIdx.x; j < R; j += EVT_THREADS) {
                 const int i = d.reloc_slot[reloc_base + j];
                 if (i >= st.first && i < st.first + st.count) {
@@ -698,6 +707,31 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
 
     // ---- photonEvent: walk candidates in ascending time, Src/mclib.c:1128-1339 ----
     while (true) {
+        // The reference's walk has no bound on the number of rejected candidates (Src/mclib.c:1128-1339), the push
+        // list has MAX_DT entries: when it is full, the recorded pushes are applied here to every photon of the shard
+        // (one by one, in order -- exactly what the next pass would have done) and recording starts over.  No other
+        // block touches this shard's photons at this point (streamed loop: stream order; persistent loop: the pass
+        // blocks wait on the generation word).
+        if (n_dt == MAX_DT) {
+            for (int j = threadIdx.x; j < st.count; j += EVT_THREADS) {
+                const int i = st.first + j;
+                if (d.ph.flags[i] & F_MOVABLE) {
+                    double r0 = d.ph.r0[i], r1 = d.ph.r1[i], r2 = d.ph.r2[i];
+                    apply_pushes_v(st, MAX_DT, d.ph.v0[i], d.ph.v1[i], d.ph.v2[i], r0, r1, r2);
+                    d.ph.r0[i] = r0;
+                    d.ph.r1[i] = r1;
+                    d.ph.r2[i] = r2;
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                st.n_dt = MAX_DT;
+                fold_path(st, d.path_pad);
+                st.n_dt = 0;
+                n_dt = 0;
+            }
+            __syncthreads();
+        }
         if (threadIdx.x == 0) {
             const int i = sh_cand_i;
             const double t = sh_cand_t;
@@ -705,18 +739,13 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
             ph_index = i;
             scatt_time = t;
             if (t < dt_max) {
-                if (n_dt < MAX_DT) {
-                    st.dt_list[n_dt] = t - old_scatt_time;
-                    n_dt++;
-                    attempt = true;
-                } else {
-                    gs.error = MCRAT_B200_ERR_STATE;
-                    event = true;
-                }
+                st.dt_list[n_dt] = t - old_scatt_time;
+                n_dt++;
+                attempt = true;
             } else {
                 scatt_time = dt_max;
-                st.dt_list[n_dt < MAX_DT ? n_dt : MAX_DT - 1] = scatt_time - old_scatt_time;
-                n_dt = min(n_dt + 1, MAX_DT);
+                st.dt_list[n_dt] = scatt_time - old_scatt_time;
+                n_dt++;
                 event = true;
             }
             old_scatt_time = scatt_time;
@@ -748,7 +777,7 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
             // photons re-located in this iteration are not in any minimum and come from the re-location list.  Same
             // result as reading every time of the shard, without the 80 MB read by one block at 10^7 photons.
             const bool two_level = (early_gst == nullptr) && !have_pre && step_mode == 0 && !d.replay && nb_per_shard > 1 &&
-                                   R <= RELOC_LIST_SCAN_MAX;
+                                   reloc_list_cheaper(R, st.count);
             if (two_level) {
                 for (int k = threadIdx.x; k < nb_per_shard; k += EVT_THREADS) {
                     const int q = s * nb_per_shard + k;
@@ -858,7 +887,7 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
         }
         if (d.replay) {
             gs.replay_cursor = rng_sh.pos;
-            if (rng_sh.exhausted) gs.error = MCRAT_B200_ERR_REPLAY;
+            if (rng_sh.exhausted) raise_error(&gs, MCRAT_B200_ERR_REPLAY, ph_index, ERR_SITE_EVENT_REPLAY);
         }
     }
     __syncthreads();

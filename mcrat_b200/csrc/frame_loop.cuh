@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
                     while (ld_relaxed_u32(word) < target) {
                         __nanosleep(40);
                         if (++spins > (1u << 24)) { // never in a healthy run; refuse to hang the GPU
-                            gs.error = MCRAT_B200_ERR_STATE;
+                            raise_error(&gs, MCRAT_B200_ERR_STATE, -1, ERR_SITE_LOOP_SPIN);
                             ok = 0;
                             break;
                         }

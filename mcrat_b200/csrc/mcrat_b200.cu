@@ -500,6 +500,7 @@ static int layout_shards(mcrat_b200_ctx *ctx, int n)
     S = n > 0 ? (n + size - 1) / size : 1;
     if (int rc = fetch_state(ctx)) return rc; // keep per-shard iteration counters (RNG stream positions)
     const bool relayout = (S != d.nshards) || (size != d.shard_size);
+    const int old_S = d.nshards;
     d.nshards = S;
     d.shard_size = size;
     int bps = (size + PASS_THREADS - 1) / PASS_THREADS;
@@ -509,12 +510,18 @@ static int layout_shards(mcrat_b200_ctx *ctx, int n)
     if (bps > BLOCKMIN_CAP / S) bps = BLOCKMIN_CAP / S;
     if (bps < 1) bps = 1;
     d.blocks_per_shard = bps;
+    // The iteration number is the only per-iteration word of the Philox counters (free path: (slot, iter, 0);
+    // event: (draw / 2, iter, 1)) and the key holds seed and shard only, so a shard must never see an iteration
+    // number twice in the life of a context: when the list is laid out anew (injection, growth, another number of
+    // sub-shards) every shard continues from the largest iteration number any shard had reached.
+    unsigned long long it_max = 0;
+    for (int s = 0; s < old_S; ++s)
+        if (ctx->sh_host[s].iter > it_max) it_max = ctx->sh_host[s].iter;
     for (int s = 0; s < S; ++s) {
         ShardState &sh = ctx->sh_host[s];
         if (relayout) {
-            unsigned long long it = (s == 0) ? sh.iter : 0;
             memset(&sh, 0, sizeof(sh));
-            sh.iter = it;
+            sh.iter = it_max;
         }
         sh.first = s * size;
         sh.count = (s * size + size <= n) ? size : (n - s * size);
@@ -738,12 +745,20 @@ static int launch_mfp_unfused(mcrat_b200_ctx *ctx, int &nb)
 
 static int device_error(mcrat_b200_ctx *ctx)
 {
-    int e = ctx->gs_host->error;
-    if (e == MCRAT_B200_ERR_REPLAY) return fail(ctx, e, "replay uniform stream exhausted");
-    if (e == MCRAT_B200_ERR_TABLE)
-        return fail(ctx, e, "hot cross-section lookup outside the table (the reference would integrate by Monte Carlo here)");
-    if (e) return fail(ctx, e, "device-side error");
-    return MCRAT_B200_OK;
+    const int e = ctx->gs_host->error;
+    if (!e) return MCRAT_B200_OK;
+    static const char *const sites[] = {"?", "pass: optical depth", "pass: verified re-check skip", "finish: optical depth",
+                                        "calcMeanFreePath: optical depth", "calcMeanFreePath: replay stream",
+                                        "photonEvent: replay stream", "photonEvent: mini-pass optical depth",
+                                        "persistent loop: a block waited > 1 s for its team", "rebin", "cyclo-synchrotron emission"};
+    const int site = ctx->gs_host->error_site;
+    const char *what = e == MCRAT_B200_ERR_REPLAY ? "replay uniform stream exhausted"
+                       : e == MCRAT_B200_ERR_TABLE ? "hot cross-section lookup outside the table"
+                                                   : "device-side error";
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s (first raised in %s, photon slot %d)", what,
+             (site >= 0 && site < (int)(sizeof(sites) / sizeof(sites[0]))) ? sites[site] : "?", ctx->gs_host->error_slot);
+    return fail(ctx, e, buf);
 }
 
 __global__ void reset_loop_kernel(DevCtx d, int set_times, double time_now, double remaining, long long max_iters)

@@ -446,7 +446,7 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
             } else {
                 if (idx != -1) d.ph.idx[i] = -1; // Src/mclib.c:589-595
             }
-            if (skip && !inside) d.gs->error = MCRAT_B200_ERR_STATE; // verify mode: the bound was wrong
+            if (skip && !inside) raise_error(d.gs, MCRAT_B200_ERR_STATE, i, ERR_SITE_PASS_VERIFY); // verify mode: the bound was wrong
         }
         if (inside && FUSE_MFP) {
             // calcMeanFreePath, Src/mclib.c:657-687
@@ -456,7 +456,7 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
                 int terr = 0;
                 const double tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, d.ph.p1[i], d.ph.p2[i],
                                                  d.ph.p3[i], d.ph.c0[i], &terr);
-                if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
+                if (terr) raise_error(d.gs, MCRAT_B200_ERR_TABLE, i, ERR_SITE_PASS_TABLE);
                 store_tau(d.ph, i, tau);
                 ntau = -1.0 / tau;
                 d.ph.flags[i] = flags & ~F_RECALC;

@@ -316,7 +316,7 @@ __device__ __forceinline__ bool finish_one(DevCtx &d, ShardState &sh, const int 
         d.ph.c3[i] = pc[3];
         int terr = 0;
         double tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, p[1], p[2], p[3], pc[0], &terr);
-        if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
+        if (terr) raise_error(d.gs, MCRAT_B200_ERR_TABLE, i, ERR_SITE_FINISH_TABLE);
         store_tau(d.ph, i, tau);
         d.ph.flags[i] = d.ph.flags[i] & ~F_RECALC;
         if (sw == 0) atomicAdd((unsigned long long *)&sh.reloc_total, 1ull); // Src/mclib.c:579, 608-611
@@ -368,7 +368,7 @@ __global__ void mfp_scan_kernel(DevCtx d, int nblocks)
         }
         d.gs->replay_base = d.gs->replay_cursor;
         d.gs->replay_cursor += run;
-        if (d.gs->replay_cursor > d.gs->replay_n) d.gs->error = MCRAT_B200_ERR_REPLAY;
+        if (d.gs->replay_cursor > d.gs->replay_n) raise_error(d.gs, MCRAT_B200_ERR_REPLAY, -1, ERR_SITE_MFP_REPLAY);
     }
 }
 
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(256) mfp_kernel(DevCtx d, int write_blockmin)
             int terr = 0;
             tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, d.ph.r0[i], d.ph.r1[i], d.ph.p1[i], d.ph.p2[i],
                                 d.ph.p3[i], d.ph.c0[i], &terr);
-            if (terr) d.gs->error = MCRAT_B200_ERR_TABLE;
+            if (terr) raise_error(d.gs, MCRAT_B200_ERR_TABLE, i, ERR_SITE_MFP_TABLE);
             store_tau(d.ph, i, tau);
             d.ph.flags[i] = flags & ~F_RECALC;
         } else {

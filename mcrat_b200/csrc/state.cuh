@@ -103,6 +103,7 @@ static_assert(offsetof(ShardState, arrive) % 8 == 0, "ShardState: copied part mu
 struct GlobalState {
     int reloc_count[2];
     int error, not_found, n_stopped;
+    int error_slot, error_site; // photon slot (or -1) and ERR_SITE_* of the first error raised (raise_error)
     long long cell_evals, box_evals, max_iters;
     unsigned long long replay_cursor, replay_base, replay_n;
     int abs_count, cs_scatt_count;
@@ -129,6 +130,20 @@ struct GlobalState {
 #define TSTAMP_DECL
 #define TSTAMP(gsref, k)
 #endif
+
+// where a device-side error was raised (GlobalState.error_site)
+enum { ERR_SITE_NONE = 0, ERR_SITE_PASS_TABLE = 1, ERR_SITE_PASS_VERIFY = 2, ERR_SITE_FINISH_TABLE = 3, ERR_SITE_MFP_TABLE = 4,
+       ERR_SITE_MFP_REPLAY = 5, ERR_SITE_EVENT_REPLAY = 6, ERR_SITE_EVENT_MINIPASS = 7, ERR_SITE_LOOP_SPIN = 8,
+       ERR_SITE_REBIN = 9, ERR_SITE_CS_EMIT = 10 };
+
+// first error wins: many threads may fail in the same launch, the host reports the first one with its photon slot
+__device__ __forceinline__ void raise_error(GlobalState *gs, int code, int slot, int site)
+{
+    if (atomicCAS(&gs->error, 0, code) == 0) {
+        gs->error_slot = slot;
+        gs->error_site = site;
+    }
+}
 
 struct DevCtx {
     int dims, geom, stokes, tau_calc, cs, b_calc;

@@ -109,6 +109,12 @@ def oracle_lib():
         L.mc_oracle_free.argtypes = [C.c_void_p]
         L.mc_oracle_set_thermal_table.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.mc_oracle_set_log.argtypes = [C.c_void_p, C.c_char_p]
+        L.mc_oracle_set_iter.argtypes = [C.c_void_p, C.c_ulonglong]
+        L.mc_oracle_get_iter.restype = C.c_ulonglong
+        L.mc_oracle_get_iter.argtypes = [C.c_void_p]
+        L.mc_oracle_set_iter.argtypes = [C.c_void_p, C.c_ulonglong]
+        L.mc_oracle_get_iter.restype = C.c_ulonglong
+        L.mc_oracle_get_iter.argtypes = [C.c_void_p]
         for name in ("mc_bessel_Kn",):
             getattr(L, name).restype = C.c_double
         L.mc_bessel_Kn.argtypes = [C.c_int, C.c_double]
@@ -219,6 +225,13 @@ class Oracle:
             self.L.mc_oracle_free(self.o)
         except Exception:
             pass
+
+    def set_iter(self, it):
+        """Position of the keyed streams (while-loop iteration number of the next iteration)."""
+        self.L.mc_oracle_set_iter(self.o, C.c_ulonglong(it))
+
+    def get_iter(self):
+        return int(self.L.mc_oracle_get_iter(self.o))
 
     def set_table(self, table):
         t = np.ascontiguousarray(table, dtype=np.float64)

@@ -198,10 +198,10 @@ void mc_philox_doubles(const uint32_t ctr[4], const uint32_t key[2], double out[
 {
     uint32_t r[4];
     mc_philox4x32_10(ctr, key, r);
-    uint64_t a = (((uint64_t)r[0] << 32) | r[1]) >> 11; /* 53 bits */
-    uint64_t b = (((uint64_t)r[2] << 32) | r[3]) >> 11;
-    out[0] = ((double)a + 0.5) * (1.0 / 9007199254740992.0);
-    out[1] = ((double)b + 0.5) * (1.0 / 9007199254740992.0);
+    uint64_t a = (((uint64_t)r[0] << 32) | r[1]) >> 12; /* 52 bits: a + 0.5 is exact */
+    uint64_t b = (((uint64_t)r[2] << 32) | r[3]) >> 12;
+    out[0] = ((double)a + 0.5) * (1.0 / 4503599627370496.0);
+    out[1] = ((double)b + 0.5) * (1.0 / 4503599627370496.0);
 }
 
 /* ======================================================================== */

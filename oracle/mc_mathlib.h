@@ -52,7 +52,7 @@ unsigned long mc_ranlxs_get(mc_ranlxs_state *st); /* k in [0,2^24) */
 
 /* ---- Philox4x32-10 (counter-based; same function as the device RNG) ----- */
 void mc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-/* two doubles in (0,1) from one Philox block: ((53-bit int) + 0.5) * 2^-53 */
+/* two doubles in (0,1) from one Philox block: ((52-bit int) + 0.5) * 2^-52, exact, strictly inside (0,1) */
 void mc_philox_doubles(const uint32_t ctr[4], const uint32_t key[2], double out[2]);
 
 /* ---- generic RNG handle used by the oracle ------------------------------ */

@@ -50,6 +50,10 @@ void mc_oracle_free(mc_oracle *o)
     free(o);
 }
 
+/* position of the keyed (Philox) streams: the while-loop iteration number the next iteration draws with */
+void mc_oracle_set_iter(mc_oracle *o, unsigned long long iter) { o->iter = iter; }
+unsigned long long mc_oracle_get_iter(const mc_oracle *o) { return o->iter; }
+
 void mc_oracle_set_log(mc_oracle *o, const char *path)
 {
     if (o->log) fclose(o->log);

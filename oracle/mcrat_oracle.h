@@ -108,6 +108,8 @@ extern const double MC_C_LIGHT, MC_A_RAD, MC_PL_CONST, MC_K_B, MC_M_P, MC_THOM_X
 mc_oracle *mc_oracle_new(const mc_config *cfg);
 void mc_oracle_free(mc_oracle *o);
 void mc_oracle_set_log(mc_oracle *o, const char *path);
+void mc_oracle_set_iter(mc_oracle *o, unsigned long long iter);
+unsigned long long mc_oracle_get_iter(const mc_oracle *o);
 /* table[i*(N_T+1)+j], i over photon energy, j over temperature */
 void mc_oracle_set_thermal_table(mc_oracle *o, const double *table);
 int mc_sizeof_photon(void);

@@ -304,3 +304,68 @@ def test_klein_nishina_rejections_streamed_equals_persistent(nph, shards):
     assert a[1] == b[1] and a[2] == b[2] == 200
     for f in a[0].dtype.names:
         assert np.array_equal(a[0][f], b[0][f], equal_nan=a[0].dtype[f].kind == "f"), f
+
+
+@pytest.mark.parametrize("shards", [1, 3])
+def test_walks_longer_than_the_push_list_match_the_oracle(shards):
+    """photonEvent's walk over rejected candidates is unbounded in the reference (Src/mclib.c:1128-1339); the device
+    records 16 pushes per event and, when the list is full, applies them in place and goes on.  Photons of x = h nu / m c^2
+    ~ 50 are rejected 25 times in a row on average (sigma_KN / sigma_T ~ 0.04), so nearly every event overflows the list:
+    streamed loop == persistent loop bit for bit, and shard 0 == the oracle."""
+    cfg, hydro, photons, frame = synth.workload("C2", scale=1.0 / 16, n_photons=900 * shards, seed=23)
+    ph = photons.copy()
+    f = 50.0 * synth.M_EL * synth.C_LIGHT / ph["comv_p0"]
+    for k in ("p0", "p1", "p2", "p3", "comv_p0", "comv_p1", "comv_p2", "comv_p3"):
+        ph[k] *= f
+    out = {}
+    for mode in ("streamed", "persistent"):
+        hp = HotPath(cfg, seed=616, shard=2, num_shards=shards, loop_mode=mode)
+        hp.set_hydro(hydro)
+        hp.set_photons(ph)
+        st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=40, switch=1)
+        out[mode] = (st, hp.get_photons(), hp.shard_stats(0))
+        hp.close()
+    (sa, pa, _), (sb, pb, ss) = out["streamed"], out["persistent"]
+    assert sa["iterations"] == sb["iterations"] == 40 and sa["scatterings"] == sb["scatterings"]
+    for fld in pa.dtype.names:
+        assert np.array_equal(pa[fld], pb[fld], equal_nan=pa.dtype[fld].kind == "f"), fld
+    sl = slice(ss["first_slot"], ss["first_slot"] + ss["num_slots"])
+    o = api.Oracle(cfg)
+    o.set_hydro(hydro)
+    o.set_photons(ph[sl])
+    rng = api.OracleRng("philox", seed=616, shard=2)
+    ost = o.run_frame(rng, frame["time_now"], 1.0 / frame["fps"], max_iters=40, switch=1)
+    assert ss["scatterings"] == ost["scatterings"] and ss["iterations"] == ost["iterations"]
+    # every iteration draws (electron + 1) uniforms per candidate: far more than 17 candidates per event on average
+    assert rng.ndraws > 40 * 17 * 4, rng.ndraws
+    compare_photons(pb[sl], o.photons(), label="long walks", stokes_tol=1e-9, hydro=hydro)
+
+
+def test_a_new_list_layout_never_replays_a_stream():
+    """The Philox counters hold (slot, iteration): when set_photons lays the list out anew (injection, list growth) every
+    sub-shard continues from the largest iteration number reached so far, so no (key, counter) pair is ever used twice.
+    Checked against oracle ranks told to continue at that iteration."""
+    cfg, hydro, photons, frame = synth.workload("C2", scale=1.0 / 16, n_photons=2400, seed=29)
+    hp = HotPath(cfg, seed=31337, shard=40, num_shards=4)
+    hp.set_hydro(hydro)
+    hp.set_photons(photons[:2000])
+    st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=25, switch=1)
+    assert st["iterations"] == 25
+    first = hp.get_photons()
+    hp.set_photons(photons)  # 2400 photons: other slot ranges
+    assert hp.num_shards() == 4
+    st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=10, switch=1)
+    got = hp.get_photons()
+    for s in range(4):
+        ss = hp.shard_stats(s)
+        sl = slice(ss["first_slot"], ss["first_slot"] + ss["num_slots"])
+        o = api.Oracle(cfg)
+        o.set_hydro(hydro)
+        o.set_photons(photons[sl])
+        o.set_iter(25)
+        rng = api.OracleRng("philox", seed=31337, shard=40 + s)
+        ost = o.run_frame(rng, frame["time_now"], 1.0 / frame["fps"], max_iters=10, switch=1)
+        assert ss["scatterings"] == ost["scatterings"], (s, ss, ost)
+        compare_photons(got[sl], o.photons(), label="relayout shard %d" % s, stokes_tol=1e-9, hydro=hydro)
+    # and the draws of the second frame are not those of the first one (shards >= 1 used to restart at iteration 0)
+    assert not np.array_equal(first["time_to_scatter"][600:1100], got["time_to_scatter"][600:1100])
