@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MCRAT_B200_ABI_VERSION 1
+#define MCRAT_B200_ABI_VERSION 2
 
 /* reference codes, Src/mcrat.h:36-65 */
 enum { MCRAT_CARTESIAN = 0, MCRAT_SPHERICAL = 1, MCRAT_CYLINDRICAL = 2, MCRAT_POLAR = 3 };
@@ -107,6 +107,10 @@ typedef struct mcrat_b200_frame_stats {
     int cs_emitted;         /* pool photons replaced on the device (photonEmitCyclosynch, single mode) */
     int scatt_cyclosynch_num_ph;      /* running scatt_cyclosynch_num_ph, Src/mcrat.c:803 */
     double cs_comptonized_weight;     /* n_comptonized added in this call, Src/mcrat.c:794 */
+    long long ref_equiv_evals; /* checkInBlock calls the reference's early-exit loop (Src/geometry.c:356-370) would have made
+                                * for the photons re-located by full rescans in this call: first-hit index + 1 each, or
+                                * num_elements for a photon without a containing cell.  cell_evals counts what the device
+                                * executed (every photon x every cell for K1). */
 } mcrat_b200_frame_stats;
 
 typedef struct mcrat_b200_kernel_times {
@@ -228,6 +232,9 @@ int mcrat_b200_get_shard_stats(mcrat_b200_ctx *ctx, int shard, mcrat_b200_frame_
 
 /* ---- measurement ------------------------------------------------------------------------------ */
 int mcrat_b200_get_kernel_times(mcrat_b200_ctx *ctx, mcrat_b200_kernel_times *out, int reset);
+/* switch per-kernel-class timing (mcrat_b200_config.profile) on or off for the following calls; while it is on every
+ * launch is bracketed by CUDA events and the loop runs streamed */
+int mcrat_b200_set_profile(mcrat_b200_ctx *ctx, int on);
 /* number of kernels launched through this context so far */
 long long mcrat_b200_launch_count(const mcrat_b200_ctx *ctx);
 /* full photon x cell rescan only (the K1 kernel on the current list), for roofline timing */

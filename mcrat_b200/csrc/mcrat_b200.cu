@@ -74,6 +74,7 @@ struct mcrat_b200_ctx {
     int want_shards;    // sub-shards requested for the next set_photons
     int loop_mode;      // MCRAT_B200_LOOP_AUTO / _STREAMED / _PERSISTENT
     double cs_rebin_e_perc, cs_rebin_ang, cs_rebin_ang_phi; // CYCLOSYNCHROTRON_REBIN_E_PERC / _ANG / _ANG_PHI, Src/mcrat.h:308-322
+    int occ_scan[2];              // resident CTAs per SM of scan_kernel<0> / <1>
     int occ_loop256, occ_loop128; // resident blocks per SM of frame_loop_kernel<256>, frame_loop_solo_kernel<256> / <128>
     long long launches; // kernels launched through this context
     GlobalState *gs_host;          // pinned
@@ -210,6 +211,7 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
     ctx->cs_rebin_ang = 0.5;
     ctx->cs_rebin_ang_phi = 10;
     ctx->occ_loop256 = ctx->occ_loop128 = 0;
+    ctx->occ_scan[0] = ctx->occ_scan[1] = 0;
     ctx->launches = 0;
     ctx->replay_dev = nullptr;
     ctx->replay_cap = 0;
@@ -294,6 +296,10 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
         return bail(e, "cudaFuncSetAttribute");
     if ((e = cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(1))) != cudaSuccess)
         return bail(e, "cudaFuncSetAttribute");
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_scan[0], scan_kernel<0>, SCAN_THREADS, scan_smem_bytes(0))) != cudaSuccess)
+        return bail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_scan[1], scan_kernel<1>, SCAN_THREADS, scan_smem_bytes(1))) != cudaSuccess)
+        return bail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_loop256, frame_loop_kernel<256>, 256, 0)) != cudaSuccess)
         return bail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_loop128, frame_loop_solo_kernel<128>, 128, 0)) != cudaSuccess)
@@ -636,30 +642,32 @@ static int need_single_shard(mcrat_b200_ctx *ctx, const char *what)
     return MCRAT_B200_OK;
 }
 
-static void scan_grid(mcrat_b200_ctx *ctx, int nphot, dim3 &grid, int &tiles_per_chunk)
+// K1 is a persistent launch: as many CTAs as fit on the device, pulling (photon chunk, cell chunk) items from a
+// counter.  Items are sized for ~MCRAT_SCAN_ITEMS_PER_CTA items per resident CTA (the SMs run dry only during a CTA's
+// last item), between 4 and 64 tiles of cells each (an item re-loads its photons: 27 loads against >= 4 x 256 x 9 x 7
+// instructions).
+static void scan_grid(mcrat_b200_ctx *ctx, int nphot, int &grid, int &tiles_per_item)
 {
+    const int ndim3 = ctx->d.dims == D_THREE;
     const int ntiles = ctx->d.cells.n_padded / SCAN_TILE;
-    const int SCAN_P = (ctx->d.dims == D_THREE) ? SCAN_P3 : SCAN_P2;
-    int pchunks = (nphot + SCAN_THREADS * SCAN_P - 1) / (SCAN_THREADS * SCAN_P);
+    const int SCAN_P = ndim3 ? SCAN_P3 : SCAN_P2;
+    long long pchunks = ((long long)nphot + SCAN_THREADS * SCAN_P - 1) / (SCAN_THREADS * SCAN_P);
     if (pchunks < 1) pchunks = 1;
-    // enough cell chunks for ~32 CTAs per SM over the launch (measured best: short CTAs balance the
-    // 148 SMs better than long ones), each with >= 4 tiles
-    int want = (ctx->num_sms * MCRAT_SCAN_CTAS_PER_SM + pchunks - 1) / pchunks;
-    int maxc = ntiles / 4;
-    if (maxc < 1) maxc = 1;
-    int cchunks = want < maxc ? want : maxc;
-    if (cchunks < 1) cchunks = 1;
-    if (cchunks > 65535) cchunks = 65535;
-    tiles_per_chunk = (ntiles + cchunks - 1) / cchunks;
-    cchunks = (ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
-    grid = dim3(pchunks, cchunks, 1);
+    const int resident = ctx->num_sms * (ctx->occ_scan[ndim3] > 0 ? ctx->occ_scan[ndim3] : 1);
+    long long tpi = ((long long)ntiles * pchunks) / ((long long)MCRAT_SCAN_ITEMS_PER_CTA * resident);
+    if (tpi < 4) tpi = 4;
+    if (tpi > 64) tpi = 64;
+    if (tpi > ntiles) tpi = ntiles;
+    tiles_per_item = (int)tpi;
+    const long long items = pchunks * ((ntiles + tpi - 1) / tpi);
+    grid = (int)(items < resident ? items : resident);
+    if (grid < 1) grid = 1;
 }
 
 // full scan of the current relocation list with K1 (count known only on the device: sized for cap)
 static int launch_scan_full(mcrat_b200_ctx *ctx, int parity, int nphot_bound)
 {
-    dim3 grid;
-    int tpc;
+    int grid, tpc;
     scan_grid(ctx, nphot_bound, grid, tpc);
     Timed t(ctx, KC_SCAN);
     if (ctx->d.dims == D_THREE)
@@ -1173,6 +1181,7 @@ static void fill_stats(const ShardState &s, const ShardState &b, mcrat_b200_fram
     o->cs_emitted = 0;
     o->scatt_cyclosynch_num_ph = 0;
     o->cs_comptonized_weight = 0;
+    o->ref_equiv_evals = 0;
 }
 
 API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remaining_time, long long max_iters, int sw,
@@ -1278,6 +1287,7 @@ API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remain
     }
     stats->cell_evals = ctx->gs_host->cell_evals - gbefore.cell_evals;
     stats->box_evals = ctx->gs_host->box_evals - gbefore.box_evals;
+    stats->ref_equiv_evals = ctx->gs_host->ref_equiv_evals - gbefore.ref_equiv_evals;
     stats->not_found = ctx->gs_host->not_found - gbefore.not_found;
     stats->error = ctx->gs_host->error;
     stats->cs_emitted = ctx->gs_host->cs_emitted - gbefore.cs_emitted;
@@ -1334,6 +1344,14 @@ API int mcrat_b200_get_kernel_times(mcrat_b200_ctx *ctx, mcrat_b200_kernel_times
     return MCRAT_B200_OK;
 }
 
+API int mcrat_b200_set_profile(mcrat_b200_ctx *ctx, int on)
+{
+    if (!ctx) return MCRAT_B200_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->cfg.profile = on ? 1 : 0;
+    return MCRAT_B200_OK;
+}
+
 #ifdef MCRAT_TIMING
 API int mcrat_b200_debug_counters(mcrat_b200_ctx *ctx, long long *out32, int reset)
 {
@@ -1363,8 +1381,7 @@ API int mcrat_b200_rescan_all(mcrat_b200_ctx *ctx, long long *cell_evals, float 
     const int nbp = ctx->d.nshards * ctx->d.blocks_per_shard;
     pass_kernel<false><<<nbp, PASS_THREADS, 0, ctx->stream>>>(ctx->d, 1, parity);
     if (int rc = check_launch(ctx, "pass_kernel")) return rc;
-    dim3 grid;
-    int tpc;
+    int grid, tpc;
     scan_grid(ctx, ctx->d.cap, grid, tpc);
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     if (ctx->d.dims == D_THREE)

@@ -376,7 +376,7 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
         int idx = 0;
         unsigned long long safe = 0;
         double r0, r1, r2, v0, v1, v2, ntau;
-        if (!LOCAL_RELOC && d.stream_hints) {
+        if (d.stream_hints) {
             flags = __ldcs(d.ph.flags + i);
             if (may_skip) safe = __ldcs(d.ph.safe + i); else idx = __ldcs(d.ph.idx + i);
             r0 = __ldcs(d.ph.r0 + i); r1 = __ldcs(d.ph.r1 + i); r2 = __ldcs(d.ph.r2 + i);
@@ -391,7 +391,7 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
         }
         if (n_dt > 0 && (flags & F_MOVABLE) && i != pushed) {
             apply_pushes_v(sh, n_dt, v0, v1, v2, r0, r1, r2);
-            if (!LOCAL_RELOC && d.stream_hints) {
+            if (d.stream_hints) {
                 __stcs(d.ph.r0 + i, r0);
                 __stcs(d.ph.r1 + i, r1);
                 __stcs(d.ph.r2 + i, r2);
@@ -471,7 +471,7 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
 #endif
         }
         if (FUSE_MFP && have_t) {
-            if (!LOCAL_RELOC && d.stream_hints)
+            if (d.stream_hints)
                 __stcs(d.ph.tts + i, t);
             else
                 d.ph.tts[i] = t;
@@ -488,7 +488,10 @@ __global__ void __launch_bounds__(PASS_THREADS, MCRAT_PASS_MINB) pass_kernel(Dev
 {
     const int s = blockIdx.x / d.blocks_per_shard;
     const int b = blockIdx.x - s * d.blocks_per_shard;
-    if (blockIdx.x == 0 && threadIdx.x == 0) d.gs->reloc_count[parity ^ 1] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        d.gs->reloc_count[parity ^ 1] = 0;
+        d.gs->scan_work = 0;
+    }
     double best_t = DBL_MAX;
     int best_i = INT_MAX;
     if (!loop_stopped(*d.gs, d.sh[s]))

@@ -39,15 +39,77 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                  : "memory");
 }
 
-template <int NDIM3>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(DevCtx d, int parity, int tiles_per_chunk)
+// One photon-cell containment test, checkInBlock (Src/geometry.c:394-417) as |x - c| <= size / 2 per dimension.
+// Written in PTX so that it compiles to the minimum the FP64 pipe can do bit-equivalently -- one DADD (d = x - c) and
+// one DSETP (|d| <= h, |.| as a source modifier) per dimension, the DSETPs chained through their predicate operand --
+// plus ONE integer instruction, the predicated minimum that keeps the lowest containing index (first match wins,
+// Src/geometry.c:361-368).  From C++ the compiler emits three independent DSETP.GTU and combines them with an
+// unconditional VIMNMX and two SELs per test: 9 issue slots per 6 FP64-pipe instructions instead of 7.
+// NaN (padding cells, padding photons) compares false.
+__device__ __forceinline__ void scan_test2(double x0, double x1, const double4 &a, int cell, int &best)
 {
-    const GlobalState &gs = *d.gs;
+#if MCRAT_SCAN_PTX_TEST
+    const double d0 = x0 - a.x, d1 = x1 - a.y;
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .f64 e0, e1;\n\t"
+        "abs.f64 e0, %1;\n\t"
+        "abs.f64 e1, %2;\n\t"
+        "setp.le.f64 p, e0, %3;\n\t"
+        "setp.le.and.f64 p, e1, %4, p;\n\t"
+        "@p min.s32 %0, %0, %5;\n\t"
+        "}"
+        : "+r"(best)
+        : "d"(d0), "d"(d1), "d"(a.z), "d"(a.w), "r"(cell));
+#else
+    bool hit = (fabs(x0 - a.x) <= a.z) & (fabs(x1 - a.y) <= a.w);
+    if (hit) best = min(best, cell);
+#endif
+}
+
+__device__ __forceinline__ void scan_test3(double x0, double x1, double x2, const double4 &a, const double2 &b, int cell, int &best)
+{
+#if MCRAT_SCAN_PTX_TEST
+    const double d0 = x0 - a.x, d1 = x1 - a.y, d2 = x2 - a.z;
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .f64 e0, e1, e2;\n\t"
+        "abs.f64 e0, %1;\n\t"
+        "abs.f64 e1, %2;\n\t"
+        "abs.f64 e2, %3;\n\t"
+        "setp.le.f64 p, e0, %4;\n\t"
+        "setp.le.and.f64 p, e1, %5, p;\n\t"
+        "setp.le.and.f64 p, e2, %6, p;\n\t"
+        "@p min.s32 %0, %0, %7;\n\t"
+        "}"
+        : "+r"(best)
+        : "d"(d0), "d"(d1), "d"(d2), "d"(a.w), "d"(b.x), "d"(b.y), "r"(cell));
+#else
+    bool hit = (fabs(x0 - a.x) <= a.w) & (fabs(x1 - a.y) <= b.x) & (fabs(x2 - a.z) <= b.y);
+    if (hit) best = min(best, cell);
+#endif
+}
+
+// Work distribution: the launch is PERSISTENT -- as many CTAs as the device holds at once, each pulling work items
+// (photon chunk pc, cell chunk cc) from a counter in global memory until none is left.  An item is SCAN_THREADS x
+// SCAN_P photons against tiles_per_item tiles of SCAN_TILE cells.  A static grid of the same items left the last
+// wave of CTAs 40-60 % empty (4785 CTAs over 888 resident slots = 5.39 waves at 10^5 photons: a tenth of the
+// kernel's time with half of the SMs idle); with the counter the SMs run dry only during the last item of each CTA,
+// and items are sized so that this is <= 2-3 % of the kernel (scan_grid).  Items are numbered cell-chunk-major, so
+// the CTAs running at any moment stream the same few tiles out of L2.
+template <int NDIM3>
+__global__ void __launch_bounds__(SCAN_THREADS, NDIM3 ? MCRAT_SCAN_MINB3 : MCRAT_SCAN_MINB) scan_kernel(DevCtx d, int parity, int tiles_per_item)
+{
+    GlobalState &gs = *d.gs;
     if (gs.error != 0) return;
     constexpr int SCAN_P = NDIM3 ? SCAN_P3 : SCAN_P2;
+    constexpr int PCHUNK = SCAN_THREADS * SCAN_P;
     const int count = gs.reloc_count[parity];
-    const int pbase = blockIdx.x * (SCAN_THREADS * SCAN_P);
-    if (pbase >= count) return;
+    if (count <= 0) return;
+    const int pchunks = (count + PCHUNK - 1) / PCHUNK;
+    const int ntiles_total = d.cells.n_padded / SCAN_TILE;
+    const int cchunks = (ntiles_total + tiles_per_item - 1) / tiles_per_item;
+    const unsigned total_items = (unsigned)pchunks * (unsigned)cchunks;
 
     extern __shared__ __align__(128) unsigned char scan_smem[];
     constexpr uint32_t BYTES_A = SCAN_TILE * sizeof(double4);
@@ -55,75 +117,78 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(DevCtx d, int parity
     double4(*sA)[SCAN_TILE] = reinterpret_cast<double4(*)[SCAN_TILE]>(scan_smem);
     double2(*sB)[SCAN_TILE] = reinterpret_cast<double2(*)[SCAN_TILE]>(scan_smem + 2 * BYTES_A);
     uint64_t *bar = reinterpret_cast<uint64_t *>(scan_smem + 2 * BYTES_A + 2 * BYTES_B);
-
-    const int ntiles_total = d.cells.n_padded / SCAN_TILE;
-    const int tile0 = blockIdx.y * tiles_per_chunk;
-    const int ntiles = min(tiles_per_chunk, ntiles_total - tile0);
-    if (ntiles <= 0) return;
-
-    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-    double x0[SCAN_P], x1[SCAN_P], x2[SCAN_P];
-    int best[SCAN_P];
-#pragma unroll
-    for (int p = 0; p < SCAN_P; ++p) {
-        int j = pbase + p * SCAN_THREADS + threadIdx.x;
-        bool ok = j < count;
-        x0[p] = ok ? d.reloc_h0[j] : qnan;
-        x1[p] = ok ? d.reloc_h1[j] : qnan;
-        x2[p] = (ok && NDIM3) ? d.reloc_h2[j] : qnan;
-        best[p] = INT_MAX;
-    }
+    __shared__ unsigned sh_item;
 
     if (threadIdx.x == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(&bar[0], BYTES_A + BYTES_B);
-        tma_bulk_g2s(&sA[0][0], d.cells.geoA + (size_t)tile0 * SCAN_TILE, BYTES_A, &bar[0]);
-        if (NDIM3) tma_bulk_g2s(&sB[0][0], d.cells.geoB + (size_t)tile0 * SCAN_TILE, BYTES_B, &bar[0]);
-    }
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    unsigned g = 0; // tiles this CTA has consumed so far: stage = g & 1, mbarrier phase = (g >> 1) & 1
 
-    for (int t = 0; t < ntiles; ++t) {
-        const int s = t & 1;
-        if (threadIdx.x == 0 && t + 1 < ntiles) {
-            mbar_expect_tx(&bar[s ^ 1], BYTES_A + BYTES_B);
-            tma_bulk_g2s(&sA[s ^ 1][0], d.cells.geoA + (size_t)(tile0 + t + 1) * SCAN_TILE, BYTES_A, &bar[s ^ 1]);
-            if (NDIM3)
-                tma_bulk_g2s(&sB[s ^ 1][0], d.cells.geoB + (size_t)(tile0 + t + 1) * SCAN_TILE, BYTES_B, &bar[s ^ 1]);
+    for (;;) {
+        __syncthreads(); // sh_item of the previous item has been read by everyone; both stages are free
+        if (threadIdx.x == 0) sh_item = atomicAdd(&gs.scan_work, 1u);
+        __syncthreads();
+        const unsigned item = sh_item;
+        if (item >= total_items) break;
+        const int cc = (int)(item / (unsigned)pchunks), pc = (int)(item - (unsigned)cc * (unsigned)pchunks);
+        const int pbase = pc * PCHUNK;
+        const int tile0 = cc * tiles_per_item;
+        const int ntiles = min(tiles_per_item, ntiles_total - tile0);
+
+        if (threadIdx.x == 0) {
+            const int s0 = g & 1;
+            mbar_expect_tx(&bar[s0], BYTES_A + BYTES_B);
+            tma_bulk_g2s(&sA[s0][0], d.cells.geoA + (size_t)tile0 * SCAN_TILE, BYTES_A, &bar[s0]);
+            if (NDIM3) tma_bulk_g2s(&sB[s0][0], d.cells.geoB + (size_t)tile0 * SCAN_TILE, BYTES_B, &bar[s0]);
         }
-        mbar_wait(&bar[s], (uint32_t)((t >> 1) & 1));
-        const int cbase = (tile0 + t) * SCAN_TILE;
+        double x0[SCAN_P], x1[SCAN_P], x2[SCAN_P];
+        int best[SCAN_P];
+#pragma unroll
+        for (int p = 0; p < SCAN_P; ++p) {
+            int j = pbase + p * SCAN_THREADS + threadIdx.x;
+            bool ok = j < count;
+            x0[p] = ok ? d.reloc_h0[j] : qnan;
+            x1[p] = ok ? d.reloc_h1[j] : qnan;
+            x2[p] = (ok && NDIM3) ? d.reloc_h2[j] : qnan;
+            best[p] = INT_MAX;
+        }
+
+        for (int t = 0; t < ntiles; ++t, ++g) {
+            const int s = g & 1;
+            if (threadIdx.x == 0 && t + 1 < ntiles) {
+                mbar_expect_tx(&bar[s ^ 1], BYTES_A + BYTES_B);
+                tma_bulk_g2s(&sA[s ^ 1][0], d.cells.geoA + (size_t)(tile0 + t + 1) * SCAN_TILE, BYTES_A, &bar[s ^ 1]);
+                if (NDIM3)
+                    tma_bulk_g2s(&sB[s ^ 1][0], d.cells.geoB + (size_t)(tile0 + t + 1) * SCAN_TILE, BYTES_B, &bar[s ^ 1]);
+            }
+            mbar_wait(&bar[s], (g >> 1) & 1u);
+            const int cbase = (tile0 + t) * SCAN_TILE;
 _Pragma(MCRAT_PRAGMA_STR(unroll MCRAT_SCAN_UNROLL))
-        for (int c = 0; c < SCAN_TILE; ++c) {
-            const double4 a = sA[s][c];
-            if (!NDIM3) {
+            for (int c = 0; c < SCAN_TILE; ++c) {
+                const double4 a = sA[s][c];
+                if (!NDIM3) {
 #pragma unroll
-                for (int p = 0; p < SCAN_P; ++p) {
-                    bool hit = (fabs(x0[p] - a.x) <= a.z) & (fabs(x1[p] - a.y) <= a.w);
-                    if (hit) best[p] = min(best[p], cbase + c);
-                }
-            } else {
-                const double2 b = sB[s][c];
+                    for (int p = 0; p < SCAN_P; ++p) scan_test2(x0[p], x1[p], a, cbase + c, best[p]);
+                } else {
+                    const double2 b = sB[s][c];
 #pragma unroll
-                for (int p = 0; p < SCAN_P; ++p) {
-                    bool hit = (fabs(x0[p] - a.x) <= a.w) & (fabs(x1[p] - a.y) <= b.x) & (fabs(x2[p] - a.z) <= b.y);
-                    if (hit) best[p] = min(best[p], cbase + c);
+                    for (int p = 0; p < SCAN_P; ++p) scan_test3(x0[p], x1[p], x2[p], a, b, cbase + c, best[p]);
                 }
             }
+            __syncthreads(); // everyone is done with stage s before it is refilled two tiles later
         }
-        __syncthreads(); // everyone is done with stage s before it is refilled at t+2
-    }
 #pragma unroll
-    for (int p = 0; p < SCAN_P; ++p) {
-        int j = pbase + p * SCAN_THREADS + threadIdx.x;
-        if (best[p] != INT_MAX && j < count) atomicMin(&d.reloc_best[j], best[p]);
-    }
-    if (threadIdx.x == 0 && blockIdx.y == 0) {
-        int nph = min(count - pbase, SCAN_THREADS * SCAN_P);
-        atomicAdd((unsigned long long *)&d.gs->cell_evals, (unsigned long long)nph * (unsigned long long)d.cells.n);
+        for (int p = 0; p < SCAN_P; ++p) {
+            int j = pbase + p * SCAN_THREADS + threadIdx.x;
+            if (best[p] != INT_MAX && j < count) atomicMin(&d.reloc_best[j], best[p]);
+        }
+        if (threadIdx.x == 0 && cc == 0) {
+            int nph = min(count - pbase, PCHUNK);
+            atomicAdd((unsigned long long *)&d.gs->cell_evals, (unsigned long long)nph * (unsigned long long)d.cells.n);
+        }
     }
 }
 
@@ -337,12 +402,20 @@ __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(DevCtx d, int sw, i
     if (gs.error != 0) return;
     const int count = gs.reloc_count[parity];
     int missing = 0;
+    long long ref_evals = 0; // the reference's loop stops at the first hit (Src/geometry.c:361-368)
     for (int j = blockIdx.x * FIN_THREADS + threadIdx.x; j < count; j += gridDim.x * FIN_THREADS)
     {
         const int i = d.reloc_slot[j], s = shard_of(d, i);
-        if (finish_one<FUSE_MFP>(d, d.sh[s], s, i, d.reloc_best[j], sw)) missing++;
+        const int best = d.reloc_best[j];
+        if (sw == 1) ref_evals += (best == INT_MAX) ? d.cells.n : best + 1;
+        if (finish_one<FUSE_MFP>(d, d.sh[s], s, i, best, sw)) missing++;
     }
     if (missing) atomicAdd(&d.gs->not_found, missing);
+    if (sw == 1) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) ref_evals += __shfl_xor_sync(0xffffffffu, ref_evals, off);
+        if ((threadIdx.x & 31) == 0 && ref_evals) atomicAdd((unsigned long long *)&d.gs->ref_equiv_evals, (unsigned long long)ref_evals);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

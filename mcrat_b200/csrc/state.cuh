@@ -14,11 +14,12 @@ constexpr int PERSISTENT_MAX_PHOTONS = 1 << 21; // above this the list no longer
 #ifndef MCRAT_SCAN_THREADS
 #define MCRAT_SCAN_THREADS 128
 #endif
-// photons per thread: 7 in 2-D (10^5 photons x 2^20 cells: 24.87 ms = 98.9 % of the measured DFMA issue rate, against
-// 25.84 ms / 95.3 % with 8 and 25.54 ms with 6), 9 in 3-D (39.85 ms = 92.6 %; 6 / 7 / 8 / 10 / 11 / 12 / 13 photons:
-// 41.52 / 41.20 / 41.03 / 41.21 / 40.17 / 41.15 / 40.17 ms -- the grid's last wave decides)
+// photons per thread / resident CTAs per SM (round 2, persistent work-counter launch + PTX containment test; 10^5
+// photons x 2^20 cells, CUDA events; % = of 148 SMs x 64 FP64 lanes x 1965 MHz): 3-D 9 / 5: 35.34 ms = 95.6 % (10^6
+// photons: 96.0 %), 9 / 6: 35.48, 8 / 6: 35.73, 7 / 7: 37.06, 12 / 4: 35.41 (10^6: 96.9 %); 2-D 8 / 6: 23.95 ms = 94.1 %,
+// 7 / 5: 24.01, 7 / 6: 24.45, 6 / 7: 24.29, 12 / 4: 24.11.  Round 1 (static grid, C++ test): 3-D 39.85 ms, 2-D 24.89 ms.
 #ifndef MCRAT_SCAN_P
-#define MCRAT_SCAN_P 7
+#define MCRAT_SCAN_P 8
 #endif
 #ifndef MCRAT_SCAN_P3
 #define MCRAT_SCAN_P3 9
@@ -29,8 +30,18 @@ constexpr int PERSISTENT_MAX_PHOTONS = 1 << 21; // above this the list no longer
 #ifndef MCRAT_SCAN_UNROLL
 #define MCRAT_SCAN_UNROLL 8
 #endif
-#ifndef MCRAT_SCAN_CTAS_PER_SM
-#define MCRAT_SCAN_CTAS_PER_SM 32
+#ifndef MCRAT_SCAN_ITEMS_PER_CTA
+#define MCRAT_SCAN_ITEMS_PER_CTA 40 // work items per resident CTA the scan is cut into (tail <= 1 / this)
+#endif
+#ifndef MCRAT_SCAN_MINB
+#define MCRAT_SCAN_MINB 6 // 2-D: resident CTAs per SM the register allocation aims at
+#endif
+#ifndef MCRAT_SCAN_MINB3
+#define MCRAT_SCAN_MINB3 5 // 3-D
+#endif
+// 1: the containment test is written in PTX (chained DSETP + one predicated minimum); 0: plain C++ (A/B)
+#ifndef MCRAT_SCAN_PTX_TEST
+#define MCRAT_SCAN_PTX_TEST 1
 #endif
 #define MCRAT_PRAGMA_STR2(x) #x
 #define MCRAT_PRAGMA_STR(x) MCRAT_PRAGMA_STR2(x)
@@ -103,8 +114,10 @@ static_assert(offsetof(ShardState, arrive) % 8 == 0, "ShardState: copied part mu
 struct GlobalState {
     int reloc_count[2];
     int error, not_found, n_stopped;
+    unsigned int scan_work; // K1: next work item (photon chunk, cell chunk); zeroed by the pass kernel that feeds the scan
     int error_slot, error_site; // photon slot (or -1) and ERR_SITE_* of the first error raised (raise_error)
     long long cell_evals, box_evals, max_iters;
+    long long ref_equiv_evals; // first-hit index + 1 summed over the photons of full rescans (what the reference's loop executes)
     unsigned long long replay_cursor, replay_base, replay_n;
     int abs_count, cs_scatt_count;
     double abs_weight;

@@ -20,7 +20,7 @@ DROPIN_PATH = os.path.join(CSRC, "libmcrat_b200_dropin.so")
 HYDRO_FIELDS = ["r0", "r1", "r2", "r0_size", "r1_size", "r2_size", "r", "theta", "v0", "v1", "v2",
                 "dens", "dens_lab", "pres", "temp", "gamma", "B0", "B1", "B2"]
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 RNG_PHILOX, RNG_REPLAY = 0, 1
 LOOP_MODES = {"auto": 0, "streamed": 1, "persistent": 2}
 
@@ -46,7 +46,8 @@ class FrameStats(C.Structure):
                 ("time_now", C.c_double),
                 ("last_time_step", C.c_double), ("last_scattered_index", C.c_int), ("not_found", C.c_int),
                 ("cs_host_pending", C.c_int), ("error", C.c_int), ("cs_emitted", C.c_int),
-                ("scatt_cyclosynch_num_ph", C.c_int), ("cs_comptonized_weight", C.c_double)]
+                ("scatt_cyclosynch_num_ph", C.c_int), ("cs_comptonized_weight", C.c_double),
+                ("ref_equiv_evals", C.c_longlong)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -72,7 +73,7 @@ EXPORTS = [
     "mcrat_b200_average_photon_energy", "mcrat_b200_run_frame", "mcrat_b200_set_loop_mode",
     "mcrat_b200_rebin_cyclosynch_comp_photons", "mcrat_b200_set_cs_rebin_params", "mcrat_b200_get_kernel_times",
     "mcrat_b200_launch_count", "mcrat_b200_rescan_all", "mcrat_b200_measure_fp64_peak", "mcrat_b200_measure_hbm_peak",
-    "mcrat_b200_selftest_div_by_c", "mcrat_b200_set_recheck_skip",
+    "mcrat_b200_selftest_div_by_c", "mcrat_b200_set_recheck_skip", "mcrat_b200_set_profile",
 ]
 
 
@@ -312,6 +313,9 @@ class HotPath:
         t = KernelTimes()
         self._ck(self.L.mcrat_b200_get_kernel_times(self.ctx, C.byref(t), C.c_int(1 if reset else 0)))
         return t.as_dict()
+
+    def set_profile(self, on):
+        self._ck(self.L.mcrat_b200_set_profile(self.ctx, C.c_int(1 if on else 0)))
 
     def rescan_all(self):
         ev, ms = C.c_longlong(0), C.c_float(0)

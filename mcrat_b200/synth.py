@@ -312,6 +312,13 @@ def make_photons(h, n, r_range, theta_range, seed=1234, weight=1e50, phi_range=(
     return out
 
 
+def locate_photons(h, photons):
+    """Containing cell of every photon on the structured grids of make_grid (-1 outside the domain).  Input
+    preparation only: lets a bounded CPU sample start from located photons without a full photon x cell scan."""
+    hc0, hc1, hc2 = mcrat_to_hydro(h["dimensions"], h["geometry"], photons["r0"], photons["r1"], photons["r2"])
+    return locate_cells(h, hc0, hc1, hc2).astype(np.int32)
+
+
 # ---------------------------------------------------------------------------------------
 # named workloads (BASELINE.json configs; SURVEY.md section 8d)
 # ---------------------------------------------------------------------------------------

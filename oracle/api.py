@@ -352,19 +352,29 @@ class Oracle:
 # --------------------------------------------------------------------------------------
 # reference sources (oracle/_ref)
 # --------------------------------------------------------------------------------------
-def ref_lib_path(name):
-    return os.path.join(HERE, "_ref", "libmcrat_ref_%s.so" % name)
+def ref_lib_path(name, timing=False):
+    """timing=True: the -O3 -march=x86-64-v3 build of the same sources (bench.py's CPU arm only; see build_ref.py)."""
+    return os.path.join(HERE, "_ref", "libmcrat_ref_%s%s.so" % (name, "_o3" if timing else ""))
 
 
-def ref_available(name):
-    return os.path.exists(ref_lib_path(name))
+def ref_available(name, timing=False):
+    return os.path.exists(ref_lib_path(name, timing))
+
+
+def host_runs_timing_build():
+    """The timing build needs AVX2 and FMA (x86-64-v3)."""
+    try:
+        flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags")).split()
+    except Exception:
+        return False
+    return all(f in flags for f in ("avx2", "fma", "bmi2", "movbe"))
 
 
 class RefLib:
     """One compile-time configuration of the reference's own sources."""
 
-    def __init__(self, name):
-        path = ref_lib_path(name)
+    def __init__(self, name, timing=False):
+        path = ref_lib_path(name, timing)
         if not os.path.exists(path):
             raise FileNotFoundError(path)
         self.name = name

@@ -15,8 +15,17 @@ symlinks to ``/root/reference/Src/*`` is created so that the per-configuration
 ``mcrat_input.h`` (generated, #define-only) shadows the reference's own, and is
 removed afterwards.  Outputs go only to oracle/_ref/ (git-ignored).
 
-Flags: ``gcc -O2 -std=gnu11 -fopenmp`` and no ``-march``, i.e. plain x86-64
-without FMA contraction, matching the reference's default Makefile arithmetic.
+Two variants per configuration:
+
+* parity  (``libmcrat_ref_<cfg>.so``): ``gcc -O2 -std=gnu11 -fopenmp -ffp-contract=off`` and no ``-march``,
+  i.e. plain x86-64 without FMA contraction, matching the reference's default Makefile arithmetic.  Every
+  parity test and golden fixture uses this one.
+* timing  (``libmcrat_ref_<cfg>_o3.so``, only for the configurations bench.py times): ``gcc -O3
+  -march=x86-64-v3 -fopenmp`` -- AVX2 + FMA with contraction allowed, the fastest arithmetic the
+  reference's own sources can be given.  BASELINE.md asks for ``-march=native``; the library is built in the
+  build container and travels to the GPU box prebuilt (the reference sources do not exist there), so the
+  instruction set has to be one every x86-64 server CPU of the last decade runs: x86-64-v3.  bench.py checks
+  ``/proc/cpuinfo`` for avx2 / fma before loading it and says which build was timed.
 """
 import os
 import shutil
@@ -33,15 +42,17 @@ OUT = os.path.join(HERE, "_ref")
 HOT_TUS = ["mclib.c", "optical_depth.c", "mcrat_scattering.c", "electron.c", "hot_x_section.c",
            "geometry.c", "photons.c", "mc_cyclosynch.c", "analytic_outflows.c"]
 CFLAGS = ["-O2", "-std=gnu11", "-fopenmp", "-fPIC", "-w", "-fno-strict-aliasing", "-ffp-contract=off"]
+CFLAGS_TIMING = ["-O3", "-march=x86-64-v3", "-std=gnu11", "-fopenmp", "-fPIC", "-w", "-fno-strict-aliasing"]
+TIMING_CONFIGS = ("c2_2d_cyl_stokes", "c5_3d_sph")  # the workloads bench.py's CPU arm runs
 
 
 def available():
     return os.path.isdir(REF_SRC)
 
 
-def build_one(name, cfg, force=False):
+def build_one(name, cfg, force=False, timing=False):
     os.makedirs(OUT, exist_ok=True)
-    lib = os.path.join(OUT, "libmcrat_ref_%s.so" % name)
+    lib = os.path.join(OUT, "libmcrat_ref_%s%s.so" % (name, "_o3" if timing else ""))
     deps = [os.path.join(HERE, "ref_harness.c"), os.path.join(HERE, "gsl_shim", "gsl_shim.c"),
             os.path.join(HERE, "mc_mathlib.c"), os.path.join(HERE, "mc_mathlib.h"),
             os.path.join(HERE, "gsl_shim", "gsl", "gsl_shim_all.h"), os.path.join(HERE, "configs.py"),
@@ -59,7 +70,7 @@ def build_one(name, cfg, force=False):
         os.symlink(os.path.join(HERE, "ref_harness.c"), os.path.join(farm, "ref_harness.c"))
         srcs = [os.path.join(farm, f) for f in HOT_TUS + ["ref_harness.c"]]
         srcs += [os.path.join(HERE, "gsl_shim", "gsl_shim.c"), os.path.join(HERE, "mc_mathlib.c")]
-        cmd = ["gcc"] + CFLAGS + ["-shared", "-o", lib, "-I", farm, "-I", os.path.join(HERE, "gsl_shim"),
+        cmd = ["gcc"] + (CFLAGS_TIMING if timing else CFLAGS) + ["-shared", "-o", lib, "-I", farm, "-I", os.path.join(HERE, "gsl_shim"),
                                   "-I", HERE] + srcs + ["-lm"]
         subprocess.check_call(cmd)
     finally:
@@ -79,6 +90,10 @@ def build_all(names=None, force=False, verbose=True):
         libs.append(build_one(name, cfg, force=force))
         if verbose:
             print("build_ref: %s" % libs[-1])
+        if name in TIMING_CONFIGS:
+            libs.append(build_one(name, cfg, force=force, timing=True))
+            if verbose:
+                print("build_ref: %s" % libs[-1])
     return libs
 
 
