@@ -215,15 +215,22 @@ int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remaining_
  * mode 0: never skip; 1 (default): skip; 2: decide as in 1 but re-check anyway and fail the frame with
  * MCRAT_B200_ERR_STATE if a skipped photon had left its cell (test mode). */
 int mcrat_b200_set_recheck_skip(mcrat_b200_ctx *ctx, int mode);
-/* How the loop is driven.  STREAMED: four stream-ordered kernel launches per iteration (pass, re-locate,
- * finish, event), enqueued in growing batches.  PERSISTENT: one cooperative launch per frame; every
- * sub-shard is iterated by resident blocks that hand over through a generation word in global memory
- * (no launch boundary inside the loop; sub-shards advance independently, like MPI ranks).  AUTO
- * (default): PERSISTENT while the list fits in L2 (<= 2^21 photons), STREAMED above.  Both give
- * bit-identical photons; the replay harness and profile = 1 always use STREAMED. */
+/* How the loop is driven.
+ * STREAMED: stream-ordered kernel launches per iteration, enqueued in growing batches.  With two or more sub-shards
+ *   an iteration is two launches per half of the sub-shards (pass; re-locate + event), the halves on two streams half a
+ *   period apart, so that one half's scattering events run beside the other half's pass and the HBM pipe never waits
+ *   for a scattering.  New hydro frames (everything re-locates) and optically thin flows (many photons change cell per
+ *   iteration) go through the grid-wide re-location kernels: pass, K1 / K1b / K1c, finish, event.
+ * PERSISTENT: one cooperative launch per frame; every sub-shard is iterated by resident blocks that hand over through
+ *   a generation word in global memory (no launch boundary inside the loop).
+ * AUTO (default): PERSISTENT while the list fits in L2 (<= 2^21 photons), STREAMED above.
+ * In all of them sub-shards advance independently, like MPI ranks, and the photons are bit-identical; the replay
+ * harness always runs STREAMED_GLOBAL. */
 #define MCRAT_B200_LOOP_AUTO 0
 #define MCRAT_B200_LOOP_STREAMED 1
 #define MCRAT_B200_LOOP_PERSISTENT 2
+#define MCRAT_B200_LOOP_STREAMED_GLOBAL 3 /* streamed, every iteration through the grid-wide re-location kernels (four launches;
+                                          * what STREAMED falls back to for new hydro frames and optically thin flows) */
 int mcrat_b200_set_loop_mode(mcrat_b200_ctx *ctx, int mode);
 
 /* per-sub-shard view of the counters (cumulative since the shard layout was set) and its slot range */

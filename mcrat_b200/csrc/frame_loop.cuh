@@ -244,6 +244,44 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_so
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Streamed loop for lists larger than L2, two launches per iteration and half of the sub-shards:
+//   pass_local_kernel   the fused pass over the shards [shard0, shard0 + n) (photons that left their cell go to the
+//                       shard's own region of the relocation list, as in the persistent loop)
+//   event_local_kernel  one block per shard: re-locate those few photons through the bounding-box index (one warp per
+//                       photon), finish them, shard arg-min, scattering event
+// The host puts the two halves of the shards on two streams, half a period apart: while the blocks of one half run
+// their events (latency-bound, 64 KB of registers per SM left free for them) the other half's pass streams its
+// photons through the SMs, so the HBM pipe never waits for a scattering (mcrat_b200_run_frame).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PASS_THREADS, MCRAT_PASS_MINB) pass_local_kernel(DevCtx d, const int shard0, const int bps)
+{
+    const int s = shard0 + blockIdx.x / bps;
+    const int b = blockIdx.x - (blockIdx.x / bps) * bps;
+    double best_t = DBL_MAX;
+    int best_i = INT_MAX;
+    if (!loop_stopped(*d.gs, d.sh[s])) pass_body<true, true, PASS_THREADS>(d, d.sh[s], s, b, bps, 0, 0, best_t, best_i);
+    block_argmin<PASS_THREADS>(best_t, best_i);
+    if (threadIdx.x == 0) {
+        d.bm_t[s * bps + b] = best_t;
+        d.bm_i[s * bps + b] = best_i;
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) event_local_kernel(DevCtx d, const int shard0, const int bps)
+{
+    const int s = shard0 + blockIdx.x;
+    ShardState &st = d.sh[s];
+    if (loop_stopped(*d.gs, st)) return;
+    const int R = *(volatile int *)&st.reloc_n;
+    if (R > 0) {
+        relocate_shard<THREADS>(d, st, s, R);
+        if (threadIdx.x == 0 && R > RELOC_HEAVY) d.gs->reloc_heavy_any = 1; // the host hands the next batch to K1b / K1c
+    }
+    event_body<THREADS>(d, s, st.first, R, bps, 0, 0.0, st);
+}
+
 // head of the time order only (step API calcMeanFreePath; single shard)
 __global__ void __launch_bounds__(EVT_THREADS) head_kernel(DevCtx d, int nb)
 {

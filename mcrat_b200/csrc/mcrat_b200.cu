@@ -61,6 +61,8 @@ struct mcrat_b200_ctx {
     DevCtx d;
     cudaStream_t stream;
     bool own_stream;
+    cudaStream_t stream2;          // second stream of the interleaved streamed loop (the other half of the sub-shards)
+    cudaEvent_t ev_pass[2], ev_join; // pass of half h has finished; stream2 has drained
     int num_sms;
     std::string err;
     // device allocations
@@ -234,6 +236,10 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
         if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
         ctx->own_stream = true;
     }
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    for (int k = 0; k < 2; ++k)
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_pass[k], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaMallocHost((void **)&ctx->gs_host, sizeof(GlobalState))) != cudaSuccess) return bail(e, "cudaMallocHost");
@@ -326,6 +332,11 @@ API void mcrat_b200_destroy(mcrat_b200_ctx *ctx)
     if (ctx->gs_host) cudaFreeHost(ctx->gs_host);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    cudaStreamSynchronize(ctx->stream2);
+    cudaEventDestroy(ctx->ev_pass[0]);
+    cudaEventDestroy(ctx->ev_pass[1]);
+    cudaEventDestroy(ctx->ev_join);
+    cudaStreamDestroy(ctx->stream2);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -791,6 +802,7 @@ __global__ void reset_loop_kernel(DevCtx d, int set_times, double time_now, doub
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         d.gs->max_iters = max_iters;
         d.gs->n_stopped = 0;
+        d.gs->reloc_heavy_any = 0;
     }
 }
 
@@ -1158,7 +1170,8 @@ API int mcrat_b200_set_recheck_skip(mcrat_b200_ctx *ctx, int mode)
 API int mcrat_b200_set_loop_mode(mcrat_b200_ctx *ctx, int mode)
 {
     if (!ctx) return MCRAT_B200_ERR_ARG;
-    if (mode != MCRAT_B200_LOOP_AUTO && mode != MCRAT_B200_LOOP_STREAMED && mode != MCRAT_B200_LOOP_PERSISTENT)
+    if (mode != MCRAT_B200_LOOP_AUTO && mode != MCRAT_B200_LOOP_STREAMED && mode != MCRAT_B200_LOOP_PERSISTENT &&
+        mode != MCRAT_B200_LOOP_STREAMED_GLOBAL)
         return fail(ctx, MCRAT_B200_ERR_ARG, "set_loop_mode: unknown mode");
     ctx->loop_mode = mode;
     return MCRAT_B200_OK;
@@ -1217,6 +1230,54 @@ API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remain
         sw = 0; // Src/mcrat.c:773
         return MCRAT_B200_OK;
     };
+    // Streamed loop, interleaved halves (see frame_loop.cuh): the shards [0, S/2) run on the context's stream, the shards
+    // [S/2, S) on a second one; the pass of a half waits for the other half's pass (so the two passes never share the HBM
+    // pipe and the halves stay half a period apart) and, through stream order, for its own half's event.
+    const bool local_ok = fused && !ctx->d.cs && S >= 2 && ctx->loop_mode != MCRAT_B200_LOOP_STREAMED_GLOBAL;
+    const int nsh[2] = {S - S / 2, S / 2}, sh0[2] = {0, S - S / 2};
+    int bps_local[2];
+    for (int h = 0; h < 2; ++h) {
+        int b = (MCRAT_PASS_LOCAL_CTAS_PER_SM * ctx->num_sms) / (nsh[h] > 0 ? nsh[h] : 1);
+        const int need = (ctx->d.shard_size + PASS_THREADS - 1) / PASS_THREADS;
+        if (b > need) b = need;
+        if (b > BLOCKMIN_CAP / S) b = BLOCKMIN_CAP / S;
+        if (b < 1) b = 1;
+        bps_local[h] = b;
+    }
+    if (bps_local[1] < bps_local[0]) bps_local[0] = bps_local[1]; // one layout of the block minima for both halves
+    bps_local[1] = bps_local[0];
+    auto local_iterations = [&](long long count) -> int {
+        const bool serial = ctx->cfg.profile != 0; // per-kernel timing: everything on one stream
+        cudaStream_t st[2] = {ctx->stream, serial ? ctx->stream : ctx->stream2};
+        if (!serial) {
+            CK(cudaEventRecord(ctx->ev_join, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_join, 0));
+            CK(cudaEventRecord(ctx->ev_pass[1], ctx->stream2)); // "the other half's pass is done" for the very first pass
+        }
+        for (long long it = 0; it < count; ++it)
+            for (int h = 0; h < 2; ++h) {
+                if (!serial) CK(cudaStreamWaitEvent(st[h], ctx->ev_pass[h ^ 1], 0));
+                {
+                    Timed t(ctx, KC_PASS);
+                    pass_local_kernel<<<nsh[h] * bps_local[h], PASS_THREADS, 0, st[h]>>>(ctx->d, sh0[h], bps_local[h]);
+                    if (int rc = check_launch(ctx, "pass_local_kernel")) return rc;
+                }
+                if (!serial) CK(cudaEventRecord(ctx->ev_pass[h], st[h]));
+                {
+                    Timed t(ctx, KC_EVENT);
+                    if (nsh[h] >= 32)
+                        event_local_kernel<EVT_THREADS_MANY><<<nsh[h], EVT_THREADS_MANY, 0, st[h]>>>(ctx->d, sh0[h], bps_local[h]);
+                    else
+                        event_local_kernel<EVT_THREADS><<<nsh[h], EVT_THREADS, 0, st[h]>>>(ctx->d, sh0[h], bps_local[h]);
+                    if (int rc = check_launch(ctx, "event_local_kernel")) return rc;
+                }
+            }
+        if (!serial) {
+            CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        }
+        return MCRAT_B200_OK;
+    };
     bool persistent = fused && !ctx->cfg.profile &&
                       (ctx->loop_mode == MCRAT_B200_LOOP_PERSISTENT ||
                        (ctx->loop_mode == MCRAT_B200_LOOP_AUTO && ctx->d.cap <= PERSISTENT_MAX_PHOTONS));
@@ -1260,14 +1321,21 @@ API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remain
         // iterations are enqueued in batches; kernels of a shard past its stop condition return at once
         int batch = 1;
         long long launched = streamed_done;
+        bool heavy = false; // many photons change cell per iteration: the grid-wide K1b / K1c serve that better
         for (;;) {
-            for (int b = 0; b < batch; ++b) {
-                if (int rc = streamed_iteration()) return rc;
-                launched++;
+            if (local_ok && sw == 0 && !heavy) {
+                if (int rc = local_iterations(batch)) return rc;
+                launched += batch;
+            } else {
+                for (int b = 0; b < batch; ++b) {
+                    if (int rc = streamed_iteration()) return rc;
+                    launched++;
+                }
             }
             if (int rc = fetch_global(ctx)) return rc;
             const GlobalState &g = *ctx->gs_host;
             if (g.error || g.n_stopped >= S) break;
+            if (g.reloc_heavy_any) heavy = true;
             if (batch < 64) batch *= 2;
             if (max_iters >= 0 && launched + batch > max_iters) batch = (int)(max_iters - launched);
             if (batch < 1) batch = 1;

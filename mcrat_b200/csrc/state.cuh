@@ -49,6 +49,9 @@ constexpr int SCAN_THREADS = MCRAT_SCAN_THREADS;
 constexpr int SCAN_P2 = MCRAT_SCAN_P;      // photons per thread held in registers, 2-D
 constexpr int SCAN_P3 = MCRAT_SCAN_P3;     // ... 3-D
 constexpr int SCAN_TILE = MCRAT_SCAN_TILE; // cells per shared-memory stage
+#ifndef MCRAT_PASS_LOCAL_CTAS_PER_SM
+#define MCRAT_PASS_LOCAL_CTAS_PER_SM 4 // pass blocks per SM of the interleaved streamed loop: leaves room for one event block
+#endif
 constexpr int FEW_RMAX = 128;  // relocating photons handled per pass of the cell-parallel scan
 constexpr int RELOC_LIST_SCAN_MAX = 2048;
 
@@ -114,6 +117,7 @@ static_assert(offsetof(ShardState, arrive) % 8 == 0, "ShardState: copied part mu
 struct GlobalState {
     int reloc_count[2];
     int error, not_found, n_stopped;
+    int reloc_heavy_any;    // streamed loop (local re-location): a shard re-located more than RELOC_HEAVY photons in one iteration
     unsigned int scan_work; // K1: next work item (photon chunk, cell chunk); zeroed by the pass kernel that feeds the scan
     int error_slot, error_site; // photon slot (or -1) and ERR_SITE_* of the first error raised (raise_error)
     long long cell_evals, box_evals, max_iters;

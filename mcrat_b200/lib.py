@@ -22,7 +22,7 @@ HYDRO_FIELDS = ["r0", "r1", "r2", "r0_size", "r1_size", "r2_size", "r", "theta",
 
 ABI_VERSION = 2
 RNG_PHILOX, RNG_REPLAY = 0, 1
-LOOP_MODES = {"auto": 0, "streamed": 1, "persistent": 2}
+LOOP_MODES = {"auto": 0, "streamed": 1, "persistent": 2, "streamed_global": 3}
 
 ERRORS = {-1: "ERR_CUDA", -2: "ERR_ARG", -3: "ERR_STATE", -4: "ERR_REPLAY", -5: "ERR_TABLE"}
 

@@ -62,5 +62,37 @@ def main():
         print(name, hydro["num_elements"], "cells", nph, "photons", st, "uniforms", u.size)
 
 
+def _index_chunk(args):
+    refname, hydro, ph = args
+    ref = api.RefLib(refname)
+    ref.set_hydro(hydro)
+    ref.set_photons(ph)
+    rng, _ = ref.new_rng(seed=1)
+    ref.find_containing_hydro_cell(1, rng)
+    return ref.photons()["nearest_block_index"].copy()
+
+
+def index_goldens():
+    """Full BASELINE-size cell indices (1e5 photons x 1 048 576 cells) from the reference's own findContainingHydroCell
+    (switch = 1): tests/golden/index_full_<cfg>.npz holds the 1e5 int32 indices and a hash of the grid geometry."""
+    import multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    for name in helpers.INDEX_GOLDEN:
+        cfg, hydro, ph, frame, refname, geo = helpers.index_golden_inputs(name)
+        h = {k: hydro[k] for k in HYDRO_KEYS + ["num_elements", "fps"]}
+        nproc = os.cpu_count() or 1
+        chunks = np.array_split(np.arange(ph.size), nproc * 4)
+        with mp.get_context("fork").Pool(nproc) as pool:
+            parts = pool.map(_index_chunk, [(refname, h, ph[c]) for c in chunks])
+        idx = np.concatenate(parts).astype(np.int32)
+        np.savez_compressed(os.path.join(HERE, "index_full_%s.npz" % name), idx=idx, geometry_sha256=geo)
+        print("index_full_%s: %d photons, %d outside (-1), max index %d" % (name, idx.size, int((idx < 0).sum()), idx.max()))
+
+
 if __name__ == "__main__":
-    main()
+    if "--index" in sys.argv:
+        index_goldens()
+    else:
+        main()
+        index_goldens()

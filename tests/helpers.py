@@ -31,35 +31,39 @@ def dump_parity_log(path):
     with open(path, "w") as fh:
         json.dump(PARITY_LOG, fh, indent=0)
 
-# Parity bars (BASELINE.json north_star): cell indices bit-exact; optical depth,
-# time-to-scatter, 4-momenta and Stokes parameters within 1e-12 relative when both sides
-# consume the same uniform stream.  "Relative" is taken against the natural scale of each
-# quantity: |r| for positions, p0 for 4-momentum components, 1 for the normalised Stokes vector.
+# Parity bars (BASELINE.json north_star): cell indices, types, counters bit-exact; positions, optical depth,
+# time-to-scatter, 4-momenta and Stokes parameters "within 1e-12 relative" when both sides consume the same uniform
+# stream.  "Relative" is taken against the natural scale of each quantity: |r| for positions, p0 for 4-momentum
+# components, the value itself for tau' and time_to_scatter, 1 for the normalised Stokes vector.
+#
+# What is asserted, per photon (not per median):
+#   * positions: 1e-12 flat (achieved: 1.6e-15) -- nothing between the uniforms and a position goes through libm
+#     except the scattered photon's own history;
+#   * everything downstream of a libm call (sin / cos / atan2 / acos / log, where CUDA's libdevice and glibc differ in
+#     the last ulp and the reference's own formulas then cancel -- tau' = n sigma (1 - beta cos theta),
+#     p0' = Gamma (p0 - beta.p), acos of dot products near +-1 in the Stokes rotations): FOUR TIMES THE LARGEST ERROR
+#     MEASURED over the whole GPU suite (2021 field comparisons, 24 654 photons, all seven geometries, replay and
+#     Philox modes; profiles/parity_r02.json, written by this module on every `-m gpu` run):
+#         field                  measured max   photons > 1e-12      asserted
+#         p0..p3 / p0            2.4e-12        3 of 24 654          1e-11
+#         comv_p0..3 / comv_p0   3.9e-12        10 of 24 654         2e-11
+#         tau', time_to_scatter  6.5e-12        179 of 24 347        3e-11
+#         s1, s2 (absolute)      1.5e-11        6 of 24 654          6e-11
+#   * and the MEDIAN of every field must meet 1e-12 itself.
+# Round 1 allowed 1e-12 x 2 Gamma^2 (x (2 Gamma^2)^2 for scattered photons: up to 4e-4) and 1e-9 on Stokes.
 TOL = 1e-12
-
+TOL_MOMENTUM = 1e-11
+TOL_COMOVING = 2e-11
+TOL_TAU = 3e-11
+TOL_STOKES = 6e-11
 
 M_P, THOM_X_SECT = 1.6726231e-24, 6.65246e-25  # Src/mclib.c:5
 
 
 def compare_photons(got, want, tol=TOL, stokes_tol=None, check_tts=True, label="", hydro=None):
-    """Assert photon lists agree: integers exactly, floating point to `tol` relative.
-
-    Positions are held to `tol` outright.  Three quantities come out of formulas of the reference
-    that cancel catastrophically for photons moving with (or scattered against) a Gamma ~ 100 flow:
-
-      tau'   = n_lab sigma_T sigma_hat (1 - beta cos theta)          Src/optical_depth.c:46-58
-      p'     = Lambda(beta) p,   p0' = Gamma (p0 - beta.p)            Src/mclib.c:332-350, 558
-      p_new  = Lambda(-beta) p'_new                                   Src/mclib.c:1262-1265
-
-    Each loses up to kappa = 2 Gamma^2 (2e4) digits' worth, and that amplifies the last-ulp differences
-    between CUDA's and glibc's sin/cos/atan2 (the only operations on the device that are not
-    IEEE-exact and evaluated in the reference's order).  They are therefore checked twice:
-    the median of the plain relative error must meet `tol`, and every photon must meet
-    `tol` times the conditioning bound kappa of its cell (kappa^2 for the lab momentum of scattered
-    photons, which went through two such boosts).  Pass `hydro` to enable the bound; without it
-    everything is held to `tol`.
-    """
-    stokes_tol = tol if stokes_tol is None else stokes_tol
+    """Assert photon lists agree: integers exactly, floating point to the per-field tolerances above.
+    `hydro` is accepted for the callers' convenience and unused (no conditioning allowance is made any more)."""
+    stokes_tol = TOL_STOKES if stokes_tol is None else stokes_tol
     assert got.size == want.size, (label, got.size, want.size)
     assert np.array_equal(got["type"], want["type"]), label + ": photon types differ"
     assert np.array_equal(got["nearest_block_index"], want["nearest_block_index"]), \
@@ -68,16 +72,12 @@ def compare_photons(got, want, tol=TOL, stokes_tol=None, check_tts=True, label="
     assert np.array_equal(got["recalc_properties"], want["recalc_properties"]), label + ": recalc_properties differs"
     assert np.array_equal(got["weight"], want["weight"]), label + ": weights differ"
     live = want["nearest_block_index"] != -1
-    kappa = np.ones(want.size)
-    if hydro is not None:
-        gidx = np.where(live, want["nearest_block_index"], 0)
-        kappa = np.where(live, 2.0 * np.asarray(hydro["gamma"])[gidx] ** 2, 1.0)
     errs, bad = {}, {}
 
     def check(name, a, b, scale, bound, mask=None):
         slots = np.arange(a.size)
         if mask is not None:
-            a, b, scale, bound, slots = a[mask], b[mask], scale[mask], bound[mask], slots[mask]
+            a, b, scale, slots = a[mask], b[mask], scale[mask], slots[mask]
         if a.size == 0:
             errs[name] = 0.0
             return
@@ -86,23 +86,21 @@ def compare_photons(got, want, tol=TOL, stokes_tol=None, check_tts=True, label="
         _record(label, name, d, slots)
         errs[name] = float(np.nanmax(d)) if not np.isnan(d).any() else float("nan")
         p50 = float(np.percentile(d, 50)) if not np.isnan(d).any() else float("nan")
-        if not (p50 <= tol) or not np.all(d <= tol * bound):
-            bad[name] = dict(max=errs[name], median=p50, worst_vs_bound=float(np.max(d / bound)))
+        if not (p50 <= tol) or not np.all(d <= bound):
+            bad[name] = dict(max=errs[name], median=p50, bound=bound, worst_slot=int(slots[int(np.nanargmax(d))]))
 
-    one = np.ones(want.size)
     rnorm = np.sqrt(want["r0"] ** 2 + want["r1"] ** 2 + want["r2"] ** 2)
     for f in ("r0", "r1", "r2"):
-        check(f, got[f], want[f], rnorm, one)
-    scattered = want["num_scatt"] > 0
+        check(f, got[f], want[f], rnorm, tol)
     for f in ("p0", "p1", "p2", "p3"):
-        check(f, got[f], want[f], np.abs(want["p0"]), np.where(scattered, kappa * kappa, one))
+        check(f, got[f], want[f], np.abs(want["p0"]), max(tol, TOL_MOMENTUM))
     for f in ("comv_p0", "comv_p1", "comv_p2", "comv_p3"):
-        check(f, got[f], want[f], np.abs(want["comv_p0"]), kappa)
+        check(f, got[f], want[f], np.abs(want["comv_p0"]), max(tol, TOL_COMOVING))
     tau = np.abs(want["total_optical_depth"])
-    check("total_optical_depth", got["total_optical_depth"], want["total_optical_depth"], tau, kappa * kappa, mask=live)
+    check("total_optical_depth", got["total_optical_depth"], want["total_optical_depth"], tau, max(tol, TOL_TAU), mask=live)
     if check_tts:
         check("time_to_scatter", got["time_to_scatter"], want["time_to_scatter"], np.abs(want["time_to_scatter"]),
-              kappa * kappa)
+              max(tol, TOL_TAU))
     for f in ("s0", "s1", "s2", "s3"):
         both_nan = np.isnan(got[f]) & np.isnan(want[f])
         _record(label, f, np.where(both_nan, 0.0, np.abs(got[f] - want[f])))
@@ -122,3 +120,33 @@ def _rel(a, b, scale):
     if np.any(np.isnan(d)):
         return float("nan")
     return float(np.max(d))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# full-size cell-index goldens (tests/golden/index_full_<cfg>.npz, generated by tests/golden/make_golden.py from oracle/_ref)
+# ---------------------------------------------------------------------------------------------------------------------
+INDEX_GOLDEN = {
+    # name: (workload, reference configuration, photons, box of Cartesian positions (lo, hi) per axis)
+    # positions are affine maps of PCG64 uniforms: +, * only, hence bit-identical on every machine
+    "c2": ("C2", "c2_2d_cyl_stokes", 100000, ((-2.4e11, 2.4e11), (-2.4e11, 2.4e11), (1.0e12, 3.0e12))),
+    "c5": ("C5", "c5_3d_sph", 100000, ((-2.5e11, 2.5e11), (-2.5e11, 2.5e11), (0.8e12, 1.2e12))),
+}
+
+
+def index_golden_inputs(name):
+    """(cfg, hydro, photons) of a full-size index golden: the BASELINE grid and 1e5 photons spread over a box that
+    reaches a little outside the domain (so that -1 is exercised too).  Only the positions matter."""
+    import hashlib
+    from mcrat_b200 import synth
+    wl, refname, n, box = INDEX_GOLDEN[name]
+    cfg, hydro, photons, frame = synth.workload(wl, n_photons=256, seed=3)
+    rng = np.random.default_rng(20261018)
+    ph = np.zeros(n, dtype=photons.dtype)
+    ph[:] = photons[0]
+    for k, f in enumerate(("r0", "r1", "r2")):
+        ph[f] = box[k][0] + rng.random(n) * (box[k][1] - box[k][0])
+    ph["nearest_block_index"] = 0
+    geo = hashlib.sha256()
+    for f in ("r0", "r1", "r2", "r0_size", "r1_size", "r2_size"):
+        geo.update(np.ascontiguousarray(hydro[f], dtype=np.float64).tobytes())
+    return cfg, hydro, ph, frame, refname, geo.hexdigest()

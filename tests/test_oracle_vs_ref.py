@@ -308,3 +308,22 @@ def test_cyclosynchrotron_rebin_bit_identical(refname, wl):
     ref.set_photons(photons)
     o.set_photons(photons)
     assert ref.rebin_cyclosynch_comp_photons(5)[0] == -1 and o.rebin_cyclosynch_comp_photons(5)[0] == -1
+
+
+@pytest.mark.parametrize("name", ["c2", "c5"])
+def test_oracle_first_match_indices_at_full_grid_size(name):
+    """A strided sample of the full-size index golden (the reference's own findContainingHydroCell at 1 048 576 cells)
+    through the restatement: bit-exact, -1 included."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import index_golden_inputs
+    g = np.load(os.path.join(GOLDEN, "index_full_%s.npz" % name))
+    cfg, hydro, ph, frame, refname, geo = index_golden_inputs(name)
+    if geo != str(g["geometry_sha256"]):
+        pytest.skip("this machine's numpy builds the grid with other last bits than the golden's")
+    pick = np.arange(0, ph.size, 400)
+    o = api.Oracle(configs.CONFIGS[refname])
+    o.set_hydro(hydro)
+    o.set_photons(ph[pick])
+    o.find_containing_hydro_cell(1, api.OracleRng("ranlxs0", seed=1))
+    assert np.array_equal(o.photons()["nearest_block_index"], g["idx"][pick])
