@@ -194,6 +194,20 @@ int mcrat_b200_set_cs_limits(mcrat_b200_ctx *ctx, int max_photons, int scatt_cyc
  * must grow the list.  Single shard only (CYCLOSYNCHROTRON_SWITCH ON). */
 int mcrat_b200_rebin_cyclosynch_comp_photons(mcrat_b200_ctx *ctx, int max_photons, int *num_cyclosynch_ph_emit,
                                              int *scatt_cyclosynch_num_ph, int *num_null_rebin_ph);
+/* photonEmitCyclosynch with inject_single_switch == 0, Src/mc_cyclosynch.h:90, Src/mc_cyclosynch.c:1176-1464, on the device
+ * (K6): cells of the emission shell of the hydro frame last uploaded (its fps, scatt_frame_number and inj_frame_number
+ * give rmin / rmax, :1206-1207), photon-weight search with Poisson counts per cell, the new 'p' photons placed into the
+ * null slots of the list in slot order (addToPhotonList).  A list with too few null slots grows on the device
+ * (mcrat_b200_list_capacity changes; download accordingly).  Outputs: the return value of the reference's function
+ * (photons emitted), the weight the search settled on, the number of cells in the shell.  Single shard.
+ * (inject_single_switch == 1, the replacement of one scattered pool photon, happens inside the frame loop.) */
+int mcrat_b200_photon_emit_cyclosynch(mcrat_b200_ctx *ctx, double r_inj, double ph_weight, int maximum_photons, double theta_min,
+                                      double theta_max, int *num_emitted, double *ph_weight_adjusted, int *num_cells_selected);
+/* photonEmitCyclosynch with inject_single_switch == 1 for hosts that drive the loop call by call (Src/mcrat.c:792-803, right
+ * after the photonEvent that scattered pool photon `scatt_ph_index`): the photon becomes a comptonised one ('k'), a fresh
+ * pool photon goes into the first null slot (*new_photon_index; the list grows when it has none) and the scattered photon
+ * is re-positioned inside its cell.  Draws continue the event's stream.  mcrat_b200_run_frame does all this by itself. */
+int mcrat_b200_photon_emit_cyclosynch_single(mcrat_b200_ctx *ctx, int scatt_ph_index, int *new_photon_index);
 /* CYCLOSYNCHROTRON_REBIN_E_PERC, _REBIN_ANG (degrees), _REBIN_ANG_PHI (degrees); defaults 0.1, 0.5, 10 (Src/mcrat.h:308-322) */
 int mcrat_b200_set_cs_rebin_params(mcrat_b200_ctx *ctx, double rebin_e_perc, double rebin_ang_deg, double rebin_ang_phi_deg);
 /* phMinMax / phScattStats / averagePhotonEnergy, Src/mclib.c:1465 / 1385 / 1358 */

@@ -8,6 +8,9 @@
  *
  *     -Wl,--wrap=findContainingHydroCell -Wl,--wrap=calcMeanFreePath
  *     -Wl,--wrap=photonEvent -Wl,--wrap=updatePhotonPosition -Wl,--wrap=averagePhotonEnergy
+ *     -Wl,--wrap=phMinMax -Wl,--wrap=phScattStats -Wl,--wrap=phAbsCyclosynch -Wl,--wrap=photonEmitCyclosynch
+ *     -Wl,--wrap=rebinCyclosynchCompPhotons -Wl,--wrap=calcCyclosynchRLimits
+ *     -Wl,--wrap=initalizeHotCrossSection -Wl,--wrap=cleanupInterpolationData
  *     -lmcrat_b200_dropin -lmcrat_b200
  *
  * (see INTEGRATION.md).  The structs below mirror the member sequence of the reference's
@@ -91,6 +94,31 @@ void __wrap_updatePhotonPosition(mcrat_dropin_photonList *photon_list, double t,
 double __wrap_averagePhotonEnergy(mcrat_dropin_photonList *photon_list);
 double __wrap_phAbsCyclosynch(mcrat_dropin_photonList *photon_list, int *num_abs_ph, int *scatt_cyclosynch_num_ph,
                               mcrat_dropin_hydro_dataframe *hydro_data, FILE *fPtr);
+/* phMinMax / phScattStats, Src/mclib.h:27-29 (Src/mcrat.c:704, 745, 881): device reductions over the mirrored list */
+void __wrap_phMinMax(mcrat_dropin_photonList *photon_list, double *min, double *max, double *min_theta, double *max_theta,
+                     FILE *fPtr);
+void __wrap_phScattStats(mcrat_dropin_photonList *photon_list, int *max, int *min, double *avg, double *r_avg, FILE *fPtr);
+/* calcCyclosynchRLimits, Src/mc_cyclosynch.h:84 (Src/mcrat.c:711, 714) */
+double __wrap_calcCyclosynchRLimits(int frame_scatt, int frame_inj, double fps, double r_inj, char *min_or_max);
+/* rebinCyclosynchCompPhotons, Src/mc_cyclosynch.h:86 (Src/mcrat.c:825, 865): on the device; when the list has fewer null
+ * slots than rebinned photons the host list is grown the way addToPhotonList does (Src/photons.c:117-129: realloc to
+ * capacity + missing slots, new slots nulled) and the call is repeated.  Returns the number of empty bins. */
+int __wrap_rebinCyclosynchCompPhotons(mcrat_dropin_photonList *photon_list, int *num_cyclosynch_ph_emit,
+                                      int *scatt_cyclosynch_num_ph, int max_photons, double thread_theta_min,
+                                      double thread_theta_max, void *rand, FILE *fPtr);
+/* photonEmitCyclosynch, Src/mc_cyclosynch.h:90 (Src/mcrat.c:747 all cells, :799 single): on the device
+ * (mcrat_b200_photon_emit_cyclosynch); the host list is grown first when it cannot take the new photons */
+int __wrap_photonEmitCyclosynch(mcrat_dropin_photonList *photon_list, double r_inj, double ph_weight, int maximum_photons,
+                                double theta_min, double theta_max, mcrat_dropin_hydro_dataframe *hydro_data, void *rand,
+                                int inject_single_switch, int scatt_ph_index, FILE *fPtr);
+/* initalizeHotCrossSection / cleanupInterpolationData, Src/hot_x_section.h:31, 59 (Src/mcrat.c:585, 931).  The table file
+ * (reference layout, Src/hot_x_section.c:116-131) is read if it exists; otherwise the table is built on the device (K7,
+ * 500 000 samples per point like the reference) and rank 0 writes the file.  Path: mcrat_b200_dropin_set_table_path(), else
+ * $MCRAT_B200_HOT_X_SECTION_FILE, else "thermal_hot_x_section.dat" in the working directory (the reference composes it from
+ * its compile-time FILEPATH / MC_PATH). */
+void __wrap_initalizeHotCrossSection(int rank, void *rand, FILE *fPtr);
+void __wrap_cleanupInterpolationData(void);
+void mcrat_b200_dropin_set_table_path(const char *path);
 
 #ifdef __cplusplus
 }

@@ -84,20 +84,6 @@ __global__ void __launch_bounds__(256) cs_absorb_kernel(DevCtx d)
 // [1, 1 + 12 theta] x [-1, 1], integrand = Maxwell-Juttner pdf x boosted KN cross section,
 // result = 0.5 * volume * mean), drawn from a Philox stream keyed by the point.
 // ------------------------------------------------------------------------------------------
-__device__ inline double maxwell_juttner_pdf(double gamma, double theta, double normalization)
-{
-    // Src/electron.c:538-560 singleMaxwellJuttner (normalization computed once per point)
-    return ((gamma * sqrt(gamma * gamma - 1.) / (theta * normalization)) * exp(-(gamma - 1.) / theta));
-}
-
-__device__ inline double boosted_cross_section(double norm_ph_comv, double mu, double gamma)
-{
-    // Src/hot_x_section.c:369-400 boostedCrossSection
-    double beta = sqrt(gamma * gamma - 1.) / gamma;
-    double norm_ph_e = norm_ph_comv * gamma * (1. - mu * beta);
-    return kn_cross_section(norm_ph_e) * (1. - mu * beta);
-}
-
 __global__ void __launch_bounds__(256) hot_table_kernel(double *table, long long calls, uint32_t k0, uint32_t k1)
 {
     const int point = blockIdx.x; // i * (N_T + 1) + j, the reference's loop order (:90-105)
@@ -111,11 +97,7 @@ __global__ void __launch_bounds__(256) hot_table_kernel(double *table, long long
     } else if (theta < pow(10., LOG_T_MIN)) {
         result = kn_cross_section(comv_ph_e); // :338-339
     } else {
-        double normalization;
-        if (theta > 1.e-2)
-            normalization = bessel_K2(1. / theta) * exp(1. / theta);
-        else
-            normalization = sqrt(PI * theta / 2.);
+        const double normalization = maxwell_juttner_norm(theta);
         const double xl0 = 1, xu0 = 1. + 12 * theta;
         double sum = 0;
         for (long long n = threadIdx.x; n < calls; n += 256) {

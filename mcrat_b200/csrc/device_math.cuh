@@ -462,13 +462,66 @@ __device__ inline bool bilinear_eval(const HotTable &t, double x, double y, doub
     return true;
 }
 
+// Src/electron.c:538-560 singleMaxwellJuttner with its normalisation (K_2(1/theta) e^{1/theta}, or the asymptotic form
+// below theta = 1e-2) formed once per integral: the same value in every call of the reference
+__device__ inline double maxwell_juttner_norm(double theta)
+{
+    if (theta > 1.e-2) return bessel_K2(1. / theta) * exp(1. / theta);
+    return sqrt(PI * theta / 2.);
+}
+__device__ inline double maxwell_juttner_pdf(double gamma, double theta, double normalization)
+{
+    return ((gamma * sqrt(gamma * gamma - 1.) / (theta * normalization)) * exp(-(gamma - 1.) / theta));
+}
+
+// Src/hot_x_section.c:369-400 boostedCrossSection
+__device__ inline double boosted_cross_section(double norm_ph_comv, double mu, double gamma)
+{
+    double beta = sqrt(gamma * gamma - 1.) / gamma;
+    double norm_ph_e = norm_ph_comv * gamma * (1. - mu * beta);
+    return kn_cross_section(norm_ph_e) * (1. - mu * beta);
+}
+
+// Where a hot cross-section lookup falls outside the table the reference integrates the cross section on the spot by
+// plain Monte Carlo with its gsl_rng (calculateTotalThermalCrossSection, Src/hot_x_section.c:324-357, reached from
+// interpolateThermalHotCrossSection :563-599): 500 000 samples of (gamma, mu) over [1, 1 + 12 theta] x [-1, 1],
+// gsl_monte_plain's running mean.  The device does the same integral, sample for sample, from a Philox stream of its own
+// keyed by the photon and the iteration: counter (sample, iteration_lo, slot, 3 + 8 * iteration_hi), the two doubles of a
+// block = the sample's (gamma, mu) draws.  One thread, sequentially, like the reference (a catastrophic path there as
+// here: ~0.4 s per lookup; photons outside the table in the same launch integrate in parallel).  The replay harness
+// (uniforms of a recorded gsl_rng stream) cannot supply the 10^6 draws in stream order from parallel threads: there the
+// lookup is reported as MCRAT_B200_ERR_TABLE, as in round 1.
+struct FallbackRng {
+    uint32_t k0, k1, slot;
+    uint64_t iter;
+    int replay;
+};
+
+__device__ __noinline__ double total_thermal_cross_section_mc(double ph_comv, double theta, uint32_t k0, uint32_t k1, uint32_t slot,
+                                                              uint64_t iter)
+{
+    const double normalization = maxwell_juttner_norm(theta);
+    const double xl0 = 1, xu0 = 1. + 12 * theta, xl1 = -1, xu1 = 1;
+    const double vol = (xu0 - xl0) * (xu1 - xl1);
+    const uint32_t c1 = (uint32_t)iter, c3 = 3u + ((uint32_t)(iter >> 32) << 3);
+    double m = 0; // gsl_monte_plain_integrate: m += (f - m) / (n + 1)
+    for (uint32_t n = 0; n < 500000u; ++n) {
+        double u1, u2;
+        philox_doubles(n, c1, slot, c3, k0, k1, u1, u2);
+        const double gamma = xl0 + u1 * (xu0 - xl0);
+        const double mu = xl1 + u2 * (xu1 - xl1);
+        const double fval = maxwell_juttner_pdf(gamma, theta, normalization) * boosted_cross_section(ph_comv, mu, gamma);
+        const double dd = fval - m;
+        m += dd / (n + 1.0);
+    }
+    return 0.5 * (vol * m);
+}
+
 // Src/optical_depth.c:132-149 getThermalCrossSection + Src/hot_x_section.c:545-605.
-// Outside the table the reference integrates the cross section by plain Monte Carlo with its
-// gsl_rng (500 000 samples, Src/hot_x_section.c:324-357).  The two closed-form early returns of
-// that routine (theta below the table, :336-339) are reproduced; the Monte Carlo branch raises
-// `*table_err` instead (reported to the host as MCRAT_B200_ERR_TABLE).
+// Outside the table: the two closed-form early returns of calculateTotalThermalCrossSection (theta below the table,
+// :336-339), else the Monte Carlo integral above (`fr` given and not in replay mode) or `*table_err`.
 __device__ inline double thermal_cross_section(int tau_calc, const HotTable &t, double comv_e, double temp,
-                                               int *table_err)
+                                               int *table_err, const FallbackRng *fr = nullptr)
 {
     if (tau_calc != TAU_TABLE) return 1;
     double ne = comv_e / (M_EL * C_LIGHT);
@@ -483,6 +536,8 @@ __device__ inline double thermal_cross_section(int tau_calc, const HotTable &t, 
             direct = 1;
         } else if (th < pow(10.0, LOG_T_MIN)) {
             direct = kn_cross_section(ph_comv);
+        } else if (fr && !fr->replay) {
+            direct = total_thermal_cross_section_mc(ph_comv, th, fr->k0, fr->k1, fr->slot, fr->iter);
         } else {
             if (table_err) *table_err = 1;
             direct = kn_cross_section(ph_comv);
@@ -500,7 +555,7 @@ struct CellState {
 // Src/optical_depth.c:7-115 calculateOpticalDepth (NONTHERMAL_E_DIST == OFF)
 __device__ inline double optical_depth(int dims, int g, int tau_calc, const HotTable &t, const CellState &c,
                                        double ph_r0, double ph_r1, double p1, double p2, double p3, double comv_p0,
-                                       int *table_err)
+                                       int *table_err, const FallbackRng *fr = nullptr)
 {
     double fb[3];
     if (dims == D_THREE) {
@@ -518,7 +573,7 @@ __device__ inline double optical_depth(int dims, int g, int tau_calc, const HotT
     double beta = sqrt(1.0 - 1.0 / (c.gamma * c.gamma));
     double fluid_factor = (1.0 - beta * n_cosangle);
     double n_lab = c.dens_lab / M_P;
-    double sig = thermal_cross_section(tau_calc, t, comv_p0, c.temp, table_err);
+    double sig = thermal_cross_section(tau_calc, t, comv_p0, c.temp, table_err, fr);
     return (n_lab) * (THOM_X_SECT * sig) * fluid_factor;
 }
 

@@ -433,8 +433,10 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
             if (in_domain) {
                 if (in_cell(ndim3, d.cells, cell_idx, h0, h1, h2)) {
                     int terr = 0;
+                    const FallbackRng fr = {d.k0, d.k1 ^ (d.shard_base + (uint32_t)(early.gst - d.sh)), (uint32_t)(i - st.first),
+                                            st.iter, d.replay};
                     tau_next = optical_depth(d.dims, d.geom, d.tau_calc, d.table, cell, m.r[0], m.r[1], m.p_new[1], m.p_new[2],
-                                             m.p_new[3], m.pc_fin[0], &terr);
+                                             m.p_new[3], m.pc_fin[0], &terr, &fr);
                     if (terr) raise_error(d.gs, MCRAT_B200_ERR_TABLE, i, ERR_SITE_EVENT_MINIPASS);
                     const uint32_t k1 = d.k1 ^ (d.shard_base + (uint32_t)(early.gst - d.sh));
                     const double xi = philox_mfp_uniform(d.k0, k1, st.iter, (uint32_t)(i - st.first));
@@ -889,6 +891,7 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
             gs.replay_cursor = rng_sh.pos;
             if (rng_sh.exhausted) raise_error(&gs, MCRAT_B200_ERR_REPLAY, ph_index, ERR_SITE_EVENT_REPLAY);
         }
+        st.last_event_draw = rng_sh.draw;
     }
     __syncthreads();
     return early.released != 0;

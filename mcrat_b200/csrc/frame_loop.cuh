@@ -104,7 +104,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
                 if (ld_acquire_u32(word) < target) { // fast path: already there, one round trip
                     while (ld_relaxed_u32(word) < target) {
                         __nanosleep(40);
-                        if (++spins > (1u << 24)) { // never in a healthy run; refuse to hang the GPU
+                        // never in a healthy run; refuse to hang the GPU.  A hot cross-section lookup outside the table
+                        // integrates for ~0.4 s inside a pass (total_thermal_cross_section_mc): allow for a few of them
+                        if (++spins > (d.tau_calc == TAU_TABLE ? (1u << 28) : (1u << 24))) {
                             raise_error(&gs, MCRAT_B200_ERR_STATE, -1, ERR_SITE_LOOP_SPIN);
                             ok = 0;
                             break;

@@ -50,6 +50,7 @@ static_assert(sizeof(mcrat_photon) == 176, "struct photon layout (Src/mcrat.h:14
 #include "event.cuh"
 #include "frame_loop.cuh"
 #include "aux_kernels.cuh"
+#include "cs_emit.cuh"
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -79,6 +80,9 @@ struct mcrat_b200_ctx {
     int occ_scan[2];              // resident CTAs per SM of scan_kernel<0> / <1>
     int occ_loop256, occ_loop128; // resident blocks per SM of frame_loop_kernel<256>, frame_loop_solo_kernel<256> / <128>
     long long launches; // kernels launched through this context
+    double hydro_fps;   // of the frame last uploaded (calcCyclosynchRLimits, Src/mc_cyclosynch.c:1206-1207)
+    int hydro_scatt_frame, hydro_inj_frame;
+    unsigned int emit_epoch; // photonEmitCyclosynch (all cells) calls so far: part of the key of the emission streams
     GlobalState *gs_host;          // pinned
     std::vector<ShardState> sh_host;
     double *replay_dev;
@@ -215,6 +219,9 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
     ctx->occ_loop256 = ctx->occ_loop128 = 0;
     ctx->occ_scan[0] = ctx->occ_scan[1] = 0;
     ctx->launches = 0;
+    ctx->hydro_fps = 0;
+    ctx->hydro_scatt_frame = ctx->hydro_inj_frame = 0;
+    ctx->emit_epoch = 0;
     ctx->replay_dev = nullptr;
     ctx->replay_cap = 0;
     ctx->table_dev = nullptr;
@@ -385,7 +392,9 @@ static int grid_for(mcrat_b200_ctx *ctx, int n, int threads, int per_sm)
 API int mcrat_b200_set_hydro(mcrat_b200_ctx *ctx, int n, const double *const *fields, const double *domains, double fps,
                              int scatt_frame_number, int inj_frame_number)
 {
-    (void)fps; (void)scatt_frame_number; (void)inj_frame_number;
+    ctx->hydro_fps = fps;
+    ctx->hydro_scatt_frame = scatt_frame_number;
+    ctx->hydro_inj_frame = inj_frame_number;
     if (!ctx || !fields || !domains || n < 0) return ctx ? fail(ctx, MCRAT_B200_ERR_ARG, "set_hydro: bad argument") : MCRAT_B200_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -424,6 +433,7 @@ API int mcrat_b200_set_hydro(mcrat_b200_ctx *ctx, int n, const double *const *fi
             CK(cudaMemsetAsync(cols[f], 0, (size_t)(n ? n : 1) * sizeof(double), ctx->stream));
     }
     c.r0 = cols[0]; c.r1 = cols[1]; c.r2 = cols[2];
+    c.s0 = cols[3]; c.s1 = cols[4]; c.s2 = cols[5];
     c.v0 = cols[8]; c.v1 = cols[9]; c.v2 = cols[10];
     c.dens = cols[11]; c.dens_lab = cols[12]; c.temp = cols[14]; c.gamma = cols[15];
     c.B0 = cols[16]; c.B1 = cols[17]; c.B2 = cols[18];
@@ -465,11 +475,17 @@ API int mcrat_b200_set_thermal_table(mcrat_b200_ctx *ctx, const double *table)
     return MCRAT_B200_OK;
 }
 
-static int ensure_photon_capacity(mcrat_b200_ctx *ctx, int n)
+// keep = number of leading slots whose contents must survive a re-allocation (0: the list is about to be overwritten)
+static int ensure_photon_capacity(mcrat_b200_ctx *ctx, int n, int keep = 0)
 {
     if (n <= ctx->ph_cap_alloc) return MCRAT_B200_OK;
     CK(cudaStreamSynchronize(ctx->stream));
-    free_pool(ctx->ph_allocs);
+    const PhotonCols old = ctx->d.ph;
+    std::vector<void *> old_allocs;
+    if (keep > 0)
+        old_allocs.swap(ctx->ph_allocs);
+    else
+        free_pool(ctx->ph_allocs);
     int cap = n + n / 8 + 1024;
     PhotonCols &p = ctx->d.ph;
     double **cols[23] = {&p.r0, &p.r1, &p.r2, &p.p0, &p.p1, &p.p2, &p.p3, &p.c0, &p.c1, &p.c2, &p.c3, &p.s0,
@@ -491,6 +507,19 @@ static int ensure_photon_capacity(mcrat_b200_ctx *ctx, int n)
     CK(cudaMalloc((void **)&ctx->aos_dev, (size_t)cap * sizeof(mcrat_photon)));
     ctx->aos_cap = cap;
     ctx->ph_cap_alloc = cap;
+    if (keep > 0) {
+        const PhotonCols &o = old;
+        double *const src[23] = {o.r0, o.r1, o.r2, o.p0, o.p1, o.p2, o.p3, o.c0, o.c1, o.c2, o.c3, o.s0,
+                                 o.s1, o.s2, o.s3, o.nscatt, o.weight, o.tau, o.tts, o.v0, o.v1, o.v2, o.ntau};
+        for (int k = 0; k < 23; ++k)
+            CK(cudaMemcpyAsync(*cols[k], src[k], (size_t)keep * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(p.safe, o.safe, (size_t)keep * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(p.idx, o.idx, (size_t)keep * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(p.flags, o.flags, (size_t)keep, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(p.type, o.type, (size_t)keep, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        free_pool(old_allocs);
+    }
     return MCRAT_B200_OK;
 }
 
@@ -1074,6 +1103,140 @@ API int mcrat_b200_rebin_cyclosynch_comp_photons(mcrat_b200_ctx *ctx, int max_ph
     CK(cudaMemcpyAsync(ctx->d.gs, ctx->gs_host, sizeof(GlobalState), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     cleanup();
+    return device_error(ctx);
+}
+
+// photonEmitCyclosynch with inject_single_switch == 0 (Src/mc_cyclosynch.h:90, Src/mc_cyclosynch.c:1176-1464) on the device,
+// see cs_emit.cuh.  The list grows on the device when it has fewer null slots than new photons (the reference's
+// addToPhotonList reallocates, Src/photons.c:117-129; new slots are null photons and sit at the end, so the slots the new
+// photons land in are the reference's whatever the capacity becomes).
+static int grow_list(mcrat_b200_ctx *ctx, int new_cap)
+{
+    const int old_cap = ctx->d.cap;
+    if (new_cap <= old_cap) return MCRAT_B200_OK;
+    if (int rc = ensure_photon_capacity(ctx, new_cap, old_cap)) return rc;
+    ctx->d.cap = new_cap;
+    init_null_kernel<<<grid_for(ctx, new_cap - old_cap, 256, 8), 256, 0, ctx->stream>>>(ctx->d, old_cap, new_cap - old_cap);
+    if (int rc = check_launch(ctx, "init_null_kernel")) return rc;
+    ctx->d.stream_hints = (getenv("MCRAT_B200_NO_STREAM_HINTS") == nullptr && new_cap > PERSISTENT_MAX_PHOTONS) ? 1 : 0;
+    return layout_shards(ctx, new_cap);
+}
+
+static int count_null_slots(mcrat_b200_ctx *ctx, int *counter_dev, int *nulls)
+{
+    const int nblocks = (ctx->d.cap + 255) / 256;
+    count_null_kernel<<<nblocks, 256, 0, ctx->stream>>>(ctx->d);
+    rebin_scan_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d, nblocks, counter_dev);
+    if (int rc = check_launch(ctx, "count_null_kernel", 2)) return rc;
+    CK(cudaMemcpyAsync(nulls, counter_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MCRAT_B200_OK;
+}
+
+API int mcrat_b200_photon_emit_cyclosynch(mcrat_b200_ctx *ctx, double r_inj, double ph_weight, int maximum_photons,
+                                          double theta_min, double theta_max, int *num_emitted, double *ph_weight_adjusted,
+                                          int *num_cells_selected)
+{
+    if (!ctx) return MCRAT_B200_ERR_ARG;
+    if (int rc = need_ready(ctx)) return rc;
+    if (int rc = need_single_shard(ctx, "photon_emit_cyclosynch")) return rc;
+    if (!(ph_weight > 0) || maximum_photons < 1) return fail(ctx, MCRAT_B200_ERR_ARG, "photon_emit_cyclosynch: ph_weight > 0, maximum_photons >= 1");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (int rc = flush_pushes(ctx)) return rc;
+    DevCtx &d = ctx->d;
+    const int n = d.cells.n, nblocks = (n + 255) / 256;
+    const double rmin = mcrat_b200_calc_cyclosynch_r_limits(ctx->hydro_scatt_frame, ctx->hydro_inj_frame, ctx->hydro_fps, r_inj, "min");
+    const double rmax = mcrat_b200_calc_cyclosynch_r_limits(ctx->hydro_scatt_frame, ctx->hydro_inj_frame, ctx->hydro_fps, r_inj, "max");
+    const double max_photons = ctx->cs_rebin_e_perc * maximum_photons; // Src/mc_cyclosynch.c:1178
+    std::vector<void *> pool;
+    mcrat_photon *emitted = nullptr;
+    auto cleanup = [&]() {
+        free_pool(pool);
+        if (emitted) cudaFree(emitted);
+    };
+    CsEmitWork w;
+    w.n_cells = n;
+    if (dev_alloc(pool, &w.flag, (size_t)n) != cudaSuccess || dev_alloc(pool, &w.block_base, (size_t)nblocks + 1) != cudaSuccess ||
+        dev_alloc(pool, &w.meta, 4) != cudaSuccess || dev_alloc(pool, &w.weight, 1) != cudaSuccess) {
+        cleanup();
+        return fail(ctx, MCRAT_B200_ERR_CUDA, "photon_emit_cyclosynch: cudaMalloc");
+    }
+    w.sel_cell = nullptr; w.integ = w.vol = w.nu_c = nullptr; w.count = nullptr; w.offset = nullptr;
+    cudaMemsetAsync(w.meta, 0, 4 * sizeof(int), ctx->stream);
+    cs_select_kernel<<<nblocks, 256, 0, ctx->stream>>>(d, w, rmin, rmax, theta_min, theta_max);
+    cs_block_scan_kernel<<<1, 1024, 0, ctx->stream>>>(w, nblocks);
+    if (int rc = check_launch(ctx, "cs_select_kernel", 2)) { cleanup(); return rc; }
+    int meta[4] = {0, 0, 0, 0};
+    cudaMemcpyAsync(meta, w.meta, sizeof(meta), cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cleanup(); return fail(ctx, MCRAT_B200_ERR_CUDA, "photon_emit_cyclosynch: synchronize"); }
+    const int n_sel = meta[0];
+    if (num_cells_selected) *num_cells_selected = n_sel;
+    const size_t ns = (size_t)(n_sel > 0 ? n_sel : 1);
+    if (dev_alloc(pool, &w.sel_cell, ns) != cudaSuccess || dev_alloc(pool, &w.integ, ns) != cudaSuccess ||
+        dev_alloc(pool, &w.vol, ns) != cudaSuccess || dev_alloc(pool, &w.nu_c, ns) != cudaSuccess ||
+        dev_alloc(pool, &w.count, ns) != cudaSuccess || dev_alloc(pool, &w.offset, ns + 1) != cudaSuccess) {
+        cleanup();
+        return fail(ctx, MCRAT_B200_ERR_CUDA, "photon_emit_cyclosynch: cudaMalloc");
+    }
+    ctx->emit_epoch += 1;
+    cs_compact_kernel<<<nblocks, 256, 0, ctx->stream>>>(d, w);
+    cs_weight_kernel<<<1, 1024, 0, ctx->stream>>>(d, w, ph_weight, max_photons, ctx->emit_epoch);
+    if (int rc = check_launch(ctx, "cs_weight_kernel", 2)) { cleanup(); return rc; }
+    double weight = 0;
+    cudaMemcpyAsync(meta, w.meta, sizeof(meta), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(&weight, w.weight, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cleanup(); return fail(ctx, MCRAT_B200_ERR_CUDA, "photon_emit_cyclosynch: synchronize"); }
+    if (meta[3] == 1) { cleanup(); return fail(ctx, MCRAT_B200_ERR_STATE, "photon_emit_cyclosynch: the black-body tail integral did not converge in 48 intervals"); }
+    if (meta[3] == 2) { cleanup(); return fail(ctx, MCRAT_B200_ERR_STATE, "photon_emit_cyclosynch: the photon weight search did not settle in 400 passes"); }
+    const int ph_tot = meta[1];
+    if (num_emitted) *num_emitted = ph_tot;
+    if (ph_weight_adjusted) *ph_weight_adjusted = weight;
+    if (ph_tot > 0) {
+        int nulls = 0;
+        if (int rc = count_null_slots(ctx, w.meta, &nulls)) { cleanup(); return rc; }
+        if (nulls < ph_tot) {
+            const int need = ph_tot - nulls;
+            int new_cap = d.cap * 2 > d.cap + need ? d.cap * 2 : d.cap + need;
+            if (int rc = grow_list(ctx, new_cap)) { cleanup(); return rc; }
+            if (int rc = count_null_slots(ctx, w.meta, &nulls)) { cleanup(); return rc; }
+        }
+        if (cudaMalloc((void **)&emitted, (size_t)ph_tot * sizeof(mcrat_photon)) != cudaSuccess) { cleanup(); return fail(ctx, MCRAT_B200_ERR_CUDA, "photon_emit_cyclosynch: cudaMalloc"); }
+        // count_null_slots overwrote meta[0]: the fill kernel reads n_sel and ph_tot from it
+        int m2[2] = {n_sel, ph_tot};
+        cudaMemcpyAsync(w.meta, m2, sizeof(m2), cudaMemcpyHostToDevice, ctx->stream);
+        cs_fill_kernel<<<ctx->d.replay ? 1 : grid_for(ctx, ph_tot, 256, 8), 256, 0, ctx->stream>>>(d, w, emitted, ctx->emit_epoch);
+        place_photons_kernel<<<(d.cap + 255) / 256, 256, 0, ctx->stream>>>(d, emitted, ph_tot);
+        if (int rc = check_launch(ctx, "cs_fill_kernel", 2)) { cleanup(); return rc; }
+    }
+    if (int rc = fetch_global(ctx)) { cleanup(); return rc; }
+    cleanup();
+    return device_error(ctx);
+}
+
+API int mcrat_b200_photon_emit_cyclosynch_single(mcrat_b200_ctx *ctx, int scatt_ph_index, int *new_photon_index)
+{
+    if (!ctx) return MCRAT_B200_ERR_ARG;
+    if (int rc = need_ready(ctx)) return rc;
+    if (int rc = need_single_shard(ctx, "photon_emit_cyclosynch_single")) return rc;
+    if (scatt_ph_index < 0 || scatt_ph_index >= ctx->d.cap) return fail(ctx, MCRAT_B200_ERR_ARG, "photon_emit_cyclosynch_single: bad photon index");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (int rc = flush_pushes(ctx)) return rc;
+    int *out = nullptr;
+    CK(cudaMalloc((void **)&out, sizeof(int)));
+    int slot = -1;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        cs_emit_single_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d, scatt_ph_index, out);
+        if (int rc = check_launch(ctx, "cs_emit_single_kernel")) { cudaFree(out); return rc; }
+        cudaMemcpyAsync(&slot, out, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaFree(out); return fail(ctx, MCRAT_B200_ERR_CUDA, "photon_emit_cyclosynch_single: synchronize"); }
+        if (slot >= 0) break;
+        // addToPhotonList doubles a list without null slots (Src/photons.c:117-129)
+        if (int rc = grow_list(ctx, ctx->d.cap * 2 > ctx->d.cap + 1 ? ctx->d.cap * 2 : ctx->d.cap + 1)) { cudaFree(out); return rc; }
+    }
+    cudaFree(out);
+    if (slot < 0) return fail(ctx, MCRAT_B200_ERR_STATE, "photon_emit_cyclosynch_single: no null slot after growing the list");
+    if (new_photon_index) *new_photon_index = slot;
+    if (int rc = fetch_global(ctx)) return rc;
     return device_error(ctx);
 }
 

@@ -454,8 +454,9 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
                 if (skip) idx = d.ph.idx[i];
                 CellState c = load_cell_state(d.cells, idx);
                 int terr = 0;
+                const FallbackRng fr = {d.k0, k1, (uint32_t)j, iter, d.replay};
                 const double tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, d.ph.p1[i], d.ph.p2[i],
-                                                 d.ph.p3[i], d.ph.c0[i], &terr);
+                                                 d.ph.p3[i], d.ph.c0[i], &terr, &fr);
                 if (terr) raise_error(d.gs, MCRAT_B200_ERR_TABLE, i, ERR_SITE_PASS_TABLE);
                 store_tau(d.ph, i, tau);
                 ntau = -1.0 / tau;

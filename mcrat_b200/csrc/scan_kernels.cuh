@@ -380,7 +380,8 @@ __device__ __forceinline__ bool finish_one(DevCtx &d, ShardState &sh, const int 
         d.ph.c2[i] = pc[2];
         d.ph.c3[i] = pc[3];
         int terr = 0;
-        double tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, p[1], p[2], p[3], pc[0], &terr);
+        const FallbackRng fr = {d.k0, d.k1 ^ (d.shard_base + (uint32_t)s), (uint32_t)(i - sh.first), sh.iter, d.replay};
+        double tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, r0, r1, p[1], p[2], p[3], pc[0], &terr, &fr);
         if (terr) raise_error(d.gs, MCRAT_B200_ERR_TABLE, i, ERR_SITE_FINISH_TABLE);
         store_tau(d.ph, i, tau);
         d.ph.flags[i] = d.ph.flags[i] & ~F_RECALC;
@@ -470,8 +471,9 @@ __global__ void __launch_bounds__(256) mfp_kernel(DevCtx d, int write_blockmin)
         if (flags & F_RECALC) {
             CellState c = load_cell_state(d.cells, idx);
             int terr = 0;
+            const FallbackRng fr = {d.k0, d.k1 ^ d.shard_base, (uint32_t)i, sh.iter, d.replay};
             tau = optical_depth(d.dims, d.geom, d.tau_calc, d.table, c, d.ph.r0[i], d.ph.r1[i], d.ph.p1[i], d.ph.p2[i],
-                                d.ph.p3[i], d.ph.c0[i], &terr);
+                                d.ph.p3[i], d.ph.c0[i], &terr, &fr);
             if (terr) raise_error(d.gs, MCRAT_B200_ERR_TABLE, i, ERR_SITE_MFP_TABLE);
             store_tau(d.ph, i, tau);
             d.ph.flags[i] = flags & ~F_RECALC;

@@ -75,6 +75,7 @@ struct CellCols {
     const double4 *geoA; // 2-D: (c0, c1, h0, h1); 3-D: (c0, c1, c2, h0)     h = 0.5 * size
     const double2 *geoB; // 3-D: (h1, h2)
     const double *r0, *r1, *r2, *v0, *v1, *v2, *dens, *dens_lab, *temp, *gamma, *B0, *B1, *B2;
+    const double *s0, *s1, *s2; // r0_size, r1_size, r2_size as uploaded (cyclo-synchrotron emission: corners, volumes)
     double *k2; // K_2(1/theta) of the cell's temperature (Src/electron.c:215), filled on first use; 0 = not yet
     double dom[6];
     // optional two-level bounding-box index over consecutive cells (BOX_T cells per level-1 box,
@@ -95,6 +96,7 @@ struct ShardState {
     unsigned long long iter;
     unsigned long long path; // length of all pushes before the pending ones, in 1/PATH_SCALE cm, rounded up (path_units)
     long long scatt_cnt, reloc_total, slots, iters_done;
+    unsigned long long last_event_draw; // draws the last event took from its Philox stream (step API: the pool replacement continues there)
     int n_dt, pushed_slot; // pushed_slot: global slot index
     int done, pause_cs, counted_stopped;
     int last_scattered_idx, head_idx; // global slot indices

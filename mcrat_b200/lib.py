@@ -74,6 +74,7 @@ EXPORTS = [
     "mcrat_b200_rebin_cyclosynch_comp_photons", "mcrat_b200_set_cs_rebin_params", "mcrat_b200_get_kernel_times",
     "mcrat_b200_launch_count", "mcrat_b200_rescan_all", "mcrat_b200_measure_fp64_peak", "mcrat_b200_measure_hbm_peak",
     "mcrat_b200_selftest_div_by_c", "mcrat_b200_set_recheck_skip", "mcrat_b200_set_profile",
+    "mcrat_b200_photon_emit_cyclosynch", "mcrat_b200_photon_emit_cyclosynch_single",
 ]
 
 
@@ -261,6 +262,20 @@ class HotPath:
         na, ns, w = C.c_int(0), C.c_int(0), C.c_double(0)
         self._ck(self.L.mcrat_b200_ph_abs_cyclosynch(self.ctx, C.byref(na), C.byref(ns), C.byref(w)))
         return w.value, na.value, ns.value
+
+    def photonEmitCyclosynch(self, r_inj, ph_weight, maximum_photons, theta_min, theta_max):
+        """All-cells mode (inject_single_switch = 0) -> (photons emitted, adjusted weight, cells in the shell)."""
+        n, w, nc = C.c_int(0), C.c_double(0), C.c_int(0)
+        self._ck(self.L.mcrat_b200_photon_emit_cyclosynch(self.ctx, C.c_double(r_inj), C.c_double(ph_weight), C.c_int(maximum_photons),
+                                                          C.c_double(theta_min), C.c_double(theta_max), C.byref(n), C.byref(w),
+                                                          C.byref(nc)))
+        return n.value, w.value, nc.value
+
+    def photonEmitCyclosynchSingle(self, scatt_ph_index):
+        """inject_single_switch = 1 -> slot of the new pool photon."""
+        slot = C.c_int(-1)
+        self._ck(self.L.mcrat_b200_photon_emit_cyclosynch_single(self.ctx, C.c_int(scatt_ph_index), C.byref(slot)))
+        return slot.value
 
     def rebinCyclosynchCompPhotons(self, max_photons):
         """-> (number of empty bins, num_cyclosynch_ph_emit, scatt_cyclosynch_num_ph), Src/mc_cyclosynch.c:600-710"""

@@ -281,6 +281,21 @@ static double philox_uniform(mc_rng *r)
         mc_philox_doubles(ctr, r->key, d);
         return rng_note(r, d[0]);
     }
+    if (r->hint_stream >= 3) {
+        /* keyed side streams, counter (draw / 2, iter_lo, slot, stream + 8 * iter_hi):
+         *   3  Monte Carlo integral of an out-of-table hot cross section (slot = photon slot, iter = loop iteration)
+         *   4  Poisson count of a cell in photonEmitCyclosynch (slot = rank of the cell among the selected ones,
+         *      iter = emission call << 32 | weight-search pass)
+         *   5  direction / azimuth draws of an emitted photon (slot = index of the photon, iter = emission call << 32) */
+        ctr[0] = (uint32_t)(r->hint_draw >> 1);
+        ctr[1] = (uint32_t)r->hint_iter;
+        ctr[2] = r->hint_slot;
+        ctr[3] = r->hint_stream + ((uint32_t)(r->hint_iter >> 32) << 3);
+        mc_philox_doubles(ctr, r->key, d);
+        double v = d[r->hint_draw & 1u];
+        r->hint_draw++;
+        return rng_note(r, v);
+    }
     ctr[0] = (uint32_t)(r->hint_draw >> 1);
     ctr[1] = (uint32_t)r->hint_iter;
     ctr[2] = (uint32_t)(r->hint_iter >> 32);
@@ -317,6 +332,14 @@ void mc_rng_hint_mfp(mc_rng *r, uint64_t iter, uint32_t slot)
     r->hint_stream = 0;
     r->hint_iter = iter;
     r->hint_slot = slot;
+}
+
+void mc_rng_hint_keyed(mc_rng *r, uint32_t stream, uint32_t slot, uint64_t iter)
+{
+    r->hint_stream = stream;
+    r->hint_slot = slot;
+    r->hint_iter = iter;
+    r->hint_draw = 0;
 }
 
 void mc_rng_hint_event(mc_rng *r, uint64_t event)

@@ -87,6 +87,7 @@ void mc_rng_init_philox(mc_rng *r, uint64_t seed, uint32_t shard);
 void mc_rng_set_tee(mc_rng *r, double *buf, size_t cap);
 /* stream selection for keyed generators (no-ops for sequential ones) */
 void mc_rng_hint_mfp(mc_rng *r, uint64_t iter, uint32_t slot);
+void mc_rng_hint_keyed(mc_rng *r, uint32_t stream, uint32_t slot, uint64_t iter);
 void mc_rng_hint_event(mc_rng *r, uint64_t event);
 
 double mc_ran_gaussian(mc_rng *r, double sigma);

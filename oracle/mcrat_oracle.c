@@ -422,7 +422,19 @@ double mc_total_thermal_cross_section(double ph_comv, double theta, mc_rng *rng)
     struct mj_params params = {ph_comv, theta};
     if (theta < pow(10, MC_LOG_T_MIN) && ph_comv < pow(10, MC_LOG_PH_E_MIN)) return 1;
     if (theta < pow(10, MC_LOG_T_MIN)) return mc_klein_nishina_cross_section(ph_comv);
-    mc_monte_plain(thermal_integrand, &params, xl, xu, 2, 500000, rng, &result, &error);
+    if (rng->kind == MC_RNG_PHILOX) {
+        /* keyed generators draw the integral's samples from a stream of its own, (sample, iteration, slot, 3): what the
+         * device does (total_thermal_cross_section_mc in mcrat_b200/csrc/device_math.cuh) */
+        const uint32_t stream = rng->hint_stream;
+        const uint64_t draw = rng->hint_draw;
+        rng->hint_stream = 3;
+        rng->hint_draw = 0;
+        mc_monte_plain(thermal_integrand, &params, xl, xu, 2, 500000, rng, &result, &error);
+        rng->hint_stream = stream;
+        rng->hint_draw = draw;
+    } else {
+        mc_monte_plain(thermal_integrand, &params, xl, xu, 2, 500000, rng, &result, &error);
+    }
     return 0.5 * result;
 }
 
@@ -536,6 +548,7 @@ int mc_find_containing_hydro_cell(mc_oracle *o, mc_photon_list *l, const mc_hydr
                     ph->comv_p1 = ph_p_comv[1];
                     ph->comv_p2 = ph_p_comv[2];
                     ph->comv_p3 = ph_p_comv[3];
+                    if (rng) mc_rng_hint_mfp(rng, o->iter, (uint32_t)i); /* keyed generators: (slot, iteration) of a table fall-back */
                     mc_calculate_optical_depth(o, ph, h, rng);
                     if (ph->recalc_properties == 1) ph->recalc_properties = 0;
                     count += 1;
@@ -1342,6 +1355,7 @@ int mc_photon_emit_cyclosynch(mc_oracle *o, mc_photon_list *l, double r_inj, dou
     double ph_weight_adjusted = 0, position_phi = 0, nu_c = 0, error = 0, ph_dens_calc = 0, b_field = 0;
     double ri = 0, ro = 0, ti = 0, to = 0, params[3];
     int block_cnt = 0, i, j = 0, k = 0, *ph_dens = NULL, ph_tot = 0, net_ph = 0, min_photons = 1, idx = 0;
+    unsigned int search_pass = 0;
     mc_photon *ph_emit = NULL;
     const int dims = o->cfg.dimensions;
 
@@ -1357,9 +1371,11 @@ int mc_photon_emit_cyclosynch(mc_oracle *o, mc_photon_list *l, double r_inj, dou
         j = 0;
         ph_tot = -1;
         ph_weight_adjusted = ph_weight;
+        o->emit_epoch += 1;
         while ((ph_tot > max_photons) || (ph_tot < min_photons)) {
             j = 0;
             ph_tot = 0;
+            search_pass += 1;
             for (i = 0; i < h->num_elements; i++) {
                 cell_corners(o, h, i, &ri, &ti, &ro, &to);
                 if ((rmin <= ro) && (ri < rmax) && (to >= theta_min) && (ti < theta_max)) {
@@ -1370,6 +1386,9 @@ int mc_photon_emit_cyclosynch(mc_oracle *o, mc_photon_list *l, double r_inj, dou
                     params[2] = h->dens[i] / M_P;
                     mc_integrate_adaptive(blackbody_ph_spect, params, 10, nu_c, 0, 1e-2, 10000, &ph_dens_calc, &error);
                     ph_dens_calc *= mc_hydro_element_volume(o, h, i) / (ph_weight_adjusted);
+                    /* keyed generators: one stream per selected cell and weight-search pass (the device draws them in parallel) */
+                    if (rng->kind == MC_RNG_PHILOX)
+                        mc_rng_hint_keyed(rng, 4, (uint32_t)j, ((uint64_t)o->emit_epoch << 32) | (uint64_t)(search_pass - 1));
                     ph_dens[j] = (int)mc_ran_poisson(rng, ph_dens_calc);
                     ph_tot += ph_dens[j];
                     j++;
@@ -1395,6 +1414,7 @@ int mc_photon_emit_cyclosynch(mc_oracle *o, mc_photon_list *l, double r_inj, dou
                 b_field = mc_magnetic_field_magnitude(o, h, i);
                 nu_c = mc_calc_cyclotron_freq(b_field);
                 for (j = 0; j < ph_dens[k]; j++) {
+                    if (rng->kind == MC_RNG_PHILOX) mc_rng_hint_keyed(rng, 5, (uint32_t)ph_tot, (uint64_t)o->emit_epoch << 32);
                     fill_emitted_photon(o, &ph_emit[ph_tot], h, i, nu_c, ph_weight_adjusted, 0, rng, &position_phi);
                     ph_tot++;
                     if (net_ph == ph_tot) i = h->num_elements;
@@ -1423,6 +1443,7 @@ int mc_photon_emit_cyclosynch(mc_oracle *o, mc_photon_list *l, double r_inj, dou
         idx = 0;
         (void)idx;
     }
+    o->last_emit_weight = ph_weight_adjusted;
     mc_list_add(l, ph_emit, (size_t)ph_tot);
     free(ph_dens);
     free(ph_emit);

@@ -98,6 +98,10 @@ typedef struct mc_oracle {
     double za[(MC_N_PH_E + 1) * (MC_N_T + 1)]; /* za[j*(N_PH_E+1)+i] = table[i][j] */
     /* while-loop iteration counter: stream key for keyed generators */
     unsigned long long iter;
+    /* photonEmitCyclosynch (all cells) calls so far: part of the key of the keyed emission streams; and the weight
+     * the last call settled on (ph_weight_adjusted) */
+    unsigned int emit_epoch;
+    double last_emit_weight;
     FILE *log;
     long long checkinblock_evals; /* instrumentation: containment tests executed */
 } mc_oracle;

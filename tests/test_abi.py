@@ -32,8 +32,11 @@ def test_dropin_exports_reference_surface():
     names = _declared("mcrat_b200_dropin.h")
     for n in names:
         assert hasattr(D, n), "libmcrat_b200_dropin.so does not export %s" % n
+    # every function of SURVEY 8(b) the driver calls inside the hydro-frame loop (Src/mcrat.c:585-931)
     for ref_fn in ("findContainingHydroCell", "calcMeanFreePath", "photonEvent", "updatePhotonPosition",
-                   "averagePhotonEnergy", "phAbsCyclosynch"):
+                   "averagePhotonEnergy", "phAbsCyclosynch", "phMinMax", "phScattStats", "calcCyclosynchRLimits",
+                   "rebinCyclosynchCompPhotons", "photonEmitCyclosynch", "initalizeHotCrossSection",
+                   "cleanupInterpolationData"):
         assert "__wrap_" + ref_fn in names
 
 

@@ -571,3 +571,247 @@ def test_c1_at_full_baseline_size_replays_the_reference_sources():
     for k in ("iterations", "scatterings", "relocations"):
         assert st[k] == ost[k], (k, st, ost)
     compare_photons(hp.get_photons(), eng.photons(), label="C1 full size vs _ref")
+
+
+@pytest.mark.parametrize("loop", ["streamed", "persistent"])
+def test_hot_cross_section_outside_the_table_is_integrated_on_the_device(loop):
+    """A lookup outside the 221 x 81 table (here: photons of x = h nu / m c^2 = 1e-14, below the table's 1e-12) makes the
+    reference integrate the cross section by plain Monte Carlo on the spot (Src/hot_x_section.c:563-599 -> :324-357,
+    500 000 samples).  Round 1 reported MCRAT_B200_ERR_TABLE; the device now does the integral from a keyed stream of
+    its own, sample for sample like gsl_monte_plain, and the oracle draws the same stream."""
+    cfg, hydro, photons, frame = synth.workload("C3", scale=1.0 / 16, n_photons=240, seed=17)
+    ph = photons.copy()
+    cold = np.arange(5, 240, 40)  # six photons far below the table's energy range
+    f = 1e-14 * synth.M_EL * synth.C_LIGHT / ph["comv_p0"][cold]
+    for k in ("p0", "p1", "p2", "p3", "comv_p0", "comv_p1", "comv_p2", "comv_p3"):
+        ph[k][cold] *= f
+    tab = _table()
+    hp = HotPath(cfg, seed=9, shard=4, loop_mode=loop, num_shards=2 if loop == "persistent" else 1)
+    hp.set_thermal_table(tab)
+    hp.set_hydro(hydro)
+    hp.set_photons(ph)
+    st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=12, switch=1)  # round 1: McratB200Error ERR_TABLE
+    got = hp.get_photons()
+    assert st["error"] == 0 and st["iterations"] == 12
+    ss = hp.shard_stats(0)
+    sl = slice(ss["first_slot"], ss["first_slot"] + ss["num_slots"])
+    o = api.Oracle(cfg, table=tab)
+    o.set_hydro(hydro)
+    o.set_photons(ph[sl])
+    ost = o.run_frame(api.OracleRng("philox", seed=9, shard=4), frame["time_now"], 1.0 / frame["fps"], max_iters=12)
+    assert ss["scatterings"] == ost["scatterings"]
+    want = o.photons()
+    compare_photons(got[sl], want, label="table fall-back")
+    # the integral really is what stands behind those optical depths: sigma / sigma_T ~ 1 for such soft photons
+    idx = want["nearest_block_index"][cold[cold < ss["num_slots"]]]
+    assert np.all(idx >= 0)
+
+
+def _cs_emit_case(three, dead_fraction=0.2):
+    if three:
+        cfg, hydro, photons, frame = synth.workload("C4", scale=1.0 / 8, n_photons=600, seed=8)
+        refname, r_inj = "c4_3d_sph_cs", 1e12
+    else:
+        cfg, hydro, photons, frame = synth.workload("C2", scale=1.0 / 16, n_photons=600, seed=8)
+        cfg = dict(cfg, cyclosynch=1, b_field_calc=0)  # g_2d_cyl_cs: B from the internal energy, epsilon_B = 0.5
+        synth.toroidal_b_field(hydro, r_ref=2e12)
+        refname, r_inj = "g_2d_cyl_cs", 2e12
+    hydro["scatt_frame_number"], hydro["inj_frame_number"] = 3, 2
+    # a list in mid-run: a fifth of the slots are null photons (absorbed earlier), scattered irregularly
+    ph = photons.copy()
+    rng = np.random.default_rng(3)
+    dead = rng.random(ph.size) < dead_fraction
+    ph["type"][dead] = b"N"
+    ph["weight"][dead] = 0
+    ph["nearest_block_index"][dead] = -1
+    for f in ("p0", "p1", "p2", "p3", "comv_p0", "comv_p1", "comv_p2", "comv_p3", "r0", "r1", "r2", "s0", "s1", "s2", "s3"):
+        ph[f][dead] = 0
+    args = dict(r_inj=r_inj - 2.99792458e10 / 5, ph_weight=1e48, theta_min=0.0, theta_max=0.2)
+    return cfg, hydro, ph, frame, refname, args
+
+
+@pytest.mark.parametrize("three", [True, False])
+@pytest.mark.parametrize("ph_weight,max_photons,dead", [(1e48, 600, 0.2), (1e43, 600, 0.2), (1e43, 6000, 0.0)])
+def test_cyclosynchrotron_emission_into_all_cells_on_the_device(three, ph_weight, max_photons, dead):
+    """K6 = photonEmitCyclosynch(..., inject_single_switch = 0), Src/mc_cyclosynch.c:1176-1464: shell selection, black-body
+    tail integral, weight search with Poisson counts, placement into the null slots -- against the oracle drawing the same
+    keyed streams (per cell and pass, per photon).  A suggested weight of 1e48 is too large (no photon: the search halves
+    it), 1e43 too small (the search multiplies it by 10 until at most 0.1 max_photons are emitted); with a list without
+    null slots the list grows (addToPhotonList doubles a full list, Src/photons.c:117-129)."""
+    cfg, hydro, ph, frame, refname, args = _cs_emit_case(three, dead)
+    args["ph_weight"] = ph_weight
+    hp = HotPath(cfg, seed=21, shard=6)
+    hp.set_hydro(hydro)
+    hp.set_photons(ph)
+    n, w, ncells = hp.photonEmitCyclosynch(args["r_inj"], args["ph_weight"], max_photons, args["theta_min"], args["theta_max"])
+    got = hp.get_photons()
+    o = api.Oracle(cfg)
+    o.set_hydro(hydro)
+    o.set_photons(ph)
+    orng = api.OracleRng("philox", seed=21, shard=6)
+    n_o = o.photon_emit_cyclosynch(orng, max_photons=max_photons, **args)
+    want = o.photons()
+    assert n == n_o and n > 0 and ncells > 0, (n, n_o, ncells)
+    assert n <= 0.1 * max_photons
+    m = min(got.size, want.size)  # capacities may differ (both grow; only trailing null slots differ)
+    assert np.all(got["type"][m:] == b"N") and np.all(want["type"][m:] == b"N")
+    g, wv = got[:m], want[:m]
+    assert np.array_equal(g["type"], wv["type"]) and np.array_equal(g["weight"], wv["weight"])
+    new = (wv["type"] == b"p")
+    assert new.sum() == n and np.all(g["weight"][new] == w)
+    for f in ("p0", "p1", "p2", "p3", "comv_p0", "comv_p1", "comv_p2", "comv_p3"):
+        scale = np.abs(wv["p0" if f[0] == "p" else "comv_p0"])
+        assert np.all(np.abs(g[f] - wv[f]) <= 1e-11 * np.maximum(scale, 1e-300)), f
+    rn = np.sqrt(wv["r0"] ** 2 + wv["r1"] ** 2 + wv["r2"] ** 2)
+    for f in ("r0", "r1", "r2"):
+        assert np.all(np.abs(g[f] - wv[f]) <= 1e-12 * np.maximum(rn, 1e-300)), f
+    for f in ("s0", "s1", "s2", "s3", "num_scatt", "nearest_block_index", "recalc_properties"):
+        assert np.array_equal(g[f], wv[f]), f
+    # and the frame loop runs on the list the device has just extended
+    st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=30, switch=1)
+    assert st["iterations"] == 30 and st["error"] == 0
+
+
+@pytest.mark.parametrize("three", [True, False])
+def test_cyclosynchrotron_emission_replays_the_reference_stream(three):
+    """The same call against the reference's own photonEmitCyclosynch (oracle/_ref) fed from a tee'd RANLXS0 stream:
+    the device consumes the recorded uniforms in the reference's order (Poisson draws cell by cell and pass by pass,
+    then three (3-D: two) draws per photon)."""
+    cfg, hydro, ph, frame, refname, args = _cs_emit_case(three)
+    for seed in range(5, 60):
+        if api.ref_available(refname):
+            eng = api.RefLib(refname)
+            eng.set_hydro(hydro)
+            eng.set_photons(ph)
+            rng, tee = eng.new_rng(seed=seed, tee=4_000_000)
+            n_ref = eng.photon_emit_cyclosynch(rng, max_photons=600, **args)
+            u = eng.tee_values(rng, tee)
+        else:
+            eng = api.Oracle(cfg)
+            eng.set_hydro(hydro)
+            eng.set_photons(ph)
+            rng = api.OracleRng("ranlxs0", seed=seed)
+            rng.tee(4_000_000)
+            n_ref = eng.photon_emit_cyclosynch(rng, max_photons=600, **args)
+            u = rng.tee_values()
+        if not np.any(u == 0.0):
+            break
+    want = eng.photons()
+    hp = HotPath(cfg, rng_mode=lib.RNG_REPLAY)
+    hp.set_hydro(hydro)
+    hp.set_photons(ph)
+    hp.set_replay_uniforms(u)
+    n, w, ncells = hp.photonEmitCyclosynch(args["r_inj"], args["ph_weight"], 600, args["theta_min"], args["theta_max"])
+    assert n == n_ref and n > 0
+    assert hp.replay_consumed() == u.size
+    got = hp.get_photons()
+    m = min(got.size, want.size)
+    g, wv = got[:m], want[:m]
+    assert np.array_equal(g["type"], wv["type"]) and np.array_equal(g["weight"], wv["weight"])
+    for f in ("p0", "p1", "p2", "p3"):
+        assert np.all(np.abs(g[f] - wv[f]) <= 1e-11 * np.abs(wv["p0"])), f
+    for f in ("r0", "r1", "r2"):
+        assert np.all(np.abs(g[f] - wv[f]) <= 1e-12 * np.sqrt(wv["r0"] ** 2 + wv["r1"] ** 2 + wv["r2"] ** 2 + 1e-300)), f
+
+
+def test_dropin_covers_the_cyclosynchrotron_calls_of_the_driver(tmp_path):
+    """The rest of SURVEY 8(b) through libmcrat_b200_dropin.so, in the order Src/mcrat.c:704-881 calls it with
+    CYCLOSYNCHROTRON_SWITCH ON: phMinMax, phScattStats, photonEmitCyclosynch (all cells), the loop with a pool replacement
+    (photonEmitCyclosynch single), rebinCyclosynchCompPhotons, phAbsCyclosynch; and initalizeHotCrossSection reading a
+    table file in the reference's layout."""
+    D = C.CDLL(lib.DROPIN_PATH)
+    D.__wrap_photonEvent.restype = C.c_double
+    D.__wrap_phAbsCyclosynch.restype = C.c_double
+    D.__wrap_calcCyclosynchRLimits.restype = C.c_double
+    cfg, hydro, ph, frame, refname, args = _cs_emit_case(True)
+
+    class PL(C.Structure):
+        _fields_ = [("photons", C.c_void_p), ("sorted_indexes", C.POINTER(C.c_int)), ("num_photons", C.c_int),
+                    ("num_null_photons", C.c_int), ("list_capacity", C.c_int)]
+
+    class HD(C.Structure):
+        _fields_ = ([("num_elements", C.c_int)] + [(f, C.POINTER(C.c_double)) for f in lib.HYDRO_FIELDS] +
+                    [("r0_domain", C.c_double * 2), ("r1_domain", C.c_double * 2), ("r2_domain", C.c_double * 2),
+                     ("fps", C.c_double), ("scatt_frame_number", C.c_int), ("inj_frame_number", C.c_int),
+                     ("last_frame", C.c_int), ("increment_inj_frame", C.c_int), ("increment_scatt_frame", C.c_int),
+                     ("grid", C.c_void_p)])
+
+    c = lib.Config(lib.ABI_VERSION, cfg["dimensions"], cfg["geometry"], cfg["stokes"], cfg["tau_calculation"],
+                   cfg["cyclosynch"], cfg["b_field_calc"], cfg["epsilon_b"], 0, 0, 4711, 0, 0, None, 0)
+    assert D.mcrat_b200_dropin_configure(C.byref(c)) == 0
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    n = ph.size
+    buf = libc.malloc(C.c_size_t(n * 176))  # the wrappers realloc() the list like addToPhotonList does
+    C.memmove(buf, ph.ctypes.data, n * 176)
+    sidx = libc.malloc(C.c_size_t(n * 4))
+    nulls = int((ph["type"] == b"N").sum())
+    pl = PL(buf, C.cast(sidx, C.POINTER(C.c_int)), n - nulls, nulls, n)
+    keep = {f: np.ascontiguousarray(hydro[f], dtype=np.float64) for f in lib.HYDRO_FIELDS}
+    h = HD()
+    h.num_elements = int(hydro["num_elements"])
+    for f in lib.HYDRO_FIELDS:
+        setattr(h, f, keep[f].ctypes.data_as(C.POINTER(C.c_double)))
+    for k in ("r0_domain", "r1_domain", "r2_domain"):
+        getattr(h, k)[0], getattr(h, k)[1] = hydro[k]
+    h.fps, h.scatt_frame_number, h.inj_frame_number, h.increment_scatt_frame = 5.0, 3, 2, 1
+    v = [C.c_double(0) for _ in range(4)]
+    D.__wrap_phMinMax(C.byref(pl), *[C.byref(x) for x in v], None)
+    live = ph[ph["weight"] != 0]
+    rr = np.sqrt(live["r0"] ** 2 + live["r1"] ** 2 + live["r2"] ** 2)
+    assert abs(v[0].value - rr.min()) <= 1e-12 * rr.min() and abs(v[1].value - rr.max()) <= 1e-12 * rr.max()
+    assert abs(D.__wrap_calcCyclosynchRLimits(3, 2, C.c_double(5.0), C.c_double(1e12), b"max") -
+               (1e12 + 2.99792458e10 * (3 - 2) / 5.0 + 0.5 * 2.99792458e10 / 5.0)) < 1.0
+    emitted = D.__wrap_photonEmitCyclosynch(C.byref(pl), C.c_double(args["r_inj"]), C.c_double(1e43), C.c_int(600),
+                                            C.c_double(0.0), C.c_double(0.2), C.byref(h), None, C.c_int(0), C.c_int(0), None)
+    assert 0 < emitted <= 60
+    host = np.ctypeslib.as_array(C.cast(pl.photons, C.POINTER(C.c_uint8)), shape=(pl.list_capacity * 176,)).view(lib.PHOTON_DTYPE)
+    assert int((host["type"] == b"p").sum()) == emitted and pl.num_null_photons == nulls - emitted
+    mx, mn, avg, ravg = C.c_int(0), C.c_int(0), C.c_double(0), C.c_double(0)
+    D.__wrap_phScattStats(C.byref(pl), C.byref(mx), C.byref(mn), C.byref(avg), C.byref(ravg), None)
+    assert mx.value == 0 and mn.value == 0
+    # the loop, call by call, until a pool photon scatters (Src/mcrat.c:768-803)
+    D.__wrap_findContainingHydroCell(C.byref(pl), C.byref(h), C.c_int(1), None, None)
+    replaced = 0
+    scatt, ab, idx = C.c_int(0), C.c_int(0), C.c_int(0)
+    for it in range(4000):
+        if it:
+            D.__wrap_findContainingHydroCell(C.byref(pl), C.byref(h), C.c_int(0), None, None)
+        D.__wrap_calcMeanFreePath(C.byref(pl), C.byref(h), None, None)
+        D.__wrap_photonEvent(C.byref(pl), C.c_double(0.2), C.byref(h), C.byref(idx), C.byref(scatt), C.byref(ab), None, None)
+        host = np.ctypeslib.as_array(C.cast(pl.photons, C.POINTER(C.c_uint8)), shape=(pl.list_capacity * 176,)).view(lib.PHOTON_DTYPE)
+        if host["type"][idx.value] == b"p":
+            host["type"][idx.value] = b"k"  # the driver's own line, Src/mcrat.c:795
+            before = pl.num_photons
+            got = D.__wrap_photonEmitCyclosynch(C.byref(pl), C.c_double(args["r_inj"]), C.c_double(1e43), C.c_int(600),
+                                                C.c_double(0.0), C.c_double(0.2), C.byref(h), None, C.c_int(1), idx, None)
+            assert got == 1 and pl.num_photons == before + 1
+            replaced += 1
+            if replaced == 2:
+                break
+    assert replaced == 2, "no pool photon scattered in 4000 iterations"
+    host = np.ctypeslib.as_array(C.cast(pl.photons, C.POINTER(C.c_uint8)), shape=(pl.list_capacity * 176,)).view(lib.PHOTON_DTYPE)
+    assert int((host["type"] == b"p").sum()) == emitted and int((host["type"] == b"k").sum()) == 2
+    # the whole list as the device holds it agrees with the host copy the wrappers kept up to date
+    D.mcrat_b200_dropin_context.restype = C.c_void_p
+    L = lib.load()  # coarse rebin angles: 60 energy bins x 1 x 1 <= max_photons (Src/mc_cyclosynch.c:637)
+    assert L.mcrat_b200_set_cs_rebin_params(C.c_void_p(D.mcrat_b200_dropin_context()), C.c_double(0.1), C.c_double(90.0),
+                                            C.c_double(360.0)) == 0
+    emit, sc = C.c_int(emitted), C.c_int(2)
+    nnull = D.__wrap_rebinCyclosynchCompPhotons(C.byref(pl), C.byref(emit), C.byref(sc), C.c_int(600), C.c_double(0), C.c_double(0.2),
+                                                None, None)
+    host = np.ctypeslib.as_array(C.cast(pl.photons, C.POINTER(C.c_uint8)), shape=(pl.list_capacity * 176,)).view(lib.PHOTON_DTYPE)
+    # 60 energy bins x 1 x 1; every non-empty bin became one weighted-mean photon of type COMPTONIZED ('k', Src/mc_cyclosynch.c:575)
+    assert 0 <= nnull < 60 and int((host["type"] == b"k").sum()) == 60 - nnull and sc.value == 60 - nnull
+    na, ns = C.c_int(0), C.c_int(0)
+    D.__wrap_phAbsCyclosynch(C.byref(pl), C.byref(na), C.byref(ns), C.byref(h), None)
+    host = np.ctypeslib.as_array(C.cast(pl.photons, C.POINTER(C.c_uint8)), shape=(pl.list_capacity * 176,)).view(lib.PHOTON_DTYPE)
+    assert int((host["type"] == b"p").sum()) == 0 and na.value >= emitted
+    # hot cross-section table file in the reference's layout
+    from mcrat_b200 import hotxs
+    path = str(tmp_path / "thermal_hot_x_section.dat")
+    hotxs.write_table(path, _table())
+    D.mcrat_b200_dropin_set_table_path(path.encode())
+    D.__wrap_initalizeHotCrossSection(C.c_int(0), None, None)
+    D.__wrap_cleanupInterpolationData()
+    D.mcrat_b200_dropin_shutdown()
