@@ -363,6 +363,16 @@ def main():
                  scan_index=args.index, loop_mode=args.loop)
     hp.set_hydro(hydro)
     hp.set_photons(photons)
+    # product-side communicator (include/mcrat_b200.h, mcrat_b200_comm_*): per-frame counter reduction inside the timed
+    # steps, photon-count gather and the photon gather for the merged output measured once below
+    from mcrat_b200 import Comm
+    comm, comm_err = None, None
+    try:
+        comm = Comm.from_torch_dist(hp, dist if world > 1 else None)
+    except Exception as exc:
+        if world > 1:
+            raise
+        comm_err = str(exc)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     dt_frame = 1.0 / frame["fps"]
     config["photons_this_gpu"] = int(photons.size)
@@ -380,7 +390,7 @@ def main():
         clocks.start()
     launches0 = hp.launch_count()
     tot_ms = 0.0
-    scatt = evals = slots = ref_evals = 0
+    scatt = evals = slots = ref_evals = job_scatt = 0
     barrier()
     for _ in range(args.steps):
         flush_buf.fill_(1)
@@ -388,6 +398,10 @@ def main():
         torch.cuda.synchronize()
         e0.record()
         st = hp.run_frame(time_now, dt_frame, max_iters=args.iters, switch=1)
+        if comm is not None:
+            job_st = comm.reduce_frame_stats(st)   # the frame's counters over all GPUs (NCCL, on the context's stream)
+        else:
+            job_st = st
         e1.record()
         torch.cuda.synchronize()
         tot_ms += e0.elapsed_time(e1)
@@ -396,6 +410,7 @@ def main():
         evals += st["cell_evals"]
         slots += st["photon_slots"]
         ref_evals += st["ref_equiv_evals"]
+        job_scatt += job_st["scatterings"]
     barrier()
     launches = hp.launch_count() - launches0
 
@@ -424,6 +439,8 @@ def main():
     hp.set_profile(False)
     pass_ms = kt["pass_ms"] / max(kt["pass_launches"], 1)
     event_ms = kt["event_ms"] / max(kt["event_launches"], 1)
+    # photons one pass launch covers: the interleaved streamed loop launches the pass per half of the ranks
+    pass_photons = st["photon_slots"] / max(kt["pass_launches"], 1)
 
     log("loop %.1f us/iteration (pass %.1f us, event %.1f us in profile mode); scan roofline" % (loop_us, 1e3 * pass_ms, 1e3 * event_ms))
     # ---- roofline of the kernel that owns the step (K1 scan), timed alone with CUDA events on its stream ----
@@ -459,13 +476,14 @@ def main():
                 "algorithmic": "%d FP64-pipe instr per photon-cell eval x %d evals per launch" % (instr_per_eval, scan_evals),
                 "evals_per_s": scan_evals / (scan_ms_avg * 1e-3), "ms_per_launch": scan_ms_avg, "share_of_step": k1_share}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    pass_gbs = photons.size * BYTES_PER_PHOTON_ITERATION / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else None
-    pass_roofline = {"kernel": "pass_kernel<fused> (K4+K2: push + re-check + free-path draw + block arg-min) over %d photons" % photons.size,
+    pass_gbs = pass_photons * BYTES_PER_PHOTON_ITERATION / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else None
+    pass_roofline = {"kernel": "pass kernel (K4+K2: push + re-check + free-path draw + block arg-min), %d photons per launch "
+                               "(%d launches per iteration of the %d-photon list)" % (pass_photons, round(photons.size / max(pass_photons, 1)), photons.size),
                      "bound": "hbm", "achieved": pass_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": pass_gbs / hbm_peak if pass_gbs else None,
                      "traffic": (json.load(open(tpath)).get("pass_kernel_1e7_bytes") if os.path.exists(tpath) and photons.size == 10_000_000 else None),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
-                     "algorithmic": "100 B per photon-iteration (SURVEY 8d) x %d photons; columns actually moved: 97 B" % photons.size,
+                     "algorithmic": "100 B per photon-iteration (SURVEY 8d) x %d photons per launch; columns actually moved: 97 B" % pass_photons,
                      "ms_per_launch": pass_ms, "event_kernel_ms_per_launch": event_ms,
                      "note": "meaningful while the list exceeds L2 (> 2^21 photons per GPU); below that the pass runs out of L2"}
     loop_roofline = {"kernel": "whole loop iteration (pass + re-locate + finish + event) over %d photons" % photons.size,
@@ -533,6 +551,46 @@ def main():
         barrier()
         e2e_s = time.perf_counter() - t0
 
+    # ---- the exchanges either side of the frame loop, measured once: photon counts, photon gather to rank 0 ----
+    comm_info = {"error": comm_err} if comm is None else None
+    if comm is not None:
+        log("comm: counts + gather")
+        ver = hp.L.mcrat_b200_comm_nccl_version()
+        barrier()
+        t0 = time.perf_counter()
+        cnt = comm.photon_counts()
+        t_counts = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for _ in range(20):
+            comm.reduce_frame_stats(st)
+        t_reduce = (time.perf_counter() - t0) / 20
+        gather_ms, gathered = None, None
+        total_records = int(cnt["list_capacity"].sum())
+        if not args.no_e2e:
+            out = None
+            if rank == 0:
+                out_t = torch.empty(total_records * PHOTON_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+                out = out_t.numpy().view(PHOTON_DTYPE)
+            barrier()
+            t0 = time.perf_counter()
+            allp, counts = comm.gather_photons(root=0, out=out)
+            barrier()
+            gather_ms = 1e3 * (time.perf_counter() - t0)
+            gathered = int(counts.sum())
+            if rank == 0:  # rank order = slot order of the one list the job started from
+                assert allp.size == total_records
+                mine_now = hp.get_photons()
+                assert allp[:mine_now.size].tobytes() == mine_now.tobytes(), "gathered list does not start with rank 0's photons"
+        comm_info = {"library": "NCCL %d.%d.%d (bound at run time)" % (ver // 10000, (ver // 100) % 100, ver % 100), "ranks": comm.size,
+                     "per_step_inside_timed_region": "all-reduce of the frame counters (4 NCCL reductions in one group, 20 words)",
+                     "frame_stats_allreduce_us": 1e6 * t_reduce, "photon_counts_allgather_us": 1e6 * t_counts,
+                     "photons_per_gpu": [int(x) for x in cnt["list_capacity"]],
+                     "output_photons_per_gpu": [int(x) for x in cnt["output_photons"]],
+                     "gather_photons_to_rank0_ms": gather_ms, "gather_records": gathered,
+                     "gather_bytes": None if gathered is None else gathered * PHOTON_DTYPE.itemsize,
+                     "scatterings_per_step_from_the_allreduce": job_scatt / args.steps,
+                     "nccl_operations": comm.collectives()}
+
     # ---- aggregate over ranks ----
     t_max, scatt_all, evals_all, slots_all, e2e_max, e2e_all = tot_ms, scatt, evals, slots, e2e_s, e2e_scatt
     ref_evals_all, loop_slots_all, loop_scatt_all, scan_evals_rate = ref_evals, loop_slots_per_s, loop_scatt_per_s, roofline["evals_per_s"]
@@ -565,11 +623,13 @@ def main():
                 "loop_only": {"scatterings_per_sec": loop_scatt_all, "photon_iterations_per_sec": loop_slots_all,
                               "note": "frame loop without the per-step rescan, %d iterations, summed over GPUs" % probe_iters},
                 "roofline": roofline, "pass_roofline": pass_roofline, "loop_roofline": loop_roofline,
-                "s_sweep": s_sweep, "cpu_baseline": cpu,
+                "s_sweep": s_sweep, "comm": comm_info, "cpu_baseline": cpu,
                 "e2e": None if args.no_e2e else {"value": e2e_all / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                                                  "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_max / args.steps},
                 "gpu_launches": int(launches), "clocks": clk}
         print(json.dumps(line), flush=True)
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -270,6 +270,48 @@ int mcrat_b200_selftest_div_by_c(mcrat_b200_ctx *ctx, long long n, unsigned seed
 /* streaming copy bandwidth of this GPU, GB/s (read+write bytes) */
 int mcrat_b200_measure_hbm_peak(mcrat_b200_ctx *ctx, double *gb_per_s);
 
+/* ---- multi-GPU: the reference's MPI exchanges either side of the frame loop, over NCCL ------------------ */
+/* One process per GPU, one communicator per context.  The frame loop needs no exchange (a GPU's sub-shards are MPI
+ * ranks of the reference, Src/mcrat.c:139-164, 457-479); these calls cover what the reference does exchange.  NCCL is
+ * bound at run time: without it every comm call fails with MCRAT_B200_ERR_STATE, the rest of the library is unaffected.
+ * All calls are collective over the communicator and run on the context's stream. */
+typedef struct mcrat_b200_comm mcrat_b200_comm;
+#define MCRAT_B200_COMM_ID_BYTES 128
+/* ncclGetUniqueId on one rank; the host distributes the bytes (MPI_Bcast in mcrat.c, a store in the test harness) */
+int mcrat_b200_comm_unique_id(unsigned char *id, size_t len);
+int mcrat_b200_comm_nccl_version(void); /* 0: NCCL not available */
+int mcrat_b200_comm_create(mcrat_b200_ctx *ctx, int nranks, int rank, const unsigned char *id, size_t len,
+                           mcrat_b200_comm **out);
+void mcrat_b200_comm_destroy(mcrat_b200_comm *comm);
+int mcrat_b200_comm_rank(const mcrat_b200_comm *comm);
+int mcrat_b200_comm_size(const mcrat_b200_comm *comm);
+long long mcrat_b200_comm_collectives(const mcrat_b200_comm *comm); /* NCCL operations issued so far */
+/* broadcastInterpolationData, Src/hot_x_section.c:709-826 (MPI_Bcast :717): the table installed in `root`'s context
+ * replaces the one of every other rank */
+int mcrat_b200_comm_bcast_thermal_table(mcrat_b200_comm *comm, int root);
+/* createHotCrossSection (Src/hot_x_section.c:82-206) by all GPUs at once: rank r integrates 1/nranks of the table's
+ * points (K7), one all-gather assembles and installs the table on every rank.  Same result as
+ * mcrat_b200_build_thermal_table with the same (calls, seed), whatever the number of ranks. */
+int mcrat_b200_comm_build_thermal_table(mcrat_b200_comm *comm, long long calls, uint64_t seed, double *table_out,
+                                        float *elapsed_ms);
+/* per-frame counters over all ranks: sums of scatterings, relocations, photon_slots, cell_evals, box_evals,
+ * ref_equiv_evals, not_found, cs_emitted, scatt_cyclosynch_num_ph, cs_comptonized_weight; maxima of iterations,
+ * time_now, last_time_step, cs_host_pending; error = the most severe (most negative) error of any rank */
+int mcrat_b200_comm_reduce_frame_stats(mcrat_b200_comm *comm, const mcrat_b200_frame_stats *mine,
+                                       mcrat_b200_frame_stats *total);
+/* per-rank photon counts (load balance; what Src/merge.c:784-790 gathers before the merge): list capacity, photons
+ * with weight != 0 (the ones printPhotons writes, Src/mcrat_io.c:150-160), null slots; arrays of comm_size entries,
+ * any of them may be NULL */
+int mcrat_b200_comm_photon_counts(mcrat_b200_comm *comm, long long *list_capacity, long long *output_photons,
+                                  long long *null_slots);
+/* the photon lists of all ranks concatenated in rank order -- what Src/merge.c:840-876 assembles column by column with
+ * MPI_Allgatherv -- packed on the device and moved GPU to GPU; `root` receives them in `photons` (host memory,
+ * `capacity` records; root = -1: every rank does), ready for mcrat_b200_print_photons.  counts[r] = records of rank r
+ * (may be NULL), *total their sum.  If a receiver's capacity is too small no rank transfers anything, *total says how
+ * much is needed and the call returns MCRAT_B200_ERR_ARG everywhere. */
+int mcrat_b200_comm_gather_photons(mcrat_b200_comm *comm, int root, mcrat_photon *photons, long long capacity,
+                                   long long *counts, long long *total);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,4 +5,4 @@ this package holds the Python harness around it: a ctypes binding (:mod:`mcrat_b
 synthetic BASELINE workloads (:mod:`mcrat_b200.synth`) and shard helpers
 (:mod:`mcrat_b200.shard`)."""
 from . import synth  # noqa: F401
-from .lib import HotPath, McratB200Error, build, load  # noqa: F401
+from .lib import Comm, HotPath, McratB200Error, build, comm_unique_id, load  # noqa: F401

@@ -84,9 +84,9 @@ __global__ void __launch_bounds__(256) cs_absorb_kernel(DevCtx d)
 // [1, 1 + 12 theta] x [-1, 1], integrand = Maxwell-Juttner pdf x boosted KN cross section,
 // result = 0.5 * volume * mean), drawn from a Philox stream keyed by the point.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) hot_table_kernel(double *table, long long calls, uint32_t k0, uint32_t k1)
+__global__ void __launch_bounds__(256) hot_table_kernel(double *table, long long calls, uint32_t k0, uint32_t k1, int point0)
 {
-    const int point = blockIdx.x; // i * (N_T + 1) + j, the reference's loop order (:90-105)
+    const int point = point0 + blockIdx.x; // i * (N_T + 1) + j, the reference's loop order (:90-105); table[] starts at point0
     const int i = point / (N_T + 1), j = point - i * (N_T + 1);
     const double dt = (LOG_T_MAX - LOG_T_MIN) / N_T, dph_e = (LOG_PH_E_MAX - LOG_PH_E_MIN) / N_PH_E;
     const double comv_ph_e = pow(10., LOG_PH_E_MIN + i * dph_e);
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) hot_table_kernel(double *table, long long
         const double vol = (xu0 - xl0) * (1 - (-1));
         result = 0.5 * (vol * (tot / (double)calls));
     }
-    if (threadIdx.x == 0) table[point] = log10(result);
+    if (threadIdx.x == 0) table[blockIdx.x] = log10(result);
 }
 
 // ------------------------------------------------------------------------------------------

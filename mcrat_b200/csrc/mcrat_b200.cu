@@ -1645,7 +1645,7 @@ API int mcrat_b200_build_thermal_table(mcrat_b200_ctx *ctx, long long calls, uin
     double *tab = nullptr;
     CK(cudaMalloc((void **)&tab, npts * sizeof(double)));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    hot_table_kernel<<<npts, 256, 0, ctx->stream>>>(tab, calls, (uint32_t)seed ^ 0x4D435261u, (uint32_t)(seed >> 32));
+    hot_table_kernel<<<npts, 256, 0, ctx->stream>>>(tab, calls, (uint32_t)seed ^ 0x4D435261u, (uint32_t)(seed >> 32), 0);
     if (int rc = check_launch(ctx, "hot_table_kernel")) {
         cudaFree(tab);
         return rc;
@@ -1747,3 +1747,6 @@ API int mcrat_b200_measure_hbm_peak(mcrat_b200_ctx *ctx, double *gb_per_s)
     *gb_per_s = 2.0 * (double)n * sizeof(double4) / (best * 1e-3) / 1e9;
     return MCRAT_B200_OK;
 }
+
+// the reference's MPI exchanges either side of the frame loop, over NCCL
+#include "comm.cuh"

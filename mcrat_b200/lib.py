@@ -75,6 +75,10 @@ EXPORTS = [
     "mcrat_b200_launch_count", "mcrat_b200_rescan_all", "mcrat_b200_measure_fp64_peak", "mcrat_b200_measure_hbm_peak",
     "mcrat_b200_selftest_div_by_c", "mcrat_b200_set_recheck_skip", "mcrat_b200_set_profile",
     "mcrat_b200_photon_emit_cyclosynch", "mcrat_b200_photon_emit_cyclosynch_single",
+    "mcrat_b200_comm_unique_id", "mcrat_b200_comm_nccl_version", "mcrat_b200_comm_create", "mcrat_b200_comm_destroy",
+    "mcrat_b200_comm_rank", "mcrat_b200_comm_size", "mcrat_b200_comm_collectives", "mcrat_b200_comm_bcast_thermal_table",
+    "mcrat_b200_comm_build_thermal_table", "mcrat_b200_comm_reduce_frame_stats", "mcrat_b200_comm_photon_counts",
+    "mcrat_b200_comm_gather_photons",
 ]
 
 
@@ -110,6 +114,12 @@ def load():
         L.mcrat_b200_destroy.argtypes = [C.c_void_p]
         L.mcrat_b200_launch_count.restype = C.c_longlong
         L.mcrat_b200_launch_count.argtypes = [C.c_void_p]
+        L.mcrat_b200_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.mcrat_b200_comm_destroy.argtypes = [C.c_void_p]
+        L.mcrat_b200_comm_collectives.restype = C.c_longlong
+        L.mcrat_b200_comm_collectives.argtypes = [C.c_void_p]
+        for f in ("rank", "size"):
+            getattr(L, "mcrat_b200_comm_" + f).argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -354,3 +364,99 @@ class HotPath:
         v = C.c_double(0)
         self._ck(self.L.mcrat_b200_measure_hbm_peak(self.ctx, C.byref(v)))
         return v.value
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library (rank 0 calls it, the host distributes the bytes)."""
+    L = load()
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = L.mcrat_b200_comm_unique_id(buf, C.c_size_t(COMM_ID_BYTES))
+    if rc != 0:
+        raise McratB200Error(rc, L.mcrat_b200_last_error(None).decode())
+    return buf.raw
+
+
+class Comm:
+    """The reference's MPI exchanges either side of the frame loop, over NCCL (include/mcrat_b200.h, mcrat_b200_comm_*):
+    one communicator per HotPath context, one process per GPU.  `dist` (torch.distributed, any backend) is used only to
+    hand the unique id from rank 0 to the others, the way mcrat.c would MPI_Bcast it."""
+
+    def __init__(self, hot_path, nranks, rank, unique_id):
+        self.hp = hot_path
+        self.L = hot_path.L
+        self.c = C.c_void_p()
+        rc = self.L.mcrat_b200_comm_create(hot_path.ctx, int(nranks), int(rank), unique_id, C.c_size_t(len(unique_id)),
+                                           C.byref(self.c))
+        hot_path._ck(rc)
+
+    @classmethod
+    def from_torch_dist(cls, hot_path, dist):
+        """unique id created on rank 0 and broadcast as an object over the existing process group."""
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None and dist.is_initialized() else (0, 1)
+        box = [comm_unique_id() if rank == 0 else None]
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
+        return cls(hot_path, world, rank, box[0])
+
+    def close(self):
+        if getattr(self, "c", None) is not None and self.c and self.hp.ctx:
+            self.L.mcrat_b200_comm_destroy(self.c)
+        self.c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def rank(self):
+        return int(self.L.mcrat_b200_comm_rank(self.c))
+
+    @property
+    def size(self):
+        return int(self.L.mcrat_b200_comm_size(self.c))
+
+    def collectives(self):
+        return int(self.L.mcrat_b200_comm_collectives(self.c))
+
+    def bcast_thermal_table(self, root=0):
+        self.hp._ck(self.L.mcrat_b200_comm_bcast_thermal_table(self.c, C.c_int(root)))
+
+    def build_thermal_table(self, calls=500000, seed=1):
+        t = np.zeros((221, 81), dtype=np.float64)
+        ms = C.c_float(0)
+        self.hp._ck(self.L.mcrat_b200_comm_build_thermal_table(self.c, C.c_longlong(calls), C.c_uint64(seed), _dp(t), C.byref(ms)))
+        return t, ms.value
+
+    def reduce_frame_stats(self, stats):
+        mine, tot = FrameStats(), FrameStats()
+        for f, _ in FrameStats._fields_:
+            setattr(mine, f, stats[f])
+        self.hp._ck(self.L.mcrat_b200_comm_reduce_frame_stats(self.c, C.byref(mine), C.byref(tot)))
+        return tot.as_dict()
+
+    def photon_counts(self):
+        n = self.size
+        a, b, c = (np.zeros(n, dtype=np.int64) for _ in range(3))
+        ip = lambda x: x.ctypes.data_as(C.POINTER(C.c_longlong))
+        self.hp._ck(self.L.mcrat_b200_comm_photon_counts(self.c, ip(a), ip(b), ip(c)))
+        return {"list_capacity": a, "output_photons": b, "null_slots": c}
+
+    def gather_photons(self, root=0, out=None, capacity=None):
+        """-> (photons of all ranks in rank order or None on non-receiving ranks, per-rank counts)."""
+        n = self.size
+        counts = np.zeros(n, dtype=np.int64)
+        tot = C.c_longlong(0)
+        recv = root == -1 or root == self.rank
+        if out is None and recv:
+            if capacity is None:
+                capacity = int(self.photon_counts()["list_capacity"].sum())
+            out = np.zeros(capacity, dtype=PHOTON_DTYPE)
+        ptr = out.ctypes.data_as(C.c_void_p) if out is not None else None
+        self.hp._ck(self.L.mcrat_b200_comm_gather_photons(self.c, C.c_int(root), ptr, C.c_longlong(out.size if out is not None else 0),
+                                                          counts.ctypes.data_as(C.POINTER(C.c_longlong)), C.byref(tot)))
+        return (out[:tot.value] if recv else None), counts
