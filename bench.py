@@ -157,6 +157,22 @@ def workload_name(job, args):
     return base
 
 
+class stdout_to_stderr:
+    """NCCL prints its version banner on stdout when a communicator is created; stdout is reserved for the one JSON
+    line, so file descriptor 1 points at stderr while communicators come up."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def cpu_model():
     try:
         for line in open("/proc/cpuinfo"):
@@ -336,19 +352,10 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL prints its version banner on stdout when the communicator is created; stdout is reserved for the one
-        # JSON line, so file descriptor 1 points at stderr until the communicator exists
-        sys.stdout.flush()
-        saved_stdout = os.dup(1)
-        os.dup2(2, 1)
-        try:
+        with stdout_to_stderr():
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
             dist.all_reduce(torch.zeros(1, device="cuda"))
             torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved_stdout, 1)
-            os.close(saved_stdout)
 
     def barrier():
         if world > 1:
@@ -368,7 +375,10 @@ def main():
     from mcrat_b200 import Comm
     comm, comm_err = None, None
     try:
-        comm = Comm.from_torch_dist(hp, dist if world > 1 else None)
+        with stdout_to_stderr():
+            comm = Comm.from_torch_dist(hp, dist if world > 1 else None)
+            from mcrat_b200.lib import FrameStats
+            comm.reduce_frame_stats(FrameStats().as_dict())  # first collective: the channels come up outside the timed steps
     except Exception as exc:
         if world > 1:
             raise
@@ -594,7 +604,12 @@ def main():
     # ---- aggregate over ranks ----
     t_max, scatt_all, evals_all, slots_all, e2e_max, e2e_all = tot_ms, scatt, evals, slots, e2e_s, e2e_scatt
     ref_evals_all, loop_slots_all, loop_scatt_all, scan_evals_rate = ref_evals, loop_slots_per_s, loop_scatt_per_s, roofline["evals_per_s"]
+    per_gpu_ms = [tot_ms / args.steps]
     if world > 1:
+        mine_ms = torch.tensor([tot_ms / args.steps], dtype=torch.float64, device="cuda")
+        all_ms = [torch.zeros_like(mine_ms) for _ in range(world)]
+        dist.all_gather(all_ms, mine_ms)
+        per_gpu_ms = [float(x) for x in all_ms]
         t = torch.tensor([tot_ms, e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         c = torch.tensor([scatt, evals, slots, e2e_scatt, ref_evals, loop_slots_per_s, loop_scatt_per_s, roofline["evals_per_s"]],
@@ -619,6 +634,7 @@ def main():
                 "photon_cell_evals_executed_per_step": evals_all / args.steps,
                 "reference_equivalent_evals_per_step": ref_evals_all / args.steps,
                 "k1_full_scan_ms": scan_ms_avg,
+                "ms_per_step_per_gpu": per_gpu_ms,
                 "loop_us_per_iteration": loop_us,
                 "loop_only": {"scatterings_per_sec": loop_scatt_all, "photon_iterations_per_sec": loop_slots_all,
                               "note": "frame loop without the per-step rescan, %d iterations, summed over GPUs" % probe_iters},

@@ -237,7 +237,8 @@ int mcrat_b200_set_recheck_skip(mcrat_b200_ctx *ctx, int mode);
  *   iteration) go through the grid-wide re-location kernels: pass, K1 / K1b / K1c, finish, event.
  * PERSISTENT: one cooperative launch per frame; every sub-shard is iterated by resident blocks that hand over through
  *   a generation word in global memory (no launch boundary inside the loop).
- * AUTO (default): PERSISTENT while the list fits in L2 (<= 2^21 photons), STREAMED above.
+ * AUTO (default): PERSISTENT while the list fits in L2 (<= 2^21 photons); above, PERSISTENT_STREAM with up to one
+ *   sub-shard per SM and STREAMED with more.
  * In all of them sub-shards advance independently, like MPI ranks, and the photons are bit-identical; the replay
  * harness always runs STREAMED_GLOBAL. */
 #define MCRAT_B200_LOOP_AUTO 0
@@ -245,11 +246,22 @@ int mcrat_b200_set_recheck_skip(mcrat_b200_ctx *ctx, int mode);
 #define MCRAT_B200_LOOP_PERSISTENT 2
 #define MCRAT_B200_LOOP_STREAMED_GLOBAL 3 /* streamed, every iteration through the grid-wide re-location kernels (four launches;
                                           * what STREAMED falls back to for new hydro frames and optically thin flows) */
+#define MCRAT_B200_LOOP_PERSISTENT_STREAM 4 /* lists larger than L2, up to one sub-shard per SM: resident event blocks (one per
+                                           * sub-shard) beside resident pass blocks that pull (iteration, sub-shard, slice)
+                                           * items from a counter -- the PERSISTENT protocol without tying pass blocks to a
+                                           * shard, so the photon columns stream through the SMs without a launch boundary
+                                           * while the scatterings run beside them.  AUTO picks it above 2^21 photons. */
 int mcrat_b200_set_loop_mode(mcrat_b200_ctx *ctx, int mode);
 
 /* per-sub-shard view of the counters (cumulative since the shard layout was set) and its slot range */
 int mcrat_b200_get_shard_stats(mcrat_b200_ctx *ctx, int shard, mcrat_b200_frame_stats *stats, int *first_slot,
                                int *num_slots);
+
+/* findContainingBlock logs every photon it finds no cell for with its hydro coordinates (Src/geometry.c:373-388).  The
+ * device keeps the first 32 of them since the last call: slot index and (r0, r1, r2) in the hydro coordinate system.
+ * Returns the number of entries copied (<= max_entries), *n_total = photons not found since the last call; the log is
+ * cleared.  frame_stats.not_found counts them per frame. */
+int mcrat_b200_get_not_found(mcrat_b200_ctx *ctx, int max_entries, int *slots, double *hydro_coords, int *n_total);
 
 /* ---- measurement ------------------------------------------------------------------------------ */
 int mcrat_b200_get_kernel_times(mcrat_b200_ctx *ctx, mcrat_b200_kernel_times *out, int reset);

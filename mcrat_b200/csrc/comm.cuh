@@ -102,7 +102,7 @@ __global__ void count_output_kernel(DevCtx d, int n, long long *out)
     int cnt = 0, nulls = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         cnt += d.ph.weight[i] != 0;
-        nulls += d.ph.type[i] == 'n'; // NULL_PHOTON, Src/mcrat.h:76
+        nulls += d.ph.type[i] == 'N'; // NULL_PHOTON, Src/mcrat.h:57
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {

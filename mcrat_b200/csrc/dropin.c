@@ -16,15 +16,49 @@ static int g_configured = 0;
 static int g_host_dirty = 1; /* host list newer than the device mirror */
 static int g_cs = 0;
 
+static mcrat_dropin_photonList *g_last_list = NULL; /* the host list of the last call: where a failing run leaves its photons */
+
 static void die(FILE *fPtr, const char *where)
 {
     const char *msg = mcrat_b200_last_error(g_ctx);
+    char copy[512];
+    snprintf(copy, sizeof(copy), "%s", msg ? msg : "?"); /* the flush below may overwrite the message */
     if (fPtr) {
-        fprintf(fPtr, "mcrat_b200 (%s): %s\n", where, msg ? msg : "?");
+        fprintf(fPtr, "mcrat_b200 (%s): %s\n", where, copy);
         fflush(fPtr);
     }
-    fprintf(stderr, "mcrat_b200 (%s): %s\n", where, msg ? msg : "?");
+    fprintf(stderr, "mcrat_b200 (%s): %s\n", where, copy);
+    /* the reference exits with its list as it stands (Src/photons.c:54); ours stands on the device: bring back what
+     * can be brought back, so that an atexit handler / core dump of the host sees the state the failure left */
+    if (g_ctx && g_last_list && g_last_list->photons && !g_host_dirty) {
+        int n = mcrat_b200_list_capacity(g_ctx);
+        if (n > g_last_list->list_capacity) n = g_last_list->list_capacity;
+        if (n > 0 && mcrat_b200_get_photons(g_ctx, g_last_list->photons, n) == 0 && fPtr) {
+            fprintf(fPtr, "mcrat_b200: %d photons flushed from the device to the host list before exiting\n", n);
+            fflush(fPtr);
+        }
+    }
     exit(1);
+}
+
+/* findContainingBlock's log line for every photon without a containing cell, Src/geometry.c:373-388 */
+static void log_not_found(FILE *fPtr)
+{
+    int slots[32], total = 0, n, k;
+    double h[96];
+    if (!g_ctx) return;
+    n = mcrat_b200_get_not_found(g_ctx, 32, slots, h, &total);
+    if (n <= 0 || !fPtr) return;
+    for (k = 0; k < n; k++) {
+        if (g_cfg.dimensions == MCRAT_THREE) fprintf(fPtr, "3D switch is: %d and SIM switch is: %d\n", g_cfg.dimensions, 0);
+        if (g_cfg.dimensions == MCRAT_THREE)
+            fprintf(fPtr, "MCRaT Couldn't find a block for the photon located at r0=%e r1=%e r2=%e in the hydro simulation coordinate system.\n",
+                    h[3 * k], h[3 * k + 1], h[3 * k + 2]);
+        else
+            fprintf(fPtr, "MCRaT Couldn't find a block for the photon located at r0=%e r1=%e\n", h[3 * k], h[3 * k + 1]);
+    }
+    if (total > n) fprintf(fPtr, "mcrat_b200: ... and %d more photons without a containing block\n", total - n);
+    fflush(fPtr);
 }
 
 int mcrat_b200_dropin_configure(const mcrat_b200_config *cfg)
@@ -109,7 +143,9 @@ int __wrap_findContainingHydroCell(mcrat_dropin_photonList *photon_list, mcrat_d
     } else if (g_host_dirty || mcrat_b200_list_capacity(g_ctx) != photon_list->list_capacity) {
         upload_photons(photon_list, fPtr);
     }
+    g_last_list = photon_list;
     if (mcrat_b200_find_containing_hydro_cell(g_ctx, find_nearest_block_switch, &n) != 0) die(fPtr, "findContainingHydroCell");
+    log_not_found(fPtr);
     return n;
 }
 
@@ -139,6 +175,7 @@ double __wrap_photonEvent(mcrat_dropin_photonList *photon_list, double dt_max, m
     (void)hydro_data;
     (void)rand;
     ensure_ctx(fPtr);
+    g_last_list = photon_list;
     if (mcrat_b200_photon_event(g_ctx, dt_max, &ts, &idx, frame_scatt_cnt, frame_abs_cnt) != 0) die(fPtr, "photonEvent");
     *scattered_ph_index = idx;
     if (!(ts < dt_max)) {

@@ -209,6 +209,174 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Persistent loop for lists LARGER than L2 (PERSISTENT_STREAM): the same team protocol -- tickets on gst.arrive, early
+// release on gst.gen, mini-pass by the event block -- but the pass blocks are not tied to a shard.  Two kernels run
+// side by side (the pass needs 48 registers and 40 warps per SM to keep HBM busy, the event 128 registers and three
+// warps; one kernel could not have both):
+//   frame_stream_event_kernel  one resident block per sub-shard; exactly the event block of frame_loop_kernel
+//   frame_stream_pass_kernel   resident blocks pull pass items (iteration k, shard s, block b) from a counter, in that
+//                              order: the item waits until shard s has released generation k (its event of iteration
+//                              k - 1 has accepted a candidate), runs pass_body over its slice and draws a ticket.
+// With S shards the stream reaches shard s again one whole list later, so an event (tens of microseconds) has the time
+// the other S - 1 shards' photons take to stream past (hundreds): the HBM pipe never waits for a scattering and never
+// meets a launch boundary.  An item depends only on items before it in the order, and every block that holds an item
+// is running (items are pulled, not assigned), so the protocol cannot deadlock as long as the event blocks are resident:
+// they are launched first and counted (stream_evt_ready) before the first item is pulled; a block that waits longer
+// than ~1 s raises MCRAT_B200_ERR_STATE instead of hanging the device and the host falls back to the streamed loop.
+// A halted shard (frame end, max_iters, pause, many re-locations) releases generation UINT_MAX: its items are skipped.
+// ------------------------------------------------------------------------------------------
+constexpr unsigned STREAM_SPIN_LIMIT = 1u << 24;
+
+__device__ __forceinline__ bool stream_wait_ge(GlobalState &gs, const unsigned *word, unsigned target, unsigned limit)
+{
+    if (ld_acquire_u32(word) >= target) return true;
+    unsigned spins = 0;
+    while (ld_relaxed_u32(word) < target) {
+        __nanosleep(40);
+        if (++spins > limit) {
+            raise_error(&gs, MCRAT_B200_ERR_STATE, -1, ERR_SITE_LOOP_SPIN);
+            return false;
+        }
+        if ((spins & 1023u) == 0 && *(volatile int *)&gs.error != 0) return false; // somebody else gave up
+    }
+    (void)ld_acquire_u32(word);
+    return true;
+}
+
+__global__ void __launch_bounds__(PASS_THREADS, MCRAT_PASS_MINB) frame_stream_pass_kernel(DevCtx d, const int bps, const int evt_blocks)
+{
+    __shared__ ShardState st;
+    __shared__ unsigned long long sh_item;
+    __shared__ int sh_flag;
+    GlobalState &gs = *d.gs;
+    const int S = d.nshards, team = bps + 1;
+    const unsigned long long per_iter = (unsigned long long)S * (unsigned long long)bps;
+    const unsigned limit = d.tau_calc == TAU_TABLE ? (1u << 28) : STREAM_SPIN_LIMIT;
+    if (threadIdx.x == 0) sh_flag = stream_wait_ge(gs, (const unsigned *)&gs.stream_evt_ready, (unsigned)evt_blocks, limit) ? 1 : 0;
+    __syncthreads();
+    if (!sh_flag) return;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            sh_item = atomicAdd(&gs.stream_work, 1ull);
+            sh_flag = (*(volatile int *)&gs.stream_halted >= S || *(volatile int *)&gs.error != 0) ? 0 : 1;
+        }
+        __syncthreads();
+        if (!sh_flag) return;
+        const unsigned long long item = sh_item;
+        const unsigned long long k64 = item / per_iter;
+        const unsigned rem = (unsigned)(item - k64 * per_iter);
+        const int s = (int)(rem / (unsigned)bps), b = (int)(rem - (unsigned)s * (unsigned)bps);
+        const unsigned k = (unsigned)k64;
+        ShardState &gst = d.sh[s];
+        if (k > 0) {
+            if (threadIdx.x == 0) sh_flag = stream_wait_ge(gs, &gst.gen, k, limit) ? 1 : 0;
+            __syncthreads();
+            if (!sh_flag) return;
+        }
+        if (threadIdx.x < SHARD_STATE_WORDS)
+            reinterpret_cast<unsigned long long *>(&st)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&gst)[threadIdx.x];
+        __syncthreads();
+        // the stop test at entry, shard state only (the event block decides alike), later the published halt flag
+        // (a shard that was stopped at entry never publishes: its state says so by itself)
+        const bool halt = (st.halt != 0) | st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters);
+        if (halt) continue;
+        double best_t = DBL_MAX;
+        int best_i = INT_MAX;
+        pass_body<true, true, PASS_THREADS>(d, st, s, b, bps, 0, 0, best_t, best_i);
+        block_argmin<PASS_THREADS>(best_t, best_i);
+        if (threadIdx.x == 0) {
+            int bidx = -1;
+            double btemp = 0;
+            if (best_i != INT_MAX) {
+                bidx = d.ph.idx[best_i];
+                if (bidx >= 0) btemp = d.cells.temp[bidx];
+            }
+            d.bm_t[s * team + b] = best_t;
+            d.bm_i[s * team + b] = best_i;
+            d.bm_idx[s * team + b] = bidx;
+            d.bm_temp[s * team + b] = btemp;
+            __threadfence();
+            atomicAdd(&gst.arrive, 1u);
+        }
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_stream_event_kernel(DevCtx d, const int bps)
+{
+    __shared__ ShardState st;
+    __shared__ int sh_flag;
+    GlobalState &gs = *d.gs;
+    const int team = bps + 1;
+    const int s = blockIdx.x;
+    ShardState &gst = d.sh[s];
+    const unsigned limit = d.tau_calc == TAU_TABLE ? (1u << 28) : STREAM_SPIN_LIMIT;
+    if (threadIdx.x < SHARD_STATE_WORDS)
+        reinterpret_cast<unsigned long long *>(&st)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&gst)[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        d.bm_t[s * team + bps] = DBL_MAX;
+        d.bm_i[s * team + bps] = INT_MAX;
+        st.mini_slot = -1;
+        __threadfence();
+        atomicAdd(&gs.stream_evt_ready, 1); // resident: the pass blocks may start pulling items
+    }
+    __syncthreads();
+    bool halt = st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters);
+    unsigned k = 0;
+    while (!halt) {
+        if (threadIdx.x == 0) sh_flag = stream_wait_ge(gs, &gst.arrive, (k + 1) * (unsigned)bps, limit) ? 1 : 0;
+        __syncthreads();
+        if (!sh_flag) break;
+        ++k;
+        double pre_t = DBL_MAX;
+        int pre_i = INT_MAX;
+        const bool have_pre = (team <= THREADS);
+        int pre_idx = -2;
+        double pre_temp = 0;
+        if (have_pre && (int)threadIdx.x < team) {
+            pre_t = *(volatile double *)&d.bm_t[s * team + threadIdx.x];
+            pre_i = *(volatile int *)&d.bm_i[s * team + threadIdx.x];
+            pre_idx = *(volatile int *)&d.bm_idx[s * team + threadIdx.x];
+            pre_temp = *(volatile double *)&d.bm_temp[s * team + threadIdx.x];
+        }
+        const int R = *(volatile int *)&gst.reloc_n;
+        if (R > 0) relocate_shard<THREADS>(d, st, s, R);
+        const bool released = event_body<THREADS>(d, s, st.first, R, team, 0, 0.0, st, &gst, k, s * team + bps, have_pre,
+                                                  pre_t, pre_i, pre_idx, pre_temp);
+        if (!released) {
+            if (threadIdx.x == 0) {
+                st.halt = (loop_stopped(gs, st) || st.reloc_heavy) ? 1 : 0;
+                st.mini_slot = -1;
+                d.bm_t[s * team + bps] = DBL_MAX;
+                d.bm_i[s * team + bps] = INT_MAX;
+            }
+            __syncthreads();
+            if (threadIdx.x < SHARD_STATE_WORDS)
+                reinterpret_cast<unsigned long long *>(&gst)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&st)[threadIdx.x];
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                st_release_u32(&gst.gen, k);
+            }
+        } else if (threadIdx.x == 0 && st.mini_slot < 0) {
+            d.bm_t[s * team + bps] = DBL_MAX;
+            d.bm_i[s * team + bps] = INT_MAX;
+        }
+        __syncthreads();
+        halt = st.halt != 0;
+    }
+    // halted (or gave up): every later item of this shard is skipped
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        st_release_u32(&gst.gen, 0xFFFFFFFFu);
+        atomicAdd(&gs.stream_halted, 1);
+    }
+}
+
 // With more sub-shards than resident teams the GPU is busy anyway (many events in flight per SM) and throughput,
 // not the latency of one shard, is what counts: one block per sub-shard does pass and event in turn, and walks through
 // its shards one after the other if there are more shards than resident blocks.  No inter-block protocol at all.

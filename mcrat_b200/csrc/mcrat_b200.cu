@@ -832,6 +832,9 @@ __global__ void reset_loop_kernel(DevCtx d, int set_times, double time_now, doub
         d.gs->max_iters = max_iters;
         d.gs->n_stopped = 0;
         d.gs->reloc_heavy_any = 0;
+        d.gs->stream_work = 0;
+        d.gs->stream_evt_ready = 0;
+        d.gs->stream_halted = 0;
     }
 }
 
@@ -1262,6 +1265,11 @@ __global__ void reset_protocol_kernel(DevCtx d)
         st.halt = 0;
         st.reloc_heavy = 0;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        d.gs->stream_work = 0;
+        d.gs->stream_evt_ready = 0;
+        d.gs->stream_halted = 0;
+    }
 }
 
 static int reset_protocol(mcrat_b200_ctx *ctx)
@@ -1293,8 +1301,57 @@ static void frame_loop_grid(const mcrat_b200_ctx *ctx, int &threads, int &bps, i
     }
 }
 
-static int launch_frame_loop(mcrat_b200_ctx *ctx)
+// persistent loop for lists larger than L2 (frame_loop.cuh, PERSISTENT_STREAM): resident event blocks, one per sub-shard, on
+// the second stream; pass blocks pulling items on the first.  All sub-shards' event blocks must be resident next to the
+// pass blocks: one 128-thread block per SM beside four pass blocks.
+static bool frame_stream_fits(const mcrat_b200_ctx *ctx)
 {
+    return ctx->d.nshards >= 1 && ctx->d.nshards <= ctx->num_sms && !ctx->d.cs && !ctx->d.replay;
+}
+
+static int frame_stream_bps(const mcrat_b200_ctx *ctx)
+{
+    // about 16 photons per thread and item: the item's fixed cost (pull, wait, state, ticket: three round trips) stays below
+    // a fifth of its time, and a shard's items are spread over enough blocks to finish together
+    int bps = (ctx->d.shard_size + PASS_THREADS * 16 - 1) / (PASS_THREADS * 16);
+    if (const char *e = getenv("MCRAT_B200_STREAM_PPT")) {
+        const int ppt = atoi(e);
+        if (ppt > 0) bps = (ctx->d.shard_size + PASS_THREADS * ppt - 1) / (PASS_THREADS * ppt);
+    }
+    if (bps > BLOCKMIN_CAP / ctx->d.nshards - 1) bps = BLOCKMIN_CAP / ctx->d.nshards - 1;
+    if (bps > EVT_THREADS_MANY - 1) bps = EVT_THREADS_MANY - 1; // the event block reads the minima with one load per thread
+    if (bps < 1) bps = 1;
+    return bps;
+}
+
+static int launch_frame_stream(mcrat_b200_ctx *ctx)
+{
+    const int S = ctx->d.nshards;
+    const int bps = frame_stream_bps(ctx);
+    if (getenv("MCRAT_B200_REFUSE_COOPERATIVE")) return MCRAT_B200_LOOP_FALLBACK;
+    CK(cudaEventRecord(ctx->ev_join, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_join, 0));
+    {
+        Timed t(ctx, KC_EVENT);
+        frame_stream_event_kernel<EVT_THREADS_MANY><<<S, EVT_THREADS_MANY, 0, ctx->stream2>>>(ctx->d, bps);
+        if (int rc = check_launch(ctx, "frame_stream_event_kernel")) return rc;
+    }
+    {
+        Timed t(ctx, KC_PASS);
+        int grid = ctx->num_sms * MCRAT_PASS_MINB; // what cannot be resident next to the event blocks starts when the others leave
+        if (const char *e = getenv("MCRAT_B200_STREAM_CTAS_PER_SM"))
+            if (atoi(e) > 0) grid = ctx->num_sms * atoi(e);
+        frame_stream_pass_kernel<<<grid, PASS_THREADS, 0, ctx->stream>>>(ctx->d, bps, S);
+        if (int rc = check_launch(ctx, "frame_stream_pass_kernel")) return rc;
+    }
+    CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    return MCRAT_B200_OK;
+}
+
+static int launch_frame_loop(mcrat_b200_ctx *ctx, bool stream = false)
+{
+    if (stream) return launch_frame_stream(ctx);
     int threads, bps, grid;
     frame_loop_grid(ctx, threads, bps, grid);
     if (grid < 1) return fail(ctx, MCRAT_B200_ERR_STATE, "frame_loop_kernel does not fit on this device");
@@ -1334,7 +1391,7 @@ API int mcrat_b200_set_loop_mode(mcrat_b200_ctx *ctx, int mode)
 {
     if (!ctx) return MCRAT_B200_ERR_ARG;
     if (mode != MCRAT_B200_LOOP_AUTO && mode != MCRAT_B200_LOOP_STREAMED && mode != MCRAT_B200_LOOP_PERSISTENT &&
-        mode != MCRAT_B200_LOOP_STREAMED_GLOBAL)
+        mode != MCRAT_B200_LOOP_STREAMED_GLOBAL && mode != MCRAT_B200_LOOP_PERSISTENT_STREAM)
         return fail(ctx, MCRAT_B200_ERR_ARG, "set_loop_mode: unknown mode");
     ctx->loop_mode = mode;
     return MCRAT_B200_OK;
@@ -1444,6 +1501,12 @@ API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remain
     bool persistent = fused && !ctx->cfg.profile &&
                       (ctx->loop_mode == MCRAT_B200_LOOP_PERSISTENT ||
                        (ctx->loop_mode == MCRAT_B200_LOOP_AUTO && ctx->d.cap <= PERSISTENT_MAX_PHOTONS));
+    // lists larger than L2: the persistent stream of pass items beside resident event blocks, if every sub-shard's event
+    // block fits on the device at once; else the interleaved streamed loop
+    const bool pstream = fused && !ctx->cfg.profile && !persistent && frame_stream_fits(ctx) &&
+                         (ctx->loop_mode == MCRAT_B200_LOOP_PERSISTENT_STREAM ||
+                          (ctx->loop_mode == MCRAT_B200_LOOP_AUTO && ctx->d.cap > PERSISTENT_MAX_PHOTONS));
+    if (pstream) persistent = true;
     long long streamed_done = 0; // iterations already launched when the persistent loop hands over for good
     if (persistent) {
         // the first iteration of a new hydro frame re-locates every photon: that is K1's job
@@ -1453,7 +1516,7 @@ API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remain
             launched++;
         }
         for (;;) {
-            if (int rc = launch_frame_loop(ctx)) {
+            if (int rc = launch_frame_loop(ctx, pstream)) {
                 if (rc != MCRAT_B200_LOOP_FALLBACK) return rc;
                 ctx->loop_mode = MCRAT_B200_LOOP_STREAMED; // for the rest of this context's life
                 persistent = false;
@@ -1567,6 +1630,26 @@ API int mcrat_b200_get_shard_stats(mcrat_b200_ctx *ctx, int shard, mcrat_b200_fr
 }
 
 // ---- measurement -------------------------------------------------------------------------------------
+// photons for which findContainingBlock found no cell since the last call (Src/geometry.c:373-388 logs each of them)
+API int mcrat_b200_get_not_found(mcrat_b200_ctx *ctx, int max_entries, int *slots, double *hydro_coords, int *n_total)
+{
+    if (!ctx || max_entries < 0) return ctx ? fail(ctx, MCRAT_B200_ERR_ARG, "get_not_found: bad argument") : MCRAT_B200_ERR_ARG;
+    if (int rc = fetch_global(ctx)) return rc;
+    const GlobalState &g = *ctx->gs_host;
+    const int n = std::min(std::min(g.nf_logged, NF_LOG_CAP), max_entries);
+    for (int k = 0; k < n; ++k) {
+        if (slots) slots[k] = g.nf_slot[k];
+        if (hydro_coords) memcpy(hydro_coords + 3 * k, g.nf_h + 3 * k, 3 * sizeof(double));
+    }
+    if (n_total) *n_total = g.nf_logged;
+    if (g.nf_logged) {
+        ctx->gs_host->nf_logged = 0;
+        CK(cudaMemsetAsync(&ctx->d.gs->nf_logged, 0, sizeof(int), ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return n;
+}
+
 API int mcrat_b200_get_kernel_times(mcrat_b200_ctx *ctx, mcrat_b200_kernel_times *out, int reset)
 {
     if (!ctx || !out) return MCRAT_B200_ERR_ARG;

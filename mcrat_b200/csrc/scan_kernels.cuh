@@ -366,6 +366,15 @@ __device__ __forceinline__ bool finish_one(DevCtx &d, ShardState &sh, const int 
         d.ph.idx[i] = -1; // Src/mclib.c:536, 581-584
         d.ph.safe[i] = 0;
         missing = true;
+        const int k = atomicAdd(&d.gs->nf_logged, 1);
+        if (k < NF_LOG_CAP) { // for the rank's log line, Src/geometry.c:373-388
+            double h0, h1, h2;
+            coord_to_hydro(d.dims, d.geom, d.ph.r0[i], d.ph.r1[i], d.ph.r2[i], h0, h1, h2);
+            d.gs->nf_slot[k] = i;
+            d.gs->nf_h[3 * k] = h0;
+            d.gs->nf_h[3 * k + 1] = h1;
+            d.gs->nf_h[3 * k + 2] = h2;
+        }
     } else {
         d.ph.idx[i] = b;
         d.ph.safe[i] = 0; // the next pass re-checks the new cell and sets the threshold

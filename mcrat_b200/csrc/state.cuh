@@ -116,11 +116,16 @@ struct ShardState {
 constexpr int SHARD_STATE_WORDS = offsetof(ShardState, arrive) / 8; // 8-byte words of the copied part
 static_assert(offsetof(ShardState, arrive) % 8 == 0, "ShardState: copied part must be a whole number of 8-byte words");
 
+constexpr int NF_LOG_CAP = 32;
+
 struct GlobalState {
     int reloc_count[2];
     int error, not_found, n_stopped;
     int reloc_heavy_any;    // streamed loop (local re-location): a shard re-located more than RELOC_HEAVY photons in one iteration
     unsigned int scan_work; // K1: next work item (photon chunk, cell chunk); zeroed by the pass kernel that feeds the scan
+    // persistent loop for lists larger than L2 (frame_stream_*_kernel): next pass item, event blocks resident, shards halted
+    unsigned long long stream_work;
+    int stream_evt_ready, stream_halted;
     int error_slot, error_site; // photon slot (or -1) and ERR_SITE_* of the first error raised (raise_error)
     long long cell_evals, box_evals, max_iters;
     long long ref_equiv_evals; // first-hit index + 1 summed over the photons of full rescans (what the reference's loop executes)
@@ -132,6 +137,11 @@ struct GlobalState {
     int cs_scatt_num;          // scatt_cyclosynch_num_ph
     int cs_emitted;            // pool photons replaced on the device
     double cs_comptonized_w;   // n_comptonized
+    // the first NF_LOG_CAP photons for which no containing cell exists since the host last read the log: slot and hydro
+    // coordinates, what findContainingBlock writes to the rank's log file (Src/geometry.c:373-388)
+    int nf_logged;
+    int nf_slot[NF_LOG_CAP];
+    double nf_h[3 * NF_LOG_CAP];
 #ifdef MCRAT_TIMING
     long long dbg[32];         // SM-cycle accumulators of shard 0 (tools/loop_timing.py; not in the product build)
 #endif

@@ -22,7 +22,7 @@ HYDRO_FIELDS = ["r0", "r1", "r2", "r0_size", "r1_size", "r2_size", "r", "theta",
 
 ABI_VERSION = 2
 RNG_PHILOX, RNG_REPLAY = 0, 1
-LOOP_MODES = {"auto": 0, "streamed": 1, "persistent": 2, "streamed_global": 3}
+LOOP_MODES = {"auto": 0, "streamed": 1, "persistent": 2, "streamed_global": 3, "persistent_stream": 4}
 
 ERRORS = {-1: "ERR_CUDA", -2: "ERR_ARG", -3: "ERR_STATE", -4: "ERR_REPLAY", -5: "ERR_TABLE"}
 
@@ -75,6 +75,7 @@ EXPORTS = [
     "mcrat_b200_launch_count", "mcrat_b200_rescan_all", "mcrat_b200_measure_fp64_peak", "mcrat_b200_measure_hbm_peak",
     "mcrat_b200_selftest_div_by_c", "mcrat_b200_set_recheck_skip", "mcrat_b200_set_profile",
     "mcrat_b200_photon_emit_cyclosynch", "mcrat_b200_photon_emit_cyclosynch_single",
+    "mcrat_b200_get_not_found",
     "mcrat_b200_comm_unique_id", "mcrat_b200_comm_nccl_version", "mcrat_b200_comm_create", "mcrat_b200_comm_destroy",
     "mcrat_b200_comm_rank", "mcrat_b200_comm_size", "mcrat_b200_comm_collectives", "mcrat_b200_comm_bcast_thermal_table",
     "mcrat_b200_comm_build_thermal_table", "mcrat_b200_comm_reduce_frame_stats", "mcrat_b200_comm_photon_counts",
@@ -97,6 +98,25 @@ def build(force=False):
 _lib = None
 
 
+def _pin_nccl():
+    """The library binds NCCL at run time by soname (libnccl.so.2).  In a Python process that also imports torch the copy
+    torch was built against (the nvidia-nccl wheel next to it) must be the one that gets loaded, whichever of the two
+    comes first: the dynamic linker keeps one object per soname, and an older system NCCL loaded first would make a
+    later `import torch` fail on missing symbols.  A C host (mcrat.c under MPI) has no such concern and uses the system's."""
+    if os.environ.get("MCRAT_B200_NCCL"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["MCRAT_B200_NCCL"] = cand
+                return
+    except Exception:
+        pass
+
+
 def load():
     """dlopen the library; raises if it is not built (no fallback of any kind)."""
     global _lib
@@ -105,6 +125,7 @@ def load():
         if not os.path.exists(path):
             raise FileNotFoundError("%s is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                     "(there is no CPU fallback)" % LIB_PATH)
+        _pin_nccl()
         L = C.CDLL(path, mode=C.RTLD_GLOBAL)
         L.mcrat_b200_last_error.restype = C.c_char_p
         L.mcrat_b200_last_error.argtypes = [C.c_void_p]
@@ -326,6 +347,16 @@ class HotPath:
         self._ck(self.L.mcrat_b200_run_frame(self.ctx, C.c_double(time_now), C.c_double(remaining_time),
                                              C.c_longlong(max_iters), C.c_int(switch), C.byref(st)))
         return st.as_dict()
+
+    def not_found(self, max_entries=32):
+        """-> (slots, hydro coordinates [n, 3], total count) of the photons without a containing cell since the last call."""
+        slots = np.zeros(max_entries, dtype=np.int32)
+        h = np.zeros((max_entries, 3), dtype=np.float64)
+        tot = C.c_int(0)
+        n = self.L.mcrat_b200_get_not_found(self.ctx, C.c_int(max_entries), slots.ctypes.data_as(C.POINTER(C.c_int)), _dp(h), C.byref(tot))
+        if n < 0:
+            self._ck(n)
+        return slots[:n], h[:n], tot.value
 
     # ---- measurement -----------------------------------------------------------------------------
     def synchronize(self):

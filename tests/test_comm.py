@@ -61,6 +61,7 @@ def test_one_rank_communicator_is_the_identity():
     from mcrat_b200 import Comm, HotPath, comm_unique_id
     cfg, hydro, photons, frame = synth.workload("C2", scale=1.0 / 16, n_photons=3000, seed=3)
     photons["weight"][::7] = 0.0
+    photons["type"][::7] = b"N"  # null photons, Src/mcrat.h:57 (setNullPhoton zeroes the weight too, Src/photons.c:230-250)
     hp = HotPath(cfg, device=0, seed=99, shard=0, num_shards=4)
     st = _frame(hp, photons, hydro, frame)
     comm = Comm(hp, 1, 0, comm_unique_id())
@@ -72,7 +73,7 @@ def test_one_rank_communicator_is_the_identity():
     cnt = comm.photon_counts()
     assert cnt["list_capacity"].tolist() == [photons.size]
     assert cnt["output_photons"].tolist() == [int((got["weight"] != 0).sum())]
-    assert cnt["null_slots"].tolist() == [int((got["type"] == b"n").sum())]
+    assert cnt["null_slots"].tolist() == [int((got["type"] == b"N").sum())]
     for root in (0, -1):
         allp, counts = comm.gather_photons(root=root)
         assert counts.tolist() == [photons.size]

@@ -129,7 +129,7 @@ def test_persistent_loop_is_bit_identical_to_streamed_loop_and_matches_oracle(wl
     if dilute != 1.0:
         hydro = _thin(hydro, dilute)
     out = {}
-    for mode in ("streamed_global", "streamed", "persistent"):
+    for mode in ("streamed_global", "streamed", "persistent", "persistent_stream"):
         hp = HotPath(cfg, seed=5150, shard=7, num_shards=shards, scan_index=scan_index, loop_mode=mode)
         hp.set_hydro(hydro)
         hp.set_photons(photons)
@@ -139,7 +139,9 @@ def test_persistent_loop_is_bit_identical_to_streamed_loop_and_matches_oracle(wl
         out[mode] = (st1, st2, hp.get_photons(), [hp.shard_stats(s) for s in range(hp.num_shards())], hp.launch_count())
         hp.close()
     a = out["streamed_global"]
-    for mode in ("streamed", "persistent"):  # two-stream interleaved halves; one cooperative launch
+    # two-stream interleaved halves; one cooperative launch; resident event blocks beside a stream of pass items (the
+    # loop of lists larger than L2, forced onto these small ones; with more sub-shards than SMs it is the streamed loop)
+    for mode in ("streamed", "persistent", "persistent_stream"):
         b = out[mode]
         for k in ("iterations", "scatterings", "relocations", "photon_slots", "not_found", "time_now", "last_time_step",
                   "last_scattered_index"):
@@ -172,7 +174,7 @@ def test_persistent_loop_runs_a_frame_to_its_end():
     cfg, hydro, photons, frame = synth.workload("C2", scale=1.0 / 16, n_photons=600, seed=43)
     hydro = _thin(hydro, 3e-4)  # a few hundred scatterings per shard and frame instead of millions
     res = {}
-    for mode in ("streamed", "persistent"):
+    for mode in ("streamed", "persistent", "persistent_stream"):
         hp = HotPath(cfg, seed=99, num_shards=4, loop_mode=mode)
         hp.set_hydro(hydro)
         hp.set_photons(photons)
@@ -184,8 +186,10 @@ def test_persistent_loop_runs_a_frame_to_its_end():
     for s in shards:
         assert abs(s["time_now"] - (frame["time_now"] + 1.0 / frame["fps"])) <= 1e-9 * s["time_now"], s
     assert res["streamed"][0]["scatterings"] == st["scatterings"] and res["streamed"][0]["iterations"] == st["iterations"]
+    assert res["persistent_stream"][0]["scatterings"] == st["scatterings"] and res["persistent_stream"][0]["iterations"] == st["iterations"]
     for f in ph.dtype.names:
         assert np.array_equal(ph[f], res["streamed"][1][f], equal_nan=(ph.dtype[f].kind == "f")), f
+        assert np.array_equal(ph[f], res["persistent_stream"][1][f], equal_nan=(ph.dtype[f].kind == "f")), f
 
 
 def test_refused_cooperative_launch_falls_back_to_the_streamed_loop(monkeypatch):
@@ -295,7 +299,7 @@ def test_klein_nishina_rejections_streamed_equals_persistent(nph, shards):
     same photons bit for bit, and fewer scatterings than shard-iterations would give without rejections' extra pushes."""
     cfg, hydro, photons, frame = synth.workload("C3", scale=1.0 / 8, n_photons=nph, seed=19)
     out = {}
-    for mode in ("streamed", "persistent", "streamed_global"):
+    for mode in ("streamed", "persistent", "persistent_stream", "streamed_global"):
         hp = HotPath(cfg, seed=777, num_shards=shards, loop_mode=mode)
         hp.set_hydro(hydro)
         hp.build_thermal_table(calls=20000, seed=3)
@@ -304,7 +308,7 @@ def test_klein_nishina_rejections_streamed_equals_persistent(nph, shards):
         st2 = hp.run_frame(st["time_now"], 1.0 / frame["fps"], max_iters=80, switch=0)
         out[mode] = (hp.get_photons(), st["scatterings"] + st2["scatterings"], st["iterations"] + st2["iterations"])
     a = out["streamed_global"]
-    for mode in ("streamed", "persistent"):
+    for mode in ("streamed", "persistent", "persistent_stream"):
         b = out[mode]
         assert a[1] == b[1] and a[2] == b[2] == 200
         for f in a[0].dtype.names:
@@ -323,7 +327,7 @@ def test_walks_longer_than_the_push_list_match_the_oracle(shards):
     for k in ("p0", "p1", "p2", "p3", "comv_p0", "comv_p1", "comv_p2", "comv_p3"):
         ph[k] *= f
     out = {}
-    for mode in ("streamed", "persistent"):
+    for mode in ("streamed", "persistent", "persistent_stream"):
         hp = HotPath(cfg, seed=616, shard=2, num_shards=shards, loop_mode=mode)
         hp.set_hydro(hydro)
         hp.set_photons(ph)
@@ -332,8 +336,10 @@ def test_walks_longer_than_the_push_list_match_the_oracle(shards):
         hp.close()
     (sa, pa, _), (sb, pb, ss) = out["streamed"], out["persistent"]
     assert sa["iterations"] == sb["iterations"] == 40 and sa["scatterings"] == sb["scatterings"]
+    assert out["persistent_stream"][0]["scatterings"] == sa["scatterings"]
     for fld in pa.dtype.names:
         assert np.array_equal(pa[fld], pb[fld], equal_nan=pa.dtype[fld].kind == "f"), fld
+        assert np.array_equal(pa[fld], out["persistent_stream"][1][fld], equal_nan=pa.dtype[fld].kind == "f"), fld
     sl = slice(ss["first_slot"], ss["first_slot"] + ss["num_slots"])
     o = api.Oracle(cfg)
     o.set_hydro(hydro)
