@@ -227,6 +227,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
 // A halted shard (frame end, max_iters, pause, many re-locations) releases generation UINT_MAX: its items are skipped.
 // ------------------------------------------------------------------------------------------
 constexpr unsigned STREAM_SPIN_LIMIT = 1u << 24;
+constexpr int STREAM_PASS_CTAS_PER_SM = 4;      // pass blocks per SM: leaves the registers of one event block free on every SM
+constexpr int STREAM_PASS_SMEM_PAD = 50 * 1024; // dynamic shared memory that enforces it: 4 x (50 KB + static) fit in 228 KB, 5 do not
 
 __device__ __forceinline__ bool stream_wait_ge(GlobalState &gs, const unsigned *word, unsigned target, unsigned limit)
 {

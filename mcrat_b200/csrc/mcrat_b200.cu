@@ -305,6 +305,8 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
         d.table.za = g + N_PH_E + 1 + N_T + 1;
         ctx->table_dev = g + N_PH_E + 1 + N_T + 1;
     }
+    if ((e = cudaFuncSetAttribute(frame_stream_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_PASS_SMEM_PAD)) != cudaSuccess)
+        return bail(e, "cudaFuncSetAttribute");
     if ((e = cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(0))) != cudaSuccess)
         return bail(e, "cudaFuncSetAttribute");
     if ((e = cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(1))) != cudaSuccess)
@@ -1337,11 +1339,12 @@ static int launch_frame_stream(mcrat_b200_ctx *ctx)
         if (int rc = check_launch(ctx, "frame_stream_event_kernel")) return rc;
     }
     {
+        // Whatever order the two grids reach the SMs in, every event block must find room: the pass blocks carry enough
+        // (unused) dynamic shared memory that at most STREAM_PASS_CTAS_PER_SM of them fit on an SM, which leaves the
+        // registers of one event block (128 threads x 128) free on every SM -- one slot per SM >= one per sub-shard.
         Timed t(ctx, KC_PASS);
-        int grid = ctx->num_sms * MCRAT_PASS_MINB; // what cannot be resident next to the event blocks starts when the others leave
-        if (const char *e = getenv("MCRAT_B200_STREAM_CTAS_PER_SM"))
-            if (atoi(e) > 0) grid = ctx->num_sms * atoi(e);
-        frame_stream_pass_kernel<<<grid, PASS_THREADS, 0, ctx->stream>>>(ctx->d, bps, S);
+        const int grid = ctx->num_sms * STREAM_PASS_CTAS_PER_SM;
+        frame_stream_pass_kernel<<<grid, PASS_THREADS, STREAM_PASS_SMEM_PAD, ctx->stream>>>(ctx->d, bps, S);
         if (int rc = check_launch(ctx, "frame_stream_pass_kernel")) return rc;
     }
     CK(cudaEventRecord(ctx->ev_join, ctx->stream2));

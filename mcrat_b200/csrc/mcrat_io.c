@@ -304,6 +304,8 @@ typedef struct {
     int is_i8;      /* 0: IEEE F64LE, 1: STD_I8LE (H5T_NATIVE_CHAR on the reference's platforms) */
     size_t n;       /* 1-D length */
     void *data;     /* n doubles or n signed chars */
+    size_t chunk;   /* 0: contiguous, fixed size (mcdata files, Src/mcrat_io.c:1649); > 0: chunked with this many elements per
+                     * chunk and an unlimited maximum dimension (the per-rank files, Src/mcrat_io.c:140, 254-263) */
 } h5_dset;
 
 typedef struct {
@@ -500,17 +502,23 @@ static size_t write_group(wbuf *w, size_t at, link_t *links, int n, int K, uint6
 }
 
 #define DSET_OHDR_SIZE (16 + (8 + 8) + (8 + 24) + (8 + 16) + (8 + 24))
+#define DSET_OHDR_SIZE_CHUNKED (16 + (8 + 8) + (8 + 24) + (8 + 24) + (8 + 24))
+#define H5_ISTORE_K 32 /* chunk B-tree: superblock version 0 has no field for it, the library's default applies */
+#define CHUNK_KEY_SIZE 24 /* chunk bytes (4), filter mask (4), offsets of a 1-D dataset + the element dimension (2 x 8) */
+
+static size_t dset_ohdr_size(const h5_dset *d) { return d->chunk ? DSET_OHDR_SIZE_CHUNKED : DSET_OHDR_SIZE; }
+static size_t chunk_node_size(void) { return 24 + (size_t)(2 * H5_ISTORE_K + 1) * CHUNK_KEY_SIZE + (size_t)(2 * H5_ISTORE_K) * 8; }
 
 /* dataset object header at `at` pointing at raw data (addr, bytes) */
 static size_t write_dataset_header(wbuf *w, size_t at, const h5_dset *d, uint64_t data_addr)
 {
-    const size_t end = at + DSET_OHDR_SIZE;
+    const size_t end = at + dset_ohdr_size(d);
     if (!wb_reserve(w, end)) return 0;
     unsigned char *b = w->b + at;
     b[0] = 1;
     put_le(b + 2, 4, 2);
     put_le(b + 4, 1, 4);
-    put_le(b + 8, DSET_OHDR_SIZE - 16, 4);
+    put_le(b + 8, dset_ohdr_size(d) - 16, 4);
     unsigned char *m = b + 16;
     /* fill value (old libraries' version-1 form: allocation late, fill time if-set, default value) */
     put_le(m, 0x0005, 2);
@@ -539,20 +547,113 @@ static size_t write_dataset_header(wbuf *w, size_t at, const h5_dset *d, uint64_
         put_le(m + 18, 8, 2);
     }
     m += 32;
-    /* dataspace, version 1, rank 1, no maximum dimensions */
-    put_le(m, 0x0001, 2);
-    put_le(m + 2, 16, 2);
-    m[8] = 1; m[9] = 1; m[10] = 0;
-    put_le(m + 16, d->n, 8);
-    m += 24;
-    /* data layout, version 3, contiguous */
-    put_le(m, 0x0008, 2);
-    put_le(m + 2, 24, 2);
-    m[8] = 3; m[9] = 1;
-    put_le(m + 10, d->n ? data_addr : H5_UNDEF, 8);
-    put_le(m + 18, (uint64_t)d->n * (d->is_i8 ? 1 : 8), 8);
+    if (d->chunk) {
+        /* dataspace, version 1, rank 1, maximum dimension present and unlimited (H5S_UNLIMITED, Src/mcrat_io.c:140) */
+        put_le(m, 0x0001, 2);
+        put_le(m + 2, 24, 2);
+        m[8] = 1; m[9] = 1; m[10] = 1;
+        put_le(m + 16, d->n, 8);
+        put_le(m + 24, H5_UNDEF, 8);
+        m += 32;
+        /* data layout, version 3, chunked: dimensionality rank + 1, chunk B-tree, chunk dimensions (elements, element size) */
+        put_le(m, 0x0008, 2);
+        put_le(m + 2, 24, 2);
+        m[8] = 3; m[9] = 2; m[10] = 2;
+        put_le(m + 11, d->n ? data_addr : H5_UNDEF, 8); /* data_addr: the root node of the chunk B-tree */
+        put_le(m + 19, (uint64_t)d->chunk, 4);
+        put_le(m + 23, (uint64_t)(d->is_i8 ? 1 : 8), 4);
+    } else {
+        /* dataspace, version 1, rank 1, no maximum dimensions */
+        put_le(m, 0x0001, 2);
+        put_le(m + 2, 16, 2);
+        m[8] = 1; m[9] = 1; m[10] = 0;
+        put_le(m + 16, d->n, 8);
+        m += 24;
+        /* data layout, version 3, contiguous */
+        put_le(m, 0x0008, 2);
+        put_le(m + 2, 24, 2);
+        m[8] = 3; m[9] = 1;
+        put_le(m + 10, d->n ? data_addr : H5_UNDEF, 8);
+        put_le(m + 18, (uint64_t)d->n * (d->is_i8 ? 1 : 8), 8);
+    }
     if (end > w->n) w->n = end;
     return end;
+}
+
+/* Raw data of a chunked dataset at `at`: the chunks one after the other (the last one zero-filled to full size, as the
+ * library allocates it), then the version-1 B-tree (node type 1) that indexes them -- leaves of up to 2K entries linked
+ * left to right, internal levels above them while more than one node remains.  Returns the new cursor, *root_out = address
+ * of the root node. */
+static size_t write_chunks(wbuf *w, size_t at, const h5_dset *d, uint64_t *root_out)
+{
+    const size_t es = d->is_i8 ? 1 : 8, cbytes = d->chunk * es;
+    const size_t nchunks = (d->n + d->chunk - 1) / d->chunk;
+    const size_t data_at = at;
+    if (!wb_reserve(w, at + nchunks * cbytes + 8)) return 0;
+    memset(w->b + at, 0, nchunks * cbytes);
+    memcpy(w->b + at, d->data, d->n * es);
+    at = align8(at + nchunks * cbytes);
+    /* level by level: entry e of a level = (first chunk index it covers, address) */
+    size_t nent = nchunks;
+    uint64_t *first = (uint64_t *)malloc(sizeof(uint64_t) * nent), *addr = (uint64_t *)malloc(sizeof(uint64_t) * nent);
+    if (!first || !addr) {
+        free(first);
+        free(addr);
+        return 0;
+    }
+    for (size_t c = 0; c < nchunks; ++c) {
+        first[c] = c;
+        addr[c] = data_at + c * cbytes;
+    }
+    const size_t per = 2 * H5_ISTORE_K, nsz = chunk_node_size();
+    for (int level = 0;; ++level) {
+        const size_t nnodes = (nent + per - 1) / per;
+        if (!wb_reserve(w, at + nnodes * nsz)) {
+            free(first);
+            free(addr);
+            return 0;
+        }
+        memset(w->b + at, 0, nnodes * nsz);
+        for (size_t q = 0; q < nnodes; ++q) {
+            unsigned char *b = w->b + at + q * nsz;
+            const size_t e0 = q * per, used = (nent - e0 < per) ? nent - e0 : per;
+            memcpy(b, "TREE", 4);
+            b[4] = 1;
+            b[5] = (unsigned char)level;
+            put_le(b + 6, used, 2);
+            put_le(b + 8, q ? at + (q - 1) * nsz : H5_UNDEF, 8);
+            put_le(b + 16, (q + 1 < nnodes) ? at + (q + 1) * nsz : H5_UNDEF, 8);
+            unsigned char *k = b + 24;
+            for (size_t e = 0; e < used; ++e, k += CHUNK_KEY_SIZE + 8) {
+                put_le(k, cbytes, 4);                         /* chunk size in bytes (no filters) */
+                put_le(k + 4, 0, 4);                          /* filter mask */
+                put_le(k + 8, first[e0 + e] * d->chunk, 8);   /* element offset along the dataset's dimension */
+                put_le(k + 16, 0, 8);                         /* ... along the element dimension */
+                put_le(k + CHUNK_KEY_SIZE, addr[e0 + e], 8);
+            }
+            /* the key after the last child: the far corner of the last chunk this node covers */
+            const size_t next_first = (e0 + used < nent) ? first[e0 + used] : nchunks;
+            put_le(k, 0, 4);
+            put_le(k + 4, 0, 4);
+            put_le(k + 8, next_first * d->chunk, 8);
+            put_le(k + 16, es, 8);
+        }
+        for (size_t q = 0; q < nnodes; ++q) { /* the next level's entries: one per node of this one */
+            first[q] = first[q * per];
+            addr[q] = at + q * nsz;
+        }
+        const size_t level_at = at;
+        at += nnodes * nsz;
+        if (at > w->n) w->n = at;
+        nent = nnodes;
+        if (nnodes == 1) {
+            *root_out = level_at;
+            break;
+        }
+    }
+    free(first);
+    free(addr);
+    return at;
 }
 
 static int h5_write(const char *path, h5_file *f)
@@ -578,7 +679,7 @@ static int h5_write(const char *path, h5_file *f)
     for (int i = 0; i < f->ng; ++i)
         for (int j = 0; j < f->g[i].nd; ++j) {
             hdr_addr[k++] = cursor;
-            cursor += DSET_OHDR_SIZE;
+            cursor += dset_ohdr_size(&f->g[i].d[j]);
         }
     cursor = align8(cursor);
     k = 0;
@@ -586,6 +687,18 @@ static int h5_write(const char *path, h5_file *f)
         for (int j = 0; j < f->g[i].nd; ++j) {
             const h5_dset *d = &f->g[i].d[j];
             const size_t bytes = d->n * (d->is_i8 ? 1 : 8);
+            if (d->chunk && d->n) {
+                uint64_t root = 0;
+                const size_t next = write_chunks(&w, cursor, d, &root);
+                if (!next || !write_dataset_header(&w, hdr_addr[k], d, root)) {
+                    rc = MCRAT_IO_ERR_NOMEM;
+                    break;
+                }
+                cursor = align8(next);
+                if (cursor > w.n) w.n = cursor;
+                k++;
+                continue;
+            }
             if (!write_dataset_header(&w, hdr_addr[k], d, cursor) || !wb_reserve(&w, cursor + bytes + 8)) {
                 rc = MCRAT_IO_ERR_NOMEM;
                 break;
@@ -1129,6 +1242,10 @@ static int load_dset_cb(void *ctx, const char *name, uint64_t ohdr)
     if (!tmp) return MCRAT_IO_ERR_NOMEM;
     rc = read_dataset_raw(L->r, &o, tmp, n, is_i8);
     if (rc == MCRAT_IO_OK) rc = h5_dset_append(L->g, name, is_i8, tmp, n);
+    if (rc == MCRAT_IO_OK && o.layout_class == 2) { /* an extendible dataset stays one, with the chunk size it was created with */
+        h5_dset *d = h5_dset_get(L->g, name, 0);
+        if (d) d->chunk = o.chunk_dims[0] ? o.chunk_dims[0] : 1;
+    }
     free(tmp);
     return rc;
 }
@@ -1232,13 +1349,18 @@ API int mcrat_b200_print_photons(const char *dir, int angle_rank, int frame, con
         size_t c = 0;
         for (int i = 0; i < list_capacity; ++i)
             if (photons[i].weight != 0) col[c++] = photon_field(&photons[i], k);
+        const int is_new = h5_dset_get(g, F64_NAMES_ALL[k], 0) == NULL;
         rc = h5_dset_append(g, F64_NAMES_ALL[k], 0, col, n);
+        /* H5Pset_chunk(prop, rank, dims) with dims = the number of photons of the first write, Src/mcrat_io.c:254 */
+        if (rc == MCRAT_IO_OK && is_new) h5_dset_get(g, F64_NAMES_ALL[k], 0)->chunk = n ? n : 1;
     }
     if (rc == MCRAT_IO_OK && sw->save_type) {
         size_t c = 0;
         for (int i = 0; i < list_capacity; ++i)
             if (photons[i].weight != 0) types[c++] = (signed char)photons[i].type;
+        const int is_new = h5_dset_get(g, "PT", 0) == NULL;
         rc = h5_dset_append(g, "PT", 1, types, n);
+        if (rc == MCRAT_IO_OK && is_new) h5_dset_get(g, "PT", 0)->chunk = n ? n : 1;
     }
     free(col);
     free(types);

@@ -137,6 +137,31 @@ class H5File:
             assert (size, off, prec) == (1, 0, 8) and (ty[1] & 8), "signed 8-bit integer"
             dt = np.dtype("i1")
         n = int(np.prod(dims)) if rank else 1
+        self.last_dataset_info = dict(chunk=None, maxdims=None)
+        if flags & 1:
+            self.last_dataset_info["maxdims"] = struct.unpack("<%dQ" % rank, sp[8 + 8 * rank:8 + 16 * rank])
+        if lay[0] == 3 and lay[1] == 2:
+            # chunked storage: dimensionality = rank + 1 (the last one is the element size), version-1 B-tree of node type 1
+            ndim = lay[2]
+            assert ndim == rank + 1 == 2, "1-D chunked dataset"
+            bt = struct.unpack("<Q", lay[3:11])[0]
+            cdims = struct.unpack("<%dI" % ndim, lay[11:11 + 4 * ndim])
+            assert cdims[-1] == dt.itemsize and cdims[0] > 0
+            self.last_dataset_info["chunk"] = cdims[0]
+            out = np.zeros(n, dt)
+            if bt != UNDEF:
+                chunks = self.chunk_tree(bt, ndim, cdims)
+                # chunks tile the dataset from 0 in steps of the chunk size, none missing, none past the end
+                assert [c[0] for c in chunks] == list(range(0, len(chunks) * cdims[0], cdims[0]))
+                assert (len(chunks) - 1) * cdims[0] < n <= len(chunks) * cdims[0]
+                for off, nbytes, addr in chunks:
+                    assert nbytes == cdims[0] * dt.itemsize
+                    part = np.frombuffer(self.at(addr, nbytes), dtype=dt)
+                    m = min(cdims[0], n - off)
+                    out[off:off + m] = part[:m]
+            else:
+                assert n == 0
+            return "dataset", out.reshape(dims)
         if lay[0] == 3:
             assert lay[1] == 1, "contiguous layout"
             addr, nbytes = struct.unpack("<QQ", lay[2:18])
@@ -146,6 +171,45 @@ class H5File:
             addr = struct.unpack("<Q", lay[8:16])[0]
         data = np.frombuffer(self.at(addr, n * dt.itemsize), dtype=dt).reshape(dims) if n else np.zeros(dims, dt)
         return "dataset", data
+
+    def chunk_tree(self, node, ndim, cdims, level=None, left=UNDEF):
+        """Version-1 B-tree, node type 1 (raw data chunks): -> [(element offset, chunk bytes, address)] in key order.
+        Checks the node header, the ascending keys, the key after the last child and the sibling links."""
+        keysz = 8 + 8 * ndim
+        hdr = self.at(node, 24)
+        assert hdr[:4] == b"TREE" and hdr[4] == 1
+        lvl, used = hdr[5], struct.unpack("<H", hdr[6:8])[0]
+        lsib, rsib = struct.unpack("<QQ", hdr[8:24])
+        assert level is None or lvl == level
+        assert 0 < used <= 64, "2K entries at most, K = 32 for superblock version 0"
+        # the library reads whole nodes: the full-size node must lie inside the file
+        self.at(node, 24 + 65 * keysz + 64 * 8)
+        body = self.at(node + 24, used * (keysz + 8) + keysz)
+        keys, kids = [], []
+        for e in range(used + 1):
+            k = body[e * (keysz + 8):e * (keysz + 8) + keysz]
+            nbytes, mask = struct.unpack("<II", k[:8])
+            offs = struct.unpack("<%dQ" % ndim, k[8:])
+            keys.append((nbytes, mask, offs))
+            if e < used:
+                kids.append(struct.unpack("<Q", body[e * (keysz + 8) + keysz:(e + 1) * (keysz + 8)])[0])
+        for e in range(used):
+            assert keys[e][1] == 0 and keys[e][2][-1] == 0, "no filters; element-dimension offset 0"
+            assert keys[e][2][0] % cdims[0] == 0
+            assert keys[e][2][0] < keys[e + 1][2][0], "keys ascend; the last key bounds the node from above"
+        out = []
+        if lvl == 0:
+            for e in range(used):
+                out.append((keys[e][2][0], keys[e][0], kids[e]))
+            self._chunk_leaves.append((node, lsib, rsib))
+        else:
+            for e in range(used):
+                sub = self.chunk_tree(kids[e], ndim, cdims, lvl - 1)
+                assert sub[0][0] == keys[e][2][0], "an internal key is the first key of its child"
+                out += sub
+        return out
+
+    _chunk_leaves = []
 
     def tree(self):
         """Whole file as nested dicts {name: array | dict}."""

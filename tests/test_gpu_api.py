@@ -815,3 +815,83 @@ def test_dropin_covers_the_cyclosynchrotron_calls_of_the_driver(tmp_path):
     D.__wrap_initalizeHotCrossSection(C.c_int(0), None, None)
     D.__wrap_cleanupInterpolationData()
     D.mcrat_b200_dropin_shutdown()
+
+
+@pytest.mark.gpu
+def test_photons_without_a_containing_cell_are_reported_and_logged_like_the_reference(tmp_path):
+    """findContainingBlock writes one line per photon it finds no block for (Src/geometry.c:373-388) and returns -1
+    (Src/mclib.c:581-584).  The device counts them (frame_stats.not_found), keeps slot and hydro coordinates of the first
+    32, and the drop-in writes the reference's line to the rank's log."""
+    cfg, hydro, photons, frame = synth.workload("C2", scale=1.0 / 16, n_photons=300, seed=4)
+    cells = synth.locate_photons(hydro, photons)
+    hole = int(cells[5])
+    keep = np.ones(int(hydro["num_elements"]), dtype=bool)
+    keep[hole] = False
+    h2 = dict(hydro)
+    for f in lib.HYDRO_FIELDS:
+        if f in hydro:
+            h2[f] = np.ascontiguousarray(np.asarray(hydro[f])[keep])
+    h2["num_elements"] = int(keep.sum())
+    lost = np.nonzero(cells == hole)[0]
+    hp = HotPath(cfg, seed=1)
+    hp.set_hydro(h2)
+    hp.set_photons(photons)
+    hp.findContainingHydroCell(1)
+    slots, hc, total = hp.not_found()
+    assert total == lost.size and sorted(slots.tolist()) == lost.tolist()
+    e0, e1, _ = synth.mcrat_to_hydro(cfg["dimensions"], cfg["geometry"], photons["r0"], photons["r1"], photons["r2"])
+    for s, c in zip(slots, hc):
+        assert c[0] == e0[s] and c[1] == e1[s]
+    assert hp.not_found()[2] == 0                     # reading clears the log
+    got = hp.get_photons()
+    assert (got["nearest_block_index"][lost] == -1).all()
+    o = api.Oracle(cfg)
+    o.set_hydro(h2)
+    o.set_photons(photons)
+    o.find_containing_hydro_cell(1, api.OracleRng("philox", seed=1, shard=0))
+    assert np.array_equal(o.photons()["nearest_block_index"], got["nearest_block_index"])
+    hp.close()
+
+    # the same through the reference-signature wrapper, with a rank log file
+    D = C.CDLL(lib.DROPIN_PATH)
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+
+    class PhotonList(C.Structure):
+        _fields_ = [("photons", C.c_void_p), ("sorted_indexes", C.POINTER(C.c_int)), ("num_photons", C.c_int),
+                    ("num_null_photons", C.c_int), ("list_capacity", C.c_int)]
+
+    class Hydro(C.Structure):
+        _fields_ = ([("num_elements", C.c_int)] + [(f, C.POINTER(C.c_double)) for f in api.HYDRO_FIELDS] +
+                    [("r0_domain", C.c_double * 2), ("r1_domain", C.c_double * 2), ("r2_domain", C.c_double * 2),
+                     ("fps", C.c_double), ("scatt_frame_number", C.c_int), ("inj_frame_number", C.c_int),
+                     ("last_frame", C.c_int), ("increment_inj_frame", C.c_int), ("increment_scatt_frame", C.c_int),
+                     ("grid", C.c_void_p)])
+
+    c = lib.Config(lib.ABI_VERSION, cfg["dimensions"], cfg["geometry"], cfg["stokes"], cfg["tau_calculation"],
+                   cfg["cyclosynch"], cfg["b_field_calc"], cfg["epsilon_b"], 0, 0, 99, 2, 0, None, 0)
+    assert D.mcrat_b200_dropin_configure(C.byref(c)) == 0
+    ph = np.ascontiguousarray(photons.copy())
+    sorted_idx = np.zeros(ph.size, dtype=np.int32)
+    pl = PhotonList(ph.ctypes.data, sorted_idx.ctypes.data_as(C.POINTER(C.c_int)), ph.size, 0, ph.size)
+    h = Hydro()
+    keep_alive = []
+    h.num_elements = h2["num_elements"]
+    for f in api.HYDRO_FIELDS:
+        a = np.ascontiguousarray(h2[f], dtype=np.float64)
+        keep_alive.append(a)
+        setattr(h, f, a.ctypes.data_as(C.POINTER(C.c_double)))
+    for k in ("r0_domain", "r1_domain", "r2_domain"):
+        getattr(h, k)[0], getattr(h, k)[1] = h2[k]
+    h.fps = h2["fps"]
+    log = tmp_path / "mc_output_0.log"
+    fp = libc.fopen(str(log).encode(), b"w")
+    D.__wrap_findContainingHydroCell.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    D.__wrap_findContainingHydroCell(C.byref(pl), C.byref(h), 1, None, fp)
+    libc.fclose(fp)
+    D.mcrat_b200_dropin_shutdown()
+    lines = log.read_text().splitlines()
+    want = sorted("MCRaT Couldn't find a block for the photon located at r0=%e r1=%e" % (e0[s], e1[s]) for s in lost)
+    assert sorted(lines) == want

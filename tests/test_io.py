@@ -318,3 +318,50 @@ def test_reader_takes_chunked_extendible_datasets(tmp_path):
     _hand_built_chunked_file(path, vals, chunk=500)
     assert mio.h5_list(path) == ["PW"]
     assert np.array_equal(mio.h5_read(path, "PW"), vals)
+
+
+def test_mc_proc_datasets_are_chunked_and_extendible_like_the_reference(tmp_path):
+    """printPhotons creates every dataset with H5Pset_chunk(dims = photons of the first write) and an unlimited maximum
+    dimension, then H5Dset_extent + a hyperslab write per append (Src/mcrat_io.c:140, 254-263, 423-705); dirFileMerge
+    creates plain contiguous datasets (:1649).  Checked with the independent parser: chunk size, maximum dimension,
+    chunk B-tree invariants, data."""
+    from h5spec import UNDEF
+    d = str(tmp_path)
+    sw = mio.switches(comv=1, save_type=1, stokes=1)
+    first, second, third = _photons(211, seed=5), _photons(97, seed=6), _photons(500, seed=7)
+    n1 = int((first["weight"] != 0).sum())
+    for ph in (first, second, third):
+        mio.print_photons(d, 0, 300, ph, sw)
+    f = H5File(os.path.join(d, "mc_proc_0.h5"))
+    g = f.tree()["300"]
+    links = f.object(f.object(f.root_ohdr)[1]["300"])[1]
+    for name in NAMES:
+        kind, arr = f.object(links[name])
+        assert kind == "dataset"
+        assert f.last_dataset_info["chunk"] == n1, name                    # the first write's count, kept by the appends
+        assert f.last_dataset_info["maxdims"] == (UNDEF,), name            # H5S_UNLIMITED
+        want = np.concatenate([_expect(first, name), _expect(second, name), _expect(third, name)])
+        assert np.array_equal(arr, want) and np.array_equal(g[name], want), name
+        assert np.array_equal(mio.h5_read(os.path.join(d, "mc_proc_0.h5"), "300/" + name), want)
+    mio.merge_frame(d, 300, [0], sw)
+    m = H5File(os.path.join(d, "mcdata_300.h5"))
+    for name, oh in m.object(m.root_ohdr)[1].items():
+        m.object(oh)
+        assert m.last_dataset_info["chunk"] is None and m.last_dataset_info["maxdims"] is None, name
+
+
+def test_many_appends_build_a_chunk_tree_with_internal_nodes(tmp_path):
+    """More chunks than one B-tree node holds (2K = 64): leaves linked left to right under an internal level."""
+    d = str(tmp_path)
+    sw = mio.switches(comv=0, save_type=1, stokes=0)
+    blocks = [_photons(8, seed=100 + k) for k in range(150)]
+    for ph in blocks:
+        mio.print_photons(d, 2, 77, ph, sw)
+    f = H5File(os.path.join(d, "mc_proc_2.h5"))
+    g = f.tree()["77"]
+    n0 = int((blocks[0]["weight"] != 0).sum())
+    for name in ("P0", "R2", "NS", "PW", "PT"):
+        want = np.concatenate([_expect(ph, name) for ph in blocks])
+        assert want.size > 64 * n0, "the case must need more than one leaf"
+        assert np.array_equal(g[name], want), name
+        assert np.array_equal(mio.h5_read(os.path.join(d, "mc_proc_2.h5"), "77/" + name), want), name
