@@ -227,6 +227,26 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
 // A halted shard (frame end, max_iters, pause, many re-locations) releases generation UINT_MAX: its items are skipped.
 // ------------------------------------------------------------------------------------------
 constexpr unsigned STREAM_SPIN_LIMIT = 1u << 24;
+constexpr unsigned STREAM_START_SPINS = 1u << 19; // x >= 40 ns: the other grid has ~30 ms to show up before the launch is called off
+enum { STREAM_UNDECIDED = 0, STREAM_GO = 1, STREAM_ABORT = 2 };
+
+// Start-up handshake of the two grids (thread 0 of every block).  Pass blocks: wait until all event blocks are resident,
+// then vote GO; event blocks: wait for the vote.  Whoever waits too long votes ABORT; the first vote stands (atomicCAS)
+// and is taken before any photon is touched, so an aborted launch leaves the lists exactly as they were.
+__device__ __forceinline__ int stream_handshake(GlobalState &gs, const bool is_pass, const int evt_blocks)
+{
+    unsigned spins = 0;
+    for (;;) {
+        const int state = *(volatile int *)&gs.stream_state;
+        if (state != STREAM_UNDECIDED) return state;
+        if (is_pass && *(volatile int *)&gs.stream_evt_ready >= evt_blocks) {
+            atomicCAS(&gs.stream_state, STREAM_UNDECIDED, STREAM_GO);
+            continue;
+        }
+        __nanosleep(40);
+        if (++spins > STREAM_START_SPINS) atomicCAS(&gs.stream_state, STREAM_UNDECIDED, STREAM_ABORT);
+    }
+}
 constexpr int STREAM_PASS_CTAS_PER_SM = 4;      // pass blocks per SM: leaves the registers of one event block free on every SM
 constexpr int STREAM_PASS_SMEM_PAD = 50 * 1024; // dynamic shared memory that enforces it: 4 x (50 KB + static) fit in 228 KB, 5 do not
 
@@ -255,9 +275,10 @@ __global__ void __launch_bounds__(PASS_THREADS, MCRAT_PASS_MINB) frame_stream_pa
     const int S = d.nshards, team = bps + 1;
     const unsigned long long per_iter = (unsigned long long)S * (unsigned long long)bps;
     const unsigned limit = d.tau_calc == TAU_TABLE ? (1u << 28) : STREAM_SPIN_LIMIT;
-    if (threadIdx.x == 0) sh_flag = stream_wait_ge(gs, (const unsigned *)&gs.stream_evt_ready, (unsigned)evt_blocks, limit) ? 1 : 0;
+    if (threadIdx.x == 0) sh_flag = (stream_handshake(gs, true, evt_blocks) == STREAM_GO) ? 1 : 0;
     __syncthreads();
     if (!sh_flag) return;
+    __threadfence();
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -315,6 +336,12 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_stream_
     const int s = blockIdx.x;
     ShardState &gst = d.sh[s];
     const unsigned limit = d.tau_calc == TAU_TABLE ? (1u << 28) : STREAM_SPIN_LIMIT;
+    if (threadIdx.x == 0) {
+        atomicAdd(&gs.stream_evt_ready, 1); // resident
+        sh_flag = (stream_handshake(gs, false, 0) == STREAM_GO) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!sh_flag) return; // called off: nothing touched
     if (threadIdx.x < SHARD_STATE_WORDS)
         reinterpret_cast<unsigned long long *>(&st)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&gst)[threadIdx.x];
     __syncthreads();
@@ -322,8 +349,6 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_stream_
         d.bm_t[s * team + bps] = DBL_MAX;
         d.bm_i[s * team + bps] = INT_MAX;
         st.mini_slot = -1;
-        __threadfence();
-        atomicAdd(&gs.stream_evt_ready, 1); // resident: the pass blocks may start pulling items
     }
     __syncthreads();
     bool halt = st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters);

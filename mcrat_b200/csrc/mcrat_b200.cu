@@ -307,6 +307,14 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
     }
     if ((e = cudaFuncSetAttribute(frame_stream_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_PASS_SMEM_PAD)) != cudaSuccess)
         return bail(e, "cudaFuncSetAttribute");
+    // blocks of the two grids of the persistent stream share SMs: both ask for the same L1 / shared-memory split, or the
+    // SM would have to drain before it could take a block of the other kernel
+    if (!getenv("MCRAT_B200_STREAM_NOCARVE")) {
+        if ((e = cudaFuncSetAttribute(frame_stream_pass_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
+            return bail(e, "cudaFuncSetAttribute");
+        if ((e = cudaFuncSetAttribute(frame_stream_event_kernel<EVT_THREADS_MANY>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
+            return bail(e, "cudaFuncSetAttribute");
+    }
     if ((e = cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(0))) != cudaSuccess)
         return bail(e, "cudaFuncSetAttribute");
     if ((e = cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(1))) != cudaSuccess)
@@ -837,6 +845,7 @@ __global__ void reset_loop_kernel(DevCtx d, int set_times, double time_now, doub
         d.gs->stream_work = 0;
         d.gs->stream_evt_ready = 0;
         d.gs->stream_halted = 0;
+        d.gs->stream_state = 0;
     }
 }
 
@@ -1271,6 +1280,7 @@ __global__ void reset_protocol_kernel(DevCtx d)
         d.gs->stream_work = 0;
         d.gs->stream_evt_ready = 0;
         d.gs->stream_halted = 0;
+        d.gs->stream_state = 0;
     }
 }
 
@@ -1337,6 +1347,8 @@ static int launch_frame_stream(mcrat_b200_ctx *ctx)
         Timed t(ctx, KC_EVENT);
         frame_stream_event_kernel<EVT_THREADS_MANY><<<S, EVT_THREADS_MANY, 0, ctx->stream2>>>(ctx->d, bps);
         if (int rc = check_launch(ctx, "frame_stream_event_kernel")) return rc;
+        // test hook: what a profiler that serialises kernels does to the pair (the event blocks never meet the pass blocks)
+        if (getenv("MCRAT_B200_STREAM_SERIALIZE")) CK(cudaStreamSynchronize(ctx->stream2));
     }
     {
         // Whatever order the two grids reach the SMs in, every event block must find room: the pass blocks carry enough
@@ -1344,11 +1356,16 @@ static int launch_frame_stream(mcrat_b200_ctx *ctx)
         // registers of one event block (128 threads x 128) free on every SM -- one slot per SM >= one per sub-shard.
         Timed t(ctx, KC_PASS);
         const int grid = ctx->num_sms * STREAM_PASS_CTAS_PER_SM;
-        frame_stream_pass_kernel<<<grid, PASS_THREADS, STREAM_PASS_SMEM_PAD, ctx->stream>>>(ctx->d, bps, S);
+        int pad = STREAM_PASS_SMEM_PAD;
+        if (const char *e = getenv("MCRAT_B200_STREAM_PAD")) pad = atoi(e); // experiments
+        frame_stream_pass_kernel<<<grid, PASS_THREADS, pad, ctx->stream>>>(ctx->d, bps, S);
         if (int rc = check_launch(ctx, "frame_stream_pass_kernel")) return rc;
     }
     CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    // did the two grids meet?  (a profiler that serialises kernels, a device shared with another tenant: they may not)
+    if (int rc = fetch_global(ctx)) return rc;
+    if (ctx->gs_host->stream_state == 2 /* STREAM_ABORT */) return MCRAT_B200_LOOP_FALLBACK;
     return MCRAT_B200_OK;
 }
 

@@ -126,6 +126,9 @@ struct GlobalState {
     // persistent loop for lists larger than L2 (frame_stream_*_kernel): next pass item, event blocks resident, shards halted
     unsigned long long stream_work;
     int stream_evt_ready, stream_halted;
+    int stream_state; // 0 undecided, 1 go (every event block is resident and the pass blocks have seen it), 2 abort (the two
+                      // grids did not become co-resident in time -- a profiler serialising kernels, a shared device --:
+                      // nothing has been touched, the host runs the streamed loop instead)
     int error_slot, error_site; // photon slot (or -1) and ERR_SITE_* of the first error raised (raise_error)
     long long cell_evals, box_evals, max_iters;
     long long ref_equiv_evals; // first-hit index + 1 summed over the photons of full rescans (what the reference's loop executes)

@@ -291,6 +291,32 @@ def test_warp_wide_maxwell_juttner_sampling_equals_the_sequential_loop(monkeypat
             assert np.array_equal(out[None][0][f], out[r][0][f], equal_nan=out[None][0].dtype[f].kind == "f"), (r, f)
 
 
+def test_persistent_stream_pair_is_called_off_when_its_grids_cannot_meet(monkeypatch):
+    """The loop of lists larger than L2 runs as two co-resident grids.  Where they cannot be co-resident (ncu serialises
+    kernels; a device shared with another tenant) the start-up handshake calls the launch off before a photon is touched
+    and the frame runs through the streamed loop: same photons, no error."""
+    cfg, hydro, photons, frame = synth.workload("C5", scale=1.0 / 8, n_photons=4000, seed=41)
+    out = {}
+    for mode, serialise in (("streamed", False), ("persistent_stream", False), ("persistent_stream", True)):
+        if serialise:
+            monkeypatch.setenv("MCRAT_B200_STREAM_SERIALIZE", "1")
+        hp = HotPath(cfg, seed=31, shard=3, num_shards=8, loop_mode=mode)
+        hp.set_hydro(hydro)
+        hp.set_photons(photons)
+        st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=80, switch=1)
+        st2 = hp.run_frame(st["time_now"], 1.0 / frame["fps"], max_iters=40, switch=0)  # stays on the streamed loop
+        out[(mode, serialise)] = (st, st2, hp.get_photons(), hp.launch_count())
+        hp.close()
+        monkeypatch.delenv("MCRAT_B200_STREAM_SERIALIZE", raising=False)
+    a = out[("streamed", False)]
+    for key in (("persistent_stream", False), ("persistent_stream", True)):
+        b = out[key]
+        assert a[0]["scatterings"] == b[0]["scatterings"] and a[1]["scatterings"] == b[1]["scatterings"], key
+        for f in a[2].dtype.names:
+            assert np.array_equal(a[2][f], b[2][f], equal_nan=(a[2].dtype[f].kind == "f")), (key, f)
+    assert out[("persistent_stream", False)][3] < out[("persistent_stream", True)][3]  # the called-off run paid per-iteration launches
+
+
 @pytest.mark.parametrize("nph,shards", [(6000, 2), (9000, 1), (40000, 80)])
 def test_klein_nishina_rejections_streamed_equals_persistent(nph, shards):
     """C3 (x = h nu / m c^2 up to 10): a third of the candidates is rejected by the Klein-Nishina test and the event
