@@ -237,8 +237,8 @@ int mcrat_b200_set_recheck_skip(mcrat_b200_ctx *ctx, int mode);
  *   iteration) go through the grid-wide re-location kernels: pass, K1 / K1b / K1c, finish, event.
  * PERSISTENT: one cooperative launch per frame; every sub-shard is iterated by resident blocks that hand over through
  *   a generation word in global memory (no launch boundary inside the loop).
- * AUTO (default): PERSISTENT while the list fits in L2 (<= 2^21 photons); above, PERSISTENT_STREAM with up to one
- *   sub-shard per SM and STREAMED with more.
+ * AUTO (default): PERSISTENT while the list fits in L2 (<= 2^21 photons); above, PERSISTENT_STREAM from 32 sub-shards
+ *   on and STREAMED with fewer.
  * In all of them sub-shards advance independently, like MPI ranks, and the photons are bit-identical; the replay
  * harness always runs STREAMED_GLOBAL. */
 #define MCRAT_B200_LOOP_AUTO 0
@@ -246,8 +246,8 @@ int mcrat_b200_set_recheck_skip(mcrat_b200_ctx *ctx, int mode);
 #define MCRAT_B200_LOOP_PERSISTENT 2
 #define MCRAT_B200_LOOP_STREAMED_GLOBAL 3 /* streamed, every iteration through the grid-wide re-location kernels (four launches;
                                           * what STREAMED falls back to for new hydro frames and optically thin flows) */
-#define MCRAT_B200_LOOP_PERSISTENT_STREAM 4 /* lists larger than L2, up to one sub-shard per SM: resident event blocks (one per
-                                           * sub-shard) beside resident pass blocks that pull (iteration, sub-shard, slice)
+#define MCRAT_B200_LOOP_PERSISTENT_STREAM 4 /* lists larger than L2: resident event blocks (each serving a few sub-shards
+                                           * in turn) beside resident pass blocks that pull (iteration, sub-shard, slice)
                                            * items from a counter -- the PERSISTENT protocol without tying pass blocks to a
                                            * shard, so the photon columns stream through the SMs without a launch boundary
                                            * while the scatterings run beside them.  AUTO picks it above 2^21 photons. */

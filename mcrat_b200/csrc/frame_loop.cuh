@@ -214,7 +214,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
 // release on gst.gen, mini-pass by the event block -- but the pass blocks are not tied to a shard.  Two kernels run
 // side by side (the pass needs 48 registers and 40 warps per SM to keep HBM busy, the event 128 registers and three
 // warps; one kernel could not have both):
-//   frame_stream_event_kernel  one resident block per sub-shard; exactly the event block of frame_loop_kernel
+//   frame_stream_event_kernel  resident blocks, each serving a few sub-shards in turn; per shard exactly the event block of
+//                              frame_loop_kernel
 //   frame_stream_pass_kernel   resident blocks pull pass items (iteration k, shard s, block b) from a counter, in that
 //                              order: the item waits until shard s has released generation k (its event of iteration
 //                              k - 1 has accepted a candidate), runs pass_body over its slice and draws a ticket.
@@ -247,8 +248,14 @@ __device__ __forceinline__ int stream_handshake(GlobalState &gs, const bool is_p
         if (++spins > STREAM_START_SPINS) atomicCAS(&gs.stream_state, STREAM_UNDECIDED, STREAM_ABORT);
     }
 }
-constexpr int STREAM_PASS_CTAS_PER_SM = 4;      // pass blocks per SM: leaves the registers of one event block free on every SM
-constexpr int STREAM_PASS_SMEM_PAD = 50 * 1024; // dynamic shared memory that enforces it: 4 x (50 KB + static) fit in 228 KB, 5 do not
+constexpr int STREAM_PASS_CTAS_PER_SM = 4; // pass blocks on an SM that also holds an event block (48 + 16 K registers); 5 elsewhere
+// Blocks of the two grids share SMs, and an SM runs with ONE split of its 256 KB between L1 and shared memory: a block of a
+// kernel the driver has configured for another split waits until the SM has drained.  Both kernels therefore (a) ask for the
+// same carve-out (cudaFuncAttributePreferredSharedMemoryCarveout, 32 KB) and (b) actually need it at full occupancy -- the
+// pass blocks carry 3 KB of unused dynamic shared memory for that -- or the driver overrides the preference.  Measured:
+// without (a) or without (b) the pass grid starts only when the event grid has left (the start-up handshake calls the launch
+// off); with the maximum carve-out for both they meet, but the pass loses its spills' L1 (281 against 207 us per iteration).
+constexpr int STREAM_PASS_SMEM_PAD = 3072;
 
 __device__ __forceinline__ bool stream_wait_ge(GlobalState &gs, const unsigned *word, unsigned target, unsigned limit)
 {
@@ -275,66 +282,81 @@ __global__ void __launch_bounds__(PASS_THREADS, MCRAT_PASS_MINB) frame_stream_pa
     const int S = d.nshards, team = bps + 1;
     const unsigned long long per_iter = (unsigned long long)S * (unsigned long long)bps;
     const unsigned limit = d.tau_calc == TAU_TABLE ? (1u << 28) : STREAM_SPIN_LIMIT;
-    if (threadIdx.x == 0) sh_flag = (stream_handshake(gs, true, evt_blocks) == STREAM_GO) ? 1 : 0;
+    if (threadIdx.x == 0) {
+        sh_flag = (stream_handshake(gs, true, evt_blocks) == STREAM_GO) ? 1 : 0;
+        if (sh_flag) sh_item = atomicAdd(&gs.stream_work, 1ull);
+    }
     __syncthreads();
     if (!sh_flag) return;
-    __threadfence();
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            sh_item = atomicAdd(&gs.stream_work, 1ull);
-            sh_flag = (*(volatile int *)&gs.stream_halted >= S || *(volatile int *)&gs.error != 0) ? 0 : 1;
-        }
-        __syncthreads();
-        if (!sh_flag) return;
         const unsigned long long item = sh_item;
         const unsigned long long k64 = item / per_iter;
         const unsigned rem = (unsigned)(item - k64 * per_iter);
         const int s = (int)(rem / (unsigned)bps), b = (int)(rem - (unsigned)s * (unsigned)bps);
         const unsigned k = (unsigned)k64;
         ShardState &gst = d.sh[s];
-        if (k > 0) {
-            if (threadIdx.x == 0) sh_flag = stream_wait_ge(gs, &gst.gen, k, limit) ? 1 : 0;
-            __syncthreads();
-            if (!sh_flag) return;
+        // wait until shard s has released generation k (halted shards release UINT_MAX); stop when every shard has halted
+        if (threadIdx.x == 0) {
+            int ok = (*(volatile int *)&gs.stream_halted >= S || *(volatile int *)&gs.error != 0) ? 0 : 1;
+            if (ok && k > 0) ok = stream_wait_ge(gs, &gst.gen, k, limit) ? 1 : 0;
+            sh_flag = ok;
         }
+        __syncthreads();
+        if (!sh_flag) return;
         if (threadIdx.x < SHARD_STATE_WORDS)
             reinterpret_cast<unsigned long long *>(&st)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&gst)[threadIdx.x];
         __syncthreads();
         // the stop test at entry, shard state only (the event block decides alike), later the published halt flag
         // (a shard that was stopped at entry never publishes: its state says so by itself)
         const bool halt = (st.halt != 0) | st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters);
-        if (halt) continue;
         double best_t = DBL_MAX;
         int best_i = INT_MAX;
-        pass_body<true, true, PASS_THREADS>(d, st, s, b, bps, 0, 0, best_t, best_i);
-        block_argmin<PASS_THREADS>(best_t, best_i);
-        if (threadIdx.x == 0) {
-            int bidx = -1;
-            double btemp = 0;
-            if (best_i != INT_MAX) {
-                bidx = d.ph.idx[best_i];
-                if (bidx >= 0) btemp = d.cells.temp[bidx];
-            }
-            d.bm_t[s * team + b] = best_t;
-            d.bm_i[s * team + b] = best_i;
-            d.bm_idx[s * team + b] = bidx;
-            d.bm_temp[s * team + b] = btemp;
-            __threadfence();
-            atomicAdd(&gst.arrive, 1u);
+        if (!halt) {
+            pass_body<true, true, PASS_THREADS>(d, st, s, b, bps, 0, 0, best_t, best_i);
+            block_argmin<PASS_THREADS>(best_t, best_i);
         }
+        __syncthreads(); // everybody is done with sh_item and st
+        if (threadIdx.x == 0) {
+            // the next item is requested before this one's result is published: one round trip instead of two
+            const unsigned long long next = atomicAdd(&gs.stream_work, 1ull);
+            if (!halt) {
+                int bidx = -1;
+                double btemp = 0;
+                if (best_i != INT_MAX) {
+                    bidx = d.ph.idx[best_i];
+                    if (bidx >= 0) btemp = d.cells.temp[bidx];
+                }
+                d.bm_t[s * team + b] = best_t;
+                d.bm_i[s * team + b] = best_i;
+                d.bm_idx[s * team + b] = bidx;
+                d.bm_temp[s * team + b] = btemp;
+                __threadfence();
+                atomicAdd(&gst.arrive, 1u);
+            }
+            sh_item = next;
+        }
+        __syncthreads();
     }
 }
+
+// One event block serves `stride`-spaced sub-shards s = blockIdx.x, blockIdx.x + gridDim.x, ... (at most STREAM_EVT_SHARDS of
+// them), one after the other within an iteration -- the order the pass stream reaches them in, gridDim.x shards (tens
+// of microseconds of streaming) apart, so a block is rarely asked for two events at once.  Fewer event blocks leave
+// more SMs with room for a fifth pass block.  Every shard keeps its own state in shared memory between iterations,
+// exactly as the event block of frame_loop_kernel does for its one shard.
+constexpr int STREAM_EVT_SHARDS = 8;
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_stream_event_kernel(DevCtx d, const int bps)
 {
-    __shared__ ShardState st;
+    __shared__ ShardState sts[STREAM_EVT_SHARDS];
     __shared__ int sh_flag;
+    __shared__ int sh_halted[STREAM_EVT_SHARDS];
+    __shared__ unsigned sh_k[STREAM_EVT_SHARDS];
     GlobalState &gs = *d.gs;
     const int team = bps + 1;
-    const int s = blockIdx.x;
-    ShardState &gst = d.sh[s];
+    const int S = d.nshards, E = gridDim.x;
+    const int mine = (S - (int)blockIdx.x + E - 1) / E; // shards of this block
     const unsigned limit = d.tau_calc == TAU_TABLE ? (1u << 28) : STREAM_SPIN_LIMIT;
     if (threadIdx.x == 0) {
         atomicAdd(&gs.stream_evt_ready, 1); // resident
@@ -342,65 +364,100 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_stream_
     }
     __syncthreads();
     if (!sh_flag) return; // called off: nothing touched
-    if (threadIdx.x < SHARD_STATE_WORDS)
-        reinterpret_cast<unsigned long long *>(&st)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&gst)[threadIdx.x];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        d.bm_t[s * team + bps] = DBL_MAX;
-        d.bm_i[s * team + bps] = INT_MAX;
-        st.mini_slot = -1;
-    }
-    __syncthreads();
-    bool halt = st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters);
-    unsigned k = 0;
-    while (!halt) {
-        if (threadIdx.x == 0) sh_flag = stream_wait_ge(gs, &gst.arrive, (k + 1) * (unsigned)bps, limit) ? 1 : 0;
+    int running = 0;
+    for (int j = 0; j < mine; ++j) {
+        const int s = blockIdx.x + j * E;
+        ShardState &gst = d.sh[s];
+        ShardState &st = sts[j];
+        if (threadIdx.x < SHARD_STATE_WORDS)
+            reinterpret_cast<unsigned long long *>(&st)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&gst)[threadIdx.x];
         __syncthreads();
-        if (!sh_flag) break;
-        ++k;
-        double pre_t = DBL_MAX;
-        int pre_i = INT_MAX;
-        const bool have_pre = (team <= THREADS);
-        int pre_idx = -2;
-        double pre_temp = 0;
-        if (have_pre && (int)threadIdx.x < team) {
-            pre_t = *(volatile double *)&d.bm_t[s * team + threadIdx.x];
-            pre_i = *(volatile int *)&d.bm_i[s * team + threadIdx.x];
-            pre_idx = *(volatile int *)&d.bm_idx[s * team + threadIdx.x];
-            pre_temp = *(volatile double *)&d.bm_temp[s * team + threadIdx.x];
+        const bool halt = st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters);
+        if (threadIdx.x == 0) {
+            d.bm_t[s * team + bps] = DBL_MAX;
+            d.bm_i[s * team + bps] = INT_MAX;
+            st.mini_slot = -1;
+            sh_halted[j] = halt ? 1 : 0;
+            sh_k[j] = 0;
+            if (halt) { // stopped at entry: every item of this shard is skipped
+                __threadfence();
+                st_release_u32(&gst.gen, 0xFFFFFFFFu);
+                atomicAdd(&gs.stream_halted, 1);
+            }
         }
-        const int R = *(volatile int *)&gst.reloc_n;
-        if (R > 0) relocate_shard<THREADS>(d, st, s, R);
-        const bool released = event_body<THREADS>(d, s, st.first, R, team, 0, 0.0, st, &gst, k, s * team + bps, have_pre,
-                                                  pre_t, pre_i, pre_idx, pre_temp);
-        if (!released) {
-            if (threadIdx.x == 0) {
-                st.halt = (loop_stopped(gs, st) || st.reloc_heavy) ? 1 : 0;
-                st.mini_slot = -1;
-                d.bm_t[s * team + bps] = DBL_MAX;
+        if (!halt) running++;
+        __syncthreads();
+    }
+    bool gave_up = false;
+    while (running > 0 && !gave_up) {
+        for (int j = 0; j < mine; ++j) {
+            if (sh_halted[j]) continue;
+            const int s = blockIdx.x + j * E;
+            ShardState &gst = d.sh[s];
+            ShardState &st = sts[j];
+            unsigned k = sh_k[j];
+            if (threadIdx.x == 0) sh_flag = stream_wait_ge(gs, &gst.arrive, (k + 1) * (unsigned)bps, limit) ? 1 : 0;
+            __syncthreads();
+            if (!sh_flag) {
+                gave_up = true;
+                break;
+            }
+            ++k;
+            double pre_t = DBL_MAX;
+            int pre_i = INT_MAX;
+            const bool have_pre = (team <= THREADS);
+            int pre_idx = -2;
+            double pre_temp = 0;
+            if (have_pre && (int)threadIdx.x < team) {
+                pre_t = *(volatile double *)&d.bm_t[s * team + threadIdx.x];
+                pre_i = *(volatile int *)&d.bm_i[s * team + threadIdx.x];
+                pre_idx = *(volatile int *)&d.bm_idx[s * team + threadIdx.x];
+                pre_temp = *(volatile double *)&d.bm_temp[s * team + threadIdx.x];
+            }
+            const int R = *(volatile int *)&gst.reloc_n;
+            if (R > 0) relocate_shard<THREADS>(d, st, s, R);
+            const bool released = event_body<THREADS>(d, s, st.first, R, team, 0, 0.0, st, &gst, k, s * team + bps, have_pre,
+                                                      pre_t, pre_i, pre_idx, pre_temp);
+            if (!released) {
+                // frame end, Klein-Nishina walk exhausted: publish now
+                if (threadIdx.x == 0) {
+                    st.halt = (loop_stopped(gs, st) || st.reloc_heavy) ? 1 : 0;
+                    st.mini_slot = -1;
+                    d.bm_t[s * team + bps] = DBL_MAX;
+                    d.bm_i[s * team + bps] = INT_MAX;
+                }
+                __syncthreads();
+                if (threadIdx.x < SHARD_STATE_WORDS)
+                    reinterpret_cast<unsigned long long *>(&gst)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&st)[threadIdx.x];
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    __threadfence();
+                    st_release_u32(&gst.gen, k);
+                }
+            } else if (threadIdx.x == 0 && st.mini_slot < 0) {
+                d.bm_t[s * team + bps] = DBL_MAX; // released with a halt: no mini-pass ran
                 d.bm_i[s * team + bps] = INT_MAX;
             }
             __syncthreads();
-            if (threadIdx.x < SHARD_STATE_WORDS)
-                reinterpret_cast<unsigned long long *>(&gst)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&st)[threadIdx.x];
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                __threadfence();
-                st_release_u32(&gst.gen, k);
+            if (threadIdx.x == 0) sh_k[j] = k;
+            if (st.halt != 0) { // halted: every later item of this shard is skipped
+                running--;
+                if (threadIdx.x == 0) {
+                    sh_halted[j] = 1;
+                    __threadfence();
+                    st_release_u32(&gst.gen, 0xFFFFFFFFu);
+                    atomicAdd(&gs.stream_halted, 1);
+                }
             }
-        } else if (threadIdx.x == 0 && st.mini_slot < 0) {
-            d.bm_t[s * team + bps] = DBL_MAX;
-            d.bm_i[s * team + bps] = INT_MAX;
+            __syncthreads();
         }
-        __syncthreads();
-        halt = st.halt != 0;
     }
-    // halted (or gave up): every later item of this shard is skipped
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        st_release_u32(&gst.gen, 0xFFFFFFFFu);
-        atomicAdd(&gs.stream_halted, 1);
+    if (gave_up && threadIdx.x == 0) { // an error has been raised; let the pass blocks go
+        for (int j = 0; j < mine; ++j)
+            if (!sh_halted[j]) {
+                st_release_u32(&d.sh[blockIdx.x + j * E].gen, 0xFFFFFFFFu);
+                atomicAdd(&gs.stream_halted, 1);
+            }
     }
 }
 

@@ -305,15 +305,19 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
         d.table.za = g + N_PH_E + 1 + N_T + 1;
         ctx->table_dev = g + N_PH_E + 1 + N_T + 1;
     }
-    if ((e = cudaFuncSetAttribute(frame_stream_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_PASS_SMEM_PAD)) != cudaSuccess)
-        return bail(e, "cudaFuncSetAttribute");
-    // blocks of the two grids of the persistent stream share SMs: both ask for the same L1 / shared-memory split, or the
-    // SM would have to drain before it could take a block of the other kernel
-    if (!getenv("MCRAT_B200_STREAM_NOCARVE")) {
-        if ((e = cudaFuncSetAttribute(frame_stream_pass_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
-            return bail(e, "cudaFuncSetAttribute");
-        if ((e = cudaFuncSetAttribute(frame_stream_event_kernel<EVT_THREADS_MANY>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
-            return bail(e, "cudaFuncSetAttribute");
+    // The two grids of the persistent stream share SMs.  An SM runs with ONE split of its 256 KB between L1 and shared memory;
+    // blocks of a kernel that prefers another split wait until the SM has drained (measured: with different preferences the
+    // event blocks took 128 SMs for themselves and the pass ran on the remaining 20).  Both kernels therefore ask for the same
+    // small carve-out: 32 KB of shared memory covers 5 pass blocks + 1 event block, and the pass keeps its spills in L1.
+    {
+        int carve = 14; // per cent of 228 KB, rounded up by the driver to the 32 KB configuration
+        if (const char *c = getenv("MCRAT_B200_STREAM_CARVEOUT")) carve = atoi(c);
+        if (carve != -2) { // -2: leave the kernels' attributes alone (experiments)
+            if ((e = cudaFuncSetAttribute(frame_stream_pass_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess)
+                return bail(e, "cudaFuncSetAttribute");
+            if ((e = cudaFuncSetAttribute(frame_stream_event_kernel<EVT_THREADS_MANY>, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess)
+                return bail(e, "cudaFuncSetAttribute");
+        }
     }
     if ((e = cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(0))) != cudaSuccess)
         return bail(e, "cudaFuncSetAttribute");
@@ -402,17 +406,17 @@ static int grid_for(mcrat_b200_ctx *ctx, int n, int threads, int per_sm)
 API int mcrat_b200_set_hydro(mcrat_b200_ctx *ctx, int n, const double *const *fields, const double *domains, double fps,
                              int scatt_frame_number, int inj_frame_number)
 {
+    if (!ctx || !fields || !domains || n < 0) return ctx ? fail(ctx, MCRAT_B200_ERR_ARG, "set_hydro: bad argument") : MCRAT_B200_ERR_ARG;
     ctx->hydro_fps = fps;
     ctx->hydro_scatt_frame = scatt_frame_number;
     ctx->hydro_inj_frame = inj_frame_number;
-    if (!ctx || !fields || !domains || n < 0) return ctx ? fail(ctx, MCRAT_B200_ERR_ARG, "set_hydro: bad argument") : MCRAT_B200_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
-    CK(cudaStreamSynchronize(ctx->stream));
     CellCols &c = ctx->d.cells;
     const int ndim3 = ctx->d.dims == D_THREE;
     const int n_padded = n > 0 ? ((n + SCAN_TILE - 1) / SCAN_TILE) * SCAN_TILE : SCAN_TILE;
     // a frame with the same number of cells reuses the device arrays (one frame per step in the driver)
     if (!ctx->have_hydro || c.n != n) {
+        CK(cudaStreamSynchronize(ctx->stream)); // kernels of the previous frame may still read the arrays about to be freed
         free_pool(ctx->cell_allocs);
         double *cols[19];
         for (int f = 0; f < 19; ++f) CK(dev_alloc(ctx->cell_allocs, &cols[f], (size_t)n));
@@ -466,9 +470,10 @@ API int mcrat_b200_set_hydro(mcrat_b200_ctx *ctx, int n, const double *const *fi
         ctx->d.path_pad = 4e-16 * sqrt(r2sum);
         CK(cudaMemcpyAsync((void *)ctx->d.dom_dev, domains, 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         // thresholds refer to the cells of the previous frame
-        if (ctx->ph_cap_alloc > 0) CK(cudaMemsetAsync(ctx->d.ph.safe, 0, sizeof(unsigned long long) * (size_t)ctx->ph_cap_alloc, ctx->stream));
+        if (ctx->have_photons && ctx->d.cap > 0)
+            CK(cudaMemsetAsync(ctx->d.ph.safe, 0, sizeof(unsigned long long) * (size_t)ctx->d.cap, ctx->stream));
     }
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); // the caller may reuse its (possibly pinned) arrays when this returns
     ctx->have_hydro = true;
     return MCRAT_B200_OK;
 }
@@ -1316,55 +1321,88 @@ static void frame_loop_grid(const mcrat_b200_ctx *ctx, int &threads, int &bps, i
 // persistent loop for lists larger than L2 (frame_loop.cuh, PERSISTENT_STREAM): resident event blocks, one per sub-shard, on
 // the second stream; pass blocks pulling items on the first.  All sub-shards' event blocks must be resident next to the
 // pass blocks: one 128-thread block per SM beside four pass blocks.
+// Event blocks of the persistent stream.  Fewer blocks leave more SMs with room for a fifth pass block, but a block serves
+// its shards one after the other: m shards per block keep it busy for m x (one event incl. re-locations, ~50 us) of every
+// iteration, which must stay well below the iteration itself (~20 ps per photon of the list) or releases queue up and the
+// pass stream stalls (measured, 10^7 photons, 128 shards: 16 blocks 256 us, 32: 207, 64: 200, 128: 206 per iteration).
+static int frame_stream_evt_blocks(const mcrat_b200_ctx *ctx)
+{
+    const int S = ctx->d.nshards;
+    int m = ctx->d.cap / 5000000;
+    if (m < 1) m = 1;
+    if (m > STREAM_EVT_SHARDS) m = STREAM_EVT_SHARDS;
+    int E = (S + m - 1) / m;
+    if (const char *e = getenv("MCRAT_B200_STREAM_EVT_BLOCKS"))
+        if (atoi(e) > 0) E = atoi(e);
+    if (E > S) E = S;
+    if (E > ctx->num_sms) E = ctx->num_sms;
+    while ((S + E - 1) / E > STREAM_EVT_SHARDS) ++E;
+    return E;
+}
+
+// AUTO picks the persistent stream from this many sub-shards on: with few, long shards a pass item waits for its shard's event
+// more often than the missing launch boundaries save (10^7 photons, 16 shards: 272 us per iteration against 229 streamed)
+constexpr int STREAM_AUTO_MIN_SHARDS = 32;
+
 static bool frame_stream_fits(const mcrat_b200_ctx *ctx)
 {
-    return ctx->d.nshards >= 1 && ctx->d.nshards <= ctx->num_sms && !ctx->d.cs && !ctx->d.replay;
+    return ctx->d.nshards >= 1 && ctx->d.nshards <= ctx->num_sms * STREAM_EVT_SHARDS && !ctx->d.cs && !ctx->d.replay &&
+           frame_stream_evt_blocks(ctx) <= ctx->num_sms;
 }
 
 static int frame_stream_bps(const mcrat_b200_ctx *ctx)
 {
-    // about 16 photons per thread and item: the item's fixed cost (pull, wait, state, ticket: three round trips) stays below
-    // a fifth of its time, and a shard's items are spread over enough blocks to finish together
-    int bps = (ctx->d.shard_size + PASS_THREADS * 16 - 1) / (PASS_THREADS * 16);
-    if (const char *e = getenv("MCRAT_B200_STREAM_PPT")) {
-        const int ppt = atoi(e);
-        if (ppt > 0) bps = (ctx->d.shard_size + PASS_THREADS * ppt - 1) / (PASS_THREADS * ppt);
-    }
+    // about 32 photons per thread and item: the item's fixed cost (wait, state, ticket: a few round trips to L2) stays a small
+    // part of its time (measured at 10^7 photons, 128 shards: 8 per thread 218 us per iteration, 16: 207, 32: 201)
+    int ppt = 32;
+    if (const char *e = getenv("MCRAT_B200_STREAM_PPT"))
+        if (atoi(e) > 0) ppt = atoi(e);
+    int bps = (ctx->d.shard_size + PASS_THREADS * ppt - 1) / (PASS_THREADS * ppt);
     if (bps > BLOCKMIN_CAP / ctx->d.nshards - 1) bps = BLOCKMIN_CAP / ctx->d.nshards - 1;
     if (bps > EVT_THREADS_MANY - 1) bps = EVT_THREADS_MANY - 1; // the event block reads the minima with one load per thread
     if (bps < 1) bps = 1;
     return bps;
 }
 
+// Persistent loop for lists larger than L2 (frame_loop.cuh, PERSISTENT_STREAM): E resident event blocks on the second stream,
+// pass blocks pulling items on the first.  The pass grid is what fits beside them: 4 blocks on an SM that holds an event
+// block (48 K + 16 K registers), 5 elsewhere.  If the block scheduler places them differently some blocks simply start
+// late (items are pulled, not assigned); if the two grids do not meet at all the start-up handshake calls the launch off.
 static int launch_frame_stream(mcrat_b200_ctx *ctx)
 {
     const int S = ctx->d.nshards;
     const int bps = frame_stream_bps(ctx);
+    const int E = frame_stream_evt_blocks(ctx);
     if (getenv("MCRAT_B200_REFUSE_COOPERATIVE")) return MCRAT_B200_LOOP_FALLBACK;
     CK(cudaEventRecord(ctx->ev_join, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_join, 0));
     {
         Timed t(ctx, KC_EVENT);
-        frame_stream_event_kernel<EVT_THREADS_MANY><<<S, EVT_THREADS_MANY, 0, ctx->stream2>>>(ctx->d, bps);
+        int pad_evt = 0;
+        if (const char *e = getenv("MCRAT_B200_STREAM_PAD_EVT")) pad_evt = atoi(e);
+        frame_stream_event_kernel<EVT_THREADS_MANY><<<E, EVT_THREADS_MANY, pad_evt, ctx->stream2>>>(ctx->d, bps);
         if (int rc = check_launch(ctx, "frame_stream_event_kernel")) return rc;
         // test hook: what a profiler that serialises kernels does to the pair (the event blocks never meet the pass blocks)
         if (getenv("MCRAT_B200_STREAM_SERIALIZE")) CK(cudaStreamSynchronize(ctx->stream2));
     }
     {
-        // Whatever order the two grids reach the SMs in, every event block must find room: the pass blocks carry enough
-        // (unused) dynamic shared memory that at most STREAM_PASS_CTAS_PER_SM of them fit on an SM, which leaves the
-        // registers of one event block (128 threads x 128) free on every SM -- one slot per SM >= one per sub-shard.
         Timed t(ctx, KC_PASS);
-        const int grid = ctx->num_sms * STREAM_PASS_CTAS_PER_SM;
-        int pad = STREAM_PASS_SMEM_PAD;
-        if (const char *e = getenv("MCRAT_B200_STREAM_PAD")) pad = atoi(e); // experiments
-        frame_stream_pass_kernel<<<grid, PASS_THREADS, pad, ctx->stream>>>(ctx->d, bps, S);
+        int grid = E * STREAM_PASS_CTAS_PER_SM + (ctx->num_sms - E) * MCRAT_PASS_MINB;
+        if (const char *e = getenv("MCRAT_B200_STREAM_PASS_BLOCKS"))
+            if (atoi(e) > 0) grid = atoi(e);
+        int pad_pass = STREAM_PASS_SMEM_PAD;
+        if (const char *e = getenv("MCRAT_B200_STREAM_PAD_PASS")) pad_pass = atoi(e);
+        frame_stream_pass_kernel<<<grid, PASS_THREADS, pad_pass, ctx->stream>>>(ctx->d, bps, E);
         if (int rc = check_launch(ctx, "frame_stream_pass_kernel")) return rc;
     }
     CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     // did the two grids meet?  (a profiler that serialises kernels, a device shared with another tenant: they may not)
     if (int rc = fetch_global(ctx)) return rc;
+    if (getenv("MCRAT_B200_DEBUG"))
+        fprintf(stderr, "[mcrat_b200] persistent stream: S=%d E=%d bps=%d pass grid=%d -> event blocks seen %d, state %d, items pulled %llu, shards halted %d\n",
+                S, E, bps, E * STREAM_PASS_CTAS_PER_SM + (ctx->num_sms - E) * MCRAT_PASS_MINB, ctx->gs_host->stream_evt_ready,
+                ctx->gs_host->stream_state, ctx->gs_host->stream_work, ctx->gs_host->stream_halted);
     if (ctx->gs_host->stream_state == 2 /* STREAM_ABORT */) return MCRAT_B200_LOOP_FALLBACK;
     return MCRAT_B200_OK;
 }
@@ -1525,7 +1563,7 @@ API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remain
     // block fits on the device at once; else the interleaved streamed loop
     const bool pstream = fused && !ctx->cfg.profile && !persistent && frame_stream_fits(ctx) &&
                          (ctx->loop_mode == MCRAT_B200_LOOP_PERSISTENT_STREAM ||
-                          (ctx->loop_mode == MCRAT_B200_LOOP_AUTO && ctx->d.cap > PERSISTENT_MAX_PHOTONS));
+                          (ctx->loop_mode == MCRAT_B200_LOOP_AUTO && ctx->d.cap > PERSISTENT_MAX_PHOTONS && S >= STREAM_AUTO_MIN_SHARDS));
     if (pstream) persistent = true;
     long long streamed_done = 0; // iterations already launched when the persistent loop hands over for good
     if (persistent) {

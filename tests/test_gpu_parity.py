@@ -51,6 +51,46 @@ def test_frame_philox_parity(wl, refname, scale, nph, iters, scan_index):
     print(wl, "max rel errors", {k: "%.1e" % v for k, v in errs.items()})
 
 
+LARGE_CASES = [
+    # workload, grid scale (cells), photons, sub-shards, iterations per shard: tens of seconds of oracle time each
+    ("C2", 1.0 / 4, 24000, 4, 1500),     # 65 536 cells, 6 000 scatterings in all
+    ("C5", 1.0 / 2, 20000, 4, 1200),     # 131 072 cells, 3-D spherical
+    ("C3", 1.0 / 8, 12000, 3, 600),      # hot electrons + table, a third of the candidates rejected
+]
+
+
+@pytest.mark.parametrize("wl,scale,nph,shards,iters", LARGE_CASES)
+def test_longer_frames_on_larger_grids_hold_the_same_tolerances(wl, scale, nph, shards, iters):
+    """The per-field tolerances of tests/helpers.py were measured on 400-photon, 300-iteration frames.  Here: tens of
+    thousands of photons, thousands of scatterings per rank, every sub-shard against its own oracle rank -- errors do
+    not accumulate beyond them (a photon's error is reset by nothing, but each scattering re-derives its momenta from
+    freshly drawn angles, and positions are sums of exact pushes)."""
+    cfg, hydro, photons, frame = synth.workload(wl, scale=scale, n_photons=nph, seed=97)
+    hp = HotPath(cfg, seed=4711, shard=20, num_shards=shards, scan_index=True)
+    hp.set_hydro(hydro)
+    table = None
+    if wl == "C3":
+        table, _ = hp.build_thermal_table(calls=20000, seed=3)
+    hp.set_photons(photons)
+    st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=iters, switch=1)
+    got = hp.get_photons()
+    total = 0
+    for s in range(hp.num_shards()):
+        ss = hp.shard_stats(s)
+        sl = slice(ss["first_slot"], ss["first_slot"] + ss["num_slots"])
+        o = api.Oracle(cfg)
+        o.set_hydro(hydro)
+        if table is not None:
+            o.set_table(table)
+        o.set_photons(photons[sl])
+        ost = o.run_frame(api.OracleRng("philox", seed=4711, shard=20 + s), frame["time_now"], 1.0 / frame["fps"],
+                          max_iters=iters, switch=1)
+        assert ss["iterations"] == ost["iterations"] and ss["scatterings"] == ost["scatterings"], (s, ss, ost)
+        compare_photons(got[sl], o.photons(), label="%s large shard %d" % (wl, s), hydro=hydro)
+        total += ost["scatterings"]
+    assert st["scatterings"] == total and total > 0.5 * shards * iters
+
+
 @pytest.mark.parametrize("wl,refname,scale,nph,iters", CASES)
 def test_frame_replay_parity(wl, refname, scale, nph, iters):
     """Replay harness: the uniform stream the reference consumed, fed to the GPU in reference order."""
