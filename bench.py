@@ -323,7 +323,9 @@ def main():
                                   "GPU g of N owns ranks rank_slice(%d, g, N) and their photons -- same job, same photons for every N" % job["ranks"]),
               "step": "full photon x cell rescan of the GPU's photons (new hydro frame) + loop iterations in every rank; steps continue one simulation",
               "l2": "photon list and cell arrays exceed L2 at N <= 4 (1e7 x 100 B per pass); additionally flushed between timed steps (256 MiB write)",
-              "loop": args.loop + " (auto: persistent frame_loop_kernel while a GPU's list fits in L2 (<= 2^21 photons), streamed loop above)",
+              "loop": args.loop + " (auto: one cooperative launch per frame while a GPU's list fits in L2 (<= 2^21 photons); from 4e6 "
+                      "photons and 32 ranks per GPU on, a pair of co-resident grids per frame (resident event blocks beside pass "
+                      "blocks streaming the photon columns); two launches per iteration and half of the ranks otherwise)",
               "relocation": "bounding-box index over the cells in array order (K1c, identical first-match results)"
               if args.index else "full photon x cell scan of every new hydro frame (K1), as the reference does; "
               "steady-state re-locations inside the loop go through the bounding-box index"}
@@ -491,12 +493,12 @@ def main():
                                "(%d launches per iteration of the %d-photon list)" % (pass_photons, round(photons.size / max(pass_photons, 1)), photons.size),
                      "bound": "hbm", "achieved": pass_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": pass_gbs / hbm_peak if pass_gbs else None,
-                     "traffic": (json.load(open(tpath)).get("pass_kernel_1e7_bytes") if os.path.exists(tpath) and photons.size == 10_000_000 else None),
+                     "traffic": (json.load(open(tpath)).get("pass_local_kernel_C5_%d_bytes" % round(pass_photons)) if os.path.exists(tpath) else None),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
                      "algorithmic": "100 B per photon-iteration (SURVEY 8d) x %d photons per launch; columns actually moved: 97 B" % pass_photons,
                      "ms_per_launch": pass_ms, "event_kernel_ms_per_launch": event_ms,
                      "note": "meaningful while the list exceeds L2 (> 2^21 photons per GPU); below that the pass runs out of L2"}
-    loop_roofline = {"kernel": "whole loop iteration (pass + re-locate + finish + event) over %d photons" % photons.size,
+    loop_roofline = {"kernel": "whole loop iteration (pass over %d photons + one scattering event per rank, as the loop driver in use overlaps them)" % photons.size,
                      "bound": "hbm", "achieved": loop_slots_per_s * BYTES_PER_PHOTON_ITERATION / 1e9, "peak": hbm_peak, "unit": "GB/s",
                      "frac": loop_slots_per_s * BYTES_PER_PHOTON_ITERATION / 1e9 / hbm_peak, "us_per_iteration": loop_us}
 

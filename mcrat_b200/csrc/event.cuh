@@ -64,7 +64,46 @@ struct EarlyRelease {
     int n_dt, ph_index;
     double scatt_time;
     int released;       // out: the state has been published
+    // cluster team (frame_loop_cluster_kernel): the state is pushed into the pass blocks' shared memory and their
+    // generation barriers are arrived on remotely; 0 pass blocks = not a cluster team
+    int cl_bps;
+    uint32_t cl_st_addr, cl_bar_addr; // shared-space addresses of `st` and the generation mbarrier (the same in every block)
+    int mini_reloc;     // out: the mini-pass put its photon on the shard's relocation list
 };
+
+// distributed shared memory of a thread-block cluster
+__device__ __forceinline__ uint32_t cluster_map(uint32_t smem_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_st_u64(uint32_t addr, unsigned long long v)
+{
+    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_st_u32(uint32_t addr, unsigned v)
+{
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_mbar_arrive(uint32_t bar_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+
+// one warp: the shard state into the shared memory of pass blocks 0 .. bps-1 of this cluster, then an arrival on each one's
+// generation barrier (release at cluster scope: the pushes are visible to whoever wakes up on it)
+__device__ __forceinline__ void cluster_publish_warp(const ShardState &st, const int bps, const uint32_t st_addr, const uint32_t bar_addr,
+                                                     const int lane)
+{
+    for (int b = 0; b < bps; ++b)
+        for (int k = lane; k < SHARD_STATE_WORDS; k += 32)
+            cluster_st_u64(cluster_map(st_addr + 8u * (uint32_t)k, (uint32_t)b), reinterpret_cast<const unsigned long long *>(&st)[k]);
+    __syncwarp();
+    __threadfence(); // the event block's global writes (scattered photon, relocation list) before the wake-up
+    if (lane < bps) cluster_mbar_arrive(cluster_map(bar_addr, (uint32_t)lane));
+    __syncwarp();
+}
 
 // the driver's bookkeeping after photonEvent returned (Src/mcrat.c:783-787, 834-846), without the cyclo-synchrotron part
 __device__ __forceinline__ void event_bookkeeping(ShardState &st, int n_dt, int ph_index, double scatt_time, int step_mode)
@@ -324,7 +363,10 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
         for (int k = lane; k < SHARD_STATE_WORDS; k += 32)
             reinterpret_cast<unsigned long long *>(early.gst)[k] = reinterpret_cast<const unsigned long long *>(&st)[k];
         __syncwarp();
-        if (lane == 0) {
+        if (early.cl_bps > 0) {
+            cluster_publish_warp(st, early.cl_bps, early.cl_st_addr, early.cl_bar_addr, lane);
+            if (lane == 0) early.released = 1;
+        } else if (lane == 0) {
             __threadfence();
             st_release_u32(&early.gst->gen, early.gen_value);
             early.released = 1;
@@ -458,6 +500,7 @@ __device__ void scatter_candidate_3w(DevCtx &d, ShardState &st, EventRng &rng_sh
                 bt = t_next;
                 bi = i;
             } else if (state == 2) {
+                early.mini_reloc = 1;
                 const int pos = st.first + atomicAdd(&early.gst->reloc_n, 1);
                 d.reloc_slot[pos] = i;
                 d.reloc_h0[pos] = h0;
@@ -584,7 +627,8 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
                                            int step_mode, double dt_max_arg, ShardState &st, ShardState *early_gst = nullptr,
                                            unsigned early_gen = 0, int early_bm = 0, const bool have_pre = false,
                                            const double pre_t = DBL_MAX, const int pre_i = INT_MAX, const int pre_idx = -2,
-                                           const double pre_temp = 0)
+                                           const double pre_temp = 0, const int cl_bps = 0, const uint32_t cl_st_addr = 0,
+                                           const uint32_t cl_bar_addr = 0, int *mini_reloc_out = nullptr)
 {
     GlobalState &gs = *d.gs;
     __shared__ EarlyRelease early;
@@ -666,6 +710,10 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
         st.pushed_slot = -1;
         early.enabled = 0;
         early.released = 0;
+        early.cl_bps = cl_bps;
+        early.cl_st_addr = cl_st_addr;
+        early.cl_bar_addr = cl_bar_addr;
+        early.mini_reloc = 0;
         early.gst = early_gst;
         early.gen_value = early_gen;
         early.bm_index = early_bm;
@@ -894,6 +942,7 @@ __device__ __forceinline__ bool event_body(DevCtx &d, const int s, const int rel
         st.last_event_draw = rng_sh.draw;
     }
     __syncthreads();
+    if (mini_reloc_out && threadIdx.x == 0) *mini_reloc_out = early.mini_reloc;
     return early.released != 0;
 }
 

@@ -210,6 +210,199 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
 }
 
 // ------------------------------------------------------------------------------------------
+// The same team as ONE THREAD-BLOCK CLUSTER (round 2): bps pass blocks (cluster ranks 0 .. bps-1) + the event block (rank
+// bps), at most 16 blocks.  The protocol is frame_loop_kernel's, but its three hand-overs no longer go through L2:
+//   pass block -> event block   the block's minimum (time, slot, cell, temperature, "some photon left its cell") is stored
+//                               into the event block's shared memory (st.shared::cluster) and the block arrives on the event
+//                               block's mbarrier (mbarrier.arrive.release.cluster on the remote address) -- instead of four
+//                               global stores, a fence and an atomicAdd that the event block polls through L2;
+//   event block -> pass blocks  on the early release the helper warp pushes the new shard state into every pass block's
+//                               shared memory and arrives on each one's generation mbarrier -- instead of a global copy the
+//                               pass blocks poll for and then read back;
+//   waiting                     mbarrier.try_wait on the block's OWN shared memory (acquire at cluster scope).
+// Photon data still travels through global memory; __threadfence() on the producing side before the arrival and the acquire
+// on the waiting side order it, as before.  A cluster needs no cooperative launch (its blocks are co-scheduled by
+// definition), clusters never talk to each other, and a team that cannot get a cluster (bps + 1 > 16 is clamped; a device
+// without free cluster slots) runs frame_loop_kernel instead.
+// ------------------------------------------------------------------------------------------
+constexpr int CLUSTER_TEAM_MAX = 16;
+
+struct TeamMail { // one per pass block, in the event block's shared memory; written remotely
+    double t, temp;
+    int i, idx;
+    int reloc, pad;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// thread 0 of a block: wait for phase `parity` of its own barrier; false after ~1 s (never in a healthy run)
+__device__ __forceinline__ bool mbar_wait_cluster(GlobalState &gs, uint64_t *bar, uint32_t parity, unsigned limit)
+{
+    unsigned spins = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (++spins > limit) {
+            raise_error(&gs, MCRAT_B200_ERR_STATE, -1, ERR_SITE_LOOP_SPIN);
+            return false;
+        }
+        if ((spins & 4095u) == 0 && *(volatile int *)&gs.error != 0) return false;
+    }
+    return true;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 2) frame_loop_cluster_kernel(DevCtx d, const int bps)
+{
+    __shared__ ShardState st;  // pass blocks: written remotely by the event block at every release
+    __shared__ int sh_flag, sh_reloc;
+    __shared__ __align__(8) uint64_t bar_gen; // pass blocks: one arrival (the event block's) per iteration
+    __shared__ __align__(8) uint64_t bar_arr; // event block: bps arrivals per iteration
+    __shared__ TeamMail mail[CLUSTER_TEAM_MAX];
+    GlobalState &gs = *d.gs;
+    const int team = bps + 1;
+    const int groups = gridDim.x / team;
+    const int g = blockIdx.x / team;
+    const int role = (int)cluster_ctarank();
+    const bool is_event_block = (role == bps);
+    const unsigned limit = d.tau_calc == TAU_TABLE ? (1u << 30) : (1u << 26); // try_wait suspends for a while by itself
+    uint32_t ph_gen = 0, ph_arr = 0; // phases completed of this block's own barriers
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_gen, 1);
+        mbar_init(&bar_arr, bps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster_sync_all();
+    const uint32_t st_addr = smem_u32(&st), gen_addr = smem_u32(&bar_gen);
+    const uint32_t arr_remote = cluster_map(smem_u32(&bar_arr), (uint32_t)bps);
+
+    for (int s = g; s < d.nshards; s += groups) {
+        ShardState &gst = d.sh[s];
+        __syncthreads();
+        if (threadIdx.x < SHARD_STATE_WORDS)
+            reinterpret_cast<unsigned long long *>(&st)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&gst)[threadIdx.x];
+        __syncthreads();
+        // stop test at entry: shard state only, so that all blocks of the team decide alike
+        bool halt = st.done | st.pause_cs | (gs.max_iters >= 0 && st.iters_done >= gs.max_iters);
+        if (!is_event_block) {
+            // ---------------- pass block ----------------
+            const int b = role;
+            const uint32_t mail_remote = cluster_map(smem_u32(&mail[b]), (uint32_t)bps);
+            while (!halt) {
+                if (threadIdx.x == 0) sh_reloc = 0;
+                __syncthreads();
+                double best_t = DBL_MAX;
+                int best_i = INT_MAX;
+                pass_body<true, true, THREADS>(d, st, s, b, bps, 0, 0, best_t, best_i, &sh_reloc);
+                block_argmin<THREADS>(best_t, best_i);
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    int bidx = -1;
+                    double btemp = 0;
+                    if (best_i != INT_MAX) {
+                        bidx = d.ph.idx[best_i];
+                        if (bidx >= 0) btemp = d.cells.temp[bidx];
+                    }
+                    __threadfence(); // this block's photon columns and relocation entries before the arrival
+                    cluster_st_u64(mail_remote, (unsigned long long)__double_as_longlong(best_t));
+                    cluster_st_u64(mail_remote + 8, (unsigned long long)__double_as_longlong(btemp));
+                    cluster_st_u64(mail_remote + 16, ((unsigned long long)(unsigned)bidx << 32) | (unsigned long long)(unsigned)best_i);
+                    cluster_st_u32(mail_remote + 24, (unsigned)sh_reloc);
+                    cluster_mbar_arrive(arr_remote);
+                    sh_flag = mbar_wait_cluster(gs, &bar_gen, ph_gen & 1u, limit) ? 1 : 0; // the new state is in `st`
+                }
+                ++ph_gen;
+                __syncthreads();
+                if (!sh_flag) break;
+                halt = st.halt != 0;
+            }
+        } else {
+            // ---------------- event block ----------------
+            if (threadIdx.x == 0) {
+                d.bm_t[s * team + bps] = DBL_MAX; // the mini-pass slot stays in global memory (written and read by this block)
+                d.bm_i[s * team + bps] = INT_MAX;
+                st.mini_slot = -1;
+                sh_reloc = 0;
+            }
+            __syncthreads();
+            unsigned k = 0;
+            while (!halt) {
+                // this block's own mini-pass result of the last event, requested before the wait
+                double pre_t = DBL_MAX, pre_temp = 0;
+                int pre_i = INT_MAX, pre_idx = -2;
+                if ((int)threadIdx.x == bps) {
+                    pre_t = *(volatile double *)&d.bm_t[s * team + bps];
+                    pre_i = *(volatile int *)&d.bm_i[s * team + bps];
+                    pre_idx = *(volatile int *)&d.bm_idx[s * team + bps];
+                    pre_temp = *(volatile double *)&d.bm_temp[s * team + bps];
+                }
+                if (threadIdx.x == 0) sh_flag = mbar_wait_cluster(gs, &bar_arr, ph_arr & 1u, limit) ? 1 : 0;
+                ++ph_arr;
+                __syncthreads();
+                if (!sh_flag) break;
+                ++k;
+                int any_reloc = sh_reloc; // the last mini-pass
+                if ((int)threadIdx.x < bps) {
+                    const volatile TeamMail &m = mail[threadIdx.x];
+                    pre_t = m.t;
+                    pre_i = m.i;
+                    pre_idx = m.idx;
+                    pre_temp = m.temp;
+                    any_reloc |= m.reloc;
+                }
+                any_reloc = __syncthreads_or(any_reloc);
+                int R = 0;
+                if (any_reloc) {
+                    R = *(volatile int *)&gst.reloc_n;
+                    if (R > 0) relocate_shard<THREADS>(d, st, s, R);
+                }
+                const bool released = event_body<THREADS>(d, s, st.first, R, team, 0, 0.0, st, &gst, k, s * team + bps, true, pre_t,
+                                                          pre_i, pre_idx, pre_temp, bps, st_addr, gen_addr, &sh_reloc);
+                if (!released) {
+                    // frame end, Klein-Nishina walk exhausted, cyclo-synchrotron run: publish now
+                    if (threadIdx.x == 0) {
+                        st.halt = (loop_stopped(gs, st) || st.reloc_heavy) ? 1 : 0;
+                        st.mini_slot = -1;
+                        d.bm_t[s * team + bps] = DBL_MAX;
+                        d.bm_i[s * team + bps] = INT_MAX;
+                    }
+                    __syncthreads();
+                    if (threadIdx.x < SHARD_STATE_WORDS)
+                        reinterpret_cast<unsigned long long *>(&gst)[threadIdx.x] = reinterpret_cast<const unsigned long long *>(&st)[threadIdx.x];
+                    __syncthreads();
+                    if (threadIdx.x < 32) cluster_publish_warp(st, bps, st_addr, gen_addr, (int)threadIdx.x);
+                } else if (threadIdx.x == 0 && st.mini_slot < 0) {
+                    d.bm_t[s * team + bps] = DBL_MAX; // released with a halt: no mini-pass ran
+                    d.bm_i[s * team + bps] = INT_MAX;
+                }
+                __syncthreads();
+                halt = st.halt != 0;
+            }
+            // the state proper is current in global memory (written with every release)
+        }
+    }
+    cluster_sync_all(); // nobody leaves while its shared memory may still be written remotely
+}
+
+// ------------------------------------------------------------------------------------------
 // Persistent loop for lists LARGER than L2 (PERSISTENT_STREAM): the same team protocol -- tickets on gst.arrive, early
 // release on gst.gen, mini-pass by the event block -- but the pass blocks are not tied to a shard.  Two kernels run
 // side by side (the pass needs 48 registers and 40 warps per SM to keep HBM busy, the event 128 registers and three

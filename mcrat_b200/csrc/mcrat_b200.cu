@@ -79,6 +79,7 @@ struct mcrat_b200_ctx {
     double cs_rebin_e_perc, cs_rebin_ang, cs_rebin_ang_phi; // CYCLOSYNCHROTRON_REBIN_E_PERC / _ANG / _ANG_PHI, Src/mcrat.h:308-322
     int occ_scan[2];              // resident CTAs per SM of scan_kernel<0> / <1>
     int occ_loop256, occ_loop128; // resident blocks per SM of frame_loop_kernel<256>, frame_loop_solo_kernel<256> / <128>
+    int cluster_state;            // 0 untried, 1 the cluster team kernel launches on this device, -1 it does not (cooperative team instead)
     long long launches; // kernels launched through this context
     double hydro_fps;   // of the frame last uploaded (calcCyclosynchRLimits, Src/mc_cyclosynch.c:1206-1207)
     int hydro_scatt_frame, hydro_inj_frame;
@@ -225,6 +226,7 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
     ctx->replay_dev = nullptr;
     ctx->replay_cap = 0;
     ctx->table_dev = nullptr;
+    ctx->cluster_state = getenv("MCRAT_B200_NO_CLUSTER") ? -1 : 0;
     ctx->stat_dev = nullptr;
     ctx->gs_host = nullptr;
     auto bail = [&](cudaError_t err, const char *what) {
@@ -304,6 +306,10 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
         d.table.ya = g + N_PH_E + 1;
         d.table.za = g + N_PH_E + 1 + N_T + 1;
         ctx->table_dev = g + N_PH_E + 1 + N_T + 1;
+    }
+    if ((e = cudaFuncSetAttribute(frame_loop_cluster_kernel<256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        ctx->cluster_state = -1; // no 16-block clusters here: the cooperative team kernel does the job
     }
     // The two grids of the persistent stream share SMs.  An SM runs with ONE split of its 256 KB between L1 and shared memory;
     // blocks of a kernel that prefers another split wait until the SM has drained (measured: with different preferences the
@@ -1322,15 +1328,13 @@ static void frame_loop_grid(const mcrat_b200_ctx *ctx, int &threads, int &bps, i
 // the second stream; pass blocks pulling items on the first.  All sub-shards' event blocks must be resident next to the
 // pass blocks: one 128-thread block per SM beside four pass blocks.
 // Event blocks of the persistent stream.  Fewer blocks leave more SMs with room for a fifth pass block, but a block serves
-// its shards one after the other: m shards per block keep it busy for m x (one event incl. re-locations, ~50 us) of every
-// iteration, which must stay well below the iteration itself (~20 ps per photon of the list) or releases queue up and the
-// pass stream stalls (measured, 10^7 photons, 128 shards: 16 blocks 256 us, 32: 207, 64: 200, 128: 206 per iteration).
+// its shards one after the other, and releases that queue up stall the pass stream.  Two shards per block is the measured
+// optimum (10^7 photons, 128 shards: 16 blocks 256 us per iteration, 32: 207, 43: 199, 64: 198, 128: 206; 5 x 10^6 photons,
+// 64 shards: 32 blocks 108 us, 64: 115).
 static int frame_stream_evt_blocks(const mcrat_b200_ctx *ctx)
 {
     const int S = ctx->d.nshards;
-    int m = ctx->d.cap / 5000000;
-    if (m < 1) m = 1;
-    if (m > STREAM_EVT_SHARDS) m = STREAM_EVT_SHARDS;
+    int m = 2;
     int E = (S + m - 1) / m;
     if (const char *e = getenv("MCRAT_B200_STREAM_EVT_BLOCKS"))
         if (atoi(e) > 0) E = atoi(e);
@@ -1340,9 +1344,11 @@ static int frame_stream_evt_blocks(const mcrat_b200_ctx *ctx)
     return E;
 }
 
-// AUTO picks the persistent stream from this many sub-shards on: with few, long shards a pass item waits for its shard's event
-// more often than the missing launch boundaries save (10^7 photons, 16 shards: 272 us per iteration against 229 streamed)
+// AUTO picks the persistent stream from this many sub-shards and photons on: with few, long shards a pass item waits for its
+// shard's event more often than the missing launch boundaries save (10^7 photons, 16 shards: 272 us per iteration against
+// 229 streamed), and a short list leaves the interleaved loop little to lose (2.5 x 10^6 photons, 32 shards: 93 against 87)
 constexpr int STREAM_AUTO_MIN_SHARDS = 32;
+constexpr int STREAM_AUTO_MIN_PHOTONS = 4000000;
 
 static bool frame_stream_fits(const mcrat_b200_ctx *ctx)
 {
@@ -1407,6 +1413,49 @@ static int launch_frame_stream(mcrat_b200_ctx *ctx)
     return MCRAT_B200_OK;
 }
 
+// The team of a sub-shard as one thread-block cluster (frame_loop_cluster_kernel): the largest team of at most 16 blocks for
+// which every sub-shard's cluster is resident at once.  Returns MCRAT_B200_OK after a launch, MCRAT_B200_LOOP_FALLBACK when the
+// cooperative team kernel should run instead (no such team, clusters unavailable).
+static int launch_frame_cluster(mcrat_b200_ctx *ctx, int bps_wanted)
+{
+    const int S = ctx->d.nshards;
+    if (ctx->cluster_state < 0) return MCRAT_B200_LOOP_FALLBACK;
+    int bps = bps_wanted < CLUSTER_TEAM_MAX - 1 ? bps_wanted : CLUSTER_TEAM_MAX - 1;
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(256);
+    cfg.stream = ctx->stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    for (; bps >= 2; --bps) {
+        const int team = bps + 1;
+        attr[0].val.clusterDim.x = team;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3(S * team);
+        int nclusters = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, frame_loop_cluster_kernel<256>, &cfg);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            ctx->cluster_state = -1;
+            return MCRAT_B200_LOOP_FALLBACK;
+        }
+        if (nclusters >= S) break;
+    }
+    if (bps < 2) return MCRAT_B200_LOOP_FALLBACK; // too many sub-shards for resident clusters
+    Timed t(ctx, KC_EVENT);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, frame_loop_cluster_kernel<256>, ctx->d, bps);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        ctx->cluster_state = -1;
+        return MCRAT_B200_LOOP_FALLBACK;
+    }
+    ctx->cluster_state = 1;
+    return check_launch(ctx, "frame_loop_cluster_kernel");
+}
+
 static int launch_frame_loop(mcrat_b200_ctx *ctx, bool stream = false)
 {
     if (stream) return launch_frame_stream(ctx);
@@ -1415,6 +1464,10 @@ static int launch_frame_loop(mcrat_b200_ctx *ctx, bool stream = false)
     if (grid < 1) return fail(ctx, MCRAT_B200_ERR_STATE, "frame_loop_kernel does not fit on this device");
     void *args[2] = {(void *)&ctx->d, (void *)&bps};
     if (getenv("MCRAT_B200_REFUSE_COOPERATIVE")) return MCRAT_B200_LOOP_FALLBACK; // test hook for the hand-over below
+    if (bps >= 2) {
+        const int rc = launch_frame_cluster(ctx, bps);
+        if (rc != MCRAT_B200_LOOP_FALLBACK) return rc;
+    }
     Timed t(ctx, KC_EVENT);
     cudaError_t e;
     if (bps == 0) { // independent blocks: an ordinary launch
@@ -1563,7 +1616,7 @@ API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remain
     // block fits on the device at once; else the interleaved streamed loop
     const bool pstream = fused && !ctx->cfg.profile && !persistent && frame_stream_fits(ctx) &&
                          (ctx->loop_mode == MCRAT_B200_LOOP_PERSISTENT_STREAM ||
-                          (ctx->loop_mode == MCRAT_B200_LOOP_AUTO && ctx->d.cap > PERSISTENT_MAX_PHOTONS && S >= STREAM_AUTO_MIN_SHARDS));
+                          (ctx->loop_mode == MCRAT_B200_LOOP_AUTO && ctx->d.cap >= STREAM_AUTO_MIN_PHOTONS && S >= STREAM_AUTO_MIN_SHARDS));
     if (pstream) persistent = true;
     long long streamed_done = 0; // iterations already launched when the persistent loop hands over for good
     if (persistent) {

@@ -350,7 +350,7 @@ constexpr int PASS_THREADS = MCRAT_PASS_THREADS;
 // list (persistent loop: shards advance independently of each other).
 template <bool FUSE_MFP, bool LOCAL_RELOC, int THREADS>
 __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const int s, const int b, const int nblk,
-                                          const int sw, const int parity, double &best_t, int &best_i)
+                                          const int sw, const int parity, double &best_t, int &best_i, int *reloc_flag = nullptr)
 {
     const int n_dt = sh.n_dt;
     const int pushed = sh.pushed_slot;
@@ -431,6 +431,7 @@ __device__ __forceinline__ void pass_body(DevCtx &d, const ShardState &sh, const
                 }
                 if (sw == 1 || !inb) {
                     int pos = LOCAL_RELOC ? first + atomicAdd(&d.sh[s].reloc_n, 1) : atomicAdd(&d.gs->reloc_count[parity], 1);
+                    if (LOCAL_RELOC && reloc_flag) *reloc_flag = 1; // cluster team: tells the event block to look at the list
                     d.reloc_slot[pos] = i;
                     d.reloc_h0[pos] = h0;
                     d.reloc_h1[pos] = h1;

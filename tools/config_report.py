@@ -33,10 +33,15 @@ CASES = [
     ("C5, 1e6 photons", "C5", 1_000_000, 16, True, iters),
     ("C5, 3e6 photons (streamed loop)", "C5", 3_000_000, 16, True, max(iters // 10, 100)),
     ("C5, 1e7 photons (streamed loop)", "C5", 10_000_000, 16, True, max(iters // 10, 100)),
+    ("C5, 1e7 photons, 128 ranks (bench default; persistent stream)", "C5", 10_000_000, 128, True, max(iters // 10, 100)),
+    ("C5, 5e6 photons, 64 ranks (one of 2 GPUs)", "C5", 5_000_000, 64, True, max(iters // 10, 100)),
+    ("C5, 2.5e6 photons, 32 ranks (one of 4 GPUs)", "C5", 2_500_000, 32, True, max(iters // 10, 100)),
+    ("C5, 1.25e6 photons, 16 ranks (one of 8 GPUs)", "C5", 1_250_000, 16, True, iters),
     ("C5, 1e7 photons, 1 rank", "C5", 10_000_000, 1, True, max(iters // 10, 100)),
 ]
 
 fp64 = None
+hw = 148 * 64 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e9  # hardware FP64 issue peak, G thread-instr/s
 rows = []
 for label, wl, nph, shards, index, n_it in CASES:
     cfg, hydro, photons, frame = synth.workload(wl, n_photons=nph, seed=5)
@@ -72,12 +77,13 @@ for label, wl, nph, shards, index, n_it in CASES:
     instr = 6 if cfg["dimensions"] == synth.THREE else 4
     e_scan = ev / (ms * 1e-3) if ms > 0 else 0.0
     e_mfp = st2["photon_slots"] / dt
-    rows.append((label, ms, e_scan, (e_scan * instr / 1e9 / fp64) if ms > 0 else None, 1e6 * dt / max(st2["iterations"], 1),
+    rows.append((label, ms, e_scan, (e_scan * instr / 1e9 / hw) if ms > 0 else None, 1e6 * dt / max(st2["iterations"], 1),
                  e_mfp, e_mfp * 100.0 / 1e9 / hbm, st2["scatterings"] / dt, st2["relocations"], hp.launch_count(), t_table))
     hp.close()
 
-print("FP64 issue rate measured on this GPU: %.0f G instr/s; HBM copy rate (MEASURED_PEAKS.json): %.1f GB/s\n" % (fp64, hbm))
-print("| config | K1 rescan (ms) | E_scan (evals/s) | of FP64 issue rate | loop (us / iteration) | E_mfp (photon-iterations/s) | "
+print("FP64 pipe: hardware issue peak 148 SMs x 64 lanes x %.0f MHz = %.0f G instr/s (the 'of FP64 peak' column); DFMA probe on this GPU: "
+      "%.0f G instr/s; HBM copy rate (MEASURED_PEAKS.json): %.1f GB/s\n" % (peaks.get("sm_max_mhz", 1965.0), hw, fp64, hbm))
+print("| config | K1 rescan (ms) | E_scan (evals/s) | of FP64 peak | loop (us / iteration) | E_mfp (photon-iterations/s) | "
       "x 100 B of HBM | S (scatterings/s) | re-locations | launches |")
 print("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
 for r in rows:
