@@ -224,6 +224,12 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 4) frame_loop_ke
 // on the waiting side order it, as before.  A cluster needs no cooperative launch (its blocks are co-scheduled by
 // definition), clusters never talk to each other, and a team that cannot get a cluster (bps + 1 > 16 is clamped; a device
 // without free cluster slots) runs frame_loop_kernel instead.
+// MEASURED (tools/gpu_o.sh, gpurun_out/ab_o.log -> profiles/ncu_r02_summary.md): photons bit-identical to the cooperative team
+// kernel's on every workload, iteration time NOT better -- C2 16 ranks 21.5 against 20.8 us, C1 20.5 / 19.3, C5 24.4 / 23.8,
+// C3 33.8 / 33.9, C2 64 ranks 23.1 / 24.2, C5 10^6 photons 47.0 / 40.0 (15 instead of 17 pass blocks per rank).  The six to
+// seven microseconds between two scatterings of a rank are not signalling latency: they are the pass itself (one dependent
+// L2 round trip for the photon columns, the draw, the stores) and the event's first loads.  The kernel therefore runs only
+// on request (MCRAT_B200_CLUSTER_TEAM=1); the cooperative team kernel stays the default.
 // ------------------------------------------------------------------------------------------
 constexpr int CLUSTER_TEAM_MAX = 16;
 

@@ -226,7 +226,9 @@ API int mcrat_b200_create(const mcrat_b200_config *cfg, mcrat_b200_ctx **out)
     ctx->replay_dev = nullptr;
     ctx->replay_cap = 0;
     ctx->table_dev = nullptr;
-    ctx->cluster_state = getenv("MCRAT_B200_NO_CLUSTER") ? -1 : 0;
+    // the cluster team kernel is correct (bit-identical photons) but no faster than the cooperative one (profiles/ncu_r02_summary.md):
+    // it runs only on request
+    ctx->cluster_state = getenv("MCRAT_B200_CLUSTER_TEAM") ? 0 : -1;
     ctx->stat_dev = nullptr;
     ctx->gs_host = nullptr;
     auto bail = [&](cudaError_t err, const char *what) {

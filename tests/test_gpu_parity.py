@@ -331,6 +331,32 @@ def test_warp_wide_maxwell_juttner_sampling_equals_the_sequential_loop(monkeypat
             assert np.array_equal(out[None][0][f], out[r][0][f], equal_nan=out[None][0].dtype[f].kind == "f"), (r, f)
 
 
+@pytest.mark.parametrize("wl,scale,nph,shards,iters", [("C2", 1.0 / 16, 6000, 6, 200), ("C5", 1.0 / 8, 8000, 16, 120),
+                                                     ("C3", 1.0 / 8, 6000, 2, 120)])
+def test_cluster_team_kernel_equals_the_cooperative_one(monkeypatch, wl, scale, nph, shards, iters):
+    """The team of a sub-shard as one thread-block cluster (minima and state through distributed shared memory, remote
+    mbarrier arrivals; MCRAT_B200_CLUSTER_TEAM=1) against the default cooperative team kernel: same photons, same counters."""
+    cfg, hydro, photons, frame = synth.workload(wl, scale=scale, n_photons=nph, seed=61)
+    out = {}
+    for cluster in (False, True):
+        if cluster:
+            monkeypatch.setenv("MCRAT_B200_CLUSTER_TEAM", "1")
+        hp = HotPath(cfg, seed=8, shard=1, num_shards=shards, loop_mode="persistent")
+        hp.set_hydro(hydro)
+        if wl == "C3":
+            hp.build_thermal_table(calls=20000, seed=3)
+        hp.set_photons(photons)
+        st = hp.run_frame(frame["time_now"], 1.0 / frame["fps"], max_iters=iters, switch=1)
+        st2 = hp.run_frame(st["time_now"], 1.0 / frame["fps"], max_iters=iters // 2, switch=0)
+        out[cluster] = (st, st2, hp.get_photons())
+        hp.close()
+        monkeypatch.delenv("MCRAT_B200_CLUSTER_TEAM", raising=False)
+    for k in ("iterations", "scatterings", "relocations", "photon_slots", "time_now"):
+        assert out[False][0][k] == out[True][0][k] and out[False][1][k] == out[True][1][k], k
+    for f in out[False][2].dtype.names:
+        assert np.array_equal(out[False][2][f], out[True][2][f], equal_nan=(out[False][2].dtype[f].kind == "f")), f
+
+
 def test_persistent_stream_pair_is_called_off_when_its_grids_cannot_meet(monkeypatch):
     """The loop of lists larger than L2 runs as two co-resident grids.  Where they cannot be co-resident (ncu serialises
     kernels; a device shared with another tenant) the start-up handshake calls the launch off before a photon is touched
