@@ -483,9 +483,10 @@ class Comm:
         counts = np.zeros(n, dtype=np.int64)
         tot = C.c_longlong(0)
         recv = root == -1 or root == self.rank
+        if out is None and capacity is None:
+            # a collective: EVERY rank takes part, whether it receives or not
+            capacity = int(self.photon_counts()["list_capacity"].sum())
         if out is None and recv:
-            if capacity is None:
-                capacity = int(self.photon_counts()["list_capacity"].sum())
             out = np.zeros(capacity, dtype=PHOTON_DTYPE)
         ptr = out.ctypes.data_as(C.c_void_p) if out is not None else None
         self.hp._ck(self.L.mcrat_b200_comm_gather_photons(self.c, C.c_int(root), ptr, C.c_longlong(out.size if out is not None else 0),

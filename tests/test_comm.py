@@ -91,6 +91,8 @@ def test_one_rank_communicator_is_the_identity():
 
 
 def _two_gpu_worker(rank, world, pipe, q):
+    import faulthandler
+    faulthandler.dump_traceback_later(150, exit=True)  # a rank stuck in a collective must not outlive the test
     import numpy as np
     from mcrat_b200 import Comm, HotPath, comm_unique_id, shard, synth
     cfg, hydro, photons, frame = synth.workload("C3", scale=1.0 / 16, n_photons=4001, seed=3)
@@ -124,6 +126,7 @@ def _two_gpu_worker(rank, world, pipe, q):
 
 
 @pytest.mark.gpu
+@pytest.mark.timeout(400)
 def test_two_gpus_table_counters_and_photon_gather():
     import torch
     if torch.cuda.device_count() < 2:
@@ -133,12 +136,18 @@ def test_two_gpus_table_counters_and_photon_gather():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     a, b = ctx.Pipe()
-    procs = [ctx.Process(target=_two_gpu_worker, args=(r, 2, (a, b)[r], q)) for r in range(2)]
+    procs = [ctx.Process(target=_two_gpu_worker, args=(r, 2, (a, b)[r], q), daemon=True) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=300) for _ in procs)
-    for p in procs:
-        p.join(timeout=60)
+    try:
+        res = dict(q.get(timeout=200) for _ in procs)
+        for p in procs:
+            p.join(timeout=30)
+    finally:
+        for p in procs:  # never leave a rank behind (it would hold its GPU and keep pytest from exiting)
+            if p.is_alive():
+                p.kill()
+                p.join(timeout=10)
     r0, r1 = res[0], res[1]
     # counters: sums and maxima of the two ranks' own statistics, the same on both
     for k in ("scatterings", "relocations", "photon_slots", "cell_evals", "box_evals", "ref_equiv_evals", "not_found"):

@@ -69,3 +69,27 @@ def test_reduce_frame_stats_gloo_world2():
 def test_load_imbalance():
     assert shard.load_imbalance([1.0, 1.0, 1.0]) == 1.0
     assert abs(shard.load_imbalance([1.0, 3.0]) - 1.5) < 1e-15
+
+
+def test_bench_splits_one_job_over_the_gpus_without_gaps_or_overlap():
+    """bench.py --gpus N: the SAME list and the same 128 reference ranks whatever N is; GPU g owns rank_slice(128, g, N) and
+    those ranks' photons (strong scaling, as Src/mcrat.c:139-164 splits a run over ranks)."""
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    for workload, photons, ranks in (("C5", 0, 0), ("C5", 3_000_001, 96), ("C2", 0, 0)):
+        args = argparse.Namespace(workload=workload, photons=photons, ranks=ranks)
+        job = bench.job_of(args)
+        assert job["ranks"] * job["rank_size"] >= job["photons"] > (job["ranks"] - 1) * job["rank_size"]
+        for world in (1, 2, 4, 8):
+            covered, rank_owner = 0, []
+            for g in range(world):
+                ra, rb, lo, hi = bench.my_share(job, g, world, weak=False)
+                assert lo == covered and hi > lo
+                assert lo == ra * job["rank_size"] and hi == min(rb * job["rank_size"], job["photons"])
+                covered = hi
+                rank_owner += [g] * (rb - ra)
+            assert covered == job["photons"] and len(rank_owner) == job["ranks"]
+            assert max(rank_owner.count(g) for g in range(world)) - min(rank_owner.count(g) for g in range(world)) <= 1
+        # weak scaling: every GPU runs the whole job
+        assert bench.my_share(job, 3, 8, weak=True) == (0, job["ranks"], 0, job["photons"])
