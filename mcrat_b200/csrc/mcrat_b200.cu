@@ -1346,11 +1346,11 @@ static int frame_stream_evt_blocks(const mcrat_b200_ctx *ctx)
     return E;
 }
 
-// AUTO picks the persistent stream from this many sub-shards and photons on: with few, long shards a pass item waits for its
-// shard's event more often than the missing launch boundaries save (10^7 photons, 16 shards: 272 us per iteration against
-// 229 streamed), and a short list leaves the interleaved loop little to lose (2.5 x 10^6 photons, 32 shards: 93 against 87)
+// AUTO picks the persistent stream for every list larger than L2 from this many sub-shards on: with few, long shards a pass
+// item waits for its shard's event more often than the missing launch boundaries save (10^7 photons, 16 shards: 272 us per
+// iteration against 229 streamed).  With 32 shards it wins at every size above L2 (2.5 x 10^6 photons: 68 us against 87).
 constexpr int STREAM_AUTO_MIN_SHARDS = 32;
-constexpr int STREAM_AUTO_MIN_PHOTONS = 4000000;
+constexpr int STREAM_AUTO_MIN_PHOTONS = PERSISTENT_MAX_PHOTONS + 1;
 
 static bool frame_stream_fits(const mcrat_b200_ctx *ctx)
 {
@@ -1360,9 +1360,16 @@ static bool frame_stream_fits(const mcrat_b200_ctx *ctx)
 
 static int frame_stream_bps(const mcrat_b200_ctx *ctx)
 {
-    // about 32 photons per thread and item: the item's fixed cost (wait, state, ticket: a few round trips to L2) stays a small
-    // part of its time (measured at 10^7 photons, 128 shards: 8 per thread 218 us per iteration, 16: 207, 32: 201)
-    int ppt = 32;
+    // Photons per thread and item.  Large items keep the item's fixed cost (wait, state, ticket: a few round trips to L2) a small
+    // part of its time; small items give every resident block work when the list is short and let a shard's pass finish -- and
+    // its event start -- sooner.  Measured (us per iteration; tools/gpu_r.sh, profiles/stream_coresidency_r02.txt):
+    //   photons / shards   4      8      12     16     24     32
+    //   10^7 / 128         224.8  210.0  202.6  199.3  197.2  198.0
+    //   5 x 10^6 / 64      128.5  114.2  109.0  107.7  110.5  115
+    //   2.5 x 10^6 / 32     74.1   69.9   67.8   70.9   83.6   94
+    int ppt = (int)(ctx->d.cap / 420000);
+    if (ppt < 12) ppt = 12;
+    if (ppt > 24) ppt = 24;
     if (const char *e = getenv("MCRAT_B200_STREAM_PPT"))
         if (atoi(e) > 0) ppt = atoi(e);
     int bps = (ctx->d.shard_size + PASS_THREADS * ppt - 1) / (PASS_THREADS * ppt);
