@@ -444,10 +444,11 @@ def main():
 
     # ---- per-kernel times of the streamed loop (profile mode: every launch bracketed by CUDA events) ----
     hp.set_profile(True)
-    hp.kernel_times(reset=True)
-    st = hp.run_frame(time_now, dt_frame, max_iters=24, switch=0)
-    time_now = st["time_now"]
-    kt = hp.kernel_times(reset=True)
+    for _ in range(2):  # the first round loads the streamed loop's kernels (the timed steps ran another driver); the second counts
+        hp.kernel_times(reset=True)
+        st = hp.run_frame(time_now, dt_frame, max_iters=24, switch=0)
+        time_now = st["time_now"]
+        kt = hp.kernel_times(reset=True)
     hp.set_profile(False)
     pass_ms = kt["pass_ms"] / max(kt["pass_launches"], 1)
     event_ms = kt["event_ms"] / max(kt["event_launches"], 1)
