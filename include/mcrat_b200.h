@@ -170,6 +170,11 @@ int mcrat_b200_find_containing_hydro_cell(mcrat_b200_ctx *ctx, int find_nearest_
 /* calcMeanFreePath, Src/mclib.h:10, Src/mclib.c:617.  Returns the head of the time-ordered
  * list: sorted_indexes[0] and its time_to_scatter (what Src/mcrat.c:777 reads). */
 int mcrat_b200_calc_mean_free_path(mcrat_b200_ctx *ctx, int *first_index, double *first_time_to_scatter);
+/* The rest of photonList.sorted_indexes, for hosts that read more than its head: the slot indices 0 .. n-1 ordered by the
+ * time_to_scatter the last calcMeanFreePath left (Src/mclib.c:717-729), sorted on the device.  Equal times -- the 1e12 / c of
+ * every photon outside the domain -- come in ascending slot order (the reference's qsort_r leaves their order to the C
+ * library).  Call after mcrat_b200_calc_mean_free_path; single shard. */
+int mcrat_b200_get_sorted_indexes(mcrat_b200_ctx *ctx, int *sorted_indexes, int n);
 /* photonEvent, Src/mclib.h:23, Src/mclib.c:1107 */
 int mcrat_b200_photon_event(mcrat_b200_ctx *ctx, double dt_max, double *time_step, int *scattered_ph_index,
                             int *frame_scatt_cnt, int *frame_abs_cnt);

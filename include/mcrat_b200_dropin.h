@@ -81,6 +81,10 @@ mcrat_b200_ctx *mcrat_b200_dropin_context(void);
 /* explicit mirror control for hosts that mutate the list between wrapped calls */
 int mcrat_b200_dropin_download(mcrat_dropin_photonList *photon_list);
 void mcrat_b200_dropin_mark_host_dirty(void);
+/* __wrap_calcMeanFreePath materialises only sorted_indexes[0] (all Src/mcrat.c reads, :777).  A host that walks the order
+ * further switches the full sort on (or sets MCRAT_B200_FULL_SORT=1): the whole array is then filled from a stable sort of
+ * the time column on the device, equal times in slot order. */
+void mcrat_b200_dropin_set_full_sort(int on);
 
 /* the wrapped surface; `rand` (gsl_rng *) is accepted and ignored: the device draws from
  * counter-based Philox streams keyed per photon and iteration */

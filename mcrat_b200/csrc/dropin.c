@@ -15,6 +15,7 @@ static mcrat_b200_config g_cfg;
 static int g_configured = 0;
 static int g_host_dirty = 1; /* host list newer than the device mirror */
 static int g_cs = 0;
+static int g_full_sort = -1; /* -1: ask the environment (MCRAT_B200_FULL_SORT) on first use */
 
 static mcrat_dropin_photonList *g_last_list = NULL; /* the host list of the last call: where a failing run leaves its photons */
 
@@ -85,6 +86,8 @@ void mcrat_b200_dropin_shutdown(void)
 mcrat_b200_ctx *mcrat_b200_dropin_context(void) { return g_ctx; }
 
 void mcrat_b200_dropin_mark_host_dirty(void) { g_host_dirty = 1; }
+
+void mcrat_b200_dropin_set_full_sort(int on) { g_full_sort = on ? 1 : 0; }
 
 static void ensure_ctx(FILE *fPtr)
 {
@@ -160,6 +163,11 @@ void __wrap_calcMeanFreePath(mcrat_dropin_photonList *photon_list, mcrat_dropin_
     (void)rand;
     ensure_ctx(fPtr);
     if (mcrat_b200_calc_mean_free_path(g_ctx, &head, &t) != 0) die(fPtr, "calcMeanFreePath");
+    if (g_full_sort < 0) g_full_sort = getenv("MCRAT_B200_FULL_SORT") ? 1 : 0;
+    if (g_full_sort && photon_list->list_capacity > 0) {
+        /* a host that reads more of the order than its head: all of sorted_indexes, sorted on the device */
+        if (mcrat_b200_get_sorted_indexes(g_ctx, photon_list->sorted_indexes, photon_list->list_capacity) != 0) die(fPtr, "sorted_indexes");
+    }
     if (photon_list->list_capacity > 0 && head >= 0 && head < photon_list->list_capacity) {
         photon_list->sorted_indexes[0] = head;
         photon_list->photons[head].time_to_scatter = t;

@@ -34,6 +34,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cub/device/device_radix_sort.cuh>
 #include <string>
 #include <vector>
 
@@ -901,6 +902,48 @@ API int mcrat_b200_calc_mean_free_path(mcrat_b200_ctx *ctx, int *first_index, do
     if (first_tts) *first_tts = ctx->sh_host[0].head_tts;
     ctx->last_nb_mfp = nb; // block minima stay valid for a following photon_event
     return device_error(ctx);
+}
+
+__global__ void iota_kernel(int *v, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = i;
+}
+
+// The whole time order, for hosts that read more of photonList.sorted_indexes than its head (Src/mclib.c:717-729: qsort_r
+// of the slot indices by time_to_scatter).  A stable radix sort of the time column on the device: equal times (the 1e12 / c of
+// every photon outside the domain, Src/mclib.c:684-687) come in ascending slot order, where the reference's qsort leaves
+// their order to the C library.  time_to_scatter >= 0, so the bit pattern of the doubles sorts like the values.
+API int mcrat_b200_get_sorted_indexes(mcrat_b200_ctx *ctx, int *sorted_indexes, int n)
+{
+    if (!ctx || !sorted_indexes || n < 0 || n > ctx->d.cap) return ctx ? fail(ctx, MCRAT_B200_ERR_ARG, "get_sorted_indexes: bad argument") : MCRAT_B200_ERR_ARG;
+    if (int rc = need_ready(ctx)) return rc;
+    if (int rc = need_single_shard(ctx, "get_sorted_indexes")) return rc;
+    if (n == 0) return MCRAT_B200_OK;
+    CK(cudaSetDevice(ctx->cfg.device));
+    double *keys_out = nullptr;
+    int *vals_in = nullptr, *vals_out = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cudaError_t e = cudaMalloc((void **)&keys_out, (size_t)n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&vals_in, (size_t)n * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&vals_out, (size_t)n * sizeof(int));
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->d.ph.tts, keys_out, vals_in, vals_out, n, 0, 64, ctx->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
+    if (e == cudaSuccess) {
+        iota_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(vals_in, n);
+        ctx->launches++;
+        e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, ctx->d.ph.tts, keys_out, vals_in, vals_out, n, 0, 64, ctx->stream);
+        ctx->launches++;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sorted_indexes, vals_out, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(keys_out);
+    cudaFree(vals_in);
+    cudaFree(vals_out);
+    cudaFree(tmp);
+    CK(e);
+    CK(e2);
+    return MCRAT_B200_OK;
 }
 
 API int mcrat_b200_photon_event(mcrat_b200_ctx *ctx, double dt_max, double *time_step, int *scattered_ph_index,

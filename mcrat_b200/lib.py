@@ -75,7 +75,7 @@ EXPORTS = [
     "mcrat_b200_launch_count", "mcrat_b200_rescan_all", "mcrat_b200_measure_fp64_peak", "mcrat_b200_measure_hbm_peak",
     "mcrat_b200_selftest_div_by_c", "mcrat_b200_set_recheck_skip", "mcrat_b200_set_profile",
     "mcrat_b200_photon_emit_cyclosynch", "mcrat_b200_photon_emit_cyclosynch_single",
-    "mcrat_b200_get_not_found",
+    "mcrat_b200_get_not_found", "mcrat_b200_get_sorted_indexes",
     "mcrat_b200_comm_unique_id", "mcrat_b200_comm_nccl_version", "mcrat_b200_comm_create", "mcrat_b200_comm_destroy",
     "mcrat_b200_comm_rank", "mcrat_b200_comm_size", "mcrat_b200_comm_collectives", "mcrat_b200_comm_bcast_thermal_table",
     "mcrat_b200_comm_build_thermal_table", "mcrat_b200_comm_reduce_frame_stats", "mcrat_b200_comm_photon_counts",
@@ -279,6 +279,13 @@ class HotPath:
         i, t = C.c_int(0), C.c_double(0)
         self._ck(self.L.mcrat_b200_calc_mean_free_path(self.ctx, C.byref(i), C.byref(t)))
         return i.value, t.value
+
+    def sortedIndexes(self, n=None):
+        """photonList.sorted_indexes in full (slot indices by ascending time_to_scatter, ties in slot order)."""
+        n = int(self.L.mcrat_b200_list_capacity(self.ctx)) if n is None else int(n)
+        out = np.zeros(n, dtype=np.int32)
+        self._ck(self.L.mcrat_b200_get_sorted_indexes(self.ctx, out.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(n)))
+        return out
 
     def photonEvent(self, dt_max):
         ts, idx, sc, ab = C.c_double(0), C.c_int(0), C.c_int(0), C.c_int(0)

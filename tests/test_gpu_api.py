@@ -895,3 +895,43 @@ def test_photons_without_a_containing_cell_are_reported_and_logged_like_the_refe
     lines = log.read_text().splitlines()
     want = sorted("MCRaT Couldn't find a block for the photon located at r0=%e r1=%e" % (e0[s], e1[s]) for s in lost)
     assert sorted(lines) == want
+
+
+@pytest.mark.gpu
+def test_full_time_order_is_available_on_request():
+    """calcMeanFreePath's qsort_r (Src/mclib.c:717-729) orders ALL slot indices by time_to_scatter.  The device keeps only
+    the head (what Src/mcrat.c:777 reads); mcrat_b200_get_sorted_indexes sorts the rest on request: same order as the
+    oracle's qsort wherever the times differ, slot order among equal times (photons outside the domain share 1e12 / c)."""
+    cfg, hydro, photons, frame = synth.workload("C2", scale=1.0 / 16, n_photons=5000, seed=12)
+    ph = photons.copy()
+    ph["r2"][::9] *= 10.0  # every ninth photon far outside the domain: equal default times
+    # the oracle (the reference's own qsort_r) and the uniform stream it consumed
+    for seed in range(1, 50):
+        src = api.OracleRng("ranlxs0", seed=seed)
+        src.tee(100_000)
+        o = api.Oracle(cfg)
+        o.set_hydro(hydro)
+        o.set_photons(ph)
+        o.find_containing_hydro_cell(1, src)
+        o.calc_mean_free_path(src)
+        u = src.tee_values()
+        if not np.any(u == 0.0):
+            break
+    hp = HotPath(cfg, rng_mode=RNG_REPLAY)
+    hp.set_hydro(hydro)
+    hp.set_photons(ph)
+    hp.set_replay_uniforms(u)
+    hp.findContainingHydroCell(1)
+    head, t_head = hp.calcMeanFreePath()
+    order = hp.sortedIndexes()
+    got = hp.get_photons()
+    tts = got["time_to_scatter"]
+    assert order[0] == head and tts[head] == t_head
+    assert sorted(order.tolist()) == list(range(ph.size))
+    assert np.array_equal(order, np.lexsort((np.arange(ph.size), tts)))  # by time, ties by slot
+    assert (got["nearest_block_index"][::9] == -1).all() and len(set(tts[::9].tolist())) == 1
+    oo = np.asarray(o.sorted_indexes())
+    n_in = int((got["nearest_block_index"] != -1).sum())
+    assert np.array_equal(oo[:n_in], order[:n_in])      # distinct times: the reference's order exactly
+    assert sorted(oo[n_in:].tolist()) == sorted(order[n_in:].tolist())  # the tie block: same set, library-defined order there
+    hp.close()
