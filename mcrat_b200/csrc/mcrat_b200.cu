@@ -553,7 +553,8 @@ API int mcrat_b200_set_num_shards(mcrat_b200_ctx *ctx, int num_shards)
     if (num_shards < 1 || num_shards > MAX_SHARDS) return fail(ctx, MCRAT_B200_ERR_ARG, "set_num_shards: 1..4096 sub-shards");
     if (num_shards > 1 && ctx->d.replay) return fail(ctx, MCRAT_B200_ERR_ARG, "the replay harness drives a single shard");
     if (num_shards > 1 && ctx->d.cs)
-        return fail(ctx, MCRAT_B200_ERR_ARG, "sub-shards need CYCLOSYNCHROTRON_SWITCH OFF (host-side emission re-packs the list)");
+        return fail(ctx, MCRAT_B200_ERR_ARG, "with CYCLOSYNCHROTRON_SWITCH ON a context holds one rank: emission, absorption and rebinning manage "
+                                             "the null slots and counters of one list (use one context per rank; contexts on different streams run side by side)");
     ctx->want_shards = num_shards;
     return MCRAT_B200_OK;
 }
