@@ -323,9 +323,9 @@ def main():
                                   "GPU g of N owns ranks rank_slice(%d, g, N) and their photons -- same job, same photons for every N" % job["ranks"]),
               "step": "full photon x cell rescan of the GPU's photons (new hydro frame) + loop iterations in every rank; steps continue one simulation",
               "l2": "photon list and cell arrays exceed L2 at N <= 4 (1e7 x 100 B per pass); additionally flushed between timed steps (256 MiB write)",
-              "loop": args.loop + " (auto: one cooperative launch per frame while a GPU's list fits in L2 (<= 2^21 photons); above, from 32 ranks "
-                      "per GPU on, a pair of co-resident grids per frame (resident event blocks beside pass "
-                      "blocks streaming the photon columns); two launches per iteration and half of the ranks otherwise)",
+              "loop": args.loop + " (auto: from 1.2e6 photons and 16 ranks of <= 2e5 photons per GPU on, a pair of co-resident grids per frame "
+                      "(resident event blocks beside pass blocks streaming the photon columns); otherwise one cooperative launch per "
+                      "frame up to 2^21 photons and two launches per iteration and half of the ranks above)",
               "relocation": "bounding-box index over the cells in array order (K1c, identical first-match results)"
               if args.index else "full photon x cell scan of every new hydro frame (K1), as the reference does; "
               "steady-state re-locations inside the loop go through the bounding-box index"}

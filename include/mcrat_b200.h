@@ -242,8 +242,8 @@ int mcrat_b200_set_recheck_skip(mcrat_b200_ctx *ctx, int mode);
  *   iteration) go through the grid-wide re-location kernels: pass, K1 / K1b / K1c, finish, event.
  * PERSISTENT: one cooperative launch per frame; every sub-shard is iterated by resident blocks that hand over through
  *   a generation word in global memory (no launch boundary inside the loop).
- * AUTO (default): PERSISTENT while the list fits in L2 (<= 2^21 photons); above, PERSISTENT_STREAM from 32 sub-shards
- *   on and STREAMED with fewer.
+ * AUTO (default): PERSISTENT_STREAM once the photon columns outgrow L2 (>= 1.2 x 10^6 photons) and there are 16 or more
+ *   sub-shards of at most 200 000 photons; otherwise PERSISTENT up to 2^21 photons and STREAMED above.
  * In all of them sub-shards advance independently, like MPI ranks, and the photons are bit-identical; the replay
  * harness always runs STREAMED_GLOBAL. */
 #define MCRAT_B200_LOOP_AUTO 0

@@ -1374,13 +1374,14 @@ static void frame_loop_grid(const mcrat_b200_ctx *ctx, int &threads, int &bps, i
 // the second stream; pass blocks pulling items on the first.  All sub-shards' event blocks must be resident next to the
 // pass blocks: one 128-thread block per SM beside four pass blocks.
 // Event blocks of the persistent stream.  Fewer blocks leave more SMs with room for a fifth pass block, but a block serves
-// its shards one after the other, and releases that queue up stall the pass stream.  Two shards per block is the measured
-// optimum (10^7 photons, 128 shards: 16 blocks 256 us per iteration, 32: 207, 43: 199, 64: 198, 128: 206; 5 x 10^6 photons,
-// 64 shards: 32 blocks 108 us, 64: 115).
+// its shards one after the other, and releases that queue up stall the pass stream: two shards per block for long lists
+// (10^7 photons, 128 shards: 16 blocks 256 us per iteration, 32: 207, 43: 199, 64: 198, 128: 206; 5 x 10^6 photons, 64
+// shards: 32 blocks 108 us, 64: 115), one for short ones, where an iteration is not much longer than an event
+// (2.5 x 10^6 photons, 32 shards: 16 blocks 68 us, 32: 61; 1.25 x 10^6, 16 shards: 8 blocks 60 us, 16: 48).
 static int frame_stream_evt_blocks(const mcrat_b200_ctx *ctx)
 {
     const int S = ctx->d.nshards;
-    int m = 2;
+    int m = ctx->d.cap >= 4000000 ? 2 : 1;
     int E = (S + m - 1) / m;
     if (const char *e = getenv("MCRAT_B200_STREAM_EVT_BLOCKS"))
         if (atoi(e) > 0) E = atoi(e);
@@ -1390,11 +1391,14 @@ static int frame_stream_evt_blocks(const mcrat_b200_ctx *ctx)
     return E;
 }
 
-// AUTO picks the persistent stream for every list larger than L2 from this many sub-shards on: with few, long shards a pass
-// item waits for its shard's event more often than the missing launch boundaries save (10^7 photons, 16 shards: 272 us per
-// iteration against 229 streamed).  With 32 shards it wins at every size above L2 (2.5 x 10^6 photons: 68 us against 87).
-constexpr int STREAM_AUTO_MIN_SHARDS = 32;
-constexpr int STREAM_AUTO_MIN_PHOTONS = PERSISTENT_MAX_PHOTONS + 1;
+// AUTO picks the persistent stream once the photon columns no longer fit in L2 beside the cells (1.2 x 10^6 photons x 97 B),
+// for 16 or more sub-shards of at most 200 000 photons: with few, long shards a pass item waits for its shard's event more
+// often than the missing launch boundaries save (10^7 photons, 16 shards: 272 us per iteration against 229 streamed).
+// Measured against what AUTO used before: 1.25 x 10^6 photons / 16 shards 48 us (cooperative team 52), 2.5 x 10^6 / 32: 61
+// (streamed 87), 5 x 10^6 / 64: 108 (127), 10^7 / 128: 197 (224).
+constexpr int STREAM_AUTO_MIN_SHARDS = 16;
+constexpr int STREAM_AUTO_MIN_PHOTONS = 1200000;
+constexpr int STREAM_AUTO_MAX_SHARD_SIZE = 200000;
 
 static bool frame_stream_fits(const mcrat_b200_ctx *ctx)
 {
@@ -1411,8 +1415,10 @@ static int frame_stream_bps(const mcrat_b200_ctx *ctx)
     //   10^7 / 128         224.8  210.0  202.6  199.3  197.2  198.0
     //   5 x 10^6 / 64      128.5  114.2  109.0  107.7  110.5  115
     //   2.5 x 10^6 / 32     74.1   69.9   67.8   70.9   83.6   94
-    int ppt = (int)(ctx->d.cap / 420000);
-    if (ppt < 12) ppt = 12;
+    //   2.5 x 10^6 / 32 (one shard per event block):  4: 64.6   6: 61.2   8: 60.6   12: 63.6
+    //   1.25 x 10^6 / 16 (one shard per event block): 3: 49.2   4: 47.6   6: 48.1    8: 50.5   12: 55.2
+    int ppt = (int)(ctx->d.cap / 312500);
+    if (ppt < 4) ppt = 4;
     if (ppt > 24) ppt = 24;
     if (const char *e = getenv("MCRAT_B200_STREAM_PPT"))
         if (atoi(e) > 0) ppt = atoi(e);
@@ -1662,14 +1668,15 @@ API int mcrat_b200_run_frame(mcrat_b200_ctx *ctx, double time_now, double remain
         }
         return MCRAT_B200_OK;
     };
+    const bool auto_stream = ctx->loop_mode == MCRAT_B200_LOOP_AUTO && ctx->d.cap >= STREAM_AUTO_MIN_PHOTONS &&
+                             S >= STREAM_AUTO_MIN_SHARDS && ctx->d.shard_size <= STREAM_AUTO_MAX_SHARD_SIZE && frame_stream_fits(ctx);
     bool persistent = fused && !ctx->cfg.profile &&
                       (ctx->loop_mode == MCRAT_B200_LOOP_PERSISTENT ||
-                       (ctx->loop_mode == MCRAT_B200_LOOP_AUTO && ctx->d.cap <= PERSISTENT_MAX_PHOTONS));
+                       (ctx->loop_mode == MCRAT_B200_LOOP_AUTO && ctx->d.cap <= PERSISTENT_MAX_PHOTONS && !auto_stream));
     // lists larger than L2: the persistent stream of pass items beside resident event blocks, if every sub-shard's event
     // block fits on the device at once; else the interleaved streamed loop
     const bool pstream = fused && !ctx->cfg.profile && !persistent && frame_stream_fits(ctx) &&
-                         (ctx->loop_mode == MCRAT_B200_LOOP_PERSISTENT_STREAM ||
-                          (ctx->loop_mode == MCRAT_B200_LOOP_AUTO && ctx->d.cap >= STREAM_AUTO_MIN_PHOTONS && S >= STREAM_AUTO_MIN_SHARDS));
+                         (ctx->loop_mode == MCRAT_B200_LOOP_PERSISTENT_STREAM || auto_stream);
     if (pstream) persistent = true;
     long long streamed_done = 0; // iterations already launched when the persistent loop hands over for good
     if (persistent) {
