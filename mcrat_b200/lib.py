@@ -485,17 +485,30 @@ class Comm:
         return {"list_capacity": a, "output_photons": b, "null_slots": c}
 
     def gather_photons(self, root=0, out=None, capacity=None):
-        """-> (photons of all ranks in rank order or None on non-receiving ranks, per-rank counts)."""
+        """-> (photons of all ranks in rank order, or None on non-receiving ranks; per-rank counts).
+
+        Collective: every rank of the communicator calls it, with the same `root`.  A receiving rank passes a buffer
+        (`out`) or a `capacity`, or neither: the C call itself finds out -- collectively -- whether every receiver has room;
+        if not, nothing is transferred, every rank learns the total and comes back once more, the receivers with a buffer of
+        that size (a too small `out` is replaced, the returned array is then not `out`).  The wrapper issues no collective
+        of its own, so ranks may differ in what they pass."""
         n = self.size
         counts = np.zeros(n, dtype=np.int64)
         tot = C.c_longlong(0)
         recv = root == -1 or root == self.rank
-        if out is None and capacity is None:
-            # a collective: EVERY rank takes part, whether it receives or not
-            capacity = int(self.photon_counts()["list_capacity"].sum())
-        if out is None and recv:
-            out = np.zeros(capacity, dtype=PHOTON_DTYPE)
-        ptr = out.ctypes.data_as(C.c_void_p) if out is not None else None
-        self.hp._ck(self.L.mcrat_b200_comm_gather_photons(self.c, C.c_int(root), ptr, C.c_longlong(out.size if out is not None else 0),
-                                                          counts.ctypes.data_as(C.POINTER(C.c_longlong)), C.byref(tot)))
-        return (out[:tot.value] if recv else None), counts
+        if recv and out is None and capacity is not None:
+            out = np.zeros(int(capacity), dtype=PHOTON_DTYPE)
+        for attempt in range(2):
+            have = recv and out is not None
+            ptr = out.ctypes.data_as(C.c_void_p) if have else None
+            rc = self.L.mcrat_b200_comm_gather_photons(self.c, C.c_int(root), ptr, C.c_longlong(out.size if have else 0),
+                                                       counts.ctypes.data_as(C.POINTER(C.c_longlong)), C.byref(tot))
+            if rc == 0:
+                return (out[:tot.value] if recv else None), counts
+            if rc == -2 and attempt == 0 and tot.value > 0:
+                # agreed by all ranks inside the call: some receiver lacks room.  Everybody calls again.
+                if recv and (out is None or out.size < tot.value):
+                    out = np.zeros(tot.value, dtype=PHOTON_DTYPE)
+                continue
+            self.hp._ck(rc)
+        raise McratB200Error(-3, "comm_gather_photons: no agreement on the buffer sizes after two rounds")

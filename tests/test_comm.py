@@ -49,6 +49,91 @@ def test_table_points_are_partitioned_like_the_device_does():
         assert (seen == 1).all()
 
 
+class _FakeCollectiveLib:
+    """Stands in for libmcrat_b200.so in the wrapper test below: `mcrat_b200_comm_gather_photons` behaves like the C function --
+    every rank must enter it (a barrier with a time-out stands for the NCCL calls inside), the ranks agree on whether all
+    receivers have room, and either all of them fail with ERR_ARG and the total, or the data moves."""
+
+    def __init__(self, nranks, sizes):
+        import threading
+        self.n, self.sizes = nranks, sizes
+        self.barrier = threading.Barrier(nranks, timeout=5)
+        self.room = [1] * nranks
+        self.calls = [0] * nranks
+
+    def gather(self, rank, root, ptr, cap, counts, tot):
+        total = sum(self.sizes)
+        recv = root == -1 or root == rank
+        self.room[rank] = 1 if (not recv or (ptr is not None and cap >= total)) else 0
+        self.calls[rank] += 1
+        self.barrier.wait()                      # the all-gather of the counts
+        ok = min(self.room)
+        self.barrier.wait()                      # the all-reduce of the flag
+        for k in range(self.n):
+            counts[k] = self.sizes[k]
+        tot.value = total
+        return 0 if ok else -2
+
+
+@pytest.mark.parametrize("root,buffers", [(0, "root_only"), (0, "none"), (-1, "none"), (0, "too_small"), (-1, "mixed")])
+def test_gather_wrapper_keeps_the_ranks_in_step(root, buffers):
+    """Comm.gather_photons must issue exactly the same sequence of collectives on every rank whatever each rank passes
+    (rank 0 with a buffer and the others without is how bench.py calls it).  Four fake ranks on threads; a rank that enters a
+    collective the others do not enter trips the barrier's time-out."""
+    import threading
+    n, sizes = 4, [5, 0, 7, 3]
+    fake = _FakeCollectiveLib(n, sizes)
+    results, errors = [None] * n, []
+
+    def rank_main(r):
+        class L:
+            @staticmethod
+            def mcrat_b200_comm_gather_photons(c, root_, ptr, cap, counts_ptr, tot_ref):
+                counts = np.ctypeslib.as_array(counts_ptr, shape=(n,))
+                return fake.gather(r, root_.value, ptr, cap.value, counts, tot_ref._obj)
+
+            @staticmethod
+            def mcrat_b200_comm_size(c):
+                return n
+
+            @staticmethod
+            def mcrat_b200_comm_rank(c):
+                return r
+
+            @staticmethod
+            def mcrat_b200_comm_photon_counts(*a):
+                raise AssertionError("the wrapper must not issue collectives of its own")
+        comm = lib.Comm.__new__(lib.Comm)
+        comm.L, comm.c, comm.hp = L, None, None
+        out = None
+        if buffers == "root_only" and r == 0:
+            out = np.zeros(sum(sizes), dtype=lib.PHOTON_DTYPE)
+        if buffers == "too_small" and r == 0:
+            out = np.zeros(2, dtype=lib.PHOTON_DTYPE)
+        if buffers == "mixed" and r % 2 == 0:
+            out = np.zeros(sum(sizes) + r, dtype=lib.PHOTON_DTYPE)
+        try:
+            results[r] = comm.gather_photons(root=root, out=out)
+        except Exception as exc:  # a broken barrier = ranks out of step
+            errors.append((r, repr(exc)))
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(n)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=30)
+    assert not errors, errors
+    assert len(set(fake.calls)) == 1, "ranks made different numbers of collective calls: %s" % fake.calls
+    assert fake.calls[0] == (1 if buffers in ("root_only",) else 2)
+    for r in range(n):
+        allp, counts = results[r]
+        assert counts.tolist() == sizes
+        if root == -1 or root == r:
+            assert allp is not None and allp.size == sum(sizes)
+        else:
+            assert allp is None
+
+
 # ------------------------------------------------------------------------------------------------
 def _frame(hp, photons, hydro, frame, iters=60):
     hp.set_hydro(hydro)
@@ -78,9 +163,15 @@ def test_one_rank_communicator_is_the_identity():
         allp, counts = comm.gather_photons(root=root)
         assert counts.tolist() == [photons.size]
         assert allp.tobytes() == got.tobytes()
-    # a receive buffer that is too small: nothing moves, the needed size comes back
-    with pytest.raises(lib.McratB200Error):
-        comm.gather_photons(root=0, out=np.zeros(10, dtype=lib.PHOTON_DTYPE))
+    # a receive buffer that is too small: the C call moves nothing and says how much is needed ...
+    small = np.zeros(10, dtype=lib.PHOTON_DTYPE)
+    cnts, tot = np.zeros(1, dtype=np.int64), C.c_longlong(0)
+    rc = hp.L.mcrat_b200_comm_gather_photons(comm.c, C.c_int(0), small.ctypes.data_as(C.c_void_p), C.c_longlong(small.size),
+                                             cnts.ctypes.data_as(C.POINTER(C.c_longlong)), C.byref(tot))
+    assert rc == -2 and tot.value == photons.size and cnts.tolist() == [photons.size] and not small["weight"].any()
+    # ... and the wrapper comes back with a buffer of that size
+    allp, _ = comm.gather_photons(root=0, out=small)
+    assert allp.tobytes() == got.tobytes()
     t1, _ = hp.build_thermal_table(calls=3000, seed=5)
     t2, _ = comm.build_thermal_table(calls=3000, seed=5)
     assert np.array_equal(t1, t2)
