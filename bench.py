@@ -69,6 +69,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-scan-photons", type=int, default=0, help="photons per CPU rank sample of the rescan (0: auto)")
     ap.add_argument("--cpu-iters", type=int, default=0, help="loop iterations per CPU rank sample (0: auto)")
+    ap.add_argument("--cpu-build", default="o3", choices=["o3", "o2"],
+                    help="CPU arm: o3 = the reference's sources built -O3 -march=x86-64-v3 (default); o2 = the -O2 -ffp-contract=off "
+                         "build the parity oracle uses (-O2 is what the reference's authors advise)")
     return ap.parse_args()
 
 
@@ -225,14 +228,14 @@ def _cpu_core(core, ncores, job, cfg, hydro, photons, cells, frame, n_scan, k_it
     out.put((core, res))
 
 
-def run_cpu_arm(job, cfg, hydro, photons, frame, iters, nsamples, refname, n_scan=0, k_iters=0):
+def run_cpu_arm(job, cfg, hydro, photons, frame, iters, nsamples, refname, n_scan=0, k_iters=0, build="o3"):
     """The reference's own CPU code on all host cores, one rank per core at a time (the reference's own way of using
     more cores).  Returns one entry per sample with the step time of the WHOLE job extrapolated from it:
         t_step(core) = sum over the core's ranks of [ photons(rank) x t_scan_per_photon + iters x t_iteration ]
         t_step(job)  = max over cores;   scatterings(job) = ranks x iters x (scatterings per iteration, measured)."""
     from oracle import api
     from mcrat_b200 import synth
-    timing = api.ref_available(refname, timing=True) and api.host_runs_timing_build()
+    timing = build == "o3" and api.ref_available(refname, timing=True) and api.host_runs_timing_build()
     kind = "reference" if api.ref_available(refname, timing=timing) else "port"
     if kind == "port":
         api.build_oracle()
@@ -332,7 +335,7 @@ def main():
 
     if args.impl == "reference":
         r = run_cpu_arm(job, cfg, hydro, photons_all, frame, args.iters, args.warmup + args.steps, refname,
-                        args.cpu_scan_photons, args.cpu_iters)
+                        args.cpu_scan_photons, args.cpu_iters, build=args.cpu_build)
         r["samples"] = r["samples"][args.warmup:]
         f = cpu_line_fields(r)
         line = {"impl": "reference", "metric": METRIC, "value": f["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -626,7 +629,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             log("cpu baseline")
             r = run_cpu_arm(job, cfg, hydro, photons_all, frame, args.iters, 1, refname,
-                            args.cpu_scan_photons or 0, args.cpu_iters or 0)
+                            args.cpu_scan_photons or 0, args.cpu_iters or 0, build=args.cpu_build)
             cpu = cpu_line_fields(r)
         line = {"metric": METRIC, "value": scatt_all / (t_max * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_max / args.steps,
