@@ -128,3 +128,25 @@ def test_every_kernel_source_is_a_build_dependency_and_nothing_imports_the_oracl
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), os.path.join(dirpath, f)
                 assert '#include "../../oracle' not in text, os.path.join(dirpath, f)
+
+
+def test_c_hosts_compile_against_the_headers_and_refuse_to_run_without_a_gpu(tmp_path):
+    """examples/host_frame.c (one GPU) and examples/host_multi_gpu.c (one thread per GPU, the communicator in place of MPI)
+    are plain C against include/*.h: they must compile warning-free, and without a CUDA device they must say so and stop --
+    there is no CPU fallback to drift into."""
+    import subprocess
+    import shutil
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    csrc = os.path.join(ROOT, "mcrat_b200", "csrc")
+    for name, extra in (("host_frame", []), ("host_multi_gpu", ["-pthread"])):
+        exe = str(tmp_path / name)
+        subprocess.check_call(["gcc", "-O2", "-std=gnu11", "-Wall", "-Wextra", "-Werror"] + extra +
+                              [os.path.join(ROOT, "examples", name + ".c"), "-I" + os.path.join(ROOT, "include"), "-L" + csrc,
+                               "-lmcrat_b200", "-lmcrat_b200_io", "-Wl,-rpath," + csrc, "-o", exe])
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 2 and "usage" in r.stderr
+    import ctypes as C
+    if C.CDLL(lib.LIB_PATH).mcrat_b200_device_count() == 0:
+        r = subprocess.run([str(tmp_path / "host_multi_gpu"), str(tmp_path), "2"], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr
