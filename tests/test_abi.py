@@ -4,6 +4,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 from mcrat_b200 import lib, synth
 from oracle import api
