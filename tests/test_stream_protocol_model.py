@@ -145,3 +145,64 @@ def test_one_pass_block_and_one_event_block_suffice():
     # the degenerate geometry: everything funnels through two blocks
     m = run(S=5, bps=3, E=1, W=1, stop_at=[4, 0, 2, 4, 1], seed=7)
     assert m.events == [4, 0, 2, 4, 1]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the start-up handshake (stream_handshake): GO only if every event block is resident, ABORT if somebody waited too long,
+# one decision for all (atomicCAS on one word), taken before anything is touched
+# ---------------------------------------------------------------------------------------------------------------------
+def _handshake_run(n_evt, n_pass, evt_present, patience, seed):
+    rng = random.Random(seed)
+    state = {"word": 0, "ready": 0}
+    outcome = {}
+
+    def cas(new):
+        if state["word"] == 0:
+            state["word"] = new
+
+    def block(ident, is_pass, present):
+        if not present:                      # a block that never becomes resident (the other grid fills the device)
+            return
+            yield
+        if not is_pass:
+            state["ready"] += 1
+        spins = 0
+        while True:
+            if state["word"] != 0:
+                outcome[ident] = state["word"]
+                return
+            if is_pass and state["ready"] >= n_evt:
+                cas(1)
+                continue
+            spins += 1
+            if spins > patience:
+                cas(2)
+            yield
+
+    procs = [block(("e", k), False, k < evt_present) for k in range(n_evt)] + [block(("p", k), True, True) for k in range(n_pass)]
+    alive = list(range(len(procs)))
+    steps = 0
+    while alive:
+        i = rng.choice(alive)
+        try:
+            next(procs[i])
+        except StopIteration:
+            alive.remove(i)
+        steps += 1
+        assert steps < 1_000_000
+    return outcome
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_handshake_reaches_one_decision(seed):
+    rng = random.Random(seed)
+    n_evt, n_pass = rng.randint(1, 6), rng.randint(1, 6)
+    # all event blocks resident, generous patience: GO
+    out = _handshake_run(n_evt, n_pass, n_evt, patience=10 ** 6, seed=seed)
+    assert set(out.values()) == {1} and len(out) == n_evt + n_pass
+    # one event block never shows up: everybody who is there agrees on ABORT
+    out = _handshake_run(n_evt, n_pass, n_evt - 1, patience=50, seed=seed)
+    assert set(out.values()) == {2} and len(out) == n_evt - 1 + n_pass
+    # impatient blocks racing with the GO vote: whatever wins, it is ONE decision
+    out = _handshake_run(n_evt, n_pass, n_evt, patience=rng.randint(0, 12), seed=seed)
+    assert len(set(out.values())) == 1
