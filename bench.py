@@ -69,6 +69,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-scan-photons", type=int, default=0, help="photons per CPU rank sample of the rescan (0: auto)")
     ap.add_argument("--cpu-iters", type=int, default=0, help="loop iterations per CPU rank sample (0: auto)")
+    ap.add_argument("--comm-gather", action="store_true",
+                    help="with --gpus N > 1: also time one gather of the whole job's photons to rank 0 through the product's communicator "
+                         "(always done at N = 1; profiles/bench_r02_2gpu.json has it for two GPUs)")
     ap.add_argument("--cpu-build", default="o3", choices=["o3", "o2"],
                     help="CPU arm: o3 = the reference's sources built -O3 -march=x86-64-v3 (default); o2 = the -O2 -ffp-contract=off "
                          "build the parity oracle uses (-O2 is what the reference's authors advise)")
@@ -582,7 +585,7 @@ def main():
         t_reduce = (time.perf_counter() - t0) / 20
         gather_ms, gathered = None, None
         total_records = int(cnt["list_capacity"].sum())
-        if not args.no_e2e:
+        if not args.no_e2e and (world == 1 or args.comm_gather):
             out = None
             if rank == 0:
                 out_t = torch.empty(total_records * PHOTON_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
