@@ -365,3 +365,26 @@ def test_many_appends_build_a_chunk_tree_with_internal_nodes(tmp_path):
         assert want.size > 64 * n0, "the case must need more than one leaf"
         assert np.array_equal(g[name], want), name
         assert np.array_equal(mio.h5_read(os.path.join(d, "mc_proc_2.h5"), "77/" + name), want), name
+
+
+def test_append_after_an_empty_first_write(tmp_path):
+    """A frame group created by a write with no live photon (chunk size 1, since a chunk cannot be empty), then filled by an
+    append: hundreds of one-element chunks, three B-tree levels for the larger block -- still the right data in both readers."""
+    d = str(tmp_path)
+    sw = mio.switches(comv=0, save_type=1, stokes=0)
+    dead = _photons(40, seed=2)
+    dead["weight"] = 0
+    mio.print_photons(d, 0, 9, dead, sw)
+    first, second = _photons(90, seed=3), _photons(5000, seed=4)
+    mio.print_photons(d, 0, 9, first, sw)
+    mio.print_photons(d, 0, 9, second, sw)
+    f = H5File(os.path.join(d, "mc_proc_0.h5"))
+    g = f.tree()["9"]
+    links = f.object(f.object(f.root_ohdr)[1]["9"])[1]
+    for name in ("P0", "R1", "NS", "PW", "PT"):
+        want = np.concatenate([_expect(first, name), _expect(second, name)])
+        assert want.size > 64 * 64, "needs a third level of the chunk tree"
+        assert np.array_equal(g[name], want), name
+        assert np.array_equal(mio.h5_read(os.path.join(d, "mc_proc_0.h5"), "9/" + name), want), name
+        f.object(links[name])
+        assert f.last_dataset_info["chunk"] == 1
