@@ -1515,6 +1515,36 @@ static int launch_frame_cluster(mcrat_b200_ctx *ctx, int bps_wanted)
     return check_launch(ctx, "frame_loop_cluster_kernel");
 }
 
+// Launch geometry of the persistent stream for a list of `list_capacity` photons in `num_shards` sub-shards on a device with
+// `num_sms` SMs -- the same functions the launch uses, without a device (tests/test_stream_geometry.py sweeps it for the
+// bounds the kernels rely on).  fits: frame_stream_fits; auto_picks: what AUTO would do (1 = persistent stream).
+API int mcrat_b200_debug_stream_geometry(int list_capacity, int num_shards, int num_sms, int *event_blocks, int *bps, int *pass_grid,
+                                         int *shards_out, int *fits, int *auto_picks)
+{
+    if (list_capacity < 1 || num_shards < 1 || num_shards > MAX_SHARDS || num_sms < 1) return MCRAT_B200_ERR_ARG;
+    mcrat_b200_ctx *ctx = new mcrat_b200_ctx();
+    int S = num_shards > list_capacity ? list_capacity : num_shards; // layout_shards()
+    const int size = (list_capacity + S - 1) / S;
+    S = (list_capacity + size - 1) / size;
+    ctx->d.nshards = S;
+    ctx->d.shard_size = size;
+    ctx->d.cap = list_capacity;
+    ctx->d.cs = 0;
+    ctx->d.replay = 0;
+    ctx->num_sms = num_sms;
+    const int E = frame_stream_evt_blocks(ctx);
+    if (event_blocks) *event_blocks = E;
+    if (bps) *bps = frame_stream_bps(ctx);
+    if (pass_grid) *pass_grid = E * STREAM_PASS_CTAS_PER_SM + (num_sms - E) * MCRAT_PASS_MINB;
+    if (shards_out) *shards_out = S;
+    const bool f = frame_stream_fits(ctx);
+    if (fits) *fits = f ? 1 : 0;
+    if (auto_picks)
+        *auto_picks = (f && list_capacity >= STREAM_AUTO_MIN_PHOTONS && S >= STREAM_AUTO_MIN_SHARDS && size <= STREAM_AUTO_MAX_SHARD_SIZE) ? 1 : 0;
+    delete ctx;
+    return MCRAT_B200_OK;
+}
+
 static int launch_frame_loop(mcrat_b200_ctx *ctx, bool stream = false)
 {
     if (stream) return launch_frame_stream(ctx);
