@@ -63,7 +63,7 @@ def parse_args():
                     help="re-locate a new hydro frame through the bounding-box index (K1c: same cells, ~2000x fewer "
                          "tests) instead of the reference's full photon x cell scan (K1, the default and the kernel "
                          "the FP64 roofline is quoted on)")
-    ap.add_argument("--loop", default="auto", choices=["auto", "streamed", "persistent"])
+    ap.add_argument("--loop", default="auto", choices=["auto", "streamed", "persistent", "persistent_stream", "streamed_global"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the s_sweep block (scatterings/s against the number of ranks)")
     ap.add_argument("--no-e2e", action="store_true")
