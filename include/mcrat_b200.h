@@ -255,7 +255,7 @@ int mcrat_b200_set_recheck_skip(mcrat_b200_ctx *ctx, int mode);
                                            * in turn) beside resident pass blocks that pull (iteration, sub-shard, slice)
                                            * items from a counter -- the PERSISTENT protocol without tying pass blocks to a
                                            * shard, so the photon columns stream through the SMs without a launch boundary
-                                           * while the scatterings run beside them.  AUTO picks it above 2^21 photons. */
+                                           * while the scatterings run beside them.  AUTO: see above. */
 int mcrat_b200_set_loop_mode(mcrat_b200_ctx *ctx, int mode);
 
 /* per-sub-shard view of the counters (cumulative since the shard layout was set) and its slot range */
