@@ -69,6 +69,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-scan-photons", type=int, default=0, help="photons per CPU rank sample of the rescan (0: auto)")
     ap.add_argument("--cpu-iters", type=int, default=0, help="loop iterations per CPU rank sample (0: auto)")
+    ap.add_argument("--cpu-cores", type=int, default=0, help="CPU arm: host cores to use (0: all the process may run on)")
     ap.add_argument("--comm-gather", action="store_true",
                     help="with --gpus N > 1: also time one gather of the whole job's photons to rank 0 through the product's communicator "
                          "(always done at N = 1; profiles/bench_r02_2gpu.json has it for two GPUs)")
@@ -231,7 +232,7 @@ def _cpu_core(core, ncores, job, cfg, hydro, photons, cells, frame, n_scan, k_it
     out.put((core, res))
 
 
-def run_cpu_arm(job, cfg, hydro, photons, frame, iters, nsamples, refname, n_scan=0, k_iters=0, build="o3"):
+def run_cpu_arm(job, cfg, hydro, photons, frame, iters, nsamples, refname, n_scan=0, k_iters=0, build="o3", cores=0):
     """The reference's own CPU code on all host cores, one rank per core at a time (the reference's own way of using
     more cores).  Returns one entry per sample with the step time of the WHOLE job extrapolated from it:
         t_step(core) = sum over the core's ranks of [ photons(rank) x t_scan_per_photon + iters x t_iteration ]
@@ -245,6 +246,8 @@ def run_cpu_arm(job, cfg, hydro, photons, frame, iters, nsamples, refname, n_sca
     else:
         api.RefLib(refname, timing=timing)  # dlopen in the parent too: the forked workers inherit the mapping
     ncores = len(os.sched_getaffinity(0))
+    if cores > 0:
+        ncores = min(ncores, cores)
     ncores = max(1, min(ncores, job["ranks"]))
     ncells = int(hydro["num_elements"])
     if not k_iters:  # ~1 s of loop per sample: one iteration costs ~0.3 us per photon of the rank (draw, push, qsort)
@@ -338,7 +341,7 @@ def main():
 
     if args.impl == "reference":
         r = run_cpu_arm(job, cfg, hydro, photons_all, frame, args.iters, args.warmup + args.steps, refname,
-                        args.cpu_scan_photons, args.cpu_iters, build=args.cpu_build)
+                        args.cpu_scan_photons, args.cpu_iters, build=args.cpu_build, cores=args.cpu_cores)
         r["samples"] = r["samples"][args.warmup:]
         f = cpu_line_fields(r)
         line = {"impl": "reference", "metric": METRIC, "value": f["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -632,7 +635,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             log("cpu baseline")
             r = run_cpu_arm(job, cfg, hydro, photons_all, frame, args.iters, 1, refname,
-                            args.cpu_scan_photons or 0, args.cpu_iters or 0, build=args.cpu_build)
+                            args.cpu_scan_photons or 0, args.cpu_iters or 0, build=args.cpu_build, cores=args.cpu_cores)
             cpu = cpu_line_fields(r)
         line = {"metric": METRIC, "value": scatt_all / (t_max * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_max / args.steps,
